@@ -1,0 +1,236 @@
+/*
+ * mpm_b200.h -- C ABI of libmpm_b200.so: a B200-native (sm_100a) MLS-MPM fluid solver that sits behind
+ * the solver surface of Miotismon/mls-mpm-godot.
+ *
+ * The reference has no FFI/plugin layer; its "API" is the fields and methods of the GPU solver node
+ *   H = mls-mpm/3d/fluid_multithread_gpu/MLSMPM3DFluidMultithreadGPU.cs
+ * (and the CPU copies F = 3d/fluid_multithread/..., X = 3d/fluid_multithread_fixed_point/...,
+ * D = 2d/fluid/..., M = 2d/fluid_multithread/...).  Every entry point below names the reference member
+ * it replaces.  A C# host binds these with [DllImport("mpm_b200", CallingConvention = Cdecl)]; see
+ * INTEGRATION.md and mls-mpm-godot_b200/host/MpmB200.cs.
+ *
+ * Conventions: plain C, cdecl, no exceptions cross the boundary.  Every call returns an int32 status
+ * (MPM_OK = 0); mpm_last_error() gives a UTF-8 message owned by the library.  Host buffers are
+ * caller-owned and only touched during the call.  Device memory is library-owned.  A handle is used from
+ * one thread at a time (the reference calls everything from Godot's main thread).  mpm_step() is
+ * asynchronous with respect to the GPU; mpm_sync() or any download waits for it.
+ * There is no CPU fallback: without a CUDA device every call that needs one fails with MPM_ERR_CUDA.
+ */
+#ifndef MPM_B200_H
+#define MPM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define MPM_API __declspec(dllexport)
+#else
+#define MPM_API __attribute__((visibility("default")))
+#endif
+
+#define MPM_ABI_VERSION 1
+
+/* ---- status codes ---- */
+#define MPM_OK 0
+#define MPM_ERR_INVALID 1  /* bad argument / parameter combination */
+#define MPM_ERR_CUDA 2     /* CUDA runtime error (message has the CUDA string) */
+#define MPM_ERR_STATE 3    /* call not valid in the current state (e.g. step before upload) */
+#define MPM_ERR_OVERFLOW 4 /* fixed-point accumulator left the int32 range (debug detector) */
+#define MPM_ERR_COMM 5     /* multi-GPU exchange failed */
+
+/* ---- enums (int32 in the struct) ---- */
+#define MPM_GRID_FLOAT 0 /* Cell{Vector3 vel; float mass}            F:16-20, D:16-20 */
+#define MPM_GRID_FIXED 1 /* Cell{int vel_x, vel_y, vel_z, mass} x1e7 X:18-24, H:25-32 */
+
+#define MPM_STRESS_3D 0       /* strain = C + C^T                     F:340-345, p2g_2.glsl:108-112 */
+#define MPM_STRESS_2D_TRACE 1 /* off-diagonals summed, diagonal kept  D:276-283 */
+
+#define MPM_EQ16_VOL4_DT 0 /* ((-volume*4)*stress)*dt  F:347, X:407, M:307, p2g_2.glsl:115 */
+#define MPM_EQ16_DTVOL_4 1 /* ((-dt*volume)*stress)*4  D:285 */
+
+#define MPM_BC_SLIP 0     /* F:402-404, X:479-481, update_grid.glsl:64-66 */
+#define MPM_BC_FRICTION 1 /* M:366-368 */
+
+#define MPM_INTERACT_NONE 0
+#define MPM_INTERACT_SPHERE_POST 1 /* X:570-576 */
+#define MPM_INTERACT_SPHERE_PRE 2  /* g2p.glsl:122-129 */
+#define MPM_INTERACT_MOUSE_2D 3    /* D:381-406 (mouse held down) */
+
+/* arithmetic mode */
+#define MPM_MATH_STRICT 0 /* every fp32 op in the C# source order, no FMA: with MPM_GRID_FIXED the grid
+                             ints and particle floats are bit-identical to the reference algorithm */
+#define MPM_MATH_FAST 1   /* FMA contraction + per-axis hoisting; results within float tolerance */
+
+/* kernel path */
+#define MPM_PATH_AUTO 0
+#define MPM_PATH_REFERENCE 1 /* one thread per particle, global atomics: the shape of p2g_1.glsl etc. */
+#define MPM_PATH_TILED 2     /* cell-sorted particles, shared-memory grid tiles (the B200 path) */
+
+/* variant presets for mpm_default_params() */
+#define MPM_VARIANT_2D_ST 0    /* D */
+#define MPM_VARIANT_2D_MT 1    /* M */
+#define MPM_VARIANT_3D_FLOAT 2 /* F */
+#define MPM_VARIANT_3D_FIXED 3 /* X */
+#define MPM_VARIANT_3D_GPU 4   /* H + GLSL: the shipping scene */
+
+/*
+ * Parameter block.  It is the union of the reference's push-constant blocks (H:444-503:
+ * {fixed_point_mult, grid_size}, {.., dt, rest_density, dynamic_viscosity, eos_stiffness, eos_power},
+ * {.., dt, gravity}, {.., dt, sphere_pos, tex_width}) plus the compile-time constants in which the five
+ * solver copies differ (SURVEY.md 8a "variant constants").  All members are 4 bytes; no padding.
+ */
+typedef struct MpmParams {
+    int32_t struct_size;      /* = sizeof(MpmParams); checked */
+    int32_t dim;              /* 2 or 3 */
+    int32_t grid_size[3];     /* Rx, Ry, Rz; the reference is cubic (H:43), this is a superset */
+    float dt;                 /* H:57-67: clamped to [0, 0.4] like the Dt setter */
+    float gravity;            /* H:71, applied on y (F:396, D:319) */
+    float rest_density;       /* H:76 */
+    float dynamic_viscosity;  /* H:78 */
+    float eos_stiffness;      /* H:82 */
+    float eos_power;          /* H:84 */
+    int32_t grid_mode;        /* MPM_GRID_* */
+    int32_t fixed_point_mult; /* H:98 */
+    int32_t stress_form;      /* MPM_STRESS_* */
+    int32_t eq16_order;       /* MPM_EQ16_* */
+    int32_t bc_mode;          /* MPM_BC_* */
+    int32_t bc_hi_off;        /* BC where idx < 2 || idx > R - bc_hi_off */
+    float bc_friction;        /* M:366 */
+    float clamp_min;          /* F:476 = 1, g2p.glsl:115 = 2 */
+    float clamp_max_off;      /* clamp max = R - clamp_max_off */
+    float wall_min;           /* F:507 */
+    float wall_max_off;       /* wall max = R - wall_max_off */
+    float wall_gain;          /* F:509 = 1, D:410 = 0.5 */
+    int32_t interaction;      /* MPM_INTERACT_* */
+    float sphere_pos[3];      /* H:93, patched per frame by HandleMouseInteraction H:618-642 */
+    float sphere_radius;      /* H:94 */
+    float mouse_pos[2];       /* D:54 */
+    float mouse_radius;       /* D:52 */
+    /* ---- B200 solver controls (no reference counterpart) ---- */
+    int32_t math_mode;        /* MPM_MATH_* */
+    int32_t kernel_path;      /* MPM_PATH_* */
+    int32_t sort_interval;    /* re-bin particles every k steps (tiled path); 0 = library default */
+    int32_t overflow_check;   /* 1: detect fixed-point overflow (slower) */
+} MpmParams;
+
+/* Particle record of the reference's GPU buffer: 80 bytes, std430 (H:8-22, p2g_1.glsl:4-9). */
+typedef struct MpmParticle80 {
+    float pos[3];
+    float pad_pos;
+    float vel[3];
+    float mass;
+    float C_x[3]; /* column 0 of C (Basis.X / GLSL C[0]) */
+    float pad_cx;
+    float C_y[3];
+    float pad_cy;
+    float C_z[3];
+    float pad_cz;
+} MpmParticle80;
+
+/* Grid cell of the reference (H:25-32): four 32-bit words (vel_x, vel_y, vel_z, mass); int32 in
+ * MPM_GRID_FIXED, float in MPM_GRID_FLOAT (the float copies order it {vel, mass} too: F:16-20). */
+typedef struct MpmCell16 {
+    int32_t w[4];
+} MpmCell16;
+
+typedef struct MpmStats {
+    int64_t num_particles;
+    int64_t num_cells;
+    int64_t steps;            /* steps executed since create */
+    int64_t kernel_launches;  /* this library's kernels launched since create */
+    /* average device time per step of each phase over the last mpm_step() call that had timing on (ms) */
+    float ms_sort, ms_clear, ms_p2g1, ms_p2g2, ms_update, ms_g2p, ms_exchange, ms_step;
+    int32_t kernel_path;      /* the path actually used (MPM_PATH_*) */
+    int32_t overflow;         /* sticky overflow flag */
+    int32_t rank, world;
+    int64_t local_particles;  /* particles owned by this rank (multi-GPU) */
+} MpmStats;
+
+typedef struct MpmSolver MpmSolver; /* opaque */
+
+/* Version / capability probe; usable without a GPU. */
+MPM_API int32_t mpm_abi_version(void);
+/* Number of visible CUDA devices (0 without a driver); never fails. */
+MPM_API int32_t mpm_device_count(void);
+
+/* Fill *p with the constants of one of the reference's five solver copies (variant constants table). */
+MPM_API int32_t mpm_default_params(int32_t variant, MpmParams* p);
+
+/* _Ready + InitGPU (H:158-207, 265-435): allocate device state for up to max_particles on `device`. */
+MPM_API int32_t mpm_create(const MpmParams* p, int64_t max_particles, int32_t device, MpmSolver** out);
+/* CleanupGpu on NotificationPredelete (H:546-616, 709-715). */
+MPM_API int32_t mpm_destroy(MpmSolver* s);
+MPM_API const char* mpm_last_error(const MpmSolver* s); /* s may be NULL: error of the last failed create */
+
+/* UpdatePushConstants (H:444-503) and the UI setters (main_ui.tscn:70-72).  Grid size, dim and grid_mode
+ * are fixed at create time. */
+MPM_API int32_t mpm_set_params(MpmSolver* s, const MpmParams* p);
+MPM_API int32_t mpm_get_params(const MpmSolver* s, MpmParams* p);
+/* HandleMouseInteraction (H:618-642): patch only the sphere position. */
+MPM_API int32_t mpm_set_sphere(MpmSolver* s, const float pos[3]);
+
+/* InitialiseSim (H:654-707, F:129-183): lattice of points in [lo, hi) with the reference's
+ * float-accumulating loops, vel = 0, C = 0, mass = 1, grid zeroed.  Replaces the particle set. */
+MPM_API int32_t mpm_init_block(MpmSolver* s, const float lo[3], const float hi[3], float spacing);
+/* As above but appended to the current set (multi-block scenes). */
+MPM_API int32_t mpm_add_block(MpmSolver* s, const float lo[3], const float hi[3], float spacing);
+
+/* StorageBufferCreate(particle_bytes) (H:293-322): upload n particles in the reference's 80-byte layout. */
+MPM_API int32_t mpm_upload_particles(MpmSolver* s, const MpmParticle80* ps, int64_t n);
+/* SoA overload: pos[3n], vel[3n], C[9n] column-major, mass[n]; vel/C/mass may be NULL (0, 0, 1). */
+MPM_API int32_t mpm_upload_particles_soa(MpmSolver* s, const float* pos, const float* vel, const float* C,
+                                         const float* mass, int64_t n);
+/* BufferGetData(particle_buffer) (H:210-228, commented out in the reference): particles in ORIGINAL
+ * index order (particle i keeps index i), whatever the internal binning. */
+MPM_API int32_t mpm_download_particles(MpmSolver* s, MpmParticle80* ps, int64_t cap);
+MPM_API int32_t mpm_download_particles_soa(MpmSolver* s, float* pos, float* vel, float* C, float* mass,
+                                           int64_t cap);
+/* BufferGetData(grid_buffer): cells in reference order x*Ry*Rz + y*Rz + z (F:282), field order of H:25-32. */
+MPM_API int32_t mpm_download_grid(MpmSolver* s, MpmCell16* cells, int64_t cap);
+
+/* _Process -> sim_iterations x SetComputeLists (H:234-251, 505-544): enqueue `iterations` steps
+ * (clear, P2G_1, P2G_2, update, G2P) on the solver's stream and return. */
+MPM_API int32_t mpm_step(MpmSolver* s, int32_t iterations);
+MPM_API int32_t mpm_sync(MpmSolver* s);
+
+/* The five phases of Simulate() one by one (F:185-220), for per-kernel parity tests and profiling.
+ * phase: 0 clear, 1 p2g_1, 2 p2g_2, 3 update_grid, 4 g2p, 5 bin/sort (no reference counterpart). */
+MPM_API int32_t mpm_run_phase(MpmSolver* s, int32_t phase);
+
+/* particle_pos_tex (H:196, 342-355; g2p.glsl:149-150): float4 (x, y, z, |v|) per particle in original
+ * index order; texel (i % width, i / width) with width = (uint)sqrt(N) + 1 is element i of this array.
+ * dst may be NULL to only query.  *device_ptr (optional) receives the device address of the array so a
+ * renderer can consume it without a host round trip. */
+MPM_API int32_t mpm_get_positions(MpmSolver* s, float* dst4, int64_t cap, void** device_ptr,
+                                  uint32_t* tex_width);
+
+MPM_API int32_t mpm_num_particles(const MpmSolver* s, int64_t* n);
+/* Per-phase timing (Time.GetTicksUsec around each phase, F:190-219) is off by default. */
+MPM_API int32_t mpm_set_timing(MpmSolver* s, int32_t enabled);
+MPM_API int32_t mpm_get_stats(MpmSolver* s, MpmStats* st);
+
+/* Binning introspection (tiled path): the cell keys and the permutation (sorted rank -> index before the
+ * sort) of the most recent bin phase, for the bit-exact sort parity test. */
+MPM_API int32_t mpm_debug_last_sort(MpmSolver* s, uint32_t* keys_before, uint32_t* perm, int64_t cap);
+
+/* The CUDA stream the solver enqueues on (cudaStream_t as void*), so callers can time with events. */
+MPM_API int32_t mpm_get_stream(MpmSolver* s, void** stream);
+
+/* Pinned host memory for fast mpm_get_positions()/downloads (a C# host keeps it as IntPtr). */
+MPM_API int32_t mpm_host_alloc(int64_t bytes, void** out);
+MPM_API int32_t mpm_host_free(void* p);
+
+/* ---- multi-GPU: one process per GPU, x-slab decomposition, NCCL halo exchange + migration ---- */
+#define MPM_COMM_ID_BYTES 128
+/* rank 0 creates the id, the host broadcasts it by any means (torch.distributed, a file, a socket). */
+MPM_API int32_t mpm_comm_unique_id(uint8_t id[MPM_COMM_ID_BYTES]);
+/* Collective over all ranks.  Particles uploaded afterwards are kept by the rank whose slab holds them. */
+MPM_API int32_t mpm_comm_init(MpmSolver* s, const uint8_t id[MPM_COMM_ID_BYTES], int32_t rank, int32_t world);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPM_B200_H */

@@ -1,0 +1,85 @@
+// mpm_common.cuh -- device-side parameter block, particle/grid layout and exact-arithmetic helpers shared
+// by every kernel of libmpm_b200.so.
+//
+// Layout in HBM
+//   particles : SoA planes of `pitch` floats inside one allocation (pitch % 32 == 0 so every plane starts
+//               on a 128-B line): planes 0-2 pos, 3-5 vel, 6 mass, 7-15 C column-major (7-9 = Basis.X).
+//               One warp reads 128 contiguous bytes per plane -> every access is a full-line transaction.
+//   grid      : array of 16-B cells (vel_x, vel_y, vel_z, mass) in the reference's index order
+//               x*Ry*Rz + y*Rz + z (MLSMPM3DFluidMultithread.cs:282), int32 x 1e7 or float.
+//               A multi-GPU rank stores only its x-slab: local plane lx = x - gx0, nxl planes.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mpm {
+
+enum Plane { PX = 0, PY, PZ, VX, VY, VZ, PM, C0, C1, C2, C3, C4, C5, C6, C7, C8, NPLANES };
+
+struct DevParams {
+    int dim;
+    int Rx, Ry, Rz;  // global grid resolution (Rz = 1 in 2D)
+    int gx0, nxl;    // first global x plane stored locally, number of local planes (incl. ghosts)
+    float dt, gravity, rest_density, visc, eos_k, eos_p;
+    int eos_pi;      // eos_p if it is an integer in [1,64], else 0
+    int grid_mode;   // 0 float, 1 fixed
+    float fmult;     // (float)fixed_point_mult
+    int stress_form, eq16_order, bc_mode, bc_hi_off;
+    float bc_friction;
+    float clamp_min, clamp_max_off, wall_min, wall_max_off, wall_gain;
+    int interaction;
+    float sphere[3], sphere_r, mouse[2], mouse_r;
+    int overflow_check;
+};
+
+struct ParticleView {
+    float* base;
+    int64_t pitch;
+    __host__ __device__ __forceinline__ float* plane(int k) const { return base + (int64_t)k * pitch; }
+};
+
+// ---- strict IEEE binary32 operators: the _rn intrinsics are never contracted into FMA by nvcc, so the
+// results do not depend on -fmad and equal the C# / C oracle operation by operation.
+__device__ __forceinline__ float sadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float ssub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float smul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float sdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+// EncodeFixedPoint / DecodeFixedPoint (MLSMPM3DFluidMultithreadNew.cs:151-159)
+__device__ __forceinline__ int encode_fixed(float f, float fmult) { return __float2int_rz(__fmul_rn(f, fmult)); }
+__device__ __forceinline__ float decode_fixed(int i, float fmult) { return __fdiv_rn(__int2float_rn(i), fmult); }
+
+// Quadratic B-spline weights of one axis (MLSMPM3DFluidMultithread.cs:259-263), exact op order.
+__device__ __forceinline__ int axis_weights(float p, float w[3])
+{
+    int c = __float2int_rz(p);
+    float cd = ssub(ssub(p, __int2float_rn(c)), 0.5f);
+    float a = ssub(0.5f, cd), b = sadd(0.5f, cd);
+    w[0] = smul(0.5f, smul(a, a));
+    w[1] = ssub(0.75f, smul(cd, cd));
+    w[2] = smul(0.5f, smul(b, b));
+    return c;
+}
+
+// EOS power (Mathf.Pow, MLSMPM3DFluidMultithread.cs:331).  The reference value is the platform CRT's
+// powf (<= 1 ulp, platform-dependent); the solver evaluates in binary64 and rounds once, which is
+// reproducible on any IEEE machine (integer exponents: left-to-right repeated multiplication).
+__device__ __forceinline__ float eos_pow(float x, const DevParams& P)
+{
+    if (P.eos_pi > 0) {
+        double xd = (double)x, r = xd;
+        for (int k = 1; k < P.eos_pi; ++k) r = __dmul_rn(r, xd);
+        return __double2float_rn(r);
+    }
+    return __double2float_rn(pow((double)x, (double)P.eos_p));
+}
+
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// local cell index of global node (nx, ny, nz)
+__device__ __forceinline__ int64_t cell_index(const DevParams& P, int nx, int ny, int nz)
+{
+    return ((int64_t)(nx - P.gx0) * P.Ry + ny) * P.Rz + nz;
+}
+
+}  // namespace mpm

@@ -1,0 +1,138 @@
+// mpm_io.cu -- layout conversion between the reference's buffers and the solver's SoA planes, the
+// position hand-off array, and the lattice scene generator.  None of this is on the per-step hot path.
+#include "mpm_kernels.h"
+
+namespace mpm {
+
+// Reference particle record (MLSMPM3DFluidMultithreadGPU.cs:8-22): 20 floats =
+// pos.xyz pad | vel.xyz mass | C_x.xyz pad | C_y.xyz pad | C_z.xyz pad
+__global__ void __launch_bounds__(256) k_aos80_to_soa(const float4* __restrict__ aos, ParticleView pv,
+                                                      int64_t dst_off, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 a = aos[5 * i], b = aos[5 * i + 1], c0 = aos[5 * i + 2], c1 = aos[5 * i + 3], c2 = aos[5 * i + 4];
+    const int64_t d = dst_off + i;
+    pv.plane(PX)[d] = a.x; pv.plane(PY)[d] = a.y; pv.plane(PZ)[d] = a.z;
+    pv.plane(VX)[d] = b.x; pv.plane(VY)[d] = b.y; pv.plane(VZ)[d] = b.z; pv.plane(PM)[d] = b.w;
+    pv.plane(C0)[d] = c0.x; pv.plane(C1)[d] = c0.y; pv.plane(C2)[d] = c0.z;
+    pv.plane(C3)[d] = c1.x; pv.plane(C4)[d] = c1.y; pv.plane(C5)[d] = c1.z;
+    pv.plane(C6)[d] = c2.x; pv.plane(C7)[d] = c2.y; pv.plane(C8)[d] = c2.z;
+}
+
+__global__ void __launch_bounds__(256) k_soa_to_aos80(ParticleView pv, const uint32_t* __restrict__ orig_id,
+                                                      float4* __restrict__ aos, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t o = orig_id ? (int64_t)orig_id[i] : i;
+    aos[5 * o] = make_float4(pv.plane(PX)[i], pv.plane(PY)[i], pv.plane(PZ)[i], 0.0f);
+    aos[5 * o + 1] = make_float4(pv.plane(VX)[i], pv.plane(VY)[i], pv.plane(VZ)[i], pv.plane(PM)[i]);
+    aos[5 * o + 2] = make_float4(pv.plane(C0)[i], pv.plane(C1)[i], pv.plane(C2)[i], 0.0f);
+    aos[5 * o + 3] = make_float4(pv.plane(C3)[i], pv.plane(C4)[i], pv.plane(C5)[i], 0.0f);
+    aos[5 * o + 4] = make_float4(pv.plane(C6)[i], pv.plane(C7)[i], pv.plane(C8)[i], 0.0f);
+}
+
+__global__ void __launch_bounds__(256) k_packed_to_soa(const float* __restrict__ pos, const float* __restrict__ vel,
+                                                       const float* __restrict__ C, const float* __restrict__ mass,
+                                                       ParticleView pv, int64_t dst_off, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t d = dst_off + i;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        pv.plane(PX + a)[d] = pos[3 * i + a];
+        pv.plane(VX + a)[d] = vel ? vel[3 * i + a] : 0.0f;
+    }
+    pv.plane(PM)[d] = mass ? mass[i] : 1.0f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) pv.plane(C0 + k)[d] = C ? C[9 * i + k] : 0.0f;
+}
+
+__global__ void __launch_bounds__(256) k_soa_to_packed(ParticleView pv, const uint32_t* __restrict__ orig_id,
+                                                       float* pos, float* vel, float* C, float* mass, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t o = orig_id ? (int64_t)orig_id[i] : i;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        if (pos) pos[3 * o + a] = pv.plane(PX + a)[i];
+        if (vel) vel[3 * o + a] = pv.plane(VX + a)[i];
+    }
+    if (mass) mass[o] = pv.plane(PM)[i];
+    if (C) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) C[9 * o + k] = pv.plane(C0 + k)[i];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_iota(uint32_t* p, uint32_t start, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = start + (uint32_t)i;
+}
+
+// (x, y, z, |v|) of g2p.glsl:149-150, original index order
+__global__ void __launch_bounds__(256) k_positions(ParticleView pv, const uint32_t* __restrict__ orig_id,
+                                                   float4* __restrict__ positions, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float vx = pv.plane(VX)[i], vy = pv.plane(VY)[i], vz = pv.plane(VZ)[i];
+    const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz)));
+    positions[orig_id ? orig_id[i] : (uint32_t)i] = make_float4(pv.plane(PX)[i], pv.plane(PY)[i], pv.plane(PZ)[i], len);
+}
+
+__global__ void __launch_bounds__(256) k_lattice(const float* __restrict__ xs, int nx, const float* __restrict__ ys,
+                                                 int ny, const float* __restrict__ zs, int nz, ParticleView pv,
+                                                 int64_t dst_off)
+{
+    const int64_t n = (int64_t)nx * ny * nz;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int iz = (int)(i % nz), iy = (int)(i / nz % ny), ix = (int)(i / nz / ny);
+    const int64_t d = dst_off + i;
+    pv.plane(PX)[d] = xs[ix]; pv.plane(PY)[d] = ys[iy]; pv.plane(PZ)[d] = zs[iz];
+    pv.plane(VX)[d] = 0.0f; pv.plane(VY)[d] = 0.0f; pv.plane(VZ)[d] = 0.0f; pv.plane(PM)[d] = 1.0f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) pv.plane(C0 + k)[d] = 0.0f;
+}
+
+static inline unsigned nb(int64_t n) { return (unsigned)((n + 255) / 256); }
+
+void launch_aos80_to_soa(const float* aos, ParticleView pv, int64_t dst_off, int64_t n, cudaStream_t st)
+{
+    if (n > 0) k_aos80_to_soa<<<nb(n), 256, 0, st>>>(reinterpret_cast<const float4*>(aos), pv, dst_off, n);
+}
+void launch_soa_to_aos80(ParticleView pv, const uint32_t* orig_id, float* aos, int64_t n, cudaStream_t st)
+{
+    if (n > 0) k_soa_to_aos80<<<nb(n), 256, 0, st>>>(pv, orig_id, reinterpret_cast<float4*>(aos), n);
+}
+void launch_packed_to_soa(const float* pos, const float* vel, const float* C, const float* mass, ParticleView pv,
+                          int64_t dst_off, int64_t n, cudaStream_t st)
+{
+    if (n > 0) k_packed_to_soa<<<nb(n), 256, 0, st>>>(pos, vel, C, mass, pv, dst_off, n);
+}
+void launch_soa_to_packed(ParticleView pv, const uint32_t* orig_id, float* pos, float* vel, float* C, float* mass,
+                          int64_t n, cudaStream_t st)
+{
+    if (n > 0) k_soa_to_packed<<<nb(n), 256, 0, st>>>(pv, orig_id, pos, vel, C, mass, n);
+}
+void launch_iota(uint32_t* p, uint32_t start, int64_t n, cudaStream_t st)
+{
+    if (n > 0) k_iota<<<nb(n), 256, 0, st>>>(p, start, n);
+}
+void launch_positions(ParticleView pv, const uint32_t* orig_id, float4* positions, int64_t n, cudaStream_t st)
+{
+    if (n > 0) k_positions<<<nb(n), 256, 0, st>>>(pv, orig_id, positions, n);
+}
+void launch_lattice(const float* xs, int nx, const float* ys, int ny, const float* zs, int nz, ParticleView pv,
+                    int64_t dst_off, cudaStream_t st)
+{
+    const int64_t n = (int64_t)nx * ny * nz;
+    if (n > 0) k_lattice<<<nb(n), 256, 0, st>>>(xs, nx, ys, ny, zs, nz, pv, dst_off);
+}
+
+}  // namespace mpm

@@ -1,0 +1,295 @@
+// mpm_kernels_tiled.cu -- the B200 kernel path (MPM_PATH_TILED) for the 3D int32 fixed-point grid.
+//
+// Particles are binned by BxBxB grid block (mpm_sort.cu); one CTA owns one block's contiguous particle
+// range and stages the block's (B+2)^3-node grid tile (block + 1-node apron = everything a quadratic
+// B-spline stencil of a particle in the block can touch) in shared memory:
+//   P2G_1 : smem tile of int32 accumulators (mass, momentum), native ATOMS.ADD, then one global RED per
+//           touched node and channel -> global atomics drop from 108/particle to ~1-2/particle.
+//   P2G_2 : mass tile loaded once and decoded once per node; momentum tile accumulated as above.
+//   G2P   : velocity tile loaded and decoded once per node, 27-node gather from smem, fused advection,
+//           clamp, interaction, predictive wall and the (x,y,z,|v|) hand-off write.
+// A particle whose base cell has drifted out of its CTA's block since the last bin phase (sort_interval>1)
+// takes a slow path straight to global memory, so the result never depends on how stale the binning is.
+// Arithmetic is the strict path of mpm_particle_math.cuh: bit-identical to the reference-shaped kernels.
+#include "mpm_kernels.h"
+#include "mpm_particle_math.cuh"
+#include "mpm_solver.h"
+
+namespace mpm {
+
+const uint32_t* sort_block_start(const MpmSolver* s);
+void sort_geometry(const MpmSolver* s, int& B, int& nbx, int& nby, int& nbz, int64_t& nblocks);
+
+constexpr int TILED_THREADS = 256;
+
+struct TileGeom {
+    int nby, nbz;
+    int x_owned0;  // global x of the first plane covered by blocks (gx0, or gx0+1 with a ghost plane)
+};
+
+template <int B>
+struct Tile {
+    static constexpr int T = B + 2;
+    static constexpr int N = T * T * T;
+    int ox, oy, oz;  // global node coordinates of tile node (0,0,0)
+    __device__ __forceinline__ void init(const TileGeom& g, int b)
+    {
+        const int bz = b % g.nbz, by = (b / g.nbz) % g.nby, bx = b / (g.nbz * g.nby);
+        ox = g.x_owned0 + bx * B - 1; oy = by * B - 1; oz = bz * B - 1;
+    }
+    // tile index of the stencil's first node if the whole 3x3x3 stencil of base cell (cx,cy,cz) is inside
+    __device__ __forceinline__ bool stencil_base(int cx, int cy, int cz, int& idx) const
+    {
+        const int tx = cx - 1 - ox, ty = cy - 1 - oy, tz = cz - 1 - oz;
+        idx = (tx * T + ty) * T + tz;
+        return (unsigned)tx <= (unsigned)(T - 3) && (unsigned)ty <= (unsigned)(T - 3) && (unsigned)tz <= (unsigned)(T - 3);
+    }
+    __device__ __forceinline__ bool node_global(const DevParams& P, int idx, int64_t& ci) const
+    {
+        const int tz = idx % T, ty = (idx / T) % T, tx = idx / (T * T);
+        const int nx = ox + tx, ny = oy + ty, nz = oz + tz;
+        if (nx < P.gx0 || nx >= P.gx0 + P.nxl || ny < 0 || ny >= P.Ry || nz < 0 || nz >= P.Rz) return false;
+        ci = cell_index(P, nx, ny, nz);
+        return true;
+    }
+};
+
+// ---------------------------------------------------------------- P2G_1
+template <int B>
+__global__ void __launch_bounds__(TILED_THREADS) k_p2g1_tiled(DevParams P, TileGeom g, ParticleView pv,
+                                                              const uint32_t* __restrict__ block_start, int* __restrict__ grid)
+{
+    using TL = Tile<B>;
+    __shared__ int tile[4][TL::N];
+    const int b = blockIdx.x;
+    const uint32_t s0 = block_start[b], s1 = block_start[b + 1];
+    if (s0 == s1) return;
+    TL tl; tl.init(g, b);
+    for (int k = threadIdx.x; k < 4 * TL::N; k += TILED_THREADS) (&tile[0][0])[k] = 0;
+    __syncthreads();
+    for (uint32_t i = s0 + threadIdx.x; i < s1; i += TILED_THREADS) {
+        ParticleIn p;
+        p.px = pv.plane(PX)[i]; p.py = pv.plane(PY)[i]; p.pz = pv.plane(PZ)[i];
+        p.vx = pv.plane(VX)[i]; p.vy = pv.plane(VY)[i]; p.vz = pv.plane(VZ)[i];
+        p.m = pv.plane(PM)[i];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) p.c[k] = pv.plane(C0 + k)[i];
+        float wx[3], wy[3], wz[3];
+        const int cx = axis_weights(p.px, wx), cy = axis_weights(p.py, wy), cz = axis_weights(p.pz, wz);
+        int base;
+        const bool inside = tl.stencil_base(cx, cy, cz, base);
+#pragma unroll
+        for (int gx = 0; gx < 3; ++gx)
+#pragma unroll
+            for (int gy = 0; gy < 3; ++gy)
+#pragma unroll
+                for (int gz = 0; gz < 3; ++gz) {
+                    const float weight = smul(smul(wx[gx], wy[gy]), wz[gz]);
+                    const int nx = cx + gx - 1, ny = cy + gy - 1, nz = cz + gz - 1;
+                    float mc, ox, oy, oz;
+                    p2g1_node<3>(p, weight, node_dist(nx, p.px), node_dist(ny, p.py), node_dist(nz, p.pz), mc, ox, oy, oz);
+                    const int em = encode_fixed(mc, P.fmult), ex = encode_fixed(ox, P.fmult), ey = encode_fixed(oy, P.fmult),
+                              ez = encode_fixed(oz, P.fmult);
+                    if (inside) {
+                        const int idx = base + (gx * TL::T + gy) * TL::T + gz;
+                        atomicAdd(&tile[3][idx], em); atomicAdd(&tile[0][idx], ex);
+                        atomicAdd(&tile[1][idx], ey); atomicAdd(&tile[2][idx], ez);
+                    } else {
+                        int* c = grid + 4 * cell_index(P, nx, ny, nz);
+                        atomicAdd(c + 3, em); atomicAdd(c + 0, ex); atomicAdd(c + 1, ey); atomicAdd(c + 2, ez);
+                    }
+                }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < TL::N; idx += TILED_THREADS) {
+        const int vx = tile[0][idx], vy = tile[1][idx], vz = tile[2][idx], m = tile[3][idx];
+        if ((vx | vy | vz | m) == 0) continue;
+        int64_t ci;
+        if (!tl.node_global(P, idx, ci)) continue;
+        int* c = grid + 4 * ci;
+        if (vx) atomicAdd(c + 0, vx);
+        if (vy) atomicAdd(c + 1, vy);
+        if (vz) atomicAdd(c + 2, vz);
+        if (m) atomicAdd(c + 3, m);
+    }
+}
+
+// ---------------------------------------------------------------- P2G_2
+template <int B>
+__global__ void __launch_bounds__(TILED_THREADS) k_p2g2_tiled(DevParams P, TileGeom g, ParticleView pv,
+                                                              const uint32_t* __restrict__ block_start, int* __restrict__ grid)
+{
+    using TL = Tile<B>;
+    __shared__ int tile[3][TL::N];
+    __shared__ float tmass[TL::N];
+    const int b = blockIdx.x;
+    const uint32_t s0 = block_start[b], s1 = block_start[b + 1];
+    if (s0 == s1) return;
+    TL tl; tl.init(g, b);
+    for (int idx = threadIdx.x; idx < TL::N; idx += TILED_THREADS) {
+        tile[0][idx] = 0; tile[1][idx] = 0; tile[2][idx] = 0;
+        int64_t ci;
+        tmass[idx] = tl.node_global(P, idx, ci) ? decode_fixed(grid[4 * ci + 3], P.fmult) : 0.0f;
+    }
+    __syncthreads();
+    for (uint32_t i = s0 + threadIdx.x; i < s1; i += TILED_THREADS) {
+        const float px = pv.plane(PX)[i], py = pv.plane(PY)[i], pz = pv.plane(PZ)[i], m = pv.plane(PM)[i];
+        float c[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) c[k] = pv.plane(C0 + k)[i];
+        float wx[3], wy[3], wz[3];
+        const int cx = axis_weights(px, wx), cy = axis_weights(py, wy), cz = axis_weights(pz, wz);
+        int base;
+        const bool inside = tl.stencil_base(cx, cy, cz, base);
+        float density = 0.0f;
+#pragma unroll
+        for (int gx = 0; gx < 3; ++gx)
+#pragma unroll
+            for (int gy = 0; gy < 3; ++gy)
+#pragma unroll
+                for (int gz = 0; gz < 3; ++gz) {
+                    const float weight = smul(smul(wx[gx], wy[gy]), wz[gz]);
+                    float gm;
+                    if (inside) gm = tmass[base + (gx * TL::T + gy) * TL::T + gz];
+                    else gm = decode_fixed(grid[4 * cell_index(P, cx + gx - 1, cy + gy - 1, cz + gz - 1) + 3], P.fmult);
+                    density = sadd(density, smul(gm, weight));
+                }
+        float e[9];
+        p2g2_stress<3>(P, c, m, density, e);
+#pragma unroll
+        for (int gx = 0; gx < 3; ++gx)
+#pragma unroll
+            for (int gy = 0; gy < 3; ++gy)
+#pragma unroll
+                for (int gz = 0; gz < 3; ++gz) {
+                    const float weight = smul(smul(wx[gx], wy[gy]), wz[gz]);
+                    const int nx = cx + gx - 1, ny = cy + gy - 1, nz = cz + gz - 1;
+                    float ox, oy, oz;
+                    p2g2_node<3>(e, weight, node_dist(nx, px), node_dist(ny, py), node_dist(nz, pz), ox, oy, oz);
+                    const int ex = encode_fixed(ox, P.fmult), ey = encode_fixed(oy, P.fmult), ez = encode_fixed(oz, P.fmult);
+                    if (inside) {
+                        const int idx = base + (gx * TL::T + gy) * TL::T + gz;
+                        atomicAdd(&tile[0][idx], ex); atomicAdd(&tile[1][idx], ey); atomicAdd(&tile[2][idx], ez);
+                    } else {
+                        int* cc = grid + 4 * cell_index(P, nx, ny, nz);
+                        atomicAdd(cc + 0, ex); atomicAdd(cc + 1, ey); atomicAdd(cc + 2, ez);
+                    }
+                }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < TL::N; idx += TILED_THREADS) {
+        const int vx = tile[0][idx], vy = tile[1][idx], vz = tile[2][idx];
+        if ((vx | vy | vz) == 0) continue;
+        int64_t ci;
+        if (!tl.node_global(P, idx, ci)) continue;
+        int* c = grid + 4 * ci;
+        if (vx) atomicAdd(c + 0, vx);
+        if (vy) atomicAdd(c + 1, vy);
+        if (vz) atomicAdd(c + 2, vz);
+    }
+}
+
+// ---------------------------------------------------------------- G2P
+template <int B>
+__global__ void __launch_bounds__(TILED_THREADS) k_g2p_tiled(DevParams P, TileGeom g, ParticleView pv,
+                                                             const uint32_t* __restrict__ block_start, const int4* __restrict__ grid,
+                                                             const uint32_t* __restrict__ orig_id, float4* __restrict__ positions)
+{
+    using TL = Tile<B>;
+    __shared__ float tv[3][TL::N];
+    const int b = blockIdx.x;
+    const uint32_t s0 = block_start[b], s1 = block_start[b + 1];
+    if (s0 == s1) return;
+    TL tl; tl.init(g, b);
+    for (int idx = threadIdx.x; idx < TL::N; idx += TILED_THREADS) {
+        int64_t ci;
+        float vx = 0.0f, vy = 0.0f, vz = 0.0f;
+        if (tl.node_global(P, idx, ci)) {
+            const int4 c = grid[ci];
+            vx = decode_fixed(c.x, P.fmult); vy = decode_fixed(c.y, P.fmult); vz = decode_fixed(c.z, P.fmult);
+        }
+        tv[0][idx] = vx; tv[1][idx] = vy; tv[2][idx] = vz;
+    }
+    __syncthreads();
+    for (uint32_t i = s0 + threadIdx.x; i < s1; i += TILED_THREADS) {
+        const float old[3] = {pv.plane(PX)[i], pv.plane(PY)[i], pv.plane(PZ)[i]};
+        float wx[3], wy[3], wz[3];
+        const int cx = axis_weights(old[0], wx), cy = axis_weights(old[1], wy), cz = axis_weights(old[2], wz);
+        int base;
+        const bool inside = tl.stencil_base(cx, cy, cz, base);
+        float Bm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, v[3] = {0, 0, 0};
+#pragma unroll
+        for (int gx = 0; gx < 3; ++gx)
+#pragma unroll
+            for (int gy = 0; gy < 3; ++gy)
+#pragma unroll
+                for (int gz = 0; gz < 3; ++gz) {
+                    const float weight = smul(smul(wx[gx], wy[gy]), wz[gz]);
+                    const int nx = cx + gx - 1, ny = cy + gy - 1, nz = cz + gz - 1;
+                    float gvx, gvy, gvz;
+                    if (inside) {
+                        const int idx = base + (gx * TL::T + gy) * TL::T + gz;
+                        gvx = tv[0][idx]; gvy = tv[1][idx]; gvz = tv[2][idx];
+                    } else {
+                        const int4 c = grid[cell_index(P, nx, ny, nz)];
+                        gvx = decode_fixed(c.x, P.fmult); gvy = decode_fixed(c.y, P.fmult); gvz = decode_fixed(c.z, P.fmult);
+                    }
+                    g2p_node<3>(gvx, gvy, gvz, weight, node_dist(nx, old[0]), node_dist(ny, old[1]), node_dist(nz, old[2]), Bm, v);
+                }
+        float np[3], c[9];
+        g2p_finish<3>(P, old, Bm, v, np, c);
+        pv.plane(PX)[i] = np[0]; pv.plane(PY)[i] = np[1]; pv.plane(PZ)[i] = np[2];
+        pv.plane(VX)[i] = v[0]; pv.plane(VY)[i] = v[1]; pv.plane(VZ)[i] = v[2];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) pv.plane(C0 + k)[i] = c[k];
+        const float len = __fsqrt_rn(sadd(sadd(smul(v[0], v[0]), smul(v[1], v[1])), smul(v[2], v[2])));
+        positions[orig_id[i]] = make_float4(np[0], np[1], np[2], len);
+    }
+}
+
+// ---------------------------------------------------------------- host side
+static int check_supported(MpmSolver* s)
+{
+    if (s->dp.dim != 3 || s->dp.grid_mode != MPM_GRID_FIXED) {
+        s->err = "the tiled path implements the 3D fixed-point grid; use MPM_PATH_REFERENCE (or AUTO) for 2D / float grids";
+        return MPM_ERR_INVALID;
+    }
+    return MPM_OK;
+}
+
+#define LAUNCH_TILED(KERNEL, ...)                                                                         \
+    do {                                                                                                  \
+        int B, nbx, nby, nbz; int64_t nblocks;                                                            \
+        sort_geometry(s, B, nbx, nby, nbz, nblocks);                                                      \
+        TileGeom g{nby, nbz, s->dp.gx0 + (s->comm ? 1 : 0)};                                              \
+        if (B == 8) KERNEL<8><<<(unsigned)nblocks, TILED_THREADS, 0, s->stream>>>(s->dp, g, __VA_ARGS__); \
+        else KERNEL<4><<<(unsigned)nblocks, TILED_THREADS, 0, s->stream>>>(s->dp, g, __VA_ARGS__);        \
+        s->launches += 1;                                                                                 \
+    } while (0)
+
+int tiled_p2g1(MpmSolver* s)
+{
+    int rc = check_supported(s);
+    if (rc) return rc;
+    if (s->n == 0) return MPM_OK;
+    LAUNCH_TILED(k_p2g1_tiled, s->view(), sort_block_start(s), reinterpret_cast<int*>(s->grid));
+    return MPM_OK;
+}
+int tiled_p2g2(MpmSolver* s)
+{
+    int rc = check_supported(s);
+    if (rc) return rc;
+    if (s->n == 0) return MPM_OK;
+    LAUNCH_TILED(k_p2g2_tiled, s->view(), sort_block_start(s), reinterpret_cast<int*>(s->grid));
+    return MPM_OK;
+}
+int tiled_g2p(MpmSolver* s)
+{
+    int rc = check_supported(s);
+    if (rc) return rc;
+    if (s->n == 0) return MPM_OK;
+    LAUNCH_TILED(k_g2p_tiled, s->view(), sort_block_start(s), reinterpret_cast<const int4*>(s->grid), s->orig_id, s->positions);
+    return MPM_OK;
+}
+
+}  // namespace mpm

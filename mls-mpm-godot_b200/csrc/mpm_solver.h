@@ -1,0 +1,72 @@
+// mpm_solver.h -- the opaque solver object behind the C ABI (include/mpm_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/mpm_b200.h"
+#include "mpm_common.cuh"
+
+namespace mpm {
+struct SortState;  // mpm_sort.cu
+struct CommState;  // mpm_comm.cu
+}  // namespace mpm
+
+enum { PH_CLEAR = 0, PH_P2G1, PH_P2G2, PH_UPDATE, PH_G2P, PH_SORT, PH_EXCHANGE, PH_COUNT };
+
+struct MpmSolver {
+    MpmParams hp{};
+    mpm::DevParams dp{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+
+    int64_t cap = 0;    // max particles
+    int64_t pitch = 0;  // plane stride (floats)
+    int64_t n = 0;      // particles currently held (local)
+    float* part = nullptr;      // NPLANES * pitch floats
+    float* part_alt = nullptr;  // reorder target (tiled path)
+    uint32_t* orig_id = nullptr;      // original (global) index of the particle in each slot
+    uint32_t* orig_id_alt = nullptr;
+    void* grid = nullptr;  // ncells_local * 16 B
+    int64_t ncells = 0;    // local cells (nxl * Ry * Rz)
+    float4* positions = nullptr;  // (x, y, z, |v|) in original index order
+    bool positions_valid = false;
+    int32_t* overflow_flag = nullptr;  // device
+
+    int path = MPM_PATH_REFERENCE;  // resolved kernel path
+    int sort_interval = 1;
+    int64_t steps = 0, launches = 0;
+    int64_t steps_since_sort = 0;
+    bool sorted_valid = false;
+    mpm::SortState* sort = nullptr;
+    mpm::CommState* comm = nullptr;
+
+    // per-phase timing
+    bool timing = false;
+    std::vector<cudaEvent_t> ev;  // 2 events per phase per step, recycled
+    double ms_acc[PH_COUNT] = {0};
+    double ms_step_acc = 0;
+    int64_t timed_steps = 0;
+
+    std::string err;
+
+    mpm::ParticleView view() const { return mpm::ParticleView{part, pitch}; }
+    mpm::ParticleView view_alt() const { return mpm::ParticleView{part_alt, pitch}; }
+};
+
+namespace mpm {
+// binning (mpm_sort.cu): computes keys, stable radix sort, reorders particle planes into part_alt and swaps.
+int sort_create(MpmSolver* s);
+void sort_destroy(MpmSolver* s);
+int sort_particles(MpmSolver* s);
+int sort_debug_last(MpmSolver* s, uint32_t* keys_before, uint32_t* perm, int64_t cap);
+// tiled kernels (mpm_kernels_tiled.cu)
+int tiled_p2g1(MpmSolver* s);
+int tiled_p2g2(MpmSolver* s);
+int tiled_g2p(MpmSolver* s);
+// multi-GPU (mpm_comm.cu)
+void comm_destroy(MpmSolver* s);
+int comm_exchange_halo(MpmSolver* s, int pass);  // pass 0: after P2G_1 (4 words), 1: after P2G_2 (3 words)
+int comm_migrate(MpmSolver* s);
+}  // namespace mpm

@@ -1,0 +1,73 @@
+"""CPU tests of the drop-in boundary: libmpm_b200.so loads, exports every symbol include/mpm_b200.h
+declares, its structs have the layout the reference's blittable structs have, and its presets carry the
+reference's constants.  No compute is called without a GPU; and without one the library must FAIL LOUDLY."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import helpers
+from oracle import orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "mpm_b200.h")).read()
+    return sorted(set(re.findall(r"MPM_API\s+[\w\s\*]+?\b(mpm_\w+)\s*\(", src)))
+
+
+def test_exports_every_declared_symbol(lib):
+    import mpm_b200
+    names = header_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"libmpm_b200.so does not export {n}"
+    assert sorted(mpm_b200.EXPORTS) == names, "python binding and header disagree on the export list"
+
+
+def test_abi_version_and_struct_layout(lib):
+    import mpm_b200
+    assert lib.mpm_abi_version() == 1
+    assert C.sizeof(mpm_b200.MpmParams) == 4 * 35  # all members 4 bytes, no padding
+    assert mpm_b200.default_params("3d_gpu").struct_size == C.sizeof(mpm_b200.MpmParams)  # C side agrees
+    assert mpm_b200.PARTICLE80.itemsize == 80     # MLSMPM3DFluidMultithreadGPU.cs:8-22 (std430, 80 B)
+    offs = {k: mpm_b200.PARTICLE80.fields[k][1] for k in ("pos", "vel", "mass", "C_x", "C_y", "C_z")}
+    assert offs == {"pos": 0, "vel": 16, "mass": 28, "C_x": 32, "C_y": 48, "C_z": 64}
+
+
+@pytest.mark.parametrize("name", helpers.VARIANT_NAMES)
+def test_presets_carry_the_reference_constants(lib, name):
+    import mpm_b200
+    p = mpm_b200.default_params(name)
+    o = orc.variant(name)
+    assert p.dim == o.dim and list(p.grid_size) == list(o.grid)
+    for f in helpers._SHARED:
+        assert getattr(p, f) == getattr(o, f), f
+    assert list(p.sphere_pos) == list(o.sphere_pos)
+
+
+def test_bad_params_are_rejected_before_touching_cuda(lib):
+    import mpm_b200
+    p = mpm_b200.default_params("3d_gpu")
+    p.struct_size = 12
+    h = C.c_void_p()
+    assert lib.mpm_create(C.byref(p), 1000, 0, C.byref(h)) == mpm_b200.ERR_INVALID
+    assert b"struct_size" in lib.mpm_last_error(None)
+    p = mpm_b200.default_params("3d_gpu"); p.dim = 4
+    assert lib.mpm_create(C.byref(p), 1000, 0, C.byref(h)) == mpm_b200.ERR_INVALID
+    p = mpm_b200.default_params("3d_fixed"); p.bc_mode = 1
+    assert lib.mpm_create(C.byref(p), 1000, 0, C.byref(h)) == mpm_b200.ERR_INVALID
+
+
+def test_no_gpu_means_loud_failure_not_cpu_fallback(lib):
+    import mpm_b200
+    if lib.mpm_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    p = mpm_b200.default_params("3d_gpu")
+    with pytest.raises(mpm_b200.MpmError) as e:
+        mpm_b200.Solver(p, 1000)
+    assert e.value.code == mpm_b200.ERR_CUDA
+    assert "no CPU fallback" in str(e.value)

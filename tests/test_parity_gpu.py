@@ -1,0 +1,254 @@
+"""GPU parity tests (run on the B200 box with -m gpu).  Everything goes through the C ABI.
+
+Bar: int32 fixed-point grid mode (the reference's deterministic model: MLSMPM3DFluidMultithreadNew.cs and the
+GLSL shaders) -> grid words, particle floats, cell keys and the binning permutation are BIT-EXACT against the
+oracle.  Float grid mode -> atomic order differs from the reference's serial order, so the tolerance is
+calibrated from the oracle's own sensitivity to particle order and written in the test.
+PARITY UNPINNED: the oracle is a restatement (no reference golden vectors exist)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import helpers
+from oracle import orc
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+import make_golden  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+PHASES = ["clear_grid", "p2g1", "p2g2", "update_grid", "g2p"]
+
+
+def make_solver(op, n, **over):
+    import mpm_b200
+    return mpm_b200.Solver(helpers.mpm_params_from_orc(op, **over), max(n, 1))
+
+
+def sphere_into_cloud(op):
+    if op.interaction in (1, 2):
+        op.sphere_pos[:] = [op.grid[0] * 0.3, op.grid[1] * 0.5, op.grid[2] * 0.5]
+        op.sphere_radius = 4.0
+
+
+# ---------------------------------------------------------------- fixed-point mode: bit-exact
+@pytest.mark.parametrize("path", [1, 2], ids=["reference_path", "tiled_path"])
+@pytest.mark.parametrize("variant,grid", [("3d_fixed", 32), ("3d_gpu", (40, 32, 24)), ("3d_gpu", 96)])
+def test_each_phase_bit_exact_fixed(lib, variant, grid, path):
+    op = orc.variant(variant, grid)
+    sphere_into_cloud(op)
+    n = 20000
+    pos, vel, Cm, mass = helpers.random_cloud(op, n, seed=21)
+    ref = orc.State(op, pos, vel, Cm, mass)
+    with make_solver(op, n, kernel_path=path) as s:
+        s.upload(pos, vel, Cm, mass)
+        for k, ph in enumerate(PHASES):
+            getattr(ref, ph)()
+            s.run_phase(k)
+            helpers.assert_bit_equal(s.download_grid(), ref.grid, f"grid after {ph}")
+        gp, gv, gc, gm = s.download()
+        helpers.assert_bit_equal(gp, ref.pos, "pos"); helpers.assert_bit_equal(gv, ref.vel, "vel")
+        helpers.assert_bit_equal(gc, ref.C, "C"); helpers.assert_bit_equal(gm, ref.mass, "mass")
+        helpers.assert_bit_equal(s.positions(), ref.positions(), "positions (x,y,z,|v|)")
+        assert s.stats().kernel_path == path
+
+
+@pytest.mark.parametrize("sort_interval", [1, 4])
+@pytest.mark.parametrize("path", [1, 2], ids=["reference_path", "tiled_path"])
+def test_dam_break_trajectory_bit_exact_fixed(lib, path, sort_interval):
+    """Reference GPU scene family (MLSMPM3DFluidMultithreadGPU.cs:654-707) at reduced size, 30 steps."""
+    op = orc.variant("3d_gpu", 32)
+    op.interaction = 0
+    pos = orc.init_block(3, (4, 4, 4), (20, 20, 20), 0.5)  # 32^3 = 32768 particles against a corner
+    ref = orc.State(op, pos)
+    with make_solver(op, pos.shape[0], kernel_path=path, sort_interval=sort_interval) as s:
+        assert s.initialise_sim((4, 4, 4), (20, 20, 20), 0.5) == pos.shape[0]
+        for chunk in range(3):
+            ref.step(10)
+            s.step(10)
+            gp, gv, gc, gm = s.download()
+            helpers.assert_bit_equal(gp, ref.pos, f"pos after {10 * (chunk + 1)} steps")
+            helpers.assert_bit_equal(gv, ref.vel, "vel"); helpers.assert_bit_equal(gc, ref.C, "C")
+        helpers.assert_bit_equal(s.download_grid(), ref.grid, "grid")
+        assert np.abs(gv).max() > 0.5  # the block really collapsed
+
+
+@pytest.mark.parametrize("name", ["3d_fixed", "3d_gpu"])
+@pytest.mark.parametrize("path", [1, 2], ids=["reference_path", "tiled_path"])
+def test_golden_fixed(lib, name, path):
+    op, n, steps, seed = make_golden.case_params(name)
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", f"{name}.npz"))
+    with make_solver(op, n, kernel_path=path) as s:
+        s.upload(z["pos0"], z["vel0"], z["C0"], z["mass"])
+        s.step(int(z["steps"]))
+        gp, gv, gc, _ = s.download()
+        helpers.assert_bit_equal(s.download_grid(), z["grid"], "grid")
+        helpers.assert_bit_equal(gp, z["pos"], "pos"); helpers.assert_bit_equal(gv, z["vel"], "vel")
+        helpers.assert_bit_equal(gc, z["C"], "C")
+
+
+# ---------------------------------------------------------------- binning: bit-exact
+def block_key(op, pos, B):
+    """Restatement of the cell key: block id (x-major) * B^3 + cell rank inside the block."""
+    c = pos.astype(np.int32)
+    nby, nbz = -(-op.grid[1] // B), -(-op.grid[2] // B)
+    b = c // B
+    l = c % B
+    blk = (b[:, 0] * nby + b[:, 1]) * nbz + b[:, 2]
+    return (blk.astype(np.uint32) * np.uint32(B ** 3) + ((l[:, 0] * B + l[:, 1]) * B + l[:, 2]).astype(np.uint32))
+
+
+@pytest.mark.parametrize("grid,B", [(32, 4), (96, 8), ((128, 96, 96), 8)])
+def test_cell_keys_and_sort_permutation_bit_exact(lib, grid, B):
+    op = orc.variant("3d_gpu", grid)
+    op.interaction = 0
+    n = 300000
+    pos, vel, Cm, mass = helpers.random_cloud(op, n, seed=33)
+    pos[: n // 2] = pos[: n // 2] * 0.25 + 4.0  # half the particles crowd one corner: many equal keys
+    with make_solver(op, n, kernel_path=2) as s:
+        s.upload(pos, vel, Cm, mass)
+        s.run_phase(5)
+        keys, perm = s.last_sort()
+        assert np.array_equal(keys, block_key(op, pos, B)), "cell keys"
+        expect = orc.stable_sort_perm(keys)  # == std::stable_sort order
+        assert np.array_equal(perm.astype(np.int32), expect), "binning permutation is not the stable sort"
+        assert np.array_equal(perm.astype(np.int64), np.argsort(keys, kind="stable"))
+        # binning must be invisible from outside: downloads stay in original index order
+        gp, gv, gc, gm = s.download()
+        helpers.assert_bit_equal(gp, pos, "pos order"); helpers.assert_bit_equal(gm, mass, "mass order")
+
+
+def test_sort_edge_cases(lib):
+    op = orc.variant("3d_gpu", 32)
+    op.interaction = 0
+    with make_solver(op, 5000, kernel_path=2) as s:
+        s.step(2)  # empty particle set: nothing to do, nothing to crash
+        assert s.num_particles == 0 and not s.download_grid().any()
+        one = np.array([[10.5, 10.5, 10.5]], np.float32)
+        s.upload(one)
+        ref = orc.State(op, one)
+        s.step(3); ref.step(3)
+        helpers.assert_bit_equal(s.download()[0], ref.pos, "single particle")
+        # all particles in one cell (maximum key collision), ragged count (not a multiple of any tile)
+        rng = np.random.default_rng(2)
+        same = (np.array([[12.0, 13.0, 14.0]], np.float32) + rng.uniform(0.01, 0.99, (4097, 3)).astype(np.float32))
+        light = np.full(4097, 0.01, np.float32)  # keeps the int32 x 1e7 accumulators (|v| < 214.7) in range
+        s.params.rest_density = 40.0; s.update_push_constants(); op.rest_density = 40.0
+        s.upload(same, mass=light)
+        ref = orc.State(op, same, mass=light)
+        s.step(2); ref.step(2)
+        helpers.assert_bit_equal(s.download()[0], ref.pos, "one-cell pile-up")
+        helpers.assert_bit_equal(s.download_grid(), ref.grid, "one-cell pile-up grid")
+
+
+# ---------------------------------------------------------------- float grid mode: calibrated tolerance
+def shuffle_sensitivity(op, pos, vel, Cm, mass, steps):
+    """max relative deviation of the oracle's own result between natural and shuffled particle order."""
+    a = orc.State(op, pos, vel, Cm, mass); a.step(steps)
+    perm = np.random.default_rng(0).permutation(pos.shape[0])
+    b = orc.State(op, pos[perm], vel[perm], Cm[perm], mass[perm]); b.step(steps)
+    inv = np.argsort(perm)
+    return max(helpers.rel_err(b.pos[inv], a.pos), helpers.rel_err(b.vel[inv], a.vel), helpers.rel_err(b.C[inv], a.C),
+               helpers.rel_err(b.grid_f(), a.grid_f())), a
+
+
+@pytest.mark.parametrize("name", ["2d_st", "2d_mt", "3d_float"])
+def test_float_grid_within_calibrated_tolerance(lib, name):
+    op, n, steps, seed = make_golden.case_params(name)
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", f"{name}.npz"))
+    sens, ref = shuffle_sensitivity(op, z["pos0"], z["vel0"], z["C0"], z["mass"], int(z["steps"]))
+    tol = max(4.0 * sens, 2e-6)  # kappa = 4; floor = a few fp32 ulps
+    assert tol < 1e-3, f"order sensitivity unexpectedly large: {sens}"
+    with make_solver(op, n) as s:
+        s.upload(z["pos0"], z["vel0"], z["C0"], z["mass"])
+        s.step(int(z["steps"]))
+        gp, gv, gc, _ = s.download()
+        g = s.download_grid().view(np.float32)
+    for what, a, b in (("pos", gp, ref.pos), ("vel", gv, ref.vel), ("C", gc, ref.C), ("grid", g, ref.grid_f())):
+        e = helpers.rel_err(a, b)
+        assert e <= tol, f"{name} {what}: rel err {e:.3g} > tol {tol:.3g} (oracle order sensitivity {sens:.3g})"
+    # and against the committed golden vectors (made by the NumPy restatement)
+    assert helpers.rel_err(gp, z["pos"]) <= tol and helpers.rel_err(gv, z["vel"]) <= tol
+
+
+def test_2d_dam_break_config1_drift(lib):
+    """BASELINE config 1 (2D dam-break 128^2, 16384 particles, reference 2D params), 100 steps: trajectories
+    decorrelate chaotically in float mode, so compare aggregates."""
+    op = orc.variant("2d_st", (128, 128, 1))
+    pos = orc.init_block(2, (4, 4), (68, 68), 0.5)
+    assert pos.shape[0] == 16384
+    ref = orc.State(op, pos); ref.step(100)
+    with make_solver(op, pos.shape[0]) as s:
+        s.initialise_sim((4, 4), (68, 68), 0.5)
+        s.step(100)
+        gp, gv, _, _ = s.download()
+    com_err = np.abs(gp.mean(0) - ref.pos.mean(0)).max()
+    ke, ke_ref = 0.5 * (gv.astype(np.float64) ** 2).sum(), 0.5 * (ref.vel.astype(np.float64) ** 2).sum()
+    assert com_err < 0.05, f"centre of mass drift {com_err}"          # cells, after 100 steps
+    assert abs(ke - ke_ref) / ke_ref < 0.05, (ke, ke_ref)              # kinetic energy within 5 %
+    assert gp[:, :2].min() >= 1.0 and gp[:, :2].max() <= 126.0         # clamp bounds hold
+
+
+# ---------------------------------------------------------------- buffers in the reference's layouts
+def test_aos80_round_trip_and_position_texture(lib):
+    import mpm_b200
+    op = orc.variant("3d_gpu", 32)
+    n = 12345
+    pos, vel, Cm, mass = helpers.random_cloud(op, n, seed=44)
+    rec = np.zeros(n, mpm_b200.PARTICLE80)
+    rec["pos"], rec["vel"], rec["mass"] = pos, vel, mass
+    rec["C_x"], rec["C_y"], rec["C_z"] = Cm[:, 0:3], Cm[:, 3:6], Cm[:, 6:9]
+    with make_solver(op, n) as s:
+        s.upload_aos80(rec)
+        back = s.download_aos80()
+        for f in ("pos", "vel", "mass", "C_x", "C_y", "C_z"):
+            helpers.assert_bit_equal(back[f], rec[f], f)
+        p4 = s.positions()
+        helpers.assert_bit_equal(p4[:, :3], pos, "positions before any step")
+        dev_ptr, width = s.positions_device()
+        assert dev_ptr and width == int(np.sqrt(np.float32(n))) + 1  # MLSMPM3DFluidMultithreadGPU.cs:196
+
+
+def test_params_setters(lib):
+    op = orc.variant("3d_gpu", 32)
+    pos, vel, Cm, mass = helpers.random_cloud(op, 3000, seed=5)
+    with make_solver(op, 3000) as s:
+        s.upload(pos, vel, Cm, mass)
+        s.params.dt = 0.9  # Dt setter clamps to [0, 0.4] (MLSMPM3DFluidMultithreadGPU.cs:64)
+        s.params.gravity = -0.5  # the UI's startup value (main_ui.tscn:162)
+        s.update_push_constants()
+        op.dt, op.gravity = 0.4, -0.5
+        s.set_sphere((9.0, 9.0, 9.0)); op.sphere_pos[:] = [9.0, 9.0, 9.0]
+        ref = orc.State(op, pos, vel, Cm, mass)
+        s.step(2); ref.step(2)
+        helpers.assert_bit_equal(s.download()[1], ref.vel, "vel after parameter change")
+
+
+# ---------------------------------------------------------------- full-size, size-independent properties
+def test_full_size_block_drop_properties(lib):
+    """BASELINE config 3 (128^3, 4 096 000 particles): too big for the oracle in seconds, so check
+    (1) tiled path == reference-shaped path bit for bit (two independent kernel sets),
+    (2) grid mass == sum of the particles' encoded weights within the truncation bound (partition of unity),
+    (3) download order is the upload order."""
+    op = orc.variant("3d_gpu", 128)
+    op.interaction = 0
+    lo, hi = (24, 24, 24), (104, 104, 104)
+    res = {}
+    for path in (1, 2):
+        with make_solver(op, 4096000, kernel_path=path) as s:
+            assert s.initialise_sim(lo, hi, 0.5) == 4096000
+            s.run_phase(0); s.run_phase(1)
+            g1 = s.download_grid()
+            total = g1[:, 3].astype(np.int64).sum()
+            n = 4096000
+            assert 0 <= n * 10_000_000 - total <= 27 * n, "mass not conserved within the truncation bound"
+            s.run_phase(2); s.run_phase(3); s.run_phase(4)
+            s.step(2)
+            res[path] = (s.download_grid(), s.download())
+    helpers.assert_bit_equal(res[1][0], res[2][0], "grid: reference-shaped vs tiled path")
+    for k, what in enumerate(("pos", "vel", "C", "mass")):
+        helpers.assert_bit_equal(res[1][1][k], res[2][1][k], what)
+    xm = res[2][1][0][:, 0].reshape(160, -1).mean(1)  # lattice order: index = (ix*160 + iy)*160 + iz
+    assert np.all(np.diff(xm) > 0.25), "original (lattice) order lost"
