@@ -51,30 +51,42 @@ class ClockSampler:
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.t_begin = self.t_end = None
 
     def start(self):
+        """nvidia-smi needs ~1 s to attach, so it is started before the warm-up; samples are windowed afterwards."""
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
 
     def stop(self):
         if self.proc:
             self.proc.terminate()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        inside = [r for t, r in self.rows if self.t_begin is not None and self.t_begin - 0.02 <= t <= self.t_end + 0.02]
+        window = "timed region"
+        if not inside:  # region shorter than the sampling period: fall back to every sample taken under load
+            inside, window = [r for _, r in self.rows], "warm-up + timed region + e2e"
+        sm = sorted(int(r[0]) for r in inside if r and r[0].isdigit())
+        mx = [int(r[1]) for r in inside if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[k] for r in self.rows if len(r) >= 6 for k in range(4) if r[2 + k].lower().startswith("active")})
+        reasons = sorted({names[k] for r in inside if len(r) >= 6 for k in range(4) if r[2 + k].lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def scene_params(name):
@@ -195,19 +207,20 @@ def main():
     n_local = solver.stats().local_particles
 
     # ---- warm-up, then the timed region: K steps, device-timed on the solver's stream
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     solver.step(max(args.warmup, 3))
     solver.sync()
     solver.set_timing(True)
     launches0 = solver.stats().kernel_launches
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     t0 = time.perf_counter()
     solver.step(args.steps)   # mpm_step records CUDA events on its own stream around the K steps and each phase
     solver.sync()
     wall_ms = (time.perf_counter() - t0) * 1e3
+    sampler.mark_end()
     barrier()
-    clocks = sampler.stop()
     st = solver.stats()
     solver.set_timing(False)
     dev_ms = st.ms_step * args.steps
@@ -235,6 +248,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = n_total * e2e_steps / float(t.item())
     mpm_b200.host_free(pinned)
+    clocks = sampler.stop()
 
     if rank == 0:
         peak, peak_kind = peaks()

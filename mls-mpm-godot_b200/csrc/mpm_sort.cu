@@ -1,11 +1,18 @@
 // mpm_sort.cu -- particle binning: an integer LSD radix sort by cell key, hand-written for sm_100a.
 //
 // The reference never reorders particles (particle i keeps index i forever: SURVEY a13); binning is new.
-// Key = id of the BxBxB grid block that holds the particle's base cell (the cell index formula of
-// MLSMPM3DFluidMultithread.cs:282 applied block-wise) * B^3 + the cell's rank inside the block, so a
-// thread block of the tiled kernels owns one contiguous particle range and its grid tile fits in shared
-// memory.  The sort is stable (ties keep their previous relative order), so the permutation equals
-// std::stable_sort on the same keys bit for bit (tests/test_sort_parity.py).
+// Key = id of the BxBxB grid block that holds the particle's base cell: the cell index formula of
+// MLSMPM3DFluidMultithread.cs:282 applied to block coordinates, (bx*NBy + by)*NBz + bz, so a thread block of
+// the tiled kernels owns one contiguous particle range and its grid tile fits in shared memory.  (Ordering
+// by cell inside a block would buy nothing: the tile is in shared memory either way, and it costs a radix
+// pass.)  The sort is stable (ties keep their previous relative order), so the permutation equals
+// std::stable_sort on the same keys bit for bit (tests/test_parity_gpu.py).
+//
+// Lane interleave: measured on B200 (profiles/microbench/smem_atomics.cu) a conflict-free ATOMS.ADD costs
+// 0.78 ns/warp-instr/SM but 4.17 ns when 8 lanes hit one word -- which is what neighbouring lanes do when
+// neighbouring slots hold particles of one cell.  So inside each block's range the reorder writes sorted rank
+// r to slot (r * A^-1) mod cnt, i.e. slot q holds rank (q * A) mod cnt with A >= 17 coprime to cnt:
+// neighbouring lanes then work on particles 17+ ranks apart.  Results do not depend on it (int adds commute).
 //
 // Per pass (<= 8 key bits): k_tile_hist (per-tile digit counts) -> k_scan_rows (one CTA per digit scans
 // its counts across tiles) -> k_scan_bins -> k_scatter (stable in-tile ranking with __match_any_sync,
@@ -48,9 +55,8 @@ __device__ __forceinline__ uint32_t cell_key(const KeyGeom& g, int cx, int cy, i
     const int m = (1 << g.logB) - 1;
     const int lx = cx - g.gx0;  // local slab coordinate (slab origin is block-aligned)
     const int bx = lx >> g.logB, by = cy >> g.logB, bz = cz >> g.logB;
-    const uint32_t blk = (uint32_t)((bx * g.nby + by) * g.nbz + bz);
-    if (g.dim == 3) return (blk << (3 * g.logB)) | (uint32_t)((((lx & m) << g.logB) | (cy & m)) << g.logB | (cz & m));
-    return (blk << (2 * g.logB)) | (uint32_t)(((lx & m) << g.logB) | (cy & m));
+    (void)m;
+    return (uint32_t)((bx * g.nby + by) * g.nbz + bz);
 }
 
 __global__ void __launch_bounds__(256) k_make_keys(KeyGeom g, ParticleView pv, int64_t n, uint32_t* keys, uint32_t* vals,
@@ -205,13 +211,29 @@ __global__ void __launch_bounds__(SORT_THREADS) k_scatter(const uint32_t* __rest
     }
 }
 
-// gather the particle planes through the permutation (sorted rank i takes slot perm[i])
+__device__ __forceinline__ uint32_t gcd_u32(uint32_t a, uint32_t b)
+{
+    while (b) { const uint32_t t = a % b; a = b; b = t; }
+    return a;
+}
+
+// gather the particle planes through the permutation: slot i of a block's range takes sorted rank
+// s0 + ((i - s0) * A) mod cnt (lane interleave, see the header), and sorted rank r takes pre-sort slot perm[r]
 __global__ void __launch_bounds__(256) k_reorder(ParticleView src, ParticleView dst, const uint32_t* __restrict__ perm,
+                                                 const uint32_t* __restrict__ keys_sorted, const uint32_t* __restrict__ block_start,
                                                  const uint32_t* __restrict__ id_src, uint32_t* __restrict__ id_dst, int64_t n)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t j = perm[i];
+    const uint32_t b = keys_sorted[i];
+    const uint32_t s0 = block_start[b], cnt = block_start[b + 1] - s0;
+    uint32_t A = 1;
+    if (cnt > 34) {
+        A = 17;
+        while (gcd_u32(A, cnt) != 1) ++A;
+    }
+    const uint32_t r = s0 + (uint32_t)(((uint64_t)((uint32_t)i - s0) * A) % cnt);
+    const uint32_t j = perm[r];
     float v[NPLANES];
 #pragma unroll
     for (int k = 0; k < NPLANES; ++k) v[k] = src.plane(k)[j];
@@ -231,8 +253,9 @@ __global__ void __launch_bounds__(256) k_block_bounds(const uint32_t* __restrict
         return;
     }
     if (i >= n) return;
-    const int64_t b = keys[i] >> cell_bits;
-    const int64_t bp = (i > 0) ? (int64_t)(keys[i - 1] >> cell_bits) : -1;
+    (void)cell_bits;
+    const int64_t b = keys[i];
+    const int64_t bp = (i > 0) ? (int64_t)keys[i - 1] : -1;
     for (int64_t bb = bp + 1; bb <= b; ++bb) block_start[bb] = (uint32_t)i;
     if (i == n - 1)
         for (int64_t bb = b + 1; bb <= nblocks; ++bb) block_start[bb] = (uint32_t)n;
@@ -273,8 +296,7 @@ int sort_create(MpmSolver* s)
     st->nby = (s->dp.Ry + st->B - 1) / st->B;
     st->nbz = (s->dp.dim == 3) ? (s->dp.Rz + st->B - 1) / st->B : 1;
     st->nblocks = (int64_t)st->nbx * st->nby * st->nbz;
-    const int cell_bits = s->dp.dim * st->logB;
-    st->key_bits = ilog2_ceil(st->nblocks) + cell_bits;
+    st->key_bits = std::max(1, ilog2_ceil(st->nblocks));
     if (st->key_bits > 31) { s->err = "grid too large for 32-bit cell keys"; return MPM_ERR_INVALID; }
     st->passes = (st->key_bits + 7) / 8;
     st->bits_per_pass = (st->key_bits + st->passes - 1) / st->passes;
@@ -336,8 +358,9 @@ int sort_particles(MpmSolver* s)
         cur ^= 1;
     }
     st->final_buf = cur;
-    k_reorder<<<nb, 256, 0, s->stream>>>(s->view(), s->view_alt(), st->vals[cur], s->orig_id, s->orig_id_alt, n);
     k_block_bounds<<<nb, 256, 0, s->stream>>>(st->keys[cur], n, cell_bits, st->nblocks, st->block_start);
+    k_reorder<<<nb, 256, 0, s->stream>>>(s->view(), s->view_alt(), st->vals[cur], st->keys[cur], st->block_start, s->orig_id,
+                                         s->orig_id_alt, n);
     s->launches += 2;
     std::swap(s->part, s->part_alt);
     std::swap(s->orig_id, s->orig_id_alt);

@@ -91,13 +91,12 @@ def test_golden_fixed(lib, name, path):
 
 # ---------------------------------------------------------------- binning: bit-exact
 def block_key(op, pos, B):
-    """Restatement of the cell key: block id (x-major) * B^3 + cell rank inside the block."""
-    c = pos.astype(np.int32)
+    """Restatement of the bin key: id of the BxBxB block holding the base cell, (bx*NBy + by)*NBz + bz
+    (the reference's index formula, MLSMPM3DFluidMultithread.cs:282, on block coordinates)."""
+    c = pos.astype(np.int32)  # (Vector3I)p.pos: truncation (MLSMPM3DFluidMultithread.cs:259)
     nby, nbz = -(-op.grid[1] // B), -(-op.grid[2] // B)
     b = c // B
-    l = c % B
-    blk = (b[:, 0] * nby + b[:, 1]) * nbz + b[:, 2]
-    return (blk.astype(np.uint32) * np.uint32(B ** 3) + ((l[:, 0] * B + l[:, 1]) * B + l[:, 2]).astype(np.uint32))
+    return ((b[:, 0] * nby + b[:, 1]) * nbz + b[:, 2]).astype(np.uint32)
 
 
 @pytest.mark.parametrize("grid,B", [(32, 4), (96, 8), ((128, 96, 96), 8)])
