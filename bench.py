@@ -163,6 +163,8 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--sort-interval", type=int, default=0)
     ap.add_argument("--path", type=int, default=0, help="0 auto, 1 reference-shaped, 2 tiled")
+    ap.add_argument("--math", default="fast", choices=["strict", "fast"],
+                    help="strict = bit-exact vs the reference algorithm; fast = FMA/hoisted (tolerance in tests)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -189,7 +191,8 @@ def main():
         torch.cuda.synchronize()
 
     op, lo, hi, sp = scene_params(args.workload)
-    params = helpers.mpm_params_from_orc(op, kernel_path=args.path, sort_interval=args.sort_interval)
+    params = helpers.mpm_params_from_orc(op, kernel_path=args.path, sort_interval=args.sort_interval,
+                                         math_mode=1 if args.math == "fast" else 0)
     grid = WORKLOADS[args.workload][0]
     n_total = int(round((hi[0] - lo[0]) / sp)) ** 3
     G = grid[0] * grid[1] * grid[2]
@@ -265,7 +268,7 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32+int32-fixed-point", "data": "synthetic",
             "config": {"workload": WORKLOAD_DESC[args.workload], "grid": list(grid), "particles": n_total, "variant": "3d_gpu (H)",
-                       "grid_mode": "fixed 1e7", "math": "strict", "kernel_path": {1: "reference-shaped", 2: "tiled"}[st.kernel_path],
+                       "grid_mode": "fixed 1e7", "math": args.math, "kernel_path": {1: "reference-shaped", 2: "tiled"}[st.kernel_path],
                        "sort_interval": solver.params.sort_interval or 1, "parallelism": f"x-slab x{world}",
                        "l2": "inputs (2.1 GB particle planes) exceed the 126 MB L2; no flush needed",
                        "timing": "CUDA events on the solver stream inside mpm_step; wall-clock cross-check in wall_ms_per_step"},

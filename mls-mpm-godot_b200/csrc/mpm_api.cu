@@ -249,6 +249,7 @@ static void particles_changed(MpmSolver* s)
     s->positions_valid = false;
     s->sorted_valid = false;
     s->steps_since_sort = 0;
+    s->fresh_particles = true;
 }
 
 static int lattice_axis(float lo, float hi, float spacing, std::vector<float>& out)

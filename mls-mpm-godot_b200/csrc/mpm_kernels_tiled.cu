@@ -14,45 +14,14 @@
 #include "mpm_kernels.h"
 #include "mpm_particle_math.cuh"
 #include "mpm_solver.h"
+#include "mpm_tile.cuh"
+
+#include <type_traits>
 
 namespace mpm {
 
 const uint32_t* sort_block_start(const MpmSolver* s);
 void sort_geometry(const MpmSolver* s, int& B, int& nbx, int& nby, int& nbz, int64_t& nblocks);
-
-constexpr int TILED_THREADS = 256;
-
-struct TileGeom {
-    int nby, nbz;
-    int x_owned0;  // global x of the first plane covered by blocks (gx0, or gx0+1 with a ghost plane)
-};
-
-template <int B>
-struct Tile {
-    static constexpr int T = B + 2;
-    static constexpr int N = T * T * T;
-    int ox, oy, oz;  // global node coordinates of tile node (0,0,0)
-    __device__ __forceinline__ void init(const TileGeom& g, int b)
-    {
-        const int bz = b % g.nbz, by = (b / g.nbz) % g.nby, bx = b / (g.nbz * g.nby);
-        ox = g.x_owned0 + bx * B - 1; oy = by * B - 1; oz = bz * B - 1;
-    }
-    // tile index of the stencil's first node if the whole 3x3x3 stencil of base cell (cx,cy,cz) is inside
-    __device__ __forceinline__ bool stencil_base(int cx, int cy, int cz, int& idx) const
-    {
-        const int tx = cx - 1 - ox, ty = cy - 1 - oy, tz = cz - 1 - oz;
-        idx = (tx * T + ty) * T + tz;
-        return (unsigned)tx <= (unsigned)(T - 3) && (unsigned)ty <= (unsigned)(T - 3) && (unsigned)tz <= (unsigned)(T - 3);
-    }
-    __device__ __forceinline__ bool node_global(const DevParams& P, int idx, int64_t& ci) const
-    {
-        const int tz = idx % T, ty = (idx / T) % T, tx = idx / (T * T);
-        const int nx = ox + tx, ny = oy + ty, nz = oz + tz;
-        if (nx < P.gx0 || nx >= P.gx0 + P.nxl || ny < 0 || ny >= P.Ry || nz < 0 || nz >= P.Rz) return false;
-        ci = cell_index(P, nx, ny, nz);
-        return true;
-    }
-};
 
 // ---------------------------------------------------------------- P2G_1
 template <int B>
@@ -60,12 +29,12 @@ __global__ void __launch_bounds__(TILED_THREADS) k_p2g1_tiled(DevParams P, TileG
                                                               const uint32_t* __restrict__ block_start, int* __restrict__ grid)
 {
     using TL = Tile<B>;
-    __shared__ int tile[4][TL::N];
+    __shared__ int tile[4][TL::WORDS];
     const int b = blockIdx.x;
     const uint32_t s0 = block_start[b], s1 = block_start[b + 1];
     if (s0 == s1) return;
     TL tl; tl.init(g, b);
-    for (int k = threadIdx.x; k < 4 * TL::N; k += TILED_THREADS) (&tile[0][0])[k] = 0;
+    for (int k = threadIdx.x; k < 4 * TL::WORDS; k += TILED_THREADS) (&tile[0][0])[k] = 0;
     __syncthreads();
     for (uint32_t i = s0 + threadIdx.x; i < s1; i += TILED_THREADS) {
         ParticleIn p;
@@ -77,7 +46,9 @@ __global__ void __launch_bounds__(TILED_THREADS) k_p2g1_tiled(DevParams P, TileG
         float wx[3], wy[3], wz[3];
         const int cx = axis_weights(p.px, wx), cy = axis_weights(p.py, wy), cz = axis_weights(p.pz, wz);
         int base;
-        const bool inside = tl.stencil_base(cx, cy, cz, base);
+        const bool in_block = tl.stencil_base(cx, cy, cz, base);
+        auto scatter = [&](auto in_tile) {
+        constexpr bool inside = decltype(in_tile)::value;
 #pragma unroll
         for (int gx = 0; gx < 3; ++gx)
 #pragma unroll
@@ -90,8 +61,8 @@ __global__ void __launch_bounds__(TILED_THREADS) k_p2g1_tiled(DevParams P, TileG
                     p2g1_node<3>(p, weight, node_dist(nx, p.px), node_dist(ny, p.py), node_dist(nz, p.pz), mc, ox, oy, oz);
                     const int em = encode_fixed(mc, P.fmult), ex = encode_fixed(ox, P.fmult), ey = encode_fixed(oy, P.fmult),
                               ez = encode_fixed(oz, P.fmult);
-                    if (inside) {
-                        const int idx = base + (gx * TL::T + gy) * TL::T + gz;
+                    if constexpr (inside) {
+                        const int idx = base + gx * TL::PX + gy * TL::PY + gz;
                         atomicAdd(&tile[3][idx], em); atomicAdd(&tile[0][idx], ex);
                         atomicAdd(&tile[1][idx], ey); atomicAdd(&tile[2][idx], ez);
                     } else {
@@ -99,13 +70,15 @@ __global__ void __launch_bounds__(TILED_THREADS) k_p2g1_tiled(DevParams P, TileG
                         atomicAdd(c + 3, em); atomicAdd(c + 0, ex); atomicAdd(c + 1, ey); atomicAdd(c + 2, ez);
                     }
                 }
+        };
+        if (in_block) scatter(std::true_type{}); else scatter(std::false_type{});
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < TL::N; idx += TILED_THREADS) {
+    for (int k = threadIdx.x; k < TL::NODES; k += TILED_THREADS) {
+        int idx; int64_t ci;
+        const bool ok = tl.node(P, k, idx, ci);
         const int vx = tile[0][idx], vy = tile[1][idx], vz = tile[2][idx], m = tile[3][idx];
-        if ((vx | vy | vz | m) == 0) continue;
-        int64_t ci;
-        if (!tl.node_global(P, idx, ci)) continue;
+        if (!ok || (vx | vy | vz | m) == 0) continue;
         int* c = grid + 4 * ci;
         if (vx) atomicAdd(c + 0, vx);
         if (vy) atomicAdd(c + 1, vy);
@@ -120,16 +93,17 @@ __global__ void __launch_bounds__(TILED_THREADS) k_p2g2_tiled(DevParams P, TileG
                                                               const uint32_t* __restrict__ block_start, int* __restrict__ grid)
 {
     using TL = Tile<B>;
-    __shared__ int tile[3][TL::N];
-    __shared__ float tmass[TL::N];
+    __shared__ int tile[3][TL::WORDS];
+    __shared__ float tmass[TL::WORDS];
     const int b = blockIdx.x;
     const uint32_t s0 = block_start[b], s1 = block_start[b + 1];
     if (s0 == s1) return;
     TL tl; tl.init(g, b);
-    for (int idx = threadIdx.x; idx < TL::N; idx += TILED_THREADS) {
-        tile[0][idx] = 0; tile[1][idx] = 0; tile[2][idx] = 0;
-        int64_t ci;
-        tmass[idx] = tl.node_global(P, idx, ci) ? decode_fixed(grid[4 * ci + 3], P.fmult) : 0.0f;
+    for (int k = threadIdx.x; k < 3 * TL::WORDS; k += TILED_THREADS) (&tile[0][0])[k] = 0;
+    for (int k = threadIdx.x; k < TL::NODES; k += TILED_THREADS) {
+        int idx; int64_t ci;
+        const bool ok = tl.node(P, k, idx, ci);
+        tmass[idx] = ok ? decode_fixed(grid[4 * ci + 3], P.fmult) : 0.0f;
     }
     __syncthreads();
     for (uint32_t i = s0 + threadIdx.x; i < s1; i += TILED_THREADS) {
@@ -140,8 +114,10 @@ __global__ void __launch_bounds__(TILED_THREADS) k_p2g2_tiled(DevParams P, TileG
         float wx[3], wy[3], wz[3];
         const int cx = axis_weights(px, wx), cy = axis_weights(py, wy), cz = axis_weights(pz, wz);
         int base;
-        const bool inside = tl.stencil_base(cx, cy, cz, base);
+        const bool in_block = tl.stencil_base(cx, cy, cz, base);
         float density = 0.0f;
+        auto gather = [&](auto in_tile) {
+        constexpr bool inside = decltype(in_tile)::value;
 #pragma unroll
         for (int gx = 0; gx < 3; ++gx)
 #pragma unroll
@@ -150,12 +126,16 @@ __global__ void __launch_bounds__(TILED_THREADS) k_p2g2_tiled(DevParams P, TileG
                 for (int gz = 0; gz < 3; ++gz) {
                     const float weight = smul(smul(wx[gx], wy[gy]), wz[gz]);
                     float gm;
-                    if (inside) gm = tmass[base + (gx * TL::T + gy) * TL::T + gz];
+                    if constexpr (inside) gm = tmass[base + gx * TL::PX + gy * TL::PY + gz];
                     else gm = decode_fixed(grid[4 * cell_index(P, cx + gx - 1, cy + gy - 1, cz + gz - 1) + 3], P.fmult);
                     density = sadd(density, smul(gm, weight));
                 }
+        };
+        if (in_block) gather(std::true_type{}); else gather(std::false_type{});
         float e[9];
         p2g2_stress<3>(P, c, m, density, e);
+        auto scatter = [&](auto in_tile) {
+        constexpr bool inside = decltype(in_tile)::value;
 #pragma unroll
         for (int gx = 0; gx < 3; ++gx)
 #pragma unroll
@@ -167,21 +147,23 @@ __global__ void __launch_bounds__(TILED_THREADS) k_p2g2_tiled(DevParams P, TileG
                     float ox, oy, oz;
                     p2g2_node<3>(e, weight, node_dist(nx, px), node_dist(ny, py), node_dist(nz, pz), ox, oy, oz);
                     const int ex = encode_fixed(ox, P.fmult), ey = encode_fixed(oy, P.fmult), ez = encode_fixed(oz, P.fmult);
-                    if (inside) {
-                        const int idx = base + (gx * TL::T + gy) * TL::T + gz;
+                    if constexpr (inside) {
+                        const int idx = base + gx * TL::PX + gy * TL::PY + gz;
                         atomicAdd(&tile[0][idx], ex); atomicAdd(&tile[1][idx], ey); atomicAdd(&tile[2][idx], ez);
                     } else {
                         int* cc = grid + 4 * cell_index(P, nx, ny, nz);
                         atomicAdd(cc + 0, ex); atomicAdd(cc + 1, ey); atomicAdd(cc + 2, ez);
                     }
                 }
+        };
+        if (in_block) scatter(std::true_type{}); else scatter(std::false_type{});
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < TL::N; idx += TILED_THREADS) {
+    for (int k = threadIdx.x; k < TL::NODES; k += TILED_THREADS) {
+        int idx; int64_t ci;
+        const bool ok = tl.node(P, k, idx, ci);
         const int vx = tile[0][idx], vy = tile[1][idx], vz = tile[2][idx];
-        if ((vx | vy | vz) == 0) continue;
-        int64_t ci;
-        if (!tl.node_global(P, idx, ci)) continue;
+        if (!ok || (vx | vy | vz) == 0) continue;
         int* c = grid + 4 * ci;
         if (vx) atomicAdd(c + 0, vx);
         if (vy) atomicAdd(c + 1, vy);
@@ -196,15 +178,15 @@ __global__ void __launch_bounds__(TILED_THREADS) k_g2p_tiled(DevParams P, TileGe
                                                              const uint32_t* __restrict__ orig_id, float4* __restrict__ positions)
 {
     using TL = Tile<B>;
-    __shared__ float tv[3][TL::N];
+    __shared__ float tv[3][TL::WORDS];
     const int b = blockIdx.x;
     const uint32_t s0 = block_start[b], s1 = block_start[b + 1];
     if (s0 == s1) return;
     TL tl; tl.init(g, b);
-    for (int idx = threadIdx.x; idx < TL::N; idx += TILED_THREADS) {
-        int64_t ci;
+    for (int k = threadIdx.x; k < TL::NODES; k += TILED_THREADS) {
+        int idx; int64_t ci;
         float vx = 0.0f, vy = 0.0f, vz = 0.0f;
-        if (tl.node_global(P, idx, ci)) {
+        if (tl.node(P, k, idx, ci)) {
             const int4 c = grid[ci];
             vx = decode_fixed(c.x, P.fmult); vy = decode_fixed(c.y, P.fmult); vz = decode_fixed(c.z, P.fmult);
         }
@@ -216,8 +198,10 @@ __global__ void __launch_bounds__(TILED_THREADS) k_g2p_tiled(DevParams P, TileGe
         float wx[3], wy[3], wz[3];
         const int cx = axis_weights(old[0], wx), cy = axis_weights(old[1], wy), cz = axis_weights(old[2], wz);
         int base;
-        const bool inside = tl.stencil_base(cx, cy, cz, base);
+        const bool in_block = tl.stencil_base(cx, cy, cz, base);
         float Bm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, v[3] = {0, 0, 0};
+        auto gather = [&](auto in_tile) {
+        constexpr bool inside = decltype(in_tile)::value;
 #pragma unroll
         for (int gx = 0; gx < 3; ++gx)
 #pragma unroll
@@ -227,8 +211,8 @@ __global__ void __launch_bounds__(TILED_THREADS) k_g2p_tiled(DevParams P, TileGe
                     const float weight = smul(smul(wx[gx], wy[gy]), wz[gz]);
                     const int nx = cx + gx - 1, ny = cy + gy - 1, nz = cz + gz - 1;
                     float gvx, gvy, gvz;
-                    if (inside) {
-                        const int idx = base + (gx * TL::T + gy) * TL::T + gz;
+                    if constexpr (inside) {
+                        const int idx = base + gx * TL::PX + gy * TL::PY + gz;
                         gvx = tv[0][idx]; gvy = tv[1][idx]; gvz = tv[2][idx];
                     } else {
                         const int4 c = grid[cell_index(P, nx, ny, nz)];
@@ -236,6 +220,8 @@ __global__ void __launch_bounds__(TILED_THREADS) k_g2p_tiled(DevParams P, TileGe
                     }
                     g2p_node<3>(gvx, gvy, gvz, weight, node_dist(nx, old[0]), node_dist(ny, old[1]), node_dist(nz, old[2]), Bm, v);
                 }
+        };
+        if (in_block) gather(std::true_type{}); else gather(std::false_type{});
         float np[3], c[9];
         g2p_finish<3>(P, old, Bm, v, np, c);
         pv.plane(PX)[i] = np[0]; pv.plane(PY)[i] = np[1]; pv.plane(PZ)[i] = np[2];
@@ -267,11 +253,17 @@ static int check_supported(MpmSolver* s)
         s->launches += 1;                                                                                 \
     } while (0)
 
+// fast-math variants (mpm_kernels_fast.cu)
+void fast_p2g1(MpmSolver* s);
+void fast_p2g2(MpmSolver* s);
+void fast_g2p(MpmSolver* s);
+
 int tiled_p2g1(MpmSolver* s)
 {
     int rc = check_supported(s);
     if (rc) return rc;
     if (s->n == 0) return MPM_OK;
+    if (s->hp.math_mode == MPM_MATH_FAST) { fast_p2g1(s); return MPM_OK; }
     LAUNCH_TILED(k_p2g1_tiled, s->view(), sort_block_start(s), reinterpret_cast<int*>(s->grid));
     return MPM_OK;
 }
@@ -280,6 +272,7 @@ int tiled_p2g2(MpmSolver* s)
     int rc = check_supported(s);
     if (rc) return rc;
     if (s->n == 0) return MPM_OK;
+    if (s->hp.math_mode == MPM_MATH_FAST) { fast_p2g2(s); return MPM_OK; }
     LAUNCH_TILED(k_p2g2_tiled, s->view(), sort_block_start(s), reinterpret_cast<int*>(s->grid));
     return MPM_OK;
 }
@@ -288,6 +281,7 @@ int tiled_g2p(MpmSolver* s)
     int rc = check_supported(s);
     if (rc) return rc;
     if (s->n == 0) return MPM_OK;
+    if (s->hp.math_mode == MPM_MATH_FAST) { fast_g2p(s); return MPM_OK; }
     LAUNCH_TILED(k_g2p_tiled, s->view(), sort_block_start(s), reinterpret_cast<const int4*>(s->grid), s->orig_id, s->positions);
     return MPM_OK;
 }

@@ -39,6 +39,7 @@ struct MpmSolver {
     int64_t steps = 0, launches = 0;
     int64_t steps_since_sort = 0;
     bool sorted_valid = false;
+    bool fresh_particles = true;  // particle set changed since the last bin phase (-> lane interleave once)
     mpm::SortState* sort = nullptr;
     mpm::CommState* comm = nullptr;
 

@@ -8,11 +8,14 @@
 // pass.)  The sort is stable (ties keep their previous relative order), so the permutation equals
 // std::stable_sort on the same keys bit for bit (tests/test_parity_gpu.py).
 //
-// Lane interleave: measured on B200 (profiles/microbench/smem_atomics.cu) a conflict-free ATOMS.ADD costs
-// 0.78 ns/warp-instr/SM but 4.17 ns when 8 lanes hit one word -- which is what neighbouring lanes do when
-// neighbouring slots hold particles of one cell.  So inside each block's range the reorder writes sorted rank
-// r to slot (r * A^-1) mod cnt, i.e. slot q holds rank (q * A) mod cnt with A >= 17 coprime to cnt:
-// neighbouring lanes then work on particles 17+ ranks apart.  Results do not depend on it (int adds commute).
+// Bank-aware slot layout: measured on B200 (profiles/microbench/smem_atomics.cu, profiles/r1) a conflict-free
+// ATOMS.ADD costs 0.78 ns/warp-instr/SM, 4.17 ns when 8 lanes hit one word, and the tiled P2G kernels were bound
+// by shared-memory wavefronts (4 per ATOMS) rather than by HBM or issue slots.  So after the stable sort a
+// per-block pass (k_block_layout) orders each block's particles by (rank inside the cell, cell): 32 consecutive
+// slots then hold particles of 32 consecutive cells, which the padded tile of mpm_kernels_fast.cu maps to 32
+// distinct banks.  The low key bits carry the cell-in-block id for that pass; the radix passes skip them.
+// The rank inside a cell comes from a shared-memory atomic counter, so the slot order inside a block is not
+// reproducible run to run -- nothing observable depends on it (int adds commute; downloads go through orig_id).
 //
 // Per pass (<= 8 key bits): k_tile_hist (per-tile digit counts) -> k_scan_rows (one CTA per digit scans
 // its counts across tiles) -> k_scan_bins -> k_scatter (stable in-tile ranking with __match_any_sync,
@@ -55,8 +58,9 @@ __device__ __forceinline__ uint32_t cell_key(const KeyGeom& g, int cx, int cy, i
     const int m = (1 << g.logB) - 1;
     const int lx = cx - g.gx0;  // local slab coordinate (slab origin is block-aligned)
     const int bx = lx >> g.logB, by = cy >> g.logB, bz = cz >> g.logB;
-    (void)m;
-    return (uint32_t)((bx * g.nby + by) * g.nbz + bz);
+    const uint32_t blk = (uint32_t)((bx * g.nby + by) * g.nbz + bz);
+    if (g.dim == 3) return (blk << (3 * g.logB)) | (uint32_t)(((((lx & m) << g.logB) | (cy & m)) << g.logB) | (cz & m));
+    return (blk << (2 * g.logB)) | (uint32_t)(((lx & m) << g.logB) | (cy & m));
 }
 
 __global__ void __launch_bounds__(256) k_make_keys(KeyGeom g, ParticleView pv, int64_t n, uint32_t* keys, uint32_t* vals,
@@ -69,7 +73,7 @@ __global__ void __launch_bounds__(256) k_make_keys(KeyGeom g, ParticleView pv, i
     const uint32_t k = cell_key(g, cx, cy, cz);
     keys[i] = k;
     vals[i] = (uint32_t)i;
-    keys_before[i] = k;
+    keys_before[i] = k >> (g.dim * g.logB);  // the sort key proper: the block id
 }
 
 __global__ void __launch_bounds__(SORT_THREADS) k_tile_hist(const uint32_t* __restrict__ keys, int64_t n, int shift, int bins,
@@ -211,29 +215,66 @@ __global__ void __launch_bounds__(SORT_THREADS) k_scatter(const uint32_t* __rest
     }
 }
 
-__device__ __forceinline__ uint32_t gcd_u32(uint32_t a, uint32_t b)
+// Per-block slot layout (see the header): slot order inside a block = (rank inside the cell, cell id).
+// gather_src[slot] = pre-sort slot of the particle that moves there.
+template <int CELL_BITS>
+__global__ void __launch_bounds__(512) k_block_layout(const uint32_t* __restrict__ keys_sorted, const uint32_t* __restrict__ vals_sorted,
+                                                      const uint32_t* __restrict__ block_start, uint32_t* __restrict__ rank_tmp,
+                                                      uint32_t* __restrict__ gather_src)
 {
-    while (b) { const uint32_t t = a % b; a = b; b = t; }
-    return a;
+    constexpr int NC = 1 << CELL_BITS;  // cells per block
+    constexpr int RMAX = 16;            // rank levels laid out cell-interleaved; deeper ranks go to a cell-major tail
+    __shared__ uint32_t count[NC];
+    __shared__ uint16_t tab[RMAX][NC];
+    __shared__ uint32_t tail_off[NC];
+    __shared__ uint32_t lvl_base[RMAX + 1];
+    __shared__ uint32_t wsum[16];
+    const uint32_t b = blockIdx.x;
+    const uint32_t s0 = block_start[b], s1 = block_start[b + 1];
+    if (s0 == s1) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int L = tid; L < NC; L += 512) count[L] = 0;
+    __syncthreads();
+    for (uint32_t q = s0 + tid; q < s1; q += 512) rank_tmp[q] = atomicAdd(&count[keys_sorted[q] & (NC - 1)], 1u);
+    __syncthreads();
+    const uint32_t c = (tid < NC) ? count[tid] : 0u;
+    uint32_t running = 0;
+    for (int r = 0; r <= RMAX; ++r) {
+        // r < RMAX: one slot per cell that has more than r particles; r == RMAX: all the remaining ones, cell-major
+        const uint32_t v = (r < RMAX) ? (c > (uint32_t)r ? 1u : 0u) : (c > (uint32_t)RMAX ? c - RMAX : 0u);
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        uint32_t woff = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { const uint32_t t = wsum[k]; if (k < warp) woff += t; total += t; }
+        if (tid < NC) {
+            if (r < RMAX) tab[r][tid] = (uint16_t)(woff + x - v);
+            else tail_off[tid] = woff + x - v;
+        }
+        if (tid == 0) lvl_base[r] = running;
+        running += total;
+        __syncthreads();
+    }
+    for (uint32_t q = s0 + tid; q < s1; q += 512) {
+        const uint32_t L = keys_sorted[q] & (NC - 1), r = rank_tmp[q];
+        const uint32_t dst = (r < RMAX) ? lvl_base[r] + tab[r][L] : lvl_base[RMAX] + tail_off[L] + (r - RMAX);
+        gather_src[s0 + dst] = vals_sorted[q];
+    }
 }
 
-// gather the particle planes through the permutation: slot i of a block's range takes sorted rank
-// s0 + ((i - s0) * A) mod cnt (lane interleave, see the header), and sorted rank r takes pre-sort slot perm[r]
-__global__ void __launch_bounds__(256) k_reorder(ParticleView src, ParticleView dst, const uint32_t* __restrict__ perm,
-                                                 const uint32_t* __restrict__ keys_sorted, const uint32_t* __restrict__ block_start,
+// gather the particle planes: slot i takes the particle from pre-sort slot gather_src[i]
+__global__ void __launch_bounds__(256) k_reorder(ParticleView src, ParticleView dst, const uint32_t* __restrict__ gather_src,
                                                  const uint32_t* __restrict__ id_src, uint32_t* __restrict__ id_dst, int64_t n)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t b = keys_sorted[i];
-    const uint32_t s0 = block_start[b], cnt = block_start[b + 1] - s0;
-    uint32_t A = 1;
-    if (cnt > 34) {
-        A = 17;
-        while (gcd_u32(A, cnt) != 1) ++A;
-    }
-    const uint32_t r = s0 + (uint32_t)(((uint64_t)((uint32_t)i - s0) * A) % cnt);
-    const uint32_t j = perm[r];
+    const uint32_t j = gather_src[i];
     float v[NPLANES];
 #pragma unroll
     for (int k = 0; k < NPLANES; ++k) v[k] = src.plane(k)[j];
@@ -253,9 +294,8 @@ __global__ void __launch_bounds__(256) k_block_bounds(const uint32_t* __restrict
         return;
     }
     if (i >= n) return;
-    (void)cell_bits;
-    const int64_t b = keys[i];
-    const int64_t bp = (i > 0) ? (int64_t)keys[i - 1] : -1;
+    const int64_t b = keys[i] >> cell_bits;
+    const int64_t bp = (i > 0) ? (int64_t)(keys[i - 1] >> cell_bits) : -1;
     for (int64_t bb = bp + 1; bb <= b; ++bb) block_start[bb] = (uint32_t)i;
     if (i == n - 1)
         for (int64_t bb = b + 1; bb <= nblocks; ++bb) block_start[bb] = (uint32_t)n;
@@ -296,8 +336,8 @@ int sort_create(MpmSolver* s)
     st->nby = (s->dp.Ry + st->B - 1) / st->B;
     st->nbz = (s->dp.dim == 3) ? (s->dp.Rz + st->B - 1) / st->B : 1;
     st->nblocks = (int64_t)st->nbx * st->nby * st->nbz;
-    st->key_bits = std::max(1, ilog2_ceil(st->nblocks));
-    if (st->key_bits > 31) { s->err = "grid too large for 32-bit cell keys"; return MPM_ERR_INVALID; }
+    st->key_bits = std::max(1, ilog2_ceil(st->nblocks));  // sorted bits: the block id (above the cell-in-block bits)
+    if (st->key_bits + s->dp.dim * st->logB > 32) { s->err = "grid too large for 32-bit cell keys"; return MPM_ERR_INVALID; }
     st->passes = (st->key_bits + 7) / 8;
     st->bits_per_pass = (st->key_bits + st->passes - 1) / st->passes;
     st->max_tiles = (s->pitch + SORT_TILE - 1) / SORT_TILE;
@@ -345,8 +385,8 @@ int sort_particles(MpmSolver* s)
     const int64_t ntiles = (n + SORT_TILE - 1) / SORT_TILE;
     int cur = 0;
     for (int p = 0; p < st->passes; ++p) {
-        const int shift = p * st->bits_per_pass;
-        const int bits = std::min(st->bits_per_pass, st->key_bits - shift);
+        const int shift = cell_bits + p * st->bits_per_pass;
+        const int bits = std::min(st->bits_per_pass, st->key_bits - p * st->bits_per_pass);
         if (bits <= 0) break;
         const int bins = 1 << bits;
         k_tile_hist<<<(unsigned)ntiles, SORT_THREADS, 0, s->stream>>>(st->keys[cur], n, shift, bins, ntiles, st->tile_hist);
@@ -359,9 +399,18 @@ int sort_particles(MpmSolver* s)
     }
     st->final_buf = cur;
     k_block_bounds<<<nb, 256, 0, s->stream>>>(st->keys[cur], n, cell_bits, st->nblocks, st->block_start);
-    k_reorder<<<nb, 256, 0, s->stream>>>(s->view(), s->view_alt(), st->vals[cur], st->keys[cur], st->block_start, s->orig_id,
-                                         s->orig_id_alt, n);
-    s->launches += 2;
+    // the spare ping-pong buffers hold the in-cell ranks and the gather list
+    uint32_t* rank_tmp = st->keys[cur ^ 1];
+    uint32_t* gather_src = st->vals[cur ^ 1];
+    if (s->dp.dim == 3 && st->logB == 3)
+        k_block_layout<9><<<(unsigned)st->nblocks, 512, 0, s->stream>>>(st->keys[cur], st->vals[cur], st->block_start, rank_tmp, gather_src);
+    else if (s->dp.dim == 3)
+        k_block_layout<6><<<(unsigned)st->nblocks, 512, 0, s->stream>>>(st->keys[cur], st->vals[cur], st->block_start, rank_tmp, gather_src);
+    else
+        k_block_layout<6><<<(unsigned)st->nblocks, 512, 0, s->stream>>>(st->keys[cur], st->vals[cur], st->block_start, rank_tmp, gather_src);
+    k_reorder<<<nb, 256, 0, s->stream>>>(s->view(), s->view_alt(), gather_src, s->orig_id, s->orig_id_alt, n);
+    s->fresh_particles = false;
+    s->launches += 3;
     std::swap(s->part, s->part_alt);
     std::swap(s->orig_id, s->orig_id_alt);
     s->sorted_valid = true;
