@@ -90,7 +90,8 @@ class ClockSampler:
 
 
 def scene_params(name):
-    from oracle import orc  # only to share the variant table with the reference arm; NOT used on the GPU path
+    """CPU arms only (oracle parameter block of the same scene)."""
+    from oracle import orc
     grid, lo, hi, sp = WORKLOADS[name]
     op = orc.variant("3d_gpu", grid)
     op.interaction = 0  # sphere disabled (SURVEY 8d C2/C4)
@@ -171,11 +172,9 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    import numpy as np
     import torch
     import torch.distributed as dist
     import mpm_b200
-    import helpers
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -190,10 +189,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    op, lo, hi, sp = scene_params(args.workload)
-    params = helpers.mpm_params_from_orc(op, kernel_path=args.path, sort_interval=args.sort_interval,
-                                         math_mode=1 if args.math == "fast" else 0)
-    grid = WORKLOADS[args.workload][0]
+    grid, lo, hi, sp = WORKLOADS[args.workload]
+    # the reference's shipping GPU scene constants (MLSMPM3DFluidMultithreadGPU.cs:54-84), sphere disabled
+    params = mpm_b200.default_params("3d_gpu", grid=grid, interaction=0, kernel_path=args.path,
+                                     sort_interval=args.sort_interval, math_mode=1 if args.math == "fast" else 0)
     n_total = int(round((hi[0] - lo[0]) / sp)) ** 3
     G = grid[0] * grid[1] * grid[2]
     solver = mpm_b200.Solver(params, n_total, device=local_rank)
@@ -201,12 +200,9 @@ def main():
         uid = [mpm_b200.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         solver.comm_init(uid[0], rank, world)
-        # every rank generates the same lattice; the library keeps the particles of its own x-slab
-        from_lattice = __import__("oracle.orc", fromlist=["orc"]).init_block(3, lo, hi, sp)  # host-side scene generation only
-        solver.upload(from_lattice)
-        del from_lattice
-    else:
-        assert solver.initialise_sim(lo, hi, sp) == n_total
+    # every rank generates the same lattice on its device; with a communicator the library cuts equal-count
+    # x-slabs from the particle histogram and keeps the particles of its own slab
+    assert solver.initialise_sim(lo, hi, sp) == n_total
     n_local = solver.stats().local_particles
 
     # ---- warm-up, then the timed region: K steps, device-timed on the solver's stream

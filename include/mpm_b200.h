@@ -223,12 +223,40 @@ MPM_API int32_t mpm_get_stream(MpmSolver* s, void** stream);
 MPM_API int32_t mpm_host_alloc(int64_t bytes, void** out);
 MPM_API int32_t mpm_host_free(void* p);
 
-/* ---- multi-GPU: one process per GPU, x-slab decomposition, NCCL halo exchange + migration ---- */
+/* ---- multi-GPU (no reference counterpart: the reference is single-device) -----------------------------------
+ * x-slab decomposition (contiguous in the reference's cell order x*Ry*Rz + y*Rz + z, F:282).  A rank owns the
+ * planes [x0, x1) and the particles whose base cell x lies there, stores [x0-1, x1+1).  Per step: exchange-add of
+ * the two overlap planes with each neighbour after P2G_1 and after P2G_2, redundant grid update on the ghost
+ * planes, particle migration after G2P.  int32 adds commute, so in MPM_GRID_FIXED the k-rank result is
+ * bit-identical to the 1-rank result.  Only MPM_GRID_FIXED, dim = 3 is supported with a communicator.
+ *
+ * Two transports:
+ *   NCCL  - one process per GPU (torchrun / mpirun): rank 0 calls mpm_comm_unique_id, the host broadcasts the
+ *           128 bytes by any means, every rank calls mpm_comm_init.  libnccl.so.2 is resolved with dlopen at that
+ *           moment (the copy already loaded in the process, e.g. torch's, else the system one).
+ *   LOCAL - k solvers inside one process (one host thread per solver, any mix of devices, peer copies +
+ *           events): mpm_local_hub_create, then mpm_comm_init_local on each.  Every rank must be inside
+ *           mpm_step / an upload concurrently, as with NCCL.
+ * After either init, mpm_init_block / mpm_upload_particles* take the GLOBAL particle set on every rank (the
+ * same data everywhere); slab cuts are chosen from its x-plane histogram (equal counts) and each rank keeps
+ * its own slab.  Downloads then return the rank's LOCAL particles in slot order; mpm_download_ids gives their
+ * global indices. */
 #define MPM_COMM_ID_BYTES 128
-/* rank 0 creates the id, the host broadcasts it by any means (torch.distributed, a file, a socket). */
 MPM_API int32_t mpm_comm_unique_id(uint8_t id[MPM_COMM_ID_BYTES]);
-/* Collective over all ranks.  Particles uploaded afterwards are kept by the rank whose slab holds them. */
 MPM_API int32_t mpm_comm_init(MpmSolver* s, const uint8_t id[MPM_COMM_ID_BYTES], int32_t rank, int32_t world);
+
+typedef struct MpmLocalHub MpmLocalHub; /* opaque rendezvous object shared by the k solvers of one process */
+MPM_API int32_t mpm_local_hub_create(int32_t world, MpmLocalHub** hub);
+MPM_API int32_t mpm_local_hub_destroy(MpmLocalHub* hub); /* after every attached solver is destroyed */
+MPM_API int32_t mpm_comm_init_local(MpmSolver* s, MpmLocalHub* hub, int32_t rank, int32_t world);
+
+/* Slab of this rank: owned planes [x0, x1), stored planes [gx0, gx0 + nxl) (what mpm_download_grid returns). */
+MPM_API int32_t mpm_comm_slab(const MpmSolver* s, int32_t* x0, int32_t* x1, int32_t* gx0, int32_t* nxl);
+/* Global (original) index of each local particle, in the slot order of mpm_download_particles_soa. */
+MPM_API int32_t mpm_download_ids(MpmSolver* s, uint32_t* ids, int64_t cap);
+/* Host-only helper (usable without a GPU): equal-count slab cuts from an x-plane particle histogram.
+ * cuts[0] = 0 <= cuts[1] <= ... <= cuts[world] = rx, every slab at least min_width planes wide. */
+MPM_API int32_t mpm_slab_cuts(const int64_t* hist, int32_t rx, int32_t world, int32_t min_width, int32_t* cuts);
 
 #ifdef __cplusplus
 }

@@ -244,12 +244,21 @@ extern "C" int32_t mpm_set_sphere(MpmSolver* s, const float pos[3])
 
 // ---------------------------------------------------------------- particle set
 
+// multi-GPU (mpm_comm.cu): the GLOBAL set is written to the planes by init/add/upload; the slab partition
+// (histogram -> cuts -> keep own particles) runs lazily before the next step / download.
+namespace mpm {
+int comm_partition(MpmSolver* s);          // no-op unless a partition is pending
+bool comm_partitioned(const MpmSolver* s);  // the planes hold this rank's local particles
+void comm_mark_global(MpmSolver* s);       // the planes now hold the global set again
+}
+
 static void particles_changed(MpmSolver* s)
 {
     s->positions_valid = false;
     s->sorted_valid = false;
     s->steps_since_sort = 0;
     s->fresh_particles = true;
+    if (s->comm) comm_mark_global(s);
 }
 
 static int lattice_axis(float lo, float hi, float spacing, std::vector<float>& out)
@@ -274,7 +283,8 @@ static int add_block(MpmSolver* s, const float lo[3], const float hi[3], float s
     const int64_t cnt = (int64_t)ax[0].size() * ax[1].size() * ax[2].size();
     const int64_t base = replace ? 0 : s->n;
     if (base + cnt > s->cap) return fail(s, MPM_ERR_INVALID, "lattice exceeds max_particles");
-    if (s->comm) return fail(s, MPM_ERR_STATE, "use mpm_upload_particles* for multi-GPU scenes");
+    if (s->comm && !replace && comm_partitioned(s))
+        return fail(s, MPM_ERR_STATE, "multi-GPU: mpm_add_block after the slab partition (a step or download) is not supported");
     float* d_ax = nullptr;
     const size_t tot = ax[0].size() + ax[1].size() + ax[2].size();
     CK(cudaMalloc(&d_ax, sizeof(float) * tot));
@@ -303,8 +313,6 @@ extern "C" int32_t mpm_add_block(MpmSolver* s, const float lo[3], const float hi
     return add_block(s, lo, hi, spacing, false);
 }
 
-// multi-GPU: keep only the particles of this rank's slab (mpm_comm.cu)
-namespace mpm { int comm_filter_upload(MpmSolver* s, int64_t n_global); }
 
 extern "C" int32_t mpm_upload_particles(MpmSolver* s, const MpmParticle80* ps, int64_t n)
 {
@@ -324,7 +332,6 @@ extern "C" int32_t mpm_upload_particles(MpmSolver* s, const MpmParticle80* ps, i
     }
     s->n = n;
     particles_changed(s);
-    if (s->comm) return comm_filter_upload(s, n);
     return MPM_OK;
 }
 
@@ -351,20 +358,20 @@ extern "C" int32_t mpm_upload_particles_soa(MpmSolver* s, const float* pos, cons
     }
     s->n = n;
     particles_changed(s);
-    if (s->comm) return comm_filter_upload(s, n);
     return MPM_OK;
 }
 
 extern "C" int32_t mpm_download_particles(MpmSolver* s, MpmParticle80* ps, int64_t cap)
 {
     if (!s || !ps) return MPM_ERR_INVALID;
-    if (cap < s->n) return fail(s, MPM_ERR_INVALID, "destination too small");
-    if (s->comm) return fail(s, MPM_ERR_STATE, "multi-GPU: use mpm_download_particles_soa (local particles + ids)");
     CK(cudaSetDevice(s->device));
+    { int rc = comm_partition(s); if (rc) return rc; }
+    if (cap < s->n) return fail(s, MPM_ERR_INVALID, "destination too small");
     if (s->n == 0) return MPM_OK;
     float* stage = nullptr;
     CK(cudaMalloc(&stage, sizeof(MpmParticle80) * s->n));
-    launch_soa_to_aos80(s->view(), s->orig_id, stage, s->n, s->stream);
+    // multi-GPU ranks return their local particles in slot order (global indices: mpm_download_ids)
+    launch_soa_to_aos80(s->view(), s->comm ? nullptr : s->orig_id, stage, s->n, s->stream);
     s->launches += 1;
     cudaMemcpyAsync(ps, stage, sizeof(MpmParticle80) * s->n, cudaMemcpyDeviceToHost, s->stream);
     cudaError_t e = cudaStreamSynchronize(s->stream);
@@ -376,14 +383,15 @@ extern "C" int32_t mpm_download_particles(MpmSolver* s, MpmParticle80* ps, int64
 extern "C" int32_t mpm_download_particles_soa(MpmSolver* s, float* pos, float* vel, float* C, float* mass, int64_t cap)
 {
     if (!s) return MPM_ERR_INVALID;
-    if (cap < s->n) return fail(s, MPM_ERR_INVALID, "destination too small");
     CK(cudaSetDevice(s->device));
+    { int rc = comm_partition(s); if (rc) return rc; }
+    if (cap < s->n) return fail(s, MPM_ERR_INVALID, "destination too small");
     const int64_t n = s->n;
     if (n == 0) return MPM_OK;
     float* stage = nullptr;
     CK(cudaMalloc(&stage, sizeof(float) * 16 * n));
     float* dpos = stage; float* dvel = stage + 3 * n; float* dC = stage + 6 * n; float* dm = stage + 15 * n;
-    // multi-GPU ranks return their local particles in slot order (ids via mpm_debug_last_sort / comm API)
+    // multi-GPU ranks return their local particles in slot order (global indices: mpm_download_ids)
     launch_soa_to_packed(s->view(), s->comm ? nullptr : s->orig_id, dpos, dvel, dC, dm, n, s->stream);
     s->launches += 1;
     if (pos) cudaMemcpyAsync(pos, dpos, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, s->stream);
@@ -399,8 +407,9 @@ extern "C" int32_t mpm_download_particles_soa(MpmSolver* s, float* pos, float* v
 extern "C" int32_t mpm_download_grid(MpmSolver* s, MpmCell16* cells, int64_t cap)
 {
     if (!s || !cells) return MPM_ERR_INVALID;
-    if (cap < s->ncells) return fail(s, MPM_ERR_INVALID, "destination too small");
     CK(cudaSetDevice(s->device));
+    { int rc = comm_partition(s); if (rc) return rc; }
+    if (cap < s->ncells) return fail(s, MPM_ERR_INVALID, "destination too small");
     CK(cudaMemcpyAsync(cells, s->grid, 16 * s->ncells, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     return MPM_OK;
@@ -472,6 +481,7 @@ extern "C" int32_t mpm_step(MpmSolver* s, int32_t iterations)
 {
     if (!s || iterations < 0) return MPM_ERR_INVALID;
     CK(cudaSetDevice(s->device));
+    { int rc = comm_partition(s); if (rc) return rc; }
     if (s->timing) { for (double& v : s->ms_acc) v = 0; s->ms_step_acc = 0; s->timed_steps = 0; }
     size_t cursor = 0;
     std::vector<int> phases;
@@ -518,6 +528,7 @@ extern "C" int32_t mpm_run_phase(MpmSolver* s, int32_t phase)
     if (!s) return MPM_ERR_INVALID;
     CK(cudaSetDevice(s->device));
     if (phase < 0 || phase > PH_SORT) return fail(s, MPM_ERR_INVALID, "phase must be 0..5");
+    if (s->comm) return fail(s, MPM_ERR_STATE, "multi-GPU: phases cannot run one by one (halo exchanges sit between them); use mpm_step");
     if (s->path == MPM_PATH_TILED && phase != PH_SORT && phase != PH_CLEAR && phase != PH_UPDATE && !s->sorted_valid) {
         size_t c0 = 0; bool tm = s->timing; s->timing = false;
         int rc = run_phase(s, PH_SORT, c0);
@@ -552,7 +563,9 @@ extern "C" int32_t mpm_get_positions(MpmSolver* s, float* dst4, int64_t cap, voi
 {
     if (!s) return MPM_ERR_INVALID;
     CK(cudaSetDevice(s->device));
-    if (!s->positions_valid && s->n > 0) {
+    { int rc = comm_partition(s); if (rc) return rc; }
+    // multi-GPU: the rank's local particles in slot order (G2P filled the array by global index instead)
+    if ((!s->positions_valid || s->comm) && s->n > 0) {
         launch_positions(s->view(), s->comm ? nullptr : s->orig_id, s->positions, s->n, s->stream);
         s->launches += 1;
         s->positions_valid = true;
@@ -586,6 +599,7 @@ namespace mpm { void comm_fill_stats(const MpmSolver* s, MpmStats* st); }
 extern "C" int32_t mpm_get_stats(MpmSolver* s, MpmStats* st)
 {
     if (!s || !st) return MPM_ERR_INVALID;
+    if (s->comm) { cudaSetDevice(s->device); int rc = comm_partition(s); if (rc) return rc; }
     memset(st, 0, sizeof(*st));
     st->num_particles = s->n;
     st->local_particles = s->n;

@@ -1,24 +1,664 @@
-// mpm_comm.cu -- multi-GPU slab decomposition (one process per GPU): halo exchange and particle migration.
-// PLACEHOLDER in this revision: the entry points exist so the ABI is stable, and report MPM_ERR_COMM.
+// mpm_comm.cu -- multi-GPU x-slab decomposition: slab cuts, halo exchange-add, particle migration.
+//
+// The reference is single-device; this is new.  A rank owns grid planes [x0, x1) (contiguous in the reference's
+// cell order x*Ry*Rz + y*Rz + z, MLSMPM3DFluidMultithread.cs:282) and the particles whose base cell x lies
+// there; it stores planes [x0-1, x1+1).  The quadratic B-spline stencil reaches +-1 cell around the base cell
+// (MLSMPM3DFluidMultithread.cs:267-275), so a rank scatters into [x0-1, x1] and only nearest neighbours talk.
+//
+// Per step and neighbour pair
+//   after P2G_1 : both sides send their copy of the two overlap planes (the ghost plane and the boundary owned
+//                 plane are adjacent in memory: one contiguous block of 2*Ry*Rz cells) and add what they receive
+//                 -> both hold complete sums (P2G_2's density gather needs complete mass on the ghost plane).
+//   after P2G_2 : the same with the increment since the first exchange (block - snapshot).
+//   grid update : pointwise, run redundantly on the ghost planes (no exchange).
+//   after G2P   : particles whose base cell left [x0, x1) move to the neighbour (counts first, then records).
+// All grid traffic is int32 adds, which commute: k ranks give the bits 1 rank gives.
+//
+// Transports: NCCL send/recv (one process per GPU) and LOCAL (k solvers in one process: peer copies ordered by
+// CUDA events, rendezvous through a mutex/condvar mailbox per directed edge).  Both are stream-ordered.
+#include <dlfcn.h>
+#include <nccl.h>  // types only: every NCCL function is resolved with dlsym
+
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <vector>
+
 #include "mpm_kernels.h"
 #include "mpm_solver.h"
 
 namespace mpm {
-void comm_destroy(MpmSolver*) {}
-int comm_exchange_halo(MpmSolver*, int) { return MPM_OK; }
-int comm_migrate(MpmSolver*) { return MPM_OK; }
-int comm_filter_upload(MpmSolver*, int64_t) { return MPM_OK; }
-void comm_fill_stats(const MpmSolver*, MpmStats*) {}
+
+int sort_create(MpmSolver* s);
+void sort_destroy(MpmSolver* s);
+
+// ================================================================ transports
+struct Transport {
+    int rank = 0, world = 1;
+    virtual ~Transport() {}
+    // Stream-ordered neighbour exchange.  L = rank-1, R = rank+1.  A size of 0 skips that message; both ends of an
+    // edge must agree on its size.  Send buffers may be rewritten by work enqueued on `st` after the call returns.
+    virtual int exchange(const void* sendL, size_t nsl, void* recvL, size_t nrl, const void* sendR, size_t nsr,
+                         void* recvR, size_t nrr, cudaStream_t st, std::string& err) = 0;
+};
+
+// ---------------------------------------------------------------- NCCL
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi* nccl_api(std::string& err)
+{
+    static NcclApi api;
+    static std::mutex m;
+    std::lock_guard<std::mutex> lk(m);
+    if (api.handle) return &api;
+    // prefer the copy this process already has (a Python host has torch's), else the system library
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { err = std::string("cannot load libnccl.so.2: ") + dlerror(); return nullptr; }
+#define SYM(field, name)                                                     \
+    do {                                                                     \
+        *(void**)(&api.field) = dlsym(h, name);                              \
+        if (!api.field) { err = std::string("libnccl lacks ") + name; return nullptr; } \
+    } while (0)
+    SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommDestroy, "ncclCommDestroy");
+    SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv"); SYM(GroupStart, "ncclGroupStart"); SYM(GroupEnd, "ncclGroupEnd");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    api.handle = h;
+    return &api;
+}
+
+struct NcclTransport : Transport {
+    NcclApi* api = nullptr;
+    ncclComm_t comm = nullptr;
+    ~NcclTransport() override { if (comm) api->CommDestroy(comm); }
+    int exchange(const void* sendL, size_t nsl, void* recvL, size_t nrl, const void* sendR, size_t nsr, void* recvR,
+                 size_t nrr, cudaStream_t st, std::string& err) override
+    {
+        ncclResult_t r = api->GroupStart();
+        if (rank > 0) {
+            if (r == ncclSuccess && nsl) r = api->Send(sendL, nsl, ncclInt8, rank - 1, comm, st);
+            if (r == ncclSuccess && nrl) r = api->Recv(recvL, nrl, ncclInt8, rank - 1, comm, st);
+        }
+        if (rank < world - 1) {
+            if (r == ncclSuccess && nsr) r = api->Send(sendR, nsr, ncclInt8, rank + 1, comm, st);
+            if (r == ncclSuccess && nrr) r = api->Recv(recvR, nrr, ncclInt8, rank + 1, comm, st);
+        }
+        ncclResult_t e = api->GroupEnd();
+        if (r == ncclSuccess) r = e;
+        if (r != ncclSuccess) { err = std::string("NCCL: ") + api->GetErrorString(r); return MPM_ERR_COMM; }
+        return MPM_OK;
+    }
+};
+
+// ---------------------------------------------------------------- LOCAL (k solvers in one process)
+struct Mailbox {  // one directed edge src -> dst
+    std::mutex m;
+    std::condition_variable cv;
+    uint64_t posted = 0, consumed = 0;
+    const void* ptr = nullptr;
+    size_t bytes = 0;
+    int src_device = 0;
+    cudaEvent_t ready = nullptr;  // sender: data final on its stream
+    cudaEvent_t done = nullptr;   // receiver: its copy has been enqueued up to here
+};
+
 }  // namespace mpm
+
+struct MpmLocalHub {
+    int world = 0;
+    std::vector<mpm::Mailbox> to_right;  // [r]: r -> r+1
+    std::vector<mpm::Mailbox> to_left;   // [r]: r -> r-1
+    int timeout_s = 60;
+};
+
+namespace mpm {
+
+struct LocalTransport : Transport {
+    MpmLocalHub* hub = nullptr;
+    int device = 0;
+
+    int post(Mailbox& mb, const void* ptr, size_t bytes, cudaStream_t st)
+    {
+        std::lock_guard<std::mutex> lk(mb.m);
+        if (!mb.ready) cudaEventCreateWithFlags(&mb.ready, cudaEventDisableTiming);
+        cudaEventRecord(mb.ready, st);
+        mb.ptr = ptr; mb.bytes = bytes; mb.src_device = device;
+        mb.posted += 1;
+        mb.cv.notify_all();
+        return MPM_OK;
+    }
+    int pull(Mailbox& mb, void* dst, size_t bytes, cudaStream_t st, std::string& err)
+    {
+        std::unique_lock<std::mutex> lk(mb.m);
+        if (!mb.cv.wait_for(lk, std::chrono::seconds(hub->timeout_s), [&] { return mb.posted > mb.consumed; })) {
+            err = "local transport: the neighbouring rank did not arrive (every rank must be stepping concurrently)";
+            return MPM_ERR_COMM;
+        }
+        if (mb.bytes != bytes) { err = "local transport: message size mismatch between neighbours"; return MPM_ERR_COMM; }
+        cudaStreamWaitEvent(st, mb.ready, 0);
+        cudaError_t e = (mb.src_device == device) ? cudaMemcpyAsync(dst, mb.ptr, bytes, cudaMemcpyDeviceToDevice, st)
+                                                  : cudaMemcpyPeerAsync(dst, device, mb.ptr, mb.src_device, bytes, st);
+        if (e != cudaSuccess) { err = std::string("local transport copy: ") + cudaGetErrorString(e); return MPM_ERR_CUDA; }
+        if (!mb.done) cudaEventCreateWithFlags(&mb.done, cudaEventDisableTiming);
+        cudaEventRecord(mb.done, st);
+        mb.consumed += 1;
+        mb.cv.notify_all();
+        return MPM_OK;
+    }
+    // my later work on `st` (which may rewrite the send buffer) must follow the receiver's copy
+    int settle(Mailbox& mb, cudaStream_t st, std::string& err)
+    {
+        std::unique_lock<std::mutex> lk(mb.m);
+        if (!mb.cv.wait_for(lk, std::chrono::seconds(hub->timeout_s), [&] { return mb.consumed == mb.posted; })) {
+            err = "local transport: the neighbouring rank did not take its message";
+            return MPM_ERR_COMM;
+        }
+        cudaStreamWaitEvent(st, mb.done, 0);
+        return MPM_OK;
+    }
+    int exchange(const void* sendL, size_t nsl, void* recvL, size_t nrl, const void* sendR, size_t nsr, void* recvR,
+                 size_t nrr, cudaStream_t st, std::string& err) override
+    {
+        const bool hasL = rank > 0, hasR = rank < world - 1;
+        int rc;
+        if (hasL && nsl) post(hub->to_left[rank], sendL, nsl, st);
+        if (hasR && nsr) post(hub->to_right[rank], sendR, nsr, st);
+        if (hasL && nrl && (rc = pull(hub->to_right[rank - 1], recvL, nrl, st, err))) return rc;
+        if (hasR && nrr && (rc = pull(hub->to_left[rank + 1], recvR, nrr, st, err))) return rc;
+        if (hasL && nsl && (rc = settle(hub->to_left[rank], st, err))) return rc;
+        if (hasR && nsr && (rc = settle(hub->to_right[rank], st, err))) return rc;
+        return MPM_OK;
+    }
+};
+
+// ================================================================ state
+constexpr int REC_WORDS = NPLANES + 1;  // 16 particle planes + original index
+
+struct CommState {
+    Transport* tr = nullptr;
+    int rank = 0, world = 1;
+    std::vector<int> cuts;  // world + 1 global x planes
+    int x0 = 0, x1 = 0;     // owned planes
+    bool slab_set = false;    // the planes hold this rank's local particles and the grid is the slab
+    bool pending = false;     // the planes hold the GLOBAL set: partition before the next step / download
+    // halo: [0] = left block (local planes 0,1), [1] = right block (local planes nxl-2, nxl-1)
+    int4* halo_recv[2] = {nullptr, nullptr};
+    int4* halo_send[2] = {nullptr, nullptr};
+    int4* halo_snap[2] = {nullptr, nullptr};
+    int64_t halo_cells = 0;  // 2 * Ry * Rz
+    // migration
+    uint32_t* d_cnt = nullptr;  // 0 nL, 1 nR (leaving), 2 mL, 3 mR (arriving), 4 holes, 5 fillers, 6 cursorL, 7 cursorR, 8 bad
+    uint32_t* h_cnt = nullptr;  // pinned mirror
+    uint32_t* send_rec[2] = {nullptr, nullptr};
+    uint32_t* recv_rec[2] = {nullptr, nullptr};
+    uint32_t* holes = nullptr;
+    uint32_t* fillers = nullptr;
+    int64_t rec_cap = 0;
+    int64_t migrated_out = 0, migrated_in = 0;
+};
+
+#define CKM(call)                                                          \
+    do {                                                                   \
+        cudaError_t e_ = (call);                                           \
+        if (e_ != cudaSuccess) {                                           \
+            s->err = std::string(#call) + ": " + cudaGetErrorString(e_);   \
+            return MPM_ERR_CUDA;                                           \
+        }                                                                  \
+    } while (0)
+
+static void free_slab_buffers(CommState* c)
+{
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(c->halo_recv[k]); cudaFree(c->halo_send[k]); cudaFree(c->halo_snap[k]);
+        c->halo_recv[k] = c->halo_send[k] = c->halo_snap[k] = nullptr;
+    }
+}
+
+void comm_destroy(MpmSolver* s)
+{
+    CommState* c = s->comm;
+    if (!c) return;
+    free_slab_buffers(c);
+    for (int k = 0; k < 2; ++k) { cudaFree(c->send_rec[k]); cudaFree(c->recv_rec[k]); }
+    cudaFree(c->d_cnt); cudaFree(c->holes); cudaFree(c->fillers);
+    if (c->h_cnt) cudaFreeHost(c->h_cnt);
+    delete c->tr;
+    delete c;
+    s->comm = nullptr;
+}
+
+static int comm_attach(MpmSolver* s, Transport* tr, int rank, int world)
+{
+    if (s->comm) { delete tr; s->err = "a communicator is already attached"; return MPM_ERR_STATE; }
+    if (s->hp.dim != 3 || s->hp.grid_mode != MPM_GRID_FIXED) {
+        delete tr;
+        s->err = "multi-GPU slabs need dim = 3 and MPM_GRID_FIXED (integer halo sums)";
+        return MPM_ERR_INVALID;
+    }
+    CommState* c = new CommState();
+    c->tr = tr; c->rank = rank; c->world = world;
+    tr->rank = rank; tr->world = world;
+    s->comm = c;
+    c->rec_cap = std::max<int64_t>(s->cap / 8, 1 << 16);
+    if (c->rec_cap > s->cap) c->rec_cap = s->cap;
+    CKM(cudaMalloc(&c->d_cnt, 16 * sizeof(uint32_t)));
+    CKM(cudaHostAlloc(&c->h_cnt, 16 * sizeof(uint32_t), cudaHostAllocDefault));
+    for (int k = 0; k < 2; ++k) {
+        CKM(cudaMalloc(&c->send_rec[k], sizeof(uint32_t) * REC_WORDS * c->rec_cap));
+        CKM(cudaMalloc(&c->recv_rec[k], sizeof(uint32_t) * REC_WORDS * c->rec_cap));
+    }
+    CKM(cudaMalloc(&c->holes, sizeof(uint32_t) * 2 * c->rec_cap));
+    CKM(cudaMalloc(&c->fillers, sizeof(uint32_t) * 2 * c->rec_cap));
+    if (!s->part_alt) {
+        CKM(cudaMalloc(&s->part_alt, sizeof(float) * NPLANES * s->pitch));
+        CKM(cudaMalloc(&s->orig_id_alt, sizeof(uint32_t) * s->pitch));
+    }
+    s->sort_interval = 1;  // arrivals are appended unbinned: re-bin every step
+    return MPM_OK;
+}
+
+void comm_fill_stats(const MpmSolver* s, MpmStats* st)
+{
+    if (!s->comm) return;
+    st->rank = s->comm->rank;
+    st->world = s->comm->world;
+}
+
+// ================================================================ slab set-up at upload time
+__global__ void __launch_bounds__(256) k_xhist(const float* __restrict__ px, int64_t n, int rx, unsigned long long* __restrict__ hist)
+{
+    extern __shared__ uint32_t sh[];
+    for (int k = threadIdx.x; k < rx; k += blockDim.x) sh[k] = 0;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int cx = __float2int_rz(px[i]);
+        cx = cx < 0 ? 0 : (cx >= rx ? rx - 1 : cx);
+        atomicAdd(&sh[cx], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < rx; k += blockDim.x)
+        if (sh[k]) atomicAdd(&hist[k], (unsigned long long)sh[k]);
+}
+
+// keep the particles whose base cell x is in [x0, x1): unordered compaction into the alternate planes
+__global__ void __launch_bounds__(256) k_filter_slab(ParticleView src, ParticleView dst, const uint32_t* __restrict__ id_src,
+                                                     uint32_t* __restrict__ id_dst, int64_t n, int x0, int x1, uint32_t* counter)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool keep = false;
+    if (i < n) {
+        const int cx = __float2int_rz(src.plane(PX)[i]);
+        keep = cx >= x0 && cx < x1;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (!m) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (!keep) return;
+    const uint32_t d = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+#pragma unroll
+    for (int k = 0; k < NPLANES; ++k) dst.plane(k)[d] = src.plane(k)[i];
+    id_dst[d] = id_src[i];
+}
+
+static int slab_cuts_host(const int64_t* hist, int rx, int world, int min_width, int* cuts)
+{
+    if (!hist || !cuts || world < 1 || min_width < 1 || (int64_t)world * min_width > rx) return MPM_ERR_INVALID;
+    int64_t total = 0;
+    for (int x = 0; x < rx; ++x) total += hist[x];
+    cuts[0] = 0;
+    int x = 0;
+    int64_t cum = 0;  // particles in planes < x
+    for (int k = 1; k < world; ++k) {
+        const int64_t target = (total * k + world - 1) / world;
+        while (x < rx && cum < target) cum += hist[x++];
+        int c = x;
+        c = std::max(c, cuts[k - 1] + min_width);
+        c = std::min(c, rx - (world - k) * min_width);
+        cuts[k] = c;
+        while (x < c) cum += hist[x++];  // keep (x, cum) consistent if the clamp moved the cut right
+    }
+    cuts[world] = rx;
+    return MPM_OK;
+}
+
+constexpr int MIN_SLAB_WIDTH = 4;
+
+bool comm_partitioned(const MpmSolver* s) { return s->comm && s->comm->slab_set; }
+void comm_mark_global(MpmSolver* s) { s->comm->pending = true; s->comm->slab_set = false; }
+
+// The planes hold the GLOBAL particle set (s->n particles, ids in orig_id): cut the slabs, keep this rank's.
+int comm_partition(MpmSolver* s)
+{
+    CommState* c = s->comm;
+    if (!c || !c->pending) return MPM_OK;
+    const int64_t n_global = s->n;
+    const int rx = s->dp.Rx;
+    // 1. x-plane histogram -> equal-count cuts (identical on every rank: same data, same arithmetic)
+    unsigned long long* d_hist = nullptr;
+    CKM(cudaMalloc(&d_hist, sizeof(unsigned long long) * rx));
+    CKM(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * rx, s->stream));
+    if (n_global > 0) {
+        const int blocks = (int)std::min<int64_t>((n_global + 255) / 256, 148 * 8);
+        k_xhist<<<blocks, 256, sizeof(uint32_t) * rx, s->stream>>>(s->view().plane(PX), n_global, rx, d_hist);
+        s->launches += 1;
+    }
+    std::vector<int64_t> hist(rx);
+    static_assert(sizeof(unsigned long long) == sizeof(int64_t), "");
+    cudaError_t e = cudaMemcpyAsync(hist.data(), d_hist, sizeof(int64_t) * rx, cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(d_hist);
+    if (e != cudaSuccess) { s->err = cudaGetErrorString(e); return MPM_ERR_CUDA; }
+    c->cuts.assign(c->world + 1, 0);
+    if (slab_cuts_host(hist.data(), rx, c->world, MIN_SLAB_WIDTH, c->cuts.data())) {
+        s->err = "grid too narrow in x for this many ranks (each slab needs >= 4 planes)";
+        return MPM_ERR_INVALID;
+    }
+    c->x0 = c->cuts[c->rank]; c->x1 = c->cuts[c->rank + 1];
+    // 2. local grid: planes [x0-1, x1+1)
+    s->dp.gx0 = c->x0 - 1; s->dp.nxl = c->x1 - c->x0 + 2;
+    cudaFree(s->grid); s->grid = nullptr;
+    s->ncells = (int64_t)s->dp.nxl * s->dp.Ry * s->dp.Rz;
+    CKM(cudaMalloc(&s->grid, 16 * s->ncells));
+    CKM(cudaMemsetAsync(s->grid, 0, 16 * s->ncells, s->stream));
+    free_slab_buffers(c);
+    c->halo_cells = 2 * (int64_t)s->dp.Ry * s->dp.Rz;
+    for (int k = 0; k < 2; ++k) {
+        CKM(cudaMalloc(&c->halo_recv[k], 16 * c->halo_cells));
+        CKM(cudaMalloc(&c->halo_send[k], 16 * c->halo_cells));
+        CKM(cudaMalloc(&c->halo_snap[k], 16 * c->halo_cells));
+    }
+    if (s->path == MPM_PATH_TILED) {  // block grid follows the slab
+        sort_destroy(s);
+        int rc = sort_create(s);
+        if (rc) return rc;
+    }
+    // 3. keep own particles
+    CKM(cudaMemsetAsync(c->d_cnt, 0, 16 * sizeof(uint32_t), s->stream));
+    if (n_global > 0) {
+        k_filter_slab<<<(unsigned)((n_global + 255) / 256), 256, 0, s->stream>>>(s->view(), s->view_alt(), s->orig_id, s->orig_id_alt,
+                                                                                 n_global, c->x0, c->x1, c->d_cnt);
+        s->launches += 1;
+    }
+    CKM(cudaMemcpyAsync(c->h_cnt, c->d_cnt, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    CKM(cudaStreamSynchronize(s->stream));
+    std::swap(s->part, s->part_alt);
+    std::swap(s->orig_id, s->orig_id_alt);
+    s->n = c->h_cnt[0];
+    c->slab_set = true;
+    c->pending = false;
+    s->sorted_valid = false;
+    s->positions_valid = false;
+    return MPM_OK;
+}
+
+// ================================================================ halo exchange
+__global__ void __launch_bounds__(256) k_halo_add(int4* __restrict__ blockL, const int4* __restrict__ recvL, int4* __restrict__ blockR,
+                                                  const int4* __restrict__ recvR, int64_t cells)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cells) return;
+    if (blockL) { int4 a = blockL[i]; const int4 b = recvL[i]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; blockL[i] = a; }
+    if (blockR) { int4 a = blockR[i]; const int4 b = recvR[i]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; blockR[i] = a; }
+}
+
+__global__ void __launch_bounds__(256) k_halo_diff(const int4* __restrict__ blockL, const int4* __restrict__ snapL, int4* __restrict__ outL,
+                                                   const int4* __restrict__ blockR, const int4* __restrict__ snapR, int4* __restrict__ outR,
+                                                   int64_t cells)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cells) return;
+    if (blockL) { const int4 a = blockL[i], b = snapL[i]; outL[i] = make_int4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+    if (blockR) { const int4 a = blockR[i], b = snapR[i]; outR[i] = make_int4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+}
+
+int comm_exchange_halo(MpmSolver* s, int pass)
+{
+    CommState* c = s->comm;
+    if (!c->slab_set) { s->err = "multi-GPU: upload the particle set after mpm_comm_init*"; return MPM_ERR_STATE; }
+    const bool hasL = c->rank > 0, hasR = c->rank < c->world - 1;
+    if (!hasL && !hasR) return MPM_OK;
+    int4* grid = reinterpret_cast<int4*>(s->grid);
+    const int64_t plane = (int64_t)s->dp.Ry * s->dp.Rz;
+    int4* blockL = hasL ? grid : nullptr;
+    int4* blockR = hasR ? grid + (int64_t)(s->dp.nxl - 2) * plane : nullptr;
+    const size_t bytes = 16 * (size_t)c->halo_cells;
+    const unsigned nb = (unsigned)((c->halo_cells + 255) / 256);
+    const int4 *sendL = blockL, *sendR = blockR;
+    if (pass == 1) {
+        k_halo_diff<<<nb, 256, 0, s->stream>>>(blockL, c->halo_snap[0], c->halo_send[0], blockR, c->halo_snap[1], c->halo_send[1], c->halo_cells);
+        s->launches += 1;
+        sendL = c->halo_send[0]; sendR = c->halo_send[1];
+    }
+    int rc = c->tr->exchange(sendL, hasL ? bytes : 0, c->halo_recv[0], hasL ? bytes : 0, sendR, hasR ? bytes : 0, c->halo_recv[1],
+                             hasR ? bytes : 0, s->stream, s->err);
+    if (rc) return rc;
+    k_halo_add<<<nb, 256, 0, s->stream>>>(blockL, c->halo_recv[0], blockR, c->halo_recv[1], c->halo_cells);
+    s->launches += 1;
+    if (pass == 0) {
+        if (hasL) CKM(cudaMemcpyAsync(c->halo_snap[0], blockL, bytes, cudaMemcpyDeviceToDevice, s->stream));
+        if (hasR) CKM(cudaMemcpyAsync(c->halo_snap[1], blockR, bytes, cudaMemcpyDeviceToDevice, s->stream));
+    }
+    return MPM_OK;
+}
+
+// ================================================================ particle migration
+struct MigGeom {
+    int x0, x1;      // owned planes
+    int xl0, xr1;    // the left neighbour's first plane, the right neighbour's end plane (jump guard)
+};
+
+__device__ __forceinline__ int mig_side(const MigGeom& g, float px, uint32_t* bad)
+{
+    const int cx = __float2int_rz(px);
+    if (cx < g.x0) { if (cx < g.xl0) *bad = 1u; return 0; }
+    if (cx >= g.x1) { if (cx >= g.xr1) *bad = 1u; return 1; }
+    return -1;
+}
+
+__global__ void __launch_bounds__(256) k_mig_count(MigGeom g, const float* __restrict__ px, int64_t n, uint32_t* __restrict__ cnt)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int side = (i < n) ? mig_side(g, px[i], cnt + 8) : -1;
+    const unsigned mL = __ballot_sync(0xffffffffu, side == 0), mR = __ballot_sync(0xffffffffu, side == 1);
+    if ((threadIdx.x & 31) == 0) {
+        if (mL) atomicAdd(cnt + 0, (uint32_t)__popc(mL));
+        if (mR) atomicAdd(cnt + 1, (uint32_t)__popc(mR));
+    }
+}
+
+// leavers -> send records (SoA inside the buffer, stride = that side's count); holes / fillers for the compaction
+__global__ void __launch_bounds__(256) k_mig_pack(MigGeom g, ParticleView pv, const uint32_t* __restrict__ ids, int64_t n, int64_t n_stay,
+                                                  uint32_t nL, uint32_t nR, uint32_t* __restrict__ sendL, uint32_t* __restrict__ sendR,
+                                                  uint32_t* __restrict__ holes, uint32_t* __restrict__ fillers, uint32_t* __restrict__ cnt)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t dummy;
+    const int side = mig_side(g, pv.plane(PX)[i], &dummy);
+    if (side < 0) {
+        if (i >= n_stay) fillers[atomicAdd(cnt + 5, 1u)] = (uint32_t)i;
+        return;
+    }
+    if (i < n_stay) holes[atomicAdd(cnt + 4, 1u)] = (uint32_t)i;
+    uint32_t* out = side == 0 ? sendL : sendR;
+    const uint32_t stride = side == 0 ? nL : nR;
+    const uint32_t slot = atomicAdd(cnt + 6 + side, 1u);
+#pragma unroll
+    for (int k = 0; k < NPLANES; ++k) out[(size_t)k * stride + slot] = __float_as_uint(pv.plane(k)[i]);
+    out[(size_t)NPLANES * stride + slot] = ids[i];
+}
+
+__global__ void __launch_bounds__(256) k_mig_fill(ParticleView pv, uint32_t* __restrict__ ids, const uint32_t* __restrict__ holes,
+                                                  const uint32_t* __restrict__ fillers, const uint32_t* __restrict__ cnt)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= cnt[4]) return;
+    const uint32_t dst = holes[j], src = fillers[j];
+#pragma unroll
+    for (int k = 0; k < NPLANES; ++k) pv.plane(k)[dst] = pv.plane(k)[src];
+    ids[dst] = ids[src];
+}
+
+__global__ void __launch_bounds__(256) k_mig_unpack(ParticleView pv, uint32_t* __restrict__ ids, int64_t dst_off, const uint32_t* __restrict__ rec,
+                                                    uint32_t count)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+#pragma unroll
+    for (int k = 0; k < NPLANES; ++k) pv.plane(k)[dst_off + j] = __uint_as_float(rec[(size_t)k * count + j]);
+    ids[dst_off + j] = rec[(size_t)NPLANES * count + j];
+}
+
+int comm_migrate(MpmSolver* s)
+{
+    CommState* c = s->comm;
+    const bool hasL = c->rank > 0, hasR = c->rank < c->world - 1;
+    if (!hasL && !hasR) return MPM_OK;
+    const int64_t n = s->n;
+    MigGeom g{c->x0, c->x1, hasL ? c->cuts[c->rank - 1] : c->x0, hasR ? c->cuts[c->rank + 2] : c->x1};
+    CKM(cudaMemsetAsync(c->d_cnt, 0, 16 * sizeof(uint32_t), s->stream));
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    if (n > 0) { k_mig_count<<<nb, 256, 0, s->stream>>>(g, s->view().plane(PX), n, c->d_cnt); s->launches += 1; }
+    // counts: mine leaving left -> the left rank's "arriving from right" (d_cnt[3] there), and vice versa
+    int rc = c->tr->exchange(c->d_cnt + 0, hasL ? 4 : 0, c->d_cnt + 2, hasL ? 4 : 0, c->d_cnt + 1, hasR ? 4 : 0, c->d_cnt + 3, hasR ? 4 : 0,
+                             s->stream, s->err);
+    if (rc) return rc;
+    CKM(cudaMemcpyAsync(c->h_cnt, c->d_cnt, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    CKM(cudaStreamSynchronize(s->stream));
+    const uint32_t nL = c->h_cnt[0], nR = c->h_cnt[1], mL = c->h_cnt[2], mR = c->h_cnt[3];
+    if (c->h_cnt[8]) { s->err = "multi-GPU: a particle crossed more than one slab in a single step (dt * |v| too large for the slab width)"; return MPM_ERR_COMM; }
+    if ((int64_t)std::max(std::max(nL, nR), std::max(mL, mR)) > c->rec_cap) { s->err = "multi-GPU: migration buffer too small"; return MPM_ERR_COMM; }
+    const int64_t n_stay = n - nL - nR;
+    if (n_stay + mL + mR > s->cap) { s->err = "multi-GPU: arriving particles exceed max_particles of this rank"; return MPM_ERR_COMM; }
+    if (nL + nR > 0) {
+        k_mig_pack<<<nb, 256, 0, s->stream>>>(g, s->view(), s->orig_id, n, n_stay, nL, nR, c->send_rec[0], c->send_rec[1], c->holes,
+                                              c->fillers, c->d_cnt);
+        k_mig_fill<<<(nL + nR + 255) / 256, 256, 0, s->stream>>>(s->view(), s->orig_id, c->holes, c->fillers, c->d_cnt);
+        s->launches += 2;
+    }
+    const size_t rb = sizeof(uint32_t) * REC_WORDS;
+    rc = c->tr->exchange(c->send_rec[0], rb * nL, c->recv_rec[0], rb * mL, c->send_rec[1], rb * nR, c->recv_rec[1], rb * mR, s->stream, s->err);
+    if (rc) return rc;
+    if (mL) { k_mig_unpack<<<(mL + 255) / 256, 256, 0, s->stream>>>(s->view(), s->orig_id, n_stay, c->recv_rec[0], mL); s->launches += 1; }
+    if (mR) { k_mig_unpack<<<(mR + 255) / 256, 256, 0, s->stream>>>(s->view(), s->orig_id, n_stay + mL, c->recv_rec[1], mR); s->launches += 1; }
+    s->n = n_stay + mL + mR;
+    c->migrated_out += nL + nR;
+    c->migrated_in += mL + mR;
+    if (nL + nR + mL + mR) { s->sorted_valid = false; s->positions_valid = false; }
+    return MPM_OK;
+}
+
+}  // namespace mpm
+
+// ================================================================ C ABI
+using namespace mpm;
+
+extern "C" int32_t mpm_slab_cuts(const int64_t* hist, int32_t rx, int32_t world, int32_t min_width, int32_t* cuts)
+{
+    return slab_cuts_host(hist, rx, world, min_width, cuts);
+}
 
 extern "C" int32_t mpm_comm_unique_id(uint8_t id[MPM_COMM_ID_BYTES])
 {
-    (void)id;
-    return MPM_ERR_COMM;
+    static_assert(sizeof(ncclUniqueId) == MPM_COMM_ID_BYTES, "ncclUniqueId size");
+    if (!id) return MPM_ERR_INVALID;
+    std::string err;
+    NcclApi* api = nccl_api(err);
+    if (!api) return MPM_ERR_COMM;
+    ncclUniqueId u;
+    if (api->GetUniqueId(&u) != ncclSuccess) return MPM_ERR_COMM;
+    memcpy(id, &u, sizeof(u));
+    return MPM_OK;
 }
+
 extern "C" int32_t mpm_comm_init(MpmSolver* s, const uint8_t id[MPM_COMM_ID_BYTES], int32_t rank, int32_t world)
 {
-    (void)id; (void)rank; (void)world;
-    if (s) s->err = "multi-GPU slabs are not implemented in this build";
-    return MPM_ERR_COMM;
+    if (!s || !id || world < 1 || rank < 0 || rank >= world) return MPM_ERR_INVALID;
+    if (cudaSetDevice(s->device) != cudaSuccess) { s->err = "cudaSetDevice failed"; return MPM_ERR_CUDA; }
+    NcclApi* api = nccl_api(s->err);
+    if (!api) return MPM_ERR_COMM;
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof(u));
+    NcclTransport* tr = new NcclTransport();
+    tr->api = api;
+    ncclResult_t r = api->CommInitRank(&tr->comm, world, u, rank);
+    if (r != ncclSuccess) {
+        s->err = std::string("ncclCommInitRank: ") + api->GetErrorString(r);
+        tr->comm = nullptr;
+        delete tr;
+        return MPM_ERR_COMM;
+    }
+    return comm_attach(s, tr, rank, world);
+}
+
+extern "C" int32_t mpm_local_hub_create(int32_t world, MpmLocalHub** hub)
+{
+    if (!hub || world < 1 || world > 64) return MPM_ERR_INVALID;
+    MpmLocalHub* h = new MpmLocalHub();
+    h->world = world;
+    h->to_right = std::vector<Mailbox>(world);
+    h->to_left = std::vector<Mailbox>(world);
+    *hub = h;
+    return MPM_OK;
+}
+
+extern "C" int32_t mpm_local_hub_destroy(MpmLocalHub* hub)
+{
+    if (!hub) return MPM_OK;
+    for (auto* v : {&hub->to_right, &hub->to_left})
+        for (Mailbox& mb : *v) {
+            if (mb.ready) cudaEventDestroy(mb.ready);
+            if (mb.done) cudaEventDestroy(mb.done);
+        }
+    delete hub;
+    return MPM_OK;
+}
+
+extern "C" int32_t mpm_comm_init_local(MpmSolver* s, MpmLocalHub* hub, int32_t rank, int32_t world)
+{
+    if (!s || !hub || world != hub->world || rank < 0 || rank >= world) return MPM_ERR_INVALID;
+    if (cudaSetDevice(s->device) != cudaSuccess) { s->err = "cudaSetDevice failed"; return MPM_ERR_CUDA; }
+    LocalTransport* tr = new LocalTransport();
+    tr->hub = hub;
+    tr->device = s->device;
+    return comm_attach(s, tr, rank, world);
+}
+
+extern "C" int32_t mpm_comm_slab(const MpmSolver* s, int32_t* x0, int32_t* x1, int32_t* gx0, int32_t* nxl)
+{
+    if (!s) return MPM_ERR_INVALID;
+    if (x0) *x0 = s->comm ? s->comm->x0 : 0;
+    if (x1) *x1 = s->comm ? s->comm->x1 : s->dp.Rx;
+    if (gx0) *gx0 = s->dp.gx0;
+    if (nxl) *nxl = s->dp.nxl;
+    return MPM_OK;
+}
+
+extern "C" int32_t mpm_download_ids(MpmSolver* s, uint32_t* ids, int64_t cap)
+{
+    if (!s || !ids) return MPM_ERR_INVALID;
+    if (cap < s->n) { s->err = "destination too small"; return MPM_ERR_INVALID; }
+    if (cudaSetDevice(s->device) != cudaSuccess) { s->err = "cudaSetDevice failed"; return MPM_ERR_CUDA; }
+    if (s->n == 0) return MPM_OK;
+    CKM(cudaMemcpyAsync(ids, s->orig_id, sizeof(uint32_t) * s->n, cudaMemcpyDeviceToHost, s->stream));
+    CKM(cudaStreamSynchronize(s->stream));
+    return MPM_OK;
 }

@@ -74,6 +74,8 @@ EXPORTS = [
     "mpm_download_particles_soa", "mpm_download_grid", "mpm_step", "mpm_sync", "mpm_run_phase",
     "mpm_get_positions", "mpm_num_particles", "mpm_set_timing", "mpm_get_stats", "mpm_debug_last_sort",
     "mpm_get_stream", "mpm_host_alloc", "mpm_host_free", "mpm_comm_unique_id", "mpm_comm_init",
+    "mpm_local_hub_create", "mpm_local_hub_destroy", "mpm_comm_init_local", "mpm_comm_slab", "mpm_download_ids",
+    "mpm_slab_cuts",
 ]
 
 _lib = None
@@ -119,6 +121,12 @@ def load():
         "mpm_host_free": (i32, [vp]),
         "mpm_comm_unique_id": (i32, [vp]),
         "mpm_comm_init": (i32, [vp, vp, i32, i32]),
+        "mpm_local_hub_create": (i32, [i32, C.POINTER(vp)]),
+        "mpm_local_hub_destroy": (i32, [vp]),
+        "mpm_comm_init_local": (i32, [vp, vp, i32, i32]),
+        "mpm_comm_slab": (i32, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
+        "mpm_download_ids": (i32, [vp, vp, i64]),
+        "mpm_slab_cuts": (i32, [C.POINTER(i64), i32, i32, i32, C.POINTER(i32)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -211,7 +219,7 @@ class Solver:
         self._ck(self._L.mpm_upload_particles(self._h, rec.ctypes.data_as(C.c_void_p), rec.shape[0]))
 
     def download(self):
-        n = self.num_particles
+        n = self.stats().local_particles  # (multi-GPU: triggers the pending slab partition first)
         pos, vel = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
         Cm, mass = np.zeros((n, 9), np.float32), np.zeros(n, np.float32)
         self._ck(self._L.mpm_download_particles_soa(self._h, _fp(pos), _fp(vel), _fp(Cm), _fp(mass), n))
@@ -284,9 +292,56 @@ class Solver:
         self._ck(self._L.mpm_get_stream(self._h, C.byref(sp)))
         return sp.value or 0
 
+    # -- multi-GPU x-slabs (no reference counterpart)
     def comm_init(self, unique_id: bytes, rank, world):
+        """NCCL transport: one process per GPU; unique_id comes from comm_unique_id() on rank 0."""
         buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(unique_id)
         self._ck(self._L.mpm_comm_init(self._h, buf, rank, world))
+
+    def comm_init_local(self, hub, rank, world):
+        """LOCAL transport: k solvers of one process (one host thread each) share `hub`."""
+        self._hub = hub  # keep it alive as long as the solver
+        self._ck(self._L.mpm_comm_init_local(self._h, hub._h, rank, world))
+
+    def slab(self):
+        """(x0, x1, gx0, nxl): owned planes [x0, x1), stored planes [gx0, gx0 + nxl)."""
+        v = [C.c_int32() for _ in range(4)]
+        self._ck(self._L.mpm_comm_slab(self._h, *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)
+
+    def download_ids(self):
+        n = self.stats().local_particles
+        ids = np.zeros(n, np.uint32)
+        self._ck(self._L.mpm_download_ids(self._h, ids.ctypes.data_as(C.c_void_p), n))
+        return ids
+
+
+class LocalHub:
+    """Rendezvous object of the LOCAL transport (mpm_local_hub_create)."""
+
+    def __init__(self, world):
+        self._L = load()
+        self._h = C.c_void_p()
+        rc = self._L.mpm_local_hub_create(int(world), C.byref(self._h))
+        if rc:
+            raise MpmError(rc, "mpm_local_hub_create failed")
+        self.world = world
+
+    def close(self):
+        if self._h:
+            self._L.mpm_local_hub_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+def slab_cuts(hist, world, min_width=4):
+    """Equal-count x-slab cuts from an x-plane particle histogram (host-only; mpm_slab_cuts)."""
+    L = load()
+    h = np.ascontiguousarray(hist, np.int64)
+    cuts = (C.c_int32 * (world + 1))()
+    rc = L.mpm_slab_cuts(h.ctypes.data_as(C.POINTER(C.c_int64)), h.shape[0], int(world), int(min_width), cuts)
+    if rc:
+        raise MpmError(rc, "mpm_slab_cuts: invalid arguments (grid too narrow for this many ranks?)")
+    return list(cuts)
 
 
 def comm_unique_id():

@@ -1,0 +1,185 @@
+"""Multi-GPU x-slabs.  CPU part: slab cuts (host logic) alone and across two gloo ranks.
+GPU part (-m gpu, one device): k solvers in one process on the LOCAL transport -- the same halo exchange-add and
+migration code the NCCL transport runs -- must reproduce the single-solver result bit for bit in fixed-point mode."""
+import os
+import socket
+import threading
+
+import numpy as np
+import pytest
+
+import helpers
+from oracle import orc
+
+
+# ---------------------------------------------------------------- CPU: slab cuts
+def test_slab_cuts_balance_and_constraints(lib):
+    import mpm_b200
+    rng = np.random.default_rng(3)
+    hist = np.zeros(256, np.int64)
+    hist[4:164] = rng.integers(150_000, 250_000, 160)           # dam-break block occupies x in [4, 164)
+    for world in (1, 2, 3, 4, 8):
+        cuts = mpm_b200.slab_cuts(hist, world)
+        assert cuts[0] == 0 and cuts[-1] == 256 and len(cuts) == world + 1
+        assert all(b - a >= 4 for a, b in zip(cuts, cuts[1:]))
+        per = [hist[a:b].sum() for a, b in zip(cuts, cuts[1:])]
+        assert sum(per) == hist.sum()
+        assert max(per) - min(per) <= 2 * hist.max(), (world, per)   # equal counts up to one plane's worth
+    # degenerate inputs: everything in one plane, empty histogram, too many ranks
+    one = np.zeros(64, np.int64); one[10] = 1000
+    cuts = mpm_b200.slab_cuts(one, 4)
+    assert cuts[0] == 0 and cuts[-1] == 64 and all(b - a >= 4 for a, b in zip(cuts, cuts[1:]))
+    cuts = mpm_b200.slab_cuts(np.zeros(64, np.int64), 4)
+    assert cuts[-1] == 64 and all(b - a >= 4 for a, b in zip(cuts, cuts[1:]))
+    with pytest.raises(mpm_b200.MpmError):
+        mpm_b200.slab_cuts(np.ones(8, np.int64), 4)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    import mpm_b200
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # every rank holds a different part of the scene; the cuts must come out identical everywhere
+        rng = np.random.default_rng(100 + rank)
+        x = rng.uniform(4, 100 if rank == 0 else 60, 50_000).astype(np.float32)
+        local = np.bincount(x.astype(np.int32), minlength=128).astype(np.int64)
+        t = torch.from_numpy(local.copy())
+        dist.all_reduce(t)
+        cuts = mpm_b200.slab_cuts(t.numpy(), world)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, cuts)
+        # what the NCCL bootstrap does with the 128-byte id: rank 0 makes it, everyone gets the same bytes
+        uid = [bytes(range(128)) if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        q.put((rank, cuts, gathered, int(t.numpy().sum()), uid[0]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_slab_cuts_agree_across_two_gloo_ranks(lib):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    (_, c0, g0, tot0, u0), (_, c1, g1, tot1, u1) = out
+    assert c0 == c1 and g0 == [c0, c0] and g1 == g0 and tot0 == tot1 == 100_000
+    assert c0[0] == 0 and c0[2] == 128 and 4 <= c0[1] <= 124
+    assert u0 == u1 == bytes(range(128))
+
+
+# ---------------------------------------------------------------- GPU: k slabs == 1 slab, bit for bit
+def _run_ranks(op, world, pos, vel, Cm, mass, steps, **over):
+    """k solvers on device 0, one thread each (the LOCAL transport blocks until its neighbours arrive)."""
+    import mpm_b200
+    hub = mpm_b200.LocalHub(world)
+    out, errs = [None] * world, []
+
+    def work(r):
+        try:
+            with mpm_b200.Solver(helpers.mpm_params_from_orc(op, **over), pos.shape[0]) as s:
+                s.comm_init_local(hub, r, world)
+                s.upload(pos, vel, Cm, mass)          # the global set on every rank; each keeps its slab
+                s.step(steps)
+                gp, gv, gc, gm = s.download()
+                out[r] = dict(pos=gp, vel=gv, C=gc, mass=gm, ids=s.download_ids(), grid=s.download_grid(), slab=s.slab(),
+                              stats=s.stats())
+        except Exception as e:  # noqa: BLE001
+            errs.append((r, e))
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(300)
+    hub.close()
+    assert not errs, errs
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", [1, 2], ids=["reference_path", "tiled_path"])
+@pytest.mark.parametrize("world", [2, 3])
+def test_k_slabs_bit_identical_to_one(lib, world, path):
+    op = orc.variant("3d_gpu", (48, 32, 32))
+    op.interaction = 0
+    n = 60000
+    pos, vel, Cm, mass = helpers.random_cloud(op, n, seed=7, vel_sigma=1.5)   # fast particles: real migration traffic
+    steps = 8
+    ref = orc.State(op, pos, vel, Cm, mass)
+    ref.step(steps)
+    ranks = _run_ranks(op, world, pos, vel, Cm, mass, steps, kernel_path=path)
+    ids = np.concatenate([r["ids"] for r in ranks])
+    assert np.array_equal(np.sort(ids), np.arange(n, dtype=np.uint32)), "particles lost or duplicated by migration"
+    for what in ("pos", "vel", "C", "mass"):
+        full = np.zeros_like(getattr(ref, what))
+        for r in ranks:
+            full[r["ids"]] = r[what]
+        helpers.assert_bit_equal(full, getattr(ref, what), f"{what} ({world} slabs)")
+    # each rank's particles sit in its own slab, and its owned grid planes equal the single-domain grid
+    Ry, Rz = 32, 32
+    gref = ref.grid.reshape(48, Ry, Rz, 4)
+    cover = []
+    for r in ranks:
+        x0, x1, gx0, nxl = r["slab"]
+        cover.append((x0, x1))
+        cx = r["pos"][:, 0].astype(np.int32)
+        assert ((cx >= x0) & (cx < x1)).all()
+        g = r["grid"].reshape(nxl, Ry, Rz, 4)
+        helpers.assert_bit_equal(g[x0 - gx0: x1 - gx0], gref[x0:x1], f"owned planes of rank {r['stats'].rank}")
+    assert cover[0][0] == 0 and cover[-1][1] == 48 and all(a[1] == b[0] for a, b in zip(cover, cover[1:]))
+    assert sum(r["stats"].local_particles for r in ranks) == n
+
+
+@pytest.mark.gpu
+def test_slab_dam_break_trajectory_and_balance(lib):
+    """Reduced dam-break on 2 slabs, 30 steps, lattice generated on the device on every rank (mpm_init_block)."""
+    import mpm_b200
+    op = orc.variant("3d_gpu", 32)
+    op.interaction = 0
+    lo, hi = (4, 4, 4), (20, 20, 20)
+    pos = orc.init_block(3, lo, hi, 0.5)
+    ref = orc.State(op, pos)
+    ref.step(30)
+    world = 2
+    hub = mpm_b200.LocalHub(world)
+    out, errs = [None] * world, []
+
+    def work(r):
+        try:
+            with mpm_b200.Solver(helpers.mpm_params_from_orc(op, kernel_path=2), pos.shape[0]) as s:
+                s.comm_init_local(hub, r, world)
+                s.initialise_sim(lo, hi, 0.5)
+                n0 = s.stats().local_particles
+                s.step(30)
+                out[r] = (s.download(), s.download_ids(), n0, s.slab())
+        except Exception as e:  # noqa: BLE001
+            errs.append((r, e))
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    [t.start() for t in th]
+    [t.join(300) for t in th]
+    hub.close()
+    assert not errs, errs
+    assert abs(out[0][2] - out[1][2]) <= 2 * 32 * 32 * 4, "initial slabs are not balanced"   # within two lattice planes
+    full = np.zeros_like(ref.pos)
+    fullv = np.zeros_like(ref.vel)
+    for (gp, gv, gc, gm), ids, _, _ in out:
+        full[ids], fullv[ids] = gp, gv
+    helpers.assert_bit_equal(full, ref.pos, "pos after 30 steps on 2 slabs")
+    helpers.assert_bit_equal(fullv, ref.vel, "vel after 30 steps on 2 slabs")
