@@ -163,7 +163,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--sort-interval", type=int, default=0)
-    ap.add_argument("--path", type=int, default=0, help="0 auto, 1 reference-shaped, 2 tiled")
+    ap.add_argument("--path", type=int, default=0, help="0 auto, 1 reference-shaped, 2 tiled, 3 cell")
     ap.add_argument("--math", default="fast", choices=["strict", "fast"],
                     help="strict = bit-exact vs the reference algorithm; fast = FMA/hoisted (tolerance in tests)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -264,7 +264,7 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32+int32-fixed-point", "data": "synthetic",
             "config": {"workload": WORKLOAD_DESC[args.workload], "grid": list(grid), "particles": n_total, "variant": "3d_gpu (H)",
-                       "grid_mode": "fixed 1e7", "math": args.math, "kernel_path": {1: "reference-shaped", 2: "tiled"}[st.kernel_path],
+                       "grid_mode": "fixed 1e7", "math": args.math, "kernel_path": {1: "reference-shaped", 2: "tiled", 3: "cell"}[st.kernel_path],
                        "sort_interval": solver.params.sort_interval or 1, "parallelism": f"x-slab x{world}",
                        "l2": "inputs (2.1 GB particle planes) exceed the 126 MB L2; no flush needed",
                        "timing": "CUDA events on the solver stream inside mpm_step; wall-clock cross-check in wall_ms_per_step"},

@@ -67,7 +67,10 @@ extern "C" {
 /* kernel path */
 #define MPM_PATH_AUTO 0
 #define MPM_PATH_REFERENCE 1 /* one thread per particle, global atomics: the shape of p2g_1.glsl etc. */
-#define MPM_PATH_TILED 2     /* cell-sorted particles, shared-memory grid tiles (the B200 path) */
+#define MPM_PATH_TILED 2     /* block-binned particles (stable radix sort), one thread per particle, shared-memory grid tiles;
+                                runs MPM_MATH_STRICT bit-exactly (and MPM_MATH_FAST) */
+#define MPM_PATH_CELL 3      /* cell-binned particles (counting sort), one thread per grid cell with the 27-node stencil
+                                in registers: the fast B200 path; MPM_MATH_FAST only.  AUTO picks it for 3D fixed + FAST */
 
 /* variant presets for mpm_default_params() */
 #define MPM_VARIANT_2D_ST 0    /* D */

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <new>
 
+#include "mpm_bin.h"
 #include "mpm_kernels.h"
 #include "mpm_solver.h"
 
@@ -49,7 +50,7 @@ static int validate_params(const MpmParams* p, std::string& why)
     if (p->interaction < 0 || p->interaction > 3) { why = "interaction"; return MPM_ERR_INVALID; }
     if (p->interaction == MPM_INTERACT_MOUSE_2D && p->dim != 2) { why = "mouse interaction is 2D only"; return MPM_ERR_INVALID; }
     if (p->math_mode != MPM_MATH_STRICT && p->math_mode != MPM_MATH_FAST) { why = "math_mode"; return MPM_ERR_INVALID; }
-    if (p->kernel_path < 0 || p->kernel_path > 2) { why = "kernel_path"; return MPM_ERR_INVALID; }
+    if (p->kernel_path < 0 || p->kernel_path > 3) { why = "kernel_path"; return MPM_ERR_INVALID; }
     if (p->sort_interval < 0) { why = "sort_interval"; return MPM_ERR_INVALID; }
     if (!(p->rest_density > 0.0f)) { why = "rest_density must be > 0"; return MPM_ERR_INVALID; }
     return MPM_OK;
@@ -136,7 +137,8 @@ extern "C" int32_t mpm_default_params(int32_t variant, MpmParams* p)
 static int resolve_path(const MpmParams& p)
 {
     if (p.kernel_path != MPM_PATH_AUTO) return p.kernel_path;
-    return (p.dim == 3 && p.grid_mode == MPM_GRID_FIXED) ? MPM_PATH_TILED : MPM_PATH_REFERENCE;
+    if (p.dim == 3 && p.grid_mode == MPM_GRID_FIXED) return p.math_mode == MPM_MATH_FAST ? MPM_PATH_CELL : MPM_PATH_TILED;
+    return MPM_PATH_REFERENCE;
 }
 
 extern "C" int32_t mpm_create(const MpmParams* p, int64_t max_particles, int32_t device, MpmSolver** out)
@@ -180,11 +182,15 @@ extern "C" int32_t mpm_create(const MpmParams* p, int64_t max_particles, int32_t
         s->err = "MPM_PATH_TILED implements the 3D fixed-point grid; use MPM_PATH_AUTO or MPM_PATH_REFERENCE";
         return bail(MPM_ERR_INVALID);
     }
+    if (s->path == MPM_PATH_CELL && !(s->hp.dim == 3 && s->hp.grid_mode == MPM_GRID_FIXED && s->hp.math_mode == MPM_MATH_FAST)) {
+        s->err = "MPM_PATH_CELL implements dim = 3, MPM_GRID_FIXED, MPM_MATH_FAST; use MPM_PATH_AUTO";
+        return bail(MPM_ERR_INVALID);
+    }
     s->sort_interval = s->hp.sort_interval > 0 ? s->hp.sort_interval : 1;
-    if (s->path == MPM_PATH_TILED) {
+    if (s->path == MPM_PATH_TILED || s->path == MPM_PATH_CELL) {
         CKC(cudaMalloc(&s->part_alt, sizeof(float) * NPLANES * s->pitch));
         CKC(cudaMalloc(&s->orig_id_alt, sizeof(uint32_t) * s->pitch));
-        rc = sort_create(s);
+        rc = (s->path == MPM_PATH_TILED) ? sort_create(s) : bin_create(s);
         if (rc) return bail(rc);
     }
     CKC(cudaStreamSynchronize(s->stream));
@@ -200,6 +206,7 @@ extern "C" int32_t mpm_destroy(MpmSolver* s)
     if (s->stream) cudaStreamSynchronize(s->stream);
     comm_destroy(s);
     sort_destroy(s);
+    bin_destroy(s);
     for (cudaEvent_t ev : s->ev) cudaEventDestroy(ev);
     cudaFree(s->part); cudaFree(s->part_alt); cudaFree(s->orig_id); cudaFree(s->orig_id_alt);
     cudaFree(s->grid); cudaFree(s->positions); cudaFree(s->overflow_flag);
@@ -258,6 +265,7 @@ static void particles_changed(MpmSolver* s)
     s->sorted_valid = false;
     s->steps_since_sort = 0;
     s->fresh_particles = true;
+    if (s->bin) s->bin->next_valid = false;
     if (s->comm) comm_mark_global(s);
 }
 
@@ -439,16 +447,19 @@ static int run_phase(MpmSolver* s, int phase, size_t& cursor)
     switch (phase) {
         case PH_SORT:
             if (s->path == MPM_PATH_TILED) { int rc = sort_particles(s); if (rc) return rc; }
+            else if (s->path == MPM_PATH_CELL) { int rc = bin_particles(s); if (rc) return rc; }
             break;
         case PH_CLEAR:
             CK(cudaMemsetAsync(s->grid, 0, 16 * s->ncells, s->stream));
             break;
         case PH_P2G1:
             if (s->path == MPM_PATH_TILED) { int rc = tiled_p2g1(s); if (rc) return rc; }
+            else if (s->path == MPM_PATH_CELL) { int rc = cell_p2g1(s); if (rc) return rc; }
             else { launch_p2g1_ref(P, s->view(), s->n, s->grid, s->stream); s->launches += (s->n > 0); }
             break;
         case PH_P2G2:
             if (s->path == MPM_PATH_TILED) { int rc = tiled_p2g2(s); if (rc) return rc; }
+            else if (s->path == MPM_PATH_CELL) { int rc = cell_p2g2(s); if (rc) return rc; }
             else { launch_p2g2_ref(P, s->view(), s->n, s->grid, s->stream); s->launches += (s->n > 0); }
             break;
         case PH_UPDATE:
@@ -456,6 +467,7 @@ static int run_phase(MpmSolver* s, int phase, size_t& cursor)
             break;
         case PH_G2P:
             if (s->path == MPM_PATH_TILED) { int rc = tiled_g2p(s); if (rc) return rc; }
+            else if (s->path == MPM_PATH_CELL) { int rc = cell_g2p(s); if (rc) return rc; }
             else { launch_g2p_ref(P, s->view(), s->n, s->grid, s->orig_id, s->positions, s->stream); s->launches += (s->n > 0); }
             s->positions_valid = true;
             break;
@@ -494,7 +506,8 @@ extern "C" int32_t mpm_step(MpmSolver* s, int32_t iterations)
     }
     for (int it = 0; it < iterations; ++it) {
         int rc;
-        if (s->path == MPM_PATH_TILED && (!s->sorted_valid || s->steps_since_sort >= s->sort_interval)) {
+        const bool binned_path = s->path == MPM_PATH_TILED || s->path == MPM_PATH_CELL;
+        if (binned_path && (!s->sorted_valid || s->steps_since_sort >= s->sort_interval)) {
             if ((rc = run_phase(s, PH_SORT, cursor))) return rc;
             phases.push_back(PH_SORT);
         }
@@ -529,7 +542,7 @@ extern "C" int32_t mpm_run_phase(MpmSolver* s, int32_t phase)
     CK(cudaSetDevice(s->device));
     if (phase < 0 || phase > PH_SORT) return fail(s, MPM_ERR_INVALID, "phase must be 0..5");
     if (s->comm) return fail(s, MPM_ERR_STATE, "multi-GPU: phases cannot run one by one (halo exchanges sit between them); use mpm_step");
-    if (s->path == MPM_PATH_TILED && phase != PH_SORT && phase != PH_CLEAR && phase != PH_UPDATE && !s->sorted_valid) {
+    if ((s->path == MPM_PATH_TILED || s->path == MPM_PATH_CELL) && phase != PH_SORT && phase != PH_CLEAR && phase != PH_UPDATE && !s->sorted_valid) {
         size_t c0 = 0; bool tm = s->timing; s->timing = false;
         int rc = run_phase(s, PH_SORT, c0);
         s->timing = tm;

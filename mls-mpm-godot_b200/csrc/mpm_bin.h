@@ -1,0 +1,38 @@
+// mpm_bin.h -- state of the counting-sort binning used by the cell kernels (mpm_bin.cu, mpm_kernels_cell.cu).
+#pragma once
+#include "mpm_solver.h"
+
+namespace mpm {
+
+// words of BinState::misc (device): reset by the scan every step
+enum { BIN_N_ACTIVE = 0, BIN_WORK_P2G1, BIN_WORK_P2G2, BIN_WORK_G2P, BIN_MISC_WORDS = 8 };
+
+struct BinState {
+    int B = 8, logB = 3, cell_bits = 9;  // grid block edge (cells), bits of the cell-in-block id
+    int nbx = 0, nby = 0, nbz = 0;
+    int64_t nblocks = 0;
+    int64_t nslots = 0;        // nblocks << cell_bits: one count entry per (block, cell)
+    int64_t ntiles = 0;        // scan tiles
+    uint32_t* cnt[2] = {nullptr, nullptr};  // particle count per (block, cell); cnt[cur] describes the current layout,
+    int cur = 0;                            // cnt[cur ^ 1] is being accumulated by G2P for the next binning
+    bool next_valid = false;                // keys[] and cnt[cur ^ 1] were produced by the last G2P
+    uint32_t* cell_start = nullptr;  // [nslots + 1] exclusive scan of cnt[cur]
+    uint32_t* fill = nullptr;        // [nslots] placement cursor
+    uint32_t* keys = nullptr;        // [pitch] cell key of each particle for the NEXT binning (slot order)
+    uint32_t* src_of = nullptr;      // [pitch] gather list
+    uint32_t* tile_sums = nullptr;
+    uint32_t* active = nullptr;      // [nblocks] non-empty blocks (unordered)
+    uint32_t* misc = nullptr;        // BIN_MISC_WORDS counters
+    uint32_t* block_start = nullptr; // [nblocks + 1]
+};
+
+int bin_create(MpmSolver* s);
+void bin_destroy(MpmSolver* s);
+int bin_particles(MpmSolver* s);
+
+// cell kernels (mpm_kernels_cell.cu)
+int cell_p2g1(MpmSolver* s);
+int cell_p2g2(MpmSolver* s);
+int cell_g2p(MpmSolver* s);
+
+}  // namespace mpm

@@ -34,6 +34,8 @@ namespace mpm {
 
 int sort_create(MpmSolver* s);
 void sort_destroy(MpmSolver* s);
+int bin_create(MpmSolver* s);
+void bin_destroy(MpmSolver* s);
 
 // ================================================================ transports
 struct Transport {
@@ -280,13 +282,13 @@ void comm_fill_stats(const MpmSolver* s, MpmStats* st)
 }
 
 // ================================================================ slab set-up at upload time
-__global__ void __launch_bounds__(256) k_xhist(const float* __restrict__ px, int64_t n, int rx, unsigned long long* __restrict__ hist)
+__global__ void __launch_bounds__(256) k_xhist(ParticleView pv, int64_t n, int rx, unsigned long long* __restrict__ hist)
 {
     extern __shared__ uint32_t sh[];
     for (int k = threadIdx.x; k < rx; k += blockDim.x) sh[k] = 0;
     __syncthreads();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        int cx = __float2int_rz(px[i]);
+        int cx = __float2int_rz(pv.at(PX, i));
         cx = cx < 0 ? 0 : (cx >= rx ? rx - 1 : cx);
         atomicAdd(&sh[cx], 1u);
     }
@@ -302,7 +304,7 @@ __global__ void __launch_bounds__(256) k_filter_slab(ParticleView src, ParticleV
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool keep = false;
     if (i < n) {
-        const int cx = __float2int_rz(src.plane(PX)[i]);
+        const int cx = __float2int_rz(src.at(PX, i));
         keep = cx >= x0 && cx < x1;
     }
     const unsigned m = __ballot_sync(0xffffffffu, keep);
@@ -314,7 +316,7 @@ __global__ void __launch_bounds__(256) k_filter_slab(ParticleView src, ParticleV
     if (!keep) return;
     const uint32_t d = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
 #pragma unroll
-    for (int k = 0; k < NPLANES; ++k) dst.plane(k)[d] = src.plane(k)[i];
+    for (int k = 0; k < NPLANES; ++k) dst.at(k, d) = src.at(k, i);
     id_dst[d] = id_src[i];
 }
 
@@ -357,7 +359,7 @@ int comm_partition(MpmSolver* s)
     CKM(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * rx, s->stream));
     if (n_global > 0) {
         const int blocks = (int)std::min<int64_t>((n_global + 255) / 256, 148 * 8);
-        k_xhist<<<blocks, 256, sizeof(uint32_t) * rx, s->stream>>>(s->view().plane(PX), n_global, rx, d_hist);
+        k_xhist<<<blocks, 256, sizeof(uint32_t) * rx, s->stream>>>(s->view(), n_global, rx, d_hist);
         s->launches += 1;
     }
     std::vector<int64_t> hist(rx);
@@ -388,6 +390,10 @@ int comm_partition(MpmSolver* s)
     if (s->path == MPM_PATH_TILED) {  // block grid follows the slab
         sort_destroy(s);
         int rc = sort_create(s);
+        if (rc) return rc;
+    } else if (s->path == MPM_PATH_CELL) {
+        bin_destroy(s);
+        int rc = bin_create(s);
         if (rc) return rc;
     }
     // 3. keep own particles
@@ -473,10 +479,10 @@ __device__ __forceinline__ int mig_side(const MigGeom& g, float px, uint32_t* ba
     return -1;
 }
 
-__global__ void __launch_bounds__(256) k_mig_count(MigGeom g, const float* __restrict__ px, int64_t n, uint32_t* __restrict__ cnt)
+__global__ void __launch_bounds__(256) k_mig_count(MigGeom g, ParticleView pv, int64_t n, uint32_t* __restrict__ cnt)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int side = (i < n) ? mig_side(g, px[i], cnt + 8) : -1;
+    const int side = (i < n) ? mig_side(g, pv.at(PX, i), cnt + 8) : -1;
     const unsigned mL = __ballot_sync(0xffffffffu, side == 0), mR = __ballot_sync(0xffffffffu, side == 1);
     if ((threadIdx.x & 31) == 0) {
         if (mL) atomicAdd(cnt + 0, (uint32_t)__popc(mL));
@@ -492,7 +498,7 @@ __global__ void __launch_bounds__(256) k_mig_pack(MigGeom g, ParticleView pv, co
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t dummy;
-    const int side = mig_side(g, pv.plane(PX)[i], &dummy);
+    const int side = mig_side(g, pv.at(PX, i), &dummy);
     if (side < 0) {
         if (i >= n_stay) fillers[atomicAdd(cnt + 5, 1u)] = (uint32_t)i;
         return;
@@ -502,7 +508,7 @@ __global__ void __launch_bounds__(256) k_mig_pack(MigGeom g, ParticleView pv, co
     const uint32_t stride = side == 0 ? nL : nR;
     const uint32_t slot = atomicAdd(cnt + 6 + side, 1u);
 #pragma unroll
-    for (int k = 0; k < NPLANES; ++k) out[(size_t)k * stride + slot] = __float_as_uint(pv.plane(k)[i]);
+    for (int k = 0; k < NPLANES; ++k) out[(size_t)k * stride + slot] = __float_as_uint(pv.at(k, i));
     out[(size_t)NPLANES * stride + slot] = ids[i];
 }
 
@@ -513,7 +519,7 @@ __global__ void __launch_bounds__(256) k_mig_fill(ParticleView pv, uint32_t* __r
     if (j >= cnt[4]) return;
     const uint32_t dst = holes[j], src = fillers[j];
 #pragma unroll
-    for (int k = 0; k < NPLANES; ++k) pv.plane(k)[dst] = pv.plane(k)[src];
+    for (int k = 0; k < NPLANES; ++k) pv.at(k, dst) = pv.at(k, src);
     ids[dst] = ids[src];
 }
 
@@ -523,7 +529,7 @@ __global__ void __launch_bounds__(256) k_mig_unpack(ParticleView pv, uint32_t* _
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= count) return;
 #pragma unroll
-    for (int k = 0; k < NPLANES; ++k) pv.plane(k)[dst_off + j] = __uint_as_float(rec[(size_t)k * count + j]);
+    for (int k = 0; k < NPLANES; ++k) pv.at(k, dst_off + j) = __uint_as_float(rec[(size_t)k * count + j]);
     ids[dst_off + j] = rec[(size_t)NPLANES * count + j];
 }
 
@@ -536,7 +542,7 @@ int comm_migrate(MpmSolver* s)
     MigGeom g{c->x0, c->x1, hasL ? c->cuts[c->rank - 1] : c->x0, hasR ? c->cuts[c->rank + 2] : c->x1};
     CKM(cudaMemsetAsync(c->d_cnt, 0, 16 * sizeof(uint32_t), s->stream));
     const unsigned nb = (unsigned)((n + 255) / 256);
-    if (n > 0) { k_mig_count<<<nb, 256, 0, s->stream>>>(g, s->view().plane(PX), n, c->d_cnt); s->launches += 1; }
+    if (n > 0) { k_mig_count<<<nb, 256, 0, s->stream>>>(g, s->view(), n, c->d_cnt); s->launches += 1; }
     // counts: mine leaving left -> the left rank's "arriving from right" (d_cnt[3] there), and vice versa
     int rc = c->tr->exchange(c->d_cnt + 0, hasL ? 4 : 0, c->d_cnt + 2, hasL ? 4 : 0, c->d_cnt + 1, hasR ? 4 : 0, c->d_cnt + 3, hasR ? 4 : 0,
                              s->stream, s->err);

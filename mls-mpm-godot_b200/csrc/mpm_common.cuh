@@ -2,9 +2,13 @@
 // by every kernel of libmpm_b200.so.
 //
 // Layout in HBM
-//   particles : SoA planes of `pitch` floats inside one allocation (pitch % 32 == 0 so every plane starts
-//               on a 128-B line): planes 0-2 pos, 3-5 vel, 6 mass, 7-15 C column-major (7-9 = Basis.X).
-//               One warp reads 128 contiguous bytes per plane -> every access is a full-line transaction.
+//   particles : array-of-structures-of-arrays.  Slots are grouped by 32; a group is 16 "planes" of 32 floats
+//               (2 KB, contiguous): planes 0-2 pos, 3-5 vel, 6 mass, 7-15 C column-major (7-9 = Basis.X).
+//               Field k of slot i lives at  (i / 32) * 512 + k * 32 + (i % 32).  A warp reading field k of 32
+//               consecutive slots still reads one (or two) full 128-B lines, exactly as with plain SoA planes,
+//               but all 16 fields of a slot sit at CONSTANT offsets (k * 128 B) from one address: a kernel
+//               computes one pointer per particle and the other 15 accesses use immediate offsets (the
+//               per-plane 64-bit address arithmetic was ~10 % of the issued instructions with plain planes).
 //   grid      : array of 16-B cells (vel_x, vel_y, vel_z, mass) in the reference's index order
 //               x*Ry*Rz + y*Rz + z (MLSMPM3DFluidMultithread.cs:282), int32 x 1e7 or float.
 //               A multi-GPU rank stores only its x-slab: local plane lx = x - gx0, nxl planes.
@@ -15,6 +19,7 @@
 namespace mpm {
 
 enum Plane { PX = 0, PY, PZ, VX, VY, VZ, PM, C0, C1, C2, C3, C4, C5, C6, C7, C8, NPLANES };
+static_assert(NPLANES == 16, "the group layout below assumes 16 fields");
 
 struct DevParams {
     int dim;
@@ -32,10 +37,15 @@ struct DevParams {
     int overflow_check;
 };
 
+constexpr int GROUP = 32;                 // slots per group
+constexpr int GROUP_FLOATS = GROUP * 16;  // floats per group (16 planes)
+
 struct ParticleView {
     float* base;
-    int64_t pitch;
-    __host__ __device__ __forceinline__ float* plane(int k) const { return base + (int64_t)k * pitch; }
+    int64_t pitch;  // capacity in slots (multiple of 128)
+    // pointer to field 0 of slot i; field k is rec(i)[k * GROUP]
+    __host__ __device__ __forceinline__ float* rec(int64_t i) const { return base + ((i >> 5) << 9) + (i & 31); }
+    __host__ __device__ __forceinline__ float& at(int k, int64_t i) const { return base[((i >> 5) << 9) + (k << 5) + (i & 31)]; }
 };
 
 // ---- strict IEEE binary32 operators: the _rn intrinsics are never contracted into FMA by nvcc, so the

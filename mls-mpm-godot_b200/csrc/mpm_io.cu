@@ -13,11 +13,11 @@ __global__ void __launch_bounds__(256) k_aos80_to_soa(const float4* __restrict__
     if (i >= n) return;
     const float4 a = aos[5 * i], b = aos[5 * i + 1], c0 = aos[5 * i + 2], c1 = aos[5 * i + 3], c2 = aos[5 * i + 4];
     const int64_t d = dst_off + i;
-    pv.plane(PX)[d] = a.x; pv.plane(PY)[d] = a.y; pv.plane(PZ)[d] = a.z;
-    pv.plane(VX)[d] = b.x; pv.plane(VY)[d] = b.y; pv.plane(VZ)[d] = b.z; pv.plane(PM)[d] = b.w;
-    pv.plane(C0)[d] = c0.x; pv.plane(C1)[d] = c0.y; pv.plane(C2)[d] = c0.z;
-    pv.plane(C3)[d] = c1.x; pv.plane(C4)[d] = c1.y; pv.plane(C5)[d] = c1.z;
-    pv.plane(C6)[d] = c2.x; pv.plane(C7)[d] = c2.y; pv.plane(C8)[d] = c2.z;
+    pv.at(PX, d) = a.x; pv.at(PY, d) = a.y; pv.at(PZ, d) = a.z;
+    pv.at(VX, d) = b.x; pv.at(VY, d) = b.y; pv.at(VZ, d) = b.z; pv.at(PM, d) = b.w;
+    pv.at(C0, d) = c0.x; pv.at(C1, d) = c0.y; pv.at(C2, d) = c0.z;
+    pv.at(C3, d) = c1.x; pv.at(C4, d) = c1.y; pv.at(C5, d) = c1.z;
+    pv.at(C6, d) = c2.x; pv.at(C7, d) = c2.y; pv.at(C8, d) = c2.z;
 }
 
 __global__ void __launch_bounds__(256) k_soa_to_aos80(ParticleView pv, const uint32_t* __restrict__ orig_id,
@@ -26,11 +26,11 @@ __global__ void __launch_bounds__(256) k_soa_to_aos80(ParticleView pv, const uin
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int64_t o = orig_id ? (int64_t)orig_id[i] : i;
-    aos[5 * o] = make_float4(pv.plane(PX)[i], pv.plane(PY)[i], pv.plane(PZ)[i], 0.0f);
-    aos[5 * o + 1] = make_float4(pv.plane(VX)[i], pv.plane(VY)[i], pv.plane(VZ)[i], pv.plane(PM)[i]);
-    aos[5 * o + 2] = make_float4(pv.plane(C0)[i], pv.plane(C1)[i], pv.plane(C2)[i], 0.0f);
-    aos[5 * o + 3] = make_float4(pv.plane(C3)[i], pv.plane(C4)[i], pv.plane(C5)[i], 0.0f);
-    aos[5 * o + 4] = make_float4(pv.plane(C6)[i], pv.plane(C7)[i], pv.plane(C8)[i], 0.0f);
+    aos[5 * o] = make_float4(pv.at(PX, i), pv.at(PY, i), pv.at(PZ, i), 0.0f);
+    aos[5 * o + 1] = make_float4(pv.at(VX, i), pv.at(VY, i), pv.at(VZ, i), pv.at(PM, i));
+    aos[5 * o + 2] = make_float4(pv.at(C0, i), pv.at(C1, i), pv.at(C2, i), 0.0f);
+    aos[5 * o + 3] = make_float4(pv.at(C3, i), pv.at(C4, i), pv.at(C5, i), 0.0f);
+    aos[5 * o + 4] = make_float4(pv.at(C6, i), pv.at(C7, i), pv.at(C8, i), 0.0f);
 }
 
 __global__ void __launch_bounds__(256) k_packed_to_soa(const float* __restrict__ pos, const float* __restrict__ vel,
@@ -42,12 +42,12 @@ __global__ void __launch_bounds__(256) k_packed_to_soa(const float* __restrict__
     const int64_t d = dst_off + i;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        pv.plane(PX + a)[d] = pos[3 * i + a];
-        pv.plane(VX + a)[d] = vel ? vel[3 * i + a] : 0.0f;
+        pv.at(PX + a, d) = pos[3 * i + a];
+        pv.at(VX + a, d) = vel ? vel[3 * i + a] : 0.0f;
     }
-    pv.plane(PM)[d] = mass ? mass[i] : 1.0f;
+    pv.at(PM, d) = mass ? mass[i] : 1.0f;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) pv.plane(C0 + k)[d] = C ? C[9 * i + k] : 0.0f;
+    for (int k = 0; k < 9; ++k) pv.at(C0 + k, d) = C ? C[9 * i + k] : 0.0f;
 }
 
 __global__ void __launch_bounds__(256) k_soa_to_packed(ParticleView pv, const uint32_t* __restrict__ orig_id,
@@ -58,13 +58,13 @@ __global__ void __launch_bounds__(256) k_soa_to_packed(ParticleView pv, const ui
     const int64_t o = orig_id ? (int64_t)orig_id[i] : i;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        if (pos) pos[3 * o + a] = pv.plane(PX + a)[i];
-        if (vel) vel[3 * o + a] = pv.plane(VX + a)[i];
+        if (pos) pos[3 * o + a] = pv.at(PX + a, i);
+        if (vel) vel[3 * o + a] = pv.at(VX + a, i);
     }
-    if (mass) mass[o] = pv.plane(PM)[i];
+    if (mass) mass[o] = pv.at(PM, i);
     if (C) {
 #pragma unroll
-        for (int k = 0; k < 9; ++k) C[9 * o + k] = pv.plane(C0 + k)[i];
+        for (int k = 0; k < 9; ++k) C[9 * o + k] = pv.at(C0 + k, i);
     }
 }
 
@@ -80,9 +80,9 @@ __global__ void __launch_bounds__(256) k_positions(ParticleView pv, const uint32
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float vx = pv.plane(VX)[i], vy = pv.plane(VY)[i], vz = pv.plane(VZ)[i];
+    const float vx = pv.at(VX, i), vy = pv.at(VY, i), vz = pv.at(VZ, i);
     const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz)));
-    positions[orig_id ? orig_id[i] : (uint32_t)i] = make_float4(pv.plane(PX)[i], pv.plane(PY)[i], pv.plane(PZ)[i], len);
+    positions[orig_id ? orig_id[i] : (uint32_t)i] = make_float4(pv.at(PX, i), pv.at(PY, i), pv.at(PZ, i), len);
 }
 
 __global__ void __launch_bounds__(256) k_lattice(const float* __restrict__ xs, int nx, const float* __restrict__ ys,
@@ -94,10 +94,10 @@ __global__ void __launch_bounds__(256) k_lattice(const float* __restrict__ xs, i
     if (i >= n) return;
     const int iz = (int)(i % nz), iy = (int)(i / nz % ny), ix = (int)(i / nz / ny);
     const int64_t d = dst_off + i;
-    pv.plane(PX)[d] = xs[ix]; pv.plane(PY)[d] = ys[iy]; pv.plane(PZ)[d] = zs[iz];
-    pv.plane(VX)[d] = 0.0f; pv.plane(VY)[d] = 0.0f; pv.plane(VZ)[d] = 0.0f; pv.plane(PM)[d] = 1.0f;
+    pv.at(PX, d) = xs[ix]; pv.at(PY, d) = ys[iy]; pv.at(PZ, d) = zs[iz];
+    pv.at(VX, d) = 0.0f; pv.at(VY, d) = 0.0f; pv.at(VZ, d) = 0.0f; pv.at(PM, d) = 1.0f;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) pv.plane(C0 + k)[d] = 0.0f;
+    for (int k = 0; k < 9; ++k) pv.at(C0 + k, d) = 0.0f;
 }
 
 static inline unsigned nb(int64_t n) { return (unsigned)((n + 255) / 256); }

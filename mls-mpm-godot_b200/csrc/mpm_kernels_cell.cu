@@ -1,0 +1,604 @@
+// mpm_kernels_cell.cu -- the cell kernels (MPM_PATH_CELL, MPM_MATH_FAST): 3D, int32 fixed-point grid.
+//
+// ncu on B200 (profiles/r1/v3_*) showed the one-thread-per-particle tiled kernels bound by per-particle
+// instruction streams that no amount of bandwidth shrinks: P2G_1 issues 108 shared-memory atomics and 108
+// float->int conversions per particle (the conversion runs on the quarter-rate XU pipe, 61-69 % busy), G2P 81
+// shared-memory loads per particle.  Here one thread owns one grid CELL and walks that cell's particles
+// (cell-binned planes, mpm_bin.cu), keeping the cell's 27-node stencil in registers:
+//   P2G_1 / P2G_2 : 108 / 81 fp32 accumulators per thread; fixed-point conversion and the shared-memory ATOMS
+//                   happen once per cell instead of once per particle.
+//   G2P           : the 27 node velocities (81 floats) are loaded from the shared-memory tile once per cell.
+// A warp = 32 consecutive cells of a block (a "chunk"); at rank r it reads the rank-r particles of its cells
+// from consecutive slots (one full 128-B line per plane when all cells are occupied).  CTAs are persistent and
+// pull non-empty grid blocks from a list with an atomic counter.  G2P also emits each particle's next cell key
+// and counts it (RED), so the next step's binning needs no separate key pass.
+//
+// Arithmetic: MPM_MATH_FAST (FMA, per-axis hoisting, sum factorisation).  Contributions are accumulated in fp32
+// and truncated to the int32 grid once per (cell, node) instead of once per (particle, node); the difference is
+// below one fixed-point unit per particle and inside the FAST tolerance stated in tests/test_parity_gpu.py.
+#include "mpm_bin.h"
+#include "mpm_kernels.h"
+#include "mpm_particle_math.cuh"
+#include "mpm_tile.cuh"
+
+namespace mpm {
+
+KeyGeom bin_key_geom(const MpmSolver* s);
+
+template <int B>
+struct CellCfg {
+    static constexpr int LOGB = (B == 8) ? 3 : 2;
+    static constexpr int NC = B * B * B;
+    static constexpr int NCHUNK = NC / 32;
+    static constexpr int THREADS = (B == 8) ? 128 : 64;
+    static constexpr int NWARP = THREADS / 32;
+};
+
+struct CellArgs {
+    const uint32_t* cnt;         // counts of the current layout
+    const uint32_t* cell_start;  // exclusive scan
+    const uint32_t* active;      // non-empty blocks
+    uint32_t* misc;              // [BIN_N_ACTIVE], work counters
+};
+
+// next non-empty grid block for this CTA, or -1
+__device__ __forceinline__ int fetch_block(const CellArgs& a, int which, int* s_b)
+{
+    __syncthreads();  // everyone is done with the previous block's shared memory
+    if (threadIdx.x == 0) {
+        const uint32_t bi = atomicAdd(&a.misc[which], 1u);
+        *s_b = (bi < a.misc[BIN_N_ACTIVE]) ? (int)a.active[bi] : -1;
+    }
+    __syncthreads();
+    return *s_b;
+}
+
+// weights and node distances of one axis for a particle known to sit in cell `fc` (as float)
+__device__ __forceinline__ void cell_axis(float p, float fc, float w[3], float d[3])
+{
+    const float cd = (p - fc) - 0.5f;
+    const float a = 0.5f - cd, b = 0.5f + cd;
+    w[0] = 0.5f * a * a;
+    w[1] = 0.75f - cd * cd;
+    w[2] = 0.5f * b * b;
+    d[0] = -1.0f - cd; d[1] = -cd; d[2] = 1.0f - cd;
+}
+
+// ---------------------------------------------------------------- walking a block's chunks, software-pipelined
+// ncu (profiles/r1/v6_*): with 168 registers per thread only 12 warps fit on an SM, and a loop that loads a particle
+// and then computes on it spends half its time in long-scoreboard stalls.  So the walk is pipelined: while the
+// particle of rank r is being processed, the one of rank r+1 (or rank 0 of the warp's next chunk) is already in
+// flight -- in registers where that is cheap (G2P: position + id), as an L1 prefetch of the 128-B lines otherwise.
+//
+// Body interface:  begin_chunk(chunk)   per-cell set-up (stencil registers / accumulators)
+//                  fetch(i)            start bringing particle slot i in (lane-private; may be predicated off)
+//                  take()              the particle fetched last becomes the current one
+//                  compute(i)          process the current particle (slot i)
+//                  end_chunk(has)      flush per-cell results
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+template <int B, class Body>
+__device__ __forceinline__ void walk_chunks(const CellArgs& a, int b, int lane, int warp, Body& body)
+{
+    using CF = CellCfg<B>;
+    const unsigned lt = (1u << lane) - 1u;
+    const uint32_t blk0 = (uint32_t)b << (3 * CF::LOGB);
+    bool have = false;  // the first particle of the coming chunk has already been fetched
+    uint32_t c_nx = a.cnt[blk0 + warp * 32 + lane];
+    uint32_t st_nx = a.cell_start[blk0 + warp * 32];
+#pragma unroll 1
+    for (int chunk = warp; chunk < CF::NCHUNK; chunk += CF::NWARP) {
+        const uint32_t c = c_nx;
+        uint32_t slot0 = st_nx;
+        c_nx = 0; st_nx = 0;
+        if (chunk + CF::NWARP < CF::NCHUNK) {
+            c_nx = a.cnt[blk0 + (chunk + CF::NWARP) * 32 + lane];
+            st_nx = a.cell_start[blk0 + (chunk + CF::NWARP) * 32];
+        }
+        unsigned m = __ballot_sync(0xffffffffu, c > 0);
+        if (!m) { have = false; continue; }
+        if (!have && c > 0) body.fetch(slot0 + __popc(m & lt));
+        have = false;
+        body.begin_chunk(chunk);
+#pragma unroll 1
+        for (uint32_t r = 0;; ++r) {
+            const bool on = r < c;
+            const uint32_t i = slot0 + __popc(m & lt);
+            const bool on1 = r + 1 < c;
+            const unsigned m1 = __ballot_sync(0xffffffffu, on1);
+            body.take();
+            if (m1) {
+                if (on1) body.fetch(slot0 + __popc(m) + __popc(m1 & lt));
+            } else {
+                const unsigned mn = __ballot_sync(0xffffffffu, c_nx > 0);
+                if (c_nx > 0) body.fetch(st_nx + __popc(mn & lt));
+                have = true;
+            }
+            if (on) body.compute(i);
+            slot0 += __popc(m);
+            m = m1;
+            if (!m) break;
+        }
+        body.end_chunk(c > 0);
+    }
+}
+
+template <int B>
+struct CellPos {  // which cell of the block this lane owns in chunk `chunk`
+    int base;
+    float fcx, fcy, fcz;
+    __device__ __forceinline__ void set(const Tile<B>& tl, int chunk, int lane)
+    {
+        constexpr int LOGB = CellCfg<B>::LOGB;
+        const int L = chunk * 32 + lane;
+        const int lx = L >> (2 * LOGB), ly = (L >> LOGB) & (B - 1), lz = L & (B - 1);
+        base = lx * Tile<B>::PX + ly * Tile<B>::PY + lz;
+        fcx = (float)(tl.ox + 1 + lx); fcy = (float)(tl.oy + 1 + ly); fcz = (float)(tl.oz + 1 + lz);
+    }
+};
+
+// ---------------------------------------------------------------- P2G_1
+template <int B>
+struct P2G1Body {
+    using TL = Tile<B>;
+    const DevParams& P;
+    const ParticleView& pv;
+    const TL& tl;
+    int (*tile)[TL::WORDS];
+    int lane;
+    CellPos<B> cp;
+    float am[27], ax[27], ay[27], az[27];
+    __device__ __forceinline__ P2G1Body(const DevParams& P_, const ParticleView& pv_, const TL& tl_, int (*tile_)[TL::WORDS], int lane_)
+        : P(P_), pv(pv_), tl(tl_), tile(tile_), lane(lane_) {}
+    __device__ __forceinline__ void begin_chunk(int chunk)
+    {
+        cp.set(tl, chunk, lane);
+#pragma unroll
+        for (int n = 0; n < 27; ++n) { am[n] = 0.0f; ax[n] = 0.0f; ay[n] = 0.0f; az[n] = 0.0f; }
+    }
+    __device__ __forceinline__ void fetch(uint32_t i)
+    {
+        const float* q = pv.rec(i);
+#pragma unroll
+        for (int k = 0; k < NPLANES; ++k) prefetch_l1(q + k * GROUP);
+    }
+    __device__ __forceinline__ void take() {}
+    __device__ __forceinline__ void compute(uint32_t i)
+    {
+        const float* q = pv.rec(i);
+        const float px = q[PX * GROUP], py = q[PY * GROUP], pz = q[PZ * GROUP];
+        const float vx = q[VX * GROUP], vy = q[VY * GROUP], vz = q[VZ * GROUP];
+        const float ms = q[PM * GROUP] * P.fmult;  // mass in fixed-point units
+        float cm[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) cm[k] = q[(C0 + k) * GROUP];
+        float wx[3], wy[3], wz[3], dx[3], dy[3], dz[3];
+        cell_axis(px, cp.fcx, wx, dx); cell_axis(py, cp.fcy, wy, dy); cell_axis(pz, cp.fcz, wz, dz);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) wx[k] *= ms;
+#pragma unroll
+        for (int gx = 0; gx < 3; ++gx) {
+            const float qx0 = fmaf(cm[0], dx[gx], vx), qy0 = fmaf(cm[1], dx[gx], vy), qz0 = fmaf(cm[2], dx[gx], vz);
+#pragma unroll
+            for (int gy = 0; gy < 3; ++gy) {
+                const float qx1 = fmaf(cm[3], dy[gy], qx0), qy1 = fmaf(cm[4], dy[gy], qy0), qz1 = fmaf(cm[5], dy[gy], qz0);
+                const float wxy = wx[gx] * wy[gy];
+#pragma unroll
+                for (int gz = 0; gz < 3; ++gz) {
+                    const int n = (gx * 3 + gy) * 3 + gz;
+                    const float mc = wxy * wz[gz];
+                    am[n] += mc;
+                    ax[n] = fmaf(mc, fmaf(cm[6], dz[gz], qx1), ax[n]);
+                    ay[n] = fmaf(mc, fmaf(cm[7], dz[gz], qy1), ay[n]);
+                    az[n] = fmaf(mc, fmaf(cm[8], dz[gz], qz1), az[n]);
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ void end_chunk(bool has)
+    {
+        if (!has) return;
+#pragma unroll
+        for (int gx = 0; gx < 3; ++gx)
+#pragma unroll
+            for (int gy = 0; gy < 3; ++gy)
+#pragma unroll
+                for (int gz = 0; gz < 3; ++gz) {
+                    const int n = (gx * 3 + gy) * 3 + gz;
+                    const int idx = cp.base + gx * TL::PX + gy * TL::PY + gz;
+                    atomicAdd(&tile[3][idx], __float2int_rz(am[n]));
+                    atomicAdd(&tile[0][idx], __float2int_rz(ax[n]));
+                    atomicAdd(&tile[1][idx], __float2int_rz(ay[n]));
+                    atomicAdd(&tile[2][idx], __float2int_rz(az[n]));
+                }
+    }
+};
+
+template <int B>
+__global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? 3 : 6) k_p2g1_cell(DevParams P, TileGeom g, ParticleView pv, CellArgs a,
+                                                                                     int* __restrict__ grid)
+{
+    using TL = Tile<B>;
+    using CF = CellCfg<B>;
+    __shared__ int tile[4][TL::WORDS];
+    __shared__ int s_b;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (;;) {
+        const int b = fetch_block(a, BIN_WORK_P2G1, &s_b);
+        if (b < 0) break;
+        TL tl; tl.init(g, b);
+        for (int k = threadIdx.x; k < 4 * TL::WORDS; k += CF::THREADS) (&tile[0][0])[k] = 0;
+        __syncthreads();
+        P2G1Body<B> body(P, pv, tl, tile, lane);
+        walk_chunks<B>(a, b, lane, warp, body);
+        __syncthreads();
+        for (int k = threadIdx.x; k < TL::NODES; k += CF::THREADS) {
+            int idx; int64_t ci;
+            const bool ok = tl.node(P, k, idx, ci);
+            const int vx = tile[0][idx], vy = tile[1][idx], vz = tile[2][idx], m = tile[3][idx];
+            if (!ok || (vx | vy | vz | m) == 0) continue;
+            int* cc = grid + 4 * ci;
+            if (vx) atomicAdd(cc + 0, vx);
+            if (vy) atomicAdd(cc + 1, vy);
+            if (vz) atomicAdd(cc + 2, vz);
+            if (m) atomicAdd(cc + 3, m);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- P2G_2
+__device__ __forceinline__ float cell_eos_pow(float x, const DevParams& P)
+{
+    if (P.eos_pi > 0) {
+        float r = x;
+        for (int k = 1; k < P.eos_pi; ++k) r *= x;
+        return r;
+    }
+    return __powf(x, P.eos_p);
+}
+
+template <int B>
+struct P2G2Body {
+    using TL = Tile<B>;
+    const DevParams& P;
+    const ParticleView& pv;
+    const TL& tl;
+    int (*tile)[TL::WORDS];
+    const float* tmass;
+    int lane;
+    float inv_rest;
+    CellPos<B> cp;
+    float gm[27], ax[27], ay[27], az[27];
+    __device__ __forceinline__ P2G2Body(const DevParams& P_, const ParticleView& pv_, const TL& tl_, int (*tile_)[TL::WORDS], const float* tmass_,
+                                        int lane_)
+        : P(P_), pv(pv_), tl(tl_), tile(tile_), tmass(tmass_), lane(lane_), inv_rest(1.0f / P_.rest_density) {}
+    __device__ __forceinline__ void begin_chunk(int chunk)
+    {
+        cp.set(tl, chunk, lane);
+#pragma unroll
+        for (int gx = 0; gx < 3; ++gx)
+#pragma unroll
+            for (int gy = 0; gy < 3; ++gy)
+#pragma unroll
+                for (int gz = 0; gz < 3; ++gz) gm[(gx * 3 + gy) * 3 + gz] = tmass[cp.base + gx * TL::PX + gy * TL::PY + gz];
+#pragma unroll
+        for (int n = 0; n < 27; ++n) { ax[n] = 0.0f; ay[n] = 0.0f; az[n] = 0.0f; }
+    }
+    __device__ __forceinline__ void fetch(uint32_t i)
+    {
+        const float* q = pv.rec(i);
+        prefetch_l1(q + PX * GROUP); prefetch_l1(q + PY * GROUP); prefetch_l1(q + PZ * GROUP); prefetch_l1(q + PM * GROUP);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) prefetch_l1(q + (C0 + k) * GROUP);
+    }
+    __device__ __forceinline__ void take() {}
+    __device__ __forceinline__ void compute(uint32_t i)
+    {
+        const float* q = pv.rec(i);
+        const float px = q[PX * GROUP], py = q[PY * GROUP], pz = q[PZ * GROUP], mass = q[PM * GROUP];
+        float cm[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) cm[k] = q[(C0 + k) * GROUP];
+        float wx[3], wy[3], wz[3], dx[3], dy[3], dz[3];
+        cell_axis(px, cp.fcx, wx, dx); cell_axis(py, cp.fcy, wy, dy); cell_axis(pz, cp.fcz, wz, dz);
+        float density = 0.0f;
+#pragma unroll
+        for (int gx = 0; gx < 3; ++gx) {
+            float sx = 0.0f;
+#pragma unroll
+            for (int gy = 0; gy < 3; ++gy) {
+                const int n = (gx * 3 + gy) * 3;
+                const float row = fmaf(gm[n + 2], wz[2], fmaf(gm[n + 1], wz[1], gm[n] * wz[0]));
+                sx = fmaf(row, wy[gy], sx);
+            }
+            density = fmaf(sx, wx[gx], density);
+        }
+        // eq_16_term_0 = -volume * 4 * stress * dt (symmetric), pre-scaled to fixed-point units
+        const float volume = __fdividef(mass, density);
+        const float pr = P.eos_k * (cell_eos_pow(density * inv_rest, P) - 1.0f);
+        const float pressure = fmaxf(-0.1f, pr);
+        const float s = -volume * 4.0f * P.dt * P.fmult;
+        const float mu = P.visc;
+        const float e00 = s * fmaf(2.0f * mu, cm[0], -pressure), e11 = s * fmaf(2.0f * mu, cm[4], -pressure),
+                    e22 = s * fmaf(2.0f * mu, cm[8], -pressure);
+        const float e01 = s * mu * (cm[1] + cm[3]), e02 = s * mu * (cm[2] + cm[6]), e12 = s * mu * (cm[5] + cm[7]);
+#pragma unroll
+        for (int gx = 0; gx < 3; ++gx) {
+            const float fx0 = e00 * dx[gx], fy0 = e01 * dx[gx], fz0 = e02 * dx[gx];
+#pragma unroll
+            for (int gy = 0; gy < 3; ++gy) {
+                const float fx1 = fmaf(e01, dy[gy], fx0), fy1 = fmaf(e11, dy[gy], fy0), fz1 = fmaf(e12, dy[gy], fz0);
+                const float wxy = wx[gx] * wy[gy];
+#pragma unroll
+                for (int gz = 0; gz < 3; ++gz) {
+                    const int n = (gx * 3 + gy) * 3 + gz;
+                    const float w = wxy * wz[gz];
+                    ax[n] = fmaf(w, fmaf(e02, dz[gz], fx1), ax[n]);
+                    ay[n] = fmaf(w, fmaf(e12, dz[gz], fy1), ay[n]);
+                    az[n] = fmaf(w, fmaf(e22, dz[gz], fz1), az[n]);
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ void end_chunk(bool has)
+    {
+        if (!has) return;
+#pragma unroll
+        for (int gx = 0; gx < 3; ++gx)
+#pragma unroll
+            for (int gy = 0; gy < 3; ++gy)
+#pragma unroll
+                for (int gz = 0; gz < 3; ++gz) {
+                    const int n = (gx * 3 + gy) * 3 + gz;
+                    const int idx = cp.base + gx * TL::PX + gy * TL::PY + gz;
+                    atomicAdd(&tile[0][idx], __float2int_rz(ax[n]));
+                    atomicAdd(&tile[1][idx], __float2int_rz(ay[n]));
+                    atomicAdd(&tile[2][idx], __float2int_rz(az[n]));
+                }
+    }
+};
+
+template <int B>
+__global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? 3 : 6) k_p2g2_cell(DevParams P, TileGeom g, ParticleView pv, CellArgs a,
+                                                                                     int* __restrict__ grid)
+{
+    using TL = Tile<B>;
+    using CF = CellCfg<B>;
+    __shared__ int tile[3][TL::WORDS];
+    __shared__ float tmass[TL::WORDS];
+    __shared__ int s_b;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float inv_mult = 1.0f / P.fmult;
+    for (;;) {
+        const int b = fetch_block(a, BIN_WORK_P2G2, &s_b);
+        if (b < 0) break;
+        TL tl; tl.init(g, b);
+        for (int k = threadIdx.x; k < 3 * TL::WORDS; k += CF::THREADS) (&tile[0][0])[k] = 0;
+        for (int k = threadIdx.x; k < TL::NODES; k += CF::THREADS) {
+            int idx; int64_t ci;
+            const bool ok = tl.node(P, k, idx, ci);
+            tmass[idx] = ok ? (float)grid[4 * ci + 3] * inv_mult : 0.0f;
+        }
+        __syncthreads();
+        P2G2Body<B> body(P, pv, tl, tile, tmass, lane);
+        walk_chunks<B>(a, b, lane, warp, body);
+        __syncthreads();
+        for (int k = threadIdx.x; k < TL::NODES; k += CF::THREADS) {
+            int idx; int64_t ci;
+            const bool ok = tl.node(P, k, idx, ci);
+            const int vx = tile[0][idx], vy = tile[1][idx], vz = tile[2][idx];
+            if (!ok || (vx | vy | vz) == 0) continue;
+            int* cc = grid + 4 * ci;
+            if (vx) atomicAdd(cc + 0, vx);
+            if (vy) atomicAdd(cc + 1, vy);
+            if (vz) atomicAdd(cc + 2, vz);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- G2P
+template <int B>
+struct G2PBody {
+    using TL = Tile<B>;
+    const DevParams& P;
+    const ParticleView& pv;
+    const TL& tl;
+    const float (*tv)[TL::WORDS];
+    const uint32_t* orig_id;
+    float4* positions;
+    const KeyGeom& kg;
+    uint32_t nslots;
+    uint32_t* keys;
+    uint32_t* cnt_next;
+    int lane;
+    CellPos<B> cp;
+    float gvx[27], gvy[27], gvz[27];
+    float nx_[3], cur[3];  // next / current particle position
+    uint32_t nid, cid;     // and original index
+    __device__ __forceinline__ G2PBody(const DevParams& P_, const ParticleView& pv_, const TL& tl_, const float (*tv_)[TL::WORDS],
+                                       const uint32_t* orig_id_, float4* positions_, const KeyGeom& kg_, uint32_t nslots_, uint32_t* keys_,
+                                       uint32_t* cnt_next_, int lane_)
+        : P(P_), pv(pv_), tl(tl_), tv(tv_), orig_id(orig_id_), positions(positions_), kg(kg_), nslots(nslots_), keys(keys_),
+          cnt_next(cnt_next_), lane(lane_) {}
+    __device__ __forceinline__ void begin_chunk(int chunk)
+    {
+        cp.set(tl, chunk, lane);
+#pragma unroll
+        for (int gx = 0; gx < 3; ++gx)
+#pragma unroll
+            for (int gy = 0; gy < 3; ++gy)
+#pragma unroll
+                for (int gz = 0; gz < 3; ++gz) {
+                    const int n = (gx * 3 + gy) * 3 + gz, idx = cp.base + gx * TL::PX + gy * TL::PY + gz;
+                    gvx[n] = tv[0][idx]; gvy[n] = tv[1][idx]; gvz[n] = tv[2][idx];
+                }
+    }
+    __device__ __forceinline__ void fetch(uint32_t i)
+    {
+        nx_[0] = pv.at(PX, i); nx_[1] = pv.at(PY, i); nx_[2] = pv.at(PZ, i);
+        nid = orig_id[i];
+    }
+    __device__ __forceinline__ void take() { cur[0] = nx_[0]; cur[1] = nx_[1]; cur[2] = nx_[2]; cid = nid; }
+    __device__ __forceinline__ void compute(uint32_t i)
+    {
+        const float old[3] = {cur[0], cur[1], cur[2]};
+        float wx[3], wy[3], wz[3], dx[3], dy[3], dz[3];
+        cell_axis(old[0], cp.fcx, wx, dx); cell_axis(old[1], cp.fcy, wy, dy); cell_axis(old[2], cp.fcz, wz, dz);
+        const float wdz[3] = {wz[0] * dz[0], wz[1] * dz[1], wz[2] * dz[2]};
+        float v[3] = {0, 0, 0};
+        float Bx[3] = {0, 0, 0}, By[3] = {0, 0, 0}, Bz[3] = {0, 0, 0};  // columns of B = sum w * v (x) d
+#pragma unroll
+        for (int gx = 0; gx < 3; ++gx) {
+            float S[3] = {0, 0, 0}, Ty[3] = {0, 0, 0}, Tz[3] = {0, 0, 0};
+#pragma unroll
+            for (int gy = 0; gy < 3; ++gy) {
+                const int n = (gx * 3 + gy) * 3;
+                float s[3], t[3];
+                s[0] = fmaf(wz[2], gvx[n + 2], fmaf(wz[1], gvx[n + 1], wz[0] * gvx[n]));
+                s[1] = fmaf(wz[2], gvy[n + 2], fmaf(wz[1], gvy[n + 1], wz[0] * gvy[n]));
+                s[2] = fmaf(wz[2], gvz[n + 2], fmaf(wz[1], gvz[n + 1], wz[0] * gvz[n]));
+                t[0] = fmaf(wdz[2], gvx[n + 2], fmaf(wdz[1], gvx[n + 1], wdz[0] * gvx[n]));
+                t[1] = fmaf(wdz[2], gvy[n + 2], fmaf(wdz[1], gvy[n + 1], wdz[0] * gvy[n]));
+                t[2] = fmaf(wdz[2], gvz[n + 2], fmaf(wdz[1], gvz[n + 1], wdz[0] * gvz[n]));
+                const float wyd = wy[gy] * dy[gy];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    S[k] = fmaf(wy[gy], s[k], S[k]);
+                    Ty[k] = fmaf(wyd, s[k], Ty[k]);
+                    Tz[k] = fmaf(wy[gy], t[k], Tz[k]);
+                }
+            }
+            const float wxd = wx[gx] * dx[gx];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                v[k] = fmaf(wx[gx], S[k], v[k]);
+                Bx[k] = fmaf(wxd, S[k], Bx[k]);
+                By[k] = fmaf(wx[gx], Ty[k], By[k]);
+                Bz[k] = fmaf(wx[gx], Tz[k], Bz[k]);
+            }
+        }
+        const float Bm[9] = {Bx[0], Bx[1], Bx[2], By[0], By[1], By[2], Bz[0], Bz[1], Bz[2]};
+        float np[3], cm[9];
+        g2p_finish<3>(P, old, Bm, v, np, cm);
+        float* q = pv.rec(i);
+        q[PX * GROUP] = np[0]; q[PY * GROUP] = np[1]; q[PZ * GROUP] = np[2];
+        q[VX * GROUP] = v[0]; q[VY * GROUP] = v[1]; q[VZ * GROUP] = v[2];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) q[(C0 + k) * GROUP] = cm[k];
+        const float len = sqrtf(fmaf(v[0], v[0], fmaf(v[1], v[1], v[2] * v[2])));
+        positions[cid] = make_float4(np[0], np[1], np[2], len);
+        if (cnt_next) {  // bin key of the NEW position for the next step (single-GPU: the slab is the domain)
+            uint32_t k = cell_key(kg, __float2int_rz(np[0]), __float2int_rz(np[1]), __float2int_rz(np[2]));
+            k = k < nslots ? k : nslots - 1;
+            keys[i] = k;
+            atomicAdd(&cnt_next[k], 1u);
+        }
+    }
+    __device__ __forceinline__ void end_chunk(bool) {}
+};
+
+template <int B>
+__global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? 3 : 6) k_g2p_cell(DevParams P, TileGeom g, ParticleView pv, CellArgs a,
+                                                                                    const int4* __restrict__ grid, const uint32_t* __restrict__ orig_id,
+                                                                                    float4* __restrict__ positions, KeyGeom kg, uint32_t nslots,
+                                                                                    uint32_t* __restrict__ keys, uint32_t* __restrict__ cnt_next)
+{
+    using TL = Tile<B>;
+    using CF = CellCfg<B>;
+    __shared__ float tv[3][TL::WORDS];
+    __shared__ int s_b;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float inv_mult = 1.0f / P.fmult;
+    for (;;) {
+        const int b = fetch_block(a, BIN_WORK_G2P, &s_b);
+        if (b < 0) break;
+        TL tl; tl.init(g, b);
+        for (int k = threadIdx.x; k < TL::NODES; k += CF::THREADS) {
+            int idx; int64_t ci;
+            float vx = 0.0f, vy = 0.0f, vz = 0.0f;
+            if (tl.node(P, k, idx, ci)) {
+                const int4 c = grid[ci];
+                vx = (float)c.x * inv_mult; vy = (float)c.y * inv_mult; vz = (float)c.z * inv_mult;
+            }
+            tv[0][idx] = vx; tv[1][idx] = vy; tv[2][idx] = vz;
+        }
+        __syncthreads();
+        G2PBody<B> body(P, pv, tl, tv, orig_id, positions, kg, nslots, keys, cnt_next, lane);
+        walk_chunks<B>(a, b, lane, warp, body);
+    }
+}
+
+// ---------------------------------------------------------------- host side
+static int check_cell_supported(MpmSolver* s)
+{
+    if (s->dp.dim != 3 || s->dp.grid_mode != MPM_GRID_FIXED || s->hp.math_mode != MPM_MATH_FAST) {
+        s->err = "MPM_PATH_CELL implements dim = 3, MPM_GRID_FIXED, MPM_MATH_FAST";
+        return MPM_ERR_INVALID;
+    }
+    if (!s->sorted_valid) { s->err = "cell kernels need freshly binned particles"; return MPM_ERR_STATE; }
+    return MPM_OK;
+}
+
+template <typename K>
+static unsigned persistent_grid(K kernel, int threads, int64_t nblocks)
+{
+    int per_sm = 1, dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return (unsigned)std::max<int64_t>(1, std::min<int64_t>(nblocks, (int64_t)per_sm * sms));
+}
+
+#define LAUNCH_CELL(KERNEL, ...)                                                                                          \
+    do {                                                                                                                  \
+        BinState* st = s->bin;                                                                                            \
+        TileGeom g{st->nby, st->nbz, s->dp.gx0 + (s->comm ? 1 : 0)};                                                      \
+        CellArgs a{st->cnt[st->cur], st->cell_start, st->active, st->misc};                                               \
+        if (st->B == 8) {                                                                                                 \
+            static unsigned grid8 = 0;                                                                                    \
+            if (!grid8) grid8 = persistent_grid(KERNEL<8>, CellCfg<8>::THREADS, 1 << 30);                                 \
+            KERNEL<8><<<(unsigned)std::min<int64_t>(grid8, st->nblocks), CellCfg<8>::THREADS, 0, s->stream>>>(s->dp, g, s->view(), a, __VA_ARGS__); \
+        } else {                                                                                                          \
+            static unsigned grid4 = 0;                                                                                    \
+            if (!grid4) grid4 = persistent_grid(KERNEL<4>, CellCfg<4>::THREADS, 1 << 30);                                 \
+            KERNEL<4><<<(unsigned)std::min<int64_t>(grid4, st->nblocks), CellCfg<4>::THREADS, 0, s->stream>>>(s->dp, g, s->view(), a, __VA_ARGS__); \
+        }                                                                                                                 \
+        s->launches += 1;                                                                                                 \
+    } while (0)
+
+int cell_p2g1(MpmSolver* s)
+{
+    int rc = check_cell_supported(s);
+    if (rc) return rc;
+    if (s->n == 0) return MPM_OK;
+    LAUNCH_CELL(k_p2g1_cell, reinterpret_cast<int*>(s->grid));
+    return MPM_OK;
+}
+
+int cell_p2g2(MpmSolver* s)
+{
+    int rc = check_cell_supported(s);
+    if (rc) return rc;
+    if (s->n == 0) return MPM_OK;
+    LAUNCH_CELL(k_p2g2_cell, reinterpret_cast<int*>(s->grid));
+    return MPM_OK;
+}
+
+int cell_g2p(MpmSolver* s)
+{
+    int rc = check_cell_supported(s);
+    if (rc) return rc;
+    if (s->n == 0) return MPM_OK;
+    BinState* bs = s->bin;
+    // multi-GPU: particles may leave the slab and arrivals are appended afterwards, so keys are recomputed after
+    // the migration instead (bin_particles sees next_valid == false)
+    const bool fuse = (s->comm == nullptr);
+    uint32_t* cnt_next = fuse ? bs->cnt[bs->cur ^ 1] : nullptr;
+    LAUNCH_CELL(k_g2p_cell, reinterpret_cast<const int4*>(s->grid), s->orig_id, s->positions, bin_key_geom(s), (uint32_t)bs->nslots, bs->keys,
+                cnt_next);
+    bs->next_valid = fuse;
+    s->sorted_valid = false;  // positions moved: the layout is exact for one step only
+    return MPM_OK;
+}
+
+}  // namespace mpm

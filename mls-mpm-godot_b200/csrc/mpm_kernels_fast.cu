@@ -50,12 +50,12 @@ __global__ void __launch_bounds__(TILED_THREADS) k_p2g1_fast(DevParams P, TileGe
     for (int k = threadIdx.x; k < 4 * TL::WORDS; k += TILED_THREADS) (&tile[0][0])[k] = 0;
     __syncthreads();
     for (uint32_t i = s0 + threadIdx.x; i < s1; i += TILED_THREADS) {
-        const float px = pv.plane(PX)[i], py = pv.plane(PY)[i], pz = pv.plane(PZ)[i];
-        const float vx = pv.plane(VX)[i], vy = pv.plane(VY)[i], vz = pv.plane(VZ)[i];
-        const float ms = pv.plane(PM)[i] * P.fmult;  // mass in fixed-point units
+        const float px = pv.at(PX, i), py = pv.at(PY, i), pz = pv.at(PZ, i);
+        const float vx = pv.at(VX, i), vy = pv.at(VY, i), vz = pv.at(VZ, i);
+        const float ms = pv.at(PM, i) * P.fmult;  // mass in fixed-point units
         float c[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) c[k] = pv.plane(C0 + k)[i];
+        for (int k = 0; k < 9; ++k) c[k] = pv.at(C0 + k, i);
         float wx[3], wy[3], wz[3], dx[3], dy[3], dz[3];
         const int cx = fast_axis(px, wx, dx), cy = fast_axis(py, wy, dy), cz = fast_axis(pz, wz, dz);
         int base;
@@ -138,10 +138,10 @@ __global__ void __launch_bounds__(TILED_THREADS) k_p2g2_fast(DevParams P, TileGe
     __syncthreads();
     const float inv_rest = 1.0f / P.rest_density;
     for (uint32_t i = s0 + threadIdx.x; i < s1; i += TILED_THREADS) {
-        const float px = pv.plane(PX)[i], py = pv.plane(PY)[i], pz = pv.plane(PZ)[i], m = pv.plane(PM)[i];
+        const float px = pv.at(PX, i), py = pv.at(PY, i), pz = pv.at(PZ, i), m = pv.at(PM, i);
         float c[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) c[k] = pv.plane(C0 + k)[i];
+        for (int k = 0; k < 9; ++k) c[k] = pv.at(C0 + k, i);
         float wx[3], wy[3], wz[3], dx[3], dy[3], dz[3];
         const int cx = fast_axis(px, wx, dx), cy = fast_axis(py, wy, dy), cz = fast_axis(pz, wz, dz);
         int base;
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(TILED_THREADS) k_g2p_fast(DevParams P, TileGeo
     }
     __syncthreads();
     for (uint32_t i = s0 + threadIdx.x; i < s1; i += TILED_THREADS) {
-        const float old[3] = {pv.plane(PX)[i], pv.plane(PY)[i], pv.plane(PZ)[i]};
+        const float old[3] = {pv.at(PX, i), pv.at(PY, i), pv.at(PZ, i)};
         float wx[3], wy[3], wz[3], dx[3], dy[3], dz[3];
         const int cx = fast_axis(old[0], wx, dx), cy = fast_axis(old[1], wy, dy), cz = fast_axis(old[2], wz, dz);
         int base;
@@ -291,10 +291,10 @@ __global__ void __launch_bounds__(TILED_THREADS) k_g2p_fast(DevParams P, TileGeo
         const float Bm[9] = {Bx[0], Bx[1], Bx[2], By[0], By[1], By[2], Bz[0], Bz[1], Bz[2]};
         float np[3], c[9];
         g2p_finish<3>(P, old, Bm, v, np, c);
-        pv.plane(PX)[i] = np[0]; pv.plane(PY)[i] = np[1]; pv.plane(PZ)[i] = np[2];
-        pv.plane(VX)[i] = v[0]; pv.plane(VY)[i] = v[1]; pv.plane(VZ)[i] = v[2];
+        pv.at(PX, i) = np[0]; pv.at(PY, i) = np[1]; pv.at(PZ, i) = np[2];
+        pv.at(VX, i) = v[0]; pv.at(VY, i) = v[1]; pv.at(VZ, i) = v[2];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) pv.plane(C0 + k)[i] = c[k];
+        for (int k = 0; k < 9; ++k) pv.at(C0 + k, i) = c[k];
         const float len = sqrtf(fmaf(v[0], v[0], fmaf(v[1], v[1], v[2] * v[2])));
         positions[orig_id[i]] = make_float4(np[0], np[1], np[2], len);
     }

@@ -22,11 +22,11 @@ __global__ void __launch_bounds__(256) k_p2g1_ref(DevParams P, ParticleView pv, 
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     ParticleIn p;
-    p.px = pv.plane(PX)[i]; p.py = pv.plane(PY)[i]; p.pz = pv.plane(PZ)[i];
-    p.vx = pv.plane(VX)[i]; p.vy = pv.plane(VY)[i]; p.vz = pv.plane(VZ)[i];
-    p.m = pv.plane(PM)[i];
+    p.px = pv.at(PX, i); p.py = pv.at(PY, i); p.pz = pv.at(PZ, i);
+    p.vx = pv.at(VX, i); p.vy = pv.at(VY, i); p.vz = pv.at(VZ, i);
+    p.m = pv.at(PM, i);
 #pragma unroll
-    for (int k = 0; k < 9; ++k) p.c[k] = pv.plane(C0 + k)[i];
+    for (int k = 0; k < 9; ++k) p.c[k] = pv.at(C0 + k, i);
     float wx[3], wy[3], wz[3] = {1.0f, 1.0f, 1.0f};
     const int cx = axis_weights(p.px, wx), cy = axis_weights(p.py, wy);
     const int cz = (DIM == 3) ? axis_weights(p.pz, wz) : 1;
@@ -57,10 +57,10 @@ __global__ void __launch_bounds__(256) k_p2g2_ref(DevParams P, ParticleView pv, 
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float px = pv.plane(PX)[i], py = pv.plane(PY)[i], pz = pv.plane(PZ)[i], m = pv.plane(PM)[i];
+    const float px = pv.at(PX, i), py = pv.at(PY, i), pz = pv.at(PZ, i), m = pv.at(PM, i);
     float c[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) c[k] = pv.plane(C0 + k)[i];
+    for (int k = 0; k < 9; ++k) c[k] = pv.at(C0 + k, i);
     float wx[3], wy[3], wz[3] = {1.0f, 1.0f, 1.0f};
     const int cx = axis_weights(px, wx), cy = axis_weights(py, wy);
     const int cz = (DIM == 3) ? axis_weights(pz, wz) : 1;
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) k_g2p_ref(DevParams P, ParticleView pv, i
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float old[3] = {pv.plane(PX)[i], pv.plane(PY)[i], pv.plane(PZ)[i]};
+    const float old[3] = {pv.at(PX, i), pv.at(PY, i), pv.at(PZ, i)};
     float wx[3], wy[3], wz[3] = {1.0f, 1.0f, 1.0f};
     const int cx = axis_weights(old[0], wx), cy = axis_weights(old[1], wy);
     const int cz = (DIM == 3) ? axis_weights(old[2], wz) : 1;
@@ -184,10 +184,10 @@ __global__ void __launch_bounds__(256) k_g2p_ref(DevParams P, ParticleView pv, i
             }
     float np[3], c[9];
     g2p_finish<DIM>(P, old, B, v, np, c);
-    pv.plane(PX)[i] = np[0]; pv.plane(PY)[i] = np[1]; pv.plane(PZ)[i] = np[2];
-    pv.plane(VX)[i] = v[0]; pv.plane(VY)[i] = v[1]; pv.plane(VZ)[i] = v[2];
+    pv.at(PX, i) = np[0]; pv.at(PY, i) = np[1]; pv.at(PZ, i) = np[2];
+    pv.at(VX, i) = v[0]; pv.at(VY, i) = v[1]; pv.at(VZ, i) = v[2];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) pv.plane(C0 + k)[i] = c[k];
+    for (int k = 0; k < 9; ++k) pv.at(C0 + k, i) = c[k];
     if (positions) {  // particle_pos texture (g2p.glsl:149-150), original index order
         const float len = __fsqrt_rn(sadd(sadd(smul(v[0], v[0]), smul(v[1], v[1])), smul(v[2], v[2])));
         positions[orig_id ? orig_id[i] : (uint32_t)i] = make_float4(np[0], np[1], np[2], len);

@@ -38,11 +38,11 @@ __global__ void __launch_bounds__(TILED_THREADS) k_p2g1_tiled(DevParams P, TileG
     __syncthreads();
     for (uint32_t i = s0 + threadIdx.x; i < s1; i += TILED_THREADS) {
         ParticleIn p;
-        p.px = pv.plane(PX)[i]; p.py = pv.plane(PY)[i]; p.pz = pv.plane(PZ)[i];
-        p.vx = pv.plane(VX)[i]; p.vy = pv.plane(VY)[i]; p.vz = pv.plane(VZ)[i];
-        p.m = pv.plane(PM)[i];
+        p.px = pv.at(PX, i); p.py = pv.at(PY, i); p.pz = pv.at(PZ, i);
+        p.vx = pv.at(VX, i); p.vy = pv.at(VY, i); p.vz = pv.at(VZ, i);
+        p.m = pv.at(PM, i);
 #pragma unroll
-        for (int k = 0; k < 9; ++k) p.c[k] = pv.plane(C0 + k)[i];
+        for (int k = 0; k < 9; ++k) p.c[k] = pv.at(C0 + k, i);
         float wx[3], wy[3], wz[3];
         const int cx = axis_weights(p.px, wx), cy = axis_weights(p.py, wy), cz = axis_weights(p.pz, wz);
         int base;
@@ -107,10 +107,10 @@ __global__ void __launch_bounds__(TILED_THREADS) k_p2g2_tiled(DevParams P, TileG
     }
     __syncthreads();
     for (uint32_t i = s0 + threadIdx.x; i < s1; i += TILED_THREADS) {
-        const float px = pv.plane(PX)[i], py = pv.plane(PY)[i], pz = pv.plane(PZ)[i], m = pv.plane(PM)[i];
+        const float px = pv.at(PX, i), py = pv.at(PY, i), pz = pv.at(PZ, i), m = pv.at(PM, i);
         float c[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) c[k] = pv.plane(C0 + k)[i];
+        for (int k = 0; k < 9; ++k) c[k] = pv.at(C0 + k, i);
         float wx[3], wy[3], wz[3];
         const int cx = axis_weights(px, wx), cy = axis_weights(py, wy), cz = axis_weights(pz, wz);
         int base;
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(TILED_THREADS) k_g2p_tiled(DevParams P, TileGe
     }
     __syncthreads();
     for (uint32_t i = s0 + threadIdx.x; i < s1; i += TILED_THREADS) {
-        const float old[3] = {pv.plane(PX)[i], pv.plane(PY)[i], pv.plane(PZ)[i]};
+        const float old[3] = {pv.at(PX, i), pv.at(PY, i), pv.at(PZ, i)};
         float wx[3], wy[3], wz[3];
         const int cx = axis_weights(old[0], wx), cy = axis_weights(old[1], wy), cz = axis_weights(old[2], wz);
         int base;
@@ -224,10 +224,10 @@ __global__ void __launch_bounds__(TILED_THREADS) k_g2p_tiled(DevParams P, TileGe
         if (in_block) gather(std::true_type{}); else gather(std::false_type{});
         float np[3], c[9];
         g2p_finish<3>(P, old, Bm, v, np, c);
-        pv.plane(PX)[i] = np[0]; pv.plane(PY)[i] = np[1]; pv.plane(PZ)[i] = np[2];
-        pv.plane(VX)[i] = v[0]; pv.plane(VY)[i] = v[1]; pv.plane(VZ)[i] = v[2];
+        pv.at(PX, i) = np[0]; pv.at(PY, i) = np[1]; pv.at(PZ, i) = np[2];
+        pv.at(VX, i) = v[0]; pv.at(VY, i) = v[1]; pv.at(VZ, i) = v[2];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) pv.plane(C0 + k)[i] = c[k];
+        for (int k = 0; k < 9; ++k) pv.at(C0 + k, i) = c[k];
         const float len = __fsqrt_rn(sadd(sadd(smul(v[0], v[0]), smul(v[1], v[1])), smul(v[2], v[2])));
         positions[orig_id[i]] = make_float4(np[0], np[1], np[2], len);
     }

@@ -10,6 +10,7 @@
 
 namespace mpm {
 struct SortState;  // mpm_sort.cu
+struct BinState;   // mpm_bin.cu
 struct CommState;  // mpm_comm.cu
 }  // namespace mpm
 
@@ -41,6 +42,7 @@ struct MpmSolver {
     bool sorted_valid = false;
     bool fresh_particles = true;  // particle set changed since the last bin phase (-> lane interleave once)
     mpm::SortState* sort = nullptr;
+    mpm::BinState* bin = nullptr;
     mpm::CommState* comm = nullptr;
 
     // per-phase timing

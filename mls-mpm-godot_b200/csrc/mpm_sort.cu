@@ -22,6 +22,7 @@
 // no atomics on the ranking path).  Then k_reorder gathers the 16 particle planes through the permutation.
 #include "mpm_kernels.h"
 #include "mpm_solver.h"
+#include "mpm_tile.cuh"
 
 namespace mpm {
 
@@ -48,28 +49,13 @@ struct SortState {
     int64_t last_n = 0;
 };
 
-// ---- key: block-major, cell-minor.  2D uses BxB blocks with bz = lz = 0.
-struct KeyGeom {
-    int dim, logB, nby, nbz, gx0;
-};
-
-__device__ __forceinline__ uint32_t cell_key(const KeyGeom& g, int cx, int cy, int cz)
-{
-    const int m = (1 << g.logB) - 1;
-    const int lx = cx - g.gx0;  // local slab coordinate (slab origin is block-aligned)
-    const int bx = lx >> g.logB, by = cy >> g.logB, bz = cz >> g.logB;
-    const uint32_t blk = (uint32_t)((bx * g.nby + by) * g.nbz + bz);
-    if (g.dim == 3) return (blk << (3 * g.logB)) | (uint32_t)(((((lx & m) << g.logB) | (cy & m)) << g.logB) | (cz & m));
-    return (blk << (2 * g.logB)) | (uint32_t)(((lx & m) << g.logB) | (cy & m));
-}
-
 __global__ void __launch_bounds__(256) k_make_keys(KeyGeom g, ParticleView pv, int64_t n, uint32_t* keys, uint32_t* vals,
                                                    uint32_t* keys_before)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int cx = __float2int_rz(pv.plane(PX)[i]), cy = __float2int_rz(pv.plane(PY)[i]);
-    const int cz = (g.dim == 3) ? __float2int_rz(pv.plane(PZ)[i]) : 0;
+    const int cx = __float2int_rz(pv.at(PX, i)), cy = __float2int_rz(pv.at(PY, i));
+    const int cz = (g.dim == 3) ? __float2int_rz(pv.at(PZ, i)) : 0;
     const uint32_t k = cell_key(g, cx, cy, cz);
     keys[i] = k;
     vals[i] = (uint32_t)i;
@@ -277,10 +263,10 @@ __global__ void __launch_bounds__(256) k_reorder(ParticleView src, ParticleView 
     const uint32_t j = gather_src[i];
     float v[NPLANES];
 #pragma unroll
-    for (int k = 0; k < NPLANES; ++k) v[k] = src.plane(k)[j];
+    for (int k = 0; k < NPLANES; ++k) v[k] = src.at(k, j);
     const uint32_t id = id_src[j];
 #pragma unroll
-    for (int k = 0; k < NPLANES; ++k) dst.plane(k)[i] = v[k];
+    for (int k = 0; k < NPLANES; ++k) dst.at(k, i) = v[k];
     id_dst[i] = id;
 }
 

@@ -45,4 +45,20 @@ struct Tile {
     }
 };
 
+// ---- bin key: block-major, cell-minor.  2D uses BxB blocks with bz = lz = 0.  The block id is the reference's
+// cell index formula (MLSMPM3DFluidMultithread.cs:282) applied to block coordinates.
+struct KeyGeom {
+    int dim, logB, nby, nbz, gx0;  // gx0 = first OWNED x plane (block origin of the slab)
+};
+
+__device__ __forceinline__ uint32_t cell_key(const KeyGeom& g, int cx, int cy, int cz)
+{
+    const int m = (1 << g.logB) - 1;
+    const int lx = cx - g.gx0;
+    const int bx = lx >> g.logB, by = cy >> g.logB, bz = cz >> g.logB;
+    const uint32_t blk = (uint32_t)((bx * g.nby + by) * g.nbz + bz);
+    if (g.dim == 3) return (blk << (3 * g.logB)) | (uint32_t)(((((lx & m) << g.logB) | (cy & m)) << g.logB) | (cz & m));
+    return (blk << (2 * g.logB)) | (uint32_t)(((lx & m) << g.logB) | (cy & m));
+}
+
 }  // namespace mpm

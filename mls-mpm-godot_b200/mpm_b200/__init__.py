@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "libmpm_b200.so")
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_OVERFLOW, ERR_COMM = 0, 1, 2, 3, 4, 5
 GRID_FLOAT, GRID_FIXED = 0, 1
 MATH_STRICT, MATH_FAST = 0, 1
-PATH_AUTO, PATH_REFERENCE, PATH_TILED = 0, 1, 2
+PATH_AUTO, PATH_REFERENCE, PATH_TILED, PATH_CELL = 0, 1, 2, 3
 VARIANT_2D_ST, VARIANT_2D_MT, VARIANT_3D_FLOAT, VARIANT_3D_FIXED, VARIANT_3D_GPU = range(5)
 VARIANTS = {"2d_st": 0, "2d_mt": 1, "3d_float": 2, "3d_fixed": 3, "3d_gpu": 4}
 PHASE_CLEAR, PHASE_P2G1, PHASE_P2G2, PHASE_UPDATE, PHASE_G2P, PHASE_SORT = range(6)

@@ -147,6 +147,25 @@ def test_k_slabs_bit_identical_to_one(lib, world, path):
 
 
 @pytest.mark.gpu
+def test_k_slabs_cell_path_within_fast_tolerance(lib):
+    """The cell path (FAST math) on 3 slabs: float accumulation order differs from the 1-slab run, so the bar is the
+    FAST tolerance against the strict oracle, plus exact particle bookkeeping."""
+    op = orc.variant("3d_gpu", (48, 32, 32))
+    op.interaction = 0
+    n, steps = 60000, 4
+    pos, vel, Cm, mass = helpers.random_cloud(op, n, seed=7, vel_sigma=1.5)
+    ref = orc.State(op, pos, vel, Cm, mass)
+    ref.step(steps)
+    ranks = _run_ranks(op, 3, pos, vel, Cm, mass, steps, kernel_path=3, math_mode=1)
+    ids = np.concatenate([r["ids"] for r in ranks])
+    assert np.array_equal(np.sort(ids), np.arange(n, dtype=np.uint32))
+    fp, fv = np.zeros_like(ref.pos), np.zeros_like(ref.vel)
+    for r in ranks:
+        fp[r["ids"]], fv[r["ids"]] = r["pos"], r["vel"]
+    assert np.abs(fp - ref.pos).max() < 2e-4 and helpers.rel_err(fv, ref.vel) < 2e-4
+
+
+@pytest.mark.gpu
 def test_slab_dam_break_trajectory_and_balance(lib):
     """Reduced dam-break on 2 slabs, 30 steps, lattice generated on the device on every rank (mpm_init_block)."""
     import mpm_b200
@@ -183,3 +202,48 @@ def test_slab_dam_break_trajectory_and_balance(lib):
         full[ids], fullv[ids] = gp, gv
     helpers.assert_bit_equal(full, ref.pos, "pos after 30 steps on 2 slabs")
     helpers.assert_bit_equal(fullv, ref.vel, "vel after 30 steps on 2 slabs")
+
+
+# ---------------------------------------------------------------- GPU x2: the NCCL transport, one process per GPU
+def _nccl_worker(rank, world, uid, op_bytes, arrs, steps, q):
+    import ctypes
+    import mpm_b200
+    op = orc.OrcParams.from_buffer_copy(op_bytes)
+    pos, vel, Cm, mass = arrs
+    try:
+        with mpm_b200.Solver(helpers.mpm_params_from_orc(op, kernel_path=2), pos.shape[0], device=rank) as s:
+            s.comm_init(uid, rank, world)
+            s.upload(pos, vel, Cm, mass)
+            s.step(steps)
+            gp, gv, gc, gm = s.download()
+            q.put((rank, gp, gv, gc, s.download_ids(), None))
+    except Exception as e:  # noqa: BLE001
+        q.put((rank, None, None, None, None, repr(e)))
+
+
+@pytest.mark.gpu
+def test_nccl_two_gpus_bit_identical_to_oracle(lib):
+    import mpm_b200
+    if lib.mpm_device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    op = orc.variant("3d_gpu", (48, 32, 32))
+    op.interaction = 0
+    n, steps = 60000, 8
+    pos, vel, Cm, mass = helpers.random_cloud(op, n, seed=11, vel_sigma=1.5)
+    ref = orc.State(op, pos, vel, Cm, mass)
+    ref.step(steps)
+    uid = mpm_b200.comm_unique_id()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, uid, bytes(op), (pos, vel, Cm, mass), steps, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=300) for _ in procs]
+    [p.join(60) for p in procs]
+    assert all(r[5] is None for r in res), [r[5] for r in res]
+    fp, fv, fc = np.zeros_like(ref.pos), np.zeros_like(ref.vel), np.zeros_like(ref.C)
+    for _, gp, gv, gc, ids, _ in res:
+        fp[ids], fv[ids], fc[ids] = gp, gv, gc
+    helpers.assert_bit_equal(fp, ref.pos, "pos (2 GPUs, NCCL)")
+    helpers.assert_bit_equal(fv, ref.vel, "vel (2 GPUs, NCCL)")
+    helpers.assert_bit_equal(fc, ref.C, "C (2 GPUs, NCCL)")
