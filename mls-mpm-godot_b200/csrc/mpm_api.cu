@@ -469,7 +469,7 @@ static int run_phase(MpmSolver* s, int phase, size_t& cursor)
             if (s->path == MPM_PATH_TILED) { int rc = tiled_g2p(s); if (rc) return rc; }
             else if (s->path == MPM_PATH_CELL) { int rc = cell_g2p(s); if (rc) return rc; }
             else { launch_g2p_ref(P, s->view(), s->n, s->grid, s->orig_id, s->positions, s->stream); s->launches += (s->n > 0); }
-            s->positions_valid = true;
+            s->positions_valid = (s->path != MPM_PATH_CELL);  // the cell path produces the hand-off on demand
             break;
         default:
             return fail(s, MPM_ERR_INVALID, "unknown phase");

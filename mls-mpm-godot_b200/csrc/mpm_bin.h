@@ -12,18 +12,21 @@ struct BinState {
     int nbx = 0, nby = 0, nbz = 0;
     int64_t nblocks = 0;
     int64_t nslots = 0;        // nblocks << cell_bits: one count entry per (block, cell)
-    int64_t ntiles = 0;        // scan tiles
     uint32_t* cnt[2] = {nullptr, nullptr};  // particle count per (block, cell); cnt[cur] describes the current layout,
     int cur = 0;                            // cnt[cur ^ 1] is being accumulated by G2P for the next binning
     bool next_valid = false;                // keys[] and cnt[cur ^ 1] were produced by the last G2P
-    uint32_t* cell_start = nullptr;  // [nslots + 1] exclusive scan of cnt[cur]
+    // layout metadata of the current binning (cells of a block ordered by count, descending, in chunks of 32)
+    uint32_t* cnts = nullptr;        // [nslots] count at sorted position
+    uint16_t* ord = nullptr;         // [nslots] sorted position -> cell id inside the block
+    uint16_t* inv = nullptr;         // [nslots] cell id -> sorted position
+    uint32_t* pstart = nullptr;      // [nslots / 32] first slot of every chunk
+    uint32_t* bsum = nullptr;        // [nblocks] particles per block
+    uint32_t* bbase = nullptr;       // [nblocks + 1] exclusive scan
     uint32_t* fill = nullptr;        // [nslots] placement cursor
     uint32_t* keys = nullptr;        // [pitch] cell key of each particle for the NEXT binning (slot order)
     uint32_t* src_of = nullptr;      // [pitch] gather list
-    uint32_t* tile_sums = nullptr;
-    uint32_t* active = nullptr;      // [nblocks] non-empty blocks (unordered)
+    uint32_t* active = nullptr;      // [nblocks] non-empty blocks, ascending
     uint32_t* misc = nullptr;        // BIN_MISC_WORDS counters
-    uint32_t* block_start = nullptr; // [nblocks + 1]
 };
 
 int bin_create(MpmSolver* s);

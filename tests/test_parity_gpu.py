@@ -365,7 +365,15 @@ def test_cell_binning_is_a_valid_cell_sort(lib):
         ref.clear_grid(); ref.p2g1()
         s.run_phase(0); s.run_phase(1)
         g = s.download_grid().astype(np.float64)
-        assert helpers.rel_err(g, ref.grid.astype(np.float64)) <= FAST_TOL["grid"]
+        # The oracle truncates every particle's addend toward zero; the cell path truncates once per (cell, node).  So a
+        # node may differ by up to one fixed-point unit per particle that touches it (particles in the 3x3x3 cells
+        # around it), plus fp32 rounding of the accumulated value.
+        R = op.grid
+        cells = np.bincount(((pos[:, 0].astype(np.int64) * R[1] + pos[:, 1].astype(np.int64)) * R[2] + pos[:, 2].astype(np.int64)),
+                            minlength=R[0] * R[1] * R[2]).reshape(R[0], R[1], R[2]).astype(np.float64)
+        touch = sum(np.roll(cells, (dx, dy, dz), (0, 1, 2)) for dx in (-1, 0, 1) for dy in (-1, 0, 1) for dz in (-1, 0, 1)).reshape(-1, 1)
+        gr = ref.grid.astype(np.float64)
+        assert (np.abs(g - gr) <= touch + 2.0 + 4e-7 * np.abs(gr)).all(), float(np.abs(g - gr).max())
         # mass is conserved up to one truncation per (cell, node)
         total, want = g[:, 3].sum(), (mass.astype(np.float64) * 1e7).sum()
         assert abs(total - want) <= 27.0 * n + 1e-7 * want
