@@ -85,6 +85,14 @@ __device__ __forceinline__ void cell_axis(float p, float fc, float w[3], float d
 //                  end_chunk(has)      flush per-cell results
 //                  finish()            after the warp's last chunk of the block
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// 4-byte asynchronous global -> shared copy (LDGSTS): no register is held while the load is in flight
+__device__ __forceinline__ void cp_async4(float* smem, const float* gmem)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <int B, class Body>
 __device__ __forceinline__ void walk_chunks(const CellArgs& a, int b, int lane, int warp, BlockWork* bw, Body& body)
@@ -164,10 +172,13 @@ struct P2G1Body {
     const TL& tl;
     int (*tile)[TL::WORDS];
     int lane;
+    float* stage;  // this lane's column of the warp's two staging buffers: stage[(buf * NPLANES + field) * 32]
+    int wr = 0, rd = 0;
     CellPos<B> cp;
     float am[27], ax[27], ay[27], az[27];
-    __device__ __forceinline__ P2G1Body(const DevParams& P_, const ParticleView& pv_, const TL& tl_, int (*tile_)[TL::WORDS], int lane_)
-        : P(P_), pv(pv_), tl(tl_), tile(tile_), lane(lane_) {}
+    __device__ __forceinline__ P2G1Body(const DevParams& P_, const ParticleView& pv_, const TL& tl_, int (*tile_)[TL::WORDS], int lane_,
+                                        float* stage_)
+        : P(P_), pv(pv_), tl(tl_), tile(tile_), lane(lane_), stage(stage_) {}
     __device__ __forceinline__ void begin_chunk(int L)
     {
         cp.set(tl, L);
@@ -177,19 +188,26 @@ struct P2G1Body {
     __device__ __forceinline__ void fetch(uint32_t i)
     {
         const float* q = pv.rec(i);
+        float* d = stage + wr * (NPLANES * 32);
 #pragma unroll
-        for (int k = 0; k < NPLANES; ++k) prefetch_l1(q + k * GROUP);
+        for (int k = 0; k < NPLANES; ++k) cp_async4(d + k * 32, q + k * GROUP);
+        cp_async_commit();
     }
-    __device__ __forceinline__ void take() {}
-    __device__ __forceinline__ void compute(uint32_t i)
+    __device__ __forceinline__ void take()
     {
-        const float* q = pv.rec(i);
-        const float px = q[PX * GROUP], py = q[PY * GROUP], pz = q[PZ * GROUP];
-        const float vx = q[VX * GROUP], vy = q[VY * GROUP], vz = q[VZ * GROUP];
-        const float ms = q[PM * GROUP] * P.fmult;  // mass in fixed-point units
+        cp_async_wait_all();  // (only this lane's own copies are read back: no warp-level sync needed)
+        rd = wr;
+        wr ^= 1;
+    }
+    __device__ __forceinline__ void compute(uint32_t)
+    {
+        const float* q = stage + rd * (NPLANES * 32);
+        const float px = q[PX * 32], py = q[PY * 32], pz = q[PZ * 32];
+        const float vx = q[VX * 32], vy = q[VY * 32], vz = q[VZ * 32];
+        const float ms = q[PM * 32] * P.fmult;  // mass in fixed-point units
         float cm[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) cm[k] = q[(C0 + k) * GROUP];
+        for (int k = 0; k < 9; ++k) cm[k] = q[(C0 + k) * 32];
         float wx[3], wy[3], wz[3], dx[3], dy[3], dz[3];
         cell_axis(px, cp.fcx, wx, dx); cell_axis(py, cp.fcy, wy, dy); cell_axis(pz, cp.fcz, wz, dz);
 #pragma unroll
@@ -239,16 +257,18 @@ __global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? 3 : 6) k_p2g1_
 {
     using TL = Tile<B>;
     using CF = CellCfg<B>;
-    __shared__ int tile[4][TL::WORDS];
+    extern __shared__ __align__(16) unsigned char dsm[];  // tile | staging (above the 48 KB static limit together)
+    int (*tile)[TL::WORDS] = reinterpret_cast<int (*)[TL::WORDS]>(dsm);
+    float* stg = reinterpret_cast<float*>(dsm + sizeof(int) * 4 * TL::WORDS);
     __shared__ BlockWork s_bw;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (;;) {
         const int b = fetch_block<CF::NWARP>(a, BIN_WORK_P2G1, &s_bw);
         if (b < 0) break;
         TL tl; tl.init(g, b);
-        for (int k = threadIdx.x; k < 4 * TL::WORDS; k += CF::THREADS) (&tile[0][0])[k] = 0;
+        for (int k = threadIdx.x; k < 4 * TL::WORDS; k += CF::THREADS) reinterpret_cast<int*>(dsm)[k] = 0;
         __syncthreads();
-        P2G1Body<B> body(P, pv, tl, tile, lane);
+        P2G1Body<B> body(P, pv, tl, tile, lane, stg + warp * (2 * NPLANES * 32) + lane);
         walk_chunks<B>(a, b, lane, warp, &s_bw, body);
         __syncthreads();
         for (int k = threadIdx.x; k < TL::NODES; k += CF::THREADS) {
@@ -286,11 +306,13 @@ struct P2G2Body {
     const float* tmass;
     int lane;
     float inv_rest;
+    float* stage;  // this lane's column of the warp's two staging buffers: stage[(buf * 13 + k) * 32]
+    int wr = 0, rd = 0;
     CellPos<B> cp;
     float gm[27], ax[27], ay[27], az[27];
     __device__ __forceinline__ P2G2Body(const DevParams& P_, const ParticleView& pv_, const TL& tl_, int (*tile_)[TL::WORDS], const float* tmass_,
-                                        int lane_)
-        : P(P_), pv(pv_), tl(tl_), tile(tile_), tmass(tmass_), lane(lane_), inv_rest(1.0f / P_.rest_density) {}
+                                        int lane_, float* stage_)
+        : P(P_), pv(pv_), tl(tl_), tile(tile_), tmass(tmass_), lane(lane_), inv_rest(1.0f / P_.rest_density), stage(stage_) {}
     __device__ __forceinline__ void begin_chunk(int L)
     {
         cp.set(tl, L);
@@ -306,18 +328,26 @@ struct P2G2Body {
     __device__ __forceinline__ void fetch(uint32_t i)
     {
         const float* q = pv.rec(i);
-        prefetch_l1(q + PX * GROUP); prefetch_l1(q + PY * GROUP); prefetch_l1(q + PZ * GROUP); prefetch_l1(q + PM * GROUP);
+        float* d = stage + wr * (13 * 32);
+        cp_async4(d + 0 * 32, q + PX * GROUP); cp_async4(d + 1 * 32, q + PY * GROUP); cp_async4(d + 2 * 32, q + PZ * GROUP);
+        cp_async4(d + 3 * 32, q + PM * GROUP);
 #pragma unroll
-        for (int k = 0; k < 9; ++k) prefetch_l1(q + (C0 + k) * GROUP);
+        for (int k = 0; k < 9; ++k) cp_async4(d + (4 + k) * 32, q + (C0 + k) * GROUP);
+        cp_async_commit();
     }
-    __device__ __forceinline__ void take() {}
-    __device__ __forceinline__ void compute(uint32_t i)
+    __device__ __forceinline__ void take()
     {
-        const float* q = pv.rec(i);
-        const float px = q[PX * GROUP], py = q[PY * GROUP], pz = q[PZ * GROUP], mass = q[PM * GROUP];
+        cp_async_wait_all();
+        rd = wr;
+        wr ^= 1;
+    }
+    __device__ __forceinline__ void compute(uint32_t)
+    {
+        const float* q = stage + rd * (13 * 32);
+        const float px = q[0 * 32], py = q[1 * 32], pz = q[2 * 32], mass = q[3 * 32];
         float cm[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) cm[k] = q[(C0 + k) * GROUP];
+        for (int k = 0; k < 9; ++k) cm[k] = q[(4 + k) * 32];
         float wx[3], wy[3], wz[3], dx[3], dy[3], dz[3];
         cell_axis(px, cp.fcx, wx, dx); cell_axis(py, cp.fcy, wy, dy); cell_axis(pz, cp.fcz, wz, dz);
         float density = 0.0f;
@@ -384,8 +414,10 @@ __global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? 3 : 6) k_p2g2_
 {
     using TL = Tile<B>;
     using CF = CellCfg<B>;
-    __shared__ int tile[3][TL::WORDS];
-    __shared__ float tmass[TL::WORDS];
+    extern __shared__ __align__(16) unsigned char dsm[];  // tile | mass tile | staging
+    int (*tile)[TL::WORDS] = reinterpret_cast<int (*)[TL::WORDS]>(dsm);
+    float* tmass = reinterpret_cast<float*>(dsm + sizeof(int) * 3 * TL::WORDS);
+    float* stg = tmass + TL::WORDS;
     __shared__ BlockWork s_bw;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float inv_mult = 1.0f / P.fmult;
@@ -393,14 +425,14 @@ __global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? 3 : 6) k_p2g2_
         const int b = fetch_block<CF::NWARP>(a, BIN_WORK_P2G2, &s_bw);
         if (b < 0) break;
         TL tl; tl.init(g, b);
-        for (int k = threadIdx.x; k < 3 * TL::WORDS; k += CF::THREADS) (&tile[0][0])[k] = 0;
+        for (int k = threadIdx.x; k < 3 * TL::WORDS; k += CF::THREADS) reinterpret_cast<int*>(dsm)[k] = 0;
         for (int k = threadIdx.x; k < TL::NODES; k += CF::THREADS) {
             int idx; int64_t ci;
             const bool ok = tl.node(P, k, idx, ci);
             tmass[idx] = ok ? (float)grid[4 * ci + 3] * inv_mult : 0.0f;
         }
         __syncthreads();
-        P2G2Body<B> body(P, pv, tl, tile, tmass, lane);
+        P2G2Body<B> body(P, pv, tl, tile, tmass, lane, stg + warp * (2 * 13 * 32) + lane);
         walk_chunks<B>(a, b, lane, warp, &s_bw, body);
         __syncthreads();
         for (int k = threadIdx.x; k < TL::NODES; k += CF::THREADS) {
@@ -553,38 +585,45 @@ static int check_cell_supported(MpmSolver* s)
 }
 
 template <typename K>
-static unsigned persistent_grid(K kernel, int threads, int64_t nblocks)
+static unsigned persistent_grid(K kernel, int threads, size_t smem)
 {
     int per_sm = 1, dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
-    return (unsigned)std::max<int64_t>(1, std::min<int64_t>(nblocks, (int64_t)per_sm * sms));
+    if (smem > 0) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return (unsigned)(per_sm * sms);
 }
 
-#define LAUNCH_CELL(KERNEL, ...)                                                                                          \
+// SMEM8 / SMEM4: dynamic shared memory of the B = 8 / B = 4 instantiation
+#define LAUNCH_CELL(KERNEL, SMEM8, SMEM4, ...)                                                                            \
     do {                                                                                                                  \
         BinState* st = s->bin;                                                                                            \
         TileGeom g{st->nby, st->nbz, s->dp.gx0 + (s->comm ? 1 : 0)};                                                      \
-        CellArgs a{st->cnts, st->ord, st->pstart, st->active, st->misc};                                               \
+        CellArgs a{st->cnts, st->ord, st->pstart, st->active, st->misc};                                                  \
         if (st->B == 8) {                                                                                                 \
             static unsigned grid8 = 0;                                                                                    \
-            if (!grid8) grid8 = persistent_grid(KERNEL<8>, CellCfg<8>::THREADS, 1 << 30);                                 \
-            KERNEL<8><<<(unsigned)std::min<int64_t>(grid8, st->nblocks), CellCfg<8>::THREADS, 0, s->stream>>>(s->dp, g, s->view(), a, __VA_ARGS__); \
+            if (!grid8) grid8 = persistent_grid(KERNEL<8>, CellCfg<8>::THREADS, (SMEM8));                                 \
+            KERNEL<8><<<(unsigned)std::min<int64_t>(grid8, st->nblocks), CellCfg<8>::THREADS, (SMEM8), s->stream>>>(s->dp, g, s->view(), a, __VA_ARGS__); \
         } else {                                                                                                          \
             static unsigned grid4 = 0;                                                                                    \
-            if (!grid4) grid4 = persistent_grid(KERNEL<4>, CellCfg<4>::THREADS, 1 << 30);                                 \
-            KERNEL<4><<<(unsigned)std::min<int64_t>(grid4, st->nblocks), CellCfg<4>::THREADS, 0, s->stream>>>(s->dp, g, s->view(), a, __VA_ARGS__); \
+            if (!grid4) grid4 = persistent_grid(KERNEL<4>, CellCfg<4>::THREADS, (SMEM4));                                 \
+            KERNEL<4><<<(unsigned)std::min<int64_t>(grid4, st->nblocks), CellCfg<4>::THREADS, (SMEM4), s->stream>>>(s->dp, g, s->view(), a, __VA_ARGS__); \
         }                                                                                                                 \
         s->launches += 1;                                                                                                 \
     } while (0)
+
+template <int B>
+constexpr size_t p2g1_smem() { return sizeof(int) * 4 * Tile<B>::WORDS + sizeof(float) * CellCfg<B>::NWARP * 2 * NPLANES * 32; }
+template <int B>
+constexpr size_t p2g2_smem() { return sizeof(int) * 3 * Tile<B>::WORDS + sizeof(float) * Tile<B>::WORDS + sizeof(float) * CellCfg<B>::NWARP * 2 * 13 * 32; }
 
 int cell_p2g1(MpmSolver* s)
 {
     int rc = check_cell_supported(s);
     if (rc) return rc;
     if (s->n == 0) return MPM_OK;
-    LAUNCH_CELL(k_p2g1_cell, reinterpret_cast<int*>(s->grid));
+    LAUNCH_CELL(k_p2g1_cell, p2g1_smem<8>(), p2g1_smem<4>(), reinterpret_cast<int*>(s->grid));
     return MPM_OK;
 }
 
@@ -593,7 +632,7 @@ int cell_p2g2(MpmSolver* s)
     int rc = check_cell_supported(s);
     if (rc) return rc;
     if (s->n == 0) return MPM_OK;
-    LAUNCH_CELL(k_p2g2_cell, reinterpret_cast<int*>(s->grid));
+    LAUNCH_CELL(k_p2g2_cell, p2g2_smem<8>(), p2g2_smem<4>(), reinterpret_cast<int*>(s->grid));
     return MPM_OK;
 }
 
@@ -609,7 +648,7 @@ int cell_g2p(MpmSolver* s)
     uint32_t* cnt_next = fuse ? bs->cnt[bs->cur ^ 1] : nullptr;
     // The (x, y, z, |v|) hand-off in original index order is a 16-B scatter per particle (0.30 ms of 1.17 ms on C4 when
     // fused here): on this path it is produced on demand by mpm_get_positions instead of every step.
-    LAUNCH_CELL(k_g2p_cell, reinterpret_cast<const int4*>(s->grid), bin_key_geom(s), (uint32_t)bs->nslots, bs->keys, cnt_next);
+    LAUNCH_CELL(k_g2p_cell, 0, 0, reinterpret_cast<const int4*>(s->grid), bin_key_geom(s), (uint32_t)bs->nslots, bs->keys, cnt_next);
     bs->next_valid = fuse;
     s->sorted_valid = false;  // positions moved: the layout is exact for one step only
     return MPM_OK;
