@@ -231,15 +231,16 @@ def main():
     value = n_total * args.steps / (total_ms * 1e-3)
 
     # ---- e2e: one reference frame per step through the C ABI with host buffers
-    pinned = mpm_b200.host_alloc(16 * n_local) if n_local else 0
+    # (multi-GPU: migration changes the local count every step, so the pinned buffer is sized for the whole scene)
+    pinned = mpm_b200.host_alloc(16 * n_total)
     e2e_steps = max(3, min(args.steps, 10))
-    solver.positions_into(pinned, n_local)
+    solver.positions_into(pinned, n_total)
     barrier()
     t0 = time.perf_counter()
     for k in range(e2e_steps):
         solver.set_sphere((-21.648403 + 0.01 * k, 0.0, 31.707275))  # HandleMouseInteraction: params H2D each frame
         solver.step(1)
-        solver.positions_into(pinned, n_local)                        # particle_pos_tex hand-off: 16 B/particle D2H
+        solver.positions_into(pinned, n_total)                        # particle_pos_tex hand-off: 16 B/particle D2H
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -287,4 +288,10 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException:  # a failed rank must not sit in NCCL teardown while its peers wait in a collective
+        import traceback
+        traceback.print_exc()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(1)
