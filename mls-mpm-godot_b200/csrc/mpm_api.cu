@@ -187,6 +187,7 @@ extern "C" int32_t mpm_create(const MpmParams* p, int64_t max_particles, int32_t
         return bail(MPM_ERR_INVALID);
     }
     s->sort_interval = s->hp.sort_interval > 0 ? s->hp.sort_interval : 1;
+    if (s->path == MPM_PATH_CELL) CKC(cudaMalloc(&s->rec, sizeof(float) * 16 * s->pitch));
     if (s->path == MPM_PATH_TILED || s->path == MPM_PATH_CELL) {
         CKC(cudaMalloc(&s->part_alt, sizeof(float) * NPLANES * s->pitch));
         CKC(cudaMalloc(&s->orig_id_alt, sizeof(uint32_t) * s->pitch));
@@ -208,7 +209,7 @@ extern "C" int32_t mpm_destroy(MpmSolver* s)
     sort_destroy(s);
     bin_destroy(s);
     for (cudaEvent_t ev : s->ev) cudaEventDestroy(ev);
-    cudaFree(s->part); cudaFree(s->part_alt); cudaFree(s->orig_id); cudaFree(s->orig_id_alt);
+    cudaFree(s->part); cudaFree(s->part_alt); cudaFree(s->rec); cudaFree(s->orig_id); cudaFree(s->orig_id_alt);
     cudaFree(s->grid); cudaFree(s->positions); cudaFree(s->overflow_flag);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
@@ -265,6 +266,7 @@ static void particles_changed(MpmSolver* s)
     s->sorted_valid = false;
     s->steps_since_sort = 0;
     s->fresh_particles = true;
+    s->in_rec = false;  // the planes were just (re)written
     if (s->bin) s->bin->next_valid = false;
     if (s->comm) comm_mark_global(s);
 }
@@ -293,6 +295,7 @@ static int add_block(MpmSolver* s, const float lo[3], const float hi[3], float s
     if (base + cnt > s->cap) return fail(s, MPM_ERR_INVALID, "lattice exceeds max_particles");
     if (s->comm && !replace && comm_partitioned(s))
         return fail(s, MPM_ERR_STATE, "multi-GPU: mpm_add_block after the slab partition (a step or download) is not supported");
+    if (!replace) ensure_planes(s);
     float* d_ax = nullptr;
     const size_t tot = ax[0].size() + ax[1].size() + ax[2].size();
     CK(cudaMalloc(&d_ax, sizeof(float) * tot));
@@ -376,6 +379,7 @@ extern "C" int32_t mpm_download_particles(MpmSolver* s, MpmParticle80* ps, int64
     { int rc = comm_partition(s); if (rc) return rc; }
     if (cap < s->n) return fail(s, MPM_ERR_INVALID, "destination too small");
     if (s->n == 0) return MPM_OK;
+    ensure_planes(s);
     float* stage = nullptr;
     CK(cudaMalloc(&stage, sizeof(MpmParticle80) * s->n));
     // multi-GPU ranks return their local particles in slot order (global indices: mpm_download_ids)
@@ -396,6 +400,7 @@ extern "C" int32_t mpm_download_particles_soa(MpmSolver* s, float* pos, float* v
     if (cap < s->n) return fail(s, MPM_ERR_INVALID, "destination too small");
     const int64_t n = s->n;
     if (n == 0) return MPM_OK;
+    ensure_planes(s);
     float* stage = nullptr;
     CK(cudaMalloc(&stage, sizeof(float) * 16 * n));
     float* dpos = stage; float* dvel = stage + 3 * n; float* dC = stage + 6 * n; float* dm = stage + 15 * n;
@@ -548,6 +553,7 @@ extern "C" int32_t mpm_run_phase(MpmSolver* s, int32_t phase)
         s->timing = tm;
         if (rc) return rc;
     }
+    if (s->in_rec && phase != PH_SORT && phase != PH_CLEAR && phase != PH_UPDATE && s->sorted_valid) ensure_planes(s);
     bool tm = s->timing; s->timing = false;
     size_t cursor = 0;
     int rc = run_phase(s, phase, cursor);
@@ -579,7 +585,8 @@ extern "C" int32_t mpm_get_positions(MpmSolver* s, float* dst4, int64_t cap, voi
     { int rc = comm_partition(s); if (rc) return rc; }
     // multi-GPU: the rank's local particles in slot order (G2P filled the array by global index instead)
     if ((!s->positions_valid || s->comm) && s->n > 0) {
-        launch_positions(s->view(), s->comm ? nullptr : s->orig_id, s->positions, s->n, s->stream);
+        if (s->in_rec) launch_positions_rec(s->rview(), s->comm ? nullptr : s->orig_id, s->positions, s->n, s->stream);
+        else launch_positions(s->view(), s->comm ? nullptr : s->orig_id, s->positions, s->n, s->stream);
         s->launches += 1;
         s->positions_valid = true;
     }

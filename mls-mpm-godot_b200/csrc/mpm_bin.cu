@@ -40,7 +40,8 @@ namespace mpm {
     } while (0)
 
 // ---- keys + counts from positions (first step, after uploads, and every step in multi-GPU mode)
-__global__ void __launch_bounds__(256) k_bin_keys(KeyGeom g, ParticleView pv, int64_t n, uint32_t nslots, uint32_t* __restrict__ keys,
+template <class View>
+__global__ void __launch_bounds__(256) k_bin_keys(KeyGeom g, View pv, int64_t n, uint32_t nslots, uint32_t* __restrict__ keys,
                                                   uint32_t* __restrict__ cnt)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -124,7 +125,7 @@ template <int CELL_BITS>
 __global__ void __launch_bounds__(1 << CELL_BITS) k_block_order(const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ bbase,
                                                                const uint32_t* __restrict__ active, const uint32_t* __restrict__ misc,
                                                                uint16_t* __restrict__ ord, uint16_t* __restrict__ inv, uint32_t* __restrict__ cnts,
-                                                               uint32_t* __restrict__ pstart)
+                                                               uint32_t* __restrict__ pstart, uint16_t* __restrict__ stab)
 {
     constexpr int NC = 1 << CELL_BITS, NBIN = 64, NW = NC / 32;
     __shared__ uint32_t hist[NBIN], base[NBIN], cursor[NBIN];
@@ -163,13 +164,24 @@ __global__ void __launch_bounds__(1 << CELL_BITS) k_block_order(const uint32_t* 
         for (int k = 0; k < w; ++k) off += wsum[k];
         pstart[b * NW + w] = bbase[b] + off;
     }
+    // S(r) = sum over the chunk's cells of min(count, r) for r = 1..15 (first slot of the rank-r row), so that k_place
+    // needs one 2-byte load instead of the chunk's 32 counts.  Entry 0 flags chunks whose counts are not strictly
+    // ordered (a count >= 63 shares the last sort bin): those take k_place's general path.
+    const uint32_t maxc = __reduce_max_sync(0xffffffffu, v);
+    uint16_t* st = stab + ((size_t)b * NW + w) * 16;
+    if (lane == 0) st[0] = (maxc >= (uint32_t)(NBIN - 1)) ? 1 : 0;
+#pragma unroll
+    for (int r = 1; r < 16; ++r) {
+        const uint32_t sr = __reduce_add_sync(0xffffffffu, min(v, (uint32_t)r));
+        if (lane == 0) st[r] = (uint16_t)sr;
+    }
 }
 
 // rank inside the cell from an atomic cursor; destination slot from the rank and the chunk's 32 counts
 template <int CELL_BITS>
 __global__ void __launch_bounds__(256) k_place(const uint32_t* __restrict__ keys, int64_t n, const uint16_t* __restrict__ inv,
-                                               const uint32_t* __restrict__ cnts, const uint32_t* __restrict__ pstart, uint32_t* __restrict__ fill,
-                                               uint32_t* __restrict__ src_of)
+                                               const uint32_t* __restrict__ cnts, const uint32_t* __restrict__ pstart,
+                                               const uint16_t* __restrict__ stab, uint32_t* __restrict__ fill, uint32_t* __restrict__ src_of)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -178,6 +190,13 @@ __global__ void __launch_bounds__(256) k_place(const uint32_t* __restrict__ keys
     const uint32_t blk0 = key & ~((1u << CELL_BITS) - 1u);
     const uint32_t pos = inv[key];
     const uint32_t chunk = pos >> 5, lane = pos & 31u;
+    const uint32_t gchunk = (blk0 >> 5) + chunk;
+    if (r < 16u && stab[(size_t)gchunk * 16] == 0) {
+        // counts strictly ordered, descending: every lower lane still has a particle at rank r (r < own count <= theirs)
+        const uint32_t below = r ? stab[(size_t)gchunk * 16 + r] : 0u;
+        src_of[pstart[gchunk] + below + lane] = (uint32_t)i;
+        return;
+    }
     const uint4* c4 = reinterpret_cast<const uint4*>(cnts + blk0 + chunk * 32u);
     uint32_t below = 0;   // sum over the chunk's cells of min(count, r)
     uint32_t before = 0;  // lower lanes that still have a particle at rank r
@@ -191,7 +210,7 @@ __global__ void __launch_bounds__(256) k_place(const uint32_t* __restrict__ keys
             before += ((uint32_t)(4 * k + j) < lane && c[j] > r) ? 1u : 0u;
         }
     }
-    src_of[pstart[(blk0 >> 5) + chunk] + below + before] = (uint32_t)i;
+    src_of[pstart[gchunk] + below + before] = (uint32_t)i;
 }
 
 __global__ void __launch_bounds__(256) k_gather(ParticleView src, ParticleView dst, const uint32_t* __restrict__ src_of,
@@ -206,6 +225,23 @@ __global__ void __launch_bounds__(256) k_gather(ParticleView src, ParticleView d
     const uint32_t id = id_src[j];
 #pragma unroll
     for (int k = 0; k < NPLANES; ++k) dst.at(k, i) = v[k];
+    id_dst[i] = id;
+}
+
+// gather from the 64-byte records G2P wrote: two full sectors per particle whatever the permutation
+__global__ void __launch_bounds__(256) k_gather_rec(const float4* __restrict__ rec, ParticleView dst, const uint32_t* __restrict__ src_of,
+                                                    const uint32_t* __restrict__ id_src, uint32_t* __restrict__ id_dst, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t j = src_of[i];
+    const float4 a = rec[4 * (size_t)j], b = rec[4 * (size_t)j + 1], c = rec[4 * (size_t)j + 2], d = rec[4 * (size_t)j + 3];
+    const uint32_t id = id_src[j];
+    float* q = dst.rec(i);
+    q[0 * GROUP] = a.x; q[1 * GROUP] = a.y; q[2 * GROUP] = a.z; q[3 * GROUP] = a.w;
+    q[4 * GROUP] = b.x; q[5 * GROUP] = b.y; q[6 * GROUP] = b.z; q[7 * GROUP] = b.w;
+    q[8 * GROUP] = c.x; q[9 * GROUP] = c.y; q[10 * GROUP] = c.z; q[11 * GROUP] = c.w;
+    q[12 * GROUP] = d.x; q[13 * GROUP] = d.y; q[14 * GROUP] = d.z; q[15 * GROUP] = d.w;
     id_dst[i] = id;
 }
 
@@ -240,6 +276,7 @@ int bin_create(MpmSolver* s)
     CKB(cudaMalloc(&st->ord, sizeof(uint16_t) * st->nslots));
     CKB(cudaMalloc(&st->inv, sizeof(uint16_t) * st->nslots));
     CKB(cudaMalloc(&st->pstart, sizeof(uint32_t) * (st->nslots >> 5)));
+    CKB(cudaMalloc(&st->stab, sizeof(uint16_t) * 16 * (st->nslots >> 5)));
     CKB(cudaMalloc(&st->bsum, sizeof(uint32_t) * st->nblocks));
     CKB(cudaMalloc(&st->bbase, sizeof(uint32_t) * (st->nblocks + 1)));
     CKB(cudaMalloc(&st->fill, sizeof(uint32_t) * st->nslots));
@@ -257,7 +294,7 @@ void bin_destroy(MpmSolver* s)
 {
     BinState* st = s->bin;
     if (!st) return;
-    cudaFree(st->cnt[0]); cudaFree(st->cnt[1]); cudaFree(st->cnts); cudaFree(st->ord); cudaFree(st->inv); cudaFree(st->pstart);
+    cudaFree(st->cnt[0]); cudaFree(st->cnt[1]); cudaFree(st->cnts); cudaFree(st->ord); cudaFree(st->inv); cudaFree(st->pstart); cudaFree(st->stab);
     cudaFree(st->bsum); cudaFree(st->bbase); cudaFree(st->fill); cudaFree(st->keys); cudaFree(st->src_of); cudaFree(st->active);
     cudaFree(st->misc);
     delete st;
@@ -279,7 +316,8 @@ int bin_particles(MpmSolver* s)
     if (!st->next_valid) {  // no G2P has produced keys/counts for this particle set: compute them from the positions
         CKB(cudaMemsetAsync(st->cnt[nxt], 0, sizeof(uint32_t) * st->nslots, s->stream));
         if (n > 0) {
-            k_bin_keys<<<nb, 256, 0, s->stream>>>(bin_key_geom(s), s->view(), n, (uint32_t)st->nslots, st->keys, st->cnt[nxt]);
+            if (s->in_rec) k_bin_keys<RecView><<<nb, 256, 0, s->stream>>>(bin_key_geom(s), s->rview(), n, (uint32_t)st->nslots, st->keys, st->cnt[nxt]);
+            else k_bin_keys<ParticleView><<<nb, 256, 0, s->stream>>>(bin_key_geom(s), s->view(), n, (uint32_t)st->nslots, st->keys, st->cnt[nxt]);
             s->launches += 1;
         }
     }
@@ -288,19 +326,24 @@ int bin_particles(MpmSolver* s)
     if (st->cell_bits == 9) {
         k_block_sums<9><<<nbw, 256, 0, s->stream>>>(st->cnt[nxt], st->nblocks, st->bsum);
         k_scan_blocks<<<1, 1024, 0, s->stream>>>(st->bsum, st->nblocks, st->bbase, st->active, st->misc);
-        k_block_order<9><<<(unsigned)st->nblocks, 512, 0, s->stream>>>(st->cnt[nxt], st->bbase, st->active, st->misc, st->ord, st->inv, st->cnts, st->pstart);
+        k_block_order<9><<<(unsigned)st->nblocks, 512, 0, s->stream>>>(st->cnt[nxt], st->bbase, st->active, st->misc, st->ord, st->inv, st->cnts, st->pstart, st->stab);
     } else {
         k_block_sums<6><<<nbw, 256, 0, s->stream>>>(st->cnt[nxt], st->nblocks, st->bsum);
         k_scan_blocks<<<1, 1024, 0, s->stream>>>(st->bsum, st->nblocks, st->bbase, st->active, st->misc);
-        k_block_order<6><<<(unsigned)st->nblocks, 64, 0, s->stream>>>(st->cnt[nxt], st->bbase, st->active, st->misc, st->ord, st->inv, st->cnts, st->pstart);
+        k_block_order<6><<<(unsigned)st->nblocks, 64, 0, s->stream>>>(st->cnt[nxt], st->bbase, st->active, st->misc, st->ord, st->inv, st->cnts, st->pstart, st->stab);
     }
     s->launches += 3;
     if (n > 0) {
-        if (st->cell_bits == 9) k_place<9><<<nb, 256, 0, s->stream>>>(st->keys, n, st->inv, st->cnts, st->pstart, st->fill, st->src_of);
-        else k_place<6><<<nb, 256, 0, s->stream>>>(st->keys, n, st->inv, st->cnts, st->pstart, st->fill, st->src_of);
-        k_gather<<<nb, 256, 0, s->stream>>>(s->view(), s->view_alt(), st->src_of, s->orig_id, s->orig_id_alt, n);
+        if (st->cell_bits == 9) k_place<9><<<nb, 256, 0, s->stream>>>(st->keys, n, st->inv, st->cnts, st->pstart, st->stab, st->fill, st->src_of);
+        else k_place<6><<<nb, 256, 0, s->stream>>>(st->keys, n, st->inv, st->cnts, st->pstart, st->stab, st->fill, st->src_of);
+        if (s->in_rec) {  // the last G2P left the state as records: gather straight into the planes
+            k_gather_rec<<<nb, 256, 0, s->stream>>>(reinterpret_cast<const float4*>(s->rec), s->view(), st->src_of, s->orig_id, s->orig_id_alt, n);
+            s->in_rec = false;
+        } else {
+            k_gather<<<nb, 256, 0, s->stream>>>(s->view(), s->view_alt(), st->src_of, s->orig_id, s->orig_id_alt, n);
+            std::swap(s->part, s->part_alt);
+        }
         s->launches += 2;
-        std::swap(s->part, s->part_alt);
         std::swap(s->orig_id, s->orig_id_alt);
     }
     st->cur = nxt;
@@ -311,6 +354,16 @@ int bin_particles(MpmSolver* s)
     s->steps_since_sort = 0;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { s->err = std::string("bin launch: ") + cudaGetErrorString(e); return MPM_ERR_CUDA; }
+    return MPM_OK;
+}
+
+int ensure_planes(MpmSolver* s)
+{
+    if (!s->in_rec) return MPM_OK;
+    launch_rec_to_planes(s->rview(), s->view(), s->n, s->stream);
+    s->launches += (s->n > 0);
+    s->in_rec = false;
+    s->sorted_valid = false;
     return MPM_OK;
 }
 

@@ -20,6 +20,7 @@ struct BinState {
     uint16_t* ord = nullptr;         // [nslots] sorted position -> cell id inside the block
     uint16_t* inv = nullptr;         // [nslots] cell id -> sorted position
     uint32_t* pstart = nullptr;      // [nslots / 32] first slot of every chunk
+    uint16_t* stab = nullptr;        // [nslots / 32][16] first slot of the rank-r row relative to pstart, r < 16 ([0] = irregular flag)
     uint32_t* bsum = nullptr;        // [nblocks] particles per block
     uint32_t* bbase = nullptr;       // [nblocks + 1] exclusive scan
     uint32_t* fill = nullptr;        // [nslots] placement cursor

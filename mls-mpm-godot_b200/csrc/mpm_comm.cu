@@ -479,7 +479,8 @@ __device__ __forceinline__ int mig_side(const MigGeom& g, float px, uint32_t* ba
     return -1;
 }
 
-__global__ void __launch_bounds__(256) k_mig_count(MigGeom g, ParticleView pv, int64_t n, uint32_t* __restrict__ cnt)
+template <class View>
+__global__ void __launch_bounds__(256) k_mig_count(MigGeom g, View pv, int64_t n, uint32_t* __restrict__ cnt)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int side = (i < n) ? mig_side(g, pv.at(PX, i), cnt + 8) : -1;
@@ -491,7 +492,8 @@ __global__ void __launch_bounds__(256) k_mig_count(MigGeom g, ParticleView pv, i
 }
 
 // leavers -> send records (SoA inside the buffer, stride = that side's count); holes / fillers for the compaction
-__global__ void __launch_bounds__(256) k_mig_pack(MigGeom g, ParticleView pv, const uint32_t* __restrict__ ids, int64_t n, int64_t n_stay,
+template <class View>
+__global__ void __launch_bounds__(256) k_mig_pack(MigGeom g, View pv, const uint32_t* __restrict__ ids, int64_t n, int64_t n_stay,
                                                   uint32_t nL, uint32_t nR, uint32_t* __restrict__ sendL, uint32_t* __restrict__ sendR,
                                                   uint32_t* __restrict__ holes, uint32_t* __restrict__ fillers, uint32_t* __restrict__ cnt)
 {
@@ -512,7 +514,8 @@ __global__ void __launch_bounds__(256) k_mig_pack(MigGeom g, ParticleView pv, co
     out[(size_t)NPLANES * stride + slot] = ids[i];
 }
 
-__global__ void __launch_bounds__(256) k_mig_fill(ParticleView pv, uint32_t* __restrict__ ids, const uint32_t* __restrict__ holes,
+template <class View>
+__global__ void __launch_bounds__(256) k_mig_fill(View pv, uint32_t* __restrict__ ids, const uint32_t* __restrict__ holes,
                                                   const uint32_t* __restrict__ fillers, const uint32_t* __restrict__ cnt)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -523,7 +526,8 @@ __global__ void __launch_bounds__(256) k_mig_fill(ParticleView pv, uint32_t* __r
     ids[dst] = ids[src];
 }
 
-__global__ void __launch_bounds__(256) k_mig_unpack(ParticleView pv, uint32_t* __restrict__ ids, int64_t dst_off, const uint32_t* __restrict__ rec,
+template <class View>
+__global__ void __launch_bounds__(256) k_mig_unpack(View pv, uint32_t* __restrict__ ids, int64_t dst_off, const uint32_t* __restrict__ rec,
                                                     uint32_t count)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -542,7 +546,13 @@ int comm_migrate(MpmSolver* s)
     MigGeom g{c->x0, c->x1, hasL ? c->cuts[c->rank - 1] : c->x0, hasR ? c->cuts[c->rank + 2] : c->x1};
     CKM(cudaMemsetAsync(c->d_cnt, 0, 16 * sizeof(uint32_t), s->stream));
     const unsigned nb = (unsigned)((n + 255) / 256);
-    if (n > 0) { k_mig_count<<<nb, 256, 0, s->stream>>>(g, s->view(), n, c->d_cnt); s->launches += 1; }
+    // after a cell-path G2P the particle state lives in the 64-byte records: migrate those
+    const bool rec = s->in_rec;
+    if (n > 0) {
+        if (rec) k_mig_count<RecView><<<nb, 256, 0, s->stream>>>(g, s->rview(), n, c->d_cnt);
+        else k_mig_count<ParticleView><<<nb, 256, 0, s->stream>>>(g, s->view(), n, c->d_cnt);
+        s->launches += 1;
+    }
     // counts: mine leaving left -> the left rank's "arriving from right" (d_cnt[3] there), and vice versa
     int rc = c->tr->exchange(c->d_cnt + 0, hasL ? 4 : 0, c->d_cnt + 2, hasL ? 4 : 0, c->d_cnt + 1, hasR ? 4 : 0, c->d_cnt + 3, hasR ? 4 : 0,
                              s->stream, s->err);
@@ -555,16 +565,28 @@ int comm_migrate(MpmSolver* s)
     const int64_t n_stay = n - nL - nR;
     if (n_stay + mL + mR > s->cap) { s->err = "multi-GPU: arriving particles exceed max_particles of this rank"; return MPM_ERR_COMM; }
     if (nL + nR > 0) {
-        k_mig_pack<<<nb, 256, 0, s->stream>>>(g, s->view(), s->orig_id, n, n_stay, nL, nR, c->send_rec[0], c->send_rec[1], c->holes,
-                                              c->fillers, c->d_cnt);
-        k_mig_fill<<<(nL + nR + 255) / 256, 256, 0, s->stream>>>(s->view(), s->orig_id, c->holes, c->fillers, c->d_cnt);
+        if (rec) {
+            k_mig_pack<RecView><<<nb, 256, 0, s->stream>>>(g, s->rview(), s->orig_id, n, n_stay, nL, nR, c->send_rec[0], c->send_rec[1], c->holes,
+                                                           c->fillers, c->d_cnt);
+            k_mig_fill<RecView><<<(nL + nR + 255) / 256, 256, 0, s->stream>>>(s->rview(), s->orig_id, c->holes, c->fillers, c->d_cnt);
+        } else {
+            k_mig_pack<ParticleView><<<nb, 256, 0, s->stream>>>(g, s->view(), s->orig_id, n, n_stay, nL, nR, c->send_rec[0], c->send_rec[1],
+                                                                c->holes, c->fillers, c->d_cnt);
+            k_mig_fill<ParticleView><<<(nL + nR + 255) / 256, 256, 0, s->stream>>>(s->view(), s->orig_id, c->holes, c->fillers, c->d_cnt);
+        }
         s->launches += 2;
     }
     const size_t rb = sizeof(uint32_t) * REC_WORDS;
     rc = c->tr->exchange(c->send_rec[0], rb * nL, c->recv_rec[0], rb * mL, c->send_rec[1], rb * nR, c->recv_rec[1], rb * mR, s->stream, s->err);
     if (rc) return rc;
-    if (mL) { k_mig_unpack<<<(mL + 255) / 256, 256, 0, s->stream>>>(s->view(), s->orig_id, n_stay, c->recv_rec[0], mL); s->launches += 1; }
-    if (mR) { k_mig_unpack<<<(mR + 255) / 256, 256, 0, s->stream>>>(s->view(), s->orig_id, n_stay + mL, c->recv_rec[1], mR); s->launches += 1; }
+    for (int side = 0; side < 2; ++side) {
+        const uint32_t m = side ? mR : mL;
+        const int64_t off = side ? n_stay + mL : n_stay;
+        if (!m) continue;
+        if (rec) k_mig_unpack<RecView><<<(m + 255) / 256, 256, 0, s->stream>>>(s->rview(), s->orig_id, off, c->recv_rec[side], m);
+        else k_mig_unpack<ParticleView><<<(m + 255) / 256, 256, 0, s->stream>>>(s->view(), s->orig_id, off, c->recv_rec[side], m);
+        s->launches += 1;
+    }
     s->n = n_stay + mL + mR;
     c->migrated_out += nL + nR;
     c->migrated_in += mL + mR;

@@ -48,6 +48,12 @@ struct ParticleView {
     __host__ __device__ __forceinline__ float& at(int k, int64_t i) const { return base[((i >> 5) << 9) + (k << 5) + (i & 31)]; }
 };
 
+// 64-byte particle records: field k of slot i at i * 16 + k (same field order as the planes)
+struct RecView {
+    float* base;
+    __host__ __device__ __forceinline__ float& at(int k, int64_t i) const { return base[i * 16 + k]; }
+};
+
 // ---- strict IEEE binary32 operators: the _rn intrinsics are never contracted into FMA by nvcc, so the
 // results do not depend on -fmad and equal the C# / C oracle operation by operation.
 __device__ __forceinline__ float sadd(float a, float b) { return __fadd_rn(a, b); }

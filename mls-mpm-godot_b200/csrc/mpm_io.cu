@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(256) k_iota(uint32_t* p, uint32_t start, int64
 }
 
 // (x, y, z, |v|) of g2p.glsl:149-150, original index order
-__global__ void __launch_bounds__(256) k_positions(ParticleView pv, const uint32_t* __restrict__ orig_id,
+template <class View>
+__global__ void __launch_bounds__(256) k_positions(View pv, const uint32_t* __restrict__ orig_id,
                                                    float4* __restrict__ positions, int64_t n)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -126,7 +127,28 @@ void launch_iota(uint32_t* p, uint32_t start, int64_t n, cudaStream_t st)
 }
 void launch_positions(ParticleView pv, const uint32_t* orig_id, float4* positions, int64_t n, cudaStream_t st)
 {
-    if (n > 0) k_positions<<<nb(n), 256, 0, st>>>(pv, orig_id, positions, n);
+    if (n > 0) k_positions<ParticleView><<<nb(n), 256, 0, st>>>(pv, orig_id, positions, n);
+}
+void launch_positions_rec(RecView rv, const uint32_t* orig_id, float4* positions, int64_t n, cudaStream_t st)
+{
+    if (n > 0) k_positions<RecView><<<nb(n), 256, 0, st>>>(rv, orig_id, positions, n);
+}
+
+// 64-byte records (slot order) back into the grouped planes
+__global__ void __launch_bounds__(256) k_rec_to_planes(const float4* __restrict__ rec, ParticleView pv, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float* q = pv.rec(i);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float4 v = rec[4 * i + k];
+        q[(4 * k + 0) * GROUP] = v.x; q[(4 * k + 1) * GROUP] = v.y; q[(4 * k + 2) * GROUP] = v.z; q[(4 * k + 3) * GROUP] = v.w;
+    }
+}
+void launch_rec_to_planes(RecView rv, ParticleView pv, int64_t n, cudaStream_t st)
+{
+    if (n > 0) k_rec_to_planes<<<nb(n), 256, 0, st>>>(reinterpret_cast<const float4*>(rv.base), pv, n);
 }
 void launch_lattice(const float* xs, int nx, const float* ys, int ny, const float* zs, int nz, ParticleView pv,
                     int64_t dst_off, cudaStream_t st)

@@ -23,6 +23,8 @@ void launch_soa_to_packed(ParticleView pv, const uint32_t* orig_id, float* pos, 
                           int64_t n, cudaStream_t st);
 void launch_iota(uint32_t* p, uint32_t start, int64_t n, cudaStream_t st);
 void launch_positions(ParticleView pv, const uint32_t* orig_id, float4* positions, int64_t n, cudaStream_t st);
+void launch_positions_rec(RecView rv, const uint32_t* orig_id, float4* positions, int64_t n, cudaStream_t st);
+void launch_rec_to_planes(RecView rv, ParticleView pv, int64_t n, cudaStream_t st);
 // lattice block with per-axis coordinate tables (the fp32 accumulating loops run on the host: they are
 // O(R) work), vel = 0, C = 0, mass = 1
 void launch_lattice(const float* xs, int nx, const float* ys, int ny, const float* zs, int nz, ParticleView pv,

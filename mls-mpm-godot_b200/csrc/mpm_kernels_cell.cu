@@ -7,7 +7,8 @@
 // (cell-binned planes, mpm_bin.cu), keeping the cell's 27-node stencil in registers:
 //   P2G_1 / P2G_2 : 108 / 81 fp32 accumulators per thread; fixed-point conversion and the shared-memory ATOMS
 //                   happen once per cell instead of once per particle.
-//   G2P           : the 27 node velocities (81 floats) are loaded from the shared-memory tile once per cell.
+//   G2P           : the 27 node velocities (81 floats) are loaded from the shared-memory tile once per cell; results go
+//                   out as 64-byte records (two full sectors) for the next binning to gather.
 // A warp = 32 consecutive cells of a block (a "chunk"); at rank r it reads the rank-r particles of its cells
 // from consecutive slots (one full 128-B line per plane when all cells are occupied).  CTAs are persistent and
 // pull non-empty grid blocks from a list with an atomic counter.  G2P also emits each particle's next cell key
@@ -463,10 +464,11 @@ struct G2PBody {
     int lane;
     CellPos<B> cp;
     float gvx[27], gvy[27], gvz[27];
-    float nx_[3], cur[3];  // next / current particle position
+    float nx_[4], cur[4];  // next / current particle: position, mass
+    float4* rec;           // output records
     __device__ __forceinline__ G2PBody(const DevParams& P_, const ParticleView& pv_, const TL& tl_, const float (*tv_)[TL::WORDS],
-                                       const KeyGeom& kg_, uint32_t nslots_, uint32_t* keys_, uint32_t* cnt_next_, int lane_)
-        : P(P_), pv(pv_), tl(tl_), tv(tv_), kg(kg_), nslots(nslots_), keys(keys_), cnt_next(cnt_next_), lane(lane_) {}
+                                       const KeyGeom& kg_, uint32_t nslots_, uint32_t* keys_, uint32_t* cnt_next_, int lane_, float4* rec_)
+        : P(P_), pv(pv_), tl(tl_), tv(tv_), kg(kg_), nslots(nslots_), keys(keys_), cnt_next(cnt_next_), lane(lane_), rec(rec_) {}
     __device__ __forceinline__ void begin_chunk(int L)
     {
         cp.set(tl, L);
@@ -482,9 +484,10 @@ struct G2PBody {
     }
     __device__ __forceinline__ void fetch(uint32_t i)
     {
-        nx_[0] = pv.at(PX, i); nx_[1] = pv.at(PY, i); nx_[2] = pv.at(PZ, i);
+        const float* q = pv.rec(i);
+        nx_[0] = q[PX * GROUP]; nx_[1] = q[PY * GROUP]; nx_[2] = q[PZ * GROUP]; nx_[3] = q[PM * GROUP];
     }
-    __device__ __forceinline__ void take() { cur[0] = nx_[0]; cur[1] = nx_[1]; cur[2] = nx_[2]; }
+    __device__ __forceinline__ void take() { cur[0] = nx_[0]; cur[1] = nx_[1]; cur[2] = nx_[2]; cur[3] = nx_[3]; }
     __device__ __forceinline__ void compute(uint32_t i)
     {
         const float old[3] = {cur[0], cur[1], cur[2]};
@@ -526,11 +529,12 @@ struct G2PBody {
         const float Bm[9] = {Bx[0], Bx[1], Bx[2], By[0], By[1], By[2], Bz[0], Bz[1], Bz[2]};
         float np[3], cm[9];
         g2p_finish<3>(P, old, Bm, v, np, cm);
-        float* q = pv.rec(i);
-        q[PX * GROUP] = np[0]; q[PY * GROUP] = np[1]; q[PZ * GROUP] = np[2];
-        q[VX * GROUP] = v[0]; q[VY * GROUP] = v[1]; q[VZ * GROUP] = v[2];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) q[(C0 + k) * GROUP] = cm[k];
+        // one 64-byte record per particle (field order of the planes): the next binning gathers it from here
+        float4* q = rec + 4 * (size_t)i;
+        q[0] = make_float4(np[0], np[1], np[2], v[0]);
+        q[1] = make_float4(v[1], v[2], cur[3], cm[0]);
+        q[2] = make_float4(cm[1], cm[2], cm[3], cm[4]);
+        q[3] = make_float4(cm[5], cm[6], cm[7], cm[8]);
         if (cnt_next) {  // bin key of the NEW position for the next step (single-GPU: the slab is the domain)
             uint32_t k = cell_key(kg, __float2int_rz(np[0]), __float2int_rz(np[1]), __float2int_rz(np[2]));
             k = k < nslots ? k : nslots - 1;
@@ -546,7 +550,8 @@ struct G2PBody {
 template <int B>
 __global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? 3 : 6) k_g2p_cell(DevParams P, TileGeom g, ParticleView pv, CellArgs a,
                                                                                     const int4* __restrict__ grid, KeyGeom kg, uint32_t nslots,
-                                                                                    uint32_t* __restrict__ keys, uint32_t* __restrict__ cnt_next)
+                                                                                    uint32_t* __restrict__ keys, uint32_t* __restrict__ cnt_next,
+                                                                                    float4* __restrict__ rec)
 {
     using TL = Tile<B>;
     using CF = CellCfg<B>;
@@ -568,7 +573,7 @@ __global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? 3 : 6) k_g2p_c
             tv[0][idx] = vx; tv[1][idx] = vy; tv[2][idx] = vz;
         }
         __syncthreads();
-        G2PBody<B> body(P, pv, tl, tv, kg, nslots, keys, cnt_next, lane);
+        G2PBody<B> body(P, pv, tl, tv, kg, nslots, keys, cnt_next, lane, rec);
         walk_chunks<B>(a, b, lane, warp, &s_bw, body);
     }
 }
@@ -648,7 +653,9 @@ int cell_g2p(MpmSolver* s)
     uint32_t* cnt_next = fuse ? bs->cnt[bs->cur ^ 1] : nullptr;
     // The (x, y, z, |v|) hand-off in original index order is a 16-B scatter per particle (0.30 ms of 1.17 ms on C4 when
     // fused here): on this path it is produced on demand by mpm_get_positions instead of every step.
-    LAUNCH_CELL(k_g2p_cell, 0, 0, reinterpret_cast<const int4*>(s->grid), bin_key_geom(s), (uint32_t)bs->nslots, bs->keys, cnt_next);
+    LAUNCH_CELL(k_g2p_cell, 0, 0, reinterpret_cast<const int4*>(s->grid), bin_key_geom(s), (uint32_t)bs->nslots, bs->keys, cnt_next,
+                reinterpret_cast<float4*>(s->rec));
+    s->in_rec = true;  // the new particle state is in the records until the next binning (or ensure_planes)
     bs->next_valid = fuse;
     s->sorted_valid = false;  // positions moved: the layout is exact for one step only
     return MPM_OK;

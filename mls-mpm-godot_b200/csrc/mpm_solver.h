@@ -27,6 +27,12 @@ struct MpmSolver {
     int64_t n = 0;      // particles currently held (local)
     float* part = nullptr;      // NPLANES * pitch floats
     float* part_alt = nullptr;  // reorder target (tiled path)
+    // Cell path: G2P writes its results as 64-byte records (the 16 fields of a slot, contiguous) instead of back into
+    // the grouped planes: the next binning gathers every particle from an arbitrary source slot, and a record is two
+    // full 32-B sectors wherever it sits, while the 16 fields of a grouped slot are 16 different sectors (measured on
+    // the evolved C4 dam-break: 25.8 GB of L2 traffic for a 4.4 GB gather).
+    float* rec = nullptr;       // [pitch] x 16 floats
+    bool in_rec = false;        // the particle state of slots [0, n) currently lives in `rec`, not in `part`
     uint32_t* orig_id = nullptr;      // original (global) index of the particle in each slot
     uint32_t* orig_id_alt = nullptr;
     void* grid = nullptr;  // ncells_local * 16 B
@@ -56,6 +62,7 @@ struct MpmSolver {
 
     mpm::ParticleView view() const { return mpm::ParticleView{part, pitch}; }
     mpm::ParticleView view_alt() const { return mpm::ParticleView{part_alt, pitch}; }
+    mpm::RecView rview() const { return mpm::RecView{rec}; }
 };
 
 namespace mpm {
@@ -68,6 +75,8 @@ int sort_debug_last(MpmSolver* s, uint32_t* keys_before, uint32_t* perm, int64_t
 int tiled_p2g1(MpmSolver* s);
 int tiled_p2g2(MpmSolver* s);
 int tiled_g2p(MpmSolver* s);
+// particle state back into the grouped planes if the last G2P left it in `rec` (mpm_bin.cu)
+int ensure_planes(MpmSolver* s);
 // multi-GPU (mpm_comm.cu)
 void comm_destroy(MpmSolver* s);
 int comm_exchange_halo(MpmSolver* s, int pass);  // pass 0: after P2G_1 (4 words), 1: after P2G_2 (3 words)
