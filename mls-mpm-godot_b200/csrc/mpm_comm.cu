@@ -211,7 +211,8 @@ struct CommState {
     uint32_t* holes = nullptr;
     uint32_t* fillers = nullptr;
     int64_t rec_cap = 0;
-    int64_t migrated_out = 0, migrated_in = 0;
+    int64_t migrated_out = 0, migrated_in = 0, overflow_rounds = 0;
+    uint32_t sent_prev[2] = {0, 0}, recv_prev[2] = {0, 0};  // particles that crossed each edge in the previous step
 };
 
 #define CKM(call)                                                          \
@@ -261,8 +262,8 @@ static int comm_attach(MpmSolver* s, Transport* tr, int rank, int world)
     CKM(cudaMalloc(&c->d_cnt, 16 * sizeof(uint32_t)));
     CKM(cudaHostAlloc(&c->h_cnt, 16 * sizeof(uint32_t), cudaHostAllocDefault));
     for (int k = 0; k < 2; ++k) {
-        CKM(cudaMalloc(&c->send_rec[k], sizeof(uint32_t) * REC_WORDS * c->rec_cap));
-        CKM(cudaMalloc(&c->recv_rec[k], sizeof(uint32_t) * REC_WORDS * c->rec_cap));
+        CKM(cudaMalloc(&c->send_rec[k], sizeof(uint32_t) * (64 + REC_WORDS * c->rec_cap)));
+        CKM(cudaMalloc(&c->recv_rec[k], sizeof(uint32_t) * (64 + REC_WORDS * c->rec_cap)));
     }
     CKM(cudaMalloc(&c->holes, sizeof(uint32_t) * 2 * c->rec_cap));
     CKM(cudaMalloc(&c->fillers, sizeof(uint32_t) * 2 * c->rec_cap));
@@ -491,14 +492,31 @@ __global__ void __launch_bounds__(256) k_mig_count(MigGeom g, View pv, int64_t n
     }
 }
 
-// leavers -> send records (SoA inside the buffer, stride = that side's count); holes / fillers for the compaction
+// Migration message: MIG_HDR header words ([0] = number of particles leaving over this edge), then the first `cap`
+// records as SoA with stride cap (word MIG_HDR + k * cap + slot), then any overflow records as 17-word AoS.  `cap` is
+// agreed by both ends without talking: it is a function of the count that crossed this edge in the previous step, which
+// sender and receiver both know.  So a step needs ONE exchange and ONE host sync; only when the count more than doubles
+// from one step to the next does a second (overflow) exchange follow.
+constexpr int MIG_HDR = 32;
+
+static inline uint32_t mig_capacity(uint32_t prev)  // the same on both ends of an edge: depends on nothing rank-local
+{
+    const uint64_t want = 2ull * prev + 4096ull;
+    uint64_t c = 4096;
+    while (c < want) c <<= 1;
+    return (uint32_t)std::min<uint64_t>(c, 1u << 30);
+}
+
+// leavers -> message; holes / fillers for the compaction.  Counts come from device memory (k_mig_count ran before).
 template <class View>
-__global__ void __launch_bounds__(256) k_mig_pack(MigGeom g, View pv, const uint32_t* __restrict__ ids, int64_t n, int64_t n_stay,
-                                                  uint32_t nL, uint32_t nR, uint32_t* __restrict__ sendL, uint32_t* __restrict__ sendR,
-                                                  uint32_t* __restrict__ holes, uint32_t* __restrict__ fillers, uint32_t* __restrict__ cnt)
+__global__ void __launch_bounds__(256) k_mig_pack(MigGeom g, View pv, const uint32_t* __restrict__ ids, int64_t n, uint32_t capL, uint32_t capR,
+                                                  uint32_t rec_cap, uint32_t* __restrict__ sendL, uint32_t* __restrict__ sendR, uint32_t* __restrict__ holes,
+                                                  uint32_t* __restrict__ fillers, uint32_t* __restrict__ cnt)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { sendL[0] = cnt[0]; sendR[0] = cnt[1]; }
     if (i >= n) return;
+    const int64_t n_stay = n - cnt[0] - cnt[1];
     uint32_t dummy;
     const int side = mig_side(g, pv.at(PX, i), &dummy);
     if (side < 0) {
@@ -507,91 +525,132 @@ __global__ void __launch_bounds__(256) k_mig_pack(MigGeom g, View pv, const uint
     }
     if (i < n_stay) holes[atomicAdd(cnt + 4, 1u)] = (uint32_t)i;
     uint32_t* out = side == 0 ? sendL : sendR;
-    const uint32_t stride = side == 0 ? nL : nR;
+    const uint32_t cap = side == 0 ? capL : capR;
     const uint32_t slot = atomicAdd(cnt + 6 + side, 1u);
+    if (slot >= rec_cap) return;  // buffer exhausted: the host reports it after the sync (count > rec_cap)
+    if (slot < cap) {
 #pragma unroll
-    for (int k = 0; k < NPLANES; ++k) out[(size_t)k * stride + slot] = __float_as_uint(pv.at(k, i));
-    out[(size_t)NPLANES * stride + slot] = ids[i];
+        for (int k = 0; k < NPLANES; ++k) out[MIG_HDR + (size_t)k * cap + slot] = __float_as_uint(pv.at(k, i));
+        out[MIG_HDR + (size_t)NPLANES * cap + slot] = ids[i];
+    } else {
+        uint32_t* o = out + MIG_HDR + (size_t)REC_WORDS * cap + (size_t)REC_WORDS * (slot - cap);
+#pragma unroll
+        for (int k = 0; k < NPLANES; ++k) o[k] = __float_as_uint(pv.at(k, i));
+        o[NPLANES] = ids[i];
+    }
 }
 
 template <class View>
 __global__ void __launch_bounds__(256) k_mig_fill(View pv, uint32_t* __restrict__ ids, const uint32_t* __restrict__ holes,
                                                   const uint32_t* __restrict__ fillers, const uint32_t* __restrict__ cnt)
 {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= cnt[4]) return;
-    const uint32_t dst = holes[j], src = fillers[j];
+    const uint32_t nh = cnt[4];
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nh; j += gridDim.x * blockDim.x) {
+        const uint32_t dst = holes[j], src = fillers[j];
 #pragma unroll
-    for (int k = 0; k < NPLANES; ++k) pv.at(k, dst) = pv.at(k, src);
-    ids[dst] = ids[src];
+        for (int k = 0; k < NPLANES; ++k) pv.at(k, dst) = pv.at(k, src);
+        ids[dst] = ids[src];
+    }
+}
+
+// arrivals of one message appended behind the stayers: left arrivals first, then right arrivals.
+// overflow = false: the SoA part (first min(count, cap) records); true: the AoS overflow records (count - cap).
+template <class View>
+__global__ void __launch_bounds__(256) k_mig_unpack(View pv, uint32_t* __restrict__ ids, int64_t n, const uint32_t* __restrict__ cnt,
+                                                    const uint32_t* __restrict__ msgL, const uint32_t* __restrict__ msg, int side, uint32_t cap,
+                                                    bool overflow)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t total = msg[0];
+    const int64_t base = n - cnt[0] - cnt[1] + (side == 1 && msgL ? (int64_t)msgL[0] : 0);
+    if (!overflow) {
+        if (j >= min(total, cap)) return;
+#pragma unroll
+        for (int k = 0; k < NPLANES; ++k) pv.at(k, base + j) = __uint_as_float(msg[MIG_HDR + (size_t)k * cap + j]);
+        ids[base + j] = msg[MIG_HDR + (size_t)NPLANES * cap + j];
+    } else {
+        if (total <= cap || j >= total - cap) return;
+        const uint32_t* o = msg + MIG_HDR + (size_t)REC_WORDS * cap + (size_t)REC_WORDS * j;
+#pragma unroll
+        for (int k = 0; k < NPLANES; ++k) pv.at(k, base + cap + j) = __uint_as_float(o[k]);
+        ids[base + cap + j] = o[NPLANES];
+    }
 }
 
 template <class View>
-__global__ void __launch_bounds__(256) k_mig_unpack(View pv, uint32_t* __restrict__ ids, int64_t dst_off, const uint32_t* __restrict__ rec,
-                                                    uint32_t count)
-{
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= count) return;
-#pragma unroll
-    for (int k = 0; k < NPLANES; ++k) pv.at(k, dst_off + j) = __uint_as_float(rec[(size_t)k * count + j]);
-    ids[dst_off + j] = rec[(size_t)NPLANES * count + j];
-}
-
-int comm_migrate(MpmSolver* s)
+static int migrate_impl(MpmSolver* s, View pv)
 {
     CommState* c = s->comm;
     const bool hasL = c->rank > 0, hasR = c->rank < c->world - 1;
-    if (!hasL && !hasR) return MPM_OK;
     const int64_t n = s->n;
     MigGeom g{c->x0, c->x1, hasL ? c->cuts[c->rank - 1] : c->x0, hasR ? c->cuts[c->rank + 2] : c->x1};
     CKM(cudaMemsetAsync(c->d_cnt, 0, 16 * sizeof(uint32_t), s->stream));
     const unsigned nb = (unsigned)((n + 255) / 256);
-    // after a cell-path G2P the particle state lives in the 64-byte records: migrate those
-    const bool rec = s->in_rec;
+    const uint32_t capS[2] = {mig_capacity(c->sent_prev[0]), mig_capacity(c->sent_prev[1])};
+    const uint32_t capR[2] = {mig_capacity(c->recv_prev[0]), mig_capacity(c->recv_prev[1])};
+    if ((int64_t)std::max(std::max(capS[0], capS[1]), std::max(capR[0], capR[1])) > c->rec_cap) {
+        s->err = "multi-GPU: migration buffer too small for the traffic over a slab boundary (raise max_particles)";
+        return MPM_ERR_COMM;
+    }
     if (n > 0) {
-        if (rec) k_mig_count<RecView><<<nb, 256, 0, s->stream>>>(g, s->rview(), n, c->d_cnt);
-        else k_mig_count<ParticleView><<<nb, 256, 0, s->stream>>>(g, s->view(), n, c->d_cnt);
+        k_mig_count<View><<<nb, 256, 0, s->stream>>>(g, pv, n, c->d_cnt);
+        k_mig_pack<View><<<nb, 256, 0, s->stream>>>(g, pv, s->orig_id, n, capS[0], capS[1], (uint32_t)c->rec_cap, c->send_rec[0], c->send_rec[1], c->holes,
+                                                    c->fillers, c->d_cnt);
+        k_mig_fill<View><<<592, 256, 0, s->stream>>>(pv, s->orig_id, c->holes, c->fillers, c->d_cnt);
+        s->launches += 3;
+    } else {
+        CKM(cudaMemsetAsync(c->send_rec[0], 0, sizeof(uint32_t) * MIG_HDR, s->stream));
+        CKM(cudaMemsetAsync(c->send_rec[1], 0, sizeof(uint32_t) * MIG_HDR, s->stream));
+    }
+    auto msg_bytes = [](uint32_t cap) { return sizeof(uint32_t) * ((size_t)MIG_HDR + (size_t)REC_WORDS * cap); };
+    int rc = c->tr->exchange(c->send_rec[0], hasL ? msg_bytes(capS[0]) : 0, c->recv_rec[0], hasL ? msg_bytes(capR[0]) : 0, c->send_rec[1],
+                             hasR ? msg_bytes(capS[1]) : 0, c->recv_rec[1], hasR ? msg_bytes(capR[1]) : 0, s->stream, s->err);
+    if (rc) return rc;
+    const uint32_t* msgL = hasL ? c->recv_rec[0] : nullptr;
+    for (int side = 0; side < 2; ++side) {
+        if (!(side ? hasR : hasL)) continue;
+        k_mig_unpack<View><<<(capR[side] + 255) / 256, 256, 0, s->stream>>>(pv, s->orig_id, n, c->d_cnt, msgL, c->recv_rec[side], side, capR[side], false);
         s->launches += 1;
     }
-    // counts: mine leaving left -> the left rank's "arriving from right" (d_cnt[3] there), and vice versa
-    int rc = c->tr->exchange(c->d_cnt + 0, hasL ? 4 : 0, c->d_cnt + 2, hasL ? 4 : 0, c->d_cnt + 1, hasR ? 4 : 0, c->d_cnt + 3, hasR ? 4 : 0,
-                             s->stream, s->err);
-    if (rc) return rc;
+    // counts to the host: [0] nL, [1] nR, [8] bad; received headers -> h_cnt[2], h_cnt[3]
     CKM(cudaMemcpyAsync(c->h_cnt, c->d_cnt, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    if (hasL) CKM(cudaMemcpyAsync(c->h_cnt + 12, c->recv_rec[0], sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    if (hasR) CKM(cudaMemcpyAsync(c->h_cnt + 13, c->recv_rec[1], sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
     CKM(cudaStreamSynchronize(s->stream));
-    const uint32_t nL = c->h_cnt[0], nR = c->h_cnt[1], mL = c->h_cnt[2], mR = c->h_cnt[3];
+    const uint32_t nL = c->h_cnt[0], nR = c->h_cnt[1], mL = hasL ? c->h_cnt[12] : 0, mR = hasR ? c->h_cnt[13] : 0;
     if (c->h_cnt[8]) { s->err = "multi-GPU: a particle crossed more than one slab in a single step (dt * |v| too large for the slab width)"; return MPM_ERR_COMM; }
     if ((int64_t)std::max(std::max(nL, nR), std::max(mL, mR)) > c->rec_cap) { s->err = "multi-GPU: migration buffer too small"; return MPM_ERR_COMM; }
     const int64_t n_stay = n - nL - nR;
     if (n_stay + mL + mR > s->cap) { s->err = "multi-GPU: arriving particles exceed max_particles of this rank"; return MPM_ERR_COMM; }
-    if (nL + nR > 0) {
-        if (rec) {
-            k_mig_pack<RecView><<<nb, 256, 0, s->stream>>>(g, s->rview(), s->orig_id, n, n_stay, nL, nR, c->send_rec[0], c->send_rec[1], c->holes,
-                                                           c->fillers, c->d_cnt);
-            k_mig_fill<RecView><<<(nL + nR + 255) / 256, 256, 0, s->stream>>>(s->rview(), s->orig_id, c->holes, c->fillers, c->d_cnt);
-        } else {
-            k_mig_pack<ParticleView><<<nb, 256, 0, s->stream>>>(g, s->view(), s->orig_id, n, n_stay, nL, nR, c->send_rec[0], c->send_rec[1],
-                                                                c->holes, c->fillers, c->d_cnt);
-            k_mig_fill<ParticleView><<<(nL + nR + 255) / 256, 256, 0, s->stream>>>(s->view(), s->orig_id, c->holes, c->fillers, c->d_cnt);
-        }
-        s->launches += 2;
-    }
+    // overflow round (only when an edge's count more than doubled since the previous step): sizes are known to both ends now
     const size_t rb = sizeof(uint32_t) * REC_WORDS;
-    rc = c->tr->exchange(c->send_rec[0], rb * nL, c->recv_rec[0], rb * mL, c->send_rec[1], rb * nR, c->recv_rec[1], rb * mR, s->stream, s->err);
-    if (rc) return rc;
-    for (int side = 0; side < 2; ++side) {
-        const uint32_t m = side ? mR : mL;
-        const int64_t off = side ? n_stay + mL : n_stay;
-        if (!m) continue;
-        if (rec) k_mig_unpack<RecView><<<(m + 255) / 256, 256, 0, s->stream>>>(s->rview(), s->orig_id, off, c->recv_rec[side], m);
-        else k_mig_unpack<ParticleView><<<(m + 255) / 256, 256, 0, s->stream>>>(s->view(), s->orig_id, off, c->recv_rec[side], m);
-        s->launches += 1;
+    const size_t oSL = nL > capS[0] ? rb * (nL - capS[0]) : 0, oSR = nR > capS[1] ? rb * (nR - capS[1]) : 0;
+    const size_t oRL = mL > capR[0] ? rb * (mL - capR[0]) : 0, oRR = mR > capR[1] ? rb * (mR - capR[1]) : 0;
+    // every rank must take the same decision: an edge overflows on both of its ends or on neither, but a rank whose edges
+    // are both quiet still has nothing to do here, and its neighbours' other edges do not involve it
+    if (oSL || oSR || oRL || oRR) {
+        rc = c->tr->exchange(c->send_rec[0] + MIG_HDR + (size_t)REC_WORDS * capS[0], oSL, c->recv_rec[0] + MIG_HDR + (size_t)REC_WORDS * capR[0], oRL,
+                             c->send_rec[1] + MIG_HDR + (size_t)REC_WORDS * capS[1], oSR, c->recv_rec[1] + MIG_HDR + (size_t)REC_WORDS * capR[1], oRR,
+                             s->stream, s->err);
+        if (rc) return rc;
+        if (oRL) { k_mig_unpack<View><<<(mL - capR[0] + 255) / 256, 256, 0, s->stream>>>(pv, s->orig_id, n, c->d_cnt, msgL, c->recv_rec[0], 0, capR[0], true); s->launches += 1; }
+        if (oRR) { k_mig_unpack<View><<<(mR - capR[1] + 255) / 256, 256, 0, s->stream>>>(pv, s->orig_id, n, c->d_cnt, msgL, c->recv_rec[1], 1, capR[1], true); s->launches += 1; }
+        c->overflow_rounds += 1;
     }
+    c->sent_prev[0] = nL; c->sent_prev[1] = nR; c->recv_prev[0] = mL; c->recv_prev[1] = mR;
     s->n = n_stay + mL + mR;
     c->migrated_out += nL + nR;
     c->migrated_in += mL + mR;
     if (nL + nR + mL + mR) { s->sorted_valid = false; s->positions_valid = false; }
     return MPM_OK;
+}
+
+int comm_migrate(MpmSolver* s)
+{
+    CommState* c = s->comm;
+    if (c->world < 2) return MPM_OK;
+    // after a cell-path G2P the particle state lives in the 64-byte records: migrate those
+    return s->in_rec ? migrate_impl<RecView>(s, s->rview()) : migrate_impl<ParticleView>(s, s->view());
 }
 
 }  // namespace mpm

@@ -147,6 +147,33 @@ def test_k_slabs_bit_identical_to_one(lib, world, path):
 
 
 @pytest.mark.gpu
+def test_migration_burst_takes_the_overflow_round(lib):
+    """A migration message is sized from the previous step's count over the same slab boundary (4096 records at
+    first): 12000 particles crossing in one step must go through the overflow round and still be bit-exact."""
+    op = orc.variant("3d_gpu", (48, 32, 32))
+    op.interaction = 0
+    rng = np.random.default_rng(5)
+    n_bg, n_jet = 30000, 24000
+    pos, vel, Cm, mass = helpers.random_cloud(op, n_bg + n_jet, seed=9, vel_sigma=0.2)
+    # a dense sheet that straddles the middle of the domain and moves in +x at 0.9 cells per step (dt = 0.2)
+    pos[n_bg:, 0] = rng.uniform(23.2, 24.8, n_jet).astype(np.float32)
+    vel[n_bg:] = (4.5, 0.0, 0.0)
+    Cm[n_bg:] = 0.0
+    mass[n_bg:] = 0.05
+    steps = 3
+    ref = orc.State(op, pos, vel, Cm, mass)
+    ref.step(steps)
+    ranks = _run_ranks(op, 2, pos, vel, Cm, mass, steps, kernel_path=2)
+    moved = (ref.pos[:, 0].astype(np.int32) >= ranks[0]["slab"][1]) & (pos[:, 0].astype(np.int32) < ranks[0]["slab"][1])
+    assert moved.sum() > 8192, "the scene does not produce a burst"
+    for what in ("pos", "vel", "C"):
+        full = np.zeros_like(getattr(ref, what))
+        for r in ranks:
+            full[r["ids"]] = r[what]
+        helpers.assert_bit_equal(full, getattr(ref, what), f"{what} after a migration burst")
+
+
+@pytest.mark.gpu
 def test_k_slabs_cell_path_within_fast_tolerance(lib):
     """The cell path (FAST math) on 3 slabs: float accumulation order differs from the 1-slab run, so the bar is the
     FAST tolerance against the strict oracle, plus exact particle bookkeeping."""
