@@ -41,11 +41,11 @@ namespace mpm {
 
 // ---- keys + counts from positions (first step, after uploads, and every step in multi-GPU mode)
 template <class View>
-__global__ void __launch_bounds__(256) k_bin_keys(KeyGeom g, View pv, int64_t n, uint32_t nslots, uint32_t* __restrict__ keys,
+__global__ void __launch_bounds__(256) k_bin_keys(KeyGeom g, View pv, int64_t first, int64_t n, uint32_t nslots, uint32_t* __restrict__ keys,
                                                   uint32_t* __restrict__ cnt)
 {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const int64_t i = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= first + n) return;
     const int cx = __float2int_rz(pv.at(PX, i)), cy = __float2int_rz(pv.at(PY, i)), cz = __float2int_rz(pv.at(PZ, i));
     uint32_t k = cell_key(g, cx, cy, cz);
     k = k < nslots ? k : nslots - 1;  // a NaN / out-of-slab position must not index outside the count array
@@ -316,8 +316,8 @@ int bin_particles(MpmSolver* s)
     if (!st->next_valid) {  // no G2P has produced keys/counts for this particle set: compute them from the positions
         CKB(cudaMemsetAsync(st->cnt[nxt], 0, sizeof(uint32_t) * st->nslots, s->stream));
         if (n > 0) {
-            if (s->in_rec) k_bin_keys<RecView><<<nb, 256, 0, s->stream>>>(bin_key_geom(s), s->rview(), n, (uint32_t)st->nslots, st->keys, st->cnt[nxt]);
-            else k_bin_keys<ParticleView><<<nb, 256, 0, s->stream>>>(bin_key_geom(s), s->view(), n, (uint32_t)st->nslots, st->keys, st->cnt[nxt]);
+            if (s->in_rec) k_bin_keys<RecView><<<nb, 256, 0, s->stream>>>(bin_key_geom(s), s->rview(), 0, n, (uint32_t)st->nslots, st->keys, st->cnt[nxt]);
+            else k_bin_keys<ParticleView><<<nb, 256, 0, s->stream>>>(bin_key_geom(s), s->view(), 0, n, (uint32_t)st->nslots, st->keys, st->cnt[nxt]);
             s->launches += 1;
         }
     }
@@ -354,6 +354,21 @@ int bin_particles(MpmSolver* s)
     s->steps_since_sort = 0;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { s->err = std::string("bin launch: ") + cudaGetErrorString(e); return MPM_ERR_CUDA; }
+    return MPM_OK;
+}
+
+// multi-GPU: keys of the particles that arrived by migration (slots [first, first + count)) join the keys and counts the
+// last G2P produced for the ones that stayed
+uint32_t* bin_next_keys(MpmSolver* s) { return (s->bin && s->bin->next_valid) ? s->bin->keys : nullptr; }
+
+int bin_keys_range(MpmSolver* s, int64_t first, int64_t count)
+{
+    BinState* st = s->bin;
+    if (!st || !st->next_valid || count <= 0) return MPM_OK;
+    const unsigned nb = (unsigned)((count + 255) / 256);
+    if (s->in_rec) k_bin_keys<RecView><<<nb, 256, 0, s->stream>>>(bin_key_geom(s), s->rview(), first, count, (uint32_t)st->nslots, st->keys, st->cnt[st->cur ^ 1]);
+    else k_bin_keys<ParticleView><<<nb, 256, 0, s->stream>>>(bin_key_geom(s), s->view(), first, count, (uint32_t)st->nslots, st->keys, st->cnt[st->cur ^ 1]);
+    s->launches += 1;
     return MPM_OK;
 }
 

@@ -36,6 +36,8 @@ int sort_create(MpmSolver* s);
 void sort_destroy(MpmSolver* s);
 int bin_create(MpmSolver* s);
 void bin_destroy(MpmSolver* s);
+uint32_t* bin_next_keys(MpmSolver* s);
+int bin_keys_range(MpmSolver* s, int64_t first, int64_t count);
 
 // ================================================================ transports
 struct Transport {
@@ -210,6 +212,8 @@ struct CommState {
     uint32_t* recv_rec[2] = {nullptr, nullptr};
     uint32_t* holes = nullptr;
     uint32_t* fillers = nullptr;
+    uint32_t* leave[2] = {nullptr, nullptr};  // slots of the particles leaving to the left / right (device lists)
+    bool classified = false;                  // this step's G2P already filled leave[] and the counts
     int64_t rec_cap = 0;
     int64_t migrated_out = 0, migrated_in = 0, overflow_rounds = 0;
     uint32_t sent_prev[2] = {0, 0}, recv_prev[2] = {0, 0};  // particles that crossed each edge in the previous step
@@ -238,7 +242,7 @@ void comm_destroy(MpmSolver* s)
     if (!c) return;
     free_slab_buffers(c);
     for (int k = 0; k < 2; ++k) { cudaFree(c->send_rec[k]); cudaFree(c->recv_rec[k]); }
-    cudaFree(c->d_cnt); cudaFree(c->holes); cudaFree(c->fillers);
+    cudaFree(c->d_cnt); cudaFree(c->holes); cudaFree(c->fillers); cudaFree(c->leave[0]); cudaFree(c->leave[1]);
     if (c->h_cnt) cudaFreeHost(c->h_cnt);
     delete c->tr;
     delete c;
@@ -265,6 +269,7 @@ static int comm_attach(MpmSolver* s, Transport* tr, int rank, int world)
         CKM(cudaMalloc(&c->send_rec[k], sizeof(uint32_t) * (64 + REC_WORDS * c->rec_cap)));
         CKM(cudaMalloc(&c->recv_rec[k], sizeof(uint32_t) * (64 + REC_WORDS * c->rec_cap)));
     }
+    for (int k = 0; k < 2; ++k) CKM(cudaMalloc(&c->leave[k], sizeof(uint32_t) * c->rec_cap));
     CKM(cudaMalloc(&c->holes, sizeof(uint32_t) * 2 * c->rec_cap));
     CKM(cudaMalloc(&c->fillers, sizeof(uint32_t) * 2 * c->rec_cap));
     if (!s->part_alt) {
@@ -472,6 +477,7 @@ struct MigGeom {
     int xl0, xr1;    // the left neighbour's first plane, the right neighbour's end plane (jump guard)
 };
 
+// d_cnt words: 0 nL, 1 nR (particles leaving left / right), 4 holes, 5 fillers, 8 "crossed more than one slab" flag
 __device__ __forceinline__ int mig_side(const MigGeom& g, float px, uint32_t* bad)
 {
     const int cx = __float2int_rz(px);
@@ -480,69 +486,79 @@ __device__ __forceinline__ int mig_side(const MigGeom& g, float px, uint32_t* ba
     return -1;
 }
 
+// generic classification pass (kernel paths whose G2P does not classify): lists of the leaving slots + counts
 template <class View>
-__global__ void __launch_bounds__(256) k_mig_count(MigGeom g, View pv, int64_t n, uint32_t* __restrict__ cnt)
+__global__ void __launch_bounds__(256) k_mig_scan(MigGeom g, View pv, int64_t n, uint32_t rec_cap, uint32_t* __restrict__ leaveL,
+                                                  uint32_t* __restrict__ leaveR, uint32_t* __restrict__ cnt)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int side = (i < n) ? mig_side(g, pv.at(PX, i), cnt + 8) : -1;
-    const unsigned mL = __ballot_sync(0xffffffffu, side == 0), mR = __ballot_sync(0xffffffffu, side == 1);
-    if ((threadIdx.x & 31) == 0) {
-        if (mL) atomicAdd(cnt + 0, (uint32_t)__popc(mL));
-        if (mR) atomicAdd(cnt + 1, (uint32_t)__popc(mR));
-    }
+    if (i >= n) return;
+    const int side = mig_side(g, pv.at(PX, i), cnt + 8);
+    if (side < 0) return;
+    const uint32_t slot = atomicAdd(cnt + side, 1u);
+    if (slot < rec_cap) (side ? leaveR : leaveL)[slot] = (uint32_t)i;
 }
 
 // Migration message: MIG_HDR header words ([0] = number of particles leaving over this edge), then the first `cap`
 // records as SoA with stride cap (word MIG_HDR + k * cap + slot), then any overflow records as 17-word AoS.  `cap` is
 // agreed by both ends without talking: it is a function of the count that crossed this edge in the previous step, which
-// sender and receiver both know.  So a step needs ONE exchange and ONE host sync; only when the count more than doubles
-// from one step to the next does a second (overflow) exchange follow.
+// sender and receiver both know.  So a step needs ONE exchange and ONE host sync; only when the count grows by more than
+// the head-room from one step to the next does a second (overflow) exchange follow.
 constexpr int MIG_HDR = 32;
 
 static inline uint32_t mig_capacity(uint32_t prev)  // the same on both ends of an edge: depends on nothing rank-local
 {
-    const uint64_t want = 2ull * prev + 4096ull;
-    uint64_t c = 4096;
-    while (c < want) c <<= 1;
-    return (uint32_t)std::min<uint64_t>(c, 1u << 30);
+    const uint64_t want = (uint64_t)prev + prev / 4 + 4096ull;
+    return (uint32_t)std::min<uint64_t>((want + 4095ull) & ~4095ull, 1u << 30);
 }
 
-// leavers -> message; holes / fillers for the compaction.  Counts come from device memory (k_mig_count ran before).
+// leavers (from the lists) -> messages; leavers below n_stay leave holes.  Everything is sized by device-side counts.
 template <class View>
-__global__ void __launch_bounds__(256) k_mig_pack(MigGeom g, View pv, const uint32_t* __restrict__ ids, int64_t n, uint32_t capL, uint32_t capR,
-                                                  uint32_t rec_cap, uint32_t* __restrict__ sendL, uint32_t* __restrict__ sendR, uint32_t* __restrict__ holes,
-                                                  uint32_t* __restrict__ fillers, uint32_t* __restrict__ cnt)
+__global__ void __launch_bounds__(256) k_mig_pack(View pv, const uint32_t* __restrict__ ids, int64_t n, uint32_t capL, uint32_t capR,
+                                                  uint32_t rec_cap, const uint32_t* __restrict__ leaveL, const uint32_t* __restrict__ leaveR,
+                                                  uint32_t* __restrict__ sendL, uint32_t* __restrict__ sendR, uint32_t* __restrict__ holes,
+                                                  uint32_t* __restrict__ cnt)
 {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) { sendL[0] = cnt[0]; sendR[0] = cnt[1]; }
-    if (i >= n) return;
+    const uint32_t nL = min(cnt[0], rec_cap), nR = min(cnt[1], rec_cap);
     const int64_t n_stay = n - cnt[0] - cnt[1];
-    uint32_t dummy;
-    const int side = mig_side(g, pv.at(PX, i), &dummy);
-    if (side < 0) {
-        if (i >= n_stay) fillers[atomicAdd(cnt + 5, 1u)] = (uint32_t)i;
-        return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { sendL[0] = cnt[0]; sendR[0] = cnt[1]; }
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nL + nR; j += gridDim.x * blockDim.x) {
+        const int side = j >= nL;
+        const uint32_t slot = side ? j - nL : j;
+        const uint32_t i = (side ? leaveR : leaveL)[slot];
+        if ((int64_t)i < n_stay) holes[atomicAdd(cnt + 4, 1u)] = i;
+        uint32_t* out = side ? sendR : sendL;
+        const uint32_t cap = side ? capR : capL;
+        if (slot < cap) {
+#pragma unroll
+            for (int k = 0; k < NPLANES; ++k) out[MIG_HDR + (size_t)k * cap + slot] = __float_as_uint(pv.at(k, i));
+            out[MIG_HDR + (size_t)NPLANES * cap + slot] = ids[i];
+        } else {
+            uint32_t* o = out + MIG_HDR + (size_t)REC_WORDS * cap + (size_t)REC_WORDS * (slot - cap);
+#pragma unroll
+            for (int k = 0; k < NPLANES; ++k) o[k] = __float_as_uint(pv.at(k, i));
+            o[NPLANES] = ids[i];
+        }
     }
-    if (i < n_stay) holes[atomicAdd(cnt + 4, 1u)] = (uint32_t)i;
-    uint32_t* out = side == 0 ? sendL : sendR;
-    const uint32_t cap = side == 0 ? capL : capR;
-    const uint32_t slot = atomicAdd(cnt + 6 + side, 1u);
-    if (slot >= rec_cap) return;  // buffer exhausted: the host reports it after the sync (count > rec_cap)
-    if (slot < cap) {
-#pragma unroll
-        for (int k = 0; k < NPLANES; ++k) out[MIG_HDR + (size_t)k * cap + slot] = __float_as_uint(pv.at(k, i));
-        out[MIG_HDR + (size_t)NPLANES * cap + slot] = ids[i];
-    } else {
-        uint32_t* o = out + MIG_HDR + (size_t)REC_WORDS * cap + (size_t)REC_WORDS * (slot - cap);
-#pragma unroll
-        for (int k = 0; k < NPLANES; ++k) o[k] = __float_as_uint(pv.at(k, i));
-        o[NPLANES] = ids[i];
+}
+
+// stayers in the tail [n_stay, n) are the fillers of the holes
+template <class View>
+__global__ void __launch_bounds__(256) k_mig_tail(MigGeom g, View pv, int64_t n, uint32_t* __restrict__ fillers, uint32_t* __restrict__ cnt)
+{
+    const uint32_t nt = cnt[0] + cnt[1];
+    const int64_t n_stay = n - nt;
+    uint32_t dummy;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
+        const int64_t i = n_stay + t;
+        if (mig_side(g, pv.at(PX, i), &dummy) < 0) fillers[atomicAdd(cnt + 5, 1u)] = (uint32_t)i;
     }
 }
 
 template <class View>
-__global__ void __launch_bounds__(256) k_mig_fill(View pv, uint32_t* __restrict__ ids, const uint32_t* __restrict__ holes,
-                                                  const uint32_t* __restrict__ fillers, const uint32_t* __restrict__ cnt)
+__global__ void __launch_bounds__(256) k_mig_fill(View pv, uint32_t* __restrict__ ids, uint32_t* __restrict__ keys,
+                                                  const uint32_t* __restrict__ holes, const uint32_t* __restrict__ fillers,
+                                                  const uint32_t* __restrict__ cnt)
 {
     const uint32_t nh = cnt[4];
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nh; j += gridDim.x * blockDim.x) {
@@ -550,6 +566,7 @@ __global__ void __launch_bounds__(256) k_mig_fill(View pv, uint32_t* __restrict_
 #pragma unroll
         for (int k = 0; k < NPLANES; ++k) pv.at(k, dst) = pv.at(k, src);
         ids[dst] = ids[src];
+        if (keys) keys[dst] = keys[src];  // next-step bin keys written by G2P travel with the particle
     }
 }
 
@@ -584,7 +601,6 @@ static int migrate_impl(MpmSolver* s, View pv)
     const bool hasL = c->rank > 0, hasR = c->rank < c->world - 1;
     const int64_t n = s->n;
     MigGeom g{c->x0, c->x1, hasL ? c->cuts[c->rank - 1] : c->x0, hasR ? c->cuts[c->rank + 2] : c->x1};
-    CKM(cudaMemsetAsync(c->d_cnt, 0, 16 * sizeof(uint32_t), s->stream));
     const unsigned nb = (unsigned)((n + 255) / 256);
     const uint32_t capS[2] = {mig_capacity(c->sent_prev[0]), mig_capacity(c->sent_prev[1])};
     const uint32_t capR[2] = {mig_capacity(c->recv_prev[0]), mig_capacity(c->recv_prev[1])};
@@ -592,16 +608,16 @@ static int migrate_impl(MpmSolver* s, View pv)
         s->err = "multi-GPU: migration buffer too small for the traffic over a slab boundary (raise max_particles)";
         return MPM_ERR_COMM;
     }
-    if (n > 0) {
-        k_mig_count<View><<<nb, 256, 0, s->stream>>>(g, pv, n, c->d_cnt);
-        k_mig_pack<View><<<nb, 256, 0, s->stream>>>(g, pv, s->orig_id, n, capS[0], capS[1], (uint32_t)c->rec_cap, c->send_rec[0], c->send_rec[1], c->holes,
-                                                    c->fillers, c->d_cnt);
-        k_mig_fill<View><<<592, 256, 0, s->stream>>>(pv, s->orig_id, c->holes, c->fillers, c->d_cnt);
-        s->launches += 3;
-    } else {
-        CKM(cudaMemsetAsync(c->send_rec[0], 0, sizeof(uint32_t) * MIG_HDR, s->stream));
-        CKM(cudaMemsetAsync(c->send_rec[1], 0, sizeof(uint32_t) * MIG_HDR, s->stream));
+    if (!c->classified) {  // this path's G2P did not classify: one pass over the positions
+        CKM(cudaMemsetAsync(c->d_cnt, 0, 16 * sizeof(uint32_t), s->stream));
+        if (n > 0) { k_mig_scan<View><<<nb, 256, 0, s->stream>>>(g, pv, n, (uint32_t)c->rec_cap, c->leave[0], c->leave[1], c->d_cnt); s->launches += 1; }
     }
+    c->classified = false;
+    k_mig_pack<View><<<296, 256, 0, s->stream>>>(pv, s->orig_id, n, capS[0], capS[1], (uint32_t)c->rec_cap, c->leave[0], c->leave[1], c->send_rec[0],
+                                                 c->send_rec[1], c->holes, c->d_cnt);
+    k_mig_tail<View><<<296, 256, 0, s->stream>>>(g, pv, n, c->fillers, c->d_cnt);
+    k_mig_fill<View><<<296, 256, 0, s->stream>>>(pv, s->orig_id, bin_next_keys(s), c->holes, c->fillers, c->d_cnt);
+    s->launches += 3;
     auto msg_bytes = [](uint32_t cap) { return sizeof(uint32_t) * ((size_t)MIG_HDR + (size_t)REC_WORDS * cap); };
     int rc = c->tr->exchange(c->send_rec[0], hasL ? msg_bytes(capS[0]) : 0, c->recv_rec[0], hasL ? msg_bytes(capR[0]) : 0, c->send_rec[1],
                              hasR ? msg_bytes(capS[1]) : 0, c->recv_rec[1], hasR ? msg_bytes(capR[1]) : 0, s->stream, s->err);
@@ -639,9 +655,28 @@ static int migrate_impl(MpmSolver* s, View pv)
     }
     c->sent_prev[0] = nL; c->sent_prev[1] = nR; c->recv_prev[0] = mL; c->recv_prev[1] = mR;
     s->n = n_stay + mL + mR;
+    rc = bin_keys_range(s, n_stay, (int64_t)mL + mR);  // arrivals: bin keys + counts for the next step
+    if (rc) return rc;
     c->migrated_out += nL + nR;
     c->migrated_in += mL + mR;
     if (nL + nR + mL + mR) { s->sorted_valid = false; s->positions_valid = false; }
+    return MPM_OK;
+}
+
+// The cell-path G2P classifies its particles itself (it has the new position in registers): zero the counters before it
+// runs and hand it the geometry and lists.
+int comm_begin_classify(MpmSolver* s, MigClassify* out)
+{
+    CommState* c = s->comm;
+    out->cnt = nullptr;
+    if (!c || c->world < 2) return MPM_OK;
+    const bool hasL = c->rank > 0, hasR = c->rank < c->world - 1;
+    CKM(cudaMemsetAsync(c->d_cnt, 0, 16 * sizeof(uint32_t), s->stream));
+    out->x0 = c->x0; out->x1 = c->x1;
+    out->xl0 = hasL ? c->cuts[c->rank - 1] : c->x0;
+    out->xr1 = hasR ? c->cuts[c->rank + 2] : c->x1;
+    out->cnt = c->d_cnt; out->leaveL = c->leave[0]; out->leaveR = c->leave[1]; out->rec_cap = (uint32_t)c->rec_cap;
+    c->classified = true;
     return MPM_OK;
 }
 

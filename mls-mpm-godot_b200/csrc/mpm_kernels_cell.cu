@@ -461,14 +461,15 @@ struct G2PBody {
     uint32_t nslots;
     uint32_t* keys;
     uint32_t* cnt_next;
+    const MigClassify& mg;
     int lane;
     CellPos<B> cp;
     float gvx[27], gvy[27], gvz[27];
     float nx_[4], cur[4];  // next / current particle: position, mass
     float4* rec;           // output records
     __device__ __forceinline__ G2PBody(const DevParams& P_, const ParticleView& pv_, const TL& tl_, const float (*tv_)[TL::WORDS],
-                                       const KeyGeom& kg_, uint32_t nslots_, uint32_t* keys_, uint32_t* cnt_next_, int lane_, float4* rec_)
-        : P(P_), pv(pv_), tl(tl_), tv(tv_), kg(kg_), nslots(nslots_), keys(keys_), cnt_next(cnt_next_), lane(lane_), rec(rec_) {}
+                                       const KeyGeom& kg_, uint32_t nslots_, uint32_t* keys_, uint32_t* cnt_next_, const MigClassify& mg_, int lane_, float4* rec_)
+        : P(P_), pv(pv_), tl(tl_), tv(tv_), kg(kg_), nslots(nslots_), keys(keys_), cnt_next(cnt_next_), mg(mg_), lane(lane_), rec(rec_) {}
     __device__ __forceinline__ void begin_chunk(int L)
     {
         cp.set(tl, L);
@@ -535,7 +536,18 @@ struct G2PBody {
         q[1] = make_float4(v[1], v[2], cur[3], cm[0]);
         q[2] = make_float4(cm[1], cm[2], cm[3], cm[4]);
         q[3] = make_float4(cm[5], cm[6], cm[7], cm[8]);
-        if (cnt_next) {  // bin key of the NEW position for the next step (single-GPU: the slab is the domain)
+        bool stays = true;
+        if (mg.cnt) {  // multi-GPU: list the particles whose new base cell left this rank's slab (few per warp)
+            const int cx = __float2int_rz(np[0]);
+            if (cx < mg.x0 || cx >= mg.x1) {
+                stays = false;
+                const int side = cx >= mg.x1;
+                if (cx < mg.xl0 || cx >= mg.xr1) mg.cnt[8] = 1u;
+                const uint32_t slot = atomicAdd(mg.cnt + side, 1u);
+                if (slot < mg.rec_cap) (side ? mg.leaveR : mg.leaveL)[slot] = i;
+            }
+        }
+        if (cnt_next && stays) {  // bin key of the NEW position for the next step (leavers get theirs where they arrive)
             uint32_t k = cell_key(kg, __float2int_rz(np[0]), __float2int_rz(np[1]), __float2int_rz(np[2]));
             k = k < nslots ? k : nslots - 1;
             keys[i] = k;
@@ -551,7 +563,7 @@ template <int B>
 __global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? 3 : 6) k_g2p_cell(DevParams P, TileGeom g, ParticleView pv, CellArgs a,
                                                                                     const int4* __restrict__ grid, KeyGeom kg, uint32_t nslots,
                                                                                     uint32_t* __restrict__ keys, uint32_t* __restrict__ cnt_next,
-                                                                                    float4* __restrict__ rec)
+                                                                                    MigClassify mg, float4* __restrict__ rec)
 {
     using TL = Tile<B>;
     using CF = CellCfg<B>;
@@ -573,7 +585,7 @@ __global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? 3 : 6) k_g2p_c
             tv[0][idx] = vx; tv[1][idx] = vy; tv[2][idx] = vz;
         }
         __syncthreads();
-        G2PBody<B> body(P, pv, tl, tv, kg, nslots, keys, cnt_next, lane, rec);
+        G2PBody<B> body(P, pv, tl, tv, kg, nslots, keys, cnt_next, mg, lane, rec);
         walk_chunks<B>(a, b, lane, warp, &s_bw, body);
     }
 }
@@ -647,13 +659,16 @@ int cell_g2p(MpmSolver* s)
     if (rc) return rc;
     if (s->n == 0) return MPM_OK;
     BinState* bs = s->bin;
-    // multi-GPU: particles may leave the slab and arrivals are appended afterwards, so keys are recomputed after
-    // the migration instead (bin_particles sees next_valid == false)
-    const bool fuse = (s->comm == nullptr);
-    uint32_t* cnt_next = fuse ? bs->cnt[bs->cur ^ 1] : nullptr;
+    // multi-GPU: particles that leave the slab are not counted here; the migration moves the keys of the particles it
+    // relocates and adds keys + counts for the arrivals (bin_keys_range)
+    const bool fuse = true;
+    uint32_t* cnt_next = bs->cnt[bs->cur ^ 1];
+    MigClassify mg;
+    rc = comm_begin_classify(s, &mg);
+    if (rc) return rc;
     // The (x, y, z, |v|) hand-off in original index order is a 16-B scatter per particle (0.30 ms of 1.17 ms on C4 when
     // fused here): on this path it is produced on demand by mpm_get_positions instead of every step.
-    LAUNCH_CELL(k_g2p_cell, 0, 0, reinterpret_cast<const int4*>(s->grid), bin_key_geom(s), (uint32_t)bs->nslots, bs->keys, cnt_next,
+    LAUNCH_CELL(k_g2p_cell, 0, 0, reinterpret_cast<const int4*>(s->grid), bin_key_geom(s), (uint32_t)bs->nslots, bs->keys, cnt_next, mg,
                 reinterpret_cast<float4*>(s->rec));
     s->in_rec = true;  // the new particle state is in the records until the next binning (or ensure_planes)
     bs->next_valid = fuse;

@@ -78,6 +78,14 @@ int tiled_g2p(MpmSolver* s);
 // particle state back into the grouped planes if the last G2P left it in `rec` (mpm_bin.cu)
 int ensure_planes(MpmSolver* s);
 // multi-GPU (mpm_comm.cu)
+struct MigClassify {  // handed to a G2P kernel that classifies leaving particles itself; cnt == nullptr: nothing to do
+    int x0, x1, xl0, xr1;
+    uint32_t* cnt;      // [0] leaving left, [1] leaving right, [8] crossed more than one slab
+    uint32_t* leaveL;
+    uint32_t* leaveR;
+    uint32_t rec_cap;
+};
+int comm_begin_classify(MpmSolver* s, MigClassify* out);
 void comm_destroy(MpmSolver* s);
 int comm_exchange_halo(MpmSolver* s, int pass);  // pass 0: after P2G_1 (4 words), 1: after P2G_2 (3 words)
 int comm_migrate(MpmSolver* s);
