@@ -8,7 +8,8 @@
 //     sorted by (block, chunk, rank r inside the cell, cell inside the chunk)
 //
 // where the cells of a block are first ORDERED BY PARTICLE COUNT, descending, and cut into chunks of 32: the 32
-// lanes of a warp then carry nearly equal work (in cell order the warp ran to the maximum count of its 32 cells:
+// lanes of a warp then carry nearly equal work -- and cells with more than 32 particles are first split into "virtual
+// cells" of 32 so that no lane walks a pile-up alone (in cell order the warp ran to the maximum count of its 32 cells:
 // 77 % lane efficiency measured on a settled lattice, ~50 % for Poisson-like counts).  Inside a chunk come first
 // the rank-0 particles of its non-empty cells, then the rank-1 particles, ...  A warp at rank r reads slots
 // chunk_start + S(r) + (number of lower lanes that still have a particle at rank r): consecutive addresses.
@@ -118,28 +119,52 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(const uint32_t* __restrict
     if (threadIdx.x == 0) { bbase[nblocks] = carry_s; misc[BIN_N_ACTIVE] = carry_a; }
 }
 
-// per non-empty block: order its cells by particle count, descending (counting sort on min(count, 63)), so that
-// the 32 cells of a chunk (= the 32 lanes of a warp in the cell kernels) carry nearly equal work; then the start
-// slot of every chunk.  ord[pos] = cell, inv[cell] = pos, cnts[pos] = count.
+// per non-empty block: split cells with more than VROWS particles into virtual cells of VROWS (within the block's budget
+// of NC extra positions), order the virtual cells by particle count, descending (counting sort on min(count, 63)), so
+// that the 32 virtual cells of a chunk (= the 32 lanes of a warp in the cell kernels) carry nearly equal work and no
+// lane ever walks more than VROWS particles; then the start slot of every chunk.
+//   ord[v0 + pos] = cell, cnts[v0 + pos] = count          (v0 = block * NV, NV = 2 * NC positions per block)
+//   vfirst[cell] = position of the cell's first full virtual cell, nfull[cell] = how many, vlast[cell] = position of the
+//   virtual cell that holds the remainder
+constexpr uint32_t VROWS = 32;
+
 template <int CELL_BITS>
 __global__ void __launch_bounds__(1 << CELL_BITS) k_block_order(const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ bbase,
                                                                const uint32_t* __restrict__ active, const uint32_t* __restrict__ misc,
-                                                               uint16_t* __restrict__ ord, uint16_t* __restrict__ inv, uint32_t* __restrict__ cnts,
-                                                               uint32_t* __restrict__ pstart, uint16_t* __restrict__ stab)
+                                                               uint16_t* __restrict__ ord, uint32_t* __restrict__ cnts,
+                                                               uint16_t* __restrict__ vfirst, uint16_t* __restrict__ vlast,
+                                                               uint16_t* __restrict__ nfull, uint32_t* __restrict__ pstart,
+                                                               uint16_t* __restrict__ stab)
 {
-    constexpr int NC = 1 << CELL_BITS, NBIN = 64, NW = NC / 32;
+    constexpr int NC = 1 << CELL_BITS, NV = 2 * NC, NBIN = 64, NW = NC / 32, EXTRA = NV - NC;
     __shared__ uint32_t hist[NBIN], base[NBIN], cursor[NBIN];
-    __shared__ uint32_t s_cnt[NC];
+    __shared__ uint32_t s_cnt[NV];
+    __shared__ uint16_t s_ord[NV];
     __shared__ uint32_t wsum[NW];
+    __shared__ uint32_t carry_s;
     if (blockIdx.x >= misc[BIN_N_ACTIVE]) return;
     const uint32_t b = active[blockIdx.x];
-    const uint32_t blk0 = b << CELL_BITS;
+    const uint32_t blk0 = b << CELL_BITS, v0 = b * NV;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     if (t < NBIN) { hist[t] = 0; cursor[t] = 0; }
+    s_cnt[t] = 0; s_cnt[t + NC] = 0; s_ord[t] = 0; s_ord[t + NC] = 0;
+    if (t == 0) carry_s = 0;
     __syncthreads();
     const uint32_t c = cnt[blk0 + t];
-    const int bin = (int)min(c, (uint32_t)(NBIN - 1));
-    atomicAdd(&hist[bin], 1u);
+    // extra virtual cells this cell wants, granted in cell order while the block's budget lasts
+    const uint32_t want = c > VROWS ? (c + VROWS - 1) / VROWS - 1 : 0;
+    uint32_t x = want;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) wsum[w] = x;
+    __syncthreads();
+    uint32_t pre = x - want;
+    for (int k = 0; k < w; ++k) pre += wsum[k];
+    const uint32_t g = pre >= (uint32_t)EXTRA ? 0u : min(want, (uint32_t)EXTRA - pre);
+    const uint32_t rem = c - g * VROWS;
+    const int binr = (int)min(rem, (uint32_t)(NBIN - 1));
+    if (g) atomicAdd(&hist[VROWS], g);
+    atomicAdd(&hist[binr], 1u);
     __syncthreads();
     if (t < NBIN) {
         uint32_t above = 0;
@@ -147,58 +172,78 @@ __global__ void __launch_bounds__(1 << CELL_BITS) k_block_order(const uint32_t* 
         base[t] = above;
     }
     __syncthreads();
-    const uint32_t pos = base[bin] + atomicAdd(&cursor[bin], 1u);
-    s_cnt[pos] = c;
-    ord[blk0 + pos] = (uint16_t)t;
-    inv[blk0 + t] = (uint16_t)pos;
+    const uint32_t pos_full = g ? base[VROWS] + atomicAdd(&cursor[VROWS], g) : 0u;
+    const uint32_t pos_rem = base[binr] + atomicAdd(&cursor[binr], 1u);
+    for (uint32_t k = 0; k < g; ++k) { s_cnt[pos_full + k] = VROWS; s_ord[pos_full + k] = (uint16_t)t; }
+    s_cnt[pos_rem] = rem; s_ord[pos_rem] = (uint16_t)t;
+    vfirst[blk0 + t] = (uint16_t)pos_full; vlast[blk0 + t] = (uint16_t)pos_rem; nfull[blk0 + t] = (uint16_t)g;
     __syncthreads();
-    const uint32_t v = s_cnt[t];
-    cnts[blk0 + t] = v;
-    uint32_t x = v;
+    // counts, chunk starts and S tables: NV positions, NC threads -> two halves
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-    if (lane == 31) wsum[w] = x;
-    __syncthreads();
-    if (lane == 0) {
-        uint32_t off = 0;
-        for (int k = 0; k < w; ++k) off += wsum[k];
-        pstart[b * NW + w] = bbase[b] + off;
-    }
-    // S(r) = sum over the chunk's cells of min(count, r) for r = 1..15 (first slot of the rank-r row), so that k_place
-    // needs one 2-byte load instead of the chunk's 32 counts.  Entry 0 flags chunks whose counts are not strictly
-    // ordered (a count >= 63 shares the last sort bin): those take k_place's general path.
-    const uint32_t maxc = __reduce_max_sync(0xffffffffu, v);
-    uint16_t* st = stab + ((size_t)b * NW + w) * 16;
-    if (lane == 0) st[0] = (maxc >= (uint32_t)(NBIN - 1)) ? 1 : 0;
+    for (int half = 0; half < 2; ++half) {
+        const int p = t + half * NC;
+        const uint32_t v = s_cnt[p];
+        cnts[v0 + p] = v;
+        ord[v0 + p] = s_ord[p];
+        uint32_t xs = v;
 #pragma unroll
-    for (int r = 1; r < 16; ++r) {
-        const uint32_t sr = __reduce_add_sync(0xffffffffu, min(v, (uint32_t)r));
-        if (lane == 0) st[r] = (uint16_t)sr;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, xs, o); if (lane >= o) xs += y; }
+        __syncthreads();  // (wsum / carry_s of the previous use are consumed)
+        if (lane == 31) wsum[w] = xs;
+        __syncthreads();
+        const int chunk = p >> 5;
+        if (lane == 0) {
+            uint32_t off = carry_s;
+            for (int k = 0; k < w; ++k) off += wsum[k];
+            pstart[(v0 >> 5) + chunk] = bbase[b] + off;
+        }
+        // S(r) = sum over the chunk's virtual cells of min(count, r) for r = 1..15 (first slot of the rank-r row), so that
+        // k_place needs one 2-byte load instead of the chunk's 32 counts.  Entry 0 flags chunks whose counts are not
+        // strictly ordered (a count >= 63 shares the last sort bin): those take k_place's general path.
+        const uint32_t maxc = __reduce_max_sync(0xffffffffu, v);
+        uint16_t* st = stab + ((size_t)(v0 >> 5) + chunk) * 16;
+        if (lane == 0) st[0] = (maxc >= (uint32_t)(NBIN - 1)) ? 1 : 0;
+#pragma unroll
+        for (int r = 1; r < 16; ++r) {
+            const uint32_t sr = __reduce_add_sync(0xffffffffu, min(v, (uint32_t)r));
+            if (lane == 0) st[r] = (uint16_t)sr;
+        }
+        __syncthreads();
+        if (t == NC - 1) {
+            uint32_t tot = carry_s;
+            for (int k = 0; k < NW; ++k) tot += wsum[k];
+            carry_s = tot;
+        }
     }
 }
 
-// rank inside the cell from an atomic cursor; destination slot from the rank and the chunk's 32 counts
+// rank inside the cell from an atomic cursor -> (virtual cell, row) -> destination slot from the chunk's counts
 template <int CELL_BITS>
-__global__ void __launch_bounds__(256) k_place(const uint32_t* __restrict__ keys, int64_t n, const uint16_t* __restrict__ inv,
+__global__ void __launch_bounds__(256) k_place(const uint32_t* __restrict__ keys, int64_t n, const uint16_t* __restrict__ vfirst,
+                                               const uint16_t* __restrict__ vlast, const uint16_t* __restrict__ nfull,
                                                const uint32_t* __restrict__ cnts, const uint32_t* __restrict__ pstart,
                                                const uint16_t* __restrict__ stab, uint32_t* __restrict__ fill, uint32_t* __restrict__ src_of)
 {
+    constexpr uint32_t NV = 2u << CELL_BITS;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t key = keys[i];
-    const uint32_t r = atomicAdd(&fill[key], 1u);
-    const uint32_t blk0 = key & ~((1u << CELL_BITS) - 1u);
-    const uint32_t pos = inv[key];
+    const uint32_t rc = atomicAdd(&fill[key], 1u);  // rank inside the (real) cell
+    const uint32_t g = nfull[key];
+    uint32_t pos, r;
+    if (rc < g * VROWS) { pos = vfirst[key] + rc / VROWS; r = rc % VROWS; }
+    else { pos = vlast[key]; r = rc - g * VROWS; }
+    const uint32_t v0 = (key >> CELL_BITS) * NV;
     const uint32_t chunk = pos >> 5, lane = pos & 31u;
-    const uint32_t gchunk = (blk0 >> 5) + chunk;
+    const uint32_t gchunk = (v0 >> 5) + chunk;
     if (r < 16u && stab[(size_t)gchunk * 16] == 0) {
         // counts strictly ordered, descending: every lower lane still has a particle at rank r (r < own count <= theirs)
         const uint32_t below = r ? stab[(size_t)gchunk * 16 + r] : 0u;
         src_of[pstart[gchunk] + below + lane] = (uint32_t)i;
         return;
     }
-    const uint4* c4 = reinterpret_cast<const uint4*>(cnts + blk0 + chunk * 32u);
-    uint32_t below = 0;   // sum over the chunk's cells of min(count, r)
+    const uint4* c4 = reinterpret_cast<const uint4*>(cnts + v0 + chunk * 32u);
+    uint32_t below = 0;   // sum over the chunk's virtual cells of min(count, r)
     uint32_t before = 0;  // lower lanes that still have a particle at rank r
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -271,18 +316,22 @@ int bin_create(MpmSolver* s)
         CKB(cudaMalloc(&st->cnt[k], sizeof(uint32_t) * (st->nslots + 32)));
         CKB(cudaMemsetAsync(st->cnt[k], 0, sizeof(uint32_t) * (st->nslots + 32), s->stream));
     }
-    CKB(cudaMalloc(&st->cnts, sizeof(uint32_t) * (st->nslots + 32)));
-    CKB(cudaMemsetAsync(st->cnts, 0, sizeof(uint32_t) * (st->nslots + 32), s->stream));
-    CKB(cudaMalloc(&st->ord, sizeof(uint16_t) * st->nslots));
-    CKB(cudaMalloc(&st->inv, sizeof(uint16_t) * st->nslots));
-    CKB(cudaMalloc(&st->pstart, sizeof(uint32_t) * (st->nslots >> 5)));
-    CKB(cudaMalloc(&st->stab, sizeof(uint16_t) * 16 * (st->nslots >> 5)));
+    const int64_t nvpos = 2 * st->nslots;  // virtual-cell positions: 2 per cell slot
+    CKB(cudaMalloc(&st->cnts, sizeof(uint32_t) * (nvpos + 32)));
+    CKB(cudaMemsetAsync(st->cnts, 0, sizeof(uint32_t) * (nvpos + 32), s->stream));
+    CKB(cudaMalloc(&st->ord, sizeof(uint16_t) * nvpos));
+    CKB(cudaMalloc(&st->vfirst, sizeof(uint16_t) * st->nslots));
+    CKB(cudaMalloc(&st->vlast, sizeof(uint16_t) * st->nslots));
+    CKB(cudaMalloc(&st->nfull, sizeof(uint16_t) * st->nslots));
+    CKB(cudaMalloc(&st->pstart, sizeof(uint32_t) * (nvpos >> 5)));
+    CKB(cudaMalloc(&st->stab, sizeof(uint16_t) * 16 * (nvpos >> 5)));
     CKB(cudaMalloc(&st->bsum, sizeof(uint32_t) * st->nblocks));
     CKB(cudaMalloc(&st->bbase, sizeof(uint32_t) * (st->nblocks + 1)));
     CKB(cudaMalloc(&st->fill, sizeof(uint32_t) * st->nslots));
     CKB(cudaMalloc(&st->keys, sizeof(uint32_t) * s->pitch));
     CKB(cudaMalloc(&st->src_of, sizeof(uint32_t) * s->pitch));
     CKB(cudaMalloc(&st->active, sizeof(uint32_t) * st->nblocks));
+
     CKB(cudaMalloc(&st->misc, sizeof(uint32_t) * BIN_MISC_WORDS));
     CKB(cudaMemsetAsync(st->misc, 0, sizeof(uint32_t) * BIN_MISC_WORDS, s->stream));
     st->cur = 0;
@@ -294,7 +343,7 @@ void bin_destroy(MpmSolver* s)
 {
     BinState* st = s->bin;
     if (!st) return;
-    cudaFree(st->cnt[0]); cudaFree(st->cnt[1]); cudaFree(st->cnts); cudaFree(st->ord); cudaFree(st->inv); cudaFree(st->pstart); cudaFree(st->stab);
+    cudaFree(st->cnt[0]); cudaFree(st->cnt[1]); cudaFree(st->cnts); cudaFree(st->ord); cudaFree(st->vfirst); cudaFree(st->vlast); cudaFree(st->nfull); cudaFree(st->pstart); cudaFree(st->stab);
     cudaFree(st->bsum); cudaFree(st->bbase); cudaFree(st->fill); cudaFree(st->keys); cudaFree(st->src_of); cudaFree(st->active);
     cudaFree(st->misc);
     delete st;
@@ -326,16 +375,16 @@ int bin_particles(MpmSolver* s)
     if (st->cell_bits == 9) {
         k_block_sums<9><<<nbw, 256, 0, s->stream>>>(st->cnt[nxt], st->nblocks, st->bsum);
         k_scan_blocks<<<1, 1024, 0, s->stream>>>(st->bsum, st->nblocks, st->bbase, st->active, st->misc);
-        k_block_order<9><<<(unsigned)st->nblocks, 512, 0, s->stream>>>(st->cnt[nxt], st->bbase, st->active, st->misc, st->ord, st->inv, st->cnts, st->pstart, st->stab);
+        k_block_order<9><<<(unsigned)st->nblocks, 512, 0, s->stream>>>(st->cnt[nxt], st->bbase, st->active, st->misc, st->ord, st->cnts, st->vfirst, st->vlast, st->nfull, st->pstart, st->stab);
     } else {
         k_block_sums<6><<<nbw, 256, 0, s->stream>>>(st->cnt[nxt], st->nblocks, st->bsum);
         k_scan_blocks<<<1, 1024, 0, s->stream>>>(st->bsum, st->nblocks, st->bbase, st->active, st->misc);
-        k_block_order<6><<<(unsigned)st->nblocks, 64, 0, s->stream>>>(st->cnt[nxt], st->bbase, st->active, st->misc, st->ord, st->inv, st->cnts, st->pstart, st->stab);
+        k_block_order<6><<<(unsigned)st->nblocks, 64, 0, s->stream>>>(st->cnt[nxt], st->bbase, st->active, st->misc, st->ord, st->cnts, st->vfirst, st->vlast, st->nfull, st->pstart, st->stab);
     }
     s->launches += 3;
     if (n > 0) {
-        if (st->cell_bits == 9) k_place<9><<<nb, 256, 0, s->stream>>>(st->keys, n, st->inv, st->cnts, st->pstart, st->stab, st->fill, st->src_of);
-        else k_place<6><<<nb, 256, 0, s->stream>>>(st->keys, n, st->inv, st->cnts, st->pstart, st->stab, st->fill, st->src_of);
+        if (st->cell_bits == 9) k_place<9><<<nb, 256, 0, s->stream>>>(st->keys, n, st->vfirst, st->vlast, st->nfull, st->cnts, st->pstart, st->stab, st->fill, st->src_of);
+        else k_place<6><<<nb, 256, 0, s->stream>>>(st->keys, n, st->vfirst, st->vlast, st->nfull, st->cnts, st->pstart, st->stab, st->fill, st->src_of);
         if (s->in_rec) {  // the last G2P left the state as records: gather straight into the planes
             k_gather_rec<<<nb, 256, 0, s->stream>>>(reinterpret_cast<const float4*>(s->rec), s->view(), st->src_of, s->orig_id, s->orig_id_alt, n);
             s->in_rec = false;

@@ -15,12 +15,15 @@ struct BinState {
     uint32_t* cnt[2] = {nullptr, nullptr};  // particle count per (block, cell); cnt[cur] describes the current layout,
     int cur = 0;                            // cnt[cur ^ 1] is being accumulated by G2P for the next binning
     bool next_valid = false;                // keys[] and cnt[cur ^ 1] were produced by the last G2P
-    // layout metadata of the current binning (cells of a block ordered by count, descending, in chunks of 32)
-    uint32_t* cnts = nullptr;        // [nslots] count at sorted position
-    uint16_t* ord = nullptr;         // [nslots] sorted position -> cell id inside the block
-    uint16_t* inv = nullptr;         // [nslots] cell id -> sorted position
-    uint32_t* pstart = nullptr;      // [nslots / 32] first slot of every chunk
-    uint16_t* stab = nullptr;        // [nslots / 32][16] first slot of the rank-r row relative to pstart, r < 16 ([0] = irregular flag)
+    // layout metadata of the current binning: per block 2 * NC "virtual cell" positions (a cell with more than 32 particles
+    // is split), ordered by count, descending, in chunks of 32
+    uint32_t* cnts = nullptr;        // [2 * nslots] count at each position
+    uint16_t* ord = nullptr;         // [2 * nslots] position -> cell id inside the block
+    uint16_t* vfirst = nullptr;      // [nslots] cell -> position of its first full virtual cell
+    uint16_t* vlast = nullptr;       // [nslots] cell -> position of the virtual cell holding the remainder
+    uint16_t* nfull = nullptr;       // [nslots] cell -> number of full virtual cells
+    uint32_t* pstart = nullptr;      // [2 * nslots / 32] first slot of every chunk
+    uint16_t* stab = nullptr;        // [2 * nslots / 32][16] first slot of the rank-r row relative to pstart, r < 16 ([0] = irregular flag)
     uint32_t* bsum = nullptr;        // [nblocks] particles per block
     uint32_t* bbase = nullptr;       // [nblocks + 1] exclusive scan
     uint32_t* fill = nullptr;        // [nslots] placement cursor

@@ -30,17 +30,18 @@ template <int B>
 struct CellCfg {
     static constexpr int LOGB = (B == 8) ? 3 : 2;
     static constexpr int NC = B * B * B;
-    static constexpr int NCHUNK = NC / 32;
+    static constexpr int NV = 2 * NC;        // virtual-cell positions per block (a cell with > 32 particles is split)
+    static constexpr int NCHUNK = NV / 32;   // chunks of 32 virtual cells
     static constexpr int THREADS = (B == 8) ? 128 : 64;
     static constexpr int NWARP = THREADS / 32;
 };
 
 struct CellArgs {
-    const uint32_t* cnts;    // particle count at each sorted cell position (descending inside a block)
-    const uint16_t* ord;     // sorted position -> cell id inside the block
+    const uint32_t* cnts;    // particle count at each virtual-cell position (descending inside a block)
+    const uint16_t* ord;     // virtual-cell position -> cell id inside the block
     const uint32_t* pstart;  // first slot of every chunk
     const uint32_t* active;  // non-empty blocks
-    uint32_t* misc;          // [BIN_N_ACTIVE], work counters
+    uint32_t* misc;          // list length, work counters
 };
 
 struct BlockWork {  // shared-memory hand-off of fetch_block
@@ -95,17 +96,21 @@ __device__ __forceinline__ void cp_async4(float* smem, const float* gmem)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// Pile-ups (cells with thousands of particles against a wall or in a corner of the evolved dam-break) would leave one
+// lane walking for ages while 31 idle; the binning therefore splits any cell with more than 32 particles into several
+// VIRTUAL cells of at most 32 (mpm_bin.cu), each taken by its own lane.  The walk below only ever sees virtual cells:
+// a block has up to 2 * NC of them (NCHUNK chunks), ordered by count, descending.
 template <int B, class Body>
 __device__ __forceinline__ void walk_chunks(const CellArgs& a, int b, int lane, int warp, BlockWork* bw, Body& body)
 {
     using CF = CellCfg<B>;
     const unsigned lt = (1u << lane) - 1u;
-    const uint32_t blk0 = (uint32_t)b << (3 * CF::LOGB);
+    const uint32_t v0 = (uint32_t)b * CF::NV;  // first virtual-cell position of the block
     bool have = false;  // the first particle of the coming chunk has already been fetched
     int chunk_nx = warp;
-    uint32_t c_nx = a.cnts[blk0 + warp * 32 + lane];
-    uint32_t L_nx = a.ord[blk0 + warp * 32 + lane];
-    uint32_t st_nx = a.pstart[(blk0 >> 5) + warp];
+    uint32_t c_nx = a.cnts[v0 + warp * 32 + lane];
+    uint32_t L_nx = a.ord[v0 + warp * 32 + lane];
+    uint32_t st_nx = a.pstart[(v0 >> 5) + warp];
 #pragma unroll 1
     for (;;) {
         const int chunk = chunk_nx;
@@ -113,16 +118,16 @@ __device__ __forceinline__ void walk_chunks(const CellArgs& a, int b, int lane, 
         const uint32_t c = c_nx, L = L_nx;
         uint32_t slot0 = st_nx;
         unsigned m = __ballot_sync(0xffffffffu, c > 0);
-        if (!m) break;  // cells are ordered by count, descending: every later chunk of the block is empty too
+        if (!m) break;  // virtual cells are ordered by count, descending: every later chunk of the block is empty too
         // claim the chunk after this one now, so that its metadata (and first particle) arrive while this one runs
         int g = 0;
         if (lane == 0) g = atomicAdd(&bw->next_chunk, 1);
         chunk_nx = __shfl_sync(0xffffffffu, g, 0);
         c_nx = 0; L_nx = 0; st_nx = 0;
         if (chunk_nx < CF::NCHUNK) {
-            c_nx = a.cnts[blk0 + chunk_nx * 32 + lane];
-            L_nx = a.ord[blk0 + chunk_nx * 32 + lane];
-            st_nx = a.pstart[(blk0 >> 5) + chunk_nx];
+            c_nx = a.cnts[v0 + chunk_nx * 32 + lane];
+            L_nx = a.ord[v0 + chunk_nx * 32 + lane];
+            st_nx = a.pstart[(v0 >> 5) + chunk_nx];
         }
         if (!have && c > 0) body.fetch(slot0 + __popc(m & lt));
         have = false;
@@ -561,7 +566,7 @@ struct G2PBody {
 
 template <int B>
 __global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? 3 : 6) k_g2p_cell(DevParams P, TileGeom g, ParticleView pv, CellArgs a,
-                                                                                    const int4* __restrict__ grid, KeyGeom kg, uint32_t nslots,
+                                                                                    const int4* __restrict__ grid, int raw_grid, KeyGeom kg, uint32_t nslots,
                                                                                     uint32_t* __restrict__ keys, uint32_t* __restrict__ cnt_next,
                                                                                     MigClassify mg, float4* __restrict__ rec)
 {
@@ -580,7 +585,19 @@ __global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? 3 : 6) k_g2p_c
             float vx = 0.0f, vy = 0.0f, vz = 0.0f;
             if (tl.node(P, k, idx, ci)) {
                 const int4 c = grid[ci];
-                vx = (float)c.x * inv_mult; vy = (float)c.y * inv_mult; vz = (float)c.z * inv_mult;
+                if (!raw_grid) {  // the grid update already ran: cells hold velocities
+                    vx = (float)c.x * inv_mult; vy = (float)c.y * inv_mult; vz = (float)c.z * inv_mult;
+                } else if (c.w > 0) {
+                    // UpdateGrid fused into the tile load (update_grid.glsl:44-66): v = p / m, gravity on y, zero the
+                    // wall-normal component for idx < 2 || idx > R - bc_hi_off.  (m and p carry the same fixed-point scale.)
+                    const float im = __frcp_rn((float)c.w);
+                    const int tz = k % TL::T, ty = (k / TL::T) % TL::T, tx = k / (TL::T * TL::T);
+                    const int nx = tl.ox + tx, ny = tl.oy + ty, nz = tl.oz + tz;
+                    const int hi = P.bc_hi_off;
+                    vx = (nx < 2 || nx > P.Rx - hi) ? 0.0f : (float)c.x * im;
+                    vy = (ny < 2 || ny > P.Ry - hi) ? 0.0f : fmaf((float)c.y, im, P.dt * P.gravity);
+                    vz = (nz < 2 || nz > P.Rz - hi) ? 0.0f : (float)c.z * im;
+                }
             }
             tv[0][idx] = vx; tv[1][idx] = vy; tv[2][idx] = vz;
         }
@@ -617,7 +634,7 @@ static unsigned persistent_grid(K kernel, int threads, size_t smem)
     do {                                                                                                                  \
         BinState* st = s->bin;                                                                                            \
         TileGeom g{st->nby, st->nbz, s->dp.gx0 + (s->comm ? 1 : 0)};                                                      \
-        CellArgs a{st->cnts, st->ord, st->pstart, st->active, st->misc};                                                  \
+        CellArgs a{st->cnts, st->ord, st->pstart, st->active, st->misc};                                       \
         if (st->B == 8) {                                                                                                 \
             static unsigned grid8 = 0;                                                                                    \
             if (!grid8) grid8 = persistent_grid(KERNEL<8>, CellCfg<8>::THREADS, (SMEM8));                                 \
@@ -668,7 +685,7 @@ int cell_g2p(MpmSolver* s)
     if (rc) return rc;
     // The (x, y, z, |v|) hand-off in original index order is a 16-B scatter per particle (0.30 ms of 1.17 ms on C4 when
     // fused here): on this path it is produced on demand by mpm_get_positions instead of every step.
-    LAUNCH_CELL(k_g2p_cell, 0, 0, reinterpret_cast<const int4*>(s->grid), bin_key_geom(s), (uint32_t)bs->nslots, bs->keys, cnt_next, mg,
+    LAUNCH_CELL(k_g2p_cell, 0, 0, reinterpret_cast<const int4*>(s->grid), s->grid_raw ? 1 : 0, bin_key_geom(s), (uint32_t)bs->nslots, bs->keys, cnt_next, mg,
                 reinterpret_cast<float4*>(s->rec));
     s->in_rec = true;  // the new particle state is in the records until the next binning (or ensure_planes)
     bs->next_valid = fuse;

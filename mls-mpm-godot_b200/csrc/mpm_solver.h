@@ -32,6 +32,8 @@ struct MpmSolver {
     // full 32-B sectors wherever it sits, while the 16 fields of a grouped slot are 16 different sectors (measured on
     // the evolved C4 dam-break: 25.8 GB of L2 traffic for a 4.4 GB gather).
     float* rec = nullptr;       // [pitch] x 16 floats
+    bool grid_raw = false;      // cell path: the grid holds mass + momentum (P2G done, UpdateGrid not yet applied): G2P applies
+                                // the update while it loads its tiles, and a grid download applies it first
     bool in_rec = false;        // the particle state of slots [0, n) currently lives in `rec`, not in `part`
     uint32_t* orig_id = nullptr;      // original (global) index of the particle in each slot
     uint32_t* orig_id_alt = nullptr;

@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libmpm_b200.so")
+LIB_PATH = os.environ.get("MPM_B200_LIB") or os.path.join(os.path.dirname(_HERE), "libmpm_b200.so")  # (override: A/B builds)
 
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_OVERFLOW, ERR_COMM = 0, 1, 2, 3, 4, 5
 GRID_FLOAT, GRID_FIXED = 0, 1
