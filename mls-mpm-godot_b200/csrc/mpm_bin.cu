@@ -158,8 +158,8 @@ __global__ void __launch_bounds__(1 << CELL_BITS) k_block_order(const uint32_t* 
     for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
     if (lane == 31) wsum[w] = x;
     __syncthreads();
-    uint32_t pre = x - want;
-    for (int k = 0; k < w; ++k) pre += wsum[k];
+    uint32_t pre = x - want, want_total = 0;
+    for (int k = 0; k < NW; ++k) { if (k < w) pre += wsum[k]; want_total += wsum[k]; }
     const uint32_t g = pre >= (uint32_t)EXTRA ? 0u : min(want, (uint32_t)EXTRA - pre);
     const uint32_t rem = c - g * VROWS;
     const int binr = (int)min(rem, (uint32_t)(NBIN - 1));
@@ -182,6 +182,10 @@ __global__ void __launch_bounds__(1 << CELL_BITS) k_block_order(const uint32_t* 
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         const int p = t + half * NC;
+        if (half == 1 && want_total == 0) {  // no cell was split (the usual case): the upper positions are simply empty
+            cnts[v0 + p] = 0;
+            continue;
+        }
         const uint32_t v = s_cnt[p];
         cnts[v0 + p] = v;
         ord[v0 + p] = s_ord[p];

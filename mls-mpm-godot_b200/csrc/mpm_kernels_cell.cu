@@ -181,7 +181,7 @@ struct P2G1Body {
     float* stage;  // this lane's column of the warp's two staging buffers: stage[(buf * NPLANES + field) * 32]
     int wr = 0, rd = 0;
     CellPos<B> cp;
-    float am[27], ax[27], ay[27], az[27];
+    float2 axy[27], azm[27];  // accumulators packed for FFMA2: (momentum x, momentum y) and (momentum z, mass)
     __device__ __forceinline__ P2G1Body(const DevParams& P_, const ParticleView& pv_, const TL& tl_, int (*tile_)[TL::WORDS], int lane_,
                                         float* stage_)
         : P(P_), pv(pv_), tl(tl_), tile(tile_), lane(lane_), stage(stage_) {}
@@ -189,7 +189,7 @@ struct P2G1Body {
     {
         cp.set(tl, L);
 #pragma unroll
-        for (int n = 0; n < 27; ++n) { am[n] = 0.0f; ax[n] = 0.0f; ay[n] = 0.0f; az[n] = 0.0f; }
+        for (int n = 0; n < 27; ++n) { axy[n] = make_float2(0.0f, 0.0f); azm[n] = make_float2(0.0f, 0.0f); }
     }
     __device__ __forceinline__ void fetch(uint32_t i)
     {
@@ -218,21 +218,27 @@ struct P2G1Body {
         cell_axis(px, cp.fcx, wx, dx); cell_axis(py, cp.fcy, wy, dy); cell_axis(pz, cp.fcz, wz, dz);
 #pragma unroll
         for (int k = 0; k < 3; ++k) wx[k] *= ms;
+        // node value = mc * (v + C d) with mc = w * m; x and y run packed (FFMA2: two FMAs per issue slot), z rides with
+        // the mass as (mc * qz, mc * 1)
+        const float2 c01 = make_float2(cm[0], cm[1]), c34 = make_float2(cm[3], cm[4]), c67 = make_float2(cm[6], cm[7]);
+        const float2 wz2[3] = {make_float2(wz[0], wz[0]), make_float2(wz[1], wz[1]), make_float2(wz[2], wz[2])};
+        const float2 dz2[3] = {make_float2(dz[0], dz[0]), make_float2(dz[1], dz[1]), make_float2(dz[2], dz[2])};
 #pragma unroll
         for (int gx = 0; gx < 3; ++gx) {
-            const float qx0 = fmaf(cm[0], dx[gx], vx), qy0 = fmaf(cm[1], dx[gx], vy), qz0 = fmaf(cm[2], dx[gx], vz);
+            const float2 q0 = __ffma2_rn(c01, make_float2(dx[gx], dx[gx]), make_float2(vx, vy));
+            const float qz0 = fmaf(cm[2], dx[gx], vz);
 #pragma unroll
             for (int gy = 0; gy < 3; ++gy) {
-                const float qx1 = fmaf(cm[3], dy[gy], qx0), qy1 = fmaf(cm[4], dy[gy], qy0), qz1 = fmaf(cm[5], dy[gy], qz0);
+                const float2 q1 = __ffma2_rn(c34, make_float2(dy[gy], dy[gy]), q0);
+                const float qz1 = fmaf(cm[5], dy[gy], qz0);
                 const float wxy = wx[gx] * wy[gy];
+                const float2 wxy2 = make_float2(wxy, wxy);
 #pragma unroll
                 for (int gz = 0; gz < 3; ++gz) {
                     const int n = (gx * 3 + gy) * 3 + gz;
-                    const float mc = wxy * wz[gz];
-                    am[n] += mc;
-                    ax[n] = fmaf(mc, fmaf(cm[6], dz[gz], qx1), ax[n]);
-                    ay[n] = fmaf(mc, fmaf(cm[7], dz[gz], qy1), ay[n]);
-                    az[n] = fmaf(mc, fmaf(cm[8], dz[gz], qz1), az[n]);
+                    const float2 mc2 = __fmul2_rn(wxy2, wz2[gz]);
+                    axy[n] = __ffma2_rn(mc2, __ffma2_rn(c67, dz2[gz], q1), axy[n]);
+                    azm[n] = __ffma2_rn(mc2, make_float2(fmaf(cm[8], dz[gz], qz1), 1.0f), azm[n]);
                 }
             }
         }
@@ -248,10 +254,10 @@ struct P2G1Body {
                 for (int gz = 0; gz < 3; ++gz) {
                     const int n = (gx * 3 + gy) * 3 + gz;
                     const int idx = cp.base + gx * TL::PX + gy * TL::PY + gz;
-                    atomicAdd(&tile[3][idx], __float2int_rz(am[n]));
-                    atomicAdd(&tile[0][idx], __float2int_rz(ax[n]));
-                    atomicAdd(&tile[1][idx], __float2int_rz(ay[n]));
-                    atomicAdd(&tile[2][idx], __float2int_rz(az[n]));
+                    atomicAdd(&tile[3][idx], __float2int_rz(azm[n].y));
+                    atomicAdd(&tile[0][idx], __float2int_rz(axy[n].x));
+                    atomicAdd(&tile[1][idx], __float2int_rz(axy[n].y));
+                    atomicAdd(&tile[2][idx], __float2int_rz(azm[n].x));
                 }
     }
     __device__ __forceinline__ void finish() {}
@@ -315,7 +321,8 @@ struct P2G2Body {
     float* stage;  // this lane's column of the warp's two staging buffers: stage[(buf * 13 + k) * 32]
     int wr = 0, rd = 0;
     CellPos<B> cp;
-    float gm[27], ax[27], ay[27], az[27];
+    float gm[27], az[27];
+    float2 axy[27];  // momentum x, y packed for FFMA2
     __device__ __forceinline__ P2G2Body(const DevParams& P_, const ParticleView& pv_, const TL& tl_, int (*tile_)[TL::WORDS], const float* tmass_,
                                         int lane_, float* stage_)
         : P(P_), pv(pv_), tl(tl_), tile(tile_), tmass(tmass_), lane(lane_), inv_rest(1.0f / P_.rest_density), stage(stage_) {}
@@ -329,7 +336,7 @@ struct P2G2Body {
 #pragma unroll
                 for (int gz = 0; gz < 3; ++gz) gm[(gx * 3 + gy) * 3 + gz] = tmass[cp.base + gx * TL::PX + gy * TL::PY + gz];
 #pragma unroll
-        for (int n = 0; n < 27; ++n) { ax[n] = 0.0f; ay[n] = 0.0f; az[n] = 0.0f; }
+        for (int n = 0; n < 27; ++n) { axy[n] = make_float2(0.0f, 0.0f); az[n] = 0.0f; }
     }
     __device__ __forceinline__ void fetch(uint32_t i)
     {
@@ -377,20 +384,26 @@ struct P2G2Body {
         const float e00 = s * fmaf(2.0f * mu, cm[0], -pressure), e11 = s * fmaf(2.0f * mu, cm[4], -pressure),
                     e22 = s * fmaf(2.0f * mu, cm[8], -pressure);
         const float e01 = s * mu * (cm[1] + cm[3]), e02 = s * mu * (cm[2] + cm[6]), e12 = s * mu * (cm[5] + cm[7]);
+        // node value = w * (E d), E symmetric; x and y run packed (FFMA2)
+        const float2 ex = make_float2(e00, e01), ey = make_float2(e01, e11), ez = make_float2(e02, e12);
+        const float2 wz2[3] = {make_float2(wz[0], wz[0]), make_float2(wz[1], wz[1]), make_float2(wz[2], wz[2])};
+        const float2 dz2[3] = {make_float2(dz[0], dz[0]), make_float2(dz[1], dz[1]), make_float2(dz[2], dz[2])};
 #pragma unroll
         for (int gx = 0; gx < 3; ++gx) {
-            const float fx0 = e00 * dx[gx], fy0 = e01 * dx[gx], fz0 = e02 * dx[gx];
+            const float2 f0 = __fmul2_rn(ex, make_float2(dx[gx], dx[gx]));
+            const float fz0 = e02 * dx[gx];
 #pragma unroll
             for (int gy = 0; gy < 3; ++gy) {
-                const float fx1 = fmaf(e01, dy[gy], fx0), fy1 = fmaf(e11, dy[gy], fy0), fz1 = fmaf(e12, dy[gy], fz0);
+                const float2 f1 = __ffma2_rn(ey, make_float2(dy[gy], dy[gy]), f0);
+                const float fz1 = fmaf(e12, dy[gy], fz0);
                 const float wxy = wx[gx] * wy[gy];
+                const float2 wxy2 = make_float2(wxy, wxy);
 #pragma unroll
                 for (int gz = 0; gz < 3; ++gz) {
                     const int n = (gx * 3 + gy) * 3 + gz;
-                    const float w = wxy * wz[gz];
-                    ax[n] = fmaf(w, fmaf(e02, dz[gz], fx1), ax[n]);
-                    ay[n] = fmaf(w, fmaf(e12, dz[gz], fy1), ay[n]);
-                    az[n] = fmaf(w, fmaf(e22, dz[gz], fz1), az[n]);
+                    const float2 w2 = __fmul2_rn(wxy2, wz2[gz]);
+                    axy[n] = __ffma2_rn(w2, __ffma2_rn(ez, dz2[gz], f1), axy[n]);
+                    az[n] = fmaf(w2.x, fmaf(e22, dz[gz], fz1), az[n]);
                 }
             }
         }
@@ -406,8 +419,8 @@ struct P2G2Body {
                 for (int gz = 0; gz < 3; ++gz) {
                     const int n = (gx * 3 + gy) * 3 + gz;
                     const int idx = cp.base + gx * TL::PX + gy * TL::PY + gz;
-                    atomicAdd(&tile[0][idx], __float2int_rz(ax[n]));
-                    atomicAdd(&tile[1][idx], __float2int_rz(ay[n]));
+                    atomicAdd(&tile[0][idx], __float2int_rz(axy[n].x));
+                    atomicAdd(&tile[1][idx], __float2int_rz(axy[n].y));
                     atomicAdd(&tile[2][idx], __float2int_rz(az[n]));
                 }
     }
@@ -469,7 +482,8 @@ struct G2PBody {
     const MigClassify& mg;
     int lane;
     CellPos<B> cp;
-    float gvx[27], gvy[27], gvz[27];
+    float2 gxy[27];        // node velocities of the cell's stencil: (x, y) packed for FFMA2, z separate
+    float gvz[27];
     float nx_[4], cur[4];  // next / current particle: position, mass
     float4* rec;           // output records
     __device__ __forceinline__ G2PBody(const DevParams& P_, const ParticleView& pv_, const TL& tl_, const float (*tv_)[TL::WORDS],
@@ -485,7 +499,7 @@ struct G2PBody {
 #pragma unroll
                 for (int gz = 0; gz < 3; ++gz) {
                     const int n = (gx * 3 + gy) * 3 + gz, idx = cp.base + gx * TL::PX + gy * TL::PY + gz;
-                    gvx[n] = tv[0][idx]; gvy[n] = tv[1][idx]; gvz[n] = tv[2][idx];
+                    gxy[n] = make_float2(tv[0][idx], tv[1][idx]); gvz[n] = tv[2][idx];
                 }
     }
     __device__ __forceinline__ void fetch(uint32_t i)
@@ -499,39 +513,37 @@ struct G2PBody {
         const float old[3] = {cur[0], cur[1], cur[2]};
         float wx[3], wy[3], wz[3], dx[3], dy[3], dz[3];
         cell_axis(old[0], cp.fcx, wx, dx); cell_axis(old[1], cp.fcy, wy, dy); cell_axis(old[2], cp.fcz, wz, dz);
+        // Sum factorisation (z, then y, then x) with the x and y components packed: fma.rn.f32x2 (FFMA2, new on sm_100)
+        // does two FMAs per issue slot, and this loop is issue-bound (ncu: 59 % issue-active at 3 warps per scheduler).
         const float wdz[3] = {wz[0] * dz[0], wz[1] * dz[1], wz[2] * dz[2]};
-        float v[3] = {0, 0, 0};
-        float Bx[3] = {0, 0, 0}, By[3] = {0, 0, 0}, Bz[3] = {0, 0, 0};  // columns of B = sum w * v (x) d
+        const float2 wz2[3] = {make_float2(wz[0], wz[0]), make_float2(wz[1], wz[1]), make_float2(wz[2], wz[2])};
+        const float2 wdz2[3] = {make_float2(wdz[0], wdz[0]), make_float2(wdz[1], wdz[1]), make_float2(wdz[2], wdz[2])};
+        float2 vxy = make_float2(0.f, 0.f), Bxxy = vxy, Byxy = vxy, Bzxy = vxy;  // (x, y) components of v and of B's columns
+        float vz = 0.f, Bxz = 0.f, Byz = 0.f, Bzz = 0.f;
 #pragma unroll
         for (int gx = 0; gx < 3; ++gx) {
-            float S[3] = {0, 0, 0}, Ty[3] = {0, 0, 0}, Tz[3] = {0, 0, 0};
+            float2 Sxy = make_float2(0.f, 0.f), Tyxy = Sxy, Tzxy = Sxy;
+            float Sz = 0.f, Tyz = 0.f, Tzz = 0.f;
 #pragma unroll
             for (int gy = 0; gy < 3; ++gy) {
                 const int n = (gx * 3 + gy) * 3;
-                float s[3], t[3];
-                s[0] = fmaf(wz[2], gvx[n + 2], fmaf(wz[1], gvx[n + 1], wz[0] * gvx[n]));
-                s[1] = fmaf(wz[2], gvy[n + 2], fmaf(wz[1], gvy[n + 1], wz[0] * gvy[n]));
-                s[2] = fmaf(wz[2], gvz[n + 2], fmaf(wz[1], gvz[n + 1], wz[0] * gvz[n]));
-                t[0] = fmaf(wdz[2], gvx[n + 2], fmaf(wdz[1], gvx[n + 1], wdz[0] * gvx[n]));
-                t[1] = fmaf(wdz[2], gvy[n + 2], fmaf(wdz[1], gvy[n + 1], wdz[0] * gvy[n]));
-                t[2] = fmaf(wdz[2], gvz[n + 2], fmaf(wdz[1], gvz[n + 1], wdz[0] * gvz[n]));
+                const float2 sxy = __ffma2_rn(wz2[2], gxy[n + 2], __ffma2_rn(wz2[1], gxy[n + 1], __fmul2_rn(wz2[0], gxy[n])));
+                const float2 txy = __ffma2_rn(wdz2[2], gxy[n + 2], __ffma2_rn(wdz2[1], gxy[n + 1], __fmul2_rn(wdz2[0], gxy[n])));
+                const float sz = fmaf(wz[2], gvz[n + 2], fmaf(wz[1], gvz[n + 1], wz[0] * gvz[n]));
+                const float tz = fmaf(wdz[2], gvz[n + 2], fmaf(wdz[1], gvz[n + 1], wdz[0] * gvz[n]));
                 const float wyd = wy[gy] * dy[gy];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    S[k] = fmaf(wy[gy], s[k], S[k]);
-                    Ty[k] = fmaf(wyd, s[k], Ty[k]);
-                    Tz[k] = fmaf(wy[gy], t[k], Tz[k]);
-                }
+                const float2 wy2 = make_float2(wy[gy], wy[gy]), wyd2 = make_float2(wyd, wyd);
+                Sxy = __ffma2_rn(wy2, sxy, Sxy); Tyxy = __ffma2_rn(wyd2, sxy, Tyxy); Tzxy = __ffma2_rn(wy2, txy, Tzxy);
+                Sz = fmaf(wy[gy], sz, Sz); Tyz = fmaf(wyd, sz, Tyz); Tzz = fmaf(wy[gy], tz, Tzz);
             }
             const float wxd = wx[gx] * dx[gx];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                v[k] = fmaf(wx[gx], S[k], v[k]);
-                Bx[k] = fmaf(wxd, S[k], Bx[k]);
-                By[k] = fmaf(wx[gx], Ty[k], By[k]);
-                Bz[k] = fmaf(wx[gx], Tz[k], Bz[k]);
-            }
+            const float2 wx2 = make_float2(wx[gx], wx[gx]), wxd2 = make_float2(wxd, wxd);
+            vxy = __ffma2_rn(wx2, Sxy, vxy); Bxxy = __ffma2_rn(wxd2, Sxy, Bxxy);
+            Byxy = __ffma2_rn(wx2, Tyxy, Byxy); Bzxy = __ffma2_rn(wx2, Tzxy, Bzxy);
+            vz = fmaf(wx[gx], Sz, vz); Bxz = fmaf(wxd, Sz, Bxz); Byz = fmaf(wx[gx], Tyz, Byz); Bzz = fmaf(wx[gx], Tzz, Bzz);
         }
+        float v[3] = {vxy.x, vxy.y, vz};
+        const float Bx[3] = {Bxxy.x, Bxxy.y, Bxz}, By[3] = {Byxy.x, Byxy.y, Byz}, Bz[3] = {Bzxy.x, Bzxy.y, Bzz};
         const float Bm[9] = {Bx[0], Bx[1], Bx[2], By[0], By[1], By[2], Bz[0], Bz[1], Bz[2]};
         float np[3], cm[9];
         g2p_finish<3>(P, old, Bm, v, np, cm);
