@@ -7,8 +7,9 @@
 A "step" is one pass of the hot path (bin -> clear -> P2G_1 -> P2G_2 -> grid update -> G2P) over the whole
 particle set.  Workload at any N: BASELINE config 4 -- 3D dam-break, 256^3 grid, 32 768 000 particles (block
 [4,164)^3 at spacing 0.5), parameters of the reference's shipping GPU scene
-(MLSMPM3DFluidMultithreadGPU.cs:54-84), int32 x 1e7 fixed-point grid, strict arithmetic.  N > 1 slab-shards that
-same scene (strong scaling).  `value` is device-timed with state resident in HBM; `e2e` is the same metric through
+(MLSMPM3DFluidMultithreadGPU.cs:54-84), int32 x 1e7 fixed-point grid.  Arithmetic: --math fast (default; FMA and
+re-association, parity within the tolerances stated in tests/test_parity_gpu.py) or --math strict (bit-exact against
+the reference algorithm; the tiled kernels).  N > 1 slab-shards that same scene (strong scaling).  `value` is device-timed with state resident in HBM; `e2e` is the same metric through
 the host-facing call sequence of one reference frame (_Process, MLSMPM3DFluidMultithreadGPU.cs:234-251): parameter
 block in (set_sphere), step, positions (x,y,z,|v|) out to pinned host memory (the particle_pos_tex hand-off).
 Prints ONE JSON line on rank 0.
@@ -36,6 +37,16 @@ WORKLOAD_DESC = {
     "c3": "3D block-drop 128^3 grid, 4096000 particles",
     "c4": "3D dam-break 256^3 grid, 32768000 particles",
 }
+
+
+def ncu_traffic(workload):
+    """DRAM bytes per launch of each kernel from the committed `ncu --set full` capture (profiles/r1/traffic_<workload>.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1", f"traffic_{workload}.json")) as f:
+            d = json.load(f)
+        return {k: v["dram_bytes"] for k, v in d["kernels"].items()}, d["source"]
+    except Exception:
+        return {}, None
 
 
 def peaks():
@@ -260,6 +271,12 @@ def main():
         achieved = alg_bytes[dom] / (phases[dom] * 1e-3) / 1e9 if phases[dom] > 0 else 0.0
         t3 = phases["p2g1"] + phases["p2g2"] + phases["g2p"]
         headline = (188 * N + 60 * Gc) / (t3 * 1e-3) / 1e9 if t3 > 0 else 0.0
+        traffic, traffic_src = ncu_traffic(args.workload) if world == 1 else ({}, None)
+        kname = {"p2g1": "k_p2g1_cell", "p2g2": "k_p2g2_cell", "g2p": "k_g2p_cell"} if st.kernel_path == 3 else {}
+        per_kernel = {k: {"ms": phases[k], "algorithmic_bytes": alg_bytes[k],
+                          "achieved_gbs": alg_bytes[k] / (phases[k] * 1e-3) / 1e9 if phases[k] > 0 else 0.0,
+                          "frac": alg_bytes[k] / (phases[k] * 1e-3) / 1e9 / peak if phases[k] > 0 else 0.0,
+                          "traffic": traffic.get(kname.get(k))} for k in alg_bytes}
         line = {
             "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -273,7 +290,11 @@ def main():
             "phase_ms": phases,
             "p2g_g2p_gbs": headline, "p2g_g2p_frac": headline / peak,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_kind": peak_kind, "traffic": None, "algorithmic_bytes": alg_bytes[dom]},
+                         "peak_kind": peak_kind, "traffic": traffic.get(kname.get(dom)), "traffic_source": traffic_src,
+                         "algorithmic_bytes": alg_bytes[dom],
+                         "note": "algorithmic bytes = SURVEY 8d per-unit figures x (local particles, local cells); duration = CUDA "
+                                 "events around the kernel on the solver's stream, averaged over the timed steps"},
+            "kernels": per_kernel,
             "e2e": {"value": e2e_val, "unit": "particle-steps/s", "h2d_bytes_per_step": 140, "d2h_bytes_per_step": 16 * n_local,
                     "what": "per step: mpm_set_sphere (140-B parameter block), mpm_step(1), mpm_get_positions -> pinned host"},
             "gpu_launches": int(launches),
