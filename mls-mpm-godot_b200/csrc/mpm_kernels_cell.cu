@@ -576,8 +576,9 @@ struct G2PBody {
     __device__ __forceinline__ void finish() {}
 };
 
+// 4 CTAs per SM (128 registers, ~30 bytes of spills): measured 0.778 vs 0.823 ms on C4 against 3 CTAs at 158 registers
 template <int B>
-__global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? 3 : 6) k_g2p_cell(DevParams P, TileGeom g, ParticleView pv, CellArgs a,
+__global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? 4 : 8) k_g2p_cell(DevParams P, TileGeom g, ParticleView pv, CellArgs a,
                                                                                     const int4* __restrict__ grid, int raw_grid, KeyGeom kg, uint32_t nslots,
                                                                                     uint32_t* __restrict__ keys, uint32_t* __restrict__ cnt_next,
                                                                                     MigClassify mg, float4* __restrict__ rec)

@@ -84,6 +84,19 @@ namespace MpmB200
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_get_stats(IntPtr s, out MpmStats st);
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_host_alloc(long bytes, out IntPtr p);
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_host_free(IntPtr p);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_get_stream(IntPtr s, out IntPtr stream);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_upload_particles_soa(IntPtr s, float* pos, float* vel, float* C, float* mass, long n);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_download_particles_soa(IntPtr s, float* pos, float* vel, float* C, float* mass, long cap);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_debug_last_sort(IntPtr s, uint* keys_before, uint* perm, long cap);
+        // multi-GPU x-slabs (no reference counterpart): NCCL (one process per GPU) or LOCAL (k solvers in this process)
+        [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_comm_unique_id(byte* id128);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_comm_init(IntPtr s, byte* id128, int rank, int world);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_local_hub_create(int world, out IntPtr hub);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_local_hub_destroy(IntPtr hub);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_comm_init_local(IntPtr s, IntPtr hub, int rank, int world);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_comm_slab(IntPtr s, out int x0, out int x1, out int gx0, out int nxl);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_download_ids(IntPtr s, uint* ids, long cap);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_slab_cuts(long* hist, int rx, int world, int min_width, int* cuts);
 
         public static void Check(int rc, IntPtr s)
         {
