@@ -210,6 +210,13 @@ MPM_API int32_t mpm_run_phase(MpmSolver* s, int32_t phase);
 MPM_API int32_t mpm_get_positions(MpmSolver* s, float* dst4, int64_t cap, void** device_ptr,
                                   uint32_t* tex_width);
 
+/* Pipelined form of the hand-off for hosts that render while the next step runs (double buffering): enqueues the
+ * hand-off array and its copy into dst4 (pinned host memory from mpm_host_alloc) on a separate copy stream and returns
+ * at once, so the device-to-host transfer overlaps the following mpm_step.  dst4 is complete after
+ * mpm_wait_positions(); the caller alternates between two host buffers.  Two device arrays are kept internally. */
+MPM_API int32_t mpm_get_positions_async(MpmSolver* s, float* dst4, int64_t cap);
+MPM_API int32_t mpm_wait_positions(MpmSolver* s);
+
 MPM_API int32_t mpm_num_particles(const MpmSolver* s, int64_t* n);
 /* Per-phase timing (Time.GetTicksUsec around each phase, F:190-219) is off by default. */
 MPM_API int32_t mpm_set_timing(MpmSolver* s, int32_t enabled);

@@ -211,7 +211,9 @@ extern "C" int32_t mpm_destroy(MpmSolver* s)
     bin_destroy(s);
     for (cudaEvent_t ev : s->ev) cudaEventDestroy(ev);
     cudaFree(s->part); cudaFree(s->part_alt); cudaFree(s->rec); cudaFree(s->orig_id); cudaFree(s->orig_id_alt);
-    cudaFree(s->grid); cudaFree(s->positions); cudaFree(s->overflow_flag);
+    cudaFree(s->grid); cudaFree(s->positions); cudaFree(s->positions_b); cudaFree(s->overflow_flag);
+    if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); }
+    for (int k = 0; k < 2; ++k) { if (s->pos_ready[k]) cudaEventDestroy(s->pos_ready[k]); if (s->pos_copied[k]) cudaEventDestroy(s->pos_copied[k]); }
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
     return MPM_OK;
@@ -606,6 +608,45 @@ extern "C" int32_t mpm_get_positions(MpmSolver* s, float* dst4, int64_t cap, voi
         CK(cudaMemcpyAsync(dst4, s->positions, sizeof(float4) * s->n, cudaMemcpyDeviceToHost, s->stream));
         CK(cudaStreamSynchronize(s->stream));
     }
+    return MPM_OK;
+}
+
+extern "C" int32_t mpm_get_positions_async(MpmSolver* s, float* dst4, int64_t cap)
+{
+    if (!s || !dst4) return MPM_ERR_INVALID;
+    CK(cudaSetDevice(s->device));
+    { int rc = comm_partition(s); if (rc) return rc; }
+    if (cap < s->n) return fail(s, MPM_ERR_INVALID, "destination too small");
+    if (!s->copy_stream) {  // first use: second device array, copy stream, events
+        CK(cudaMalloc(&s->positions_b, sizeof(float4) * s->pitch));
+        CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            CK(cudaEventCreateWithFlags(&s->pos_ready[k], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&s->pos_copied[k], cudaEventDisableTiming));
+            CK(cudaEventRecord(s->pos_copied[k], s->copy_stream));
+        }
+    }
+    if (s->n == 0) return MPM_OK;
+    const int b = s->pos_buf;
+    float4* dev = b ? s->positions_b : s->positions;
+    CK(cudaStreamWaitEvent(s->stream, s->pos_copied[b], 0));  // the copy that last read this device array is done
+    if (s->in_rec) launch_positions_rec(s->rview(), s->comm ? nullptr : s->orig_id, dev, s->n, s->stream);
+    else launch_positions(s->view(), s->comm ? nullptr : s->orig_id, dev, s->n, s->stream);
+    s->launches += 1;
+    CK(cudaEventRecord(s->pos_ready[b], s->stream));
+    CK(cudaStreamWaitEvent(s->copy_stream, s->pos_ready[b], 0));
+    CK(cudaMemcpyAsync(dst4, dev, sizeof(float4) * s->n, cudaMemcpyDeviceToHost, s->copy_stream));
+    CK(cudaEventRecord(s->pos_copied[b], s->copy_stream));
+    s->pos_buf ^= 1;
+    if (b == 0) s->positions_valid = false;  // (the synchronous getter's array was just rewritten for this snapshot)
+    return MPM_OK;
+}
+
+extern "C" int32_t mpm_wait_positions(MpmSolver* s)
+{
+    if (!s) return MPM_ERR_INVALID;
+    CK(cudaSetDevice(s->device));
+    if (s->copy_stream) CK(cudaStreamSynchronize(s->copy_stream));
     return MPM_OK;
 }
 

@@ -41,6 +41,11 @@ struct MpmSolver {
     int64_t ncells = 0;    // local cells (nxl * Ry * Rz)
     float4* positions = nullptr;  // (x, y, z, |v|) in original index order
     bool positions_valid = false;
+    // pipelined hand-off (mpm_get_positions_async): second device array, copy stream, events
+    float4* positions_b = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t pos_ready[2] = {nullptr, nullptr}, pos_copied[2] = {nullptr, nullptr};
+    int pos_buf = 0;
     int32_t* overflow_flag = nullptr;  // device
 
     int path = MPM_PATH_REFERENCE;  // resolved kernel path

@@ -79,6 +79,8 @@ namespace MpmB200
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_sync(IntPtr s);
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_run_phase(IntPtr s, int phase);
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_get_positions(IntPtr s, IntPtr dst4, long cap, out IntPtr device_ptr, out uint tex_width);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_get_positions_async(IntPtr s, IntPtr dst4, long cap);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_wait_positions(IntPtr s);
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_num_particles(IntPtr s, out long n);
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_set_timing(IntPtr s, int enabled);
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_get_stats(IntPtr s, out MpmStats st);

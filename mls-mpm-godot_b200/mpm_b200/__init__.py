@@ -75,7 +75,7 @@ EXPORTS = [
     "mpm_get_positions", "mpm_num_particles", "mpm_set_timing", "mpm_get_stats", "mpm_debug_last_sort",
     "mpm_get_stream", "mpm_host_alloc", "mpm_host_free", "mpm_comm_unique_id", "mpm_comm_init",
     "mpm_local_hub_create", "mpm_local_hub_destroy", "mpm_comm_init_local", "mpm_comm_slab", "mpm_download_ids",
-    "mpm_slab_cuts",
+    "mpm_slab_cuts", "mpm_get_positions_async", "mpm_wait_positions",
 ]
 
 _lib = None
@@ -127,6 +127,8 @@ def load():
         "mpm_comm_slab": (i32, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
         "mpm_download_ids": (i32, [vp, vp, i64]),
         "mpm_slab_cuts": (i32, [C.POINTER(i64), i32, i32, i32, C.POINTER(i32)]),
+        "mpm_get_positions_async": (i32, [vp, vp, i64]),
+        "mpm_wait_positions": (i32, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -261,6 +263,13 @@ class Solver:
 
     def positions_into(self, host_ptr, cap):
         self._ck(self._L.mpm_get_positions(self._h, C.c_void_p(host_ptr), int(cap), None, None))
+
+    def positions_into_async(self, host_ptr, cap):
+        """Pipelined hand-off: returns at once; the pinned buffer is complete after wait_positions()."""
+        self._ck(self._L.mpm_get_positions_async(self._h, C.c_void_p(host_ptr), int(cap)))
+
+    def wait_positions(self):
+        self._ck(self._L.mpm_wait_positions(self._h))
 
     def positions_device(self):
         dp, w = C.c_void_p(), C.c_uint32()

@@ -396,3 +396,37 @@ def test_cell_path_full_size_block_drop(lib):
     assert np.abs(gp.astype(np.float64) - rp).max() / 128 <= 3 * FAST_TOL["pos"]
     assert helpers.rel_err(gv, rv) <= 5 * FAST_TOL["vel"] and helpers.rel_err(gc, rc_) <= 5 * FAST_TOL["C"]  # 3 steps compound
     helpers.assert_bit_equal(gm, rm, "mass")
+
+
+def test_pipelined_position_hand_off_matches_the_synchronous_one(lib):
+    """mpm_get_positions_async (double-buffered, copy stream) must deliver exactly what mpm_get_positions delivers,
+    for consecutive steps, on both binned paths."""
+    import ctypes as C
+    import mpm_b200
+    op = orc.variant("3d_gpu", 32)
+    op.interaction = 0
+    pos = orc.init_block(3, (4, 4, 4), (20, 20, 20), 0.5)
+    n = pos.shape[0]
+    for path, math in ((2, 0), (3, 1)):
+        bufs = [mpm_b200.host_alloc(16 * n) for _ in range(2)]
+        views = [np.ctypeslib.as_array((C.c_float * (4 * n)).from_address(b)).reshape(n, 4) for b in bufs]
+        with make_solver(op, n, kernel_path=path, math_mode=math) as a, make_solver(op, n, kernel_path=path, math_mode=math) as b:
+            a.initialise_sim((4, 4, 4), (20, 20, 20), 0.5)
+            b.initialise_sim((4, 4, 4), (20, 20, 20), 0.5)
+            got = []
+            for k in range(4):
+                a.step(1)
+                a.positions_into_async(bufs[k & 1], n)
+                if k >= 1:  # the previous snapshot must already be intact while this one is in flight
+                    pass
+                a.wait_positions()
+                got.append(views[k & 1].copy())
+            for k in range(4):
+                b.step(1)
+                want = b.positions()
+                if path == 2:
+                    helpers.assert_bit_equal(got[k], want, f"async hand-off, step {k}")
+                else:  # cell path: fp32 accumulation order varies run to run
+                    assert np.abs(got[k] - want).max() < 1e-4
+        for p in bufs:
+            mpm_b200.host_free(p)
