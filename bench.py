@@ -31,12 +31,32 @@ WORKLOADS = {  # name: (grid, block lo, block hi, spacing)  -- SURVEY.md 8d synt
     "c2": ((64, 64, 64), (4, 4, 4), (36, 36, 36), 0.5),          # 262 144 particles
     "c3": ((128, 128, 128), (24, 24, 24), (104, 104, 104), 0.5),  # 4 096 000
     "c4": ((256, 256, 256), (4, 4, 4), (164, 164, 164), 0.5),     # 32 768 000
+    # BASELINE config 5 (splash, deliberately non-uniform in x): the first block is listed here, the others in EXTRA_BLOCKS
+    "c5": ((512, 256, 256), (4, 4, 4), (508, 68, 252), 0.5),      # pool: 63 995 904
+}
+EXTRA_BLOCKS = {  # more lattice blocks appended to the scene (lo, hi, spacing)
+    "c5": [((96, 90, 48), (256, 250, 208), 0.5),    # falling block, 32 768 000
+           ((320, 90, 64), (448, 218, 192), 0.4)],  # dense block,   32 768 000
 }
 WORKLOAD_DESC = {
     "c2": "3D dam-break 64^3 grid, 262144 particles",
     "c3": "3D block-drop 128^3 grid, 4096000 particles",
     "c4": "3D dam-break 256^3 grid, 32768000 particles",
+    "c5": "3D splash 512x256x256 grid, 129.5M particles (pool + falling block + dense block)",
 }
+
+
+def lattice_count(lo, hi, sp):
+    """Points of `for (float i = lo; i < hi; i += sp)` per axis, multiplied (fp32 accumulation like the reference)."""
+    import numpy as np
+    n = 1
+    for a, b in zip(lo, hi):
+        k, x = 0, np.float32(a)
+        while x < np.float32(b):
+            k += 1
+            x = np.float32(x + np.float32(sp))
+        n *= k
+    return n
 
 
 def ncu_traffic(workload):
@@ -204,7 +224,8 @@ def main():
     # the reference's shipping GPU scene constants (MLSMPM3DFluidMultithreadGPU.cs:54-84), sphere disabled
     params = mpm_b200.default_params("3d_gpu", grid=grid, interaction=0, kernel_path=args.path,
                                      sort_interval=args.sort_interval, math_mode=1 if args.math == "fast" else 0)
-    n_total = int(round((hi[0] - lo[0]) / sp)) ** 3
+    blocks = [(lo, hi, sp)] + EXTRA_BLOCKS.get(args.workload, [])
+    n_total = sum(lattice_count(*b) for b in blocks)
     G = grid[0] * grid[1] * grid[2]
     solver = mpm_b200.Solver(params, n_total, device=local_rank)
     if world > 1:
@@ -213,7 +234,9 @@ def main():
         solver.comm_init(uid[0], rank, world)
     # every rank generates the same lattice on its device; with a communicator the library cuts equal-count
     # x-slabs from the particle histogram and keeps the particles of its own slab
-    assert solver.initialise_sim(lo, hi, sp) == n_total
+    for k, (blo, bhi, bsp) in enumerate(blocks):
+        solver.initialise_sim(blo, bhi, bsp, append=k > 0)
+    assert solver.num_particles == n_total, (solver.num_particles, n_total)
     n_local = solver.stats().local_particles
 
     # ---- warm-up, then the timed region: K steps, device-timed on the solver's stream
@@ -233,6 +256,10 @@ def main():
     barrier()
     st = solver.stats()
     solver.set_timing(False)
+    if os.environ.get("MPM_BENCH_ALLRANKS"):  # per-rank phase times (load balance / exchange skew), to stderr
+        print(f"[rank {rank}] n_local={st.local_particles} cells={st.num_cells} ms_step={st.ms_step:.3f} sort={st.ms_sort:.3f} "
+              f"p2g1={st.ms_p2g1:.3f} p2g2={st.ms_p2g2:.3f} update={st.ms_update:.3f} g2p={st.ms_g2p:.3f} exchange={st.ms_exchange:.3f}",
+              file=sys.stderr, flush=True)
     dev_ms = st.ms_step * args.steps
     launches = st.kernel_launches - launches0
     t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
@@ -289,7 +316,7 @@ def main():
             "config": {"workload": WORKLOAD_DESC[args.workload], "grid": list(grid), "particles": n_total, "variant": "3d_gpu (H)",
                        "grid_mode": "fixed 1e7", "math": args.math, "kernel_path": {1: "reference-shaped", 2: "tiled", 3: "cell"}[st.kernel_path],
                        "sort_interval": solver.params.sort_interval or 1, "parallelism": f"x-slab x{world}",
-                       "l2": "inputs (2.1 GB particle planes) exceed the 126 MB L2; no flush needed",
+                       "l2": f"inputs ({64e-9 * n_total / world:.1f} GB of particle planes per GPU) exceed the 126 MB L2; no flush needed",
                        "timing": "CUDA events on the solver stream inside mpm_step; wall-clock cross-check in wall_ms_per_step"},
             "wall_ms_per_step": wall_ms / args.steps,
             "phase_ms": phases,

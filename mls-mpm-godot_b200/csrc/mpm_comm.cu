@@ -19,6 +19,8 @@
 #include <dlfcn.h>
 #include <nccl.h>  // types only: every NCCL function is resolved with dlsym
 
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -653,6 +655,10 @@ static int migrate_impl(MpmSolver* s, View pv)
         if (oRR) { k_mig_unpack<View><<<(mR - capR[1] + 255) / 256, 256, 0, s->stream>>>(pv, s->orig_id, n, c->d_cnt, msgL, c->recv_rec[1], 1, capR[1], true); s->launches += 1; }
         c->overflow_rounds += 1;
     }
+    static const bool trace = getenv("MPM_COMM_TRACE") != nullptr;
+    if (trace)
+        fprintf(stderr, "[mig r%d] n=%lld nL=%u nR=%u mL=%u mR=%u capS=%u,%u capR=%u,%u overflow=%d\n", c->rank, (long long)n, nL, nR, mL, mR,
+                capS[0], capS[1], capR[0], capR[1], (int)(oSL || oSR || oRL || oRR));
     c->sent_prev[0] = nL; c->sent_prev[1] = nR; c->recv_prev[0] = mL; c->recv_prev[1] = mR;
     s->n = n_stay + mL + mR;
     rc = bin_keys_range(s, n_stay, (int64_t)mL + mR);  // arrivals: bin keys + counts for the next step
