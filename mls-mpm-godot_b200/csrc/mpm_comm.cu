@@ -424,13 +424,25 @@ int comm_partition(MpmSolver* s)
 }
 
 // ================================================================ halo exchange
-__global__ void __launch_bounds__(256) k_halo_add(int4* __restrict__ blockL, const int4* __restrict__ recvL, int4* __restrict__ blockR,
-                                                  const int4* __restrict__ recvR, int64_t cells)
+// block += received; snap (optional) keeps the completed block for the increment of the second exchange
+__global__ void __launch_bounds__(256) k_halo_add(int4* __restrict__ blockL, const int4* __restrict__ recvL, int4* __restrict__ snapL,
+                                                  int4* __restrict__ blockR, const int4* __restrict__ recvR, int4* __restrict__ snapR,
+                                                  int64_t cells)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= cells) return;
-    if (blockL) { int4 a = blockL[i]; const int4 b = recvL[i]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; blockL[i] = a; }
-    if (blockR) { int4 a = blockR[i]; const int4 b = recvR[i]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; blockR[i] = a; }
+    if (blockL) {
+        int4 a = blockL[i]; const int4 b = recvL[i];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        blockL[i] = a;
+        if (snapL) snapL[i] = a;
+    }
+    if (blockR) {
+        int4 a = blockR[i]; const int4 b = recvR[i];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        blockR[i] = a;
+        if (snapR) snapR[i] = a;
+    }
 }
 
 __global__ void __launch_bounds__(256) k_halo_diff(const int4* __restrict__ blockL, const int4* __restrict__ snapL, int4* __restrict__ outL,
@@ -464,12 +476,9 @@ int comm_exchange_halo(MpmSolver* s, int pass)
     int rc = c->tr->exchange(sendL, hasL ? bytes : 0, c->halo_recv[0], hasL ? bytes : 0, sendR, hasR ? bytes : 0, c->halo_recv[1],
                              hasR ? bytes : 0, s->stream, s->err);
     if (rc) return rc;
-    k_halo_add<<<nb, 256, 0, s->stream>>>(blockL, c->halo_recv[0], blockR, c->halo_recv[1], c->halo_cells);
+    k_halo_add<<<nb, 256, 0, s->stream>>>(blockL, c->halo_recv[0], pass == 0 ? c->halo_snap[0] : nullptr, blockR, c->halo_recv[1],
+                                          pass == 0 ? c->halo_snap[1] : nullptr, c->halo_cells);
     s->launches += 1;
-    if (pass == 0) {
-        if (hasL) CKM(cudaMemcpyAsync(c->halo_snap[0], blockL, bytes, cudaMemcpyDeviceToDevice, s->stream));
-        if (hasR) CKM(cudaMemcpyAsync(c->halo_snap[1], blockR, bytes, cudaMemcpyDeviceToDevice, s->stream));
-    }
     return MPM_OK;
 }
 
@@ -519,10 +528,19 @@ template <class View>
 __global__ void __launch_bounds__(256) k_mig_pack(View pv, const uint32_t* __restrict__ ids, int64_t n, uint32_t capL, uint32_t capR,
                                                   uint32_t rec_cap, const uint32_t* __restrict__ leaveL, const uint32_t* __restrict__ leaveR,
                                                   uint32_t* __restrict__ sendL, uint32_t* __restrict__ sendR, uint32_t* __restrict__ holes,
-                                                  uint32_t* __restrict__ cnt)
+                                                  uint32_t* __restrict__ fillers, MigGeom g, uint32_t* __restrict__ cnt)
 {
     const uint32_t nL = min(cnt[0], rec_cap), nR = min(cnt[1], rec_cap);
     const int64_t n_stay = n - cnt[0] - cnt[1];
+    // stayers in the tail [n_stay, n) are the fillers of the holes the leavers below n_stay leave
+    {
+        const uint32_t nt = cnt[0] + cnt[1];
+        uint32_t dummy;
+        for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
+            const int64_t i = n_stay + t;
+            if (mig_side(g, pv.at(PX, i), &dummy) < 0) fillers[atomicAdd(cnt + 5, 1u)] = (uint32_t)i;
+        }
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) { sendL[0] = cnt[0]; sendR[0] = cnt[1]; }
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nL + nR; j += gridDim.x * blockDim.x) {
         const int side = j >= nL;
@@ -544,19 +562,6 @@ __global__ void __launch_bounds__(256) k_mig_pack(View pv, const uint32_t* __res
     }
 }
 
-// stayers in the tail [n_stay, n) are the fillers of the holes
-template <class View>
-__global__ void __launch_bounds__(256) k_mig_tail(MigGeom g, View pv, int64_t n, uint32_t* __restrict__ fillers, uint32_t* __restrict__ cnt)
-{
-    const uint32_t nt = cnt[0] + cnt[1];
-    const int64_t n_stay = n - nt;
-    uint32_t dummy;
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
-        const int64_t i = n_stay + t;
-        if (mig_side(g, pv.at(PX, i), &dummy) < 0) fillers[atomicAdd(cnt + 5, 1u)] = (uint32_t)i;
-    }
-}
-
 template <class View>
 __global__ void __launch_bounds__(256) k_mig_fill(View pv, uint32_t* __restrict__ ids, uint32_t* __restrict__ keys,
                                                   const uint32_t* __restrict__ holes, const uint32_t* __restrict__ fillers,
@@ -575,12 +580,18 @@ __global__ void __launch_bounds__(256) k_mig_fill(View pv, uint32_t* __restrict_
 // arrivals of one message appended behind the stayers: left arrivals first, then right arrivals.
 // overflow = false: the SoA part (first min(count, cap) records); true: the AoS overflow records (count - cap).
 template <class View>
-__global__ void __launch_bounds__(256) k_mig_unpack(View pv, uint32_t* __restrict__ ids, int64_t n, const uint32_t* __restrict__ cnt,
-                                                    const uint32_t* __restrict__ msgL, const uint32_t* __restrict__ msg, int side, uint32_t cap,
-                                                    bool overflow)
+__global__ void __launch_bounds__(256) k_mig_unpack(View pv, uint32_t* __restrict__ ids, int64_t n, uint32_t* __restrict__ cnt,
+                                                    const uint32_t* __restrict__ msgL, const uint32_t* __restrict__ msgR, uint32_t capL,
+                                                    uint32_t capR, int only_side, bool overflow)
 {
+    // blockIdx.y = side (0: from the left neighbour, 1: from the right one); a missing neighbour has a null message
+    const int side = only_side >= 0 ? only_side : (int)blockIdx.y;
+    const uint32_t* msg = side ? msgR : msgL;
+    if (!msg) return;
+    const uint32_t cap = side ? capR : capL;
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t total = msg[0];
+    if (j == 0 && !overflow) cnt[2 + side] = total;  // arrivals from this side, for the host
     const int64_t base = n - cnt[0] - cnt[1] + (side == 1 && msgL ? (int64_t)msgL[0] : 0);
     if (!overflow) {
         if (j >= min(total, cap)) return;
@@ -616,26 +627,24 @@ static int migrate_impl(MpmSolver* s, View pv)
     }
     c->classified = false;
     k_mig_pack<View><<<296, 256, 0, s->stream>>>(pv, s->orig_id, n, capS[0], capS[1], (uint32_t)c->rec_cap, c->leave[0], c->leave[1], c->send_rec[0],
-                                                 c->send_rec[1], c->holes, c->d_cnt);
-    k_mig_tail<View><<<296, 256, 0, s->stream>>>(g, pv, n, c->fillers, c->d_cnt);
+                                                 c->send_rec[1], c->holes, c->fillers, g, c->d_cnt);
     k_mig_fill<View><<<296, 256, 0, s->stream>>>(pv, s->orig_id, bin_next_keys(s), c->holes, c->fillers, c->d_cnt);
-    s->launches += 3;
+    s->launches += 2;
     auto msg_bytes = [](uint32_t cap) { return sizeof(uint32_t) * ((size_t)MIG_HDR + (size_t)REC_WORDS * cap); };
     int rc = c->tr->exchange(c->send_rec[0], hasL ? msg_bytes(capS[0]) : 0, c->recv_rec[0], hasL ? msg_bytes(capR[0]) : 0, c->send_rec[1],
                              hasR ? msg_bytes(capS[1]) : 0, c->recv_rec[1], hasR ? msg_bytes(capR[1]) : 0, s->stream, s->err);
     if (rc) return rc;
     const uint32_t* msgL = hasL ? c->recv_rec[0] : nullptr;
-    for (int side = 0; side < 2; ++side) {
-        if (!(side ? hasR : hasL)) continue;
-        k_mig_unpack<View><<<(capR[side] + 255) / 256, 256, 0, s->stream>>>(pv, s->orig_id, n, c->d_cnt, msgL, c->recv_rec[side], side, capR[side], false);
+    const uint32_t* msgR = hasR ? c->recv_rec[1] : nullptr;
+    {
+        const dim3 grid((std::max(capR[0], capR[1]) + 255) / 256, 2);
+        k_mig_unpack<View><<<grid, 256, 0, s->stream>>>(pv, s->orig_id, n, c->d_cnt, msgL, msgR, capR[0], capR[1], -1, false);
         s->launches += 1;
     }
-    // counts to the host: [0] nL, [1] nR, [8] bad; received headers -> h_cnt[2], h_cnt[3]
+    // counts to the host in one copy: [0] nL, [1] nR, [2] mL, [3] mR (written by the unpack), [8] bad
     CKM(cudaMemcpyAsync(c->h_cnt, c->d_cnt, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-    if (hasL) CKM(cudaMemcpyAsync(c->h_cnt + 12, c->recv_rec[0], sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-    if (hasR) CKM(cudaMemcpyAsync(c->h_cnt + 13, c->recv_rec[1], sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
     CKM(cudaStreamSynchronize(s->stream));
-    const uint32_t nL = c->h_cnt[0], nR = c->h_cnt[1], mL = hasL ? c->h_cnt[12] : 0, mR = hasR ? c->h_cnt[13] : 0;
+    const uint32_t nL = c->h_cnt[0], nR = c->h_cnt[1], mL = hasL ? c->h_cnt[2] : 0, mR = hasR ? c->h_cnt[3] : 0;
     if (c->h_cnt[8]) { s->err = "multi-GPU: a particle crossed more than one slab in a single step (dt * |v| too large for the slab width)"; return MPM_ERR_COMM; }
     if ((int64_t)std::max(std::max(nL, nR), std::max(mL, mR)) > c->rec_cap) { s->err = "multi-GPU: migration buffer too small"; return MPM_ERR_COMM; }
     const int64_t n_stay = n - nL - nR;
@@ -651,8 +660,8 @@ static int migrate_impl(MpmSolver* s, View pv)
                              c->send_rec[1] + MIG_HDR + (size_t)REC_WORDS * capS[1], oSR, c->recv_rec[1] + MIG_HDR + (size_t)REC_WORDS * capR[1], oRR,
                              s->stream, s->err);
         if (rc) return rc;
-        if (oRL) { k_mig_unpack<View><<<(mL - capR[0] + 255) / 256, 256, 0, s->stream>>>(pv, s->orig_id, n, c->d_cnt, msgL, c->recv_rec[0], 0, capR[0], true); s->launches += 1; }
-        if (oRR) { k_mig_unpack<View><<<(mR - capR[1] + 255) / 256, 256, 0, s->stream>>>(pv, s->orig_id, n, c->d_cnt, msgL, c->recv_rec[1], 1, capR[1], true); s->launches += 1; }
+        if (oRL) { k_mig_unpack<View><<<(mL - capR[0] + 255) / 256, 256, 0, s->stream>>>(pv, s->orig_id, n, c->d_cnt, msgL, msgR, capR[0], capR[1], 0, true); s->launches += 1; }
+        if (oRR) { k_mig_unpack<View><<<(mR - capR[1] + 255) / 256, 256, 0, s->stream>>>(pv, s->orig_id, n, c->d_cnt, msgL, msgR, capR[0], capR[1], 1, true); s->launches += 1; }
         c->overflow_rounds += 1;
     }
     static const bool trace = getenv("MPM_COMM_TRACE") != nullptr;
