@@ -150,6 +150,9 @@ typedef struct MpmStats {
     int32_t overflow;         /* sticky overflow flag */
     int32_t rank, world;
     int64_t local_particles;  /* particles owned by this rank (multi-GPU) */
+    int64_t migrated;         /* particles this rank has sent to its neighbours since the communicator was attached */
+    int64_t slab_jump_clamps; /* multi-GPU: particles that would have crossed more than one slab in a single step (|v| dt
+                                 larger than the neighbouring slab is wide) and were held back in that slab's far plane */
 } MpmStats;
 
 typedef struct MpmSolver MpmSolver; /* opaque */

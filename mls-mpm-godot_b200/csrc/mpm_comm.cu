@@ -208,7 +208,7 @@ struct CommState {
     int4* halo_snap[2] = {nullptr, nullptr};
     int64_t halo_cells = 0;  // 2 * Ry * Rz
     // migration
-    uint32_t* d_cnt = nullptr;  // 0 nL, 1 nR (leaving), 2 mL, 3 mR (arriving), 4 holes, 5 fillers, 6 cursorL, 7 cursorR, 8 bad
+    uint32_t* d_cnt = nullptr;  // 0 nL, 1 nR (leaving), 2 mL, 3 mR (arriving), 4 holes, 5 fillers, 8 held-back outliers
     uint32_t* h_cnt = nullptr;  // pinned mirror
     uint32_t* send_rec[2] = {nullptr, nullptr};
     uint32_t* recv_rec[2] = {nullptr, nullptr};
@@ -218,6 +218,7 @@ struct CommState {
     bool classified = false;                  // this step's G2P already filled leave[] and the counts
     int64_t rec_cap = 0;
     int64_t migrated_out = 0, migrated_in = 0, overflow_rounds = 0;
+    int64_t slab_jump_clamps = 0;  // particles held back because they would have crossed more than one slab in a step
     uint32_t sent_prev[2] = {0, 0}, recv_prev[2] = {0, 0};  // particles that crossed each edge in the previous step
 };
 
@@ -287,6 +288,8 @@ void comm_fill_stats(const MpmSolver* s, MpmStats* st)
     if (!s->comm) return;
     st->rank = s->comm->rank;
     st->world = s->comm->world;
+    st->slab_jump_clamps = s->comm->slab_jump_clamps;
+    st->migrated = s->comm->migrated_out;
 }
 
 // ================================================================ slab set-up at upload time
@@ -489,12 +492,10 @@ struct MigGeom {
 };
 
 // d_cnt words: 0 nL, 1 nR (particles leaving left / right), 4 holes, 5 fillers, 8 "crossed more than one slab" flag
-__device__ __forceinline__ int mig_side(const MigGeom& g, float px, uint32_t* bad)
+__device__ __forceinline__ int mig_side(const MigGeom& g, float px)
 {
     const int cx = __float2int_rz(px);
-    if (cx < g.x0) { if (cx < g.xl0) *bad = 1u; return 0; }
-    if (cx >= g.x1) { if (cx >= g.xr1) *bad = 1u; return 1; }
-    return -1;
+    return cx < g.x0 ? 0 : (cx >= g.x1 ? 1 : -1);
 }
 
 // generic classification pass (kernel paths whose G2P does not classify): lists of the leaving slots + counts
@@ -504,8 +505,13 @@ __global__ void __launch_bounds__(256) k_mig_scan(MigGeom g, View pv, int64_t n,
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int side = mig_side(g, pv.at(PX, i), cnt + 8);
+    const float px = pv.at(PX, i);
+    const int side = mig_side(g, px);
     if (side < 0) return;
+    // a particle that would land beyond the neighbouring slab is held back in that slab's far plane for this step
+    const int cx = __float2int_rz(px);
+    if (cx < g.xl0) { pv.at(PX, i) = (float)g.xl0 + 0.5f; atomicAdd(cnt + 8, 1u); }
+    else if (cx >= g.xr1) { pv.at(PX, i) = (float)g.xr1 - 0.5f; atomicAdd(cnt + 8, 1u); }
     const uint32_t slot = atomicAdd(cnt + side, 1u);
     if (slot < rec_cap) (side ? leaveR : leaveL)[slot] = (uint32_t)i;
 }
@@ -535,10 +541,9 @@ __global__ void __launch_bounds__(256) k_mig_pack(View pv, const uint32_t* __res
     // stayers in the tail [n_stay, n) are the fillers of the holes the leavers below n_stay leave
     {
         const uint32_t nt = cnt[0] + cnt[1];
-        uint32_t dummy;
         for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
             const int64_t i = n_stay + t;
-            if (mig_side(g, pv.at(PX, i), &dummy) < 0) fillers[atomicAdd(cnt + 5, 1u)] = (uint32_t)i;
+            if (mig_side(g, pv.at(PX, i)) < 0) fillers[atomicAdd(cnt + 5, 1u)] = (uint32_t)i;
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) { sendL[0] = cnt[0]; sendR[0] = cnt[1]; }
@@ -645,7 +650,7 @@ static int migrate_impl(MpmSolver* s, View pv)
     CKM(cudaMemcpyAsync(c->h_cnt, c->d_cnt, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
     CKM(cudaStreamSynchronize(s->stream));
     const uint32_t nL = c->h_cnt[0], nR = c->h_cnt[1], mL = hasL ? c->h_cnt[2] : 0, mR = hasR ? c->h_cnt[3] : 0;
-    if (c->h_cnt[8]) { s->err = "multi-GPU: a particle crossed more than one slab in a single step (dt * |v| too large for the slab width)"; return MPM_ERR_COMM; }
+    c->slab_jump_clamps += c->h_cnt[8];
     if ((int64_t)std::max(std::max(nL, nR), std::max(mL, mR)) > c->rec_cap) { s->err = "multi-GPU: migration buffer too small"; return MPM_ERR_COMM; }
     const int64_t n_stay = n - nL - nR;
     if (n_stay + mL + mR > s->cap) { s->err = "multi-GPU: arriving particles exceed max_particles of this rank"; return MPM_ERR_COMM; }

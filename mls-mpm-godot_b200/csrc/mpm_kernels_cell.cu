@@ -547,22 +547,29 @@ struct G2PBody {
         const float Bm[9] = {Bx[0], Bx[1], Bx[2], By[0], By[1], By[2], Bz[0], Bz[1], Bz[2]};
         float np[3], cm[9];
         g2p_finish<3>(P, old, Bm, v, np, cm);
+        // multi-GPU: particles whose new base cell left this rank's slab are listed for the migration (few per warp).  One
+        // that would land beyond the neighbouring slab (|v| dt larger than that slab is wide: numerical outliers of a
+        // violent scene) is held back in the neighbour's far plane for this step and counted (MpmStats.slab_jump_clamps).
+        bool stays = true;
+        int side = 0;
+        if (mg.cnt) {
+            const int cx = __float2int_rz(np[0]);
+            if (cx < mg.x0 || cx >= mg.x1) {
+                stays = false;
+                side = cx >= mg.x1;
+                if (cx < mg.xl0) { np[0] = (float)mg.xl0 + 0.5f; atomicAdd(mg.cnt + 8, 1u); }
+                else if (cx >= mg.xr1) { np[0] = (float)mg.xr1 - 0.5f; atomicAdd(mg.cnt + 8, 1u); }
+            }
+        }
         // one 64-byte record per particle (field order of the planes): the next binning gathers it from here
         float4* q = rec + 4 * (size_t)i;
         q[0] = make_float4(np[0], np[1], np[2], v[0]);
         q[1] = make_float4(v[1], v[2], cur[3], cm[0]);
         q[2] = make_float4(cm[1], cm[2], cm[3], cm[4]);
         q[3] = make_float4(cm[5], cm[6], cm[7], cm[8]);
-        bool stays = true;
-        if (mg.cnt) {  // multi-GPU: list the particles whose new base cell left this rank's slab (few per warp)
-            const int cx = __float2int_rz(np[0]);
-            if (cx < mg.x0 || cx >= mg.x1) {
-                stays = false;
-                const int side = cx >= mg.x1;
-                if (cx < mg.xl0 || cx >= mg.xr1) mg.cnt[8] = 1u;
-                const uint32_t slot = atomicAdd(mg.cnt + side, 1u);
-                if (slot < mg.rec_cap) (side ? mg.leaveR : mg.leaveL)[slot] = i;
-            }
+        if (!stays) {
+            const uint32_t slot = atomicAdd(mg.cnt + side, 1u);
+            if (slot < mg.rec_cap) (side ? mg.leaveR : mg.leaveL)[slot] = i;
         }
         if (cnt_next && stays) {  // bin key of the NEW position for the next step (leavers get theirs where they arrive)
             uint32_t k = cell_key(kg, __float2int_rz(np[0]), __float2int_rz(np[1]), __float2int_rz(np[2]));

@@ -174,6 +174,33 @@ def test_migration_burst_takes_the_overflow_round(lib):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("path,math", [(2, 0), (3, 1)], ids=["tiled_strict", "cell_fast"])
+def test_particle_jumping_more_than_one_slab_is_held_back(lib, path, math):
+    """|v| dt larger than a whole neighbouring slab (numerical outliers of violent scenes): the particle is parked in
+    the neighbour's far plane for that step and counted; nothing is lost and nothing fails."""
+    op = orc.variant("3d_gpu", (64, 32, 32))
+    op.interaction = 0
+    n = 40000
+    pos, vel, Cm, mass = helpers.random_cloud(op, n, seed=13, vel_sigma=0.2)
+    pos[:, 0] = 20.0 + (pos[:, 0] - 3.5) * (24.0 / 57.0)   # the bulk sits in x in [20, 44]: the slab cuts fall inside it
+    fast = np.arange(0, 40)   # 40 isolated outliers in the empty regions: 200 cells per unit time = 40 cells per step
+    k = np.arange(20)
+    for grp, x, vx in ((fast[:20], 6.5, 200.0), (fast[20:], 57.5, -200.0)):
+        pos[grp, 0], pos[grp, 1], pos[grp, 2] = x, 5.5 + 5.0 * (k % 5), 5.5 + 5.0 * (k // 5)
+        vel[grp] = (vx, 0.0, 0.0)
+    Cm[fast] = 0.0
+    mass[fast] = 1e-3
+    ranks = _run_ranks(op, 4, pos, vel, Cm, mass, 2, kernel_path=path, math_mode=math)
+    ids = np.concatenate([r["ids"] for r in ranks])
+    assert np.array_equal(np.sort(ids), np.arange(n, dtype=np.uint32)), "particles lost or duplicated"
+    assert sum(r["stats"].slab_jump_clamps for r in ranks) >= 20
+    for r in ranks:
+        x0, x1, _, _ = r["slab"]
+        cx = r["pos"][:, 0].astype(np.int32)
+        assert ((cx >= x0) & (cx < x1)).all(), "a particle sits outside its rank's slab"
+
+
+@pytest.mark.gpu
 def test_k_slabs_cell_path_within_fast_tolerance(lib):
     """The cell path (FAST math) on 3 slabs: float accumulation order differs from the 1-slab run, so the bar is the
     FAST tolerance against the strict oracle, plus exact particle bookkeeping."""
