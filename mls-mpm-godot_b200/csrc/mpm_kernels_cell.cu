@@ -75,10 +75,12 @@ __device__ __forceinline__ void cell_axis(float p, float fc, float w[3], float d
 }
 
 // ---------------------------------------------------------------- walking a block's chunks, software-pipelined
-// ncu (profiles/r1/v6_*): with 168 registers per thread only 12 warps fit on an SM, and a loop that loads a particle
-// and then computes on it spends half its time in long-scoreboard stalls.  So the walk is pipelined: while the
-// particle of rank r is being processed, the one of rank r+1 (or rank 0 of the warp's next chunk) is already in
-// flight -- in registers where that is cheap (G2P: position + id), as an L1 prefetch of the 128-B lines otherwise.
+// ncu (first cell-kernel capture, summarised in DESIGN.md section 4): with 168 registers per thread only 12 warps fit on
+// an SM, and a loop that loads a particle and then computes on it spends half its time in long-scoreboard stalls.  So the
+// walk is pipelined: while the particle of rank r is being processed, the one of rank r+1 (or rank 0 of the warp's next
+// chunk) is already in flight -- in registers where that is cheap (G2P: position + mass), as a cp.async into a per-warp
+// shared-memory staging buffer otherwise (P2G: 16 / 13 fields; prefetch.global.L1 was tried first and left the L1 hit
+// rate at 5 %).
 //
 // Body interface:  begin_chunk(chunk)   per-cell set-up (stencil registers / accumulators)
 //                  fetch(i)            start bringing particle slot i in (lane-private; may be predicated off)
@@ -86,7 +88,6 @@ __device__ __forceinline__ void cell_axis(float p, float fc, float w[3], float d
 //                  compute(i)          process the current particle (slot i)
 //                  end_chunk(has)      flush per-cell results
 //                  finish()            after the warp's last chunk of the block
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 // 4-byte asynchronous global -> shared copy (LDGSTS): no register is held while the load is in flight
 __device__ __forceinline__ void cp_async4(float* smem, const float* gmem)
 {
