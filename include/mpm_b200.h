@@ -263,6 +263,11 @@ MPM_API int32_t mpm_local_hub_create(int32_t world, MpmLocalHub** hub);
 MPM_API int32_t mpm_local_hub_destroy(MpmLocalHub* hub); /* after every attached solver is destroyed */
 MPM_API int32_t mpm_comm_init_local(MpmSolver* s, MpmLocalHub* hub, int32_t rank, int32_t world);
 
+/* Load balance for long runs (fluid flows from slab to slab): collective over all ranks, between steps.  Builds the
+ * global x-plane particle histogram, moves every cut towards its equal-count position by at most max_shift planes
+ * (1..3), migrates the particles that changed owner and re-creates the rank's local grid.  Results are unaffected
+ * (ownership is not physics): bit-identical in MPM_GRID_FIXED. */
+MPM_API int32_t mpm_comm_rebalance(MpmSolver* s, int32_t max_shift);
 /* Slab of this rank: owned planes [x0, x1), stored planes [gx0, gx0 + nxl) (what mpm_download_grid returns). */
 MPM_API int32_t mpm_comm_slab(const MpmSolver* s, int32_t* x0, int32_t* x1, int32_t* gx0, int32_t* nxl);
 /* Global (original) index of each local particle, in the slot order of mpm_download_particles_soa. */

@@ -19,6 +19,7 @@
 #include <dlfcn.h>
 #include <nccl.h>  // types only: every NCCL function is resolved with dlsym
 
+#include <limits.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -218,6 +219,7 @@ struct CommState {
     bool classified = false;                  // this step's G2P already filled leave[] and the counts
     int64_t rec_cap = 0;
     int64_t migrated_out = 0, migrated_in = 0, overflow_rounds = 0;
+    int64_t recuts = 0;            // times mpm_comm_rebalance moved a cut
     int64_t slab_jump_clamps = 0;  // particles held back because they would have crossed more than one slab in a step
     uint32_t sent_prev[2] = {0, 0}, recv_prev[2] = {0, 0};  // particles that crossed each edge in the previous step
 };
@@ -293,7 +295,8 @@ void comm_fill_stats(const MpmSolver* s, MpmStats* st)
 }
 
 // ================================================================ slab set-up at upload time
-__global__ void __launch_bounds__(256) k_xhist(ParticleView pv, int64_t n, int rx, unsigned long long* __restrict__ hist)
+template <class View>
+__global__ void __launch_bounds__(256) k_xhist(View pv, int64_t n, int rx, unsigned long long* __restrict__ hist)
 {
     extern __shared__ uint32_t sh[];
     for (int k = threadIdx.x; k < rx; k += blockDim.x) sh[k] = 0;
@@ -370,7 +373,7 @@ int comm_partition(MpmSolver* s)
     CKM(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * rx, s->stream));
     if (n_global > 0) {
         const int blocks = (int)std::min<int64_t>((n_global + 255) / 256, 148 * 8);
-        k_xhist<<<blocks, 256, sizeof(uint32_t) * rx, s->stream>>>(s->view(), n_global, rx, d_hist);
+        k_xhist<ParticleView><<<blocks, 256, sizeof(uint32_t) * rx, s->stream>>>(s->view(), n_global, rx, d_hist);
         s->launches += 1;
     }
     std::vector<int64_t> hist(rx);
@@ -613,12 +616,13 @@ __global__ void __launch_bounds__(256) k_mig_unpack(View pv, uint32_t* __restric
 }
 
 template <class View>
-static int migrate_impl(MpmSolver* s, View pv)
+static int migrate_impl(MpmSolver* s, View pv, bool recut = false)
 {
     CommState* c = s->comm;
     const bool hasL = c->rank > 0, hasR = c->rank < c->world - 1;
     const int64_t n = s->n;
     MigGeom g{c->x0, c->x1, hasL ? c->cuts[c->rank - 1] : c->x0, hasR ? c->cuts[c->rank + 2] : c->x1};
+    if (recut) { g.xl0 = INT_MIN; g.xr1 = INT_MAX; }  // particles change owner because the cuts moved, not because they did
     const unsigned nb = (unsigned)((n + 255) / 256);
     const uint32_t capS[2] = {mig_capacity(c->sent_prev[0]), mig_capacity(c->sent_prev[1])};
     const uint32_t capR[2] = {mig_capacity(c->recv_prev[0]), mig_capacity(c->recv_prev[1])};
@@ -708,6 +712,82 @@ int comm_migrate(MpmSolver* s)
     return s->in_rec ? migrate_impl<RecView>(s, s->rview()) : migrate_impl<ParticleView>(s, s->view());
 }
 
+// ================================================================ re-cutting the slabs
+__global__ void __launch_bounds__(256) k_hist_round(const unsigned long long* __restrict__ own, const unsigned long long* __restrict__ accL,
+                                                    const unsigned long long* __restrict__ accR, unsigned long long* __restrict__ toR,
+                                                    unsigned long long* __restrict__ toL, int rx)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= rx) return;
+    toR[x] = accL[x] + own[x];  // everything at or left of this rank
+    toL[x] = accR[x] + own[x];  // everything at or right of this rank
+}
+
+// Global x-plane histogram (world - 1 rounds of neighbour exchange: each round passes "all ranks on my left, plus me" to
+// the right and the mirror image to the left), new equal-count cuts moved at most max_shift planes from the current
+// ones, one migration round, local grid and binning re-created.  Collective over all ranks; call between steps.
+static int rebalance(MpmSolver* s, int max_shift)
+{
+    CommState* c = s->comm;
+    const int rx = s->dp.Rx, world = c->world;
+    const bool hasL = c->rank > 0, hasR = c->rank < world - 1;
+    max_shift = std::max(1, std::min(max_shift, MIN_SLAB_WIDTH - 1));  // a particle never has to travel further than the next rank
+    unsigned long long* d = nullptr;  // own | accL | accR | toR | toL
+    CKM(cudaMalloc(&d, sizeof(unsigned long long) * 5 * rx));
+    CKM(cudaMemsetAsync(d, 0, sizeof(unsigned long long) * 5 * rx, s->stream));
+    unsigned long long *own = d, *accL = d + rx, *accR = d + 2 * rx, *toR = d + 3 * rx, *toL = d + 4 * rx;
+    if (s->n > 0) {
+        const int blocks = (int)std::min<int64_t>((s->n + 255) / 256, 148 * 8);
+        if (s->in_rec) k_xhist<RecView><<<blocks, 256, sizeof(uint32_t) * rx, s->stream>>>(s->rview(), s->n, rx, own);
+        else k_xhist<ParticleView><<<blocks, 256, sizeof(uint32_t) * rx, s->stream>>>(s->view(), s->n, rx, own);
+        s->launches += 1;
+    }
+    const size_t hb = sizeof(unsigned long long) * rx;
+    int rc = MPM_OK;
+    for (int round = 1; round < world && rc == MPM_OK; ++round) {
+        k_hist_round<<<(rx + 255) / 256, 256, 0, s->stream>>>(own, accL, accR, toR, toL, rx);
+        s->launches += 1;
+        rc = c->tr->exchange(toL, hasL ? hb : 0, accL, hasL ? hb : 0, toR, hasR ? hb : 0, accR, hasR ? hb : 0, s->stream, s->err);
+    }
+    std::vector<int64_t> hist(3 * rx);
+    cudaError_t e = cudaMemcpyAsync(hist.data(), d, 3 * hb, cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(d);
+    if (rc) return rc;
+    if (e != cudaSuccess) { s->err = cudaGetErrorString(e); return MPM_ERR_CUDA; }
+    for (int x = 0; x < rx; ++x) hist[x] += hist[rx + x] + hist[2 * rx + x];
+    std::vector<int> target(world + 1), cuts(c->cuts);
+    if (slab_cuts_host(hist.data(), rx, world, MIN_SLAB_WIDTH, target.data())) return MPM_OK;
+    bool moved = false, valid = true;
+    for (int k = 1; k < world; ++k) {
+        cuts[k] = std::max(c->cuts[k] - max_shift, std::min(c->cuts[k] + max_shift, target[k]));
+        moved |= cuts[k] != c->cuts[k];
+    }
+    for (int k = 0; k < world; ++k) valid &= cuts[k + 1] - cuts[k] >= MIN_SLAB_WIDTH;
+    if (!valid) moved = false;  // two cuts closing in on each other: leave everything as it is this time
+    if (!moved) return MPM_OK;  // (the same decision on every rank: same histogram, same arithmetic)
+    c->cuts = cuts;
+    c->x0 = cuts[c->rank]; c->x1 = cuts[c->rank + 1];
+    c->classified = false;
+    rc = s->in_rec ? migrate_impl<RecView>(s, s->rview(), true) : migrate_impl<ParticleView>(s, s->view(), true);
+    if (rc) return rc;
+    // local grid and binning follow the slab
+    s->dp.gx0 = c->x0 - 1; s->dp.nxl = c->x1 - c->x0 + 2;
+    CKM(cudaStreamSynchronize(s->stream));
+    cudaFree(s->grid); s->grid = nullptr;
+    s->ncells = (int64_t)s->dp.nxl * s->dp.Ry * s->dp.Rz;
+    CKM(cudaMalloc(&s->grid, 16 * s->ncells));
+    CKM(cudaMemsetAsync(s->grid, 0, 16 * s->ncells, s->stream));
+    s->grid_raw = false;
+    if (s->path == MPM_PATH_TILED) { sort_destroy(s); rc = sort_create(s); }
+    else if (s->path == MPM_PATH_CELL) { bin_destroy(s); rc = bin_create(s); }
+    if (rc) return rc;
+    s->sorted_valid = false;
+    s->positions_valid = false;
+    c->recuts += 1;
+    return MPM_OK;
+}
+
 }  // namespace mpm
 
 // ================================================================ C ABI
@@ -782,6 +862,16 @@ extern "C" int32_t mpm_comm_init_local(MpmSolver* s, MpmLocalHub* hub, int32_t r
     tr->hub = hub;
     tr->device = s->device;
     return comm_attach(s, tr, rank, world);
+}
+
+extern "C" int32_t mpm_comm_rebalance(MpmSolver* s, int32_t max_shift)
+{
+    if (!s) return MPM_ERR_INVALID;
+    if (!s->comm || s->comm->world < 2) return MPM_OK;
+    if (cudaSetDevice(s->device) != cudaSuccess) { s->err = "cudaSetDevice failed"; return MPM_ERR_CUDA; }
+    int rc = comm_partition(s);
+    if (rc) return rc;
+    return rebalance(s, max_shift);
 }
 
 extern "C" int32_t mpm_comm_slab(const MpmSolver* s, int32_t* x0, int32_t* x1, int32_t* gx0, int32_t* nxl)

@@ -75,7 +75,7 @@ EXPORTS = [
     "mpm_get_positions", "mpm_num_particles", "mpm_set_timing", "mpm_get_stats", "mpm_debug_last_sort",
     "mpm_get_stream", "mpm_host_alloc", "mpm_host_free", "mpm_comm_unique_id", "mpm_comm_init",
     "mpm_local_hub_create", "mpm_local_hub_destroy", "mpm_comm_init_local", "mpm_comm_slab", "mpm_download_ids",
-    "mpm_slab_cuts", "mpm_get_positions_async", "mpm_wait_positions",
+    "mpm_slab_cuts", "mpm_get_positions_async", "mpm_wait_positions", "mpm_comm_rebalance",
 ]
 
 _lib = None
@@ -129,6 +129,7 @@ def load():
         "mpm_slab_cuts": (i32, [C.POINTER(i64), i32, i32, i32, C.POINTER(i32)]),
         "mpm_get_positions_async": (i32, [vp, vp, i64]),
         "mpm_wait_positions": (i32, [vp]),
+        "mpm_comm_rebalance": (i32, [vp, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -311,6 +312,10 @@ class Solver:
         """LOCAL transport: k solvers of one process (one host thread each) share `hub`."""
         self._hub = hub  # keep it alive as long as the solver
         self._ck(self._L.mpm_comm_init_local(self._h, hub._h, rank, world))
+
+    def comm_rebalance(self, max_shift=2):
+        """Re-cut the slabs towards equal particle counts (collective; between steps)."""
+        self._ck(self._L.mpm_comm_rebalance(self._h, int(max_shift)))
 
     def slab(self):
         """(x0, x1, gx0, nxl): owned planes [x0, x1), stored planes [gx0, gx0 + nxl)."""

@@ -201,6 +201,61 @@ def test_particle_jumping_more_than_one_slab_is_held_back(lib, path, math):
 
 
 @pytest.mark.gpu
+def test_rebalance_moves_the_cuts_and_keeps_the_bits(lib):
+    """A jet leaves the first slab: mpm_comm_rebalance every 5 steps must shift the cuts after it, hand the particles to
+    their new owners, and leave the physics untouched (bit-identical to the oracle on the strict path)."""
+    import mpm_b200
+    op = orc.variant("3d_gpu", (64, 32, 32))
+    op.interaction = 0
+    n = 50000
+    pos, vel, Cm, mass = helpers.random_cloud(op, n, seed=17, vel_sigma=0.2)
+    pos[:, 0] = 6.0 + (pos[:, 0] - 3.5) * (20.0 / 57.0)   # everything starts in x in [6, 26] ...
+    vel[:, 0] += 2.5                                         # ... and drifts to +x, half a cell per step
+    steps, world = 20, 3
+    ref = orc.State(op, pos, vel, Cm, mass)
+    ref.step(steps)
+    hub = mpm_b200.LocalHub(world)
+    out, errs = [None] * world, []
+
+    def work(r):
+        try:
+            with mpm_b200.Solver(helpers.mpm_params_from_orc(op, kernel_path=2), n) as s:
+                s.comm_init_local(hub, r, world)
+                s.upload(pos, vel, Cm, mass)
+                slab0 = None
+                for k in range(steps // 5):
+                    s.step(5)
+                    if slab0 is None:
+                        slab0 = s.slab()
+                    s.comm_rebalance(3)
+                gp, gv, gc, gm = s.download()
+                out[r] = dict(pos=gp, vel=gv, C=gc, ids=s.download_ids(), slab0=slab0, slab=s.slab(), stats=s.stats())
+        except Exception as e:  # noqa: BLE001
+            errs.append((r, e))
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    [t.start() for t in th]
+    [t.join(300) for t in th]
+    hub.close()
+    assert not errs, errs
+    assert any(o["slab"][:2] != o["slab0"][:2] for o in out), "the cuts never moved"
+    cover = [o["slab"][:2] for o in out]
+    assert cover[0][0] == 0 and cover[-1][1] == 64 and all(a[1] == b[0] for a, b in zip(cover, cover[1:]))
+    ids = np.concatenate([o["ids"] for o in out])
+    assert np.array_equal(np.sort(ids), np.arange(n, dtype=np.uint32))
+    for what in ("pos", "vel", "C"):
+        full = np.zeros_like(getattr(ref, what))
+        for o in out:
+            full[o["ids"]] = o[what]
+        helpers.assert_bit_equal(full, getattr(ref, what), f"{what} with re-cut slabs")
+    for o in out:
+        cx = o["pos"][:, 0].astype(np.int32)
+        assert ((cx >= o["slab"][0]) & (cx < o["slab"][1])).all()
+    counts = [o["stats"].local_particles for o in out]
+    assert max(counts) - min(counts) < 0.35 * n / world, counts   # still roughly balanced although the fluid moved 10 cells
+
+
+@pytest.mark.gpu
 def test_k_slabs_cell_path_within_fast_tolerance(lib):
     """The cell path (FAST math) on 3 slabs: float accumulation order differs from the 1-slab run, so the bar is the
     FAST tolerance against the strict oracle, plus exact particle bookkeeping."""
