@@ -71,3 +71,17 @@ def test_no_gpu_means_loud_failure_not_cpu_fallback(lib):
         mpm_b200.Solver(p, 1000)
     assert e.value.code == mpm_b200.ERR_CUDA
     assert "no CPU fallback" in str(e.value)
+
+
+def test_reference_arm_of_the_bench_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU port of the reference algorithm on the host cores) needs no GPU."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c2", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["metric"] == "particle-steps/s"
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0

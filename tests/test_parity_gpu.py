@@ -430,3 +430,44 @@ def test_pipelined_position_hand_off_matches_the_synchronous_one(lib):
                     assert np.abs(got[k] - want).max() < 1e-4
         for p in bufs:
             mpm_b200.host_free(p)
+
+
+def test_reference_shipping_scene_bit_exact(lib):
+    """The scene the reference actually ships (MLSMPM3DFluidMultithreadGPU.cs:654-707): 64^3 grid, a centred 32^3 box at
+    spacing 0.6 -> 54^3 = 157 464 particles, the GPU variant's constants, the sphere repulsor at the scene's default
+    position, the UI's start-up gravity -0.5 (main_ui.tscn:162).  20 steps, strict arithmetic, both binned-or-not paths."""
+    op = orc.variant("3d_gpu", 64)
+    op.gravity = -0.5
+    lo, hi = (16, 16, 16), (48, 48, 48)
+    pos = orc.init_block(3, lo, hi, 0.6)
+    assert pos.shape[0] == 157464
+    ref = orc.State(op, pos)
+    ref.step(20)
+    for path in (1, 2):
+        with make_solver(op, pos.shape[0], kernel_path=path) as s:
+            assert s.initialise_sim(lo, hi, 0.6) == 157464
+            s.process()            # one frame = sim_iterations (2) steps, as _Process does
+            s.step(18)
+            gp, gv, gc, _ = s.download()
+            helpers.assert_bit_equal(gp, ref.pos, "pos"); helpers.assert_bit_equal(gv, ref.vel, "vel")
+            helpers.assert_bit_equal(gc, ref.C, "C")
+            helpers.assert_bit_equal(s.positions(), ref.positions(), "particle_pos_tex contents")
+            _, width = s.positions_device()
+            assert width == 397     # (uint)sqrt(157464) + 1, MLSMPM3DFluidMultithreadGPU.cs:196
+
+
+def test_bench_line_has_the_contract_keys(lib):
+    """bench.py on the small C2 scene: one JSON line with the keys the driver reads."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--workload", "c2", "--steps", "5", "--warmup", "3",
+                          "--no-cpu-baseline"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks", "kernels"):
+        assert k in line, k
+    assert line["value"] > 0 and line["gpu_launches"] > 0 and line["config"]["workload"].startswith("3D dam-break 64^3")
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"])
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
