@@ -50,6 +50,9 @@ struct Transport {
     // edge must agree on its size.  Send buffers may be rewritten by work enqueued on `st` after the call returns.
     virtual int exchange(const void* sendL, size_t nsl, void* recvL, size_t nrl, const void* sendR, size_t nsr,
                          void* recvR, size_t nrr, cudaStream_t st, std::string& err) = 0;
+    // true when every rank is its own process on its own GPU: halo planes can then be written straight into the
+    // neighbour's memory over NVLink (CUDA IPC) with kernels that wait on each other's flags
+    virtual bool separate_gpus() const { return false; }
 };
 
 // ---------------------------------------------------------------- NCCL
@@ -93,6 +96,7 @@ struct NcclTransport : Transport {
     NcclApi* api = nullptr;
     ncclComm_t comm = nullptr;
     ~NcclTransport() override { if (comm) api->CommDestroy(comm); }
+    bool separate_gpus() const override { return true; }
     int exchange(const void* sendL, size_t nsl, void* recvL, size_t nrl, const void* sendR, size_t nsr, void* recvR,
                  size_t nrr, cudaStream_t st, std::string& err) override
     {
@@ -208,6 +212,12 @@ struct CommState {
     int4* halo_send[2] = {nullptr, nullptr};
     int4* halo_snap[2] = {nullptr, nullptr};
     int64_t halo_cells = 0;  // 2 * Ry * Rz
+    // direct peer stores for the halo planes (CUDA IPC over NVLink): own = [side][pass] receive regions + flags
+    bool p2p_tried = false, p2p_ready = false;
+    uint8_t* p2p_own = nullptr;
+    uint8_t* p2p_peer[2] = {nullptr, nullptr};  // the left / right neighbour's allocation, mapped here
+    uint32_t p2p_seq[2] = {0, 0};               // messages sent so far, per pass
+    uint32_t* p2p_done = nullptr;               // block-completion counters of the push kernels + error flag
     // migration
     uint32_t* d_cnt = nullptr;  // 0 nL, 1 nR (leaving), 2 mL, 3 mR (arriving), 4 holes, 5 fillers, 8 held-back outliers
     uint32_t* h_cnt = nullptr;  // pinned mirror
@@ -246,6 +256,8 @@ void comm_destroy(MpmSolver* s)
     CommState* c = s->comm;
     if (!c) return;
     free_slab_buffers(c);
+    for (int k = 0; k < 2; ++k) if (c->p2p_peer[k]) cudaIpcCloseMemHandle(c->p2p_peer[k]);
+    cudaFree(c->p2p_own); cudaFree(c->p2p_done);
     for (int k = 0; k < 2; ++k) { cudaFree(c->send_rec[k]); cudaFree(c->recv_rec[k]); }
     cudaFree(c->d_cnt); cudaFree(c->holes); cudaFree(c->fillers); cudaFree(c->leave[0]); cudaFree(c->leave[1]);
     if (c->h_cnt) cudaFreeHost(c->h_cnt);
@@ -411,7 +423,7 @@ int comm_partition(MpmSolver* s)
         if (rc) return rc;
     }
     // 3. keep own particles
-    CKM(cudaMemsetAsync(c->d_cnt, 0, 16 * sizeof(uint32_t), s->stream));
+    CKM(cudaMemsetAsync(c->d_cnt, 0, 9 * sizeof(uint32_t), s->stream));  // (word 9 is the sticky halo-timeout flag)
     if (n_global > 0) {
         k_filter_slab<<<(unsigned)((n_global + 255) / 256), 256, 0, s->stream>>>(s->view(), s->view_alt(), s->orig_id, s->orig_id_alt,
                                                                                  n_global, c->x0, c->x1, c->d_cnt);
@@ -461,6 +473,175 @@ __global__ void __launch_bounds__(256) k_halo_diff(const int4* __restrict__ bloc
     if (blockR) { const int4 a = blockR[i], b = snapR[i]; outR[i] = make_int4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
 }
 
+// ---------------------------------------------------------------- halo planes by direct peer stores (one process per GPU)
+// Each rank owns one allocation with four receive regions ([side][pass], 2 planes each) and four flags; the neighbours
+// map it through CUDA IPC.  A halo exchange is then two kernels and no library call:
+//   k_halo_push      writes this rank's two overlap planes (pass 1: their increment since pass 0) straight into the
+//                    neighbours' receive regions over NVLink; the last block to finish publishes the message number in
+//                    the neighbours' flags (system-scope release).
+//   k_halo_wait_add  waits for the neighbours' flags to reach the message number, then adds the received planes.
+// No acknowledgement is needed: a region is rewritten one step later, and between two pushes of the same pass this rank
+// has waited for a message that the neighbour only sent after consuming the previous one (push0, wait0, push1, wait1
+// alternate on both sides).  A wait gives up after ~2 s and raises an error flag instead of hanging the GPU.
+constexpr int P2P_FLAG_STRIDE = 32;  // uint32 words between flags (one 128-B line each)
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_halo_push(const int4* __restrict__ blockL, const int4* __restrict__ snapL, int4* __restrict__ dstL,
+                                                   uint32_t* flagL, const int4* __restrict__ blockR, const int4* __restrict__ snapR,
+                                                   int4* __restrict__ dstR, uint32_t* flagR, int64_t cells, uint32_t seq, uint32_t* done)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cells) {
+        if (dstL) {
+            int4 a = blockL[i];
+            if (snapL) { const int4 b = snapL[i]; a.x -= b.x; a.y -= b.y; a.z -= b.z; a.w -= b.w; }
+            dstL[i] = a;
+        }
+        if (dstR) {
+            int4 a = blockR[i];
+            if (snapR) { const int4 b = snapR[i]; a.x -= b.x; a.y -= b.y; a.z -= b.z; a.w -= b.w; }
+            dstR[i] = a;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t prev = atomicAdd(done, 1u);
+        if (prev == gridDim.x - 1) {  // every block's stores are fenced: publish
+            *done = 0;
+            __threadfence_system();
+            if (flagL) st_release_sys(flagL, seq);
+            if (flagR) st_release_sys(flagR, seq);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_halo_wait_add(int4* __restrict__ blockL, const int4* recvL, int4* __restrict__ snapL, const uint32_t* flagL,
+                                                       int4* __restrict__ blockR, const int4* recvR, int4* __restrict__ snapR, const uint32_t* flagR,
+                                                       int64_t cells, uint32_t seq, uint32_t* err)
+{
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        for (int side = 0; side < 2; ++side) {
+            const uint32_t* f = side ? flagR : flagL;
+            if (!f) continue;
+            while ((int32_t)(ld_acquire_sys(f) - seq) < 0) {
+                if (clock64() - t0 > 4000000000ll) { atomicExch(err, 1u); break; }
+                __nanosleep(200);
+            }
+        }
+    }
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cells) return;
+    if (blockL) {
+        int4 a = blockL[i]; const int4 b = __ldcv(recvL + i);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        blockL[i] = a;
+        if (snapL) snapL[i] = a;
+    }
+    if (blockR) {
+        int4 a = blockR[i]; const int4 b = __ldcv(recvR + i);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        blockR[i] = a;
+        if (snapR) snapR[i] = a;
+    }
+}
+
+// one-time set-up: allocate, exchange IPC handles with both neighbours (through the transport), map
+static void p2p_setup(MpmSolver* s)
+{
+    CommState* c = s->comm;
+    c->p2p_tried = true;
+    if (!c->tr->separate_gpus() || getenv("MPM_NO_P2P")) return;
+    const bool hasL = c->rank > 0, hasR = c->rank < c->world - 1;
+    const size_t region = 16 * (size_t)c->halo_cells, total = 4 * region + 4 * P2P_FLAG_STRIDE * sizeof(uint32_t);
+    uint8_t *hs = nullptr, *hr = nullptr;  // device staging: [0..63] handle for/from the left, [64..127] right
+    bool ok = cudaMalloc(&c->p2p_own, total) == cudaSuccess && cudaMemset(c->p2p_own, 0, total) == cudaSuccess &&
+              cudaMalloc(&c->p2p_done, 8 * sizeof(uint32_t)) == cudaSuccess && cudaMemset(c->p2p_done, 0, 8 * sizeof(uint32_t)) == cudaSuccess &&
+              cudaMalloc(&hs, 128) == cudaSuccess && cudaMalloc(&hr, 128) == cudaSuccess;
+    cudaIpcMemHandle_t mine, theirs[2];
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    ok = ok && cudaIpcGetMemHandle(&mine, c->p2p_own) == cudaSuccess;
+    // every rank takes part in the exchange even if its own set-up failed (an all-zero handle says so)
+    if (!ok) memset(&mine, 0, sizeof(mine));
+    if (hs && hr) {
+        cudaMemcpyAsync(hs, &mine, 64, cudaMemcpyHostToDevice, s->stream);
+        cudaMemcpyAsync(hs + 64, &mine, 64, cudaMemcpyHostToDevice, s->stream);
+        cudaMemsetAsync(hr, 0, 128, s->stream);
+        std::string err;
+        if (c->tr->exchange(hs, hasL ? 64 : 0, hr, hasL ? 64 : 0, hs + 64, hasR ? 64 : 0, hr + 64, hasR ? 64 : 0, s->stream, err)) ok = false;
+        cudaMemcpyAsync(theirs, hr, 128, cudaMemcpyDeviceToHost, s->stream);
+        cudaStreamSynchronize(s->stream);
+    } else {
+        ok = false;
+    }
+    cudaFree(hs); cudaFree(hr);
+    const cudaIpcMemHandle_t zero = {};
+    for (int side = 0; side < 2 && ok; ++side) {
+        if (!(side ? hasR : hasL)) continue;
+        if (memcmp(&theirs[side], &zero, 64) == 0) { ok = false; break; }
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, theirs[side], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+        c->p2p_peer[side] = (uint8_t*)p;
+    }
+    // every rank must take the same path: global AND of `ok` over the chain (world - 1 rounds of neighbour exchange)
+    {
+        uint32_t* d = nullptr;  // [0] mine, [1] from the left, [2] from the right
+        uint32_t h[3] = {ok ? 1u : 0u, 1u, 1u};
+        if (cudaMalloc(&d, 3 * sizeof(uint32_t)) == cudaSuccess) {
+            for (int round = 1; round < c->world; ++round) {
+                cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, s->stream);
+                std::string err;
+                if (c->tr->exchange(d, hasL ? 4 : 0, d + 1, hasL ? 4 : 0, d, hasR ? 4 : 0, d + 2, hasR ? 4 : 0, s->stream, err)) h[0] = 0;
+                uint32_t g[3] = {0, 1, 1};
+                cudaMemcpyAsync(g, d, sizeof(g), cudaMemcpyDeviceToHost, s->stream);
+                cudaStreamSynchronize(s->stream);
+                h[0] = (h[0] && (!hasL || g[1]) && (!hasR || g[2])) ? 1u : 0u;
+            }
+            cudaFree(d);
+        } else {
+            h[0] = 0;  // (cannot even take part: the neighbours will time out in exchange() -- out of memory is fatal anyway)
+        }
+        ok = h[0] != 0;
+    }
+    if (!ok) {
+        for (int k = 0; k < 2; ++k) if (c->p2p_peer[k]) { cudaIpcCloseMemHandle(c->p2p_peer[k]); c->p2p_peer[k] = nullptr; }
+        fprintf(stderr, "[mpm_b200 rank %d] direct peer halo stores unavailable (CUDA IPC); set MPM_NO_P2P=1 on every rank to use NCCL for the halos\n", c->rank);
+    }
+    c->p2p_ready = ok;
+}
+
+static int exchange_halo_p2p(MpmSolver* s, int pass, int4* blockL, int4* blockR)
+{
+    CommState* c = s->comm;
+    const size_t region = 16 * (size_t)c->halo_cells;
+    const unsigned nb = (unsigned)((c->halo_cells + 255) / 256);
+    const uint32_t seq = ++c->p2p_seq[pass];
+    auto region_of = [&](uint8_t* base, int side) { return reinterpret_cast<int4*>(base + (size_t)(side * 2 + pass) * region); };
+    auto flag_of = [&](uint8_t* base, int side) { return reinterpret_cast<uint32_t*>(base + 4 * region) + (side * 2 + pass) * P2P_FLAG_STRIDE; };
+    // my left neighbour receives from its RIGHT side (1), my right neighbour from its LEFT side (0)
+    int4* dstL = blockL ? region_of(c->p2p_peer[0], 1) : nullptr;
+    int4* dstR = blockR ? region_of(c->p2p_peer[1], 0) : nullptr;
+    uint32_t* fL = blockL ? flag_of(c->p2p_peer[0], 1) : nullptr;
+    uint32_t* fR = blockR ? flag_of(c->p2p_peer[1], 0) : nullptr;
+    k_halo_push<<<nb, 256, 0, s->stream>>>(blockL, pass == 1 ? c->halo_snap[0] : nullptr, dstL, fL, blockR, pass == 1 ? c->halo_snap[1] : nullptr,
+                                           dstR, fR, c->halo_cells, seq, c->p2p_done + pass);
+    k_halo_wait_add<<<nb, 256, 0, s->stream>>>(blockL, region_of(c->p2p_own, 0), pass == 0 ? c->halo_snap[0] : nullptr,
+                                               blockL ? flag_of(c->p2p_own, 0) : nullptr, blockR, region_of(c->p2p_own, 1),
+                                               pass == 0 ? c->halo_snap[1] : nullptr, blockR ? flag_of(c->p2p_own, 1) : nullptr, c->halo_cells,
+                                               seq, c->d_cnt + 9);
+    s->launches += 2;
+    return MPM_OK;
+}
+
 int comm_exchange_halo(MpmSolver* s, int pass)
 {
     CommState* c = s->comm;
@@ -471,6 +652,8 @@ int comm_exchange_halo(MpmSolver* s, int pass)
     const int64_t plane = (int64_t)s->dp.Ry * s->dp.Rz;
     int4* blockL = hasL ? grid : nullptr;
     int4* blockR = hasR ? grid + (int64_t)(s->dp.nxl - 2) * plane : nullptr;
+    if (!c->p2p_tried) p2p_setup(s);
+    if (c->p2p_ready) return exchange_halo_p2p(s, pass, blockL, blockR);
     const size_t bytes = 16 * (size_t)c->halo_cells;
     const unsigned nb = (unsigned)((c->halo_cells + 255) / 256);
     const int4 *sendL = blockL, *sendR = blockR;
@@ -631,7 +814,7 @@ static int migrate_impl(MpmSolver* s, View pv, bool recut = false)
         return MPM_ERR_COMM;
     }
     if (!c->classified) {  // this path's G2P did not classify: one pass over the positions
-        CKM(cudaMemsetAsync(c->d_cnt, 0, 16 * sizeof(uint32_t), s->stream));
+        CKM(cudaMemsetAsync(c->d_cnt, 0, 9 * sizeof(uint32_t), s->stream));  // (word 9 is the sticky halo-timeout flag)
         if (n > 0) { k_mig_scan<View><<<nb, 256, 0, s->stream>>>(g, pv, n, (uint32_t)c->rec_cap, c->leave[0], c->leave[1], c->d_cnt); s->launches += 1; }
     }
     c->classified = false;
@@ -655,6 +838,7 @@ static int migrate_impl(MpmSolver* s, View pv, bool recut = false)
     CKM(cudaStreamSynchronize(s->stream));
     const uint32_t nL = c->h_cnt[0], nR = c->h_cnt[1], mL = hasL ? c->h_cnt[2] : 0, mR = hasR ? c->h_cnt[3] : 0;
     c->slab_jump_clamps += c->h_cnt[8];
+    if (c->h_cnt[9]) { s->err = "multi-GPU: a neighbour's halo planes did not arrive within 2 s (peer-store path)"; return MPM_ERR_COMM; }
     if ((int64_t)std::max(std::max(nL, nR), std::max(mL, mR)) > c->rec_cap) { s->err = "multi-GPU: migration buffer too small"; return MPM_ERR_COMM; }
     const int64_t n_stay = n - nL - nR;
     if (n_stay + mL + mR > s->cap) { s->err = "multi-GPU: arriving particles exceed max_particles of this rank"; return MPM_ERR_COMM; }
@@ -695,7 +879,7 @@ int comm_begin_classify(MpmSolver* s, MigClassify* out)
     out->cnt = nullptr;
     if (!c || c->world < 2) return MPM_OK;
     const bool hasL = c->rank > 0, hasR = c->rank < c->world - 1;
-    CKM(cudaMemsetAsync(c->d_cnt, 0, 16 * sizeof(uint32_t), s->stream));
+    CKM(cudaMemsetAsync(c->d_cnt, 0, 9 * sizeof(uint32_t), s->stream));  // (word 9 is the sticky halo-timeout flag)
     out->x0 = c->x0; out->x1 = c->x1;
     out->xl0 = hasL ? c->cuts[c->rank - 1] : c->x0;
     out->xr1 = hasR ? c->cuts[c->rank + 2] : c->x1;
