@@ -178,6 +178,12 @@ MPM_API int32_t mpm_get_params(const MpmSolver* s, MpmParams* p);
 /* HandleMouseInteraction (H:618-642): patch only the sphere position. */
 MPM_API int32_t mpm_set_sphere(MpmSolver* s, const float pos[3]);
 
+/* Sphere list (colliders beyond the single hard-coded sphere, g2p.glsl:122-129 / X:570-576): up to 7 further
+ * spheres (x, y, z, radius each), applied after MpmParams.sphere_pos in order with the same test and push, on the
+ * pre- or post-advection position as MpmParams.interaction says.  count = 0 removes them. */
+#define MPM_MAX_EXTRA_SPHERES 7
+MPM_API int32_t mpm_set_colliders(MpmSolver* s, const float* xyzr, int32_t count);
+
 /* InitialiseSim (H:654-707, F:129-183): lattice of points in [lo, hi) with the reference's
  * float-accumulating loops, vel = 0, C = 0, mass = 1, grid zeroed.  Replaces the particle set. */
 MPM_API int32_t mpm_init_block(MpmSolver* s, const float lo[3], const float hi[3], float spacing);
@@ -196,6 +202,13 @@ MPM_API int32_t mpm_download_particles_soa(MpmSolver* s, float* pos, float* vel,
                                            int64_t cap);
 /* BufferGetData(grid_buffer): cells in reference order x*Ry*Rz + y*Rz + z (F:282), field order of H:25-32. */
 MPM_API int32_t mpm_download_grid(MpmSolver* s, MpmCell16* cells, int64_t cap);
+
+/* Checkpoint / resume (the reference has none: state is re-created in _Ready).  Raw little-endian
+ * file: 64-byte header {"MPMB200\0", u32 version = 1, i32 dim, i32 grid[3], i64 n, i64 steps, pad} followed by n
+ * particle records in the reference's 80-byte layout (H:8-22), original index order.  Loading replaces the particle
+ * set (like mpm_upload_particles) and restores the step counter; parameters are not stored (the host owns them). */
+MPM_API int32_t mpm_save_state(MpmSolver* s, const char* path);
+MPM_API int32_t mpm_load_state(MpmSolver* s, const char* path);
 
 /* _Process -> sim_iterations x SetComputeLists (H:234-251, 505-544): enqueue `iterations` steps
  * (clear, P2G_1, P2G_2, update, G2P) on the solver's stream and return. */

@@ -58,7 +58,7 @@ static int validate_params(const MpmParams* p, std::string& why)
 }
 
 static void to_dev(const MpmParams& h, DevParams& d, int gx0, int nxl)
-{
+{   // (the collider list in d.n_extra / d.extra is set by mpm_set_colliders and left alone here)
     d.dim = h.dim;
     d.Rx = h.grid_size[0]; d.Ry = h.grid_size[1]; d.Rz = (h.dim == 3) ? h.grid_size[2] : 1;
     d.gx0 = gx0; d.nxl = nxl;
@@ -253,6 +253,15 @@ extern "C" int32_t mpm_set_sphere(MpmSolver* s, const float pos[3])
     return MPM_OK;
 }
 
+extern "C" int32_t mpm_set_colliders(MpmSolver* s, const float* xyzr, int32_t count)
+{
+    if (!s || count < 0 || count > MPM_MAX_EXTRA_SPHERES || (count > 0 && !xyzr)) return MPM_ERR_INVALID;
+    s->dp.n_extra = count;
+    for (int k = 0; k < count; ++k)
+        for (int a = 0; a < 4; ++a) s->dp.extra[k][a] = xyzr[4 * k + a];
+    return MPM_OK;
+}
+
 // ---------------------------------------------------------------- particle set
 
 // multi-GPU (mpm_comm.cu): the GLOBAL set is written to the planes by init/add/upload; the slab partition
@@ -429,6 +438,63 @@ extern "C" int32_t mpm_download_grid(MpmSolver* s, MpmCell16* cells, int64_t cap
     if (s->grid_raw) { launch_update_grid(s->dp, s->grid, s->ncells, s->stream); s->launches += 1; s->grid_raw = false; }
     CK(cudaMemcpyAsync(cells, s->grid, 16 * s->ncells, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
+    return MPM_OK;
+}
+
+// ---------------------------------------------------------------- checkpoint / resume
+struct StateHeader {
+    char magic[8];
+    uint32_t version;
+    int32_t dim;
+    int32_t grid[3];
+    int32_t pad0;
+    int64_t n;
+    int64_t steps;
+    int64_t pad1[2];
+};
+static_assert(sizeof(StateHeader) == 64, "checkpoint header is 64 bytes");
+
+extern "C" int32_t mpm_save_state(MpmSolver* s, const char* path)
+{
+    if (!s || !path) return MPM_ERR_INVALID;
+    if (s->comm) return fail(s, MPM_ERR_STATE, "multi-GPU: checkpoint each rank's particles through mpm_download_particles + mpm_download_ids");
+    std::vector<MpmParticle80> buf((size_t)std::max<int64_t>(s->n, 1));
+    int rc = s->n > 0 ? mpm_download_particles(s, buf.data(), s->n) : MPM_OK;
+    if (rc) return rc;
+    StateHeader h{};
+    memcpy(h.magic, "MPMB200", 8);
+    h.version = 1; h.dim = s->hp.dim;
+    for (int a = 0; a < 3; ++a) h.grid[a] = s->hp.grid_size[a];
+    h.n = s->n; h.steps = s->steps;
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(s, MPM_ERR_INVALID, std::string("cannot open for writing: ") + path);
+    const bool ok = fwrite(&h, sizeof(h), 1, f) == 1 && (s->n == 0 || fwrite(buf.data(), sizeof(MpmParticle80), (size_t)s->n, f) == (size_t)s->n);
+    if (fclose(f) != 0 || !ok) return fail(s, MPM_ERR_INVALID, std::string("short write: ") + path);
+    return MPM_OK;
+}
+
+extern "C" int32_t mpm_load_state(MpmSolver* s, const char* path)
+{
+    if (!s || !path) return MPM_ERR_INVALID;
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(s, MPM_ERR_INVALID, std::string("cannot open: ") + path);
+    StateHeader h{};
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "MPMB200", 8) != 0 || h.version != 1) {
+        fclose(f);
+        return fail(s, MPM_ERR_INVALID, "not an mpm_b200 checkpoint (bad header)");
+    }
+    if (h.dim != s->hp.dim || h.grid[0] != s->hp.grid_size[0] || h.grid[1] != s->hp.grid_size[1] || h.grid[2] != s->hp.grid_size[2]) {
+        fclose(f);
+        return fail(s, MPM_ERR_INVALID, "checkpoint was written for a different dim / grid size");
+    }
+    if (h.n < 0 || h.n > s->cap) { fclose(f); return fail(s, MPM_ERR_INVALID, "checkpoint holds more particles than max_particles"); }
+    std::vector<MpmParticle80> buf((size_t)std::max<int64_t>(h.n, 1));
+    const bool ok = h.n == 0 || fread(buf.data(), sizeof(MpmParticle80), (size_t)h.n, f) == (size_t)h.n;
+    fclose(f);
+    if (!ok) return fail(s, MPM_ERR_INVALID, "checkpoint is truncated");
+    int rc = mpm_upload_particles(s, buf.data(), h.n);
+    if (rc) return rc;
+    s->steps = h.steps;
     return MPM_OK;
 }
 

@@ -35,6 +35,8 @@ struct DevParams {
     int interaction;
     float sphere[3], sphere_r, mouse[2], mouse_r;
     int overflow_check;
+    int n_extra;         // further sphere repulsors (mpm_set_colliders), applied after the first one
+    float extra[7][4];   // x, y, z, radius
 };
 
 constexpr int GROUP = 32;                 // slots per group

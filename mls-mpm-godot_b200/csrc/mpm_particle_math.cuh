@@ -147,6 +147,20 @@ __device__ __forceinline__ void g2p_finish(const DevParams& P, const float old[3
             v[1] = sadd(v[1], smul(fy, 1.0f));
             v[2] = sadd(v[2], smul(fz, 1.0f));
         }
+        for (int k = 0; k < P.n_extra; ++k) {  // sphere list (mpm_set_colliders): the same rule for every further sphere
+            const float ex = ssub(q[0], P.extra[k][0]), ey = ssub(q[1], P.extra[k][1]), ez = ssub(q[2], P.extra[k][2]);
+            const float e2 = sadd(sadd(smul(ex, ex), smul(ey, ey)), smul(ez, ez));
+            if (e2 < smul(P.extra[k][3], P.extra[k][3])) {
+                float gx = 0.0f, gy = 0.0f, gz = 0.0f;
+                if (e2 != 0.0f) {
+                    const float len = __fsqrt_rn(e2);
+                    gx = sdiv(ex, len); gy = sdiv(ey, len); gz = sdiv(ez, len);
+                }
+                v[0] = sadd(v[0], smul(gx, 1.0f));
+                v[1] = sadd(v[1], smul(gy, 1.0f));
+                v[2] = sadd(v[2], smul(gz, 1.0f));
+            }
+        }
     } else if (P.interaction == 3) {
         const float dx = ssub(np[0], P.mouse[0]), dy = ssub(np[1], P.mouse[1]);
         const float d2 = sadd(smul(dx, dx), smul(dy, dy));

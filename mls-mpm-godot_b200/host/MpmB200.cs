@@ -70,11 +70,14 @@ namespace MpmB200
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_set_params(IntPtr s, MpmParams* p);
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_get_params(IntPtr s, MpmParams* p);
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_set_sphere(IntPtr s, float* pos3);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_set_colliders(IntPtr s, float* xyzr, int count);
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_init_block(IntPtr s, float* lo3, float* hi3, float spacing);
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_add_block(IntPtr s, float* lo3, float* hi3, float spacing);
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_upload_particles(IntPtr s, [In] Particle[] ps, long n);
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_download_particles(IntPtr s, [Out] Particle[] ps, long cap);
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_download_grid(IntPtr s, [Out] Cell[] cells, long cap);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_save_state(IntPtr s, [MarshalAs(UnmanagedType.LPUTF8Str)] string path);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_load_state(IntPtr s, [MarshalAs(UnmanagedType.LPUTF8Str)] string path);
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_step(IntPtr s, int iterations);
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_sync(IntPtr s);
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_run_phase(IntPtr s, int phase);

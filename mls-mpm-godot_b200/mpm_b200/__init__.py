@@ -75,7 +75,8 @@ EXPORTS = [
     "mpm_get_positions", "mpm_num_particles", "mpm_set_timing", "mpm_get_stats", "mpm_debug_last_sort",
     "mpm_get_stream", "mpm_host_alloc", "mpm_host_free", "mpm_comm_unique_id", "mpm_comm_init",
     "mpm_local_hub_create", "mpm_local_hub_destroy", "mpm_comm_init_local", "mpm_comm_slab", "mpm_download_ids",
-    "mpm_slab_cuts", "mpm_get_positions_async", "mpm_wait_positions", "mpm_comm_rebalance",
+    "mpm_slab_cuts", "mpm_get_positions_async", "mpm_wait_positions", "mpm_comm_rebalance", "mpm_set_colliders",
+    "mpm_save_state", "mpm_load_state",
 ]
 
 _lib = None
@@ -130,6 +131,9 @@ def load():
         "mpm_get_positions_async": (i32, [vp, vp, i64]),
         "mpm_wait_positions": (i32, [vp]),
         "mpm_comm_rebalance": (i32, [vp, i32]),
+        "mpm_set_colliders": (i32, [vp, fp, i32]),
+        "mpm_save_state": (i32, [vp, C.c_char_p]),
+        "mpm_load_state": (i32, [vp, C.c_char_p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -203,6 +207,17 @@ class Solver:
     def set_sphere(self, pos):
         a = (C.c_float * 3)(*pos)
         self._ck(self._L.mpm_set_sphere(self._h, a))
+
+    def save_state(self, path):
+        self._ck(self._L.mpm_save_state(self._h, os.fsencode(path)))
+
+    def load_state(self, path):
+        self._ck(self._L.mpm_load_state(self._h, os.fsencode(path)))
+
+    def set_colliders(self, spheres):
+        """Further sphere repulsors [(x, y, z, r), ...] (at most 7) applied after `sphere_pos`."""
+        a = np.ascontiguousarray(spheres, np.float32).reshape(-1, 4)
+        self._ck(self._L.mpm_set_colliders(self._h, _fp(a), a.shape[0]))
 
     # -- scene (InitialiseSim, :654-707)
     def initialise_sim(self, lo, hi, spacing, append=False):

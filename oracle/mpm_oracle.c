@@ -471,6 +471,16 @@ static void g2p_particle(const OrcParams* P, int64_t i, float* pos, float* vel, 
             if (d2 != 0) { float len = sqrtf(d2); fx = dx / len; fy = dy / len; fz = dz / len; }
             v[0] += fx * 1.0f; v[1] += fy * 1.0f; v[2] += fz * 1.0f; /* X:574-575 */
         }
+        for (int k = 0; k < P->n_extra_spheres && k < 7; ++k) {  /* the same rule for every further sphere */
+            const float* sp = P->extra_spheres[k];
+            float ex = q[0] - sp[0], ey = q[1] - sp[1], ez = q[2] - sp[2];
+            float e2 = (ex * ex + ey * ey) + ez * ez;
+            if (e2 < sp[3] * sp[3]) {
+                float gx = 0, gy = 0, gz = 0;
+                if (e2 != 0) { float len = sqrtf(e2); gx = ex / len; gy = ey / len; gz = ez / len; }
+                v[0] += gx * 1.0f; v[1] += gy * 1.0f; v[2] += gz * 1.0f;
+            }
+        }
     } else if (P->interaction == ORC_INTERACT_MOUSE_2D) {        /* D:384-397 */
         float dx = np_[0] - P->mouse_pos[0], dy = np_[1] - P->mouse_pos[1];
         float d2 = dx * dx + dy * dy;

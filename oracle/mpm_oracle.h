@@ -81,6 +81,10 @@ typedef struct OrcParams {
     float mouse_pos[2];   /* D:54 */
     float mouse_radius;   /* D:52 (10) */
     int32_t pow_mode;     /* ORC_POW_* */
+    /* more sphere repulsors of the same kind ("sphere list with radius as a parameter"); applied
+     * after the first one, in order, each with the test and push of X:570-576 / g2p.glsl:122-129 */
+    int32_t n_extra_spheres;   /* 0..7 */
+    float extra_spheres[7][4]; /* x, y, z, radius */
 } OrcParams;
 
 /* Particle state is SoA: pos[3N], vel[3N], C[9N] (column-major like Godot's Basis: C[3*col+row], so

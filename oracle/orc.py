@@ -35,6 +35,7 @@ class OrcParams(C.Structure):
         ("interaction", C.c_int32), ("sphere_pos", C.c_float * 3), ("sphere_radius", C.c_float),
         ("mouse_pos", C.c_float * 2), ("mouse_radius", C.c_float),
         ("pow_mode", C.c_int32),
+        ("n_extra_spheres", C.c_int32), ("extra_spheres", (C.c_float * 4) * 7),
     ]
 
 

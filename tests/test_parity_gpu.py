@@ -471,3 +471,62 @@ def test_bench_line_has_the_contract_keys(lib):
     assert line["value"] > 0 and line["gpu_launches"] > 0 and line["config"]["workload"].startswith("3D dam-break 64^3")
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"])
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
+
+
+def test_sphere_list_colliders(lib):
+    """a list of sphere repulsors (mpm_set_colliders) follows the rule of the reference's single sphere
+    (g2p.glsl:122-129); strict paths bit-exact against the oracle, cell path within the FAST tolerance."""
+    op = orc.variant("3d_gpu", 32)
+    op.sphere_pos[:] = [10.0, 14.0, 16.0]
+    op.sphere_radius = 4.0
+    extra = [(20.0, 12.0, 16.0, 5.0), (16.0, 20.0, 10.0, 3.5), (16.0, 16.0, 22.0, 6.0)]
+    op.n_extra_spheres = len(extra)
+    for k, e in enumerate(extra):
+        op.extra_spheres[k][:] = list(e)
+    n = 30000
+    pos, vel, Cm, mass = helpers.random_cloud(op, n, seed=71)
+    ref = orc.State(op, pos, vel, Cm, mass)
+    ref.step(4)
+    plain = orc.variant("3d_gpu", 32)
+    plain.sphere_pos[:] = [10.0, 14.0, 16.0]; plain.sphere_radius = 4.0
+    ref1 = orc.State(plain, pos, vel, Cm, mass); ref1.step(4)
+    assert np.abs(ref.vel - ref1.vel).max() > 0.5, "the extra spheres touch nothing in this scene"
+    for path, math in ((1, 0), (2, 0), (3, 1)):
+        with make_solver(op, n, kernel_path=path, math_mode=math) as s:
+            s.set_colliders(extra)
+            s.upload(pos, vel, Cm, mass)
+            s.step(4)
+            gp, gv, gc, _ = s.download()
+        if math == 0:
+            helpers.assert_bit_equal(gp, ref.pos, "pos"); helpers.assert_bit_equal(gv, ref.vel, "vel"); helpers.assert_bit_equal(gc, ref.C, "C")
+        else:
+            # a particle within rounding of a sphere's surface may take or miss the unit push: compare the bulk
+            close = np.abs(gv - ref.vel).max(1) < 1e-3
+            assert close.mean() > 0.999 and np.abs(gp - ref.pos)[close].max() < 1e-3
+
+
+def test_checkpoint_resume_is_bit_exact(lib, tmp_path):
+    """save after 5 steps, load into a fresh solver, run 5 more: identical to 10 uninterrupted steps."""
+    import mpm_b200
+    op = orc.variant("3d_gpu", 32)
+    op.interaction = 0
+    pos, vel, Cm, mass = helpers.random_cloud(op, 20000, seed=8)
+    ref = orc.State(op, pos, vel, Cm, mass)
+    ref.step(10)
+    path = str(tmp_path / "state.mpm")
+    with make_solver(op, 20000, kernel_path=2) as a:
+        a.upload(pos, vel, Cm, mass)
+        a.step(5)
+        a.save_state(path)
+    assert os.path.getsize(path) == 64 + 80 * 20000
+    with make_solver(op, 20000, kernel_path=2) as b:
+        b.load_state(path)
+        assert b.num_particles == 20000 and b.stats().steps == 5
+        b.step(5)
+        gp, gv, gc, gm = b.download()
+    helpers.assert_bit_equal(gp, ref.pos, "pos"); helpers.assert_bit_equal(gv, ref.vel, "vel")
+    helpers.assert_bit_equal(gc, ref.C, "C"); helpers.assert_bit_equal(gm, ref.mass, "mass")
+    other = orc.variant("3d_gpu", 40)
+    with make_solver(other, 20000) as c:
+        with pytest.raises(mpm_b200.MpmError):
+            c.load_state(path)     # written for another grid
