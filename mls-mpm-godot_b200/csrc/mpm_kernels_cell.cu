@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? 3 : 6) k_p2g2_
 }
 
 // ---------------------------------------------------------------- G2P
-template <int B>
+template <int B, bool COMM, bool EXTRA>  // COMM: multi-GPU (lists the particles that leave the slab); EXTRA: sphere list
 struct G2PBody {
     using TL = Tile<B>;
     const DevParams& P;
@@ -547,13 +547,13 @@ struct G2PBody {
         const float Bx[3] = {Bxxy.x, Bxxy.y, Bxz}, By[3] = {Byxy.x, Byxy.y, Byz}, Bz[3] = {Bzxy.x, Bzxy.y, Bzz};
         const float Bm[9] = {Bx[0], Bx[1], Bx[2], By[0], By[1], By[2], Bz[0], Bz[1], Bz[2]};
         float np[3], cm[9];
-        g2p_finish<3>(P, old, Bm, v, np, cm);
+        g2p_finish<3, EXTRA>(P, old, Bm, v, np, cm);
         // multi-GPU: particles whose new base cell left this rank's slab are listed for the migration (few per warp).  One
         // that would land beyond the neighbouring slab (|v| dt larger than that slab is wide: numerical outliers of a
         // violent scene) is held back in the neighbour's far plane for this step and counted (MpmStats.slab_jump_clamps).
         bool stays = true;
         int side = 0;
-        if (mg.cnt) {
+        if constexpr (COMM) {
             const int cx = __float2int_rz(np[0]);
             if (cx < mg.x0 || cx >= mg.x1) {
                 stays = false;
@@ -568,9 +568,11 @@ struct G2PBody {
         q[1] = make_float4(v[1], v[2], cur[3], cm[0]);
         q[2] = make_float4(cm[1], cm[2], cm[3], cm[4]);
         q[3] = make_float4(cm[5], cm[6], cm[7], cm[8]);
-        if (!stays) {
-            const uint32_t slot = atomicAdd(mg.cnt + side, 1u);
-            if (slot < mg.rec_cap) (side ? mg.leaveR : mg.leaveL)[slot] = i;
+        if constexpr (COMM) {
+            if (!stays) {
+                const uint32_t slot = atomicAdd(mg.cnt + side, 1u);
+                if (slot < mg.rec_cap) (side ? mg.leaveR : mg.leaveL)[slot] = i;
+            }
         }
         if (cnt_next && stays) {  // bin key of the NEW position for the next step (leavers get theirs where they arrive)
             uint32_t k = cell_key(kg, __float2int_rz(np[0]), __float2int_rz(np[1]), __float2int_rz(np[2]));
@@ -584,8 +586,9 @@ struct G2PBody {
     __device__ __forceinline__ void finish() {}
 };
 
-// 4 CTAs per SM (128 registers, ~30 bytes of spills): measured 0.778 vs 0.823 ms on C4 against 3 CTAs at 158 registers
-template <int B>
+// 4 CTAs per SM (128 registers, ~30 bytes of spills): measured 0.778 vs 0.823 ms on C4 against 3 CTAs at 158 registers.
+// The multi-GPU classification is a separate instantiation: as a run-time branch it cost the single-GPU kernel 0.045 ms.
+template <int B, bool COMM, bool EXTRA>
 __global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? 4 : 8) k_g2p_cell(DevParams P, TileGeom g, ParticleView pv, CellArgs a,
                                                                                     const int4* __restrict__ grid, int raw_grid, KeyGeom kg, uint32_t nslots,
                                                                                     uint32_t* __restrict__ keys, uint32_t* __restrict__ cnt_next,
@@ -623,7 +626,7 @@ __global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? 4 : 8) k_g2p_c
             tv[0][idx] = vx; tv[1][idx] = vy; tv[2][idx] = vz;
         }
         __syncthreads();
-        G2PBody<B> body(P, pv, tl, tv, kg, nslots, keys, cnt_next, mg, lane, rec);
+        G2PBody<B, COMM, EXTRA> body(P, pv, tl, tv, kg, nslots, keys, cnt_next, mg, lane, rec);
         walk_chunks<B>(a, b, lane, warp, &s_bw, body);
     }
 }
@@ -691,6 +694,16 @@ int cell_p2g2(MpmSolver* s)
     return MPM_OK;
 }
 
+// the two G2P instantiations as names the launch macro can take
+template <int B>
+constexpr auto k_g2p_cell_single = k_g2p_cell<B, false, false>;
+template <int B>
+constexpr auto k_g2p_cell_comm = k_g2p_cell<B, true, false>;
+template <int B>
+constexpr auto k_g2p_cell_single_x = k_g2p_cell<B, false, true>;
+template <int B>
+constexpr auto k_g2p_cell_comm_x = k_g2p_cell<B, true, true>;
+
 int cell_g2p(MpmSolver* s)
 {
     int rc = check_cell_supported(s);
@@ -706,8 +719,14 @@ int cell_g2p(MpmSolver* s)
     if (rc) return rc;
     // The (x, y, z, |v|) hand-off in original index order is a 16-B scatter per particle (0.30 ms of 1.17 ms on C4 when
     // fused here): on this path it is produced on demand by mpm_get_positions instead of every step.
-    LAUNCH_CELL(k_g2p_cell, 0, 0, reinterpret_cast<const int4*>(s->grid), s->grid_raw ? 1 : 0, bin_key_geom(s), (uint32_t)bs->nslots, bs->keys, cnt_next, mg,
-                reinterpret_cast<float4*>(s->rec));
+#define G2P_ARGS reinterpret_cast<const int4*>(s->grid), s->grid_raw ? 1 : 0, bin_key_geom(s), (uint32_t)bs->nslots, bs->keys, cnt_next, mg, \
+                 reinterpret_cast<float4*>(s->rec)
+    const bool extra = s->dp.n_extra > 0;
+    if (mg.cnt && extra) LAUNCH_CELL(k_g2p_cell_comm_x, 0, 0, G2P_ARGS);
+    else if (mg.cnt) LAUNCH_CELL(k_g2p_cell_comm, 0, 0, G2P_ARGS);
+    else if (extra) LAUNCH_CELL(k_g2p_cell_single_x, 0, 0, G2P_ARGS);
+    else LAUNCH_CELL(k_g2p_cell_single, 0, 0, G2P_ARGS);
+#undef G2P_ARGS
     s->in_rec = true;  // the new particle state is in the records until the next binning (or ensure_planes)
     bs->next_valid = fuse;
     s->sorted_valid = false;  // positions moved: the layout is exact for one step only

@@ -121,7 +121,9 @@ __device__ __forceinline__ void g2p_node(float gvx, float gvy, float gvz, float 
 
 // Tail of G2P (F:468-514, X:548-587, D:372-416, g2p.glsl:108-150): C = 4B, advect, clamp, interaction,
 // predictive wall.  old = pre-advection position; writes new position/velocity/C into np/v/c.
-template <int DIM>
+// EXTRA = false compiles the sphere list out (the cell kernels instantiate both: at 128 registers the loop alone cost
+// the list-less case 2 %).
+template <int DIM, bool EXTRA = true>
 __device__ __forceinline__ void g2p_finish(const DevParams& P, const float old[3], const float B[9], float v[3],
                                            float np[3], float c[9])
 {
@@ -134,8 +136,9 @@ __device__ __forceinline__ void g2p_finish(const DevParams& P, const float old[3
         else np[a] = old[a];
     }
     if (P.interaction == 1 || P.interaction == 2) {
-        const float* q = (P.interaction == 1) ? np : old;
-        const float dx = ssub(q[0], P.sphere[0]), dy = ssub(q[1], P.sphere[1]), dz = ssub(q[2], P.sphere[2]);
+        const bool post = P.interaction == 1;  // (scalars, not a pointer into np / old: those arrays must stay in registers)
+        const float qx = post ? np[0] : old[0], qy = post ? np[1] : old[1], qz = post ? np[2] : old[2];
+        const float dx = ssub(qx, P.sphere[0]), dy = ssub(qy, P.sphere[1]), dz = ssub(qz, P.sphere[2]);
         const float d2 = sadd(sadd(smul(dx, dx), smul(dy, dy)), smul(dz, dz));
         if (d2 < smul(P.sphere_r, P.sphere_r)) {
             float fx = 0.0f, fy = 0.0f, fz = 0.0f;
@@ -147,8 +150,9 @@ __device__ __forceinline__ void g2p_finish(const DevParams& P, const float old[3
             v[1] = sadd(v[1], smul(fy, 1.0f));
             v[2] = sadd(v[2], smul(fz, 1.0f));
         }
+        if constexpr (EXTRA)
         for (int k = 0; k < P.n_extra; ++k) {  // sphere list (mpm_set_colliders): the same rule for every further sphere
-            const float ex = ssub(q[0], P.extra[k][0]), ey = ssub(q[1], P.extra[k][1]), ez = ssub(q[2], P.extra[k][2]);
+            const float ex = ssub(qx, P.extra[k][0]), ey = ssub(qy, P.extra[k][1]), ez = ssub(qz, P.extra[k][2]);
             const float e2 = sadd(sadd(smul(ex, ex), smul(ey, ey)), smul(ez, ez));
             if (e2 < smul(P.extra[k][3], P.extra[k][3])) {
                 float gx = 0.0f, gy = 0.0f, gz = 0.0f;
