@@ -1,5 +1,6 @@
 import sys, os
-sys.path[:0] = ['/root/repo', '/root/repo/mls-mpm-godot_b200', '/root/repo/tests']
+ROOT = __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
+sys.path[:0] = [ROOT, ROOT + '/mls-mpm-godot_b200', ROOT + '/tests']
 import numpy as np
 import mpm_b200
 grid = (256, 256, 256)

@@ -1,5 +1,6 @@
 import sys
-sys.path[:0] = ['/root/repo', '/root/repo/mls-mpm-godot_b200', '/root/repo/tests']
+ROOT = __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
+sys.path[:0] = [ROOT, ROOT + '/mls-mpm-godot_b200', ROOT + '/tests']
 import numpy as np, helpers, mpm_b200
 from oracle import orc
 # small scenes through every kernel family: reference-shaped, tiled strict, tiled fast, cell (incl. a pile-up and 2 slabs)
