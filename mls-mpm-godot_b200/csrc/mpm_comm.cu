@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(256) k_halo_diff(const int4* __restrict__ bloc
 //   k_halo_wait_add  waits for the neighbours' flags to reach the message number, then adds the received planes.
 // No acknowledgement is needed: a region is rewritten one step later, and between two pushes of the same pass this rank
 // has waited for a message that the neighbour only sent after consuming the previous one (push0, wait0, push1, wait1
-// alternate on both sides).  A wait gives up after ~2 s and raises an error flag instead of hanging the GPU.
+// alternate on both sides).  A wait gives up after ~10 s and raises an error flag instead of hanging the GPU.
 constexpr int P2P_FLAG_STRIDE = 32;  // uint32 words between flags (one 128-B line each)
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(256) k_halo_wait_add(int4* __restrict__ blockL
             const uint32_t* f = side ? flagR : flagL;
             if (!f) continue;
             while ((int32_t)(ld_acquire_sys(f) - seq) < 0) {
-                if (clock64() - t0 > 4000000000ll) { atomicExch(err, 1u); break; }
+                if (clock64() - t0 > 20000000000ll) { atomicExch(err, 1u); break; }  // ~10 s
                 __nanosleep(200);
             }
         }
@@ -838,7 +838,7 @@ static int migrate_impl(MpmSolver* s, View pv, bool recut = false)
     CKM(cudaStreamSynchronize(s->stream));
     const uint32_t nL = c->h_cnt[0], nR = c->h_cnt[1], mL = hasL ? c->h_cnt[2] : 0, mR = hasR ? c->h_cnt[3] : 0;
     c->slab_jump_clamps += c->h_cnt[8];
-    if (c->h_cnt[9]) { s->err = "multi-GPU: a neighbour's halo planes did not arrive within 2 s (peer-store path)"; return MPM_ERR_COMM; }
+    if (c->h_cnt[9]) { s->err = "multi-GPU: a neighbour's halo planes did not arrive within 10 s (peer-store path)"; return MPM_ERR_COMM; }
     if ((int64_t)std::max(std::max(nL, nR), std::max(mL, mR)) > c->rec_cap) { s->err = "multi-GPU: migration buffer too small"; return MPM_ERR_COMM; }
     const int64_t n_stay = n - nL - nR;
     if (n_stay + mL + mR > s->cap) { s->err = "multi-GPU: arriving particles exceed max_particles of this rank"; return MPM_ERR_COMM; }
