@@ -124,16 +124,15 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(const uint32_t* __restrict
 // that the 32 virtual cells of a chunk (= the 32 lanes of a warp in the cell kernels) carry nearly equal work and no
 // lane ever walks more than VROWS particles; then the start slot of every chunk.
 //   ord[v0 + pos] = cell, cnts[v0 + pos] = count          (v0 = block * NV, NV = 2 * NC positions per block)
-//   vfirst[cell] = position of the cell's first full virtual cell, nfull[cell] = how many, vlast[cell] = position of the
-//   virtual cell that holds the remainder
+//   cellmeta[cell] = {position of the cell's first full virtual cell | position of the one holding the remainder << 16,
+//                     number of full ones}
 constexpr uint32_t VROWS = 32;
 
 template <int CELL_BITS>
 __global__ void __launch_bounds__(1 << CELL_BITS) k_block_order(const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ bbase,
                                                                const uint32_t* __restrict__ active, const uint32_t* __restrict__ misc,
                                                                uint16_t* __restrict__ ord, uint32_t* __restrict__ cnts,
-                                                               uint16_t* __restrict__ vfirst, uint16_t* __restrict__ vlast,
-                                                               uint16_t* __restrict__ nfull, uint32_t* __restrict__ pstart,
+                                                               uint2* __restrict__ cellmeta, uint32_t* __restrict__ pstart,
                                                                uint16_t* __restrict__ stab)
 {
     constexpr int NC = 1 << CELL_BITS, NV = 2 * NC, NBIN = 64, NW = NC / 32, EXTRA = NV - NC;
@@ -176,7 +175,7 @@ __global__ void __launch_bounds__(1 << CELL_BITS) k_block_order(const uint32_t* 
     const uint32_t pos_rem = base[binr] + atomicAdd(&cursor[binr], 1u);
     for (uint32_t k = 0; k < g; ++k) { s_cnt[pos_full + k] = VROWS; s_ord[pos_full + k] = (uint16_t)t; }
     s_cnt[pos_rem] = rem; s_ord[pos_rem] = (uint16_t)t;
-    vfirst[blk0 + t] = (uint16_t)pos_full; vlast[blk0 + t] = (uint16_t)pos_rem; nfull[blk0 + t] = (uint16_t)g;
+    cellmeta[blk0 + t] = make_uint2(pos_full | (pos_rem << 16), g);  // one 8-byte load per particle in k_place
     __syncthreads();
     // counts, chunk starts and S tables: NV positions, NC threads -> two halves
 #pragma unroll
@@ -196,19 +195,21 @@ __global__ void __launch_bounds__(1 << CELL_BITS) k_block_order(const uint32_t* 
         if (lane == 31) wsum[w] = xs;
         __syncthreads();
         const int chunk = p >> 5;
+        // Chunk row for k_place (one 32-byte sector): [0] flags chunks whose counts are not strictly ordered (a count >= 63
+        // shares the last sort bin: those take the general path); [1..13] S(r) = sum over the chunk's virtual cells of
+        // min(count, r), the first slot of the rank-r row; [14..15] the chunk's start slot (also in pstart[] for the walk).
+        const uint32_t maxc = __reduce_max_sync(0xffffffffu, v);
+        uint16_t* st = stab + ((size_t)(v0 >> 5) + chunk) * 16;
         if (lane == 0) {
             uint32_t off = carry_s;
             for (int k = 0; k < w; ++k) off += wsum[k];
-            pstart[(v0 >> 5) + chunk] = bbase[b] + off;
+            const uint32_t ps = bbase[b] + off;
+            pstart[(v0 >> 5) + chunk] = ps;
+            st[0] = (maxc >= (uint32_t)(NBIN - 1)) ? 1 : 0;
+            st[14] = (uint16_t)(ps & 0xffffu); st[15] = (uint16_t)(ps >> 16);
         }
-        // S(r) = sum over the chunk's virtual cells of min(count, r) for r = 1..15 (first slot of the rank-r row), so that
-        // k_place needs one 2-byte load instead of the chunk's 32 counts.  Entry 0 flags chunks whose counts are not
-        // strictly ordered (a count >= 63 shares the last sort bin): those take k_place's general path.
-        const uint32_t maxc = __reduce_max_sync(0xffffffffu, v);
-        uint16_t* st = stab + ((size_t)(v0 >> 5) + chunk) * 16;
-        if (lane == 0) st[0] = (maxc >= (uint32_t)(NBIN - 1)) ? 1 : 0;
 #pragma unroll
-        for (int r = 1; r < 16; ++r) {
+        for (int r = 1; r < 14; ++r) {
             const uint32_t sr = __reduce_add_sync(0xffffffffu, min(v, (uint32_t)r));
             if (lane == 0) st[r] = (uint16_t)sr;
         }
@@ -223,8 +224,7 @@ __global__ void __launch_bounds__(1 << CELL_BITS) k_block_order(const uint32_t* 
 
 // rank inside the cell from an atomic cursor -> (virtual cell, row) -> destination slot from the chunk's counts
 template <int CELL_BITS>
-__global__ void __launch_bounds__(256) k_place(const uint32_t* __restrict__ keys, int64_t n, const uint16_t* __restrict__ vfirst,
-                                               const uint16_t* __restrict__ vlast, const uint16_t* __restrict__ nfull,
+__global__ void __launch_bounds__(256) k_place(const uint32_t* __restrict__ keys, int64_t n, const uint2* __restrict__ cellmeta,
                                                const uint32_t* __restrict__ cnts, const uint32_t* __restrict__ pstart,
                                                const uint16_t* __restrict__ stab, uint32_t* __restrict__ fill, uint32_t* __restrict__ src_of)
 {
@@ -233,17 +233,20 @@ __global__ void __launch_bounds__(256) k_place(const uint32_t* __restrict__ keys
     if (i >= n) return;
     const uint32_t key = keys[i];
     const uint32_t rc = atomicAdd(&fill[key], 1u);  // rank inside the (real) cell
-    const uint32_t g = nfull[key];
+    const uint2 cm = cellmeta[key];  // x: position of the first full virtual cell | position of the remainder << 16; y: full ones
+    const uint32_t g = cm.y;
     uint32_t pos, r;
-    if (rc < g * VROWS) { pos = vfirst[key] + rc / VROWS; r = rc % VROWS; }
-    else { pos = vlast[key]; r = rc - g * VROWS; }
+    if (rc < g * VROWS) { pos = (cm.x & 0xffffu) + rc / VROWS; r = rc % VROWS; }
+    else { pos = cm.x >> 16; r = rc - g * VROWS; }
     const uint32_t v0 = (key >> CELL_BITS) * NV;
     const uint32_t chunk = pos >> 5, lane = pos & 31u;
     const uint32_t gchunk = (v0 >> 5) + chunk;
-    if (r < 16u && stab[(size_t)gchunk * 16] == 0) {
+    const uint16_t* row = stab + (size_t)gchunk * 16;
+    if (r < 14u && row[0] == 0) {
         // counts strictly ordered, descending: every lower lane still has a particle at rank r (r < own count <= theirs)
-        const uint32_t below = r ? stab[(size_t)gchunk * 16 + r] : 0u;
-        src_of[pstart[gchunk] + below + lane] = (uint32_t)i;
+        const uint32_t below = r ? row[r] : 0u;
+        const uint32_t ps = *reinterpret_cast<const uint32_t*>(row + 14);
+        src_of[ps + below + lane] = (uint32_t)i;
         return;
     }
     const uint4* c4 = reinterpret_cast<const uint4*>(cnts + v0 + chunk * 32u);
@@ -324,9 +327,7 @@ int bin_create(MpmSolver* s)
     CKB(cudaMalloc(&st->cnts, sizeof(uint32_t) * (nvpos + 32)));
     CKB(cudaMemsetAsync(st->cnts, 0, sizeof(uint32_t) * (nvpos + 32), s->stream));
     CKB(cudaMalloc(&st->ord, sizeof(uint16_t) * nvpos));
-    CKB(cudaMalloc(&st->vfirst, sizeof(uint16_t) * st->nslots));
-    CKB(cudaMalloc(&st->vlast, sizeof(uint16_t) * st->nslots));
-    CKB(cudaMalloc(&st->nfull, sizeof(uint16_t) * st->nslots));
+    CKB(cudaMalloc(&st->cellmeta, sizeof(uint2) * st->nslots));
     CKB(cudaMalloc(&st->pstart, sizeof(uint32_t) * (nvpos >> 5)));
     CKB(cudaMalloc(&st->stab, sizeof(uint16_t) * 16 * (nvpos >> 5)));
     CKB(cudaMalloc(&st->bsum, sizeof(uint32_t) * st->nblocks));
@@ -347,7 +348,7 @@ void bin_destroy(MpmSolver* s)
 {
     BinState* st = s->bin;
     if (!st) return;
-    cudaFree(st->cnt[0]); cudaFree(st->cnt[1]); cudaFree(st->cnts); cudaFree(st->ord); cudaFree(st->vfirst); cudaFree(st->vlast); cudaFree(st->nfull); cudaFree(st->pstart); cudaFree(st->stab);
+    cudaFree(st->cnt[0]); cudaFree(st->cnt[1]); cudaFree(st->cnts); cudaFree(st->ord); cudaFree(st->cellmeta); cudaFree(st->pstart); cudaFree(st->stab);
     cudaFree(st->bsum); cudaFree(st->bbase); cudaFree(st->fill); cudaFree(st->keys); cudaFree(st->src_of); cudaFree(st->active);
     cudaFree(st->misc);
     delete st;
@@ -379,16 +380,16 @@ int bin_particles(MpmSolver* s)
     if (st->cell_bits == 9) {
         k_block_sums<9><<<nbw, 256, 0, s->stream>>>(st->cnt[nxt], st->nblocks, st->bsum);
         k_scan_blocks<<<1, 1024, 0, s->stream>>>(st->bsum, st->nblocks, st->bbase, st->active, st->misc);
-        k_block_order<9><<<(unsigned)st->nblocks, 512, 0, s->stream>>>(st->cnt[nxt], st->bbase, st->active, st->misc, st->ord, st->cnts, st->vfirst, st->vlast, st->nfull, st->pstart, st->stab);
+        k_block_order<9><<<(unsigned)st->nblocks, 512, 0, s->stream>>>(st->cnt[nxt], st->bbase, st->active, st->misc, st->ord, st->cnts, st->cellmeta, st->pstart, st->stab);
     } else {
         k_block_sums<6><<<nbw, 256, 0, s->stream>>>(st->cnt[nxt], st->nblocks, st->bsum);
         k_scan_blocks<<<1, 1024, 0, s->stream>>>(st->bsum, st->nblocks, st->bbase, st->active, st->misc);
-        k_block_order<6><<<(unsigned)st->nblocks, 64, 0, s->stream>>>(st->cnt[nxt], st->bbase, st->active, st->misc, st->ord, st->cnts, st->vfirst, st->vlast, st->nfull, st->pstart, st->stab);
+        k_block_order<6><<<(unsigned)st->nblocks, 64, 0, s->stream>>>(st->cnt[nxt], st->bbase, st->active, st->misc, st->ord, st->cnts, st->cellmeta, st->pstart, st->stab);
     }
     s->launches += 3;
     if (n > 0) {
-        if (st->cell_bits == 9) k_place<9><<<nb, 256, 0, s->stream>>>(st->keys, n, st->vfirst, st->vlast, st->nfull, st->cnts, st->pstart, st->stab, st->fill, st->src_of);
-        else k_place<6><<<nb, 256, 0, s->stream>>>(st->keys, n, st->vfirst, st->vlast, st->nfull, st->cnts, st->pstart, st->stab, st->fill, st->src_of);
+        if (st->cell_bits == 9) k_place<9><<<nb, 256, 0, s->stream>>>(st->keys, n, st->cellmeta, st->cnts, st->pstart, st->stab, st->fill, st->src_of);
+        else k_place<6><<<nb, 256, 0, s->stream>>>(st->keys, n, st->cellmeta, st->cnts, st->pstart, st->stab, st->fill, st->src_of);
         if (s->in_rec) {  // the last G2P left the state as records: gather straight into the planes
             k_gather_rec<<<nb, 256, 0, s->stream>>>(reinterpret_cast<const float4*>(s->rec), s->view(), st->src_of, s->orig_id, s->orig_id_alt, n);
             s->in_rec = false;

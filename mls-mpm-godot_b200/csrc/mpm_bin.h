@@ -19,11 +19,10 @@ struct BinState {
     // is split), ordered by count, descending, in chunks of 32
     uint32_t* cnts = nullptr;        // [2 * nslots] count at each position
     uint16_t* ord = nullptr;         // [2 * nslots] position -> cell id inside the block
-    uint16_t* vfirst = nullptr;      // [nslots] cell -> position of its first full virtual cell
-    uint16_t* vlast = nullptr;       // [nslots] cell -> position of the virtual cell holding the remainder
-    uint16_t* nfull = nullptr;       // [nslots] cell -> number of full virtual cells
+    uint2* cellmeta = nullptr;       // [nslots] cell -> {first full virtual cell | remainder's position << 16, number of full ones}
     uint32_t* pstart = nullptr;      // [2 * nslots / 32] first slot of every chunk
-    uint16_t* stab = nullptr;        // [2 * nslots / 32][16] first slot of the rank-r row relative to pstart, r < 16 ([0] = irregular flag)
+    uint16_t* stab = nullptr;        // [2 * nslots / 32][16] per chunk: [0] irregular flag, [1..13] first slot of the rank-r row
+                                     // relative to the chunk start, [14..15] the chunk start (one 32-B sector for k_place)
     uint32_t* bsum = nullptr;        // [nblocks] particles per block
     uint32_t* bbase = nullptr;       // [nblocks + 1] exclusive scan
     uint32_t* fill = nullptr;        // [nslots] placement cursor
