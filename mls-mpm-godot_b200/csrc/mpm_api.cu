@@ -630,7 +630,6 @@ extern "C" int32_t mpm_run_phase(MpmSolver* s, int32_t phase)
         s->timing = tm;
         if (rc) return rc;
     }
-    if (s->in_rec && phase != PH_SORT && phase != PH_CLEAR && phase != PH_UPDATE && s->sorted_valid) ensure_planes(s);
     bool tm = s->timing; s->timing = false;
     size_t cursor = 0;
     int rc = run_phase(s, phase, cursor);

@@ -265,36 +265,28 @@ __global__ void __launch_bounds__(256) k_place(const uint32_t* __restrict__ keys
     src_of[pstart[gchunk] + below + before] = (uint32_t)i;
 }
 
-__global__ void __launch_bounds__(256) k_gather(ParticleView src, ParticleView dst, const uint32_t* __restrict__ src_of,
-                                                const uint32_t* __restrict__ id_src, uint32_t* __restrict__ id_dst, int64_t n)
+// grouped planes -> 64-byte records (a freshly uploaded or edited particle set enters the cell path)
+__global__ void __launch_bounds__(256) k_planes_to_rec(ParticleView pv, float4* __restrict__ rec, int64_t n)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t j = src_of[i];
-    float v[NPLANES];
+    const float* q = pv.rec(i);
 #pragma unroll
-    for (int k = 0; k < NPLANES; ++k) v[k] = src.at(k, j);
-    const uint32_t id = id_src[j];
-#pragma unroll
-    for (int k = 0; k < NPLANES; ++k) dst.at(k, i) = v[k];
-    id_dst[i] = id;
+    for (int k = 0; k < 4; ++k)
+        rec[4 * i + k] = make_float4(q[(4 * k + 0) * GROUP], q[(4 * k + 1) * GROUP], q[(4 * k + 2) * GROUP], q[(4 * k + 3) * GROUP]);
 }
 
-// gather from the 64-byte records G2P wrote: two full sectors per particle whatever the permutation
-__global__ void __launch_bounds__(256) k_gather_rec(const float4* __restrict__ rec, ParticleView dst, const uint32_t* __restrict__ src_of,
-                                                    const uint32_t* __restrict__ id_src, uint32_t* __restrict__ id_dst, int64_t n)
+// What P2G_1 leaves for G2P -- position and mass planes and the original indices, in slot order -- for a G2P phase that
+// is run without a P2G_1 since the last binning (mpm_run_phase).
+__global__ void __launch_bounds__(256) k_gather_g2p_inputs(const float4* __restrict__ rec, ParticleView dst, const uint32_t* __restrict__ src_of,
+                                                           const uint32_t* __restrict__ id_src, uint32_t* __restrict__ id_dst, int64_t n)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t j = src_of[i];
-    const float4 a = rec[4 * (size_t)j], b = rec[4 * (size_t)j + 1], c = rec[4 * (size_t)j + 2], d = rec[4 * (size_t)j + 3];
-    const uint32_t id = id_src[j];
-    float* q = dst.rec(i);
-    q[0 * GROUP] = a.x; q[1 * GROUP] = a.y; q[2 * GROUP] = a.z; q[3 * GROUP] = a.w;
-    q[4 * GROUP] = b.x; q[5 * GROUP] = b.y; q[6 * GROUP] = b.z; q[7 * GROUP] = b.w;
-    q[8 * GROUP] = c.x; q[9 * GROUP] = c.y; q[10 * GROUP] = c.z; q[11 * GROUP] = c.w;
-    q[12 * GROUP] = d.x; q[13 * GROUP] = d.y; q[14 * GROUP] = d.z; q[15 * GROUP] = d.w;
-    id_dst[i] = id;
+    const float4 a = rec[4 * (size_t)j], b = rec[4 * (size_t)j + 1];
+    dst.at(PX, i) = a.x; dst.at(PY, i) = a.y; dst.at(PZ, i) = a.z; dst.at(PM, i) = b.z;
+    id_dst[i] = id_src[j];
 }
 
 // ---------------------------------------------------------------- host side
@@ -334,7 +326,8 @@ int bin_create(MpmSolver* s)
     CKB(cudaMalloc(&st->bbase, sizeof(uint32_t) * (st->nblocks + 1)));
     CKB(cudaMalloc(&st->fill, sizeof(uint32_t) * st->nslots));
     CKB(cudaMalloc(&st->keys, sizeof(uint32_t) * s->pitch));
-    CKB(cudaMalloc(&st->src_of, sizeof(uint32_t) * s->pitch));
+    CKB(cudaMalloc(&st->src_of, sizeof(uint32_t) * (s->pitch + 64)));  // (the cell kernels read one row past the last slot)
+    CKB(cudaMemsetAsync(st->src_of, 0, sizeof(uint32_t) * (s->pitch + 64), s->stream));
     CKB(cudaMalloc(&st->active, sizeof(uint32_t) * st->nblocks));
 
     CKB(cudaMalloc(&st->misc, sizeof(uint32_t) * BIN_MISC_WORDS));
@@ -367,11 +360,16 @@ int bin_particles(MpmSolver* s)
     const int64_t n = s->n;
     const int nxt = st->cur ^ 1;
     const unsigned nb = (unsigned)((n + 255) / 256);
+    // On this path the particle state lives in the 64-byte records: G2P writes them, the P2G kernels read them through
+    // src_of, and the binning never moves a particle.  A set that was just uploaded / edited is in the planes: convert once.
+    if (!s->in_rec) {
+        if (n > 0) { k_planes_to_rec<<<nb, 256, 0, s->stream>>>(s->view(), reinterpret_cast<float4*>(s->rec), n); s->launches += 1; }
+        s->in_rec = true;
+    }
     if (!st->next_valid) {  // no G2P has produced keys/counts for this particle set: compute them from the positions
         CKB(cudaMemsetAsync(st->cnt[nxt], 0, sizeof(uint32_t) * st->nslots, s->stream));
         if (n > 0) {
-            if (s->in_rec) k_bin_keys<RecView><<<nb, 256, 0, s->stream>>>(bin_key_geom(s), s->rview(), 0, n, (uint32_t)st->nslots, st->keys, st->cnt[nxt]);
-            else k_bin_keys<ParticleView><<<nb, 256, 0, s->stream>>>(bin_key_geom(s), s->view(), 0, n, (uint32_t)st->nslots, st->keys, st->cnt[nxt]);
+            k_bin_keys<RecView><<<nb, 256, 0, s->stream>>>(bin_key_geom(s), s->rview(), 0, n, (uint32_t)st->nslots, st->keys, st->cnt[nxt]);
             s->launches += 1;
         }
     }
@@ -390,16 +388,9 @@ int bin_particles(MpmSolver* s)
     if (n > 0) {
         if (st->cell_bits == 9) k_place<9><<<nb, 256, 0, s->stream>>>(st->keys, n, st->cellmeta, st->cnts, st->pstart, st->stab, st->fill, st->src_of);
         else k_place<6><<<nb, 256, 0, s->stream>>>(st->keys, n, st->cellmeta, st->cnts, st->pstart, st->stab, st->fill, st->src_of);
-        if (s->in_rec) {  // the last G2P left the state as records: gather straight into the planes
-            k_gather_rec<<<nb, 256, 0, s->stream>>>(reinterpret_cast<const float4*>(s->rec), s->view(), st->src_of, s->orig_id, s->orig_id_alt, n);
-            s->in_rec = false;
-        } else {
-            k_gather<<<nb, 256, 0, s->stream>>>(s->view(), s->view_alt(), st->src_of, s->orig_id, s->orig_id_alt, n);
-            std::swap(s->part, s->part_alt);
-        }
-        s->launches += 2;
-        std::swap(s->orig_id, s->orig_id_alt);
+        s->launches += 1;
     }
+    s->g2p_inputs = false;  // position / mass planes and slot-order ids of this layout: written by P2G_1
     st->cur = nxt;
     st->next_valid = false;
     // the other count buffer receives the next step's counts from G2P: clear it now
@@ -423,6 +414,19 @@ int bin_keys_range(MpmSolver* s, int64_t first, int64_t count)
     if (s->in_rec) k_bin_keys<RecView><<<nb, 256, 0, s->stream>>>(bin_key_geom(s), s->rview(), first, count, (uint32_t)st->nslots, st->keys, st->cnt[st->cur ^ 1]);
     else k_bin_keys<ParticleView><<<nb, 256, 0, s->stream>>>(bin_key_geom(s), s->view(), first, count, (uint32_t)st->nslots, st->keys, st->cnt[st->cur ^ 1]);
     s->launches += 1;
+    return MPM_OK;
+}
+
+// G2P without a P2G_1 since the last binning (phases run one by one)
+int bin_g2p_inputs(MpmSolver* s)
+{
+    if (s->g2p_inputs) return MPM_OK;
+    if (s->n > 0) {
+        k_gather_g2p_inputs<<<(unsigned)((s->n + 255) / 256), 256, 0, s->stream>>>(reinterpret_cast<const float4*>(s->rec), s->view(), s->bin->src_of,
+                                                                                s->orig_id, s->orig_id_alt, s->n);
+        s->launches += 1;
+    }
+    s->g2p_inputs = true;
     return MPM_OK;
 }
 

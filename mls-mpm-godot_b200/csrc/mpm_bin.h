@@ -27,7 +27,7 @@ struct BinState {
     uint32_t* bbase = nullptr;       // [nblocks + 1] exclusive scan
     uint32_t* fill = nullptr;        // [nslots] placement cursor
     uint32_t* keys = nullptr;        // [pitch] cell key of each particle for the NEXT binning (slot order)
-    uint32_t* src_of = nullptr;      // [pitch] gather list
+    uint32_t* src_of = nullptr;      // [pitch + 64] slot -> index of the particle's record (the records stay where G2P wrote them)
     uint32_t* active = nullptr;      // [nblocks] non-empty blocks, ascending
     uint32_t* misc = nullptr;        // BIN_MISC_WORDS counters
 };
@@ -35,6 +35,7 @@ struct BinState {
 int bin_create(MpmSolver* s);
 void bin_destroy(MpmSolver* s);
 int bin_particles(MpmSolver* s);
+int bin_g2p_inputs(MpmSolver* s);  // position / mass planes + slot-order ids, when no P2G_1 ran since the binning
 
 // cell kernels (mpm_kernels_cell.cu)
 int cell_p2g1(MpmSolver* s);

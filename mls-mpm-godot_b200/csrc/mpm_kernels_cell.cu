@@ -82,17 +82,28 @@ __device__ __forceinline__ void cell_axis(float p, float fc, float w[3], float d
 // shared-memory staging buffer otherwise (P2G: 16 / 13 fields; prefetch.global.L1 was tried first and left the L1 hit
 // rate at 5 %).
 //
-// Body interface:  begin_chunk(chunk)   per-cell set-up (stencil registers / accumulators)
-//                  fetch(i)            start bringing particle slot i in (lane-private; may be predicated off)
-//                  take()              the particle fetched last becomes the current one
-//                  compute(i)          process the current particle (slot i)
-//                  end_chunk(has)      flush per-cell results
-//                  finish()            after the warp's last chunk of the block
+// Body interface (all calls warp-uniform except compute):
+//                  begin_chunk(cell)      per-cell set-up (stencil registers / accumulators)
+//                  fetch(base, mask, k)   start bringing a row in: the lanes set in `mask` own slots base, base + 1, ... in lane
+//                                         order.  k says how the row was announced: ROW_NEXT = it follows the row fetched last,
+//                                         ROW_HINTED = it starts at the slot given to hint_chunk, ROW_COLD = neither
+//                  hint_chunk(slot)       the warp's next chunk will start at `slot`
+//                  take()                 the row fetched last becomes the current one
+//                  compute(i, t)          process this lane's particle of the current row (slot i = row base + t)
+//                  end_chunk(has)         flush per-cell results
+//                  finish()               after the warp's last chunk of the block
+enum { ROW_COLD = 0, ROW_NEXT = 1, ROW_HINTED = 2 };
 // 4-byte asynchronous global -> shared copy (LDGSTS): no register is held while the load is in flight
 __device__ __forceinline__ void cp_async4(float* smem, const float* gmem)
 {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem));
+}
+// 16-byte copy, L2 only (the records are read once per kernel)
+__device__ __forceinline__ void cp_async16(float* smem, const float* gmem)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -130,7 +141,7 @@ __device__ __forceinline__ void walk_chunks(const CellArgs& a, int b, int lane, 
             L_nx = a.ord[v0 + chunk_nx * 32 + lane];
             st_nx = a.pstart[(v0 >> 5) + chunk_nx];
         }
-        if (!have && c > 0) body.fetch(slot0 + __popc(m & lt));
+        if (!have) body.fetch(slot0, m, ROW_COLD);
         have = false;
         body.begin_chunk((int)L);
 #pragma unroll 1
@@ -141,13 +152,17 @@ __device__ __forceinline__ void walk_chunks(const CellArgs& a, int b, int lane, 
             const unsigned m1 = __ballot_sync(0xffffffffu, on1);
             body.take();
             if (m1) {
-                if (on1) body.fetch(slot0 + __popc(m) + __popc(m1 & lt));
+                body.fetch(slot0 + __popc(m), m1, ROW_NEXT);
             } else {
                 const unsigned mn = __ballot_sync(0xffffffffu, c_nx > 0);
-                if (c_nx > 0) body.fetch(st_nx + __popc(mn & lt));
+                if (mn) {
+                    if (r > 0) body.fetch(st_nx, mn, ROW_HINTED);
+                    else body.fetch(st_nx, mn, ROW_COLD);  // single-row chunk: no hint was given yet
+                }
                 have = true;
             }
-            if (on) body.compute(i);
+            if (on) body.compute(i, (uint32_t)__popc(m & lt));
+            if (r == 0) body.hint_chunk(st_nx);  // (here, not where the chunk is claimed: st_nx has arrived by now)
             slot0 += __popc(m);
             m = m1;
             if (!m) break;
@@ -170,51 +185,99 @@ struct CellPos {  // the cell (id L inside the block) this lane owns in the curr
     }
 };
 
+// ---------------------------------------------------------------- rows of records for the P2G kernels
+// The particle state between steps is the array of 64-byte records G2P wrote (slot order of the previous step); the
+// binning only produces src_of[slot] = record index.  The P2G kernels read the records THROUGH that index -- two full
+// sectors per particle whatever the permutation -- which saves the gather pass of the binning (136 bytes per particle,
+// 0.66 ms of 3.58 ms on C4).  A row (<= 32 particles in consecutive slots) is brought in by the whole warp: lane 4q + j
+// copies 16-byte piece j of the row's records q, q + 8, q + 16, q + 24 (one cp.async.cg each: 4 per lane and row, where
+// the plane layout needed 16), so the four lanes of a quad cover one record = one 64-byte request.  Piece j of record t
+// lands at chunk (j ^ (t >> 1)) & 3 of the record's 64 bytes: the owner's four LDS.128 are then conflict-free (8
+// consecutive records cover all 8 bank quads).  The record indices of a row come from one coalesced load that is issued
+// a row ahead (ix_row) or, for the first row of the warp's next chunk, when that chunk is announced (ix_chunk), and are
+// passed around with SHFL; only the first row after a block change pays the load's latency.
+template <bool IDS>  // IDS: also bring the particles' original indices along (P2G_1 writes them out in slot order)
+struct RowStage {
+    static constexpr int WORDS = 32 * 16 + (IDS ? 32 : 0);  // one buffer, in 4-byte words
+    const float* rec;
+    const uint32_t* src_of;
+    const uint32_t* id_src;
+    float* buf;  // the warp's two buffers
+    int lane;
+    uint32_t ix_row = 0, ix_chunk = 0;
+    int wr = 0, rd = 0;
+    __device__ __forceinline__ RowStage(const float* rec_, const uint32_t* src_of_, const uint32_t* id_src_, float* buf_, int lane_)
+        : rec(rec_), src_of(src_of_), id_src(id_src_), buf(buf_), lane(lane_) {}
+    __device__ __forceinline__ void hint_chunk(uint32_t slot) { ix_chunk = src_of[slot + lane]; }
+    __device__ __forceinline__ void fetch(uint32_t base, unsigned mask, int kind)
+    {
+        const int cnt = __popc(mask);
+        const uint32_t ix = (kind == ROW_NEXT) ? ix_row : (kind == ROW_HINTED) ? ix_chunk : src_of[base + lane];
+        float* d = buf + wr * WORDS;
+        const int q = lane >> 2, j = lane & 3;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            if (8 * it >= cnt) break;
+            const int t = 8 * it + q;
+            const uint32_t src = __shfl_sync(0xffffffffu, ix, t);
+            if (t < cnt) cp_async16(d + t * 16 + ((j ^ (t >> 1)) & 3) * 4, rec + (size_t)src * 16 + j * 4);
+        }
+        if (IDS && lane < cnt) cp_async4(d + 32 * 16 + lane, reinterpret_cast<const float*>(id_src + ix));
+        cp_async_commit();
+        ix_row = src_of[base + cnt + lane];  // (src_of is padded: reading past the last particle is harmless)
+    }
+    __device__ __forceinline__ void take()
+    {
+        cp_async_wait_all();
+        __syncwarp();  // the pieces of a record were copied by four different lanes
+        rd = wr;
+        wr ^= 1;
+    }
+    // record t of the current row: (px, py, pz, vx) (vy, vz, m, c0) (c1..c4) (c5..c8)
+    __device__ __forceinline__ void load(uint32_t t, float4& a, float4& b, float4& c, float4& d) const
+    {
+        const float4* r = reinterpret_cast<const float4*>(buf + rd * WORDS) + 4 * t;
+        const uint32_t s = (t >> 1) & 3u;
+        a = r[s]; b = r[1u ^ s]; c = r[2u ^ s]; d = r[3u ^ s];
+    }
+    __device__ __forceinline__ uint32_t id(uint32_t t) const { return __float_as_uint(buf[rd * WORDS + 32 * 16 + t]); }
+};
+
 // ---------------------------------------------------------------- P2G_1
 template <int B>
 struct P2G1Body {
     using TL = Tile<B>;
     const DevParams& P;
-    const ParticleView& pv;
+    const ParticleView& pv;  // out: position and mass planes in slot order (what G2P reads)
+    uint32_t* id_dst;        // out: original indices in slot order
     const TL& tl;
     int (*tile)[TL::WORDS];
-    int lane;
-    float* stage;  // this lane's column of the warp's two staging buffers: stage[(buf * NPLANES + field) * 32]
-    int wr = 0, rd = 0;
+    RowStage<true> st;
     CellPos<B> cp;
     float2 axy[27], azm[27];  // accumulators packed for FFMA2: (momentum x, momentum y) and (momentum z, mass)
-    __device__ __forceinline__ P2G1Body(const DevParams& P_, const ParticleView& pv_, const TL& tl_, int (*tile_)[TL::WORDS], int lane_,
-                                        float* stage_)
-        : P(P_), pv(pv_), tl(tl_), tile(tile_), lane(lane_), stage(stage_) {}
+    __device__ __forceinline__ P2G1Body(const DevParams& P_, const ParticleView& pv_, uint32_t* id_dst_, const TL& tl_, int (*tile_)[TL::WORDS],
+                                        const RowStage<true>& st_)
+        : P(P_), pv(pv_), id_dst(id_dst_), tl(tl_), tile(tile_), st(st_) {}
     __device__ __forceinline__ void begin_chunk(int L)
     {
         cp.set(tl, L);
 #pragma unroll
         for (int n = 0; n < 27; ++n) { axy[n] = make_float2(0.0f, 0.0f); azm[n] = make_float2(0.0f, 0.0f); }
     }
-    __device__ __forceinline__ void fetch(uint32_t i)
+    __device__ __forceinline__ void fetch(uint32_t base, unsigned mask, int kind) { st.fetch(base, mask, kind); }
+    __device__ __forceinline__ void hint_chunk(uint32_t slot) { st.hint_chunk(slot); }
+    __device__ __forceinline__ void take() { st.take(); }
+    __device__ __forceinline__ void compute(uint32_t i, uint32_t t)
     {
-        const float* q = pv.rec(i);
-        float* d = stage + wr * (NPLANES * 32);
-#pragma unroll
-        for (int k = 0; k < NPLANES; ++k) cp_async4(d + k * 32, q + k * GROUP);
-        cp_async_commit();
-    }
-    __device__ __forceinline__ void take()
-    {
-        cp_async_wait_all();  // (only this lane's own copies are read back: no warp-level sync needed)
-        rd = wr;
-        wr ^= 1;
-    }
-    __device__ __forceinline__ void compute(uint32_t)
-    {
-        const float* q = stage + rd * (NPLANES * 32);
-        const float px = q[PX * 32], py = q[PY * 32], pz = q[PZ * 32];
-        const float vx = q[VX * 32], vy = q[VY * 32], vz = q[VZ * 32];
-        const float ms = q[PM * 32] * P.fmult;  // mass in fixed-point units
-        float cm[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) cm[k] = q[(C0 + k) * 32];
+        float4 ra, rb, rc, rd4;
+        st.load(t, ra, rb, rc, rd4);
+        const float px = ra.x, py = ra.y, pz = ra.z;
+        const float vx = ra.w, vy = rb.x, vz = rb.y;
+        // G2P needs the position and the mass of slot i, and the particle's original index moves with it
+        pv.at(PX, i) = px; pv.at(PY, i) = py; pv.at(PZ, i) = pz; pv.at(PM, i) = rb.z;
+        id_dst[i] = st.id(t);
+        const float ms = rb.z * P.fmult;  // mass in fixed-point units
+        const float cm[9] = {rb.w, rc.x, rc.y, rc.z, rc.w, rd4.x, rd4.y, rd4.z, rd4.w};
         float wx[3], wy[3], wz[3], dx[3], dy[3], dz[3];
         cell_axis(px, cp.fcx, wx, dx); cell_axis(py, cp.fcy, wy, dy); cell_axis(pz, cp.fcz, wz, dz);
 #pragma unroll
@@ -266,7 +329,9 @@ struct P2G1Body {
 
 template <int B>
 __global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? 3 : 6) k_p2g1_cell(DevParams P, TileGeom g, ParticleView pv, CellArgs a,
-                                                                                     int* __restrict__ grid)
+                                                                                     int* __restrict__ grid, const float* __restrict__ rec,
+                                                                                     const uint32_t* __restrict__ src_of,
+                                                                                     const uint32_t* __restrict__ id_src, uint32_t* __restrict__ id_dst)
 {
     using TL = Tile<B>;
     using CF = CellCfg<B>;
@@ -281,7 +346,7 @@ __global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? 3 : 6) k_p2g1_
         TL tl; tl.init(g, b);
         for (int k = threadIdx.x; k < 4 * TL::WORDS; k += CF::THREADS) reinterpret_cast<int*>(dsm)[k] = 0;
         __syncthreads();
-        P2G1Body<B> body(P, pv, tl, tile, lane, stg + warp * (2 * NPLANES * 32) + lane);
+        P2G1Body<B> body(P, pv, id_dst, tl, tile, RowStage<true>(rec, src_of, id_src, stg + warp * (2 * RowStage<true>::WORDS), lane));
         walk_chunks<B>(a, b, lane, warp, &s_bw, body);
         __syncthreads();
         for (int k = threadIdx.x; k < TL::NODES; k += CF::THREADS) {
@@ -313,20 +378,16 @@ template <int B>
 struct P2G2Body {
     using TL = Tile<B>;
     const DevParams& P;
-    const ParticleView& pv;
     const TL& tl;
     int (*tile)[TL::WORDS];
     const float* tmass;
-    int lane;
     float inv_rest;
-    float* stage;  // this lane's column of the warp's two staging buffers: stage[(buf * 13 + k) * 32]
-    int wr = 0, rd = 0;
+    RowStage<false> st;
     CellPos<B> cp;
     float gm[27], az[27];
     float2 axy[27];  // momentum x, y packed for FFMA2
-    __device__ __forceinline__ P2G2Body(const DevParams& P_, const ParticleView& pv_, const TL& tl_, int (*tile_)[TL::WORDS], const float* tmass_,
-                                        int lane_, float* stage_)
-        : P(P_), pv(pv_), tl(tl_), tile(tile_), tmass(tmass_), lane(lane_), inv_rest(1.0f / P_.rest_density), stage(stage_) {}
+    __device__ __forceinline__ P2G2Body(const DevParams& P_, const TL& tl_, int (*tile_)[TL::WORDS], const float* tmass_, const RowStage<false>& st_)
+        : P(P_), tl(tl_), tile(tile_), tmass(tmass_), inv_rest(1.0f / P_.rest_density), st(st_) {}
     __device__ __forceinline__ void begin_chunk(int L)
     {
         cp.set(tl, L);
@@ -339,29 +400,15 @@ struct P2G2Body {
 #pragma unroll
         for (int n = 0; n < 27; ++n) { axy[n] = make_float2(0.0f, 0.0f); az[n] = 0.0f; }
     }
-    __device__ __forceinline__ void fetch(uint32_t i)
+    __device__ __forceinline__ void fetch(uint32_t base, unsigned mask, int kind) { st.fetch(base, mask, kind); }
+    __device__ __forceinline__ void hint_chunk(uint32_t slot) { st.hint_chunk(slot); }
+    __device__ __forceinline__ void take() { st.take(); }
+    __device__ __forceinline__ void compute(uint32_t, uint32_t t)
     {
-        const float* q = pv.rec(i);
-        float* d = stage + wr * (13 * 32);
-        cp_async4(d + 0 * 32, q + PX * GROUP); cp_async4(d + 1 * 32, q + PY * GROUP); cp_async4(d + 2 * 32, q + PZ * GROUP);
-        cp_async4(d + 3 * 32, q + PM * GROUP);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) cp_async4(d + (4 + k) * 32, q + (C0 + k) * GROUP);
-        cp_async_commit();
-    }
-    __device__ __forceinline__ void take()
-    {
-        cp_async_wait_all();
-        rd = wr;
-        wr ^= 1;
-    }
-    __device__ __forceinline__ void compute(uint32_t)
-    {
-        const float* q = stage + rd * (13 * 32);
-        const float px = q[0 * 32], py = q[1 * 32], pz = q[2 * 32], mass = q[3 * 32];
-        float cm[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) cm[k] = q[(4 + k) * 32];
+        float4 ra, rb, rc, rd4;
+        st.load(t, ra, rb, rc, rd4);
+        const float px = ra.x, py = ra.y, pz = ra.z, mass = rb.z;
+        const float cm[9] = {rb.w, rc.x, rc.y, rc.z, rc.w, rd4.x, rd4.y, rd4.z, rd4.w};
         float wx[3], wy[3], wz[3], dx[3], dy[3], dz[3];
         cell_axis(px, cp.fcx, wx, dx); cell_axis(py, cp.fcy, wy, dy); cell_axis(pz, cp.fcz, wz, dz);
         float density = 0.0f;
@@ -430,7 +477,8 @@ struct P2G2Body {
 
 template <int B>
 __global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? 3 : 6) k_p2g2_cell(DevParams P, TileGeom g, ParticleView pv, CellArgs a,
-                                                                                     int* __restrict__ grid)
+                                                                                     int* __restrict__ grid, const float* __restrict__ rec,
+                                                                                     const uint32_t* __restrict__ src_of)
 {
     using TL = Tile<B>;
     using CF = CellCfg<B>;
@@ -452,7 +500,7 @@ __global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? 3 : 6) k_p2g2_
             tmass[idx] = ok ? (float)grid[4 * ci + 3] * inv_mult : 0.0f;
         }
         __syncthreads();
-        P2G2Body<B> body(P, pv, tl, tile, tmass, lane, stg + warp * (2 * 13 * 32) + lane);
+        P2G2Body<B> body(P, tl, tile, tmass, RowStage<false>(rec, src_of, nullptr, stg + warp * (2 * RowStage<false>::WORDS), lane));
         walk_chunks<B>(a, b, lane, warp, &s_bw, body);
         __syncthreads();
         for (int k = threadIdx.x; k < TL::NODES; k += CF::THREADS) {
@@ -503,13 +551,15 @@ struct G2PBody {
                     gxy[n] = make_float2(tv[0][idx], tv[1][idx]); gvz[n] = tv[2][idx];
                 }
     }
-    __device__ __forceinline__ void fetch(uint32_t i)
+    __device__ __forceinline__ void fetch(uint32_t base, unsigned mask, int)
     {
-        const float* q = pv.rec(i);
+        if (!((mask >> lane) & 1u)) return;
+        const float* q = pv.rec(base + __popc(mask & ((1u << lane) - 1u)));
         nx_[0] = q[PX * GROUP]; nx_[1] = q[PY * GROUP]; nx_[2] = q[PZ * GROUP]; nx_[3] = q[PM * GROUP];
     }
+    __device__ __forceinline__ void hint_chunk(uint32_t) {}
     __device__ __forceinline__ void take() { cur[0] = nx_[0]; cur[1] = nx_[1]; cur[2] = nx_[2]; cur[3] = nx_[3]; }
-    __device__ __forceinline__ void compute(uint32_t i)
+    __device__ __forceinline__ void compute(uint32_t i, uint32_t)
     {
         const float old[3] = {cur[0], cur[1], cur[2]};
         float wx[3], wy[3], wz[3], dx[3], dy[3], dz[3];
@@ -672,16 +722,17 @@ static unsigned persistent_grid(K kernel, int threads, size_t smem)
     } while (0)
 
 template <int B>
-constexpr size_t p2g1_smem() { return sizeof(int) * 4 * Tile<B>::WORDS + sizeof(float) * CellCfg<B>::NWARP * 2 * NPLANES * 32; }
+constexpr size_t p2g1_smem() { return sizeof(int) * 4 * Tile<B>::WORDS + sizeof(float) * CellCfg<B>::NWARP * 2 * RowStage<true>::WORDS; }
 template <int B>
-constexpr size_t p2g2_smem() { return sizeof(int) * 3 * Tile<B>::WORDS + sizeof(float) * Tile<B>::WORDS + sizeof(float) * CellCfg<B>::NWARP * 2 * 13 * 32; }
+constexpr size_t p2g2_smem() { return sizeof(int) * 3 * Tile<B>::WORDS + sizeof(float) * Tile<B>::WORDS + sizeof(float) * CellCfg<B>::NWARP * 2 * RowStage<false>::WORDS; }
 
 int cell_p2g1(MpmSolver* s)
 {
     int rc = check_cell_supported(s);
     if (rc) return rc;
     if (s->n == 0) return MPM_OK;
-    LAUNCH_CELL(k_p2g1_cell, p2g1_smem<8>(), p2g1_smem<4>(), reinterpret_cast<int*>(s->grid));
+    LAUNCH_CELL(k_p2g1_cell, p2g1_smem<8>(), p2g1_smem<4>(), reinterpret_cast<int*>(s->grid), s->rec, s->bin->src_of, s->orig_id, s->orig_id_alt);
+    s->g2p_inputs = true;
     return MPM_OK;
 }
 
@@ -690,7 +741,7 @@ int cell_p2g2(MpmSolver* s)
     int rc = check_cell_supported(s);
     if (rc) return rc;
     if (s->n == 0) return MPM_OK;
-    LAUNCH_CELL(k_p2g2_cell, p2g2_smem<8>(), p2g2_smem<4>(), reinterpret_cast<int*>(s->grid));
+    LAUNCH_CELL(k_p2g2_cell, p2g2_smem<8>(), p2g2_smem<4>(), reinterpret_cast<int*>(s->grid), s->rec, s->bin->src_of);
     return MPM_OK;
 }
 
@@ -710,6 +761,7 @@ int cell_g2p(MpmSolver* s)
     if (rc) return rc;
     if (s->n == 0) return MPM_OK;
     BinState* bs = s->bin;
+    if ((rc = bin_g2p_inputs(s))) return rc;
     // multi-GPU: particles that leave the slab are not counted here; the migration moves the keys of the particles it
     // relocates and adds keys + counts for the arrivals (bin_keys_range)
     const bool fuse = true;
@@ -727,7 +779,9 @@ int cell_g2p(MpmSolver* s)
     else if (extra) LAUNCH_CELL(k_g2p_cell_single_x, 0, 0, G2P_ARGS);
     else LAUNCH_CELL(k_g2p_cell_single, 0, 0, G2P_ARGS);
 #undef G2P_ARGS
-    s->in_rec = true;  // the new particle state is in the records until the next binning (or ensure_planes)
+    std::swap(s->orig_id, s->orig_id_alt);  // the records are in this step's slot order now, and so are the ids P2G_1 wrote
+    s->g2p_inputs = false;
+    s->in_rec = true;  // the particle state lives in the records (ensure_planes converts for the plane readers)
     bs->next_valid = fuse;
     s->sorted_valid = false;  // positions moved: the layout is exact for one step only
     return MPM_OK;

@@ -35,6 +35,7 @@ struct MpmSolver {
     bool grid_raw = false;      // cell path: the grid holds mass + momentum (P2G done, UpdateGrid not yet applied): G2P applies
                                 // the update while it loads its tiles, and a grid download applies it first
     bool in_rec = false;        // the particle state of slots [0, n) currently lives in `rec`, not in `part`
+    bool g2p_inputs = false;    // cell path: P2G_1 has written the position / mass planes and orig_id_alt of the current layout
     uint32_t* orig_id = nullptr;      // original (global) index of the particle in each slot
     uint32_t* orig_id_alt = nullptr;
     void* grid = nullptr;  // ncells_local * 16 B
