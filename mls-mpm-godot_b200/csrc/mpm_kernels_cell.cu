@@ -105,6 +105,15 @@ __device__ __forceinline__ void cp_async16(float* smem, const float* gmem)
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem));
 }
+// the same, predicated (no branch around it: a row is copied by straight-line code)
+__device__ __forceinline__ void cp_async16_if(unsigned sa, const void* gmem, bool on)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}" ::"r"(sa), "l"(gmem), "r"((int)on));
+}
+__device__ __forceinline__ void cp_async4_if(unsigned sa, const void* gmem, bool on)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.ca.shared.global [%0], [%1], 4;\n\t}" ::"r"(sa), "l"(gmem), "r"((int)on));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -199,30 +208,33 @@ struct CellPos {  // the cell (id L inside the block) this lane owns in the curr
 template <bool IDS>  // IDS: also bring the particles' original indices along (P2G_1 writes them out in slot order)
 struct RowStage {
     static constexpr int WORDS = 32 * 16 + (IDS ? 32 : 0);  // one buffer, in 4-byte words
-    const float* rec;
+    const float4* rec4;
     const uint32_t* src_of;
     const uint32_t* id_src;
-    float* buf;  // the warp's two buffers
+    float* buf;   // the warp's two buffers
+    unsigned sa;  // shared-memory address of the 16 bytes this lane fills for record q = lane / 4 of buffer 0
     int lane;
     uint32_t ix_row = 0, ix_chunk = 0;
     int wr = 0, rd = 0;
     __device__ __forceinline__ RowStage(const float* rec_, const uint32_t* src_of_, const uint32_t* id_src_, float* buf_, int lane_)
-        : rec(rec_), src_of(src_of_), id_src(id_src_), buf(buf_), lane(lane_) {}
+        : rec4(reinterpret_cast<const float4*>(rec_)), src_of(src_of_), id_src(id_src_), buf(buf_), lane(lane_)
+    {
+        const int q = lane >> 2, j = lane & 3;
+        sa = (unsigned)__cvta_generic_to_shared(buf + q * 16 + ((j ^ (q >> 1)) & 3) * 4);
+    }
     __device__ __forceinline__ void hint_chunk(uint32_t slot) { ix_chunk = src_of[slot + lane]; }
     __device__ __forceinline__ void fetch(uint32_t base, unsigned mask, int kind)
     {
-        const int cnt = __popc(mask);
+        const uint32_t cnt = __popc(mask);
         const uint32_t ix = (kind == ROW_NEXT) ? ix_row : (kind == ROW_HINTED) ? ix_chunk : src_of[base + lane];
-        float* d = buf + wr * WORDS;
-        const int q = lane >> 2, j = lane & 3;
+        const unsigned dst = sa + wr * (WORDS * 4);
+        const uint32_t q = lane >> 2, j = lane & 3;
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            if (8 * it >= cnt) break;
-            const int t = 8 * it + q;
-            const uint32_t src = __shfl_sync(0xffffffffu, ix, t);
-            if (t < cnt) cp_async16(d + t * 16 + ((j ^ (t >> 1)) & 3) * 4, rec + (size_t)src * 16 + j * 4);
+        for (int it = 0; it < 4; ++it) {  // record t = 8 it + q; its swizzle (t >> 1) & 3 does not depend on it
+            const uint32_t src = __shfl_sync(0xffffffffu, ix, 8 * it + q);
+            cp_async16_if(dst + it * 512, rec4 + (src * 4u + j), 8 * it + q < cnt);
         }
-        if (IDS && lane < cnt) cp_async4(d + 32 * 16 + lane, reinterpret_cast<const float*>(id_src + ix));
+        if (IDS) cp_async4_if((unsigned)__cvta_generic_to_shared(buf + wr * WORDS + 32 * 16 + lane), id_src + ix, (uint32_t)lane < cnt);
         cp_async_commit();
         ix_row = src_of[base + cnt + lane];  // (src_of is padded: reading past the last particle is harmless)
     }
