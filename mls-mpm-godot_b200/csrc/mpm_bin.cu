@@ -226,12 +226,15 @@ __global__ void __launch_bounds__(1 << CELL_BITS) k_block_order(const uint32_t* 
 template <int CELL_BITS>
 __global__ void __launch_bounds__(256) k_place(const uint32_t* __restrict__ keys, int64_t n, const uint2* __restrict__ cellmeta,
                                                const uint32_t* __restrict__ cnts, const uint32_t* __restrict__ pstart,
-                                               const uint16_t* __restrict__ stab, uint32_t* __restrict__ fill, uint32_t* __restrict__ src_of)
+                                               const uint16_t* __restrict__ stab, uint32_t* __restrict__ fill, uint32_t* __restrict__ src_of,
+                                               const uint32_t* __restrict__ id_src, uint32_t* __restrict__ id_dst)
 {
     constexpr uint32_t NV = 2u << CELL_BITS;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t key = keys[i];
+    const uint32_t id = id_src[i];  // the particle's original index moves to its new slot here (coalesced read, one more
+                                    // scattered 4-byte store) rather than as a scattered read in P2G_1
     const uint32_t rc = atomicAdd(&fill[key], 1u);  // rank inside the (real) cell
     const uint2 cm = cellmeta[key];  // x: position of the first full virtual cell | position of the remainder << 16; y: full ones
     const uint32_t g = cm.y;
@@ -247,6 +250,7 @@ __global__ void __launch_bounds__(256) k_place(const uint32_t* __restrict__ keys
         const uint32_t below = r ? row[r] : 0u;
         const uint32_t ps = *reinterpret_cast<const uint32_t*>(row + 14);
         src_of[ps + below + lane] = (uint32_t)i;
+        id_dst[ps + below + lane] = id;
         return;
     }
     const uint4* c4 = reinterpret_cast<const uint4*>(cnts + v0 + chunk * 32u);
@@ -262,7 +266,9 @@ __global__ void __launch_bounds__(256) k_place(const uint32_t* __restrict__ keys
             before += ((uint32_t)(4 * k + j) < lane && c[j] > r) ? 1u : 0u;
         }
     }
-    src_of[pstart[gchunk] + below + before] = (uint32_t)i;
+    const uint32_t dest = pstart[gchunk] + below + before;
+    src_of[dest] = (uint32_t)i;
+    id_dst[dest] = id;
 }
 
 // grouped planes -> 64-byte records (a freshly uploaded or edited particle set enters the cell path)
@@ -276,17 +282,15 @@ __global__ void __launch_bounds__(256) k_planes_to_rec(ParticleView pv, float4* 
         rec[4 * i + k] = make_float4(q[(4 * k + 0) * GROUP], q[(4 * k + 1) * GROUP], q[(4 * k + 2) * GROUP], q[(4 * k + 3) * GROUP]);
 }
 
-// What P2G_1 leaves for G2P -- position and mass planes and the original indices, in slot order -- for a G2P phase that
-// is run without a P2G_1 since the last binning (mpm_run_phase).
-__global__ void __launch_bounds__(256) k_gather_g2p_inputs(const float4* __restrict__ rec, ParticleView dst, const uint32_t* __restrict__ src_of,
-                                                           const uint32_t* __restrict__ id_src, uint32_t* __restrict__ id_dst, int64_t n)
+// What P2G_1 leaves for G2P -- position and mass planes in slot order -- for a G2P phase that is run without a P2G_1
+// since the last binning (mpm_run_phase).
+__global__ void __launch_bounds__(256) k_gather_g2p_inputs(const float4* __restrict__ rec, ParticleView dst, const uint32_t* __restrict__ src_of, int64_t n)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t j = src_of[i];
     const float4 a = rec[4 * (size_t)j], b = rec[4 * (size_t)j + 1];
     dst.at(PX, i) = a.x; dst.at(PY, i) = a.y; dst.at(PZ, i) = a.z; dst.at(PM, i) = b.z;
-    id_dst[i] = id_src[j];
 }
 
 // ---------------------------------------------------------------- host side
@@ -386,11 +390,12 @@ int bin_particles(MpmSolver* s)
     }
     s->launches += 3;
     if (n > 0) {
-        if (st->cell_bits == 9) k_place<9><<<nb, 256, 0, s->stream>>>(st->keys, n, st->cellmeta, st->cnts, st->pstart, st->stab, st->fill, st->src_of);
-        else k_place<6><<<nb, 256, 0, s->stream>>>(st->keys, n, st->cellmeta, st->cnts, st->pstart, st->stab, st->fill, st->src_of);
+        if (st->cell_bits == 9) k_place<9><<<nb, 256, 0, s->stream>>>(st->keys, n, st->cellmeta, st->cnts, st->pstart, st->stab, st->fill, st->src_of, s->orig_id, s->orig_id_alt);
+        else k_place<6><<<nb, 256, 0, s->stream>>>(st->keys, n, st->cellmeta, st->cnts, st->pstart, st->stab, st->fill, st->src_of, s->orig_id, s->orig_id_alt);
         s->launches += 1;
     }
-    s->g2p_inputs = false;  // position / mass planes and slot-order ids of this layout: written by P2G_1
+    s->g2p_inputs = false;  // position / mass planes of this layout: written by P2G_1 (orig_id_alt holds the slot-order
+                            // ids already; the two id arrays are swapped when G2P has rewritten the records in slot order)
     st->cur = nxt;
     st->next_valid = false;
     // the other count buffer receives the next step's counts from G2P: clear it now
@@ -422,8 +427,7 @@ int bin_g2p_inputs(MpmSolver* s)
 {
     if (s->g2p_inputs) return MPM_OK;
     if (s->n > 0) {
-        k_gather_g2p_inputs<<<(unsigned)((s->n + 255) / 256), 256, 0, s->stream>>>(reinterpret_cast<const float4*>(s->rec), s->view(), s->bin->src_of,
-                                                                                s->orig_id, s->orig_id_alt, s->n);
+        k_gather_g2p_inputs<<<(unsigned)((s->n + 255) / 256), 256, 0, s->stream>>>(reinterpret_cast<const float4*>(s->rec), s->view(), s->bin->src_of, s->n);
         s->launches += 1;
     }
     s->g2p_inputs = true;

@@ -79,8 +79,8 @@ __device__ __forceinline__ void cell_axis(float p, float fc, float w[3], float d
 // an SM, and a loop that loads a particle and then computes on it spends half its time in long-scoreboard stalls.  So the
 // walk is pipelined: while the particle of rank r is being processed, the one of rank r+1 (or rank 0 of the warp's next
 // chunk) is already in flight -- in registers where that is cheap (G2P: position + mass), as a cp.async into a per-warp
-// shared-memory staging buffer otherwise (P2G: 16 / 13 fields; prefetch.global.L1 was tried first and left the L1 hit
-// rate at 5 %).
+// shared-memory staging buffer otherwise (P2G: the whole 64-byte record; prefetch.global.L1 was tried first and left the
+// L1 hit rate at 5 %).
 //
 // Body interface (all calls warp-uniform except compute):
 //                  begin_chunk(cell)      per-cell set-up (stencil registers / accumulators)
@@ -93,13 +93,9 @@ __device__ __forceinline__ void cell_axis(float p, float fc, float w[3], float d
 //                  end_chunk(has)         flush per-cell results
 //                  finish()               after the warp's last chunk of the block
 enum { ROW_COLD = 0, ROW_NEXT = 1, ROW_HINTED = 2 };
-// 4-byte asynchronous global -> shared copy (LDGSTS): no register is held while the load is in flight
-__device__ __forceinline__ void cp_async4(float* smem, const float* gmem)
-{
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem));
-}
-// 16-byte copy, L2 only (the records are read once per kernel)
+
+// asynchronous 16-byte global -> shared copy (LDGSTS: no register is held while the load is in flight), L2 only (the
+// records are read once per kernel)
 __device__ __forceinline__ void cp_async16(float* smem, const float* gmem)
 {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -109,10 +105,6 @@ __device__ __forceinline__ void cp_async16(float* smem, const float* gmem)
 __device__ __forceinline__ void cp_async16_if(unsigned sa, const void* gmem, bool on)
 {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}" ::"r"(sa), "l"(gmem), "r"((int)on));
-}
-__device__ __forceinline__ void cp_async4_if(unsigned sa, const void* gmem, bool on)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.ca.shared.global [%0], [%1], 4;\n\t}" ::"r"(sa), "l"(gmem), "r"((int)on));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -205,19 +197,17 @@ struct CellPos {  // the cell (id L inside the block) this lane owns in the curr
 // consecutive records cover all 8 bank quads).  The record indices of a row come from one coalesced load that is issued
 // a row ahead (ix_row) or, for the first row of the warp's next chunk, when that chunk is announced (ix_chunk), and are
 // passed around with SHFL; only the first row after a block change pays the load's latency.
-template <bool IDS>  // IDS: also bring the particles' original indices along (P2G_1 writes them out in slot order)
 struct RowStage {
-    static constexpr int WORDS = 32 * 16 + (IDS ? 32 : 0);  // one buffer, in 4-byte words
+    static constexpr int WORDS = 32 * 16;  // one buffer, in 4-byte words
     const float4* rec4;
     const uint32_t* src_of;
-    const uint32_t* id_src;
     float* buf;   // the warp's two buffers
     unsigned sa;  // shared-memory address of the 16 bytes this lane fills for record q = lane / 4 of buffer 0
     int lane;
     uint32_t ix_row = 0, ix_chunk = 0;
     int wr = 0, rd = 0;
-    __device__ __forceinline__ RowStage(const float* rec_, const uint32_t* src_of_, const uint32_t* id_src_, float* buf_, int lane_)
-        : rec4(reinterpret_cast<const float4*>(rec_)), src_of(src_of_), id_src(id_src_), buf(buf_), lane(lane_)
+    __device__ __forceinline__ RowStage(const float* rec_, const uint32_t* src_of_, float* buf_, int lane_)
+        : rec4(reinterpret_cast<const float4*>(rec_)), src_of(src_of_), buf(buf_), lane(lane_)
     {
         const int q = lane >> 2, j = lane & 3;
         sa = (unsigned)__cvta_generic_to_shared(buf + q * 16 + ((j ^ (q >> 1)) & 3) * 4);
@@ -234,7 +224,6 @@ struct RowStage {
             const uint32_t src = __shfl_sync(0xffffffffu, ix, 8 * it + q);
             cp_async16_if(dst + it * 512, rec4 + (src * 4u + j), 8 * it + q < cnt);
         }
-        if (IDS) cp_async4_if((unsigned)__cvta_generic_to_shared(buf + wr * WORDS + 32 * 16 + lane), id_src + ix, (uint32_t)lane < cnt);
         cp_async_commit();
         ix_row = src_of[base + cnt + lane];  // (src_of is padded: reading past the last particle is harmless)
     }
@@ -252,7 +241,6 @@ struct RowStage {
         const uint32_t s = (t >> 1) & 3u;
         a = r[s]; b = r[1u ^ s]; c = r[2u ^ s]; d = r[3u ^ s];
     }
-    __device__ __forceinline__ uint32_t id(uint32_t t) const { return __float_as_uint(buf[rd * WORDS + 32 * 16 + t]); }
 };
 
 // ---------------------------------------------------------------- P2G_1
@@ -261,15 +249,13 @@ struct P2G1Body {
     using TL = Tile<B>;
     const DevParams& P;
     const ParticleView& pv;  // out: position and mass planes in slot order (what G2P reads)
-    uint32_t* id_dst;        // out: original indices in slot order
     const TL& tl;
     int (*tile)[TL::WORDS];
-    RowStage<true> st;
+    RowStage st;
     CellPos<B> cp;
     float2 axy[27], azm[27];  // accumulators packed for FFMA2: (momentum x, momentum y) and (momentum z, mass)
-    __device__ __forceinline__ P2G1Body(const DevParams& P_, const ParticleView& pv_, uint32_t* id_dst_, const TL& tl_, int (*tile_)[TL::WORDS],
-                                        const RowStage<true>& st_)
-        : P(P_), pv(pv_), id_dst(id_dst_), tl(tl_), tile(tile_), st(st_) {}
+    __device__ __forceinline__ P2G1Body(const DevParams& P_, const ParticleView& pv_, const TL& tl_, int (*tile_)[TL::WORDS], const RowStage& st_)
+        : P(P_), pv(pv_), tl(tl_), tile(tile_), st(st_) {}
     __device__ __forceinline__ void begin_chunk(int L)
     {
         cp.set(tl, L);
@@ -285,9 +271,8 @@ struct P2G1Body {
         st.load(t, ra, rb, rc, rd4);
         const float px = ra.x, py = ra.y, pz = ra.z;
         const float vx = ra.w, vy = rb.x, vz = rb.y;
-        // G2P needs the position and the mass of slot i, and the particle's original index moves with it
+        // G2P needs the position and the mass of slot i
         pv.at(PX, i) = px; pv.at(PY, i) = py; pv.at(PZ, i) = pz; pv.at(PM, i) = rb.z;
-        id_dst[i] = st.id(t);
         const float ms = rb.z * P.fmult;  // mass in fixed-point units
         const float cm[9] = {rb.w, rc.x, rc.y, rc.z, rc.w, rd4.x, rd4.y, rd4.z, rd4.w};
         float wx[3], wy[3], wz[3], dx[3], dy[3], dz[3];
@@ -342,8 +327,7 @@ struct P2G1Body {
 template <int B>
 __global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? 3 : 6) k_p2g1_cell(DevParams P, TileGeom g, ParticleView pv, CellArgs a,
                                                                                      int* __restrict__ grid, const float* __restrict__ rec,
-                                                                                     const uint32_t* __restrict__ src_of,
-                                                                                     const uint32_t* __restrict__ id_src, uint32_t* __restrict__ id_dst)
+                                                                                     const uint32_t* __restrict__ src_of)
 {
     using TL = Tile<B>;
     using CF = CellCfg<B>;
@@ -358,7 +342,7 @@ __global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? 3 : 6) k_p2g1_
         TL tl; tl.init(g, b);
         for (int k = threadIdx.x; k < 4 * TL::WORDS; k += CF::THREADS) reinterpret_cast<int*>(dsm)[k] = 0;
         __syncthreads();
-        P2G1Body<B> body(P, pv, id_dst, tl, tile, RowStage<true>(rec, src_of, id_src, stg + warp * (2 * RowStage<true>::WORDS), lane));
+        P2G1Body<B> body(P, pv, tl, tile, RowStage(rec, src_of, stg + warp * (2 * RowStage::WORDS), lane));
         walk_chunks<B>(a, b, lane, warp, &s_bw, body);
         __syncthreads();
         for (int k = threadIdx.x; k < TL::NODES; k += CF::THREADS) {
@@ -394,11 +378,11 @@ struct P2G2Body {
     int (*tile)[TL::WORDS];
     const float* tmass;
     float inv_rest;
-    RowStage<false> st;
+    RowStage st;
     CellPos<B> cp;
     float gm[27], az[27];
     float2 axy[27];  // momentum x, y packed for FFMA2
-    __device__ __forceinline__ P2G2Body(const DevParams& P_, const TL& tl_, int (*tile_)[TL::WORDS], const float* tmass_, const RowStage<false>& st_)
+    __device__ __forceinline__ P2G2Body(const DevParams& P_, const TL& tl_, int (*tile_)[TL::WORDS], const float* tmass_, const RowStage& st_)
         : P(P_), tl(tl_), tile(tile_), tmass(tmass_), inv_rest(1.0f / P_.rest_density), st(st_) {}
     __device__ __forceinline__ void begin_chunk(int L)
     {
@@ -512,7 +496,7 @@ __global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? 3 : 6) k_p2g2_
             tmass[idx] = ok ? (float)grid[4 * ci + 3] * inv_mult : 0.0f;
         }
         __syncthreads();
-        P2G2Body<B> body(P, tl, tile, tmass, RowStage<false>(rec, src_of, nullptr, stg + warp * (2 * RowStage<false>::WORDS), lane));
+        P2G2Body<B> body(P, tl, tile, tmass, RowStage(rec, src_of, stg + warp * (2 * RowStage::WORDS), lane));
         walk_chunks<B>(a, b, lane, warp, &s_bw, body);
         __syncthreads();
         for (int k = threadIdx.x; k < TL::NODES; k += CF::THREADS) {
@@ -734,16 +718,16 @@ static unsigned persistent_grid(K kernel, int threads, size_t smem)
     } while (0)
 
 template <int B>
-constexpr size_t p2g1_smem() { return sizeof(int) * 4 * Tile<B>::WORDS + sizeof(float) * CellCfg<B>::NWARP * 2 * RowStage<true>::WORDS; }
+constexpr size_t p2g1_smem() { return sizeof(int) * 4 * Tile<B>::WORDS + sizeof(float) * CellCfg<B>::NWARP * 2 * RowStage::WORDS; }
 template <int B>
-constexpr size_t p2g2_smem() { return sizeof(int) * 3 * Tile<B>::WORDS + sizeof(float) * Tile<B>::WORDS + sizeof(float) * CellCfg<B>::NWARP * 2 * RowStage<false>::WORDS; }
+constexpr size_t p2g2_smem() { return sizeof(int) * 3 * Tile<B>::WORDS + sizeof(float) * Tile<B>::WORDS + sizeof(float) * CellCfg<B>::NWARP * 2 * RowStage::WORDS; }
 
 int cell_p2g1(MpmSolver* s)
 {
     int rc = check_cell_supported(s);
     if (rc) return rc;
     if (s->n == 0) return MPM_OK;
-    LAUNCH_CELL(k_p2g1_cell, p2g1_smem<8>(), p2g1_smem<4>(), reinterpret_cast<int*>(s->grid), s->rec, s->bin->src_of, s->orig_id, s->orig_id_alt);
+    LAUNCH_CELL(k_p2g1_cell, p2g1_smem<8>(), p2g1_smem<4>(), reinterpret_cast<int*>(s->grid), s->rec, s->bin->src_of);
     s->g2p_inputs = true;
     return MPM_OK;
 }

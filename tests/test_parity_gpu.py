@@ -379,6 +379,40 @@ def test_cell_binning_is_a_valid_cell_sort(lib):
         assert abs(total - want) <= 27.0 * n + 1e-7 * want
 
 
+def test_cell_path_phases_with_downloads_in_between(lib):
+    """On the cell path the particle state lives in 64-byte records that the P2G kernels read through the binning's
+    index, and P2G_1 leaves position / mass planes + slot-order ids for G2P.  Running the phases one by one with
+    downloads in between (each download converts records -> planes and invalidates the binning, so every particle phase
+    re-bins; G2P then runs without a P2G_1 since its binning and must rebuild its inputs) has to give the same step as
+    mpm_step, up to the order of the fp32 per-cell sums, and must keep the download order."""
+    op = orc.variant("3d_gpu", (64, 64, 64))
+    op.interaction = 0
+    n = 150000
+    pos, vel, Cm, mass = helpers.random_cloud(op, n, seed=91)
+    res = []
+    for piecewise in (False, True):
+        with make_solver(op, n, kernel_path=3, math_mode=1) as s:
+            s.upload(pos, vel, Cm, mass)
+            s.step(1)                                  # records become the live state
+            if not piecewise:
+                s.step(1)
+            else:
+                s.run_phase(5); s.run_phase(0); s.run_phase(1)
+                mid = s.download()                      # records -> planes; the binning is void again
+                s.run_phase(2)
+                s.download_grid()
+                s.run_phase(3)
+                mid2 = s.download()
+                for a, b in zip(mid, mid2):
+                    helpers.assert_bit_equal(a, b, "particles must not change before G2P")
+                s.run_phase(4)                          # fresh binning, no P2G_1 since: G2P rebuilds its inputs
+            res.append(s.download())
+            helpers.assert_bit_equal(res[-1][3], mass, "mass / download order")
+    for what, a, b in zip(("pos", "vel", "C"), res[0], res[1]):
+        e = helpers.rel_err(a, b)
+        assert e < 1e-4, f"{what}: piecewise vs mpm_step rel err {e:.3g}"  # (rounding order of the per-cell fp32 sums)
+
+
 def test_cell_path_full_size_block_drop(lib):
     """BASELINE config 3 (128^3, 4 096 000 particles) on the cell path vs the strict reference-shaped path after 3
     steps: FAST tolerance per particle (no chaos yet), exact particle count and order."""
