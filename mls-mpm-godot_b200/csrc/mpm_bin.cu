@@ -3,9 +3,9 @@
 // The reference never reorders particles (particle i keeps index i); binning is new.  The cell kernels
 // (mpm_kernels_cell.cu) give every grid cell to one thread, which keeps the cell's 27-node stencil in registers
 // across all particles of the cell.  That needs the particles of a cell to be found without searching, and the
-// loads of a warp (32 consecutive cells = one "chunk") to be coalesced.  Layout of the particle planes:
+// rows a warp works on (32 consecutive cells = one "chunk") to be contiguous.  Slot order of a step:
 //
-//     sorted by (block, chunk, rank r inside the cell, cell inside the chunk)
+//     (block, chunk, rank r inside the cell, cell inside the chunk)
 //
 // where the cells of a block are first ORDERED BY PARTICLE COUNT, descending, and cut into chunks of 32: the 32
 // lanes of a warp then carry nearly equal work -- and cells with more than 32 particles are first split into "virtual
@@ -19,8 +19,10 @@
 // Per step:  counts of the NEW cells are accumulated by G2P itself (fire-and-forget RED on cnt[next], key stored
 // per particle), so binning = clear cursor -> block totals -> scan of the block totals (also the ordered list of
 // non-empty blocks) -> per-block cell ordering + chunk starts -> k_place (rank by atomic cursor, destination
-// slot from the chunk's counts) -> k_gather (16 fields + id, coalesced writes).  The rank comes from an atomic, so the order of the particles INSIDE a cell is not
-// reproducible run to run; the fixed-point grid sums do not depend on it (int adds commute) and the
+// slot from the chunk's counts; stores src_of[slot] = where the particle's record is, and moves its original index).
+// No particle data moves here: the 64-byte records stay where G2P wrote them and the P2G kernels read them through
+// src_of (mpm_kernels_cell.cu, RowStage).  The rank comes from an atomic, so the order of the particles INSIDE a cell
+// is not reproducible run to run; the fixed-point grid sums do not depend on it (int adds commute) and the
 // MPM_MATH_FAST float accumulation is covered by its stated tolerance.
 #include "mpm_bin.h"
 

@@ -4,13 +4,14 @@
 // instruction streams that no amount of bandwidth shrinks: P2G_1 issues 108 shared-memory atomics and 108
 // float->int conversions per particle (the conversion runs on the quarter-rate XU pipe, 61-69 % busy), G2P 81
 // shared-memory loads per particle.  Here one thread owns one grid CELL and walks that cell's particles
-// (cell-binned planes, mpm_bin.cu), keeping the cell's 27-node stencil in registers:
+// (cell-binned slots, mpm_bin.cu), keeping the cell's 27-node stencil in registers:
 //   P2G_1 / P2G_2 : 108 / 81 fp32 accumulators per thread; fixed-point conversion and the shared-memory ATOMS
 //                   happen once per cell instead of once per particle.
 //   G2P           : the 27 node velocities (81 floats) are loaded from the shared-memory tile once per cell; results go
-//                   out as 64-byte records (two full sectors) for the next binning to gather.
-// A warp = 32 consecutive cells of a block (a "chunk"); at rank r it reads the rank-r particles of its cells
-// from consecutive slots (one full 128-B line per plane when all cells are occupied).  CTAs are persistent and
+//                   out as 64-byte records (two full sectors), which the next step's P2G kernels read in place.
+// A warp = 32 cells of a block (a "chunk"); at rank r it works on the rank-r particles of its cells, which sit in
+// consecutive slots (a "row").  P2G fetches a row's records through the binning's index (RowStage below), G2P reads
+// position + mass planes that P2G_1 wrote in slot order.  CTAs are persistent and
 // pull non-empty grid blocks from a list with an atomic counter.  G2P also emits each particle's next cell key
 // and counts it (RED), so the next step's binning needs no separate key pass.
 //
@@ -608,7 +609,7 @@ struct G2PBody {
                 else if (cx >= mg.xr1) { np[0] = (float)mg.xr1 - 0.5f; atomicAdd(mg.cnt + 8, 1u); }
             }
         }
-        // one 64-byte record per particle (field order of the planes): the next binning gathers it from here
+        // one 64-byte record per particle (field order of the planes): the next step's P2G kernels read it from here
         float4* q = rec + 4 * (size_t)i;
         q[0] = make_float4(np[0], np[1], np[2], v[0]);
         q[1] = make_float4(v[1], v[2], cur[3], cm[0]);

@@ -27,10 +27,10 @@ struct MpmSolver {
     int64_t n = 0;      // particles currently held (local)
     float* part = nullptr;      // NPLANES * pitch floats
     float* part_alt = nullptr;  // reorder target (tiled path)
-    // Cell path: G2P writes its results as 64-byte records (the 16 fields of a slot, contiguous) instead of back into
-    // the grouped planes: the next binning gathers every particle from an arbitrary source slot, and a record is two
-    // full 32-B sectors wherever it sits, while the 16 fields of a grouped slot are 16 different sectors (measured on
-    // the evolved C4 dam-break: 25.8 GB of L2 traffic for a 4.4 GB gather).
+    // Cell path: the particle state lives in 64-byte records (the 16 fields of a slot, contiguous).  G2P writes them in
+    // the slot order of its step; the next binning only computes src_of[new slot] = old slot, and the P2G kernels read the
+    // records through it: a record is two full 32-B sectors wherever it sits, while the 16 fields of a grouped slot are
+    // 16 different sectors (measured on the evolved C4 dam-break: 25.8 GB of L2 traffic for a 4.4 GB gather from planes).
     float* rec = nullptr;       // [pitch] x 16 floats
     bool grid_raw = false;      // cell path: the grid holds mass + momentum (P2G done, UpdateGrid not yet applied): G2P applies
                                 // the update while it loads its tiles, and a grid download applies it first
