@@ -89,7 +89,9 @@ __device__ __forceinline__ void cell_axis(float p, float fc, float w[3], float d
 //                                         order.  k says how the row was announced: ROW_NEXT = it follows the row fetched last,
 //                                         ROW_HINTED = it starts at the slot given to hint_chunk, ROW_COLD = neither
 //                  hint_chunk(slot)       the warp's next chunk will start at `slot`
-//                  take()                 the row fetched last becomes the current one
+//                  take(pending)          the oldest row not yet taken becomes the current one; `pending` (0 or 1) rows were
+//                                         requested after it and may stay in flight
+//                  FETCH_FIRST            whether the walk may request the next row before taking the current one
 //                  compute(i, t)          process this lane's particle of the current row (slot i = row base + t)
 //                  end_chunk(has)         flush per-cell results
 //                  finish()               after the warp's last chunk of the block
@@ -109,6 +111,7 @@ __device__ __forceinline__ void cp_async16_if(unsigned sa, const void* gmem, boo
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 // Pile-ups (cells with thousands of particles against a wall or in a corner of the evolved dam-break) would leave one
 // lane walking for ages while 31 idle; the binning therefore splits any cell with more than 32 particles into several
@@ -152,7 +155,10 @@ __device__ __forceinline__ void walk_chunks(const CellArgs& a, int b, int lane, 
             const uint32_t i = slot0 + __popc(m & lt);
             const bool on1 = r + 1 < c;
             const unsigned m1 = __ballot_sync(0xffffffffu, on1);
-            body.take();
+            // A body that stages rows in shared memory may be asked for the next row BEFORE the current one is waited
+            // for (two rows in flight while the warp waits); one that stages in registers takes the current row first.
+            if (!Body::FETCH_FIRST) body.take(0);
+            bool fetched = true;
             if (m1) {
                 body.fetch(slot0 + __popc(m), m1, ROW_NEXT);
             } else {
@@ -160,9 +166,10 @@ __device__ __forceinline__ void walk_chunks(const CellArgs& a, int b, int lane, 
                 if (mn) {
                     if (r > 0) body.fetch(st_nx, mn, ROW_HINTED);
                     else body.fetch(st_nx, mn, ROW_COLD);  // single-row chunk: no hint was given yet
-                }
+                } else fetched = false;
                 have = true;
             }
+            if (Body::FETCH_FIRST) body.take(fetched ? 1 : 0);
             if (on) body.compute(i, (uint32_t)__popc(m & lt));
             if (r == 0) body.hint_chunk(st_nx);  // (here, not where the chunk is claimed: st_nx has arrived by now)
             slot0 += __popc(m);
@@ -226,14 +233,14 @@ struct RowStage {
             cp_async16_if(dst + it * 512, rec4 + (src * 4u + j), 8 * it + q < cnt);
         }
         cp_async_commit();
+        wr ^= 1;
         ix_row = src_of[base + cnt + lane];  // (src_of is padded: reading past the last particle is harmless)
     }
-    __device__ __forceinline__ void take()
+    __device__ __forceinline__ void take(int pending)
     {
-        cp_async_wait_all();
+        if (pending) cp_async_wait_but_one(); else cp_async_wait_all();
         __syncwarp();  // the pieces of a record were copied by four different lanes
-        rd = wr;
-        wr ^= 1;
+        rd = pending ? wr : wr ^ 1;  // (wr = where the next request goes = the older of two outstanding rows)
     }
     // record t of the current row: (px, py, pz, vx) (vy, vz, m, c0) (c1..c4) (c5..c8)
     __device__ __forceinline__ void load(uint32_t t, float4& a, float4& b, float4& c, float4& d) const
@@ -265,7 +272,8 @@ struct P2G1Body {
     }
     __device__ __forceinline__ void fetch(uint32_t base, unsigned mask, int kind) { st.fetch(base, mask, kind); }
     __device__ __forceinline__ void hint_chunk(uint32_t slot) { st.hint_chunk(slot); }
-    __device__ __forceinline__ void take() { st.take(); }
+    static constexpr bool FETCH_FIRST = true;
+    __device__ __forceinline__ void take(int pending) { st.take(pending); }
     __device__ __forceinline__ void compute(uint32_t i, uint32_t t)
     {
         float4 ra, rb, rc, rd4;
@@ -399,7 +407,8 @@ struct P2G2Body {
     }
     __device__ __forceinline__ void fetch(uint32_t base, unsigned mask, int kind) { st.fetch(base, mask, kind); }
     __device__ __forceinline__ void hint_chunk(uint32_t slot) { st.hint_chunk(slot); }
-    __device__ __forceinline__ void take() { st.take(); }
+    static constexpr bool FETCH_FIRST = true;
+    __device__ __forceinline__ void take(int pending) { st.take(pending); }
     __device__ __forceinline__ void compute(uint32_t, uint32_t t)
     {
         float4 ra, rb, rc, rd4;
@@ -555,12 +564,16 @@ struct G2PBody {
         nx_[0] = q[PX * GROUP]; nx_[1] = q[PY * GROUP]; nx_[2] = q[PZ * GROUP]; nx_[3] = q[PM * GROUP];
     }
     __device__ __forceinline__ void hint_chunk(uint32_t) {}
-    __device__ __forceinline__ void take() { cur[0] = nx_[0]; cur[1] = nx_[1]; cur[2] = nx_[2]; cur[3] = nx_[3]; }
+    static constexpr bool FETCH_FIRST = false;  // one register set: the current row is taken before the next is requested
+    __device__ __forceinline__ void take(int) { cur[0] = nx_[0]; cur[1] = nx_[1]; cur[2] = nx_[2]; cur[3] = nx_[3]; }
     __device__ __forceinline__ void compute(uint32_t i, uint32_t)
     {
         const float old[3] = {cur[0], cur[1], cur[2]};
         float wx[3], wy[3], wz[3], dx[3], dy[3], dz[3];
-        cell_axis(old[0], cp.fcx, wx, dx); cell_axis(old[1], cp.fcy, wy, dy); cell_axis(old[2], cp.fcz, wz, dz);
+        // The particle sits in the cell its thread owns (that is what the binning key says), so the cell coordinate is
+        // trunc(p): taking it from the position frees three registers here (G2P: 20 -> 4 bytes of spills, -1 %; in the
+        // P2G kernels the same change was slower, they keep the per-thread floats).
+        cell_axis(old[0], truncf(old[0]), wx, dx); cell_axis(old[1], truncf(old[1]), wy, dy); cell_axis(old[2], truncf(old[2]), wz, dz);
         // Sum factorisation (z, then y, then x) with the x and y components packed: fma.rn.f32x2 (FFMA2, new on sm_100)
         // does two FMAs per issue slot, and this loop is issue-bound (ncu: 59 % issue-active at 3 warps per scheduler).
         const float wdz[3] = {wz[0] * dz[0], wz[1] * dz[1], wz[2] * dz[2]};
