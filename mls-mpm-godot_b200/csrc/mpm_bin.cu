@@ -316,6 +316,8 @@ int bin_create(MpmSolver* s)
     st->nbz = (s->dp.Rz + st->B - 1) / st->B;
     st->nblocks = (int64_t)st->nbx * st->nby * st->nbz;
     if (ilog2_ceil64(st->nblocks) + st->cell_bits > 31) { s->err = "grid too large for 32-bit cell keys"; return MPM_ERR_INVALID; }
+    // (the P2G kernels index 16-byte pieces of the records with 32 bits: record * 4 + piece)
+    if (s->pitch >= ((int64_t)1 << 30)) { s->err = "MPM_PATH_CELL holds at most 2^30 particles per GPU"; return MPM_ERR_INVALID; }
     st->nslots = st->nblocks << st->cell_bits;
     for (int k = 0; k < 2; ++k) {
         CKB(cudaMalloc(&st->cnt[k], sizeof(uint32_t) * (st->nslots + 32)));

@@ -35,7 +35,7 @@ struct BinState {
 int bin_create(MpmSolver* s);
 void bin_destroy(MpmSolver* s);
 int bin_particles(MpmSolver* s);
-int bin_g2p_inputs(MpmSolver* s);  // position / mass planes + slot-order ids, when no P2G_1 ran since the binning
+int bin_g2p_inputs(MpmSolver* s);  // position / mass planes in slot order, when no P2G_1 ran since the binning
 
 // cell kernels (mpm_kernels_cell.cu)
 int cell_p2g1(MpmSolver* s);

@@ -35,9 +35,9 @@ struct MpmSolver {
     bool grid_raw = false;      // cell path: the grid holds mass + momentum (P2G done, UpdateGrid not yet applied): G2P applies
                                 // the update while it loads its tiles, and a grid download applies it first
     bool in_rec = false;        // the particle state of slots [0, n) currently lives in `rec`, not in `part`
-    bool g2p_inputs = false;    // cell path: P2G_1 has written the position / mass planes and orig_id_alt of the current layout
+    bool g2p_inputs = false;    // cell path: P2G_1 has written the position / mass planes of the current layout (what G2P reads)
     uint32_t* orig_id = nullptr;      // original (global) index of the particle in each slot
-    uint32_t* orig_id_alt = nullptr;
+    uint32_t* orig_id_alt = nullptr;  // binned paths: ids in the NEW slot order (cell path: swapped in when G2P has rewritten the records)
     void* grid = nullptr;  // ncells_local * 16 B
     int64_t ncells = 0;    // local cells (nxl * Ry * Rz)
     float4* positions = nullptr;  // (x, y, z, |v|) in original index order
