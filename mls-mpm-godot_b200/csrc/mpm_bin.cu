@@ -75,50 +75,57 @@ __global__ void __launch_bounds__(256) k_block_sums(const uint32_t* __restrict__
 }
 
 // one CTA: exclusive scan of the block totals -> bbase[nblocks + 1]; ordered list of the non-empty blocks;
-// resets the per-step work counters
+// resets the per-step work counters.  Every thread takes a contiguous run of blocks (a multiple of 4, read and written
+// as uint4: one SM's load/store unit handles every request of this kernel), so the CTA synchronises twice whatever the
+// grid size; the round-per-1024-blocks version spent 36 us on C4's 32768 blocks, nearly all barrier and load latency.
+// bsum and bbase are padded (SCAN_PAD entries, bsum's padding zero) so that the last runs may pass nblocks.
+constexpr int64_t SCAN_PAD = 8192;
 __global__ void __launch_bounds__(1024) k_scan_blocks(const uint32_t* __restrict__ bsum, int64_t nblocks, uint32_t* __restrict__ bbase,
                                                       uint32_t* __restrict__ active, uint32_t* __restrict__ misc)
 {
     __shared__ uint32_t wsum[32], wact[32];
-    __shared__ uint32_t carry_s, carry_a;
-    if (threadIdx.x == 0) { carry_s = 0; carry_a = 0; }
     if (threadIdx.x < BIN_MISC_WORDS) misc[threadIdx.x] = 0;
-    __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int64_t base = 0; base < nblocks; base += 1024) {
-        const int64_t i = base + threadIdx.x;
-        const uint32_t v = (i < nblocks) ? bsum[i] : 0;
-        const uint32_t f = v > 0 ? 1u : 0u;
-        uint32_t x = v, y = f;
+    const int64_t per4 = (((nblocks + 1023) / 1024 + 3) / 4);  // uint4 per thread
+    const uint4* src = reinterpret_cast<const uint4*>(bsum) + (int64_t)threadIdx.x * per4;
+    uint32_t s = 0, a = 0;
+    for (int64_t k = 0; k < per4; ++k) {
+        const uint4 v = src[k];
+        s += v.x + v.y + v.z + v.w;
+        a += (v.x > 0) + (v.y > 0) + (v.z > 0) + (v.w > 0);
+    }
+    uint32_t x = s, y = a;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t x2 = __shfl_up_sync(0xffffffffu, x, o), y2 = __shfl_up_sync(0xffffffffu, y, o);
+        if (lane >= o) { x += x2; y += y2; }
+    }
+    if (lane == 31) { wsum[w] = x; wact[w] = y; }
+    __syncthreads();
+    if (w == 0) {
+        uint32_t sx = wsum[lane], sy = wact[lane];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t x2 = __shfl_up_sync(0xffffffffu, x, o), y2 = __shfl_up_sync(0xffffffffu, y, o);
-            if (lane >= o) { x += x2; y += y2; }
+            const uint32_t x2 = __shfl_up_sync(0xffffffffu, sx, o), y2 = __shfl_up_sync(0xffffffffu, sy, o);
+            if (lane >= o) { sx += x2; sy += y2; }
         }
-        if (lane == 31) { wsum[w] = x; wact[w] = y; }
-        __syncthreads();
-        if (w == 0) {
-            uint32_t sx = wsum[lane], sy = wact[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t x2 = __shfl_up_sync(0xffffffffu, sx, o), y2 = __shfl_up_sync(0xffffffffu, sy, o);
-                if (lane >= o) { sx += x2; sy += y2; }
-            }
-            wsum[lane] = sx; wact[lane] = sy;  // inclusive over warps
-        }
-        __syncthreads();
-        const uint32_t cs = carry_s, ca = carry_a;
-        const uint32_t ox = cs + (w ? wsum[w - 1] : 0) + x - v;   // exclusive prefix of the totals
-        const uint32_t oy = ca + (w ? wact[w - 1] : 0) + y - f;   // exclusive prefix of the non-empty flags
-        if (i < nblocks) {
-            bbase[i] = ox;
-            if (f) active[oy] = (uint32_t)i;
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) { carry_s = ox + v; carry_a = oy + f; }
-        __syncthreads();
+        wsum[lane] = sx; wact[lane] = sy;  // inclusive over warps
     }
-    if (threadIdx.x == 0) { bbase[nblocks] = carry_s; misc[BIN_N_ACTIVE] = carry_a; }
+    __syncthreads();
+    uint32_t ox = (w ? wsum[w - 1] : 0) + x - s;  // exclusive prefix of the totals at this thread's first block
+    uint32_t oy = (w ? wact[w - 1] : 0) + y - a;  // exclusive prefix of the non-empty flags
+    uint4* dst = reinterpret_cast<uint4*>(bbase) + (int64_t)threadIdx.x * per4;
+    uint32_t i = threadIdx.x * (uint32_t)(4 * per4);
+    for (int64_t k = 0; k < per4; ++k, i += 4) {  // (blocks past nblocks have total 0: they get the grand total as base)
+        const uint4 v = src[k];
+        uint4 o;
+        o.x = ox; if (v.x) active[oy++] = i;     ox += v.x;
+        o.y = ox; if (v.y) active[oy++] = i + 1; ox += v.y;
+        o.z = ox; if (v.z) active[oy++] = i + 2; ox += v.z;
+        o.w = ox; if (v.w) active[oy++] = i + 3; ox += v.w;
+        dst[k] = o;
+    }
+    if (threadIdx.x == 1023) { bbase[nblocks] = ox; misc[BIN_N_ACTIVE] = oy; }  // (nothing but padding follows its run)
 }
 
 // per non-empty block: split cells with more than VROWS particles into virtual cells of VROWS (within the block's budget
@@ -135,7 +142,7 @@ __global__ void __launch_bounds__(1 << CELL_BITS) k_block_order(const uint32_t* 
                                                                const uint32_t* __restrict__ active, const uint32_t* __restrict__ misc,
                                                                uint16_t* __restrict__ ord, uint32_t* __restrict__ cnts,
                                                                uint2* __restrict__ cellmeta, uint32_t* __restrict__ pstart,
-                                                               uint16_t* __restrict__ stab)
+                                                               uint16_t* __restrict__ stab, uint32_t* __restrict__ fill)
 {
     constexpr int NC = 1 << CELL_BITS, NV = 2 * NC, NBIN = 64, NW = NC / 32, EXTRA = NV - NC;
     __shared__ uint32_t hist[NBIN], base[NBIN], cursor[NBIN];
@@ -152,6 +159,7 @@ __global__ void __launch_bounds__(1 << CELL_BITS) k_block_order(const uint32_t* 
     if (t == 0) carry_s = 0;
     __syncthreads();
     const uint32_t c = cnt[blk0 + t];
+    fill[blk0 + t] = 0;  // k_place's cursor: only the cells of non-empty blocks are ever used, so they are reset here
     // extra virtual cells this cell wants, granted in cell order while the block's budget lasts
     const uint32_t want = c > VROWS ? (c + VROWS - 1) / VROWS - 1 : 0;
     uint32_t x = want;
@@ -330,8 +338,9 @@ int bin_create(MpmSolver* s)
     CKB(cudaMalloc(&st->cellmeta, sizeof(uint2) * st->nslots));
     CKB(cudaMalloc(&st->pstart, sizeof(uint32_t) * (nvpos >> 5)));
     CKB(cudaMalloc(&st->stab, sizeof(uint16_t) * 16 * (nvpos >> 5)));
-    CKB(cudaMalloc(&st->bsum, sizeof(uint32_t) * st->nblocks));
-    CKB(cudaMalloc(&st->bbase, sizeof(uint32_t) * (st->nblocks + 1)));
+    CKB(cudaMalloc(&st->bsum, sizeof(uint32_t) * (st->nblocks + SCAN_PAD)));
+    CKB(cudaMemsetAsync(st->bsum, 0, sizeof(uint32_t) * (st->nblocks + SCAN_PAD), s->stream));
+    CKB(cudaMalloc(&st->bbase, sizeof(uint32_t) * (st->nblocks + SCAN_PAD)));
     CKB(cudaMalloc(&st->fill, sizeof(uint32_t) * st->nslots));
     CKB(cudaMalloc(&st->keys, sizeof(uint32_t) * s->pitch));
     CKB(cudaMalloc(&st->src_of, sizeof(uint32_t) * (s->pitch + 64)));  // (the cell kernels read one row past the last slot)
@@ -381,16 +390,15 @@ int bin_particles(MpmSolver* s)
             s->launches += 1;
         }
     }
-    CKB(cudaMemsetAsync(st->fill, 0, sizeof(uint32_t) * st->nslots, s->stream));
     const unsigned nbw = (unsigned)((st->nblocks * 32 + 255) / 256);
     if (st->cell_bits == 9) {
         k_block_sums<9><<<nbw, 256, 0, s->stream>>>(st->cnt[nxt], st->nblocks, st->bsum);
         k_scan_blocks<<<1, 1024, 0, s->stream>>>(st->bsum, st->nblocks, st->bbase, st->active, st->misc);
-        k_block_order<9><<<(unsigned)st->nblocks, 512, 0, s->stream>>>(st->cnt[nxt], st->bbase, st->active, st->misc, st->ord, st->cnts, st->cellmeta, st->pstart, st->stab);
+        k_block_order<9><<<(unsigned)st->nblocks, 512, 0, s->stream>>>(st->cnt[nxt], st->bbase, st->active, st->misc, st->ord, st->cnts, st->cellmeta, st->pstart, st->stab, st->fill);
     } else {
         k_block_sums<6><<<nbw, 256, 0, s->stream>>>(st->cnt[nxt], st->nblocks, st->bsum);
         k_scan_blocks<<<1, 1024, 0, s->stream>>>(st->bsum, st->nblocks, st->bbase, st->active, st->misc);
-        k_block_order<6><<<(unsigned)st->nblocks, 64, 0, s->stream>>>(st->cnt[nxt], st->bbase, st->active, st->misc, st->ord, st->cnts, st->cellmeta, st->pstart, st->stab);
+        k_block_order<6><<<(unsigned)st->nblocks, 64, 0, s->stream>>>(st->cnt[nxt], st->bbase, st->active, st->misc, st->ord, st->cnts, st->cellmeta, st->pstart, st->stab, st->fill);
     }
     s->launches += 3;
     if (n > 0) {
