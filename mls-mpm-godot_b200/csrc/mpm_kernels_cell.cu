@@ -702,6 +702,10 @@ static int check_cell_supported(MpmSolver* s)
     return MPM_OK;
 }
 
+// One process may drive several GPUs (k solvers on the in-process transport): launch geometry and the opt-in for more
+// than 48 KB of dynamic shared memory are looked up / set once per (kernel, device).
+constexpr int MAX_DEVICES = 64;
+
 template <typename K>
 static unsigned persistent_grid(K kernel, int threads, size_t smem)
 {
@@ -720,11 +724,13 @@ static unsigned persistent_grid(K kernel, int threads, size_t smem)
         TileGeom g{st->nby, st->nbz, s->dp.gx0 + (s->comm ? 1 : 0)};                                                      \
         CellArgs a{st->cnts, st->ord, st->pstart, st->active, st->misc};                                       \
         if (st->B == 8) {                                                                                                 \
-            static unsigned grid8 = 0;                                                                                    \
+            static unsigned grid8_dev[MAX_DEVICES] = {};  /* per device: the shared-memory opt-in is a per-device attribute */ \
+            unsigned& grid8 = grid8_dev[s->device & (MAX_DEVICES - 1)];                                                   \
             if (!grid8) grid8 = persistent_grid(KERNEL<8>, CellCfg<8>::THREADS, (SMEM8));                                 \
             KERNEL<8><<<(unsigned)std::min<int64_t>(grid8, st->nblocks), CellCfg<8>::THREADS, (SMEM8), s->stream>>>(s->dp, g, s->view(), a, __VA_ARGS__); \
         } else {                                                                                                          \
-            static unsigned grid4 = 0;                                                                                    \
+            static unsigned grid4_dev[MAX_DEVICES] = {};                                                                  \
+            unsigned& grid4 = grid4_dev[s->device & (MAX_DEVICES - 1)];                                                   \
             if (!grid4) grid4 = persistent_grid(KERNEL<4>, CellCfg<4>::THREADS, (SMEM4));                                 \
             KERNEL<4><<<(unsigned)std::min<int64_t>(grid4, st->nblocks), CellCfg<4>::THREADS, (SMEM4), s->stream>>>(s->dp, g, s->view(), a, __VA_ARGS__); \
         }                                                                                                                 \
