@@ -515,6 +515,13 @@ struct PhaseTimer {
     ~PhaseTimer() { if (s->timing) cudaEventRecord(b, s->stream); }
 };
 
+// clear / update restricted to the bounding box the binning found (cell path, one GPU, binning valid for this step)
+static bool box_sweeps(const MpmSolver* s)
+{
+    static const bool off = getenv("MPM_DENSE_SWEEPS") != nullptr;
+    return !off && s->path == MPM_PATH_CELL && !s->comm && s->sorted_valid && s->bin != nullptr;
+}
+
 static int run_phase(MpmSolver* s, int phase, size_t& cursor)
 {
     const DevParams& P = s->dp;
@@ -525,7 +532,12 @@ static int run_phase(MpmSolver* s, int phase, size_t& cursor)
             else if (s->path == MPM_PATH_CELL) { int rc = bin_particles(s); if (rc) return rc; }
             break;
         case PH_CLEAR:
-            CK(cudaMemsetAsync(s->grid, 0, 16 * s->ncells, s->stream));
+            // Cell path: the binning of this step has run, so the blocks that can receive anything are known: clear and
+            // update only their bounding box (29 % of the C4 grid at the start of the dam-break).  Multi-GPU slabs keep the
+            // dense sweeps: the neighbours' halo contributions land outside a rank's own box.
+            if (box_sweeps(s)) { launch_clear_box(P, s->grid, s->bin->box + 6, s->stream); s->launches += 1; }
+            else CK(cudaMemsetAsync(s->grid, 0, 16 * s->ncells, s->stream));
+            if (s->bin) s->bin->box_cleared = true;
             s->grid_raw = false;
             break;
         case PH_P2G1:
@@ -539,7 +551,9 @@ static int run_phase(MpmSolver* s, int phase, size_t& cursor)
             else { launch_p2g2_ref(P, s->view(), s->n, s->grid, s->stream); s->launches += (s->n > 0); }
             break;
         case PH_UPDATE:
-            launch_update_grid(P, s->grid, s->ncells, s->stream); s->launches += 1;
+            if (box_sweeps(s)) launch_update_box(P, s->grid, s->bin->box, s->stream);
+            else launch_update_grid(P, s->grid, s->ncells, s->stream);
+            s->launches += 1;
             s->grid_raw = false;
             break;
         case PH_G2P:

@@ -27,6 +27,7 @@
 #include "mpm_bin.h"
 
 #include <algorithm>
+#include <climits>
 
 #include "mpm_kernels.h"
 #include "mpm_tile.cuh"
@@ -79,11 +80,26 @@ __global__ void __launch_bounds__(256) k_block_sums(const uint32_t* __restrict__
 // as uint4: one SM's load/store unit handles every request of this kernel), so the CTA synchronises twice whatever the
 // grid size; the round-per-1024-blocks version spent 36 us on C4's 32768 blocks, nearly all barrier and load latency.
 // bsum and bbase are padded (SCAN_PAD entries, bsum's padding zero) so that the last runs may pass nblocks.
+// Also the bounding box of the non-empty blocks, in cells and with the one-node apron their P2G tiles write: box[0..5] =
+// {x0, x1, y0, y1, z0, z1} (half-open, global coordinates, clamped to the local grid) for this step's grid update, and
+// box[6..11] = its union with the boxes of every binning since the last clear (`cleared` = a clear has run since the
+// previous binning) -- whatever earlier steps left behind lies in there.
 constexpr int64_t SCAN_PAD = 8192;
+struct BoxGeom { int nby, nbz, B, x_owned0, gx0, nxl, Ry, Rz; };
+
 __global__ void __launch_bounds__(1024) k_scan_blocks(const uint32_t* __restrict__ bsum, int64_t nblocks, uint32_t* __restrict__ bbase,
-                                                      uint32_t* __restrict__ active, uint32_t* __restrict__ misc)
+                                                      uint32_t* __restrict__ active, uint32_t* __restrict__ misc, BoxGeom bg,
+                                                      int* __restrict__ box, int cleared)
 {
     __shared__ uint32_t wsum[32], wact[32];
+    __shared__ int wbox[32][6];
+    int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {-1, -1, -1};  // block coordinates of the non-empty blocks of this thread
+    auto note = [&](uint32_t blk) {
+        const int bz = (int)(blk % (uint32_t)bg.nbz), by = (int)(blk / (uint32_t)bg.nbz % (uint32_t)bg.nby), bx = (int)(blk / (uint32_t)(bg.nbz * bg.nby));
+        lo[0] = min(lo[0], bx); hi[0] = max(hi[0], bx);
+        lo[1] = min(lo[1], by); hi[1] = max(hi[1], by);
+        lo[2] = min(lo[2], bz); hi[2] = max(hi[2], bz);
+    };
     if (threadIdx.x < BIN_MISC_WORDS) misc[threadIdx.x] = 0;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t per4 = (((nblocks + 1023) / 1024 + 3) / 4);  // uint4 per thread
@@ -119,13 +135,41 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(const uint32_t* __restrict
     for (int64_t k = 0; k < per4; ++k, i += 4) {  // (blocks past nblocks have total 0: they get the grand total as base)
         const uint4 v = src[k];
         uint4 o;
-        o.x = ox; if (v.x) active[oy++] = i;     ox += v.x;
-        o.y = ox; if (v.y) active[oy++] = i + 1; ox += v.y;
-        o.z = ox; if (v.z) active[oy++] = i + 2; ox += v.z;
-        o.w = ox; if (v.w) active[oy++] = i + 3; ox += v.w;
+        o.x = ox; if (v.x) { active[oy++] = i;     note(i); }     ox += v.x;
+        o.y = ox; if (v.y) { active[oy++] = i + 1; note(i + 1); } ox += v.y;
+        o.z = ox; if (v.z) { active[oy++] = i + 2; note(i + 2); } ox += v.z;
+        o.w = ox; if (v.w) { active[oy++] = i + 3; note(i + 3); } ox += v.w;
         dst[k] = o;
     }
     if (threadIdx.x == 1023) { bbase[nblocks] = ox; misc[BIN_N_ACTIVE] = oy; }  // (nothing but padding follows its run)
+    // bounding box: warp reductions, then thread 0 over the 32 warps
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        lo[d] = __reduce_min_sync(0xffffffffu, lo[d]);
+        hi[d] = __reduce_max_sync(0xffffffffu, hi[d]);
+    }
+    if (lane == 0) { for (int d = 0; d < 3; ++d) { wbox[w][2 * d] = lo[d]; wbox[w][2 * d + 1] = hi[d]; } }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 32; ++k)
+            for (int d = 0; d < 3; ++d) { lo[d] = min(lo[d], wbox[k][2 * d]); hi[d] = max(hi[d], wbox[k][2 * d + 1]); }
+        int nb[6] = {0, 0, 0, 0, 0, 0};  // empty unless there is a non-empty block
+        if (hi[0] >= 0) {
+            nb[0] = max(bg.x_owned0 + lo[0] * bg.B - 1, bg.gx0); nb[1] = min(bg.x_owned0 + (hi[0] + 1) * bg.B + 1, bg.gx0 + bg.nxl);
+            nb[2] = max(lo[1] * bg.B - 1, 0);                    nb[3] = min((hi[1] + 1) * bg.B + 1, bg.Ry);
+            nb[4] = max(lo[2] * bg.B - 1, 0);                    nb[5] = min((hi[2] + 1) * bg.B + 1, bg.Rz);
+        }
+        // union of: the new box, the previous binning's box, and (unless a clear ran since) the pending clear box
+        int u[6] = {nb[0], nb[1], nb[2], nb[3], nb[4], nb[5]};
+        auto join = [&](const int* q) {
+            if (q[0] >= q[1]) return;  // empty
+            if (u[0] >= u[1]) { for (int k = 0; k < 6; ++k) u[k] = q[k]; return; }
+            for (int d = 0; d < 3; ++d) { u[2 * d] = min(u[2 * d], q[2 * d]); u[2 * d + 1] = max(u[2 * d + 1], q[2 * d + 1]); }
+        };
+        join(box);
+        if (!cleared) join(box + 6);
+        for (int k = 0; k < 6; ++k) { box[6 + k] = u[k]; box[k] = nb[k]; }
+    }
 }
 
 // per non-empty block: split cells with more than VROWS particles into virtual cells of VROWS (within the block's budget
@@ -347,6 +391,8 @@ int bin_create(MpmSolver* s)
     CKB(cudaMemsetAsync(st->src_of, 0, sizeof(uint32_t) * (s->pitch + 64), s->stream));
     CKB(cudaMalloc(&st->active, sizeof(uint32_t) * st->nblocks));
 
+    CKB(cudaMalloc(&st->box, sizeof(int) * 12));
+    CKB(cudaMemsetAsync(st->box, 0, sizeof(int) * 12, s->stream));  // empty boxes
     CKB(cudaMalloc(&st->misc, sizeof(uint32_t) * BIN_MISC_WORDS));
     CKB(cudaMemsetAsync(st->misc, 0, sizeof(uint32_t) * BIN_MISC_WORDS, s->stream));
     st->cur = 0;
@@ -360,7 +406,7 @@ void bin_destroy(MpmSolver* s)
     if (!st) return;
     cudaFree(st->cnt[0]); cudaFree(st->cnt[1]); cudaFree(st->cnts); cudaFree(st->ord); cudaFree(st->cellmeta); cudaFree(st->pstart); cudaFree(st->stab);
     cudaFree(st->bsum); cudaFree(st->bbase); cudaFree(st->fill); cudaFree(st->keys); cudaFree(st->src_of); cudaFree(st->active);
-    cudaFree(st->misc);
+    cudaFree(st->misc); cudaFree(st->box);
     delete st;
     s->bin = nullptr;
 }
@@ -391,13 +437,14 @@ int bin_particles(MpmSolver* s)
         }
     }
     const unsigned nbw = (unsigned)((st->nblocks * 32 + 255) / 256);
+    const BoxGeom bg{st->nby, st->nbz, st->B, s->dp.gx0 + (s->comm ? 1 : 0), s->dp.gx0, s->dp.nxl, s->dp.Ry, s->dp.Rz};
     if (st->cell_bits == 9) {
         k_block_sums<9><<<nbw, 256, 0, s->stream>>>(st->cnt[nxt], st->nblocks, st->bsum);
-        k_scan_blocks<<<1, 1024, 0, s->stream>>>(st->bsum, st->nblocks, st->bbase, st->active, st->misc);
+        k_scan_blocks<<<1, 1024, 0, s->stream>>>(st->bsum, st->nblocks, st->bbase, st->active, st->misc, bg, st->box, st->box_cleared ? 1 : 0);
         k_block_order<9><<<(unsigned)st->nblocks, 512, 0, s->stream>>>(st->cnt[nxt], st->bbase, st->active, st->misc, st->ord, st->cnts, st->cellmeta, st->pstart, st->stab, st->fill);
     } else {
         k_block_sums<6><<<nbw, 256, 0, s->stream>>>(st->cnt[nxt], st->nblocks, st->bsum);
-        k_scan_blocks<<<1, 1024, 0, s->stream>>>(st->bsum, st->nblocks, st->bbase, st->active, st->misc);
+        k_scan_blocks<<<1, 1024, 0, s->stream>>>(st->bsum, st->nblocks, st->bbase, st->active, st->misc, bg, st->box, st->box_cleared ? 1 : 0);
         k_block_order<6><<<(unsigned)st->nblocks, 64, 0, s->stream>>>(st->cnt[nxt], st->bbase, st->active, st->misc, st->ord, st->cnts, st->cellmeta, st->pstart, st->stab, st->fill);
     }
     s->launches += 3;
@@ -408,6 +455,7 @@ int bin_particles(MpmSolver* s)
     }
     s->g2p_inputs = false;  // position / mass planes of this layout: written by P2G_1 (orig_id_alt holds the slot-order
                             // ids already; the two id arrays are swapped when G2P has rewritten the records in slot order)
+    st->box_cleared = false;
     st->cur = nxt;
     st->next_valid = false;
     // the other count buffer receives the next step's counts from G2P: clear it now

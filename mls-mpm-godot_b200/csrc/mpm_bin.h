@@ -30,6 +30,9 @@ struct BinState {
     uint32_t* src_of = nullptr;      // [pitch + 64] slot -> index of the particle's record (the records stay where G2P wrote them)
     uint32_t* active = nullptr;      // [nblocks] non-empty blocks, ascending
     uint32_t* misc = nullptr;        // BIN_MISC_WORDS counters
+    int* box = nullptr;              // [12] cells: bounding box of the non-empty blocks (+ apron) of the current binning, and its
+                                     // union with those since the last clear (what a sparse clear has to cover); see k_scan_blocks
+    bool box_cleared = true;         // the grid has been cleared since the last binning
 };
 
 int bin_create(MpmSolver* s);

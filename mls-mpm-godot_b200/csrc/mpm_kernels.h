@@ -8,6 +8,9 @@ namespace mpm {
 void launch_p2g1_ref(const DevParams& P, ParticleView pv, int64_t n, void* grid, cudaStream_t st);
 void launch_p2g2_ref(const DevParams& P, ParticleView pv, int64_t n, void* grid, cudaStream_t st);
 void launch_update_grid(const DevParams& P, void* grid, int64_t ncells, cudaStream_t st);
+// clear / update restricted to a device-resident box of cells {x0, x1, y0, y1, z0, z1} (3D fixed-point grid)
+void launch_clear_box(const DevParams& P, void* grid, const int* box, cudaStream_t st);
+void launch_update_box(const DevParams& P, void* grid, const int* box, cudaStream_t st);
 void launch_g2p_ref(const DevParams& P, ParticleView pv, int64_t n, const void* grid, const uint32_t* orig_id,
                     float4* positions, cudaStream_t st);
 

@@ -103,6 +103,18 @@ __global__ void __launch_bounds__(256) k_p2g2_ref(DevParams P, ParticleView pv, 
 }
 
 // ---------------------------------------------------------------- UpdateGrid  (update_grid.glsl:36-74)
+// fixed-point cell: decode, v = p / m, gravity on y, wall-normal component zeroed (ox / oy / oz), re-encode
+__device__ __forceinline__ void update_cell_fixed(const DevParams& P, int4& c, bool ox, bool oy, bool oz)
+{
+    const float mm = decode_fixed(c.w, P.fmult);
+    const float vx = sdiv(decode_fixed(c.x, P.fmult), mm);
+    const float vy = sdiv(decode_fixed(c.y, P.fmult), mm);
+    const float vz = sdiv(decode_fixed(c.z, P.fmult), mm);
+    c.x = ox ? 0 : encode_fixed(vx, P.fmult);
+    c.y = oy ? 0 : encode_fixed(sadd(vy, smul(P.dt, P.gravity)), P.fmult);
+    c.z = oz ? 0 : encode_fixed(vz, P.fmult);
+}
+
 // One thread per local cell; a whole 16-B cell per thread keeps the access a coalesced 128-bit stream.
 template <int DIM, bool FIXED>
 __global__ void __launch_bounds__(256) k_update_grid(DevParams P, void* grid, int64_t ncells)
@@ -118,13 +130,7 @@ __global__ void __launch_bounds__(256) k_update_grid(DevParams P, void* grid, in
     if (FIXED) {
         int4 c = reinterpret_cast<int4*>(grid)[i];
         if (c.w > 0) {
-            const float mm = decode_fixed(c.w, P.fmult);
-            const float vx = sdiv(decode_fixed(c.x, P.fmult), mm);
-            const float vy = sdiv(decode_fixed(c.y, P.fmult), mm);
-            const float vz = sdiv(decode_fixed(c.z, P.fmult), mm);
-            c.x = ox ? 0 : encode_fixed(vx, P.fmult);
-            c.y = oy ? 0 : encode_fixed(sadd(vy, smul(P.dt, P.gravity)), P.fmult);
-            c.z = oz ? 0 : encode_fixed(vz, P.fmult);
+            update_cell_fixed(P, c, ox, oy, oz);
             reinterpret_cast<int4*>(grid)[i] = c;
         }
     } else {
@@ -144,6 +150,46 @@ __global__ void __launch_bounds__(256) k_update_grid(DevParams P, void* grid, in
                 if (oz) { c.x = smul(f, c.x); c.y = smul(f, c.y); c.z = 0.0f; }
             }
             reinterpret_cast<float4*>(grid)[i] = c;
+        }
+    }
+}
+
+// ---- the same two grid sweeps restricted to a box of cells (cell path, 3D fixed-point grid): the binning knows which grid
+// blocks hold particles, and nothing outside their bounding box (+ the one-node apron P2G writes) is ever non-zero.
+// box = {x0, x1, y0, y1, z0, z1}, half-open, global cell coordinates, already clamped to the local grid; it lives on the
+// device (the scan of the binning writes it), so the launch covers the whole grid in strips of BOX_ROWS (x, y) rows and
+// strips outside return at once.
+constexpr int BOX_ROWS = 8;  // (x, y) rows per CTA: one row per CTA made the launch itself (65536 tiny CTAs on C4) cost 35 us
+
+__global__ void __launch_bounds__(256) k_clear_box(DevParams P, int4* __restrict__ grid, const int* __restrict__ box)
+{
+    const int x = P.gx0 + blockIdx.y;
+    if (x < box[0] || x >= box[1]) return;
+    const int y0 = max((int)blockIdx.x * BOX_ROWS, box[2]), y1 = min(min((int)blockIdx.x * BOX_ROWS + BOX_ROWS, box[3]), P.Ry);
+    const int z0 = box[4], z1 = box[5];
+    for (int y = y0; y < y1; ++y) {
+        int4* row = grid + ((int64_t)blockIdx.y * P.Ry + y) * P.Rz;
+        for (int z = z0 + threadIdx.x; z < z1; z += blockDim.x) row[z] = make_int4(0, 0, 0, 0);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_update_box(DevParams P, int4* __restrict__ grid, const int* __restrict__ box)
+{
+    const int x = P.gx0 + blockIdx.y;
+    if (x < box[0] || x >= box[1]) return;
+    const int y0 = max((int)blockIdx.x * BOX_ROWS, box[2]), y1 = min(min((int)blockIdx.x * BOX_ROWS + BOX_ROWS, box[3]), P.Ry);
+    const int z0 = box[4], z1 = box[5];
+    const int hi = P.bc_hi_off;
+    const bool ox = (x < 2 || x > P.Rx - hi);
+    for (int y = y0; y < y1; ++y) {
+        int4* row = grid + ((int64_t)blockIdx.y * P.Ry + y) * P.Rz;
+        const bool oy = (y < 2 || y > P.Ry - hi);
+        for (int z = z0 + threadIdx.x; z < z1; z += blockDim.x) {
+            int4 c = row[z];
+            if (c.w > 0) {
+                update_cell_fixed(P, c, ox, oy, z < 2 || z > P.Rz - hi);
+                row[z] = c;
+            }
         }
     }
 }
@@ -219,6 +265,14 @@ void launch_p2g2_ref(const DevParams& P, ParticleView pv, int64_t n, void* grid,
 void launch_update_grid(const DevParams& P, void* grid, int64_t ncells, cudaStream_t st)
 {
     DISPATCH_DIM_FIXED(k_update_grid, <<<blocks_for(ncells, 256), 256, 0, st>>>(P, grid, ncells));
+}
+void launch_clear_box(const DevParams& P, void* grid, const int* box, cudaStream_t st)
+{
+    k_clear_box<<<dim3((unsigned)((P.Ry + BOX_ROWS - 1) / BOX_ROWS), (unsigned)P.nxl), 256, 0, st>>>(P, reinterpret_cast<int4*>(grid), box);
+}
+void launch_update_box(const DevParams& P, void* grid, const int* box, cudaStream_t st)
+{
+    k_update_box<<<dim3((unsigned)((P.Ry + BOX_ROWS - 1) / BOX_ROWS), (unsigned)P.nxl), 256, 0, st>>>(P, reinterpret_cast<int4*>(grid), box);
 }
 void launch_g2p_ref(const DevParams& P, ParticleView pv, int64_t n, const void* grid, const uint32_t* orig_id,
                     float4* positions, cudaStream_t st)
