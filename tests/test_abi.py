@@ -85,3 +85,16 @@ def test_reference_arm_of_the_bench_prints_the_contract_line():
     assert line["impl"] == "reference" and line["value"] > 0 and line["metric"] == "particle-steps/s"
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_committed_traffic_table_has_the_kernels_the_bench_reports():
+    """`bench.py` fills `roofline.traffic` / `kernels[*].traffic` from profiles/r1/traffic_c4.json (DRAM bytes per launch
+    from one committed `ncu --set full` capture): the table must name the three stencil kernels, cite its source file,
+    and that file must be in the repo."""
+    import json
+    with open(os.path.join(ROOT, "profiles", "r1", "traffic_c4.json")) as f:
+        t = json.load(f)
+    for k in ("k_p2g1_cell", "k_p2g2_cell", "k_g2p_cell"):
+        assert t["kernels"][k]["dram_bytes"] > 1e9 and t["kernels"][k]["ncu_duration_s"] > 0
+    src = t["source"].split(" ")[0]
+    assert os.path.exists(os.path.join(ROOT, src)), src
