@@ -153,6 +153,9 @@ typedef struct MpmStats {
     int64_t migrated;         /* particles this rank has sent to its neighbours since the communicator was attached */
     int64_t slab_jump_clamps; /* multi-GPU: particles that would have crossed more than one slab in a single step (|v| dt
                                  larger than the neighbouring slab is wide) and were held back in that slab's far plane */
+    int64_t unordered_binnings; /* cell path: bin phases that could not rank stably (more than 4096 particles jumped out of
+                                   their grid block's one-cell apron in one step: the simulation has blown up) and used an
+                                   atomic cursor instead; 0 means every binning so far equals std::stable_sort */
 } MpmStats;
 
 typedef struct MpmSolver MpmSolver; /* opaque */

@@ -769,6 +769,13 @@ extern "C" int32_t mpm_get_stats(MpmSolver* s, MpmStats* st)
         cudaStreamSynchronize(s->stream);
         cudaMemcpy(&st->overflow, s->overflow_flag, sizeof(int32_t), cudaMemcpyDeviceToHost);
     }
+    if (s->bin && s->bin->far_n) {
+        uint32_t f[2] = {0, 0};
+        cudaSetDevice(s->device);
+        cudaStreamSynchronize(s->stream);
+        cudaMemcpy(f, s->bin->far_n, sizeof(f), cudaMemcpyDeviceToHost);
+        st->unordered_binnings = f[1];
+    }
     comm_fill_stats(s, st);
     return MPM_OK;
 }
@@ -776,8 +783,9 @@ extern "C" int32_t mpm_get_stats(MpmSolver* s, MpmStats* st)
 extern "C" int32_t mpm_debug_last_sort(MpmSolver* s, uint32_t* keys_before, uint32_t* perm, int64_t cap)
 {
     if (!s) return MPM_ERR_INVALID;
-    if (s->path != MPM_PATH_TILED) return fail(s, MPM_ERR_STATE, "binning exists only on the tiled path");
+    if (s->path != MPM_PATH_TILED && s->path != MPM_PATH_CELL) return fail(s, MPM_ERR_STATE, "the reference-shaped path does not bin particles");
     CK(cudaSetDevice(s->device));
+    if (s->path == MPM_PATH_CELL) return bin_debug_last(s, keys_before, perm, cap);
     return sort_debug_last(s, keys_before, perm, cap);
 }
 

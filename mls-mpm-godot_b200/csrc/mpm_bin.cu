@@ -28,6 +28,9 @@
 
 #include <algorithm>
 #include <climits>
+#include <cstdlib>
+#include <string>
+#include <vector>
 
 #include "mpm_kernels.h"
 #include "mpm_tile.cuh"
@@ -89,8 +92,9 @@ struct BoxGeom { int nby, nbz, B, x_owned0, gx0, nxl, Ry, Rz; };
 
 __global__ void __launch_bounds__(1024) k_scan_blocks(const uint32_t* __restrict__ bsum, int64_t nblocks, uint32_t* __restrict__ bbase,
                                                       uint32_t* __restrict__ active, uint32_t* __restrict__ misc, BoxGeom bg,
-                                                      int* __restrict__ box, int cleared)
+                                                      int* __restrict__ box, int cleared, uint32_t* __restrict__ nact_out, uint32_t* __restrict__ far_n)
 {
+    if (threadIdx.x == 0) far_n[0] = 0;  // the far-mover list of the stable ranking starts empty
     __shared__ uint32_t wsum[32], wact[32];
     __shared__ int wbox[32][6];
     int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {-1, -1, -1};  // block coordinates of the non-empty blocks of this thread
@@ -141,7 +145,7 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(const uint32_t* __restrict
         o.w = ox; if (v.w) { active[oy++] = i + 3; note(i + 3); } ox += v.w;
         dst[k] = o;
     }
-    if (threadIdx.x == 1023) { bbase[nblocks] = ox; misc[BIN_N_ACTIVE] = oy; }  // (nothing but padding follows its run)
+    if (threadIdx.x == 1023) { bbase[nblocks] = ox; misc[BIN_N_ACTIVE] = oy; *nact_out = oy; }  // (nothing but padding follows its run)
     // bounding box: warp reductions, then thread 0 over the 32 warps
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -276,20 +280,12 @@ __global__ void __launch_bounds__(1 << CELL_BITS) k_block_order(const uint32_t* 
     }
 }
 
-// rank inside the cell from an atomic cursor -> (virtual cell, row) -> destination slot from the chunk's counts
+// rank inside the (real) cell -> (virtual cell, row) -> destination slot from the chunk's counts
 template <int CELL_BITS>
-__global__ void __launch_bounds__(256) k_place(const uint32_t* __restrict__ keys, int64_t n, const uint2* __restrict__ cellmeta,
-                                               const uint32_t* __restrict__ cnts, const uint32_t* __restrict__ pstart,
-                                               const uint16_t* __restrict__ stab, uint32_t* __restrict__ fill, uint32_t* __restrict__ src_of,
-                                               const uint32_t* __restrict__ id_src, uint32_t* __restrict__ id_dst)
+__device__ __forceinline__ uint32_t place_slot(uint32_t key, uint32_t rc, const uint2* __restrict__ cellmeta, const uint32_t* __restrict__ cnts,
+                                               const uint32_t* __restrict__ pstart, const uint16_t* __restrict__ stab)
 {
     constexpr uint32_t NV = 2u << CELL_BITS;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t key = keys[i];
-    const uint32_t id = id_src[i];  // the particle's original index moves to its new slot here (coalesced read, one more
-                                    // scattered 4-byte store) rather than as a scattered read in P2G_1
-    const uint32_t rc = atomicAdd(&fill[key], 1u);  // rank inside the (real) cell
     const uint2 cm = cellmeta[key];  // x: position of the first full virtual cell | position of the remainder << 16; y: full ones
     const uint32_t g = cm.y;
     uint32_t pos, r;
@@ -303,9 +299,7 @@ __global__ void __launch_bounds__(256) k_place(const uint32_t* __restrict__ keys
         // counts strictly ordered, descending: every lower lane still has a particle at rank r (r < own count <= theirs)
         const uint32_t below = r ? row[r] : 0u;
         const uint32_t ps = *reinterpret_cast<const uint32_t*>(row + 14);
-        src_of[ps + below + lane] = (uint32_t)i;
-        id_dst[ps + below + lane] = id;
-        return;
+        return ps + below + lane;
     }
     const uint4* c4 = reinterpret_cast<const uint4*>(cnts + v0 + chunk * 32u);
     uint32_t below = 0;   // sum over the chunk's virtual cells of min(count, r)
@@ -320,9 +314,275 @@ __global__ void __launch_bounds__(256) k_place(const uint32_t* __restrict__ keys
             before += ((uint32_t)(4 * k + j) < lane && c[j] > r) ? 1u : 0u;
         }
     }
-    const uint32_t dest = pstart[gchunk] + below + before;
+    return pstart[gchunk] + below + before;
+}
+
+// Atomic ranking (multi-GPU slabs, where migration leaves the slots in no particular order; MPM_ATOMIC_BINNING=1): the rank
+// inside the cell comes from an atomic cursor, so the order of a cell's particles is not reproducible run to run.
+template <int CELL_BITS>
+__global__ void __launch_bounds__(256) k_place(const uint32_t* __restrict__ keys, int64_t n, const uint2* __restrict__ cellmeta,
+                                               const uint32_t* __restrict__ cnts, const uint32_t* __restrict__ pstart,
+                                               const uint16_t* __restrict__ stab, uint32_t* __restrict__ fill, uint32_t* __restrict__ src_of,
+                                               const uint32_t* __restrict__ id_src, uint32_t* __restrict__ id_dst)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t key = keys[i];
+    const uint32_t id = id_src[i];  // the particle's original index moves to its new slot here (coalesced read, one more
+                                    // scattered 4-byte store) rather than as a scattered read in P2G_1
+    const uint32_t rc = atomicAdd(&fill[key], 1u);  // rank inside the (real) cell
+    const uint32_t dest = place_slot<CELL_BITS>(key, rc, cellmeta, cnts, pstart, stab);
     src_of[dest] = (uint32_t)i;
     id_dst[dest] = id;
+}
+
+// ---------------------------------------------------------------- stable rank inside a cell (the default on one GPU)
+// The binning permutation is the STABLE sort of the particles by cell key: inside a cell they keep the order of their old
+// slots, so the layout -- and with it the fp32 accumulation order of the cell kernels -- is a pure function of the
+// particle state: two runs give the same bits, and the permutation equals std::stable_sort on the same keys.
+//
+// A full radix sort every step would cost more than the atomic placement it replaces; the ranking below uses what the
+// previous binning left: the old slots are grouped by old grid block ("tile" T = one contiguous run, tiles in block
+// order), and a particle moves less than a cell per step, so the particles of tile T land in T's (B+2)^3 region of cells
+// -- the same region as the P2G tile.  For a cell c and an old slot i in tile T
+//     rank(i) = sum over the tiles T' < T whose region holds c of count(T', c)      (at most 7 tiles: c's own block and
+//                                                                                    its face / edge / corner neighbours)
+//             + number of slots j < i of T with the same cell.
+// k_rank_count writes count(T, .) per tile (shared-memory counters, one row of (B+2)^3 words per tile); k_rank_place
+// recounts per warp (warp w of the CTA owns the w-th quarter of the tile's rows), turns the counts into starting ranks
+// (neighbour offset + prefix over the warps) and walks its rows in order: rank = counter + lower lanes of the row with
+// the same cell (match.any), leader lane bumps the counter.  No global atomics, no dependence on scheduling.
+//
+// Particles that leave their tile's region (|v| dt > 1 cell: numerical outliers) are "far movers": k_rank_count lists
+// them (old slot, key), k_far_sort orders the list by slot, and every rank is corrected exactly -- a far mover ranks
+// after the regular arrivals of lower tiles and the far movers of lower slots, a regular particle gains one per far
+// mover of a lower slot in its cell (a 2048-bit Bloom filter of the far keys keeps that test off the common path).  A
+// list overflow (> FAR_CAP in one step: the simulation has blown up) falls back to atomic ranks for that binning and is
+// counted in MpmStats.unordered_binnings.
+struct RankGeom { int nbx, nby, nbz; };
+
+template <int CELL_BITS>
+struct RankCfg {
+    static constexpr int LOGB = CELL_BITS / 3, B = 1 << LOGB, T = B + 2, RC = T * T * T;
+    static constexpr int W = 4, THREADS = 32 * W;
+};
+
+// index of the cell `key` in the region of tile (tbx, tby, tbz) = block id `tile`, or -1 (a far mover)
+template <int CELL_BITS>
+__device__ __forceinline__ int region_index(uint32_t key, uint32_t tile, int tbx, int tby, int tbz, const RankGeom& g)
+{
+    using C = RankCfg<CELL_BITS>;
+    const uint32_t blk = key >> CELL_BITS;
+    const int lx = (key >> (2 * C::LOGB)) & (C::B - 1), ly = (key >> C::LOGB) & (C::B - 1), lz = key & (C::B - 1);
+    int dx = 0, dy = 0, dz = 0;
+    if (blk != tile) {
+        const int bz = (int)(blk % (uint32_t)g.nbz), by = (int)(blk / (uint32_t)g.nbz % (uint32_t)g.nby), bx = (int)(blk / (uint32_t)(g.nbz * g.nby));
+        dx = bx - tbx; dy = by - tby; dz = bz - tbz;
+        if (dx < -1 || dx > 1 || dy < -1 || dy > 1 || dz < -1 || dz > 1) return -1;
+    }
+    const int rx = dx * C::B + lx + 1, ry = dy * C::B + ly + 1, rz = dz * C::B + lz + 1;
+    if ((unsigned)rx >= (unsigned)C::T || (unsigned)ry >= (unsigned)C::T || (unsigned)rz >= (unsigned)C::T) return -1;
+    return (rx * C::T + ry) * C::T + rz;
+}
+
+// particles of the tiles below `tile` that go to the cell (cx, cy, cz) (block-grid cell coordinates): the cell's own
+// block and the neighbours whose one-cell apron holds it
+template <int CELL_BITS>
+__device__ __forceinline__ uint32_t lower_tiles_sum(int cx, int cy, int cz, uint32_t tile, const RankGeom& g, const uint32_t* __restrict__ bsum_prev,
+                                                    const uint32_t* __restrict__ tcount)
+{
+    using C = RankCfg<CELL_BITS>;
+    if (cx < 0 || cy < 0 || cz < 0 || cx >= g.nbx * C::B || cy >= g.nby * C::B || cz >= g.nbz * C::B) return 0;
+    int bx[2], by[2], bz[2], nx = 1, ny = 1, nz = 1;
+    bx[0] = cx >> C::LOGB; by[0] = cy >> C::LOGB; bz[0] = cz >> C::LOGB;
+    const int lx = cx & (C::B - 1), ly = cy & (C::B - 1), lz = cz & (C::B - 1);
+    if (lx == 0 && bx[0] > 0) bx[nx++] = bx[0] - 1; else if (lx == C::B - 1 && bx[0] + 1 < g.nbx) bx[nx++] = bx[0] + 1;
+    if (ly == 0 && by[0] > 0) by[ny++] = by[0] - 1; else if (ly == C::B - 1 && by[0] + 1 < g.nby) by[ny++] = by[0] + 1;
+    if (lz == 0 && bz[0] > 0) bz[nz++] = bz[0] - 1; else if (lz == C::B - 1 && bz[0] + 1 < g.nbz) bz[nz++] = bz[0] + 1;
+    uint32_t sum = 0;
+    for (int a = 0; a < nx; ++a)
+        for (int b = 0; b < ny; ++b)
+            for (int c = 0; c < nz; ++c) {
+                const uint32_t t2 = (uint32_t)((bx[a] * g.nby + by[b]) * g.nbz + bz[c]);
+                if (t2 >= tile || bsum_prev[t2] == 0) continue;
+                const int rx = cx - bx[a] * C::B + 1, ry = cy - by[b] * C::B + 1, rz = cz - bz[c] * C::B + 1;
+                sum += tcount[(size_t)t2 * C::RC + (size_t)((rx * C::T + ry) * C::T + rz)];
+            }
+    return sum;
+}
+
+template <int CELL_BITS>
+__global__ void __launch_bounds__(RankCfg<CELL_BITS>::THREADS) k_rank_count(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ bbase_prev,
+                                                                            const uint32_t* __restrict__ active_prev, const uint32_t* __restrict__ nact_prev,
+                                                                            RankGeom g, uint32_t* __restrict__ tcount, uint32_t* __restrict__ far_list,
+                                                                            uint32_t* __restrict__ far_n)
+{
+    using C = RankCfg<CELL_BITS>;
+    __shared__ uint32_t cnt[C::RC];
+    const uint32_t na = *nact_prev;
+    for (uint32_t t = blockIdx.x; t < na; t += gridDim.x) {
+        const uint32_t tile = active_prev[t];
+        const int tbz = (int)(tile % (uint32_t)g.nbz), tby = (int)(tile / (uint32_t)g.nbz % (uint32_t)g.nby), tbx = (int)(tile / (uint32_t)(g.nbz * g.nby));
+        for (int k = threadIdx.x; k < C::RC; k += C::THREADS) cnt[k] = 0;
+        __syncthreads();
+        const uint32_t s0 = bbase_prev[tile], s1 = bbase_prev[tile + 1];
+        for (uint32_t i = s0 + threadIdx.x; i < s1; i += C::THREADS) {
+            const uint32_t key = keys[i];
+            const int r = region_index<CELL_BITS>(key, tile, tbx, tby, tbz, g);
+            if (r >= 0) atomicAdd(&cnt[r], 1u);
+            else {
+                const uint32_t f = atomicAdd(far_n, 1u);
+                if (f < (uint32_t)FAR_CAP) { far_list[2 * f] = i; far_list[2 * f + 1] = key; }
+            }
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < C::RC; k += C::THREADS) tcount[(size_t)tile * C::RC + k] = cnt[k];
+        __syncthreads();
+    }
+}
+
+// far movers ordered by old slot (bitonic sort in shared memory); far_n[1] counts the binnings whose list overflowed
+__global__ void __launch_bounds__(1024) k_far_sort(uint32_t* __restrict__ far_list, uint32_t* __restrict__ far_n)
+{
+    __shared__ uint2 a[FAR_CAP];
+    const uint32_t n = far_n[0];
+    if (n == 0) return;
+    if (n > (uint32_t)FAR_CAP) { if (threadIdx.x == 0) far_n[1] += 1; return; }
+    for (int k = threadIdx.x; k < FAR_CAP; k += 1024) a[k] = (uint32_t)k < n ? make_uint2(far_list[2 * k], far_list[2 * k + 1]) : make_uint2(0xffffffffu, 0u);
+    __syncthreads();
+    for (int size = 2; size <= FAR_CAP; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int k = threadIdx.x; k < FAR_CAP / 2; k += 1024) {
+                const int lo = 2 * k - (k & (stride - 1)), hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const uint2 x = a[lo], y = a[hi];
+                if ((x.x > y.x) == up) { a[lo] = y; a[hi] = x; }
+            }
+            __syncthreads();
+        }
+    for (int k = threadIdx.x; k < (int)n; k += 1024) { far_list[2 * k] = a[k].x; far_list[2 * k + 1] = a[k].y; }
+}
+
+__device__ __forceinline__ uint32_t far_hash(uint32_t key) { return (key * 2654435761u) >> 21; }  // 11 bits
+
+// VERIFY: nothing is stored; the rank of every old slot goes to dbg_rank and a mismatch between the layout in place
+// (src_of) and the one this run derives is counted in dbg_bad (mpm_debug_last_sort)
+template <int CELL_BITS, bool VERIFY>
+__global__ void __launch_bounds__(RankCfg<CELL_BITS>::THREADS) k_rank_place(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ bsum_prev,
+                                                                            const uint32_t* __restrict__ bbase_prev, const uint32_t* __restrict__ active_prev,
+                                                                            const uint32_t* __restrict__ nact_prev, RankGeom g,
+                                                                            const uint32_t* __restrict__ tcount, const uint32_t* __restrict__ far_list,
+                                                                            const uint32_t* __restrict__ far_n, const uint2* __restrict__ cellmeta,
+                                                                            const uint32_t* __restrict__ cnts, const uint32_t* __restrict__ pstart,
+                                                                            const uint16_t* __restrict__ stab, uint32_t* __restrict__ fill,
+                                                                            uint32_t* __restrict__ src_of, const uint32_t* __restrict__ id_src,
+                                                                            uint32_t* __restrict__ id_dst, uint32_t* __restrict__ dbg_rank,
+                                                                            uint32_t* __restrict__ dbg_bad)
+{
+    using C = RankCfg<CELL_BITS>;
+    constexpr int RB = 4;  // rows per batch: their loads are issued together
+    __shared__ uint32_t wcnt[C::W][C::RC];
+    __shared__ uint32_t bloom[64];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const uint32_t nfar_all = far_n[0];
+    const bool overflow = nfar_all > (uint32_t)FAR_CAP;
+    const uint32_t nfar = overflow ? 0u : nfar_all;
+    if (nfar) {
+        if (threadIdx.x < 64) bloom[threadIdx.x] = 0;
+        __syncthreads();
+        for (uint32_t f = threadIdx.x; f < nfar; f += C::THREADS) { const uint32_t h = far_hash(far_list[2 * f + 1]); atomicOr(&bloom[h >> 5], 1u << (h & 31u)); }
+        __syncthreads();
+    }
+    const uint32_t na = *nact_prev;
+    for (uint32_t t = blockIdx.x; t < na; t += gridDim.x) {
+        const uint32_t tile = active_prev[t];
+        const int tbz = (int)(tile % (uint32_t)g.nbz), tby = (int)(tile / (uint32_t)g.nbz % (uint32_t)g.nby), tbx = (int)(tile / (uint32_t)(g.nbz * g.nby));
+        for (int k = threadIdx.x; k < C::W * C::RC; k += C::THREADS) (&wcnt[0][0])[k] = 0;
+        __syncthreads();
+        const uint32_t s0 = bbase_prev[tile], s1 = bbase_prev[tile + 1];
+        const uint32_t nrows = (s1 - s0 + 31u) >> 5, rpw = (nrows + C::W - 1) / C::W;
+        const uint32_t r0 = min((uint32_t)w * rpw, nrows), r1 = min(r0 + rpw, nrows);
+        // 1. counts of this warp's rows
+        for (uint32_t row = r0; row < r1; ++row) {
+            const uint32_t i = s0 + row * 32u + lane;
+            if (i < s1) {
+                const int r = region_index<CELL_BITS>(keys[i], tile, tbx, tby, tbz, g);
+                if (r >= 0) atomicAdd(&wcnt[w][r], 1u);
+            }
+        }
+        __syncthreads();
+        // 2. starting rank of every (warp, region cell): arrivals from lower tiles, then the warps in order
+        for (int k = threadIdx.x; k < C::RC; k += C::THREADS) {
+            const int rz = k % C::T, ry = (k / C::T) % C::T, rx = k / (C::T * C::T);
+            uint32_t off = lower_tiles_sum<CELL_BITS>(tbx * C::B + rx - 1, tby * C::B + ry - 1, tbz * C::B + rz - 1, tile, g, bsum_prev, tcount);
+#pragma unroll
+            for (int q = 0; q < C::W; ++q) { const uint32_t c = wcnt[q][k]; wcnt[q][k] = off; off += c; }
+        }
+        __syncthreads();
+        // 3. the warp's rows in order
+        for (uint32_t row = r0; row < r1; row += RB) {
+            uint32_t key[RB], id[RB], rc[RB];
+            int rg[RB];
+            bool valid[RB];
+#pragma unroll
+            for (int j = 0; j < RB; ++j) {
+                const uint32_t i = s0 + (row + j) * 32u + lane;
+                valid[j] = row + j < r1 && i < s1;
+                key[j] = valid[j] ? keys[i] : 0u;
+                id[j] = valid[j] ? id_src[i] : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < RB; ++j) {
+                rg[j] = valid[j] ? region_index<CELL_BITS>(key[j], tile, tbx, tby, tbz, g) : -1;
+                const uint32_t tag = rg[j] >= 0 ? (uint32_t)rg[j] : (0x80000000u | (uint32_t)lane);
+                const unsigned peers = __match_any_sync(0xffffffffu, tag);
+                uint32_t base = 0;
+                if (rg[j] >= 0) base = wcnt[w][rg[j]];
+                rc[j] = base + (uint32_t)__popc(peers & lt);
+                __syncwarp();
+                if (rg[j] >= 0 && lane == __ffs(peers) - 1) wcnt[w][rg[j]] = base + (uint32_t)__popc(peers);
+                __syncwarp();
+            }
+            if (nfar) {
+#pragma unroll
+                for (int j = 0; j < RB; ++j) {
+                    if (!valid[j]) continue;
+                    const uint32_t i = s0 + (row + j) * 32u + lane;
+                    const uint32_t h = far_hash(key[j]);
+                    if (rg[j] >= 0 && !((bloom[h >> 5] >> (h & 31u)) & 1u)) continue;
+                    uint32_t add = 0;  // far movers of lower slots that go to the same cell
+                    for (uint32_t f = 0; f < nfar && far_list[2 * f] < i; ++f) add += far_list[2 * f + 1] == key[j];
+                    if (rg[j] >= 0) rc[j] += add;
+                    else {
+                        const uint32_t blk = key[j] >> CELL_BITS;
+                        const int bz = (int)(blk % (uint32_t)g.nbz), by = (int)(blk / (uint32_t)g.nbz % (uint32_t)g.nby), bx = (int)(blk / (uint32_t)(g.nbz * g.nby));
+                        const int cx = bx * C::B + (int)((key[j] >> (2 * C::LOGB)) & (C::B - 1)), cy = by * C::B + (int)((key[j] >> C::LOGB) & (C::B - 1)),
+                                  cz = bz * C::B + (int)(key[j] & (C::B - 1));
+                        rc[j] = lower_tiles_sum<CELL_BITS>(cx, cy, cz, tile, g, bsum_prev, tcount) + add;
+                    }
+                }
+            }
+            if (overflow && !VERIFY) {
+#pragma unroll
+                for (int j = 0; j < RB; ++j) if (valid[j]) rc[j] = atomicAdd(&fill[key[j]], 1u);
+            }
+#pragma unroll
+            for (int j = 0; j < RB; ++j) {
+                if (!valid[j]) continue;
+                const uint32_t i = s0 + (row + j) * 32u + lane;
+                const uint32_t dest = place_slot<CELL_BITS>(key[j], rc[j], cellmeta, cnts, pstart, stab);
+                if (VERIFY) {
+                    dbg_rank[i] = rc[j];
+                    if (src_of[dest] != i || id_dst[dest] != id[j]) atomicAdd(dbg_bad, 1u);
+                } else {
+                    src_of[dest] = i;
+                    id_dst[dest] = id[j];
+                }
+            }
+        }
+        __syncthreads();
+    }
 }
 
 // grouped planes -> 64-byte records (a freshly uploaded or edited particle set enters the cell path)
@@ -331,9 +591,10 @@ __global__ void __launch_bounds__(256) k_planes_to_rec(ParticleView pv, float4* 
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float* q = pv.rec(i);
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-        rec[4 * i + k] = make_float4(q[(4 * k + 0) * GROUP], q[(4 * k + 1) * GROUP], q[(4 * k + 2) * GROUP], q[(4 * k + 3) * GROUP]);
+    rec[4 * i + 0] = make_float4(q[PX * GROUP], q[PY * GROUP], q[PZ * GROUP], q[PM * GROUP]);
+    rec[4 * i + 1] = make_float4(q[VX * GROUP], q[VY * GROUP], q[VZ * GROUP], q[C2 * GROUP]);
+    rec[4 * i + 2] = make_float4(q[C0 * GROUP], q[C1 * GROUP], q[C3 * GROUP], q[C4 * GROUP]);
+    rec[4 * i + 3] = make_float4(q[C6 * GROUP], q[C7 * GROUP], q[C5 * GROUP], q[C8 * GROUP]);
 }
 
 // What P2G_1 leaves for G2P -- position and mass planes in slot order -- for a G2P phase that is run without a P2G_1
@@ -343,8 +604,37 @@ __global__ void __launch_bounds__(256) k_gather_g2p_inputs(const float4* __restr
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t j = src_of[i];
-    const float4 a = rec[4 * (size_t)j], b = rec[4 * (size_t)j + 1];
-    dst.at(PX, i) = a.x; dst.at(PY, i) = a.y; dst.at(PZ, i) = a.z; dst.at(PM, i) = b.z;
+    const float4 a = rec[4 * (size_t)j];  // (px, py, pz, m)
+    dst.at(PX, i) = a.x; dst.at(PY, i) = a.y; dst.at(PZ, i) = a.z; dst.at(PM, i) = a.w;
+}
+
+// ---- cold binning: a particle set in arbitrary order (upload, scene edit) is first brought into cell-key order by a
+// stable radix sort, so that the stable ranking above finds its tiles
+__global__ void __launch_bounds__(256) k_cold_keys(KeyGeom g, ParticleView pv, int64_t n, uint32_t nslots, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t k = cell_key(g, __float2int_rz(pv.at(PX, i)), __float2int_rz(pv.at(PY, i)), __float2int_rz(pv.at(PZ, i)));
+    keys[i] = k < nslots ? k : nslots - 1;  // (as k_bin_keys)
+    vals[i] = (uint32_t)i;
+}
+
+// planes (upload order) -> records in sorted order; keys and counts of that order; original indices follow
+__global__ void __launch_bounds__(256) k_cold_gather(ParticleView pv, const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ svals, int64_t n,
+                                                     float4* __restrict__ rec, uint32_t* __restrict__ keys, uint32_t* __restrict__ cnt,
+                                                     const uint32_t* __restrict__ id_src, uint32_t* __restrict__ id_dst)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint32_t i = svals[p], k = skeys[p];
+    const float* q = pv.rec(i);
+    rec[4 * p + 0] = make_float4(q[PX * GROUP], q[PY * GROUP], q[PZ * GROUP], q[PM * GROUP]);
+    rec[4 * p + 1] = make_float4(q[VX * GROUP], q[VY * GROUP], q[VZ * GROUP], q[C2 * GROUP]);
+    rec[4 * p + 2] = make_float4(q[C0 * GROUP], q[C1 * GROUP], q[C3 * GROUP], q[C4 * GROUP]);
+    rec[4 * p + 3] = make_float4(q[C6 * GROUP], q[C7 * GROUP], q[C5 * GROUP], q[C8 * GROUP]);
+    keys[p] = k;
+    id_dst[p] = id_src[i];
+    atomicAdd(&cnt[k], 1u);
 }
 
 // ---------------------------------------------------------------- host side
@@ -382,14 +672,29 @@ int bin_create(MpmSolver* s)
     CKB(cudaMalloc(&st->cellmeta, sizeof(uint2) * st->nslots));
     CKB(cudaMalloc(&st->pstart, sizeof(uint32_t) * (nvpos >> 5)));
     CKB(cudaMalloc(&st->stab, sizeof(uint16_t) * 16 * (nvpos >> 5)));
-    CKB(cudaMalloc(&st->bsum, sizeof(uint32_t) * (st->nblocks + SCAN_PAD)));
-    CKB(cudaMemsetAsync(st->bsum, 0, sizeof(uint32_t) * (st->nblocks + SCAN_PAD), s->stream));
-    CKB(cudaMalloc(&st->bbase, sizeof(uint32_t) * (st->nblocks + SCAN_PAD)));
+    for (int k = 0; k < 2; ++k) {
+        CKB(cudaMalloc(&st->bsum2[k], sizeof(uint32_t) * (st->nblocks + SCAN_PAD)));
+        CKB(cudaMemsetAsync(st->bsum2[k], 0, sizeof(uint32_t) * (st->nblocks + SCAN_PAD), s->stream));
+        CKB(cudaMalloc(&st->bbase2[k], sizeof(uint32_t) * (st->nblocks + SCAN_PAD)));
+        CKB(cudaMemsetAsync(st->bbase2[k], 0, sizeof(uint32_t) * (st->nblocks + SCAN_PAD), s->stream));
+        CKB(cudaMalloc(&st->active2[k], sizeof(uint32_t) * st->nblocks));
+    }
+    st->bsum = st->bsum2[0]; st->bbase = st->bbase2[0]; st->active = st->active2[0];
+    CKB(cudaMalloc(&st->nact, sizeof(uint32_t) * 2));
+    CKB(cudaMemsetAsync(st->nact, 0, sizeof(uint32_t) * 2, s->stream));
+    // stable ranking is the default on one GPU; multi-GPU slabs (migration reshuffles the slots) and MPM_ATOMIC_BINNING=1
+    // rank with an atomic cursor
+    st->stable = getenv("MPM_ATOMIC_BINNING") == nullptr;
+    const int64_t T = st->B + 2;
+    CKB(cudaMalloc(&st->tcount, sizeof(uint32_t) * st->nblocks * T * T * T));
+    CKB(cudaMalloc(&st->far_list, sizeof(uint32_t) * 2 * FAR_CAP));
+    CKB(cudaMalloc(&st->far_n, sizeof(uint32_t) * 2));
+    CKB(cudaMemsetAsync(st->far_n, 0, sizeof(uint32_t) * 2, s->stream));
     CKB(cudaMalloc(&st->fill, sizeof(uint32_t) * st->nslots));
+    CKB(cudaMemsetAsync(st->fill, 0, sizeof(uint32_t) * st->nslots, s->stream));
     CKB(cudaMalloc(&st->keys, sizeof(uint32_t) * s->pitch));
     CKB(cudaMalloc(&st->src_of, sizeof(uint32_t) * (s->pitch + 64)));  // (the cell kernels read one row past the last slot)
     CKB(cudaMemsetAsync(st->src_of, 0, sizeof(uint32_t) * (s->pitch + 64), s->stream));
-    CKB(cudaMalloc(&st->active, sizeof(uint32_t) * st->nblocks));
 
     CKB(cudaMalloc(&st->box, sizeof(int) * 12));
     CKB(cudaMemsetAsync(st->box, 0, sizeof(int) * 12, s->stream));  // empty boxes
@@ -405,7 +710,9 @@ void bin_destroy(MpmSolver* s)
     BinState* st = s->bin;
     if (!st) return;
     cudaFree(st->cnt[0]); cudaFree(st->cnt[1]); cudaFree(st->cnts); cudaFree(st->ord); cudaFree(st->cellmeta); cudaFree(st->pstart); cudaFree(st->stab);
-    cudaFree(st->bsum); cudaFree(st->bbase); cudaFree(st->fill); cudaFree(st->keys); cudaFree(st->src_of); cudaFree(st->active);
+    for (int k = 0; k < 2; ++k) { cudaFree(st->bsum2[k]); cudaFree(st->bbase2[k]); cudaFree(st->active2[k]); }
+    cudaFree(st->nact); cudaFree(st->tcount); cudaFree(st->far_list); cudaFree(st->far_n);
+    cudaFree(st->fill); cudaFree(st->keys); cudaFree(st->src_of);
     cudaFree(st->misc); cudaFree(st->box);
     delete st;
     s->bin = nullptr;
@@ -417,42 +724,113 @@ KeyGeom bin_key_geom(const MpmSolver* s)
     return KeyGeom{s->dp.dim, st->logB, st->nby, st->nbz, s->dp.gx0 + (s->comm ? 1 : 0)};
 }
 
+static bool use_stable(const MpmSolver* s) { return s->bin->stable && !s->comm; }
+
+// persistent grid of the ranking kernels (one CTA per tile, striding over the list of the previous layout's non-empty blocks)
+static unsigned rank_grid(const BinState* st)
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return (unsigned)std::min<int64_t>(st->nblocks, (int64_t)sms * 8);
+}
+
+// Cold binning: the particles sit in the planes in arbitrary (upload) order.  Stable radix sort of (cell key, index) on
+// all key bits, then the records are written in that order (with keys, counts and original indices): afterwards the
+// "previous layout" the stable ranking needs is simply the key order itself.
+static int cold_sort(MpmSolver* s)
+{
+    BinState* st = s->bin;
+    const int64_t n = s->n;
+    const int nxt = st->cur ^ 1;
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    if (s->in_rec) { int rc = ensure_planes(s); if (rc) return rc; }  // (a second binning without a G2P in between: back to the planes, in record order)
+    CKB(cudaMemsetAsync(st->cnt[nxt], 0, sizeof(uint32_t) * st->nslots, s->stream));
+    if (n > 0) {
+        uint32_t* kb[2] = {nullptr, nullptr};
+        uint32_t* vb[2] = {nullptr, nullptr};
+        for (int k = 0; k < 2; ++k) { CKB(cudaMalloc(&kb[k], sizeof(uint32_t) * n)); CKB(cudaMalloc(&vb[k], sizeof(uint32_t) * n)); }
+        k_cold_keys<<<nb, 256, 0, s->stream>>>(bin_key_geom(s), s->view(), n, (uint32_t)st->nslots, kb[0], vb[0]);
+        const int key_bits = st->cell_bits + std::max(1, ilog2_ceil64(st->nblocks));
+        const int fin = radix_sort_pairs(kb, vb, n, 0, key_bits, s->stream, &s->launches, &s->err);
+        if (fin < 0) { for (int k = 0; k < 2; ++k) { cudaFree(kb[k]); cudaFree(vb[k]); } return MPM_ERR_CUDA; }
+        k_cold_gather<<<nb, 256, 0, s->stream>>>(s->view(), kb[fin], vb[fin], n, reinterpret_cast<float4*>(s->rec), st->keys, st->cnt[nxt], s->orig_id, s->orig_id_alt);
+        s->launches += 2;
+        CKB(cudaStreamSynchronize(s->stream));
+        for (int k = 0; k < 2; ++k) { cudaFree(kb[k]); cudaFree(vb[k]); }
+        std::swap(s->orig_id, s->orig_id_alt);  // ids in record order
+    }
+    s->in_rec = true;
+    st->lay_valid = false;  // the layout this binning computes doubles as the "previous" one
+    return MPM_OK;
+}
+
 int bin_particles(MpmSolver* s)
 {
     BinState* st = s->bin;
     const int64_t n = s->n;
     const int nxt = st->cur ^ 1;
     const unsigned nb = (unsigned)((n + 255) / 256);
-    // On this path the particle state lives in the 64-byte records: G2P writes them, the P2G kernels read them through
-    // src_of, and the binning never moves a particle.  A set that was just uploaded / edited is in the planes: convert once.
-    if (!s->in_rec) {
-        if (n > 0) { k_planes_to_rec<<<nb, 256, 0, s->stream>>>(s->view(), reinterpret_cast<float4*>(s->rec), n); s->launches += 1; }
-        s->in_rec = true;
-    }
-    if (!st->next_valid) {  // no G2P has produced keys/counts for this particle set: compute them from the positions
-        CKB(cudaMemsetAsync(st->cnt[nxt], 0, sizeof(uint32_t) * st->nslots, s->stream));
-        if (n > 0) {
-            k_bin_keys<RecView><<<nb, 256, 0, s->stream>>>(bin_key_geom(s), s->rview(), 0, n, (uint32_t)st->nslots, st->keys, st->cnt[nxt]);
-            s->launches += 1;
+    const bool stable = use_stable(s);
+    if (!st->next_valid && stable) {
+        int rc = cold_sort(s);
+        if (rc) return rc;
+    } else {
+        // On this path the particle state lives in the 64-byte records: G2P writes them, the P2G kernels read them through
+        // src_of, and the binning never moves a particle.  A set that was just uploaded / edited is in the planes: convert once.
+        if (!s->in_rec) {
+            if (n > 0) { k_planes_to_rec<<<nb, 256, 0, s->stream>>>(s->view(), reinterpret_cast<float4*>(s->rec), n); s->launches += 1; }
+            s->in_rec = true;
+        }
+        if (!st->next_valid) {  // no G2P has produced keys/counts for this particle set: compute them from the positions
+            CKB(cudaMemsetAsync(st->cnt[nxt], 0, sizeof(uint32_t) * st->nslots, s->stream));
+            if (n > 0) {
+                k_bin_keys<RecView><<<nb, 256, 0, s->stream>>>(bin_key_geom(s), s->rview(), 0, n, (uint32_t)st->nslots, st->keys, st->cnt[nxt]);
+                s->launches += 1;
+            }
         }
     }
     const unsigned nbw = (unsigned)((st->nblocks * 32 + 255) / 256);
     const BoxGeom bg{st->nby, st->nbz, st->B, s->dp.gx0 + (s->comm ? 1 : 0), s->dp.gx0, s->dp.nxl, s->dp.Ry, s->dp.Rz};
+    const int nl = st->lay ^ 1;            // buffers of the layout being built
+    const int pl = st->lay_valid ? st->lay : nl;  // ... and of the one the records are in
+    uint32_t* bsum = st->bsum2[nl];
+    uint32_t* bbase = st->bbase2[nl];
+    uint32_t* active = st->active2[nl];
     if (st->cell_bits == 9) {
-        k_block_sums<9><<<nbw, 256, 0, s->stream>>>(st->cnt[nxt], st->nblocks, st->bsum);
-        k_scan_blocks<<<1, 1024, 0, s->stream>>>(st->bsum, st->nblocks, st->bbase, st->active, st->misc, bg, st->box, st->box_cleared ? 1 : 0);
-        k_block_order<9><<<(unsigned)st->nblocks, 512, 0, s->stream>>>(st->cnt[nxt], st->bbase, st->active, st->misc, st->ord, st->cnts, st->cellmeta, st->pstart, st->stab, st->fill);
+        k_block_sums<9><<<nbw, 256, 0, s->stream>>>(st->cnt[nxt], st->nblocks, bsum);
+        k_scan_blocks<<<1, 1024, 0, s->stream>>>(bsum, st->nblocks, bbase, active, st->misc, bg, st->box, st->box_cleared ? 1 : 0, st->nact + nl, st->far_n);
+        k_block_order<9><<<(unsigned)st->nblocks, 512, 0, s->stream>>>(st->cnt[nxt], bbase, active, st->misc, st->ord, st->cnts, st->cellmeta, st->pstart, st->stab, st->fill);
     } else {
-        k_block_sums<6><<<nbw, 256, 0, s->stream>>>(st->cnt[nxt], st->nblocks, st->bsum);
-        k_scan_blocks<<<1, 1024, 0, s->stream>>>(st->bsum, st->nblocks, st->bbase, st->active, st->misc, bg, st->box, st->box_cleared ? 1 : 0);
-        k_block_order<6><<<(unsigned)st->nblocks, 64, 0, s->stream>>>(st->cnt[nxt], st->bbase, st->active, st->misc, st->ord, st->cnts, st->cellmeta, st->pstart, st->stab, st->fill);
+        k_block_sums<6><<<nbw, 256, 0, s->stream>>>(st->cnt[nxt], st->nblocks, bsum);
+        k_scan_blocks<<<1, 1024, 0, s->stream>>>(bsum, st->nblocks, bbase, active, st->misc, bg, st->box, st->box_cleared ? 1 : 0, st->nact + nl, st->far_n);
+        k_block_order<6><<<(unsigned)st->nblocks, 64, 0, s->stream>>>(st->cnt[nxt], bbase, active, st->misc, st->ord, st->cnts, st->cellmeta, st->pstart, st->stab, st->fill);
     }
     s->launches += 3;
-    if (n > 0) {
+    if (n > 0 && stable) {
+        const RankGeom rg{st->nbx, st->nby, st->nbz};
+        const unsigned grid = rank_grid(st);
+#define RANK_ARGS st->keys, st->bsum2[pl], st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->far_list, st->far_n, st->cellmeta, st->cnts, \
+                  st->pstart, st->stab, st->fill, st->src_of, s->orig_id, s->orig_id_alt, nullptr, nullptr
+        if (st->cell_bits == 9) {
+            k_rank_count<9><<<grid, RankCfg<9>::THREADS, 0, s->stream>>>(st->keys, st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->far_list, st->far_n);
+            k_far_sort<<<1, 1024, 0, s->stream>>>(st->far_list, st->far_n);
+            k_rank_place<9, false><<<grid, RankCfg<9>::THREADS, 0, s->stream>>>(RANK_ARGS);
+        } else {
+            k_rank_count<6><<<grid, RankCfg<6>::THREADS, 0, s->stream>>>(st->keys, st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->far_list, st->far_n);
+            k_far_sort<<<1, 1024, 0, s->stream>>>(st->far_list, st->far_n);
+            k_rank_place<6, false><<<grid, RankCfg<6>::THREADS, 0, s->stream>>>(RANK_ARGS);
+        }
+        s->launches += 3;
+    } else if (n > 0) {
         if (st->cell_bits == 9) k_place<9><<<nb, 256, 0, s->stream>>>(st->keys, n, st->cellmeta, st->cnts, st->pstart, st->stab, st->fill, st->src_of, s->orig_id, s->orig_id_alt);
         else k_place<6><<<nb, 256, 0, s->stream>>>(st->keys, n, st->cellmeta, st->cnts, st->pstart, st->stab, st->fill, st->src_of, s->orig_id, s->orig_id_alt);
         s->launches += 1;
     }
+    st->prev_lay = pl;
+    st->lay = nl;
+    st->lay_valid = true;
+    st->bsum = bsum; st->bbase = bbase; st->active = active;
     s->g2p_inputs = false;  // position / mass planes of this layout: written by P2G_1 (orig_id_alt holds the slot-order
                             // ids already; the two id arrays are swapped when G2P has rewritten the records in slot order)
     st->box_cleared = false;
@@ -464,6 +842,53 @@ int bin_particles(MpmSolver* s)
     s->steps_since_sort = 0;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { s->err = std::string("bin launch: ") + cudaGetErrorString(e); return MPM_ERR_CUDA; }
+    return MPM_OK;
+}
+
+// Binning introspection (mpm_debug_last_sort on the cell path).  Valid between a bin phase and the next G2P (keys[] still
+// holds the keys that binning sorted by, in record order).  Re-runs the ranking kernels in verify mode: they write the
+// rank inside the cell of every record and compare the layout in place (src_of, ids) with the one they derive; the
+// permutation "cell-major position -> record index" is then assembled on the host from (key, rank).
+int bin_debug_last(MpmSolver* s, uint32_t* keys_before, uint32_t* perm, int64_t cap)
+{
+    BinState* st = s->bin;
+    if (!st || !s->sorted_valid || !st->lay_valid) { s->err = "no bin phase has run since the particles last moved"; return MPM_ERR_STATE; }
+    if (!use_stable(s)) { s->err = "binning introspection needs the stable ranking (one GPU, MPM_ATOMIC_BINNING unset)"; return MPM_ERR_STATE; }
+    const int64_t n = s->n;
+    if (cap < n) { s->err = "destination too small"; return MPM_ERR_INVALID; }
+    if (n == 0) return MPM_OK;
+    uint32_t *d_rank = nullptr, *d_bad = nullptr;
+    CKB(cudaMalloc(&d_rank, sizeof(uint32_t) * n));
+    CKB(cudaMalloc(&d_bad, sizeof(uint32_t)));
+    CKB(cudaMemsetAsync(d_bad, 0, sizeof(uint32_t), s->stream));
+    const int pl = st->prev_lay;
+    const RankGeom rg{st->nbx, st->nby, st->nbz};
+    const unsigned grid = rank_grid(st);
+#define VERIFY_ARGS st->keys, st->bsum2[pl], st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->far_list, st->far_n, st->cellmeta, st->cnts, \
+                    st->pstart, st->stab, st->fill, st->src_of, s->orig_id, s->orig_id_alt, d_rank, d_bad
+    if (st->cell_bits == 9) k_rank_place<9, true><<<grid, RankCfg<9>::THREADS, 0, s->stream>>>(VERIFY_ARGS);
+    else k_rank_place<6, true><<<grid, RankCfg<6>::THREADS, 0, s->stream>>>(VERIFY_ARGS);
+    std::vector<uint32_t> keys((size_t)n), rank((size_t)n);
+    uint32_t bad = 0;
+    CKB(cudaMemcpyAsync(keys.data(), st->keys, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s->stream));
+    CKB(cudaMemcpyAsync(rank.data(), d_rank, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s->stream));
+    CKB(cudaMemcpyAsync(&bad, d_bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    CKB(cudaStreamSynchronize(s->stream));
+    cudaFree(d_rank); cudaFree(d_bad);
+    if (bad) { s->err = "binning introspection: the layout in place differs from the re-derived one for " + std::to_string(bad) + " particles"; return MPM_ERR_STATE; }
+    if (keys_before) std::copy(keys.begin(), keys.end(), keys_before);
+    if (perm) {
+        std::vector<uint32_t> start((size_t)st->nslots + 1, 0u);
+        for (int64_t i = 0; i < n; ++i) start[keys[(size_t)i] + 1] += 1;
+        for (int64_t k = 0; k < st->nslots; ++k) start[(size_t)k + 1] += start[(size_t)k];
+        std::vector<uint8_t> seen((size_t)n, 0);
+        for (int64_t i = 0; i < n; ++i) {
+            const uint64_t p = (uint64_t)start[keys[(size_t)i]] + rank[(size_t)i];
+            if (p >= (uint64_t)start[keys[(size_t)i] + 1] || seen[p]) { s->err = "binning introspection: ranks inside a cell are not a permutation"; return MPM_ERR_STATE; }
+            seen[p] = 1;
+            perm[p] = (uint32_t)i;
+        }
+    }
     return MPM_OK;
 }
 

@@ -23,12 +23,27 @@ struct BinState {
     uint32_t* pstart = nullptr;      // [2 * nslots / 32] first slot of every chunk
     uint16_t* stab = nullptr;        // [2 * nslots / 32][16] per chunk: [0] irregular flag, [1..13] first slot of the rank-r row
                                      // relative to the chunk start, [14..15] the chunk start (one 32-B sector for k_place)
-    uint32_t* bsum = nullptr;        // [nblocks] particles per block
-    uint32_t* bbase = nullptr;       // [nblocks + 1] exclusive scan
-    uint32_t* fill = nullptr;        // [nslots] placement cursor
+    // per-block totals, their exclusive scan and the list of non-empty blocks, double-buffered: [lay] describes the current
+    // layout, [lay ^ 1] the previous one -- which is the order the records (and keys[]) are in when the next binning runs,
+    // and what its stable ranking walks (a block's particles = one contiguous run of old slots = one "tile")
+    uint32_t* bsum2[2] = {nullptr, nullptr};    // [nblocks + pad] particles per block
+    uint32_t* bbase2[2] = {nullptr, nullptr};   // [nblocks + 1 + pad] exclusive scan
+    uint32_t* active2[2] = {nullptr, nullptr};  // [nblocks] non-empty blocks, ascending
+    uint32_t* nact = nullptr;                   // [2] length of active2[k]
+    int lay = 0;
+    int prev_lay = 0;                // buffers the last binning used as the "previous layout" (= lay for a cold binning)
+    bool lay_valid = false;          // [lay] describes the order of the records (false after an upload / migration)
+    uint32_t* bsum = nullptr;        // = bsum2[lay]
+    uint32_t* bbase = nullptr;       // = bbase2[lay]
+    uint32_t* fill = nullptr;        // [nslots] placement cursor (atomic ranking only)
+    // stable ranking (k_rank_count / k_rank_place): particles of old block T that go to cell r of T's (B+2)^3 region
+    uint32_t* tcount = nullptr;      // [nblocks][(B+2)^3]; row T is valid while bsum2[previous][T] > 0
+    uint32_t* far_list = nullptr;    // [2][FAR_CAP] {old slot, key} of the particles that left their block's region ("far movers")
+    uint32_t* far_n = nullptr;       // [2]: [0] count of this binning, [1] binnings that fell back to atomic ranks (overflow of the list)
+    bool stable = true;              // rank inside a cell = order of the old slots (std::stable_sort); false: atomic cursor
     uint32_t* keys = nullptr;        // [pitch] cell key of each particle for the NEXT binning (slot order)
     uint32_t* src_of = nullptr;      // [pitch + 64] slot -> index of the particle's record (the records stay where G2P wrote them)
-    uint32_t* active = nullptr;      // [nblocks] non-empty blocks, ascending
+    uint32_t* active = nullptr;      // = active2[lay]
     uint32_t* misc = nullptr;        // BIN_MISC_WORDS counters
     int* box = nullptr;              // [12] cells: bounding box of the non-empty blocks (+ apron) of the current binning, and its
                                      // union with those since the last clear (what a sparse clear has to cover); see k_scan_blocks
@@ -39,6 +54,10 @@ int bin_create(MpmSolver* s);
 void bin_destroy(MpmSolver* s);
 int bin_particles(MpmSolver* s);
 int bin_g2p_inputs(MpmSolver* s);  // position / mass planes in slot order, when no P2G_1 ran since the binning
+// cell keys of the last binning's input (record order) and its permutation (cell-major rank -> input index), re-derived
+// by a verification run of the ranking kernels that also checks the layout in place against it
+int bin_debug_last(MpmSolver* s, uint32_t* keys_before, uint32_t* perm, int64_t cap);
+constexpr int FAR_CAP = 4096;
 
 // cell kernels (mpm_kernels_cell.cu)
 int cell_p2g1(MpmSolver* s);

@@ -50,10 +50,22 @@ struct ParticleView {
     __host__ __device__ __forceinline__ float& at(int k, int64_t i) const { return base[((i >> 5) << 9) + (k << 5) + (i & 31)]; }
 };
 
-// 64-byte particle records: field k of slot i at i * 16 + k (same field order as the planes)
+// 64-byte particle records (cell path): the 16 fields of a slot, contiguous, as four 16-byte quads
+//     (px py pz m) (vx vy vz c2) (c0 c1 c3 c4) (c6 c7 c5 c8)
+// The order is chosen for the packed fp32 instructions of sm_100 (FFMA2 / FMUL2 / FADD2 take aligned register pairs,
+// and an LDS.128 / LDG.128 lands a quad in four consecutive registers): (px, py), (vx, vy) and the (x, y) rows of the
+// three columns of C -- (c0, c1), (c3, c4), (c6, c7) -- each sit on an even offset, so the pairs the P2G kernels
+// multiply with need no register moves (with the plane order they cost ~60 MOVs per particle in P2G_1).
+// rec_pos(k) = offset of plane field k inside the record.
+__host__ __device__ __forceinline__ constexpr int rec_pos(int k)
+{
+    constexpr int pos[16] = {/*PX*/ 0, /*PY*/ 1, /*PZ*/ 2, /*VX*/ 4, /*VY*/ 5, /*VZ*/ 6, /*PM*/ 3,
+                             /*C0*/ 8, /*C1*/ 9, /*C2*/ 7, /*C3*/ 10, /*C4*/ 11, /*C5*/ 14, /*C6*/ 12, /*C7*/ 13, /*C8*/ 15};
+    return pos[k];
+}
 struct RecView {
     float* base;
-    __host__ __device__ __forceinline__ float& at(int k, int64_t i) const { return base[i * 16 + k]; }
+    __host__ __device__ __forceinline__ float& at(int k, int64_t i) const { return base[i * 16 + rec_pos(k)]; }
 };
 
 // ---- strict IEEE binary32 operators: the _rn intrinsics are never contracted into FMA by nvcc, so the

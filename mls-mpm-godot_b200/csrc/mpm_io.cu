@@ -140,11 +140,11 @@ __global__ void __launch_bounds__(256) k_rec_to_planes(const float4* __restrict_
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float* q = pv.rec(i);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float4 v = rec[4 * i + k];
-        q[(4 * k + 0) * GROUP] = v.x; q[(4 * k + 1) * GROUP] = v.y; q[(4 * k + 2) * GROUP] = v.z; q[(4 * k + 3) * GROUP] = v.w;
-    }
+    const float4 a = rec[4 * i], b = rec[4 * i + 1], c = rec[4 * i + 2], d = rec[4 * i + 3];  // (record layout: mpm_common.cuh)
+    q[PX * GROUP] = a.x; q[PY * GROUP] = a.y; q[PZ * GROUP] = a.z; q[PM * GROUP] = a.w;
+    q[VX * GROUP] = b.x; q[VY * GROUP] = b.y; q[VZ * GROUP] = b.z; q[C2 * GROUP] = b.w;
+    q[C0 * GROUP] = c.x; q[C1 * GROUP] = c.y; q[C3 * GROUP] = c.z; q[C4 * GROUP] = c.w;
+    q[C6 * GROUP] = d.x; q[C7 * GROUP] = d.y; q[C5 * GROUP] = d.z; q[C8 * GROUP] = d.w;
 }
 void launch_rec_to_planes(RecView rv, ParticleView pv, int64_t n, cudaStream_t st)
 {

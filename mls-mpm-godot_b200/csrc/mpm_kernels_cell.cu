@@ -23,6 +23,11 @@
 #include "mpm_particle_math.cuh"
 #include "mpm_tile.cuh"
 
+// resident CTAs per SM the P2G kernels are compiled for (3 -> 168 registers, 4 -> 128 registers with spills)
+#ifndef MPM_P2G_CTAS
+#define MPM_P2G_CTAS 3
+#endif
+
 namespace mpm {
 
 KeyGeom bin_key_geom(const MpmSolver* s);
@@ -74,6 +79,21 @@ __device__ __forceinline__ void cell_axis(float p, float fc, float w[3], float d
     w[2] = 0.5f * b * b;
     d[0] = -1.0f - cd; d[1] = -cd; d[2] = 1.0f - cd;
 }
+
+// The same for two axes at once (x and y as an aligned pair): every operation is one packed instruction.
+__device__ __forceinline__ void cell_axis2(float2 p, float2 fc, float2 w[3], float2 d[3])
+{
+    const float2 h = make_float2(0.5f, 0.5f), one = make_float2(1.0f, 1.0f);
+    const float2 cd = __fadd2_rn(__fadd2_rn(p, make_float2(-fc.x, -fc.y)), make_float2(-0.5f, -0.5f));
+    const float2 ncd = make_float2(-cd.x, -cd.y);
+    const float2 a = __fadd2_rn(h, ncd), b = __fadd2_rn(h, cd);
+    w[0] = __fmul2_rn(__fmul2_rn(h, a), a);
+    w[1] = __ffma2_rn(ncd, cd, make_float2(0.75f, 0.75f));
+    w[2] = __fmul2_rn(__fmul2_rn(h, b), b);
+    d[0] = __fadd2_rn(ncd, make_float2(-1.0f, -1.0f)); d[1] = ncd; d[2] = __fadd2_rn(ncd, one);
+}
+// a scalar as both halves of a pair: ptxas folds this into the packed instruction's scalar-operand form (`R.F32`), no move
+__device__ __forceinline__ float2 bc(float s) { return make_float2(s, s); }
 
 // ---------------------------------------------------------------- walking a block's chunks, software-pipelined
 // ncu (first cell-kernel capture, summarised in DESIGN.md section 4): with 168 registers per thread only 12 warps fit on
@@ -184,13 +204,14 @@ __device__ __forceinline__ void walk_chunks(const CellArgs& a, int b, int lane, 
 template <int B>
 struct CellPos {  // the cell (id L inside the block) this lane owns in the current chunk
     int base;
-    float fcx, fcy, fcz;
+    float2 fcxy;  // (x, y) of the cell as an aligned pair: the x and y weights are computed packed
+    float fcz;
     __device__ __forceinline__ void set(const Tile<B>& tl, int L)
     {
         constexpr int LOGB = CellCfg<B>::LOGB;
         const int lx = L >> (2 * LOGB), ly = (L >> LOGB) & (B - 1), lz = L & (B - 1);
         base = lx * Tile<B>::PX + ly * Tile<B>::PY + lz;
-        fcx = (float)(tl.ox + 1 + lx); fcy = (float)(tl.oy + 1 + ly); fcz = (float)(tl.oz + 1 + lz);
+        fcxy = make_float2((float)(tl.ox + 1 + lx), (float)(tl.oy + 1 + ly)); fcz = (float)(tl.oz + 1 + lz);
     }
 };
 
@@ -242,12 +263,20 @@ struct RowStage {
         __syncwarp();  // the pieces of a record were copied by four different lanes
         rd = pending ? wr : wr ^ 1;  // (wr = where the next request goes = the older of two outstanding rows)
     }
-    // record t of the current row: (px, py, pz, vx) (vy, vz, m, c0) (c1..c4) (c5..c8)
+    // record t of the current row: (px, py, pz, m) (vx, vy, vz, c2) (c0, c1, c3, c4) (c6, c7, c5, c8)
     __device__ __forceinline__ void load(uint32_t t, float4& a, float4& b, float4& c, float4& d) const
     {
         const float4* r = reinterpret_cast<const float4*>(buf + rd * WORDS) + 4 * t;
         const uint32_t s = (t >> 1) & 3u;
         a = r[s]; b = r[1u ^ s]; c = r[2u ^ s]; d = r[3u ^ s];
+    }
+    // the same without the velocity quad (P2G_2): returns c2, the one field of that quad it needs
+    __device__ __forceinline__ float load_no_vel(uint32_t t, float4& a, float4& c, float4& d) const
+    {
+        const float4* r = reinterpret_cast<const float4*>(buf + rd * WORDS) + 4 * t;
+        const uint32_t s = (t >> 1) & 3u;
+        a = r[s]; c = r[2u ^ s]; d = r[3u ^ s];
+        return reinterpret_cast<const float*>(r + (1u ^ s))[3];
     }
 };
 
@@ -261,14 +290,22 @@ struct P2G1Body {
     int (*tile)[TL::WORDS];
     RowStage st;
     CellPos<B> cp;
-    float2 axy[27], azm[27];  // accumulators packed for FFMA2: (momentum x, momentum y) and (momentum z, mass)
+    // 108 accumulators, packed for FFMA2 without register moves: (momentum x, momentum y) per node; momentum z and mass
+    // per (gx, gy) as a pair over the nodes gz = 0, 1 plus a scalar for gz = 2.  [first version: (z, mass) per node, which
+    // needs the pair (q_z, 1.0) built with a MOV for every node, and the record's old field order split (c0, c1), (c6, c7)
+    // and (vx, vy) across odd register offsets: 92 of 479 warp-instructions per row were register moves]
+    float2 axy[27];
+    float2 az01[9], am01[9];
+    float az2[9], am2[9];
     __device__ __forceinline__ P2G1Body(const DevParams& P_, const ParticleView& pv_, const TL& tl_, int (*tile_)[TL::WORDS], const RowStage& st_)
         : P(P_), pv(pv_), tl(tl_), tile(tile_), st(st_) {}
     __device__ __forceinline__ void begin_chunk(int L)
     {
         cp.set(tl, L);
 #pragma unroll
-        for (int n = 0; n < 27; ++n) { axy[n] = make_float2(0.0f, 0.0f); azm[n] = make_float2(0.0f, 0.0f); }
+        for (int n = 0; n < 27; ++n) axy[n] = make_float2(0.0f, 0.0f);
+#pragma unroll
+        for (int g = 0; g < 9; ++g) { az01[g] = make_float2(0.0f, 0.0f); am01[g] = make_float2(0.0f, 0.0f); az2[g] = 0.0f; am2[g] = 0.0f; }
     }
     __device__ __forceinline__ void fetch(uint32_t base, unsigned mask, int kind) { st.fetch(base, mask, kind); }
     __device__ __forceinline__ void hint_chunk(uint32_t slot) { st.hint_chunk(slot); }
@@ -277,39 +314,40 @@ struct P2G1Body {
     __device__ __forceinline__ void compute(uint32_t i, uint32_t t)
     {
         float4 ra, rb, rc, rd4;
-        st.load(t, ra, rb, rc, rd4);
-        const float px = ra.x, py = ra.y, pz = ra.z;
-        const float vx = ra.w, vy = rb.x, vz = rb.y;
+        st.load(t, ra, rb, rc, rd4);  // (px, py, pz, m) (vx, vy, vz, c2) (c0, c1, c3, c4) (c6, c7, c5, c8)
         // G2P needs the position and the mass of slot i
-        pv.at(PX, i) = px; pv.at(PY, i) = py; pv.at(PZ, i) = pz; pv.at(PM, i) = rb.z;
-        const float ms = rb.z * P.fmult;  // mass in fixed-point units
-        const float cm[9] = {rb.w, rc.x, rc.y, rc.z, rc.w, rd4.x, rd4.y, rd4.z, rd4.w};
-        float wx[3], wy[3], wz[3], dx[3], dy[3], dz[3];
-        cell_axis(px, cp.fcx, wx, dx); cell_axis(py, cp.fcy, wy, dy); cell_axis(pz, cp.fcz, wz, dz);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) wx[k] *= ms;
-        // node value = mc * (v + C d) with mc = w * m; x and y run packed (FFMA2: two FMAs per issue slot), z rides with
-        // the mass as (mc * qz, mc * 1)
-        const float2 c01 = make_float2(cm[0], cm[1]), c34 = make_float2(cm[3], cm[4]), c67 = make_float2(cm[6], cm[7]);
-        const float2 wz2[3] = {make_float2(wz[0], wz[0]), make_float2(wz[1], wz[1]), make_float2(wz[2], wz[2])};
-        const float2 dz2[3] = {make_float2(dz[0], dz[0]), make_float2(dz[1], dz[1]), make_float2(dz[2], dz[2])};
+        pv.at(PX, i) = ra.x; pv.at(PY, i) = ra.y; pv.at(PZ, i) = ra.z; pv.at(PM, i) = ra.w;
+        const float ms = ra.w * P.fmult;  // mass in fixed-point units
+        float2 wxy[3], dxy[3];            // (x, y) weights and node distances, computed packed
+        float wz[3], dz[3];
+        cell_axis2(make_float2(ra.x, ra.y), cp.fcxy, wxy, dxy);
+        cell_axis(ra.z, cp.fcz, wz, dz);
+        const float2 vxy = make_float2(rb.x, rb.y), c01 = make_float2(rc.x, rc.y), c34 = make_float2(rc.z, rc.w), c67 = make_float2(rd4.x, rd4.y);
+        const float vz = rb.z, c2 = rb.w, c5 = rd4.z, c8 = rd4.w;
+        const float2 wz01 = make_float2(wz[0], wz[1]), dz01 = make_float2(dz[0], dz[1]);
+        // node value = mc * (v + C d) with mc = w * m.  (x, y) run as one pair per node; z and the mass as one pair per
+        // two nodes (gz = 0, 1) and a scalar (gz = 2).  Scalars enter the packed instructions through their scalar-operand
+        // form.
 #pragma unroll
         for (int gx = 0; gx < 3; ++gx) {
-            const float2 q0 = __ffma2_rn(c01, make_float2(dx[gx], dx[gx]), make_float2(vx, vy));
-            const float qz0 = fmaf(cm[2], dx[gx], vz);
+            const float wxm = wxy[gx].x * ms;
+            const float2 q0 = __ffma2_rn(c01, bc(dxy[gx].x), vxy);
+            const float qz0 = fmaf(c2, dxy[gx].x, vz);
 #pragma unroll
             for (int gy = 0; gy < 3; ++gy) {
-                const float2 q1 = __ffma2_rn(c34, make_float2(dy[gy], dy[gy]), q0);
-                const float qz1 = fmaf(cm[5], dy[gy], qz0);
-                const float wxy = wx[gx] * wy[gy];
-                const float2 wxy2 = make_float2(wxy, wxy);
-#pragma unroll
-                for (int gz = 0; gz < 3; ++gz) {
-                    const int n = (gx * 3 + gy) * 3 + gz;
-                    const float2 mc2 = __fmul2_rn(wxy2, wz2[gz]);
-                    axy[n] = __ffma2_rn(mc2, __ffma2_rn(c67, dz2[gz], q1), axy[n]);
-                    azm[n] = __ffma2_rn(mc2, make_float2(fmaf(cm[8], dz[gz], qz1), 1.0f), azm[n]);
-                }
+                const int g = gx * 3 + gy;
+                const float2 q1 = __ffma2_rn(c34, bc(dxy[gy].y), q0);
+                const float qz1 = fmaf(c5, dxy[gy].y, qz0);
+                const float wgt = wxm * wxy[gy].y;
+                const float2 mc01 = __fmul2_rn(bc(wgt), wz01);
+                const float mc2 = wgt * wz[2];
+                az01[g] = __ffma2_rn(mc01, __ffma2_rn(bc(c8), dz01, bc(qz1)), az01[g]);
+                az2[g] = fmaf(mc2, fmaf(c8, dz[2], qz1), az2[g]);
+                am01[g] = __fadd2_rn(am01[g], mc01);
+                am2[g] += mc2;
+                axy[3 * g + 0] = __ffma2_rn(bc(mc01.x), __ffma2_rn(c67, bc(dz[0]), q1), axy[3 * g + 0]);
+                axy[3 * g + 1] = __ffma2_rn(bc(mc01.y), __ffma2_rn(c67, bc(dz[1]), q1), axy[3 * g + 1]);
+                axy[3 * g + 2] = __ffma2_rn(bc(mc2), __ffma2_rn(c67, bc(dz[2]), q1), axy[3 * g + 2]);
             }
         }
     }
@@ -322,19 +360,21 @@ struct P2G1Body {
             for (int gy = 0; gy < 3; ++gy)
 #pragma unroll
                 for (int gz = 0; gz < 3; ++gz) {
-                    const int n = (gx * 3 + gy) * 3 + gz;
+                    const int g = gx * 3 + gy, n = g * 3 + gz;
                     const int idx = cp.base + gx * TL::PX + gy * TL::PY + gz;
-                    atomicAdd(&tile[3][idx], __float2int_rz(azm[n].y));
+                    const float mz = gz == 0 ? az01[g].x : gz == 1 ? az01[g].y : az2[g];
+                    const float mm = gz == 0 ? am01[g].x : gz == 1 ? am01[g].y : am2[g];
+                    atomicAdd(&tile[3][idx], __float2int_rz(mm));
                     atomicAdd(&tile[0][idx], __float2int_rz(axy[n].x));
                     atomicAdd(&tile[1][idx], __float2int_rz(axy[n].y));
-                    atomicAdd(&tile[2][idx], __float2int_rz(azm[n].x));
+                    atomicAdd(&tile[2][idx], __float2int_rz(mz));
                 }
     }
     __device__ __forceinline__ void finish() {}
 };
 
 template <int B>
-__global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? 3 : 6) k_p2g1_cell(DevParams P, TileGeom g, ParticleView pv, CellArgs a,
+__global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? MPM_P2G_CTAS : 6) k_p2g1_cell(DevParams P, TileGeom g, ParticleView pv, CellArgs a,
                                                                                      int* __restrict__ grid, const float* __restrict__ rec,
                                                                                      const uint32_t* __restrict__ src_of)
 {
@@ -371,6 +411,14 @@ __global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? 3 : 6) k_p2g1_
 // ---------------------------------------------------------------- P2G_2
 __device__ __forceinline__ float cell_eos_pow(float x, const DevParams& P)
 {
+    if (P.eos_pi == 7) {  // the GPU variant's exponent (H:84): 4 multiplications, no loop
+        const float x2 = x * x, x3 = x2 * x;
+        return (x3 * x3) * x;
+    }
+    if (P.eos_pi == 4) {  // the CPU variants' exponent (F:40)
+        const float x2 = x * x;
+        return x2 * x2;
+    }
     if (P.eos_pi > 0) {
         float r = x;
         for (int k = 1; k < P.eos_pi; ++k) r *= x;
@@ -389,8 +437,13 @@ struct P2G2Body {
     float inv_rest;
     RowStage st;
     CellPos<B> cp;
-    float gm[27], az[27];
-    float2 axy[27];  // momentum x, y packed for FFMA2
+    // node masses of the cell's stencil: per (gx, gz) the pair over gy = 0, 1 and a scalar for gy = 2 (the density sum
+    // then runs packed); 81 accumulators: (x, y) per node, z per (gx, gy) as a pair over gz = 0, 1 and a scalar for gz = 2
+    float2 gm01[9];
+    float gm2[9];
+    float2 axy[27];
+    float2 az01[9];
+    float az2[9];
     __device__ __forceinline__ P2G2Body(const DevParams& P_, const TL& tl_, int (*tile_)[TL::WORDS], const float* tmass_, const RowStage& st_)
         : P(P_), tl(tl_), tile(tile_), tmass(tmass_), inv_rest(1.0f / P_.rest_density), st(st_) {}
     __device__ __forceinline__ void begin_chunk(int L)
@@ -399,11 +452,15 @@ struct P2G2Body {
 #pragma unroll
         for (int gx = 0; gx < 3; ++gx)
 #pragma unroll
-            for (int gy = 0; gy < 3; ++gy)
+            for (int gz = 0; gz < 3; ++gz) {
+                const float* t = tmass + cp.base + gx * TL::PX + gz;
+                gm01[gx * 3 + gz] = make_float2(t[0], t[TL::PY]);
+                gm2[gx * 3 + gz] = t[2 * TL::PY];
+            }
 #pragma unroll
-                for (int gz = 0; gz < 3; ++gz) gm[(gx * 3 + gy) * 3 + gz] = tmass[cp.base + gx * TL::PX + gy * TL::PY + gz];
+        for (int n = 0; n < 27; ++n) axy[n] = make_float2(0.0f, 0.0f);
 #pragma unroll
-        for (int n = 0; n < 27; ++n) { axy[n] = make_float2(0.0f, 0.0f); az[n] = 0.0f; }
+        for (int g = 0; g < 9; ++g) { az01[g] = make_float2(0.0f, 0.0f); az2[g] = 0.0f; }
     }
     __device__ __forceinline__ void fetch(uint32_t base, unsigned mask, int kind) { st.fetch(base, mask, kind); }
     __device__ __forceinline__ void hint_chunk(uint32_t slot) { st.hint_chunk(slot); }
@@ -411,54 +468,50 @@ struct P2G2Body {
     __device__ __forceinline__ void take(int pending) { st.take(pending); }
     __device__ __forceinline__ void compute(uint32_t, uint32_t t)
     {
-        float4 ra, rb, rc, rd4;
-        st.load(t, ra, rb, rc, rd4);
-        const float px = ra.x, py = ra.y, pz = ra.z, mass = rb.z;
-        const float cm[9] = {rb.w, rc.x, rc.y, rc.z, rc.w, rd4.x, rd4.y, rd4.z, rd4.w};
-        float wx[3], wy[3], wz[3], dx[3], dy[3], dz[3];
-        cell_axis(px, cp.fcx, wx, dx); cell_axis(py, cp.fcy, wy, dy); cell_axis(pz, cp.fcz, wz, dz);
+        float4 ra, rc, rd4;
+        const float c2 = st.load_no_vel(t, ra, rc, rd4);  // (px, py, pz, m) . (c0, c1, c3, c4) (c6, c7, c5, c8)
+        const float mass = ra.w;
+        float2 wxy[3], dxy[3];
+        float wz[3], dz[3];
+        cell_axis2(make_float2(ra.x, ra.y), cp.fcxy, wxy, dxy);
+        cell_axis(ra.z, cp.fcz, wz, dz);
+        // density = sum over the stencil of mass * weight, by sum factorisation (z, then y, then x); rows gy = 0, 1 packed
         float density = 0.0f;
 #pragma unroll
         for (int gx = 0; gx < 3; ++gx) {
-            float sx = 0.0f;
-#pragma unroll
-            for (int gy = 0; gy < 3; ++gy) {
-                const int n = (gx * 3 + gy) * 3;
-                const float row = fmaf(gm[n + 2], wz[2], fmaf(gm[n + 1], wz[1], gm[n] * wz[0]));
-                sx = fmaf(row, wy[gy], sx);
-            }
-            density = fmaf(sx, wx[gx], density);
+            const float2 r01 = __ffma2_rn(gm01[gx * 3 + 2], bc(wz[2]), __ffma2_rn(gm01[gx * 3 + 1], bc(wz[1]), __fmul2_rn(gm01[gx * 3], bc(wz[0]))));
+            const float r2 = fmaf(gm2[gx * 3 + 2], wz[2], fmaf(gm2[gx * 3 + 1], wz[1], gm2[gx * 3] * wz[0]));
+            const float sx = fmaf(r2, wxy[2].y, fmaf(r01.y, wxy[1].y, r01.x * wxy[0].y));
+            density = fmaf(sx, wxy[gx].x, density);
         }
         // eq_16_term_0 = -volume * 4 * stress * dt (symmetric), pre-scaled to fixed-point units
         const float volume = __fdividef(mass, density);
         const float pr = P.eos_k * (cell_eos_pow(density * inv_rest, P) - 1.0f);
         const float pressure = fmaxf(-0.1f, pr);
         const float s = -volume * 4.0f * P.dt * P.fmult;
-        const float mu = P.visc;
-        const float e00 = s * fmaf(2.0f * mu, cm[0], -pressure), e11 = s * fmaf(2.0f * mu, cm[4], -pressure),
-                    e22 = s * fmaf(2.0f * mu, cm[8], -pressure);
-        const float e01 = s * mu * (cm[1] + cm[3]), e02 = s * mu * (cm[2] + cm[6]), e12 = s * mu * (cm[5] + cm[7]);
-        // node value = w * (E d), E symmetric; x and y run packed (FFMA2)
+        const float smu = s * P.visc, sp = s * pressure;
+        const float e00 = fmaf(2.0f * smu, rc.x, -sp), e11 = fmaf(2.0f * smu, rc.w, -sp), e22 = fmaf(2.0f * smu, rd4.w, -sp);
+        const float e01 = smu * (rc.y + rc.z), e02 = smu * (c2 + rd4.x), e12 = smu * (rd4.z + rd4.y);
+        // node value = w * (E d), E symmetric; (x, y) as one pair per node, z as a pair over gz = 0, 1 and a scalar
         const float2 ex = make_float2(e00, e01), ey = make_float2(e01, e11), ez = make_float2(e02, e12);
-        const float2 wz2[3] = {make_float2(wz[0], wz[0]), make_float2(wz[1], wz[1]), make_float2(wz[2], wz[2])};
-        const float2 dz2[3] = {make_float2(dz[0], dz[0]), make_float2(dz[1], dz[1]), make_float2(dz[2], dz[2])};
+        const float2 wz01 = make_float2(wz[0], wz[1]), dz01 = make_float2(dz[0], dz[1]);
 #pragma unroll
         for (int gx = 0; gx < 3; ++gx) {
-            const float2 f0 = __fmul2_rn(ex, make_float2(dx[gx], dx[gx]));
-            const float fz0 = e02 * dx[gx];
+            const float2 f0 = __fmul2_rn(ex, bc(dxy[gx].x));
+            const float fz0 = e02 * dxy[gx].x;
 #pragma unroll
             for (int gy = 0; gy < 3; ++gy) {
-                const float2 f1 = __ffma2_rn(ey, make_float2(dy[gy], dy[gy]), f0);
-                const float fz1 = fmaf(e12, dy[gy], fz0);
-                const float wxy = wx[gx] * wy[gy];
-                const float2 wxy2 = make_float2(wxy, wxy);
-#pragma unroll
-                for (int gz = 0; gz < 3; ++gz) {
-                    const int n = (gx * 3 + gy) * 3 + gz;
-                    const float2 w2 = __fmul2_rn(wxy2, wz2[gz]);
-                    axy[n] = __ffma2_rn(w2, __ffma2_rn(ez, dz2[gz], f1), axy[n]);
-                    az[n] = fmaf(w2.x, fmaf(e22, dz[gz], fz1), az[n]);
-                }
+                const int g = gx * 3 + gy;
+                const float2 f1 = __ffma2_rn(ey, bc(dxy[gy].y), f0);
+                const float fz1 = fmaf(e12, dxy[gy].y, fz0);
+                const float wgt = wxy[gx].x * wxy[gy].y;
+                const float2 w01 = __fmul2_rn(bc(wgt), wz01);
+                const float w2 = wgt * wz[2];
+                az01[g] = __ffma2_rn(w01, __ffma2_rn(bc(e22), dz01, bc(fz1)), az01[g]);
+                az2[g] = fmaf(w2, fmaf(e22, dz[2], fz1), az2[g]);
+                axy[3 * g + 0] = __ffma2_rn(bc(w01.x), __ffma2_rn(ez, bc(dz[0]), f1), axy[3 * g + 0]);
+                axy[3 * g + 1] = __ffma2_rn(bc(w01.y), __ffma2_rn(ez, bc(dz[1]), f1), axy[3 * g + 1]);
+                axy[3 * g + 2] = __ffma2_rn(bc(w2), __ffma2_rn(ez, bc(dz[2]), f1), axy[3 * g + 2]);
             }
         }
     }
@@ -471,18 +524,19 @@ struct P2G2Body {
             for (int gy = 0; gy < 3; ++gy)
 #pragma unroll
                 for (int gz = 0; gz < 3; ++gz) {
-                    const int n = (gx * 3 + gy) * 3 + gz;
+                    const int g = gx * 3 + gy, n = g * 3 + gz;
                     const int idx = cp.base + gx * TL::PX + gy * TL::PY + gz;
+                    const float mz = gz == 0 ? az01[g].x : gz == 1 ? az01[g].y : az2[g];
                     atomicAdd(&tile[0][idx], __float2int_rz(axy[n].x));
                     atomicAdd(&tile[1][idx], __float2int_rz(axy[n].y));
-                    atomicAdd(&tile[2][idx], __float2int_rz(az[n]));
+                    atomicAdd(&tile[2][idx], __float2int_rz(mz));
                 }
     }
     __device__ __forceinline__ void finish() {}
 };
 
 template <int B>
-__global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? 3 : 6) k_p2g2_cell(DevParams P, TileGeom g, ParticleView pv, CellArgs a,
+__global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? MPM_P2G_CTAS : 6) k_p2g2_cell(DevParams P, TileGeom g, ParticleView pv, CellArgs a,
                                                                                      int* __restrict__ grid, const float* __restrict__ rec,
                                                                                      const uint32_t* __restrict__ src_of)
 {
@@ -573,36 +627,40 @@ struct G2PBody {
         // The particle sits in the cell its thread owns (that is what the binning key says), so the cell coordinate is
         // trunc(p): taking it from the position frees three registers here (G2P: 20 -> 4 bytes of spills, -1 %; in the
         // P2G kernels the same change was slower, they keep the per-thread floats).
-        cell_axis(old[0], truncf(old[0]), wx, dx); cell_axis(old[1], truncf(old[1]), wy, dy); cell_axis(old[2], truncf(old[2]), wz, dz);
+        float2 wxy[3], dxy[3];
+        cell_axis2(make_float2(old[0], old[1]), make_float2(truncf(old[0]), truncf(old[1])), wxy, dxy);
+        cell_axis(old[2], truncf(old[2]), wz, dz);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { wx[k] = wxy[k].x; wy[k] = wxy[k].y; dx[k] = dxy[k].x; dy[k] = dxy[k].y; }
         // Sum factorisation (z, then y, then x) with the x and y components packed: fma.rn.f32x2 (FFMA2, new on sm_100)
         // does two FMAs per issue slot, and this loop is issue-bound (ncu: 59 % issue-active at 3 warps per scheduler).
+        // The z component rides as pairs too: (s_z, t_z) = sum over gz of (w_z, w_z d_z) * v_z, then (S_z, T_zz), then
+        // (v_z, B_zz) -- natural pairs whose other operand is a scalar [first version: scalar FFMAs, 39 more per particle].
         const float wdz[3] = {wz[0] * dz[0], wz[1] * dz[1], wz[2] * dz[2]};
-        const float2 wz2[3] = {make_float2(wz[0], wz[0]), make_float2(wz[1], wz[1]), make_float2(wz[2], wz[2])};
-        const float2 wdz2[3] = {make_float2(wdz[0], wdz[0]), make_float2(wdz[1], wdz[1]), make_float2(wdz[2], wdz[2])};
+        const float2 wwd[3] = {make_float2(wz[0], wdz[0]), make_float2(wz[1], wdz[1]), make_float2(wz[2], wdz[2])};
         float2 vxy = make_float2(0.f, 0.f), Bxxy = vxy, Byxy = vxy, Bzxy = vxy;  // (x, y) components of v and of B's columns
-        float vz = 0.f, Bxz = 0.f, Byz = 0.f, Bzz = 0.f;
+        float2 vzBzz = vxy;                                                      // (v_z, B_zz)
+        float Bxz = 0.f, Byz = 0.f;
 #pragma unroll
         for (int gx = 0; gx < 3; ++gx) {
-            float2 Sxy = make_float2(0.f, 0.f), Tyxy = Sxy, Tzxy = Sxy;
-            float Sz = 0.f, Tyz = 0.f, Tzz = 0.f;
+            float2 Sxy = make_float2(0.f, 0.f), Tyxy = Sxy, Tzxy = Sxy, SzTzz = Sxy;
+            float Tyz = 0.f;
 #pragma unroll
             for (int gy = 0; gy < 3; ++gy) {
                 const int n = (gx * 3 + gy) * 3;
-                const float2 sxy = __ffma2_rn(wz2[2], gxy[n + 2], __ffma2_rn(wz2[1], gxy[n + 1], __fmul2_rn(wz2[0], gxy[n])));
-                const float2 txy = __ffma2_rn(wdz2[2], gxy[n + 2], __ffma2_rn(wdz2[1], gxy[n + 1], __fmul2_rn(wdz2[0], gxy[n])));
-                const float sz = fmaf(wz[2], gvz[n + 2], fmaf(wz[1], gvz[n + 1], wz[0] * gvz[n]));
-                const float tz = fmaf(wdz[2], gvz[n + 2], fmaf(wdz[1], gvz[n + 1], wdz[0] * gvz[n]));
+                const float2 sxy = __ffma2_rn(bc(wz[2]), gxy[n + 2], __ffma2_rn(bc(wz[1]), gxy[n + 1], __fmul2_rn(bc(wz[0]), gxy[n])));
+                const float2 txy = __ffma2_rn(bc(wdz[2]), gxy[n + 2], __ffma2_rn(bc(wdz[1]), gxy[n + 1], __fmul2_rn(bc(wdz[0]), gxy[n])));
+                const float2 stz = __ffma2_rn(wwd[2], bc(gvz[n + 2]), __ffma2_rn(wwd[1], bc(gvz[n + 1]), __fmul2_rn(wwd[0], bc(gvz[n]))));
                 const float wyd = wy[gy] * dy[gy];
-                const float2 wy2 = make_float2(wy[gy], wy[gy]), wyd2 = make_float2(wyd, wyd);
-                Sxy = __ffma2_rn(wy2, sxy, Sxy); Tyxy = __ffma2_rn(wyd2, sxy, Tyxy); Tzxy = __ffma2_rn(wy2, txy, Tzxy);
-                Sz = fmaf(wy[gy], sz, Sz); Tyz = fmaf(wyd, sz, Tyz); Tzz = fmaf(wy[gy], tz, Tzz);
+                Sxy = __ffma2_rn(bc(wy[gy]), sxy, Sxy); Tyxy = __ffma2_rn(bc(wyd), sxy, Tyxy); Tzxy = __ffma2_rn(bc(wy[gy]), txy, Tzxy);
+                SzTzz = __ffma2_rn(bc(wy[gy]), stz, SzTzz); Tyz = fmaf(wyd, stz.x, Tyz);
             }
             const float wxd = wx[gx] * dx[gx];
-            const float2 wx2 = make_float2(wx[gx], wx[gx]), wxd2 = make_float2(wxd, wxd);
-            vxy = __ffma2_rn(wx2, Sxy, vxy); Bxxy = __ffma2_rn(wxd2, Sxy, Bxxy);
-            Byxy = __ffma2_rn(wx2, Tyxy, Byxy); Bzxy = __ffma2_rn(wx2, Tzxy, Bzxy);
-            vz = fmaf(wx[gx], Sz, vz); Bxz = fmaf(wxd, Sz, Bxz); Byz = fmaf(wx[gx], Tyz, Byz); Bzz = fmaf(wx[gx], Tzz, Bzz);
+            vxy = __ffma2_rn(bc(wx[gx]), Sxy, vxy); Bxxy = __ffma2_rn(bc(wxd), Sxy, Bxxy);
+            Byxy = __ffma2_rn(bc(wx[gx]), Tyxy, Byxy); Bzxy = __ffma2_rn(bc(wx[gx]), Tzxy, Bzxy);
+            vzBzz = __ffma2_rn(bc(wx[gx]), SzTzz, vzBzz); Bxz = fmaf(wxd, SzTzz.x, Bxz); Byz = fmaf(wx[gx], Tyz, Byz);
         }
+        const float vz = vzBzz.x, Bzz = vzBzz.y;
         float v[3] = {vxy.x, vxy.y, vz};
         const float Bx[3] = {Bxxy.x, Bxxy.y, Bxz}, By[3] = {Byxy.x, Byxy.y, Byz}, Bz[3] = {Bzxy.x, Bzxy.y, Bzz};
         const float Bm[9] = {Bx[0], Bx[1], Bx[2], By[0], By[1], By[2], Bz[0], Bz[1], Bz[2]};
@@ -624,10 +682,10 @@ struct G2PBody {
         }
         // one 64-byte record per particle (field order of the planes): the next step's P2G kernels read it from here
         float4* q = rec + 4 * (size_t)i;
-        q[0] = make_float4(np[0], np[1], np[2], v[0]);
-        q[1] = make_float4(v[1], v[2], cur[3], cm[0]);
-        q[2] = make_float4(cm[1], cm[2], cm[3], cm[4]);
-        q[3] = make_float4(cm[5], cm[6], cm[7], cm[8]);
+        q[0] = make_float4(np[0], np[1], np[2], cur[3]);
+        q[1] = make_float4(v[0], v[1], v[2], cm[2]);
+        q[2] = make_float4(cm[0], cm[1], cm[3], cm[4]);
+        q[3] = make_float4(cm[6], cm[7], cm[5], cm[8]);
         if constexpr (COMM) {
             if (!stays) {
                 const uint32_t slot = atomicAdd(mg.cnt + side, 1u);

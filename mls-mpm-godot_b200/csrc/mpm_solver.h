@@ -79,6 +79,7 @@ int sort_create(MpmSolver* s);
 void sort_destroy(MpmSolver* s);
 int sort_particles(MpmSolver* s);
 int sort_debug_last(MpmSolver* s, uint32_t* keys_before, uint32_t* perm, int64_t cap);
+int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], int64_t n, int first_bit, int key_bits, cudaStream_t stream, int64_t* launches, std::string* err);
 // tiled kernels (mpm_kernels_tiled.cu)
 int tiled_p2g1(MpmSolver* s);
 int tiled_p2g2(MpmSolver* s);

@@ -20,6 +20,9 @@
 // Per pass (<= 8 key bits): k_tile_hist (per-tile digit counts) -> k_scan_rows (one CTA per digit scans
 // its counts across tiles) -> k_scan_bins -> k_scatter (stable in-tile ranking with __match_any_sync,
 // no atomics on the ranking path).  Then k_reorder gathers the 16 particle planes through the permutation.
+#include <algorithm>
+#include <string>
+
 #include "mpm_kernels.h"
 #include "mpm_solver.h"
 #include "mpm_tile.cuh"
@@ -416,6 +419,40 @@ int sort_debug_last(MpmSolver* s, uint32_t* keys_before, uint32_t* perm, int64_t
     if (perm) CKS(cudaMemcpyAsync(perm, st->vals[st->final_buf], sizeof(uint32_t) * st->last_n, cudaMemcpyDeviceToHost, s->stream));
     CKS(cudaStreamSynchronize(s->stream));
     return MPM_OK;
+}
+
+// ---------------------------------------------------------------- the radix sort on its own
+// Stable LSD radix sort of (key, value) pairs on key bits [first_bit, first_bit + key_bits), in passes of at most 8
+// bits (the kernels above).  keys[2] / vals[2] are ping-pong buffers of n entries, input in [0]; returns the index of
+// the buffer that holds the result.  Used by the cell path's cold binning (mpm_bin.cu), where a particle set arrives
+// in arbitrary order and the first layout has to be the stable sort by cell key.
+int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], int64_t n, int first_bit, int key_bits, cudaStream_t stream, int64_t* launches, std::string* err)
+{
+    if (n <= 0 || key_bits <= 0) return 0;
+    const int64_t ntiles = (n + SORT_TILE - 1) / SORT_TILE;
+    uint32_t *tile_hist = nullptr, *bin_total = nullptr, *bin_base = nullptr;
+    if (cudaMalloc(&tile_hist, sizeof(uint32_t) * MAX_BINS * ntiles) != cudaSuccess || cudaMalloc(&bin_total, sizeof(uint32_t) * MAX_BINS) != cudaSuccess ||
+        cudaMalloc(&bin_base, sizeof(uint32_t) * MAX_BINS) != cudaSuccess) {
+        cudaFree(tile_hist); cudaFree(bin_total); cudaFree(bin_base);
+        if (err) *err = "radix sort: out of device memory";
+        return -1;
+    }
+    const int passes = (key_bits + 7) / 8, per = (key_bits + passes - 1) / passes;
+    int cur = 0;
+    for (int p = 0; p < passes; ++p) {
+        const int bits = std::min(per, key_bits - p * per);
+        if (bits <= 0) break;
+        const int shift = first_bit + p * per, bins = 1 << bits;
+        k_tile_hist<<<(unsigned)ntiles, SORT_THREADS, 0, stream>>>(keys[cur], n, shift, bins, ntiles, tile_hist);
+        k_scan_rows<<<bins, 256, 0, stream>>>(tile_hist, ntiles, bin_total);
+        k_scan_bins<<<1, 32, 0, stream>>>(bin_total, bins, bin_base);
+        k_scatter<<<(unsigned)ntiles, SORT_THREADS, 0, stream>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, shift, bins, ntiles, tile_hist, bin_base);
+        if (launches) *launches += 4;
+        cur ^= 1;
+    }
+    cudaStreamSynchronize(stream);  // (cold path only) the work arrays are freed here
+    cudaFree(tile_hist); cudaFree(bin_total); cudaFree(bin_base);
+    return cur;
 }
 
 // accessors for the tiled kernels

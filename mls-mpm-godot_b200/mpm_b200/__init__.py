@@ -57,7 +57,7 @@ class MpmStats(C.Structure):
         ("ms_sort", C.c_float), ("ms_clear", C.c_float), ("ms_p2g1", C.c_float), ("ms_p2g2", C.c_float),
         ("ms_update", C.c_float), ("ms_g2p", C.c_float), ("ms_exchange", C.c_float), ("ms_step", C.c_float),
         ("kernel_path", C.c_int32), ("overflow", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
-        ("local_particles", C.c_int64), ("migrated", C.c_int64), ("slab_jump_clamps", C.c_int64),
+        ("local_particles", C.c_int64), ("migrated", C.c_int64), ("slab_jump_clamps", C.c_int64), ("unordered_binnings", C.c_int64),
     ]
 
 
@@ -316,6 +316,13 @@ class Solver:
         keys, perm = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
         self._ck(self._L.mpm_debug_last_sort(self._h, keys.ctypes.data_as(C.c_void_p), perm.ctypes.data_as(C.c_void_p), n))
         return keys, perm
+
+    def record_ids(self):
+        """Original index of the particle in each record, in the order `last_sort()` reports its keys in."""
+        n = self.num_particles
+        ids = np.zeros(n, np.uint32)
+        self._ck(self._L.mpm_download_ids(self._h, ids.ctypes.data_as(C.c_void_p), n))
+        return ids
 
     def stream(self):
         sp = C.c_void_p()

@@ -64,3 +64,22 @@ def assert_bit_equal(a, b, what):
 def rel_err(a, b):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def elem_err(a, b, atol):
+    """Element-wise error: max over elements of |a - b| / (atol + |b|).  Unlike rel_err (a norm-wise bound: max |a - b| over
+    max |b|) a small entry cannot hide behind a large one; `atol` is the magnitude below which an entry is noise."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float((np.abs(a - b) / (atol + np.abs(b))).max())
+
+
+def block_major_key(op, cell_index, B):
+    """The solver's bin key of the oracle's cell index (orc_cell_keys: (cx * Ry + cy) * Rz + cz, F:259 + F:282): the same
+    formula applied to BLOCK coordinates, then to the cell inside the B^3 block -- key = block << 3 log2(B) | cell-in-block."""
+    Ry, Rz = op.grid[1], op.grid[2]
+    ci = np.asarray(cell_index, np.int64)
+    cx, cy, cz = ci // (Ry * Rz), (ci // Rz) % Ry, ci % Rz
+    nby, nbz = -(-Ry // B), -(-Rz // B)
+    lb = {4: 2, 8: 3}[B]
+    blk = ((cx // B) * nby + cy // B) * nbz + cz // B
+    return ((blk << (3 * lb)) | ((cx % B) << (2 * lb)) | ((cy % B) << lb) | (cz % B)).astype(np.uint32)

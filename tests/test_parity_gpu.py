@@ -594,3 +594,260 @@ def test_checkpoint_resume_is_bit_exact(lib, tmp_path):
     with make_solver(other, 20000) as c:
         with pytest.raises(mpm_b200.MpmError):
             c.load_state(path)     # written for another grid
+
+
+# ---------------------------------------------------------------- cell path: the binning is the stable sort, and reproducible
+@pytest.mark.parametrize("grid,B", [(32, 4), (96, 8), ((128, 96, 96), 8)])
+def test_cell_binning_permutation_is_the_stable_sort(lib, grid, B):
+    """North-star subsystem 1 on the BENCHMARKED path: after every bin phase of the cell path the permutation
+    (cell-major rank -> record index) equals std::stable_sort of the records by cell key, bit for bit, and the keys are the
+    oracle's cell index (orc_cell_keys) of the positions the records hold.  The cloud is crowded (many equal keys) and one
+    particle in 500 is thrown several cells per step, so the cold binning (radix sort after an upload), the warm
+    binning (stable ranks from the previous layout) and its far-mover list are all exercised.  mpm_debug_last_sort also
+    verifies on the device that the layout in place (src_of, ids) is the one the ranks describe."""
+    op = orc.variant("3d_gpu", grid)
+    op.interaction = 0
+    n = 200001
+    pos, vel, Cm, mass = helpers.random_cloud(op, n, seed=33, vel_sigma=0.8)
+    pos[: n // 2] = pos[: n // 2] * 0.25 + 4.0
+    mass[: n // 2] *= 0.05
+    vel[::500] *= 25.0                                     # far movers: up to ~10 cells per step
+    with make_solver(op, n, kernel_path=3, math_mode=1) as s:
+        s.upload(pos, vel, Cm, mass)
+        far_steps = 0
+        for rnd in range(4):
+            if rnd:
+                s.step(2)                                   # warm binnings inside
+            s.run_phase(5)                                  # cold (round 0) / warm binning of the current state
+            keys, perm = s.last_sort()
+            ids = s.record_ids()
+            assert np.array_equal(np.sort(ids), np.arange(n, dtype=np.uint32)), "record ids are not a permutation"
+            expect = orc.stable_sort_perm(keys)             # == std::stable_sort order
+            assert np.array_equal(perm.astype(np.int32), expect), f"round {rnd}: binning permutation is not the stable sort"
+            gp = s.download()[0]                            # original index order; ends the binning's validity
+            ref = orc.State(op, gp)
+            want = helpers.block_major_key(op, ref.cell_keys(), B)
+            assert np.array_equal(keys, want[ids]), f"round {rnd}: cell keys differ from orc_cell_keys"
+            if rnd == 0:
+                helpers.assert_bit_equal(gp, pos, "binning must not change or reorder the particles")
+        assert s.stats().unordered_binnings == 0
+
+
+def test_cell_binning_far_mover_overflow_falls_back_and_is_counted(lib):
+    """More than 4096 particles leaving their block's apron in one step: the stable ranking cannot keep its list, the
+    binning falls back to atomic ranks (still a valid cell sort: the step matches the oracle) and says so in the stats."""
+    op = orc.variant("3d_gpu", 96)
+    op.interaction = 0
+    n = 60000
+    pos, vel, Cm, mass = helpers.random_cloud(op, n, seed=7, margin=30.0, vel_sigma=0.2)
+    vel[:6000, 0] = 60.0                                    # 12 cells per step
+    with make_solver(op, n, kernel_path=3, math_mode=1) as s:
+        s.upload(pos, vel, Cm, mass)
+        s.step(2)                                           # the second step's binning sees 6000 far movers
+        assert s.stats().unordered_binnings >= 1
+        gp, gv, gc, gm = s.download()
+    ref = orc.State(op, pos, vel, Cm, mass); ref.step(2)
+    assert np.abs(gp - ref.pos).max() < 1e-4 and helpers.rel_err(gv, ref.vel) < 1e-4
+    helpers.assert_bit_equal(gm, mass, "mass / order")
+
+
+@pytest.mark.parametrize("scene", ["dam_break_32", "c3_block_drop_128"])
+def test_cell_path_is_reproducible_bit_for_bit(lib, scene):
+    """Two runs of the FAST cell path give identical bits (stable in-cell order => fixed fp32 accumulation order).  The
+    large case is BASELINE config 3 (4 096 000 particles, 128^3), 12 steps."""
+    if scene == "dam_break_32":
+        op, lo, hi, steps = orc.variant("3d_gpu", 32), (4, 4, 4), (20, 20, 20), 40
+    else:
+        op, lo, hi, steps = orc.variant("3d_gpu", 128), (24, 24, 24), (104, 104, 104), 12
+    op.interaction = 0
+    runs = []
+    for _ in range(2):
+        with make_solver(op, 4096000 if scene != "dam_break_32" else 32768, kernel_path=3, math_mode=1) as s:
+            s.initialise_sim(lo, hi, 0.5)
+            s.step(steps)
+            runs.append((s.download(), s.download_grid(), s.stats().unordered_binnings))
+    for k, what in enumerate(("pos", "vel", "C", "mass")):
+        helpers.assert_bit_equal(runs[0][0][k], runs[1][0][k], f"{scene}: {what} differs between two runs")
+    helpers.assert_bit_equal(runs[0][1], runs[1][1], "grid differs between two runs")
+    assert runs[0][2] == 0 and runs[1][2] == 0
+
+
+# ---------------------------------------------------------------- cell path against the ORACLE on the BASELINE configs
+def _particle_report(tag, gp, gv, gc, ref):
+    dp = np.abs(gp.astype(np.float64) - ref.pos).max(1)
+    dv = np.abs(gv.astype(np.float64) - ref.vel).max(1)
+    rep = dict(pos_med=float(np.median(dp)), pos_p999=float(np.quantile(dp, 0.999)), pos_max=float(dp.max()),
+               vel_med=float(np.median(dv)), vel_p999=float(np.quantile(dv, 0.999)), vel_max=float(dv.max()),
+               vel_scale=float(np.abs(ref.vel).max()), C_rel=helpers.rel_err(gc, ref.C),
+               com=float(np.abs(gp.mean(0) - ref.pos.mean(0)).max()),
+               ke_rel=float(abs((gv.astype(np.float64) ** 2).sum() - (ref.vel.astype(np.float64) ** 2).sum()) / max((ref.vel.astype(np.float64) ** 2).sum(), 1e-30)))
+    print("CELL_VS_ORACLE", tag, {k: f"{v:.3g}" for k, v in rep.items()})
+    return rep
+
+
+def test_cell_path_config2_dam_break_vs_oracle_per_particle(lib):
+    """BASELINE config 2 (the reference's own scene size): 64^3 grid, dam-break block [4,36)^3 at spacing 0.5 = 262 144
+    particles, GPU-variant constants, 20 steps, FAST cell path against the strict oracle, PER PARTICLE.  FAST differs from
+    strict by rounding; 20 steps of a collapsing block amplify that by the flow's own sensitivity, measured here by the
+    oracle itself: the same run with the positions perturbed by 1e-6 cells.  The cell path must stay within 4x of that."""
+    op = orc.variant("3d_gpu", 64)
+    op.interaction = 0
+    lo, hi = (4, 4, 4), (36, 36, 36)
+    pos = orc.init_block(3, lo, hi, 0.5)
+    assert pos.shape[0] == 262144
+    ref = orc.State(op, pos); ref.step_mt(20)
+    rng = np.random.default_rng(1)
+    pert = orc.State(op, pos + rng.uniform(-1e-6, 1e-6, pos.shape).astype(np.float32)); pert.step_mt(20)
+    sens_p = np.abs(pert.pos.astype(np.float64) - ref.pos).max(1)
+    sens_v = np.abs(pert.vel.astype(np.float64) - ref.vel).max(1)
+    with make_solver(op, pos.shape[0], kernel_path=3, math_mode=1) as s:
+        assert s.initialise_sim(lo, hi, 0.5) == 262144
+        s.step(20)
+        gp, gv, gc, gm = s.download()
+        assert s.stats().kernel_path == 3
+    rep = _particle_report("c2", gp, gv, gc, ref)
+    print("ORACLE_SENSITIVITY c2", dict(pos_med=float(np.median(sens_p)), pos_p999=float(np.quantile(sens_p, 0.999)),
+                                        vel_med=float(np.median(sens_v)), vel_p999=float(np.quantile(sens_v, 0.999))))
+    assert rep["pos_med"] <= max(4 * np.median(sens_p), 2e-6) and rep["pos_p999"] <= max(4 * np.quantile(sens_p, 0.999), 2e-5)
+    assert rep["vel_med"] <= max(4 * np.median(sens_v), 2e-6) and rep["vel_p999"] <= max(4 * np.quantile(sens_v, 0.999), 2e-5)
+    assert rep["com"] < 1e-5 and rep["ke_rel"] < 1e-4
+    helpers.assert_bit_equal(gm, np.ones(262144, np.float32), "mass / count")
+
+
+def test_cell_path_shipping_scene_vs_oracle(lib):
+    """The scene the reference ships (H:654-707): 64^3, centred 32^3 box at spacing 0.6 = 157 464 particles, sphere
+    repulsor at the scene's default position, the UI's gravity -0.5, one frame = 2 steps (_Process) + 18 more, on the FAST
+    cell path -- the path a maintainer gets by default -- against the oracle, per particle, same bar as config 2."""
+    op = orc.variant("3d_gpu", 64)
+    op.gravity = -0.5
+    lo, hi = (16, 16, 16), (48, 48, 48)
+    pos = orc.init_block(3, lo, hi, 0.6)
+    ref = orc.State(op, pos); ref.step_mt(20)
+    rng = np.random.default_rng(1)
+    pert = orc.State(op, pos + rng.uniform(-1e-6, 1e-6, pos.shape).astype(np.float32)); pert.step_mt(20)
+    sens_p = np.abs(pert.pos.astype(np.float64) - ref.pos).max(1)
+    sens_v = np.abs(pert.vel.astype(np.float64) - ref.vel).max(1)
+    with make_solver(op, pos.shape[0], kernel_path=3, math_mode=1) as s:
+        assert s.initialise_sim(lo, hi, 0.6) == 157464
+        s.process(); s.step(18)
+        gp, gv, gc, _ = s.download()
+        p4 = s.positions()
+        _, width = s.positions_device()
+    rep = _particle_report("shipping", gp, gv, gc, ref)
+    assert rep["pos_med"] <= max(4 * np.median(sens_p), 2e-6) and rep["pos_p999"] <= max(4 * np.quantile(sens_p, 0.999), 2e-5)
+    assert rep["vel_med"] <= max(4 * np.median(sens_v), 2e-6) and rep["vel_p999"] <= max(4 * np.quantile(sens_v, 0.999), 2e-5)
+    assert width == 397
+    helpers.assert_bit_equal(p4[:, :3], gp, "particle_pos_tex xyz == particle positions")
+    assert np.abs(p4[:, 3] - np.sqrt((gv.astype(np.float64) ** 2).sum(1))).max() < 1e-5
+
+
+def test_cell_path_config3_one_step_vs_oracle(lib):
+    """BASELINE config 3 (128^3, 4 096 000 particles): one full step of the FAST cell path against the oracle (all host
+    cores, fixed-point atomics: bit-identical to the serial oracle), per phase grid and per particle, FAST tolerance."""
+    op = orc.variant("3d_gpu", 128)
+    op.interaction = 0
+    lo, hi = (24, 24, 24), (104, 104, 104)
+    pos = orc.init_block(3, lo, hi, 0.5)
+    assert pos.shape[0] == 4096000
+    rng = np.random.default_rng(5)
+    vel = rng.normal(0, 0.3, pos.shape).astype(np.float32)   # a resting lattice would leave most terms zero
+    Cm = rng.normal(0, 0.05, (pos.shape[0], 9)).astype(np.float32)
+    ref = orc.State(op, pos, vel, Cm)
+    ref.step_mt(1)
+    with make_solver(op, pos.shape[0], kernel_path=3, math_mode=1) as s:
+        s.upload(pos, vel, Cm)
+        s.step(1)
+        g = s.download_grid().astype(np.float64) / 1e7
+        gp, gv, gc, gm = s.download()
+    gr = ref.grid.astype(np.float64) / 1e7
+    # after UpdateGrid the cells hold velocity and mass: judge the velocity by the momentum it stands for
+    mom_err = float(np.abs((g[:, :3] - gr[:, :3]) * gr[:, 3:4]).max() / np.abs(gr[:, :3] * gr[:, 3:4]).max())
+    mass_err = helpers.rel_err(g[:, 3], gr[:, 3])
+    e = dict(mom=mom_err, mass=mass_err, pos=float(np.abs(gp.astype(np.float64) - ref.pos).max() / 128),
+             vel=helpers.rel_err(gv, ref.vel), C=helpers.rel_err(gc, ref.C), vel_elem=helpers.elem_err(gv, ref.vel, 1e-2))
+    print("CELL_C3_ONE_STEP", {k: f"{v:.3g}" for k, v in e.items()})
+    assert e["mom"] <= FAST_TOL["grid"] and e["mass"] <= FAST_TOL["grid"]
+    assert e["pos"] <= FAST_TOL["pos"] and e["vel"] <= FAST_TOL["vel"] and e["C"] <= FAST_TOL["C"] and e["vel_elem"] <= 2e-4
+
+
+def test_cell_path_config4_invariants(lib):
+    """BASELINE config 4, the benchmarked workload (256^3, 32 768 000 particles): size-independent properties.
+    (1) after P2G_1 the grid mass equals the particles' encoded mass up to one truncation per (cell, node);
+    (2) P2G_2 adds no net momentum (internal forces cancel) beyond truncation; (3) three steps keep every particle, in
+    the original (lattice) order, finite and inside the clamp box; (4) total momentum changes by gravity alone."""
+    op = orc.variant("3d_gpu", 256)
+    op.interaction = 0
+    n = 32768000
+    with make_solver(op, n, kernel_path=3, math_mode=1) as s:
+        assert s.initialise_sim((4, 4, 4), (164, 164, 164), 0.5) == n
+        s.run_phase(5); s.run_phase(0); s.run_phase(1)
+        g1 = s.download_grid().astype(np.int64)
+        total = int(g1[:, 3].sum())
+        occupied_nodes = int((g1[:, 3] != 0).sum())
+        assert abs(n * 10_000_000 - total) <= 27 * occupied_nodes + 1e-7 * n * 1e7, (n * 10_000_000 - total, occupied_nodes)
+        assert not g1[:, :3].any(), "a resting lattice with v = 0, C = 0 carries no momentum"
+        s.run_phase(2)
+        g2 = s.download_grid().astype(np.int64)
+        net = np.abs(g2[:, :3].sum(0))
+        assert (net <= 27 * occupied_nodes).all(), net
+        del g1, g2
+        s.step(3)
+        gp, gv, gc, gm = s.download()
+        assert s.stats().unordered_binnings == 0
+    assert gp.shape[0] == n and np.isfinite(gp).all() and np.isfinite(gv).all() and np.isfinite(gc).all()
+    assert gp.min() >= 2.0 and gp.max() <= 254.0
+    helpers.assert_bit_equal(gm, np.ones(n, np.float32), "mass")
+    xm = gp[:, 0].reshape(320, -1).mean(1)                 # lattice order: index = (ix * 320 + iy) * 320 + iz
+    assert np.all(np.diff(xm) > 0.25), "original (lattice) order lost"
+    # gravity acts on every particle alike while nothing has hit a wall yet; pressure forces are internal
+    py = gv[:, 1].astype(np.float64).mean()
+    assert abs(py - 3 * op.dt * op.gravity) < 0.05 * abs(3 * op.dt * op.gravity) + 1e-3, py
+
+
+def test_cell_path_update_grid_mass_weighted(lib):
+    """UpdateGrid on the cell path, judged by what a node's velocity stands for: |v - v_ref| * mass against the largest
+    momentum.  (The plain max-norm of the velocity grid is dominated by nodes with almost no mass, where one fixed-point
+    unit of momentum is a large velocity change that no particle ever sees.)"""
+    for variant, grid in (("3d_fixed", 32), ("3d_gpu", (40, 32, 24)), ("3d_gpu", 96)):
+        op = orc.variant(variant, grid)
+        sphere_into_cloud(op)
+        n = 20000
+        pos, vel, Cm, mass = helpers.random_cloud(op, n, seed=21)
+        ref = orc.State(op, pos, vel, Cm, mass)
+        ref.clear_grid(); ref.p2g1(); ref.p2g2(); ref.update_grid()
+        with make_solver(op, n, kernel_path=3, math_mode=1) as s:
+            s.upload(pos, vel, Cm, mass)
+            for k in range(4):
+                s.run_phase(k)
+            g = s.download_grid().astype(np.float64) / 1e7
+        gr = ref.grid.astype(np.float64) / 1e7
+        err = float(np.abs((g[:, :3] - gr[:, :3]) * gr[:, 3:4]).max() / np.abs(gr[:, :3] * gr[:, 3:4]).max())
+        print("CELL_UPDATE_GRID_MASS_WEIGHTED", variant, grid, f"{err:.3g}")
+        assert err <= FAST_TOL["grid"], (variant, grid, err)
+        assert helpers.rel_err(g[:, 3], gr[:, 3]) <= FAST_TOL["grid"]
+
+
+# ---------------------------------------------------------------- 2D mouse radial push (D:381-406)
+@pytest.mark.parametrize("variant", ["2d_st", "2d_mt"])
+def test_mouse_radial_push_2d(lib, variant):
+    """MPM_INTERACT_MOUSE_2D: the reference's 2D solvers push particles radially away from the held-down mouse
+    (MLSMPM2DFluid.cs:381-406).  Float grid (atomic order differs from the serial oracle): calibrated tolerance as in
+    test_float_grid_within_calibrated_tolerance; the push itself must be visible."""
+    op = orc.variant(variant, (64, 64, 1))
+    n = 4000
+    pos, vel, Cm, mass = helpers.random_cloud(op, n, seed=12, margin=8.0)
+    op.interaction = orc.INTERACT_MOUSE_2D
+    op.mouse_pos[:] = [30.0, 34.0]
+    op.mouse_radius = 10.0
+    off = orc.variant(variant, (64, 64, 1))
+    sens, ref = shuffle_sensitivity(op, pos, vel, Cm, mass, 5)
+    quiet = orc.State(off, pos, vel, Cm, mass); quiet.step(5)
+    assert np.abs(ref.vel - quiet.vel).max() > 0.05, "the mouse pushes nothing in this scene"
+    tol = max(4.0 * sens, 2e-6)
+    with make_solver(op, n) as s:
+        s.upload(pos, vel, Cm, mass)
+        s.step(5)
+        gp, gv, gc, _ = s.download()
+    for what, a, b in (("pos", gp, ref.pos), ("vel", gv, ref.vel), ("C", gc, ref.C)):
+        e = helpers.rel_err(a, b)
+        assert e <= tol, f"{variant} mouse push {what}: rel err {e:.3g} > tol {tol:.3g}"
