@@ -198,6 +198,7 @@ def main():
     ap.add_argument("--math", default="fast", choices=["strict", "fast"],
                     help="strict = bit-exact vs the reference algorithm; fast = FMA/hoisted (tolerance in tests)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--presteps", type=int, default=0, help="advance the scene this many untimed steps first (evolved-scene numbers)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
@@ -242,6 +243,8 @@ def main():
     # ---- warm-up, then the timed region: K steps, device-timed on the solver's stream
     sampler = ClockSampler(local_rank)
     sampler.start()
+    if args.presteps > 0:
+        solver.step(args.presteps)
     solver.step(max(args.warmup, 3))
     solver.sync()
     solver.set_timing(True)
@@ -320,6 +323,7 @@ def main():
             "config": {"workload": WORKLOAD_DESC[args.workload], "grid": list(grid), "particles": n_total, "variant": "3d_gpu (H)",
                        "grid_mode": "fixed 1e7", "math": args.math, "kernel_path": {1: "reference-shaped", 2: "tiled", 3: "cell"}[st.kernel_path],
                        "sort_interval": solver.params.sort_interval or 1, "parallelism": f"x-slab x{world}",
+                       "presteps": args.presteps,
                        "l2": f"inputs ({64e-9 * n_total / world:.1f} GB of particle planes per GPU) exceed the 126 MB L2; no flush needed",
                        "timing": "CUDA events on the solver stream inside mpm_step; wall-clock cross-check in wall_ms_per_step"},
             "wall_ms_per_step": wall_ms / args.steps,

@@ -156,6 +156,8 @@ typedef struct MpmStats {
     int64_t unordered_binnings; /* cell path: bin phases that could not rank stably (more than 4096 particles jumped out of
                                    their grid block's one-cell apron in one step: the simulation has blown up) and used an
                                    atomic cursor instead; 0 means every binning so far equals std::stable_sort */
+    int64_t far_movers;         /* cell path: particles of the most recent bin phase that had left their grid block's one-cell
+                                   apron (ranked exactly through the sorted far-mover list; normally 0) */
 } MpmStats;
 
 typedef struct MpmSolver MpmSolver; /* opaque */

@@ -775,6 +775,7 @@ extern "C" int32_t mpm_get_stats(MpmSolver* s, MpmStats* st)
         cudaStreamSynchronize(s->stream);
         cudaMemcpy(f, s->bin->far_n, sizeof(f), cudaMemcpyDeviceToHost);
         st->unordered_binnings = f[1];
+        st->far_movers = f[0];
     }
     comm_fill_stats(s, st);
     return MPM_OK;

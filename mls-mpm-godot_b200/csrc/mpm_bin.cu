@@ -28,6 +28,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <cstdio>
 #include <cstdlib>
 #include <string>
 #include <vector>
@@ -193,7 +194,8 @@ __global__ void __launch_bounds__(1 << CELL_BITS) k_block_order(const uint32_t* 
                                                                uint16_t* __restrict__ stab, uint32_t* __restrict__ fill)
 {
     constexpr int NC = 1 << CELL_BITS, NV = 2 * NC, NBIN = 64, NW = NC / 32, EXTRA = NV - NC;
-    __shared__ uint32_t hist[NBIN], base[NBIN], cursor[NBIN];
+    __shared__ uint32_t hist[NBIN], base[NBIN];
+    __shared__ uint32_t wbin[NW][NBIN];  // per warp: cells of each bin, then the count in the lower warps
     __shared__ uint32_t s_cnt[NV];
     __shared__ uint16_t s_ord[NV];
     __shared__ uint32_t wsum[NW];
@@ -202,7 +204,8 @@ __global__ void __launch_bounds__(1 << CELL_BITS) k_block_order(const uint32_t* 
     const uint32_t b = active[blockIdx.x];
     const uint32_t blk0 = b << CELL_BITS, v0 = b * NV;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    if (t < NBIN) { hist[t] = 0; cursor[t] = 0; }
+    if (t < NBIN) hist[t] = 0;
+    for (int k = t; k < NW * NBIN; k += NC) (&wbin[0][0])[k] = 0;
     s_cnt[t] = 0; s_cnt[t + NC] = 0; s_ord[t] = 0; s_ord[t + NC] = 0;
     if (t == 0) carry_s = 0;
     __syncthreads();
@@ -229,8 +232,22 @@ __global__ void __launch_bounds__(1 << CELL_BITS) k_block_order(const uint32_t* 
         base[t] = above;
     }
     __syncthreads();
-    const uint32_t pos_full = g ? base[VROWS] + atomicAdd(&cursor[VROWS], g) : 0u;
-    const uint32_t pos_rem = base[binr] + atomicAdd(&cursor[binr], 1u);
+    // position inside a bin: cells in cell order (deterministic -- an atomic cursor here made the lane a cell lands on,
+    // hence the slot order, hence the NEXT binning's stable order, vary from run to run): rank of the cell among the cells
+    // of its warp with the same bin (match.any), plus the bin's count in the lower warps.  Bin VROWS holds the full
+    // virtual cells first (grants were handed out in cell order: the ones before this cell are min(pre, EXTRA)).
+    const unsigned peers = __match_any_sync(0xffffffffu, binr);
+    const uint32_t rank_w = __popc(peers & ((1u << lane) - 1u));
+    if (lane == __ffs(peers) - 1) wbin[w][binr] = __popc(peers);
+    __syncthreads();
+    if (t < NBIN) {
+        uint32_t run = 0;
+        for (int k = 0; k < NW; ++k) { const uint32_t q = wbin[k][t]; wbin[k][t] = run; run += q; }
+    }
+    __syncthreads();
+    const uint32_t granted_total = min(want_total, (uint32_t)EXTRA);
+    const uint32_t pos_full = g ? base[VROWS] + min(pre, (uint32_t)EXTRA) : 0u;
+    const uint32_t pos_rem = base[binr] + (binr == (int)VROWS ? granted_total : 0u) + wbin[w][binr] + rank_w;
     for (uint32_t k = 0; k < g; ++k) { s_cnt[pos_full + k] = VROWS; s_ord[pos_full + k] = (uint16_t)t; }
     s_cnt[pos_rem] = rem; s_ord[pos_rem] = (uint16_t)t;
     cellmeta[blk0 + t] = make_uint2(pos_full | (pos_rem << 16), g);  // one 8-byte load per particle in k_place
@@ -280,6 +297,25 @@ __global__ void __launch_bounds__(1 << CELL_BITS) k_block_order(const uint32_t* 
     }
 }
 
+// general case of place_slot (a chunk whose counts are not strictly ordered, or a row beyond the chunk's S table)
+__device__ __noinline__ uint32_t place_slot_general(const uint32_t* __restrict__ cnts_chunk, uint32_t chunk_start, uint32_t lane, uint32_t r)
+{
+    const uint4* c4 = reinterpret_cast<const uint4*>(cnts_chunk);
+    uint32_t below = 0;   // sum over the chunk's virtual cells of min(count, r)
+    uint32_t before = 0;  // lower lanes that still have a particle at rank r
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint4 q = c4[k];
+        const uint32_t c[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            below += min(c[j], r);
+            before += ((uint32_t)(4 * k + j) < lane && c[j] > r) ? 1u : 0u;
+        }
+    }
+    return chunk_start + below + before;
+}
+
 // rank inside the (real) cell -> (virtual cell, row) -> destination slot from the chunk's counts
 template <int CELL_BITS>
 __device__ __forceinline__ uint32_t place_slot(uint32_t key, uint32_t rc, const uint2* __restrict__ cellmeta, const uint32_t* __restrict__ cnts,
@@ -301,20 +337,7 @@ __device__ __forceinline__ uint32_t place_slot(uint32_t key, uint32_t rc, const 
         const uint32_t ps = *reinterpret_cast<const uint32_t*>(row + 14);
         return ps + below + lane;
     }
-    const uint4* c4 = reinterpret_cast<const uint4*>(cnts + v0 + chunk * 32u);
-    uint32_t below = 0;   // sum over the chunk's virtual cells of min(count, r)
-    uint32_t before = 0;  // lower lanes that still have a particle at rank r
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const uint4 q = c4[k];
-        const uint32_t c[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            below += min(c[j], r);
-            before += ((uint32_t)(4 * k + j) < lane && c[j] > r) ? 1u : 0u;
-        }
-    }
-    return pstart[gchunk] + below + before;
+    return place_slot_general(cnts + v0 + chunk * 32u, pstart[gchunk], lane, r);
 }
 
 // Atomic ranking (multi-GPU slabs, where migration leaves the slots in no particular order; MPM_ATOMIC_BINNING=1): the rank
@@ -367,16 +390,42 @@ struct RankCfg {
     static constexpr int W = 4, THREADS = 32 * W;
 };
 
-// index of the cell `key` in the region of tile (tbx, tby, tbz) = block id `tile`, or -1 (a far mover)
+// index of the cell `key` in the region of tile (tbx, tby, tbz) = block id `tile`, or -1 (a far mover).
+// Nearly every particle stays in its block (first branch); one that crossed into a neighbouring block is decoded from the
+// DIFFERENCE of the block ids -- d = dx nby nbz + dy nbz + dz with |d*| <= 1 splits by two roundings when nby, nbz >= 3 --
+// and accepted only if that neighbour exists (at the grid's edge the same difference can also mean a block further away:
+// those, and grids of fewer than 3 blocks across, take the divisions).
+struct TileCtx {
+    uint32_t tile;
+    int tbx, tby, tbz;
+};
+__device__ __forceinline__ TileCtx tile_ctx(uint32_t tile, const RankGeom& g)
+{
+    TileCtx c;
+    c.tile = tile;
+    c.tbz = (int)(tile % (uint32_t)g.nbz); c.tby = (int)(tile / (uint32_t)g.nbz % (uint32_t)g.nby); c.tbx = (int)(tile / (uint32_t)(g.nbz * g.nby));
+    return c;
+}
 template <int CELL_BITS>
-__device__ __forceinline__ int region_index(uint32_t key, uint32_t tile, int tbx, int tby, int tbz, const RankGeom& g)
+__device__ __noinline__ int region_index_moved(uint32_t key, uint32_t tile, int tbx, int tby, int tbz, int nbx, int nby, int nbz)
 {
     using C = RankCfg<CELL_BITS>;
     const uint32_t blk = key >> CELL_BITS;
     const int lx = (key >> (2 * C::LOGB)) & (C::B - 1), ly = (key >> C::LOGB) & (C::B - 1), lz = key & (C::B - 1);
-    int dx = 0, dy = 0, dz = 0;
-    if (blk != tile) {
-        const int bz = (int)(blk % (uint32_t)g.nbz), by = (int)(blk / (uint32_t)g.nbz % (uint32_t)g.nby), bx = (int)(blk / (uint32_t)(g.nbz * g.nby));
+    const int s_yz = nby * nbz;
+    int dx, dy, dz;
+    const int delta = (int)blk - (int)tile;
+    bool decoded = false;
+    if (nby >= 3 && nbz >= 3 && delta > -2 * s_yz && delta < 2 * s_yz) {
+        dx = __float2int_rn((float)delta / (float)s_yz);
+        const int rem = delta - dx * s_yz;
+        dy = __float2int_rn((float)rem / (float)nbz);
+        dz = rem - dy * nbz;
+        decoded = dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1 && dz >= -1 && dz <= 1 && (unsigned)(tbx + dx) < (unsigned)nbx &&
+                  (unsigned)(tby + dy) < (unsigned)nby && (unsigned)(tbz + dz) < (unsigned)nbz;
+    }
+    if (!decoded) {
+        const int bz = (int)(blk % (uint32_t)nbz), by = (int)(blk / (uint32_t)nbz % (uint32_t)nby), bx = (int)(blk / (uint32_t)(nbz * nby));
         dx = bx - tbx; dy = by - tby; dz = bz - tbz;
         if (dx < -1 || dx > 1 || dy < -1 || dy > 1 || dz < -1 || dz > 1) return -1;
     }
@@ -384,11 +433,21 @@ __device__ __forceinline__ int region_index(uint32_t key, uint32_t tile, int tbx
     if ((unsigned)rx >= (unsigned)C::T || (unsigned)ry >= (unsigned)C::T || (unsigned)rz >= (unsigned)C::T) return -1;
     return (rx * C::T + ry) * C::T + rz;
 }
+template <int CELL_BITS>
+__device__ __forceinline__ int region_index(uint32_t key, const TileCtx& c, const RankGeom& g)
+{
+    using C = RankCfg<CELL_BITS>;
+    if ((key >> CELL_BITS) == c.tile) {
+        const int lx = (key >> (2 * C::LOGB)) & (C::B - 1), ly = (key >> C::LOGB) & (C::B - 1), lz = key & (C::B - 1);
+        return ((lx + 1) * C::T + (ly + 1)) * C::T + (lz + 1);
+    }
+    return region_index_moved<CELL_BITS>(key, c.tile, c.tbx, c.tby, c.tbz, g.nbx, g.nby, g.nbz);  // (out of line: rare, and large)
+}
 
 // particles of the tiles below `tile` that go to the cell (cx, cy, cz) (block-grid cell coordinates): the cell's own
 // block and the neighbours whose one-cell apron holds it
 template <int CELL_BITS>
-__device__ __forceinline__ uint32_t lower_tiles_sum(int cx, int cy, int cz, uint32_t tile, const RankGeom& g, const uint32_t* __restrict__ bsum_prev,
+__device__ __noinline__ uint32_t lower_tiles_sum(int cx, int cy, int cz, uint32_t tile, const RankGeom& g, const uint32_t* __restrict__ bsum_prev,
                                                     const uint32_t* __restrict__ tcount)
 {
     using C = RankCfg<CELL_BITS>;
@@ -412,27 +471,39 @@ __device__ __forceinline__ uint32_t lower_tiles_sum(int cx, int cy, int cz, uint
 }
 
 template <int CELL_BITS>
-__global__ void __launch_bounds__(RankCfg<CELL_BITS>::THREADS) k_rank_count(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ bbase_prev,
-                                                                            const uint32_t* __restrict__ active_prev, const uint32_t* __restrict__ nact_prev,
-                                                                            RankGeom g, uint32_t* __restrict__ tcount, uint32_t* __restrict__ far_list,
-                                                                            uint32_t* __restrict__ far_n)
+__global__ void __launch_bounds__(RankCfg<CELL_BITS>::THREADS, 12) k_rank_count(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ bbase_prev,
+                                                                                const uint32_t* __restrict__ active_prev, const uint32_t* __restrict__ nact_prev,
+                                                                                RankGeom g, uint32_t* __restrict__ tcount, uint32_t* __restrict__ far_list,
+                                                                                uint32_t* __restrict__ far_n)
 {
     using C = RankCfg<CELL_BITS>;
+    constexpr int KB = 8;  // keys per thread and batch: their loads are issued together
     __shared__ uint32_t cnt[C::RC];
     const uint32_t na = *nact_prev;
     for (uint32_t t = blockIdx.x; t < na; t += gridDim.x) {
         const uint32_t tile = active_prev[t];
-        const int tbz = (int)(tile % (uint32_t)g.nbz), tby = (int)(tile / (uint32_t)g.nbz % (uint32_t)g.nby), tbx = (int)(tile / (uint32_t)(g.nbz * g.nby));
+        const TileCtx tc = tile_ctx(tile, g);
+        const int tbx = tc.tbx, tby = tc.tby, tbz = tc.tbz;
         for (int k = threadIdx.x; k < C::RC; k += C::THREADS) cnt[k] = 0;
         __syncthreads();
         const uint32_t s0 = bbase_prev[tile], s1 = bbase_prev[tile + 1];
-        for (uint32_t i = s0 + threadIdx.x; i < s1; i += C::THREADS) {
-            const uint32_t key = keys[i];
-            const int r = region_index<CELL_BITS>(key, tile, tbx, tby, tbz, g);
-            if (r >= 0) atomicAdd(&cnt[r], 1u);
-            else {
-                const uint32_t f = atomicAdd(far_n, 1u);
-                if (f < (uint32_t)FAR_CAP) { far_list[2 * f] = i; far_list[2 * f + 1] = key; }
+        for (uint32_t base = s0; base < s1; base += C::THREADS * KB) {
+            uint32_t key[KB];
+#pragma unroll
+            for (int j = 0; j < KB; ++j) {
+                const uint32_t i = base + j * C::THREADS + threadIdx.x;
+                key[j] = i < s1 ? keys[i] : 0xffffffffu;
+            }
+#pragma unroll
+            for (int j = 0; j < KB; ++j) {
+                const uint32_t i = base + j * C::THREADS + threadIdx.x;
+                if (i >= s1) continue;
+                const int r = region_index<CELL_BITS>(key[j], tc, g);
+                if (r >= 0) atomicAdd(&cnt[r], 1u);
+                else {
+                    const uint32_t f = atomicAdd(far_n, 1u);
+                    if (f < (uint32_t)FAR_CAP) { far_list[2 * f] = i; far_list[2 * f + 1] = key[j]; }
+                }
             }
         }
         __syncthreads();
@@ -468,7 +539,7 @@ __device__ __forceinline__ uint32_t far_hash(uint32_t key) { return (key * 26544
 // VERIFY: nothing is stored; the rank of every old slot goes to dbg_rank and a mismatch between the layout in place
 // (src_of) and the one this run derives is counted in dbg_bad (mpm_debug_last_sort)
 template <int CELL_BITS, bool VERIFY>
-__global__ void __launch_bounds__(RankCfg<CELL_BITS>::THREADS) k_rank_place(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ bsum_prev,
+__global__ void __launch_bounds__(RankCfg<CELL_BITS>::THREADS, 8) k_rank_place(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ bsum_prev,
                                                                             const uint32_t* __restrict__ bbase_prev, const uint32_t* __restrict__ active_prev,
                                                                             const uint32_t* __restrict__ nact_prev, RankGeom g,
                                                                             const uint32_t* __restrict__ tcount, const uint32_t* __restrict__ far_list,
@@ -480,8 +551,10 @@ __global__ void __launch_bounds__(RankCfg<CELL_BITS>::THREADS) k_rank_place(cons
                                                                             uint32_t* __restrict__ dbg_bad)
 {
     using C = RankCfg<CELL_BITS>;
-    constexpr int RB = 4;  // rows per batch: their loads are issued together
+    constexpr int RB = 8;  // rows per batch: their loads are issued together
     __shared__ uint32_t wcnt[C::W][C::RC];
+    __shared__ uint32_t off[C::RC];      // arrivals from lower tiles, per region cell
+    __shared__ uint32_t nb_tile[27], nb_first[28];  // neighbour tiles below this one and the running size of their overlap boxes
     __shared__ uint32_t bloom[64];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
@@ -497,44 +570,95 @@ __global__ void __launch_bounds__(RankCfg<CELL_BITS>::THREADS) k_rank_place(cons
     const uint32_t na = *nact_prev;
     for (uint32_t t = blockIdx.x; t < na; t += gridDim.x) {
         const uint32_t tile = active_prev[t];
-        const int tbz = (int)(tile % (uint32_t)g.nbz), tby = (int)(tile / (uint32_t)g.nbz % (uint32_t)g.nby), tbx = (int)(tile / (uint32_t)(g.nbz * g.nby));
+        const TileCtx tc = tile_ctx(tile, g);
+        const int tbx = tc.tbx, tby = tc.tby, tbz = tc.tbz;
         for (int k = threadIdx.x; k < C::W * C::RC; k += C::THREADS) (&wcnt[0][0])[k] = 0;
+        for (int k = threadIdx.x; k < C::RC; k += C::THREADS) off[k] = 0;
+        // the 26 neighbouring tiles: those that come before this one and held particles contribute to the cells their
+        // region shares with ours (a box of 2 or T cells per axis)
+        if (threadIdx.x < 27) {
+            const int dz = (int)threadIdx.x % 3 - 1, dy = (int)threadIdx.x / 3 % 3 - 1, dx = (int)threadIdx.x / 9 - 1;
+            const int bx = tbx + dx, by = tby + dy, bz = tbz + dz;
+            uint32_t t2 = 0xffffffffu;
+            if ((dx | dy | dz) != 0 && bx >= 0 && by >= 0 && bz >= 0 && bx < g.nbx && by < g.nby && bz < g.nbz) {
+                t2 = (uint32_t)((bx * g.nby + by) * g.nbz + bz);
+                if (t2 >= tile || bsum_prev[t2] == 0) t2 = 0xffffffffu;
+            }
+            nb_tile[threadIdx.x] = t2;
+        }
         __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t run = 0;
+            for (int q = 0; q < 27; ++q) {
+                nb_first[q] = run;
+                if (nb_tile[q] != 0xffffffffu) {
+                    const int dz = q % 3 - 1, dy = q / 3 % 3 - 1, dx = q / 9 - 1;
+                    run += (uint32_t)((dx ? 2 : C::T) * (dy ? 2 : C::T) * (dz ? 2 : C::T));
+                }
+            }
+            nb_first[27] = run;
+        }
         const uint32_t s0 = bbase_prev[tile], s1 = bbase_prev[tile + 1];
         const uint32_t nrows = (s1 - s0 + 31u) >> 5, rpw = (nrows + C::W - 1) / C::W;
         const uint32_t r0 = min((uint32_t)w * rpw, nrows), r1 = min(r0 + rpw, nrows);
         // 1. counts of this warp's rows
-        for (uint32_t row = r0; row < r1; ++row) {
-            const uint32_t i = s0 + row * 32u + lane;
-            if (i < s1) {
-                const int r = region_index<CELL_BITS>(keys[i], tile, tbx, tby, tbz, g);
-                if (r >= 0) atomicAdd(&wcnt[w][r], 1u);
+        for (uint32_t row = r0; row < r1; row += RB) {
+            uint32_t key[RB];
+#pragma unroll
+            for (int j = 0; j < RB; ++j) {
+                const uint32_t i = s0 + (row + j) * 32u + lane;
+                key[j] = (row + j < r1 && i < s1) ? keys[i] : 0xffffffffu;
+            }
+#pragma unroll
+            for (int j = 0; j < RB; ++j) {
+                const uint32_t i = s0 + (row + j) * 32u + lane;
+                if (row + j < r1 && i < s1) {
+                    const int r = region_index<CELL_BITS>(key[j], tc, g);
+                    if (r >= 0) atomicAdd(&wcnt[w][r], 1u);
+                }
             }
         }
         __syncthreads();
-        // 2. starting rank of every (warp, region cell): arrivals from lower tiles, then the warps in order
-        for (int k = threadIdx.x; k < C::RC; k += C::THREADS) {
-            const int rz = k % C::T, ry = (k / C::T) % C::T, rx = k / (C::T * C::T);
-            uint32_t off = lower_tiles_sum<CELL_BITS>(tbx * C::B + rx - 1, tby * C::B + ry - 1, tbz * C::B + rz - 1, tile, g, bsum_prev, tcount);
-#pragma unroll
-            for (int q = 0; q < C::W; ++q) { const uint32_t c = wcnt[q][k]; wcnt[q][k] = off; off += c; }
+        // 2a. arrivals from lower tiles: all (neighbour, shared cell) pairs as one flat index space, so that the loads
+        // of a thread are independent of each other
+        for (uint32_t q = threadIdx.x; q < nb_first[27]; q += C::THREADS) {
+            int nb = 0;
+            while (nb_first[nb + 1] <= q) ++nb;   // (<= 26 steps; entries of absent neighbours are empty ranges)
+            const int dz = nb % 3 - 1, dy = nb / 3 % 3 - 1, dx = nb / 9 - 1;
+            const int ex = dx ? 2 : C::T, ey = dy ? 2 : C::T, ez = dz ? 2 : C::T;
+            uint32_t c = q - nb_first[nb];
+            const int cz = (int)(c % (uint32_t)ez), cy = (int)(c / (uint32_t)ez % (uint32_t)ey), cx = (int)(c / (uint32_t)(ez * ey));
+            (void)ex;
+            // our region coordinate r and the neighbour's r' = r - d * B on each axis: d = -1 -> r in {0, 1}; d = +1 -> r in {B, B + 1}
+            const int rx = dx < 0 ? cx : dx > 0 ? C::B + cx : cx, ry = dy < 0 ? cy : dy > 0 ? C::B + cy : cy, rz = dz < 0 ? cz : dz > 0 ? C::B + cz : cz;
+            const int qx = rx - dx * C::B, qy = ry - dy * C::B, qz = rz - dz * C::B;
+            const uint32_t v = tcount[(size_t)nb_tile[nb] * C::RC + (size_t)((qx * C::T + qy) * C::T + qz)];
+            if (v) atomicAdd(&off[(rx * C::T + ry) * C::T + rz], v);
         }
         __syncthreads();
-        // 3. the warp's rows in order
-        for (uint32_t row = r0; row < r1; row += RB) {
-            uint32_t key[RB], id[RB], rc[RB];
-            int rg[RB];
-            bool valid[RB];
+        // 2b. starting rank of every (warp, region cell): arrivals from lower tiles, then the warps in order
+        for (int k = threadIdx.x; k < C::RC; k += C::THREADS) {
+            uint32_t o = off[k];
 #pragma unroll
-            for (int j = 0; j < RB; ++j) {
+            for (int q = 0; q < C::W; ++q) { const uint32_t c = wcnt[q][k]; wcnt[q][k] = o; o += c; }
+        }
+        __syncthreads();
+        // 3. the warp's rows in order (batches of 4: the unrolled body of 8 no longer fitted the instruction cache)
+        constexpr int RB3 = 4;
+        for (uint32_t row = r0; row < r1; row += RB3) {
+            uint32_t key[RB3], id[RB3], rc[RB3];
+            int rg[RB3];
+            bool valid[RB3];
+#pragma unroll
+            for (int j = 0; j < RB3; ++j) {
                 const uint32_t i = s0 + (row + j) * 32u + lane;
                 valid[j] = row + j < r1 && i < s1;
                 key[j] = valid[j] ? keys[i] : 0u;
                 id[j] = valid[j] ? id_src[i] : 0u;
             }
 #pragma unroll
-            for (int j = 0; j < RB; ++j) {
-                rg[j] = valid[j] ? region_index<CELL_BITS>(key[j], tile, tbx, tby, tbz, g) : -1;
+            for (int j = 0; j < RB3; ++j) {
+                rg[j] = valid[j] ? region_index<CELL_BITS>(key[j], tc, g) : -1;
                 const uint32_t tag = rg[j] >= 0 ? (uint32_t)rg[j] : (0x80000000u | (uint32_t)lane);
                 const unsigned peers = __match_any_sync(0xffffffffu, tag);
                 uint32_t base = 0;
@@ -546,7 +670,7 @@ __global__ void __launch_bounds__(RankCfg<CELL_BITS>::THREADS) k_rank_place(cons
             }
             if (nfar) {
 #pragma unroll
-                for (int j = 0; j < RB; ++j) {
+                for (int j = 0; j < RB3; ++j) {
                     if (!valid[j]) continue;
                     const uint32_t i = s0 + (row + j) * 32u + lane;
                     const uint32_t h = far_hash(key[j]);
@@ -565,10 +689,10 @@ __global__ void __launch_bounds__(RankCfg<CELL_BITS>::THREADS) k_rank_place(cons
             }
             if (overflow && !VERIFY) {
 #pragma unroll
-                for (int j = 0; j < RB; ++j) if (valid[j]) rc[j] = atomicAdd(&fill[key[j]], 1u);
+                for (int j = 0; j < RB3; ++j) if (valid[j]) rc[j] = atomicAdd(&fill[key[j]], 1u);
             }
 #pragma unroll
-            for (int j = 0; j < RB; ++j) {
+            for (int j = 0; j < RB3; ++j) {
                 if (!valid[j]) continue;
                 const uint32_t i = s0 + (row + j) * 32u + lane;
                 const uint32_t dest = place_slot<CELL_BITS>(key[j], rc[j], cellmeta, cnts, pstart, stab);
@@ -604,8 +728,7 @@ __global__ void __launch_bounds__(256) k_gather_g2p_inputs(const float4* __restr
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t j = src_of[i];
-    const float4 a = rec[4 * (size_t)j];  // (px, py, pz, m)
-    dst.at(PX, i) = a.x; dst.at(PY, i) = a.y; dst.at(PZ, i) = a.z; dst.at(PM, i) = a.w;
+    reinterpret_cast<float4*>(dst.base)[i] = rec[4 * (size_t)j];  // (px, py, pz, m): one 16-byte element per slot, as P2G_1 leaves them
 }
 
 // ---- cold binning: a particle set in arbitrary order (upload, scene edit) is first brought into cell-key order by a
@@ -693,8 +816,8 @@ int bin_create(MpmSolver* s)
     CKB(cudaMalloc(&st->fill, sizeof(uint32_t) * st->nslots));
     CKB(cudaMemsetAsync(st->fill, 0, sizeof(uint32_t) * st->nslots, s->stream));
     CKB(cudaMalloc(&st->keys, sizeof(uint32_t) * s->pitch));
-    CKB(cudaMalloc(&st->src_of, sizeof(uint32_t) * (s->pitch + 64)));  // (the cell kernels read one row past the last slot)
-    CKB(cudaMemsetAsync(st->src_of, 0, sizeof(uint32_t) * (s->pitch + 64), s->stream));
+    CKB(cudaMalloc(&st->src_of, sizeof(uint32_t) * (s->pitch + 192)));  // (the cell kernels read up to two units past the last slot)
+    CKB(cudaMemsetAsync(st->src_of, 0, sizeof(uint32_t) * (s->pitch + 192), s->stream));
 
     CKB(cudaMalloc(&st->box, sizeof(int) * 12));
     CKB(cudaMemsetAsync(st->box, 0, sizeof(int) * 12, s->stream));  // empty boxes
@@ -727,12 +850,12 @@ KeyGeom bin_key_geom(const MpmSolver* s)
 static bool use_stable(const MpmSolver* s) { return s->bin->stable && !s->comm; }
 
 // persistent grid of the ranking kernels (one CTA per tile, striding over the list of the previous layout's non-empty blocks)
-static unsigned rank_grid(const BinState* st)
+static unsigned rank_grid(const BinState* st, int per_sm)
 {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return (unsigned)std::min<int64_t>(st->nblocks, (int64_t)sms * 8);
+    return (unsigned)std::min<int64_t>(st->nblocks, (int64_t)sms * per_sm);
 }
 
 // Cold binning: the particles sit in the planes in arbitrary (upload) order.  Stable radix sort of (cell key, index) on
@@ -809,15 +932,15 @@ int bin_particles(MpmSolver* s)
     s->launches += 3;
     if (n > 0 && stable) {
         const RankGeom rg{st->nbx, st->nby, st->nbz};
-        const unsigned grid = rank_grid(st);
+        const unsigned grid_c = rank_grid(st, 12), grid = rank_grid(st, 8);  // (resident CTAs per SM)
 #define RANK_ARGS st->keys, st->bsum2[pl], st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->far_list, st->far_n, st->cellmeta, st->cnts, \
                   st->pstart, st->stab, st->fill, st->src_of, s->orig_id, s->orig_id_alt, nullptr, nullptr
         if (st->cell_bits == 9) {
-            k_rank_count<9><<<grid, RankCfg<9>::THREADS, 0, s->stream>>>(st->keys, st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->far_list, st->far_n);
+            k_rank_count<9><<<grid_c, RankCfg<9>::THREADS, 0, s->stream>>>(st->keys, st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->far_list, st->far_n);
             k_far_sort<<<1, 1024, 0, s->stream>>>(st->far_list, st->far_n);
             k_rank_place<9, false><<<grid, RankCfg<9>::THREADS, 0, s->stream>>>(RANK_ARGS);
         } else {
-            k_rank_count<6><<<grid, RankCfg<6>::THREADS, 0, s->stream>>>(st->keys, st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->far_list, st->far_n);
+            k_rank_count<6><<<grid_c, RankCfg<6>::THREADS, 0, s->stream>>>(st->keys, st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->far_list, st->far_n);
             k_far_sort<<<1, 1024, 0, s->stream>>>(st->far_list, st->far_n);
             k_rank_place<6, false><<<grid, RankCfg<6>::THREADS, 0, s->stream>>>(RANK_ARGS);
         }
@@ -863,7 +986,7 @@ int bin_debug_last(MpmSolver* s, uint32_t* keys_before, uint32_t* perm, int64_t 
     CKB(cudaMemsetAsync(d_bad, 0, sizeof(uint32_t), s->stream));
     const int pl = st->prev_lay;
     const RankGeom rg{st->nbx, st->nby, st->nbz};
-    const unsigned grid = rank_grid(st);
+    const unsigned grid = rank_grid(st, 8);
 #define VERIFY_ARGS st->keys, st->bsum2[pl], st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->far_list, st->far_n, st->cellmeta, st->cnts, \
                     st->pstart, st->stab, st->fill, st->src_of, s->orig_id, s->orig_id_alt, d_rank, d_bad
     if (st->cell_bits == 9) k_rank_place<9, true><<<grid, RankCfg<9>::THREADS, 0, s->stream>>>(VERIFY_ARGS);
@@ -875,6 +998,15 @@ int bin_debug_last(MpmSolver* s, uint32_t* keys_before, uint32_t* perm, int64_t 
     CKB(cudaMemcpyAsync(&bad, d_bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
     CKB(cudaStreamSynchronize(s->stream));
     cudaFree(d_rank); cudaFree(d_bad);
+    if (getenv("MPM_DEBUG_BIN")) {  // development aid: which side is off -- the ranks of the verify run against the definition
+        std::vector<uint32_t> seen_cnt((size_t)st->nslots, 0u);
+        uint64_t wrong = 0;
+        for (int64_t i = 0; i < n; ++i) wrong += rank[(size_t)i] != seen_cnt[keys[(size_t)i]]++;
+        uint32_t f[2] = {0, 0};
+        cudaMemcpy(f, st->far_n, sizeof(f), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[mpm bin debug] n=%lld bad=%u verify-ranks-not-stable=%llu far_n=%u unordered=%u pl=%d lay=%d\n", (long long)n, bad,
+                (unsigned long long)wrong, f[0], f[1], pl, st->lay);
+    }
     if (bad) { s->err = "binning introspection: the layout in place differs from the re-derived one for " + std::to_string(bad) + " particles"; return MPM_ERR_STATE; }
     if (keys_before) std::copy(keys.begin(), keys.end(), keys_before);
     if (perm) {

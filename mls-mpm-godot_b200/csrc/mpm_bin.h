@@ -1,5 +1,7 @@
 // mpm_bin.h -- state of the counting-sort binning used by the cell kernels (mpm_bin.cu, mpm_kernels_cell.cu).
 #pragma once
+#include <cuda.h>
+
 #include "mpm_solver.h"
 
 namespace mpm {
@@ -40,6 +42,8 @@ struct BinState {
     uint32_t* tcount = nullptr;      // [nblocks][(B+2)^3]; row T is valid while bsum2[previous][T] > 0
     uint32_t* far_list = nullptr;    // [2][FAR_CAP] {old slot, key} of the particles that left their block's region ("far movers")
     uint32_t* far_n = nullptr;       // [2]: [0] count of this binning, [1] binnings that fell back to atomic ranks (overflow of the list)
+    CUtensorMap grid_map;            // TMA descriptor of the local grid (box = one block's tile), for G2P's tile prefetch
+    bool grid_map_valid = false;     // (re-encoded when the grid is re-created: multi-GPU re-cuts)
     bool stable = true;              // rank inside a cell = order of the old slots (std::stable_sort); false: atomic cursor
     uint32_t* keys = nullptr;        // [pitch] cell key of each particle for the NEXT binning (slot order)
     uint32_t* src_of = nullptr;      // [pitch + 64] slot -> index of the particle's record (the records stay where G2P wrote them)

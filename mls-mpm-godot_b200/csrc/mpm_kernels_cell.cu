@@ -18,6 +18,8 @@
 // Arithmetic: MPM_MATH_FAST (FMA, per-axis hoisting, sum factorisation).  Contributions are accumulated in fp32
 // and truncated to the int32 grid once per (cell, node) instead of once per (particle, node); the difference is
 // below one fixed-point unit per particle and inside the FAST tolerance stated in tests/test_parity_gpu.py.
+#include <cuda.h>  // CUtensorMap (the encoder itself is resolved through cudaGetDriverEntryPoint: no link to libcuda)
+
 #include "mpm_bin.h"
 #include "mpm_kernels.h"
 #include "mpm_particle_math.cuh"
@@ -26,6 +28,9 @@
 // resident CTAs per SM the P2G kernels are compiled for (3 -> 168 registers, 4 -> 128 registers with spills)
 #ifndef MPM_P2G_CTAS
 #define MPM_P2G_CTAS 3
+#endif
+#ifndef MPM_G2P_CTAS
+#define MPM_G2P_CTAS 4
 #endif
 
 namespace mpm {
@@ -95,6 +100,43 @@ __device__ __forceinline__ void cell_axis2(float2 p, float2 fc, float2 w[3], flo
 // a scalar as both halves of a pair: ptxas folds this into the packed instruction's scalar-operand form (`R.F32`), no move
 __device__ __forceinline__ float2 bc(float s) { return make_float2(s, s); }
 
+// ---------------------------------------------------------------- TMA: a block's grid tile as one bulk tensor copy
+// The (B+2)^3 nodes a block's stencils touch are a dense box of the grid array [x][y][z][4 x int32].  One elected thread
+// asks the TMA unit for the box (cp.async.bulk.tensor.4d, SASS UTMALDG): the 16 KB land in shared memory as [x][y][z][4]
+// and the copy signals an mbarrier with its byte count.  Nodes outside the (local) grid come back as zeros, which is what
+// the hand-written tile loaders wrote for them.  G2P issues the request for its NEXT block before walking the current one,
+// so the tile load -- every thread of the CTA used to stall on it behind one barrier, 13 % of the kernel's stall samples
+// -- overlaps a whole block of work.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// box of the 4-D view (channel, z, y, x) of the grid at (0, cz, cy, cx) -> dst; completion on bar
+__device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* map, int cz, int cy, int cx, unsigned long long* bar)
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // (the buffer was last read through the generic proxy)
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(0), "r"(cz), "r"(cy), "r"(cx), "r"(smem_u32(bar)) : "memory");
+}
+
 // ---------------------------------------------------------------- walking a block's chunks, software-pipelined
 // ncu (first cell-kernel capture, summarised in DESIGN.md section 4): with 168 registers per thread only 12 warps fit on
 // an SM, and a loop that loads a particle and then computes on it spends half its time in long-scoreboard stalls.  So the
@@ -103,16 +145,21 @@ __device__ __forceinline__ float2 bc(float s) { return make_float2(s, s); }
 // shared-memory staging buffer otherwise (P2G: the whole 64-byte record; prefetch.global.L1 was tried first and left the
 // L1 hit rate at 5 %).
 //
+// Round 2: the unit of the pipeline is TWO rows (up to 64 consecutive slots).  With one row per request the kernels were
+// latency-bound, not issue-bound -- 12 warps per SM x <= 2 rows x 2 KB in flight is ~5 MB over the chip, which at the ~1.2 us
+// a loaded DRAM access takes caps the read rate near 4 TB/s (measured: 3.26 GB in 0.82 ms) -- and cutting the instruction
+// count by a fifth bought only 9 %.  A unit doubles the bytes in flight with the same two buffers and the same
+// bookkeeping, and halves the per-row share of the walk's control instructions.
+//
 // Body interface (all calls warp-uniform except compute):
 //                  begin_chunk(cell)      per-cell set-up (stencil registers / accumulators)
-//                  fetch(base, mask, k)   start bringing a row in: the lanes set in `mask` own slots base, base + 1, ... in lane
-//                                         order.  k says how the row was announced: ROW_NEXT = it follows the row fetched last,
-//                                         ROW_HINTED = it starts at the slot given to hint_chunk, ROW_COLD = neither
+//                  fetch(base, n, k)      start bringing a unit in: slots base .. base + n - 1 (n <= 64).  k says how it was
+//                                         announced: ROW_NEXT = it follows the unit fetched last, ROW_HINTED = it starts at the
+//                                         slot given to hint_chunk, ROW_COLD = neither
 //                  hint_chunk(slot)       the warp's next chunk will start at `slot`
-//                  take(pending)          the oldest row not yet taken becomes the current one; `pending` (0 or 1) rows were
+//                  take(pending)          the oldest unit not yet taken becomes the current one; `pending` (0 or 1) units were
 //                                         requested after it and may stay in flight
-//                  FETCH_FIRST            whether the walk may request the next row before taking the current one
-//                  compute(i, t)          process this lane's particle of the current row (slot i = row base + t)
+//                  compute(i, t)          process this lane's particle t of the current unit (slot i = unit base + t)
 //                  end_chunk(has)         flush per-cell results
 //                  finish()               after the warp's last chunk of the block
 enum { ROW_COLD = 0, ROW_NEXT = 1, ROW_HINTED = 2 };
@@ -143,7 +190,7 @@ __device__ __forceinline__ void walk_chunks(const CellArgs& a, int b, int lane, 
     using CF = CellCfg<B>;
     const unsigned lt = (1u << lane) - 1u;
     const uint32_t v0 = (uint32_t)b * CF::NV;  // first virtual-cell position of the block
-    bool have = false;  // the first particle of the coming chunk has already been fetched
+    bool have = false;  // the first unit of the coming chunk has already been requested
     int chunk_nx = warp;
     uint32_t c_nx = a.cnts[v0 + warp * 32 + lane];
     uint32_t L_nx = a.ord[v0 + warp * 32 + lane];
@@ -154,9 +201,10 @@ __device__ __forceinline__ void walk_chunks(const CellArgs& a, int b, int lane, 
         if (chunk >= CF::NCHUNK) break;
         const uint32_t c = c_nx, L = L_nx;
         uint32_t slot0 = st_nx;
-        unsigned m = __ballot_sync(0xffffffffu, c > 0);
-        if (!m) break;  // virtual cells are ordered by count, descending: every later chunk of the block is empty too
-        // claim the chunk after this one now, so that its metadata (and first particle) arrive while this one runs
+        unsigned mA = __ballot_sync(0xffffffffu, c > 0);
+        if (!mA) break;  // virtual cells are ordered by count, descending: every later chunk of the block is empty too
+        unsigned mB = __ballot_sync(0xffffffffu, c > 1);
+        // claim the chunk after this one now, so that its metadata (and first unit) arrive while this one runs
         int g = 0;
         if (lane == 0) g = atomicAdd(&bw->next_chunk, 1);
         chunk_nx = __shfl_sync(0xffffffffu, g, 0);
@@ -166,35 +214,35 @@ __device__ __forceinline__ void walk_chunks(const CellArgs& a, int b, int lane, 
             L_nx = a.ord[v0 + chunk_nx * 32 + lane];
             st_nx = a.pstart[(v0 >> 5) + chunk_nx];
         }
-        if (!have) body.fetch(slot0, m, ROW_COLD);
+        if (!have) body.fetch(slot0, (uint32_t)(__popc(mA) + __popc(mB)), ROW_COLD);
         have = false;
         body.begin_chunk((int)L);
 #pragma unroll 1
-        for (uint32_t r = 0;; ++r) {
-            const bool on = r < c;
-            const uint32_t i = slot0 + __popc(m & lt);
-            const bool on1 = r + 1 < c;
-            const unsigned m1 = __ballot_sync(0xffffffffu, on1);
-            // A body that stages rows in shared memory may be asked for the next row BEFORE the current one is waited
-            // for (two rows in flight while the warp waits); one that stages in registers takes the current row first.
-            if (!Body::FETCH_FIRST) body.take(0);
+        for (uint32_t r = 0;; r += 2) {
+            // rows r and r + 1 are the current unit: its slots are slot0 .. slot0 + nA + nB - 1
+            const uint32_t nA = __popc(mA), nB = __popc(mB);
+            const uint32_t tA = __popc(mA & lt), tB = nA + __popc(mB & lt);
+            const unsigned mC = __ballot_sync(0xffffffffu, r + 2 < c), mD = __ballot_sync(0xffffffffu, r + 3 < c);
+            // the next unit is requested BEFORE the current one is waited for: two units in flight while the warp waits
             bool fetched = true;
-            if (m1) {
-                body.fetch(slot0 + __popc(m), m1, ROW_NEXT);
+            if (mC) {
+                body.fetch(slot0 + nA + nB, (uint32_t)(__popc(mC) + __popc(mD)), ROW_NEXT);
             } else {
-                const unsigned mn = __ballot_sync(0xffffffffu, c_nx > 0);
-                if (mn) {
-                    if (r > 0) body.fetch(st_nx, mn, ROW_HINTED);
-                    else body.fetch(st_nx, mn, ROW_COLD);  // single-row chunk: no hint was given yet
-                } else fetched = false;
+                const uint32_t n0 = __popc(__ballot_sync(0xffffffffu, c_nx > 0)), n1 = __popc(__ballot_sync(0xffffffffu, c_nx > 1));
+                if (n0) body.fetch(st_nx, n0 + n1, r > 0 ? ROW_HINTED : ROW_COLD);  // (single-unit chunk: no hint was given yet)
+                else fetched = false;
                 have = true;
             }
-            if (Body::FETCH_FIRST) body.take(fetched ? 1 : 0);
-            if (on) body.compute(i, (uint32_t)__popc(m & lt));
+            body.take(fetched ? 1 : 0);
+#pragma unroll 1
+            for (uint32_t u = 0; u < 2; ++u) {  // (one copy of the body: two inlined copies get interleaved and spill)
+                const uint32_t t = u ? tB : tA;
+                if (r + u < c) body.compute(slot0 + t, t);
+            }
             if (r == 0) body.hint_chunk(st_nx);  // (here, not where the chunk is claimed: st_nx has arrived by now)
-            slot0 += __popc(m);
-            m = m1;
-            if (!m) break;
+            slot0 += nA + nB;
+            mA = mC; mB = mD;
+            if (!mA) break;
         }
         body.end_chunk(c > 0);
     }
@@ -227,13 +275,14 @@ struct CellPos {  // the cell (id L inside the block) this lane owns in the curr
 // a row ahead (ix_row) or, for the first row of the warp's next chunk, when that chunk is announced (ix_chunk), and are
 // passed around with SHFL; only the first row after a block change pays the load's latency.
 struct RowStage {
-    static constexpr int WORDS = 32 * 16;  // one buffer, in 4-byte words
+    static constexpr int UNIT = 64;          // records per buffer (two rows)
+    static constexpr int WORDS = UNIT * 16;  // one buffer, in 4-byte words
     const float4* rec4;
     const uint32_t* src_of;
     float* buf;   // the warp's two buffers
     unsigned sa;  // shared-memory address of the 16 bytes this lane fills for record q = lane / 4 of buffer 0
     int lane;
-    uint32_t ix_row = 0, ix_chunk = 0;
+    uint32_t ix_row[2] = {0, 0}, ix_chunk[2] = {0, 0};  // record indices of the 64 slots that follow the last request / start the next chunk
     int wr = 0, rd = 0;
     __device__ __forceinline__ RowStage(const float* rec_, const uint32_t* src_of_, float* buf_, int lane_)
         : rec4(reinterpret_cast<const float4*>(rec_)), src_of(src_of_), buf(buf_), lane(lane_)
@@ -241,29 +290,32 @@ struct RowStage {
         const int q = lane >> 2, j = lane & 3;
         sa = (unsigned)__cvta_generic_to_shared(buf + q * 16 + ((j ^ (q >> 1)) & 3) * 4);
     }
-    __device__ __forceinline__ void hint_chunk(uint32_t slot) { ix_chunk = src_of[slot + lane]; }
-    __device__ __forceinline__ void fetch(uint32_t base, unsigned mask, int kind)
+    __device__ __forceinline__ void hint_chunk(uint32_t slot) { ix_chunk[0] = src_of[slot + lane]; ix_chunk[1] = src_of[slot + 32 + lane]; }
+    __device__ __forceinline__ void fetch(uint32_t base, uint32_t cnt, int kind)
     {
-        const uint32_t cnt = __popc(mask);
-        const uint32_t ix = (kind == ROW_NEXT) ? ix_row : (kind == ROW_HINTED) ? ix_chunk : src_of[base + lane];
+        uint32_t ix0, ix1;
+        if (kind == ROW_NEXT) { ix0 = ix_row[0]; ix1 = ix_row[1]; }
+        else if (kind == ROW_HINTED) { ix0 = ix_chunk[0]; ix1 = ix_chunk[1]; }
+        else { ix0 = src_of[base + lane]; ix1 = src_of[base + 32 + lane]; }
         const unsigned dst = sa + wr * (WORDS * 4);
         const uint32_t q = lane >> 2, j = lane & 3;
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {  // record t = 8 it + q; its swizzle (t >> 1) & 3 does not depend on it
-            const uint32_t src = __shfl_sync(0xffffffffu, ix, 8 * it + q);
+        for (int it = 0; it < 8; ++it) {  // record t = 8 it + q; its swizzle (t >> 1) & 3 does not depend on it
+            const uint32_t src = __shfl_sync(0xffffffffu, it < 4 ? ix0 : ix1, (8 * it + q) & 31);
             cp_async16_if(dst + it * 512, rec4 + (src * 4u + j), 8 * it + q < cnt);
         }
         cp_async_commit();
         wr ^= 1;
-        ix_row = src_of[base + cnt + lane];  // (src_of is padded: reading past the last particle is harmless)
+        ix_row[0] = src_of[base + cnt + lane];  // (src_of is padded: reading past the last particle is harmless)
+        ix_row[1] = src_of[base + cnt + 32 + lane];
     }
     __device__ __forceinline__ void take(int pending)
     {
         if (pending) cp_async_wait_but_one(); else cp_async_wait_all();
         __syncwarp();  // the pieces of a record were copied by four different lanes
-        rd = pending ? wr : wr ^ 1;  // (wr = where the next request goes = the older of two outstanding rows)
+        rd = pending ? wr : wr ^ 1;  // (wr = where the next request goes = the older of two outstanding units)
     }
-    // record t of the current row: (px, py, pz, m) (vx, vy, vz, c2) (c0, c1, c3, c4) (c6, c7, c5, c8)
+    // record t of the current unit: (px, py, pz, m) (vx, vy, vz, c2) (c0, c1, c3, c4) (c6, c7, c5, c8)
     __device__ __forceinline__ void load(uint32_t t, float4& a, float4& b, float4& c, float4& d) const
     {
         const float4* r = reinterpret_cast<const float4*>(buf + rd * WORDS) + 4 * t;
@@ -278,6 +330,36 @@ struct RowStage {
         a = r[s]; c = r[2u ^ s]; d = r[3u ^ s];
         return reinterpret_cast<const float*>(r + (1u ^ s))[3];
     }
+};
+
+// units of (px, py, pz, m) quads for G2P: P2G_1 wrote them in slot order, so a unit is one contiguous run of 16-byte
+// elements; lane l copies elements l and l + 32
+struct QuadStage {
+    static constexpr int UNIT = 64;
+    const float4* pm;
+    float4* buf;  // the warp's two buffers of UNIT quads
+    unsigned sa;
+    int lane;
+    int wr = 0, rd = 0;
+    __device__ __forceinline__ QuadStage(const float4* pm_, float4* buf_, int lane_) : pm(pm_), buf(buf_), lane(lane_)
+    {
+        sa = (unsigned)__cvta_generic_to_shared(buf + lane);
+    }
+    __device__ __forceinline__ void fetch(uint32_t base, uint32_t cnt, int)
+    {
+        const unsigned dst = sa + wr * (UNIT * 16);
+        cp_async16_if(dst, pm + base + lane, (uint32_t)lane < cnt);
+        cp_async16_if(dst + 512, pm + base + 32 + lane, (uint32_t)lane + 32u < cnt);
+        cp_async_commit();
+        wr ^= 1;
+    }
+    __device__ __forceinline__ void take(int pending)
+    {
+        if (pending) cp_async_wait_but_one(); else cp_async_wait_all();
+        __syncwarp();
+        rd = pending ? wr : wr ^ 1;
+    }
+    __device__ __forceinline__ float4 load(uint32_t t) const { return buf[rd * UNIT + t]; }
 };
 
 // ---------------------------------------------------------------- P2G_1
@@ -307,16 +389,15 @@ struct P2G1Body {
 #pragma unroll
         for (int g = 0; g < 9; ++g) { az01[g] = make_float2(0.0f, 0.0f); am01[g] = make_float2(0.0f, 0.0f); az2[g] = 0.0f; am2[g] = 0.0f; }
     }
-    __device__ __forceinline__ void fetch(uint32_t base, unsigned mask, int kind) { st.fetch(base, mask, kind); }
+    __device__ __forceinline__ void fetch(uint32_t base, uint32_t cnt, int kind) { st.fetch(base, cnt, kind); }
     __device__ __forceinline__ void hint_chunk(uint32_t slot) { st.hint_chunk(slot); }
-    static constexpr bool FETCH_FIRST = true;
     __device__ __forceinline__ void take(int pending) { st.take(pending); }
     __device__ __forceinline__ void compute(uint32_t i, uint32_t t)
     {
         float4 ra, rb, rc, rd4;
         st.load(t, ra, rb, rc, rd4);  // (px, py, pz, m) (vx, vy, vz, c2) (c0, c1, c3, c4) (c6, c7, c5, c8)
-        // G2P needs the position and the mass of slot i
-        pv.at(PX, i) = ra.x; pv.at(PY, i) = ra.y; pv.at(PZ, i) = ra.z; pv.at(PM, i) = ra.w;
+        // G2P needs the position and the mass of slot i: one 16-byte element, in slot order
+        reinterpret_cast<float4*>(pv.base)[i] = ra;
         const float ms = ra.w * P.fmult;  // mass in fixed-point units
         float2 wxy[3], dxy[3];            // (x, y) weights and node distances, computed packed
         float wz[3], dz[3];
@@ -462,9 +543,8 @@ struct P2G2Body {
 #pragma unroll
         for (int g = 0; g < 9; ++g) { az01[g] = make_float2(0.0f, 0.0f); az2[g] = 0.0f; }
     }
-    __device__ __forceinline__ void fetch(uint32_t base, unsigned mask, int kind) { st.fetch(base, mask, kind); }
+    __device__ __forceinline__ void fetch(uint32_t base, uint32_t cnt, int kind) { st.fetch(base, cnt, kind); }
     __device__ __forceinline__ void hint_chunk(uint32_t slot) { st.hint_chunk(slot); }
-    static constexpr bool FETCH_FIRST = true;
     __device__ __forceinline__ void take(int pending) { st.take(pending); }
     __device__ __forceinline__ void compute(uint32_t, uint32_t t)
     {
@@ -593,11 +673,12 @@ struct G2PBody {
     CellPos<B> cp;
     float2 gxy[27];        // node velocities of the cell's stencil: (x, y) packed for FFMA2, z separate
     float gvz[27];
-    float nx_[4], cur[4];  // next / current particle: position, mass
+    QuadStage st;          // (px, py, pz, m) of the current / next unit, staged in shared memory
     float4* rec;           // output records
     __device__ __forceinline__ G2PBody(const DevParams& P_, const ParticleView& pv_, const TL& tl_, const float (*tv_)[TL::WORDS],
-                                       const KeyGeom& kg_, uint32_t nslots_, uint32_t* keys_, uint32_t* cnt_next_, const MigClassify& mg_, int lane_, float4* rec_)
-        : P(P_), pv(pv_), tl(tl_), tv(tv_), kg(kg_), nslots(nslots_), keys(keys_), cnt_next(cnt_next_), mg(mg_), lane(lane_), rec(rec_) {}
+                                       const KeyGeom& kg_, uint32_t nslots_, uint32_t* keys_, uint32_t* cnt_next_, const MigClassify& mg_, int lane_, float4* rec_,
+                                       const QuadStage& st_)
+        : P(P_), pv(pv_), tl(tl_), tv(tv_), kg(kg_), nslots(nslots_), keys(keys_), cnt_next(cnt_next_), mg(mg_), lane(lane_), st(st_), rec(rec_) {}
     __device__ __forceinline__ void begin_chunk(int L)
     {
         cp.set(tl, L);
@@ -611,18 +692,13 @@ struct G2PBody {
                     gxy[n] = make_float2(tv[0][idx], tv[1][idx]); gvz[n] = tv[2][idx];
                 }
     }
-    __device__ __forceinline__ void fetch(uint32_t base, unsigned mask, int)
-    {
-        if (!((mask >> lane) & 1u)) return;
-        const float* q = pv.rec(base + __popc(mask & ((1u << lane) - 1u)));
-        nx_[0] = q[PX * GROUP]; nx_[1] = q[PY * GROUP]; nx_[2] = q[PZ * GROUP]; nx_[3] = q[PM * GROUP];
-    }
+    __device__ __forceinline__ void fetch(uint32_t base, uint32_t cnt, int kind) { st.fetch(base, cnt, kind); }
     __device__ __forceinline__ void hint_chunk(uint32_t) {}
-    static constexpr bool FETCH_FIRST = false;  // one register set: the current row is taken before the next is requested
-    __device__ __forceinline__ void take(int) { cur[0] = nx_[0]; cur[1] = nx_[1]; cur[2] = nx_[2]; cur[3] = nx_[3]; }
-    __device__ __forceinline__ void compute(uint32_t i, uint32_t)
+    __device__ __forceinline__ void take(int pending) { st.take(pending); }
+    __device__ __forceinline__ void compute(uint32_t i, uint32_t t)
     {
-        const float old[3] = {cur[0], cur[1], cur[2]};
+        const float4 pm = st.load(t);
+        const float old[3] = {pm.x, pm.y, pm.z};
         float wx[3], wy[3], wz[3], dx[3], dy[3], dz[3];
         // The particle sits in the cell its thread owns (that is what the binning key says), so the cell coordinate is
         // trunc(p): taking it from the position frees three registers here (G2P: 20 -> 4 bytes of spills, -1 %; in the
@@ -682,7 +758,7 @@ struct G2PBody {
         }
         // one 64-byte record per particle (field order of the planes): the next step's P2G kernels read it from here
         float4* q = rec + 4 * (size_t)i;
-        q[0] = make_float4(np[0], np[1], np[2], cur[3]);
+        q[0] = make_float4(np[0], np[1], np[2], pm.w);
         q[1] = make_float4(v[0], v[1], v[2], cm[2]);
         q[2] = make_float4(cm[0], cm[1], cm[3], cm[4]);
         q[3] = make_float4(cm[6], cm[7], cm[5], cm[8]);
@@ -706,46 +782,87 @@ struct G2PBody {
 
 // 4 CTAs per SM (128 registers, ~30 bytes of spills): measured 0.778 vs 0.823 ms on C4 against 3 CTAs at 158 registers.
 // The multi-GPU classification is a separate instantiation: as a run-time branch it cost the single-GPU kernel 0.045 ms.
+template <int B>
+struct G2PSmem {  // byte sizes of the three dynamic shared-memory regions of k_g2p_cell
+    static constexpr size_t RAW = (sizeof(int4) * Tile<B>::NODES + 127) / 128 * 128;
+    static constexpr size_t TV = sizeof(float) * 3 * Tile<B>::WORDS;
+    static constexpr size_t QUADS = sizeof(float4) * CellCfg<B>::NWARP * 2 * QuadStage::UNIT;
+    static constexpr size_t TOTAL = RAW + TV + QUADS;
+};
+
 template <int B, bool COMM, bool EXTRA>
-__global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? 4 : 8) k_g2p_cell(DevParams P, TileGeom g, ParticleView pv, CellArgs a,
-                                                                                    const int4* __restrict__ grid, int raw_grid, KeyGeom kg, uint32_t nslots,
+__global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? MPM_G2P_CTAS : 8) k_g2p_cell(DevParams P, TileGeom g, ParticleView pv, CellArgs a,
+                                                                                    const __grid_constant__ CUtensorMap grid_map, int raw_grid, KeyGeom kg, uint32_t nslots,
                                                                                     uint32_t* __restrict__ keys, uint32_t* __restrict__ cnt_next,
                                                                                     MigClassify mg, float4* __restrict__ rec)
 {
     using TL = Tile<B>;
     using CF = CellCfg<B>;
-    __shared__ float tv[3][TL::WORDS];
+    // dynamic shared memory (above the 48 KB static limit together): the tile as the TMA unit delivers it -- [x][y][z]
+    // cells of 4 x int32 -- | the velocity tile the stencils read | the per-warp staging of (px, py, pz, m) units
+    extern __shared__ __align__(128) unsigned char dsm[];
+    int4* raw = reinterpret_cast<int4*>(dsm);
+    float (*tv)[TL::WORDS] = reinterpret_cast<float (*)[TL::WORDS]>(dsm + G2PSmem<B>::RAW);
+    float4 (*s_quads)[2 * QuadStage::UNIT] = reinterpret_cast<float4 (*)[2 * QuadStage::UNIT]>(dsm + G2PSmem<B>::RAW + G2PSmem<B>::TV);
+    __shared__ __align__(8) unsigned long long tile_bar;
     __shared__ BlockWork s_bw;
+    __shared__ int s_next;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float inv_mult = 1.0f / P.fmult;
-    for (;;) {
-        const int b = fetch_block<CF::NWARP>(a, BIN_WORK_G2P, &s_bw);
-        if (b < 0) break;
+    constexpr unsigned TILE_BYTES = sizeof(int4) * TL::NODES;
+    auto request_tile = [&](int blk) {  // (one thread)
+        TL t2; t2.init(g, blk);
+        mbar_expect_tx(&tile_bar, TILE_BYTES);
+        tma_load_tile(raw, &grid_map, t2.oz, t2.oy, t2.ox - P.gx0, &tile_bar);
+    };
+    auto claim = [&]() -> int {  // (one thread) next non-empty block of the list, or -1
+        const uint32_t bi = atomicAdd(&a.misc[BIN_WORK_G2P], 1u);
+        return (bi < a.misc[BIN_N_ACTIVE]) ? (int)a.active[bi] : -1;
+    };
+    if (threadIdx.x == 0) {
+        mbar_init(&tile_bar, 1);
+        s_next = claim();
+        if (s_next >= 0) request_tile(s_next);
+    }
+    __syncthreads();
+    int b = s_next;
+    unsigned phase = 0;
+    while (b >= 0) {
         TL tl; tl.init(g, b);
+        mbar_wait(&tile_bar, phase);
+        phase ^= 1u;
         for (int k = threadIdx.x; k < TL::NODES; k += CF::THREADS) {
-            int idx; int64_t ci;
+            const int tz = k % TL::T, ty = (k / TL::T) % TL::T, tx = k / (TL::T * TL::T);
+            const int idx = tx * TL::PX + ty * TL::PY + tz;
+            const int4 c = raw[k];
             float vx = 0.0f, vy = 0.0f, vz = 0.0f;
-            if (tl.node(P, k, idx, ci)) {
-                const int4 c = grid[ci];
-                if (!raw_grid) {  // the grid update already ran: cells hold velocities
-                    vx = (float)c.x * inv_mult; vy = (float)c.y * inv_mult; vz = (float)c.z * inv_mult;
-                } else if (c.w > 0) {
-                    // UpdateGrid fused into the tile load (update_grid.glsl:44-66): v = p / m, gravity on y, zero the
-                    // wall-normal component for idx < 2 || idx > R - bc_hi_off.  (m and p carry the same fixed-point scale.)
-                    const float im = __frcp_rn((float)c.w);
-                    const int tz = k % TL::T, ty = (k / TL::T) % TL::T, tx = k / (TL::T * TL::T);
-                    const int nx = tl.ox + tx, ny = tl.oy + ty, nz = tl.oz + tz;
-                    const int hi = P.bc_hi_off;
-                    vx = (nx < 2 || nx > P.Rx - hi) ? 0.0f : (float)c.x * im;
-                    vy = (ny < 2 || ny > P.Ry - hi) ? 0.0f : fmaf((float)c.y, im, P.dt * P.gravity);
-                    vz = (nz < 2 || nz > P.Rz - hi) ? 0.0f : (float)c.z * im;
-                }
+            if (!raw_grid) {  // the grid update already ran: cells hold velocities
+                vx = (float)c.x * inv_mult; vy = (float)c.y * inv_mult; vz = (float)c.z * inv_mult;
+            } else if (c.w > 0) {
+                // UpdateGrid fused into the tile load (update_grid.glsl:44-66): v = p / m, gravity on y, zero the
+                // wall-normal component for idx < 2 || idx > R - bc_hi_off.  (m and p carry the same fixed-point scale.)
+                const float im = __frcp_rn((float)c.w);
+                const int nx = tl.ox + tx, ny = tl.oy + ty, nz = tl.oz + tz;
+                const int hi = P.bc_hi_off;
+                vx = (nx < 2 || nx > P.Rx - hi) ? 0.0f : (float)c.x * im;
+                vy = (ny < 2 || ny > P.Ry - hi) ? 0.0f : fmaf((float)c.y, im, P.dt * P.gravity);
+                vz = (nz < 2 || nz > P.Rz - hi) ? 0.0f : (float)c.z * im;
             }
             tv[0][idx] = vx; tv[1][idx] = vy; tv[2][idx] = vz;
         }
+        __syncthreads();  // tv is complete, raw is free again
+        if (threadIdx.x == 0) {
+            s_bw.next_chunk = CF::NWARP;  // chunk `warp` is every warp's first one
+            s_next = claim();
+            if (s_next >= 0) request_tile(s_next);  // in flight while this block is walked
+        }
         __syncthreads();
-        G2PBody<B, COMM, EXTRA> body(P, pv, tl, tv, kg, nslots, keys, cnt_next, mg, lane, rec);
+        const int b_next = s_next;
+        G2PBody<B, COMM, EXTRA> body(P, pv, tl, const_cast<const float (*)[TL::WORDS]>(tv), kg, nslots, keys, cnt_next, mg, lane, rec,
+                                     QuadStage(reinterpret_cast<const float4*>(pv.base), s_quads[warp], lane));
         walk_chunks<B>(a, b, lane, warp, &s_bw, body);
+        __syncthreads();  // everyone is done with tv and the work counters
+        b = b_next;
     }
 }
 
@@ -829,6 +946,31 @@ constexpr auto k_g2p_cell_single_x = k_g2p_cell<B, false, true>;
 template <int B>
 constexpr auto k_g2p_cell_comm_x = k_g2p_cell<B, true, true>;
 
+// 4-D tensor map (channel, z, y, x) of the local grid, box = one block's tile; encoded once per solver
+static int grid_tensor_map(MpmSolver* s)
+{
+    BinState* bs = s->bin;
+    if (bs->grid_map_valid) return MPM_OK;
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn || q != cudaDriverEntryPointSuccess) {
+        s->err = "cuTensorMapEncodeTiled is not available from this driver";
+        return MPM_ERR_CUDA;
+    }
+    const cuuint32_t T = (cuuint32_t)(bs->B + 2);
+    const cuuint64_t dims[4] = {4, (cuuint64_t)s->dp.Rz, (cuuint64_t)s->dp.Ry, (cuuint64_t)s->dp.nxl};
+    const cuuint64_t strides[3] = {16, 16ull * s->dp.Rz, 16ull * s->dp.Rz * s->dp.Ry};  // bytes, dimensions 1..3
+    const cuuint32_t box[4] = {4, T, T, T}, estr[4] = {1, 1, 1, 1};
+    const CUresult r = reinterpret_cast<EncodeFn>(fn)(&bs->grid_map, CU_TENSOR_MAP_DATA_TYPE_INT32, 4, s->grid, dims, strides, box, estr,
+                                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { s->err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"; return MPM_ERR_CUDA; }
+    bs->grid_map_valid = true;
+    return MPM_OK;
+}
+
 int cell_g2p(MpmSolver* s)
 {
     int rc = check_cell_supported(s);
@@ -845,13 +987,14 @@ int cell_g2p(MpmSolver* s)
     if (rc) return rc;
     // The (x, y, z, |v|) hand-off in original index order is a 16-B scatter per particle (0.30 ms of 1.17 ms on C4 when
     // fused here): on this path it is produced on demand by mpm_get_positions instead of every step.
-#define G2P_ARGS reinterpret_cast<const int4*>(s->grid), s->grid_raw ? 1 : 0, bin_key_geom(s), (uint32_t)bs->nslots, bs->keys, cnt_next, mg, \
+    if ((rc = grid_tensor_map(s))) return rc;
+#define G2P_ARGS bs->grid_map, s->grid_raw ? 1 : 0, bin_key_geom(s), (uint32_t)bs->nslots, bs->keys, cnt_next, mg, \
                  reinterpret_cast<float4*>(s->rec)
     const bool extra = s->dp.n_extra > 0;
-    if (mg.cnt && extra) LAUNCH_CELL(k_g2p_cell_comm_x, 0, 0, G2P_ARGS);
-    else if (mg.cnt) LAUNCH_CELL(k_g2p_cell_comm, 0, 0, G2P_ARGS);
-    else if (extra) LAUNCH_CELL(k_g2p_cell_single_x, 0, 0, G2P_ARGS);
-    else LAUNCH_CELL(k_g2p_cell_single, 0, 0, G2P_ARGS);
+    if (mg.cnt && extra) LAUNCH_CELL(k_g2p_cell_comm_x, G2PSmem<8>::TOTAL, G2PSmem<4>::TOTAL, G2P_ARGS);
+    else if (mg.cnt) LAUNCH_CELL(k_g2p_cell_comm, G2PSmem<8>::TOTAL, G2PSmem<4>::TOTAL, G2P_ARGS);
+    else if (extra) LAUNCH_CELL(k_g2p_cell_single_x, G2PSmem<8>::TOTAL, G2PSmem<4>::TOTAL, G2P_ARGS);
+    else LAUNCH_CELL(k_g2p_cell_single, G2PSmem<8>::TOTAL, G2PSmem<4>::TOTAL, G2P_ARGS);
 #undef G2P_ARGS
     std::swap(s->orig_id, s->orig_id_alt);  // the records are in this step's slot order now, and so are the ids P2G_1 wrote
     s->g2p_inputs = false;
