@@ -40,6 +40,10 @@ extern "C" {
 #define MPM_ERR_STATE 3    /* call not valid in the current state (e.g. step before upload) */
 #define MPM_ERR_OVERFLOW 4 /* fixed-point accumulator left the int32 range (debug detector) */
 #define MPM_ERR_COMM 5     /* multi-GPU exchange failed */
+#define MPM_ERR_DOMAIN 6   /* particle positions that are non-finite or whose 3x3(x3) stencil leaves the grid, i.e. outside
+                              [1, R-1) on some axis: rejected at upload / load; if a running simulation produces one
+                              (NaN from a blown-up step) the particle is skipped and mpm_sync reports it.  The reference
+                              indexes the grid with (int)pos unchecked and dies with IndexOutOfRangeException (F:281-283) */
 
 /* ---- enums (int32 in the struct) ---- */
 #define MPM_GRID_FLOAT 0 /* Cell{Vector3 vel; float mass}            F:16-20, D:16-20 */
@@ -116,7 +120,11 @@ typedef struct MpmParams {
     int32_t math_mode;        /* MPM_MATH_* */
     int32_t kernel_path;      /* MPM_PATH_* */
     int32_t sort_interval;    /* re-bin particles every k steps (tiled path); 0 = library default */
-    int32_t overflow_check;   /* 1: detect fixed-point overflow (slower) */
+    int32_t overflow_check;   /* 1: debug detector for the int32 x fixed_point_mult grid: every encode (saturation / NaN) and every
+                                 integer add (wrap-around) is checked, mpm_sync returns MPM_ERR_OVERFLOW and MpmStats.overflow is
+                                 set.  Slower (atomics return values); runs on the reference-shaped and tiled paths -- AUTO avoids the
+                                 cell path when it is set, MPM_PATH_CELL with it is rejected.  Values are identical either way:
+                                 bit-exact results hold for in-range data (|value| < 2^31 / fixed_point_mult = 214.7 at 1e7) */
 } MpmParams;
 
 /* Particle record of the reference's GPU buffer: 80 bytes, std430 (H:8-22, p2g_1.glsl:4-9). */

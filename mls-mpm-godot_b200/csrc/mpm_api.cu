@@ -138,7 +138,8 @@ extern "C" int32_t mpm_default_params(int32_t variant, MpmParams* p)
 static int resolve_path(const MpmParams& p)
 {
     if (p.kernel_path != MPM_PATH_AUTO) return p.kernel_path;
-    if (p.dim == 3 && p.grid_mode == MPM_GRID_FIXED) return p.math_mode == MPM_MATH_FAST ? MPM_PATH_CELL : MPM_PATH_TILED;
+    // (the overflow detector lives in the reference-shaped and tiled kernels: with it on, FAST runs the tiled kernels)
+    if (p.dim == 3 && p.grid_mode == MPM_GRID_FIXED) return (p.math_mode == MPM_MATH_FAST && !p.overflow_check) ? MPM_PATH_CELL : MPM_PATH_TILED;
     return MPM_PATH_REFERENCE;
 }
 
@@ -175,9 +176,10 @@ extern "C" int32_t mpm_create(const MpmParams* p, int64_t max_particles, int32_t
     CKC(cudaMalloc(&s->orig_id, sizeof(uint32_t) * s->pitch));
     CKC(cudaMalloc(&s->grid, 16 * s->ncells));
     CKC(cudaMalloc(&s->positions, sizeof(float4) * s->pitch));
-    CKC(cudaMalloc(&s->overflow_flag, sizeof(int32_t)));
+    CKC(cudaMalloc(&s->overflow_flag, 2 * sizeof(int32_t)));  // [0] overflow detector, [1] particles skipped for their position
+    s->dp.flags = s->overflow_flag;
     CKC(cudaMemsetAsync(s->grid, 0, 16 * s->ncells, s->stream));
-    CKC(cudaMemsetAsync(s->overflow_flag, 0, sizeof(int32_t), s->stream));
+    CKC(cudaMemsetAsync(s->overflow_flag, 0, 2 * sizeof(int32_t), s->stream));
     s->path = resolve_path(s->hp);
     if (s->path == MPM_PATH_TILED && !(s->hp.dim == 3 && s->hp.grid_mode == MPM_GRID_FIXED)) {
         s->err = "MPM_PATH_TILED implements the 3D fixed-point grid; use MPM_PATH_AUTO or MPM_PATH_REFERENCE";
@@ -185,6 +187,10 @@ extern "C" int32_t mpm_create(const MpmParams* p, int64_t max_particles, int32_t
     }
     if (s->path == MPM_PATH_CELL && !(s->hp.dim == 3 && s->hp.grid_mode == MPM_GRID_FIXED && s->hp.math_mode == MPM_MATH_FAST)) {
         s->err = "MPM_PATH_CELL implements dim = 3, MPM_GRID_FIXED, MPM_MATH_FAST; use MPM_PATH_AUTO";
+        return bail(MPM_ERR_INVALID);
+    }
+    if (s->path == MPM_PATH_CELL && s->hp.overflow_check) {
+        s->err = "overflow_check is a debug detector of the reference-shaped and tiled kernels; use MPM_PATH_AUTO or MPM_PATH_TILED with it";
         return bail(MPM_ERR_INVALID);
     }
     s->sort_interval = s->hp.sort_interval > 0 ? s->hp.sort_interval : 1;
@@ -211,7 +217,7 @@ extern "C" int32_t mpm_destroy(MpmSolver* s)
     bin_destroy(s);
     for (cudaEvent_t ev : s->ev) cudaEventDestroy(ev);
     cudaFree(s->part); cudaFree(s->part_alt); cudaFree(s->rec); cudaFree(s->orig_id); cudaFree(s->orig_id_alt);
-    cudaFree(s->grid); cudaFree(s->positions); cudaFree(s->positions_b); cudaFree(s->overflow_flag);
+    cudaFree(s->grid); cudaFree(s->positions); cudaFree(s->positions_b); cudaFree(s->overflow_flag); cudaFree(s->stage);
     if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); }
     for (int k = 0; k < 2; ++k) { if (s->pos_ready[k]) cudaEventDestroy(s->pos_ready[k]); if (s->pos_copied[k]) cudaEventDestroy(s->pos_copied[k]); }
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -272,6 +278,51 @@ bool comm_partitioned(const MpmSolver* s);  // the planes hold this rank's local
 void comm_mark_global(MpmSolver* s);       // the planes now hold the global set again
 }
 
+// Uploaded / loaded positions must be finite and leave room for the 3x3(x3) stencil: [1, R-1) per axis (the
+// reference clamps to [1, R-2] / [2, R-2] after every step, so nothing it produces is outside).
+__global__ void __launch_bounds__(256) k_count_bad_positions(mpm::ParticleView pv, int64_t first, int64_t n, int dim, float rx, float ry, float rz, int* bad)
+{
+    const int64_t i = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= first + n) return;
+    const float x = pv.at(mpm::PX, i), y = pv.at(mpm::PY, i), z = pv.at(mpm::PZ, i);
+    bool ok = x >= 1.0f && x < rx - 1.0f && y >= 1.0f && y < ry - 1.0f;  // (false for NaN)
+    if (dim == 3) ok = ok && z >= 1.0f && z < rz - 1.0f;
+    if (!ok) atomicAdd(bad, 1);
+}
+
+static int validate_positions(MpmSolver* s, int64_t first, int64_t n)
+{
+    if (n <= 0) return MPM_OK;
+    int* d_bad = nullptr;
+    int bad = 0;
+    CK(cudaMalloc(&d_bad, sizeof(int)));
+    cudaMemsetAsync(d_bad, 0, sizeof(int), s->stream);
+    k_count_bad_positions<<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>(s->view(), first, n, s->hp.dim, (float)s->hp.grid_size[0], (float)s->hp.grid_size[1],
+                                                                           (float)s->hp.grid_size[2], d_bad);
+    cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, s->stream);
+    cudaError_t e = cudaStreamSynchronize(s->stream);
+    cudaFree(d_bad);
+    if (e != cudaSuccess) return fail(s, MPM_ERR_CUDA, cudaGetErrorString(e));
+    if (bad) {
+        s->n = 0;  // the set is rejected as a whole
+        return fail(s, MPM_ERR_DOMAIN, std::to_string(bad) + " of " + std::to_string(n) + " particle positions are non-finite or outside [1, R-1)");
+    }
+    return MPM_OK;
+}
+
+// grow-only device staging buffer for uploads / downloads (they used to cudaMalloc + cudaFree on every call)
+static int stage_buffer(MpmSolver* s, size_t bytes, float** out)
+{
+    if (bytes > s->stage_bytes) {
+        cudaFree(s->stage);
+        s->stage = nullptr; s->stage_bytes = 0;
+        CK(cudaMalloc(&s->stage, bytes));
+        s->stage_bytes = bytes;
+    }
+    *out = reinterpret_cast<float*>(s->stage);
+    return MPM_OK;
+}
+
 static void particles_changed(MpmSolver* s)
 {
     s->positions_valid = false;
@@ -324,7 +375,7 @@ static int add_block(MpmSolver* s, const float lo[3], const float hi[3], float s
     if (e != cudaSuccess) return fail(s, MPM_ERR_CUDA, cudaGetErrorString(e));
     s->n = base + cnt;
     particles_changed(s);
-    return MPM_OK;
+    return validate_positions(s, base, cnt);
 }
 
 extern "C" int32_t mpm_init_block(MpmSolver* s, const float lo[3], const float hi[3], float spacing)
@@ -344,18 +395,17 @@ extern "C" int32_t mpm_upload_particles(MpmSolver* s, const MpmParticle80* ps, i
     CK(cudaSetDevice(s->device));
     if (n > 0) {
         float* stage = nullptr;
-        CK(cudaMalloc(&stage, sizeof(MpmParticle80) * n));
+        { int rc_ = stage_buffer(s, sizeof(MpmParticle80) * n, &stage); if (rc_) return rc_; }
         cudaMemcpyAsync(stage, ps, sizeof(MpmParticle80) * n, cudaMemcpyHostToDevice, s->stream);
         launch_aos80_to_soa(stage, s->view(), 0, n, s->stream);
         launch_iota(s->orig_id, 0, n, s->stream);
         s->launches += 2;
         cudaError_t e = cudaStreamSynchronize(s->stream);
-        cudaFree(stage);
         if (e != cudaSuccess) return fail(s, MPM_ERR_CUDA, cudaGetErrorString(e));
     }
     s->n = n;
     particles_changed(s);
-    return MPM_OK;
+    return validate_positions(s, 0, n);
 }
 
 extern "C" int32_t mpm_upload_particles_soa(MpmSolver* s, const float* pos, const float* vel, const float* C,
@@ -366,7 +416,7 @@ extern "C" int32_t mpm_upload_particles_soa(MpmSolver* s, const float* pos, cons
     CK(cudaSetDevice(s->device));
     if (n > 0) {
         float* stage = nullptr;
-        CK(cudaMalloc(&stage, sizeof(float) * 16 * n));
+        { int rc_ = stage_buffer(s, sizeof(float) * 16 * n, &stage); if (rc_) return rc_; }
         float* dpos = stage; float* dvel = stage + 3 * n; float* dC = stage + 6 * n; float* dm = stage + 15 * n;
         cudaMemcpyAsync(dpos, pos, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, s->stream);
         if (vel) cudaMemcpyAsync(dvel, vel, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, s->stream);
@@ -376,12 +426,11 @@ extern "C" int32_t mpm_upload_particles_soa(MpmSolver* s, const float* pos, cons
         launch_iota(s->orig_id, 0, n, s->stream);
         s->launches += 2;
         cudaError_t e = cudaStreamSynchronize(s->stream);
-        cudaFree(stage);
         if (e != cudaSuccess) return fail(s, MPM_ERR_CUDA, cudaGetErrorString(e));
     }
     s->n = n;
     particles_changed(s);
-    return MPM_OK;
+    return validate_positions(s, 0, n);
 }
 
 extern "C" int32_t mpm_download_particles(MpmSolver* s, MpmParticle80* ps, int64_t cap)
@@ -393,13 +442,12 @@ extern "C" int32_t mpm_download_particles(MpmSolver* s, MpmParticle80* ps, int64
     if (s->n == 0) return MPM_OK;
     ensure_planes(s);
     float* stage = nullptr;
-    CK(cudaMalloc(&stage, sizeof(MpmParticle80) * s->n));
+    { int rc_ = stage_buffer(s, sizeof(MpmParticle80) * s->n, &stage); if (rc_) return rc_; }
     // multi-GPU ranks return their local particles in slot order (global indices: mpm_download_ids)
     launch_soa_to_aos80(s->view(), s->comm ? nullptr : s->orig_id, stage, s->n, s->stream);
     s->launches += 1;
     cudaMemcpyAsync(ps, stage, sizeof(MpmParticle80) * s->n, cudaMemcpyDeviceToHost, s->stream);
     cudaError_t e = cudaStreamSynchronize(s->stream);
-    cudaFree(stage);
     if (e != cudaSuccess) return fail(s, MPM_ERR_CUDA, cudaGetErrorString(e));
     return MPM_OK;
 }
@@ -414,7 +462,7 @@ extern "C" int32_t mpm_download_particles_soa(MpmSolver* s, float* pos, float* v
     if (n == 0) return MPM_OK;
     ensure_planes(s);
     float* stage = nullptr;
-    CK(cudaMalloc(&stage, sizeof(float) * 16 * n));
+    { int rc_ = stage_buffer(s, sizeof(float) * 16 * n, &stage); if (rc_) return rc_; }
     float* dpos = stage; float* dvel = stage + 3 * n; float* dC = stage + 6 * n; float* dm = stage + 15 * n;
     // multi-GPU ranks return their local particles in slot order (global indices: mpm_download_ids)
     launch_soa_to_packed(s->view(), s->comm ? nullptr : s->orig_id, dpos, dvel, dC, dm, n, s->stream);
@@ -424,7 +472,6 @@ extern "C" int32_t mpm_download_particles_soa(MpmSolver* s, float* pos, float* v
     if (C) cudaMemcpyAsync(C, dC, sizeof(float) * 9 * n, cudaMemcpyDeviceToHost, s->stream);
     if (mass) cudaMemcpyAsync(mass, dm, sizeof(float) * n, cudaMemcpyDeviceToHost, s->stream);
     cudaError_t e = cudaStreamSynchronize(s->stream);
-    cudaFree(stage);
     if (e != cudaSuccess) return fail(s, MPM_ERR_CUDA, cudaGetErrorString(e));
     return MPM_OK;
 }
@@ -442,57 +489,150 @@ extern "C" int32_t mpm_download_grid(MpmSolver* s, MpmCell16* cells, int64_t cap
 }
 
 // ---------------------------------------------------------------- checkpoint / resume
+// File (little-endian): 64-byte header | parameter block | n particle records of 80 bytes (H:8-22) | [n original indices].
+// Version 2 carries the parameters the state was produced with (MpmParams + collider list): loading into a solver whose
+// physics differs is refused instead of silently resuming something else.  Under a communicator every rank writes its own
+// particles with their global indices to "<path>.rank<r>of<w>"; mpm_load_state(path) finds those files, puts every
+// particle back at its original index and uploads the whole set (on every rank when a communicator is attached: the slab
+// partition then keeps each rank's share, for any world size).
 struct StateHeader {
     char magic[8];
     uint32_t version;
     int32_t dim;
     int32_t grid[3];
-    int32_t pad0;
+    int32_t has_ids;     // v2: 1 = a table of original indices follows the records (a rank's share of a multi-GPU state)
     int64_t n;
     int64_t steps;
-    int64_t pad1[2];
+    int32_t rank, world; // v2 (0 / 1 for a single-GPU state)
+    int64_t n_global;    // v2: particles of the whole scene
 };
 static_assert(sizeof(StateHeader) == 64, "checkpoint header is 64 bytes");
+struct StateParams {
+    MpmParams p;
+    int32_t n_extra;
+    float extra[MPM_MAX_EXTRA_SPHERES][4];
+};
+namespace mpm { int64_t comm_global_count(const MpmSolver* s); int comm_rank_world(const MpmSolver* s, int* rank, int* world); }
+
+static bool same_physics(const MpmParams& a, const MpmParams& b, std::string& why)
+{
+#define SAME(f) if (memcmp(&a.f, &b.f, sizeof(a.f)) != 0) { why = #f; return false; }
+    SAME(dim) SAME(grid_size) SAME(dt) SAME(gravity) SAME(rest_density) SAME(dynamic_viscosity) SAME(eos_stiffness) SAME(eos_power)
+    SAME(grid_mode) SAME(fixed_point_mult) SAME(stress_form) SAME(eq16_order) SAME(bc_mode) SAME(bc_hi_off) SAME(bc_friction)
+    SAME(clamp_min) SAME(clamp_max_off) SAME(wall_min) SAME(wall_max_off) SAME(wall_gain) SAME(interaction) SAME(sphere_radius)
+    SAME(mouse_radius) SAME(math_mode)
+#undef SAME
+    return true;  // (sphere / mouse position are per-frame inputs, the kernel path and sort interval do not change results in strict mode)
+}
 
 extern "C" int32_t mpm_save_state(MpmSolver* s, const char* path)
 {
     if (!s || !path) return MPM_ERR_INVALID;
-    if (s->comm) return fail(s, MPM_ERR_STATE, "multi-GPU: checkpoint each rank's particles through mpm_download_particles + mpm_download_ids");
+    CK(cudaSetDevice(s->device));
+    { int rc = comm_partition(s); if (rc) return rc; }
     std::vector<MpmParticle80> buf((size_t)std::max<int64_t>(s->n, 1));
-    int rc = s->n > 0 ? mpm_download_particles(s, buf.data(), s->n) : MPM_OK;
-    if (rc) return rc;
+    std::vector<uint32_t> ids;
     StateHeader h{};
+    std::string file = path;
+    if (s->comm) {  // a rank's local particles in slot order + their global indices
+        int rank = 0, world = 1;
+        comm_rank_world(s, &rank, &world);
+        ensure_planes(s);
+        float* stage = nullptr;
+        if (s->n > 0) {
+            { int rc_ = stage_buffer(s, sizeof(MpmParticle80) * s->n, &stage); if (rc_) return rc_; }
+            launch_soa_to_aos80(s->view(), nullptr, stage, s->n, s->stream);
+            CK(cudaMemcpyAsync(buf.data(), stage, sizeof(MpmParticle80) * s->n, cudaMemcpyDeviceToHost, s->stream));
+            ids.resize((size_t)s->n);
+            CK(cudaMemcpyAsync(ids.data(), s->orig_id, sizeof(uint32_t) * s->n, cudaMemcpyDeviceToHost, s->stream));
+            CK(cudaStreamSynchronize(s->stream));
+        }
+        h.has_ids = 1; h.rank = rank; h.world = world; h.n_global = comm_global_count(s);
+        file += ".rank" + std::to_string(rank) + "of" + std::to_string(world);
+    } else {
+        int rc = s->n > 0 ? mpm_download_particles(s, buf.data(), s->n) : MPM_OK;
+        if (rc) return rc;
+        h.world = 1; h.n_global = s->n;
+    }
     memcpy(h.magic, "MPMB200", 8);
-    h.version = 1; h.dim = s->hp.dim;
+    h.version = 2; h.dim = s->hp.dim;
     for (int a = 0; a < 3; ++a) h.grid[a] = s->hp.grid_size[a];
     h.n = s->n; h.steps = s->steps;
-    FILE* f = fopen(path, "wb");
-    if (!f) return fail(s, MPM_ERR_INVALID, std::string("cannot open for writing: ") + path);
-    const bool ok = fwrite(&h, sizeof(h), 1, f) == 1 && (s->n == 0 || fwrite(buf.data(), sizeof(MpmParticle80), (size_t)s->n, f) == (size_t)s->n);
-    if (fclose(f) != 0 || !ok) return fail(s, MPM_ERR_INVALID, std::string("short write: ") + path);
+    StateParams sp{};
+    sp.p = s->hp; sp.n_extra = s->dp.n_extra;
+    memcpy(sp.extra, s->dp.extra, sizeof(sp.extra));
+    FILE* f = fopen(file.c_str(), "wb");
+    if (!f) return fail(s, MPM_ERR_INVALID, std::string("cannot open for writing: ") + file);
+    bool ok = fwrite(&h, sizeof(h), 1, f) == 1 && fwrite(&sp, sizeof(sp), 1, f) == 1 &&
+              (s->n == 0 || fwrite(buf.data(), sizeof(MpmParticle80), (size_t)s->n, f) == (size_t)s->n);
+    if (ok && h.has_ids && s->n > 0) ok = fwrite(ids.data(), sizeof(uint32_t), (size_t)s->n, f) == (size_t)s->n;
+    if (fclose(f) != 0 || !ok) return fail(s, MPM_ERR_INVALID, std::string("short write: ") + file);
+    return MPM_OK;
+}
+
+// one checkpoint file -> its records land in `all` (at their original index if the file carries one, else in file order)
+static int read_state_file(MpmSolver* s, const std::string& file, std::vector<MpmParticle80>& all, StateHeader& h, int64_t* filled)
+{
+    FILE* f = fopen(file.c_str(), "rb");
+    if (!f) return fail(s, MPM_ERR_INVALID, std::string("cannot open: ") + file);
+    auto bad = [&](const std::string& why) { fclose(f); return fail(s, MPM_ERR_INVALID, file + ": " + why); };
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "MPMB200", 8) != 0 || (h.version != 1 && h.version != 2))
+        return bad("not an mpm_b200 checkpoint (bad header)");
+    if (h.dim != s->hp.dim || h.grid[0] != s->hp.grid_size[0] || h.grid[1] != s->hp.grid_size[1] || h.grid[2] != s->hp.grid_size[2])
+        return bad("checkpoint was written for a different dim / grid size");
+    if (h.version == 1) { h.has_ids = 0; h.rank = 0; h.world = 1; h.n_global = h.n; }
+    else {
+        StateParams sp{};
+        if (fread(&sp, sizeof(sp), 1, f) != 1 || sp.p.struct_size != (int32_t)sizeof(MpmParams)) return bad("parameter block missing or of another ABI version");
+        std::string why;
+        if (!same_physics(sp.p, s->hp, why)) return bad("written with a different `" + why + "`: set the solver's parameters to the checkpoint's first");
+        if (sp.n_extra != s->dp.n_extra || memcmp(sp.extra, s->dp.extra, sizeof(float) * 4 * (size_t)std::max(sp.n_extra, 0)) != 0)
+            return bad("written with a different collider list (mpm_set_colliders)");
+    }
+    if (h.n < 0 || h.n_global < h.n || h.n_global > s->cap) return bad("holds more particles than max_particles");
+    if ((int64_t)all.size() < h.n_global) all.resize((size_t)h.n_global);
+    std::vector<MpmParticle80> buf((size_t)std::max<int64_t>(h.n, 1));
+    if (h.n > 0 && fread(buf.data(), sizeof(MpmParticle80), (size_t)h.n, f) != (size_t)h.n) return bad("truncated");
+    if (h.has_ids) {
+        std::vector<uint32_t> ids((size_t)std::max<int64_t>(h.n, 1));
+        if (h.n > 0 && fread(ids.data(), sizeof(uint32_t), (size_t)h.n, f) != (size_t)h.n) return bad("truncated (index table)");
+        for (int64_t i = 0; i < h.n; ++i) {
+            if ((int64_t)ids[(size_t)i] >= h.n_global) return bad("original index out of range");
+            all[ids[(size_t)i]] = buf[(size_t)i];
+        }
+    } else {
+        std::copy(buf.begin(), buf.begin() + h.n, all.begin());
+    }
+    fclose(f);
+    *filled += h.n;
     return MPM_OK;
 }
 
 extern "C" int32_t mpm_load_state(MpmSolver* s, const char* path)
 {
     if (!s || !path) return MPM_ERR_INVALID;
-    FILE* f = fopen(path, "rb");
-    if (!f) return fail(s, MPM_ERR_INVALID, std::string("cannot open: ") + path);
+    std::vector<MpmParticle80> all;
     StateHeader h{};
-    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "MPMB200", 8) != 0 || h.version != 1) {
-        fclose(f);
-        return fail(s, MPM_ERR_INVALID, "not an mpm_b200 checkpoint (bad header)");
+    int64_t filled = 0;
+    FILE* probe = fopen(path, "rb");
+    if (probe) {
+        fclose(probe);
+        int rc = read_state_file(s, path, all, h, &filled);
+        if (rc) return rc;
+    } else {  // the per-rank files of a multi-GPU state
+        int world = 0;
+        for (int w = 1; w <= 64 && !world; ++w) {
+            FILE* f = fopen((std::string(path) + ".rank0of" + std::to_string(w)).c_str(), "rb");
+            if (f) { fclose(f); world = w; }
+        }
+        if (!world) return fail(s, MPM_ERR_INVALID, std::string("cannot open: ") + path + " (nor " + path + ".rank0of<world>)");
+        for (int r = 0; r < world; ++r) {
+            int rc = read_state_file(s, std::string(path) + ".rank" + std::to_string(r) + "of" + std::to_string(world), all, h, &filled);
+            if (rc) return rc;
+        }
     }
-    if (h.dim != s->hp.dim || h.grid[0] != s->hp.grid_size[0] || h.grid[1] != s->hp.grid_size[1] || h.grid[2] != s->hp.grid_size[2]) {
-        fclose(f);
-        return fail(s, MPM_ERR_INVALID, "checkpoint was written for a different dim / grid size");
-    }
-    if (h.n < 0 || h.n > s->cap) { fclose(f); return fail(s, MPM_ERR_INVALID, "checkpoint holds more particles than max_particles"); }
-    std::vector<MpmParticle80> buf((size_t)std::max<int64_t>(h.n, 1));
-    const bool ok = h.n == 0 || fread(buf.data(), sizeof(MpmParticle80), (size_t)h.n, f) == (size_t)h.n;
-    fclose(f);
-    if (!ok) return fail(s, MPM_ERR_INVALID, "checkpoint is truncated");
-    int rc = mpm_upload_particles(s, buf.data(), h.n);
+    if (filled != h.n_global) return fail(s, MPM_ERR_INVALID, "checkpoint files hold " + std::to_string(filled) + " of " + std::to_string(h.n_global) + " particles");
+    int rc = mpm_upload_particles(s, all.data(), h.n_global);  // (validates the positions)
     if (rc) return rc;
     s->steps = h.steps;
     return MPM_OK;
@@ -660,11 +800,14 @@ extern "C" int32_t mpm_sync(MpmSolver* s)
     if (!s) return MPM_ERR_INVALID;
     CK(cudaSetDevice(s->device));
     CK(cudaStreamSynchronize(s->stream));
-    if (s->hp.overflow_check) {
-        int32_t f = 0;
-        CK(cudaMemcpy(&f, s->overflow_flag, sizeof(f), cudaMemcpyDeviceToHost));
-        if (f) return fail(s, MPM_ERR_OVERFLOW, "fixed-point grid accumulator overflowed int32 (lower fixed_point_mult)");
+    int32_t f[2] = {0, 0};
+    CK(cudaMemcpy(f, s->overflow_flag, sizeof(f), cudaMemcpyDeviceToHost));
+    if (f[1]) {  // reported once, then cleared: the skipped particles are still there (unchanged) and the caller may go on
+        CK(cudaMemset(s->overflow_flag + 1, 0, sizeof(int32_t)));
+        return fail(s, MPM_ERR_DOMAIN, std::to_string(f[1]) + " particle position(s) non-finite or outside [1, R-1) were skipped since the last "
+                                       "mpm_sync (the reference throws IndexOutOfRangeException here)");
     }
+    if (s->hp.overflow_check && f[0]) return fail(s, MPM_ERR_OVERFLOW, "fixed-point grid accumulator overflowed int32 (lower fixed_point_mult)");
     return MPM_OK;
 }
 

@@ -536,176 +536,239 @@ __global__ void __launch_bounds__(1024) k_far_sort(uint32_t* __restrict__ far_li
 
 __device__ __forceinline__ uint32_t far_hash(uint32_t key) { return (key * 2654435761u) >> 21; }  // 11 bits
 
+struct RankArgs {
+    const uint32_t* keys;
+    const uint32_t* bsum_prev;
+    const uint32_t* bbase_prev;
+    const uint32_t* active_prev;
+    const uint32_t* nact_prev;
+    RankGeom g;
+    const uint32_t* tcount;
+    const uint32_t* far_list;
+    const uint32_t* far_n;
+    const uint2* cellmeta;
+    const uint32_t* cnts;
+    const uint32_t* pstart;
+    const uint16_t* stab;
+    uint32_t* fill;
+    uint32_t* src_of;
+    const uint32_t* id_src;
+    uint32_t* id_dst;
+    uint32_t* dbg_rank;  // VERIFY only
+    uint32_t* dbg_bad;
+};
+
+// tiles with more rows than this are ranked by a whole CTA (k_rank_place_heavy), the others by one warp each
+constexpr uint32_t HEAVY_ROWS = 256;
+
+// One tile, W warps.  W = 1: a warp on its own (no block-wide barrier anywhere: the usual tile of ~100 rows is latency-bound,
+// and thousands of independent warps hide that); W > 1: a CTA of W warps for the pile-up tiles of an evolved scene, each
+// warp owning the w-th part of the rows, with a counting pass first so that every warp knows where its ranks start.
 // VERIFY: nothing is stored; the rank of every old slot goes to dbg_rank and a mismatch between the layout in place
-// (src_of) and the one this run derives is counted in dbg_bad (mpm_debug_last_sort)
-template <int CELL_BITS, bool VERIFY>
-__global__ void __launch_bounds__(RankCfg<CELL_BITS>::THREADS, 8) k_rank_place(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ bsum_prev,
-                                                                            const uint32_t* __restrict__ bbase_prev, const uint32_t* __restrict__ active_prev,
-                                                                            const uint32_t* __restrict__ nact_prev, RankGeom g,
-                                                                            const uint32_t* __restrict__ tcount, const uint32_t* __restrict__ far_list,
-                                                                            const uint32_t* __restrict__ far_n, const uint2* __restrict__ cellmeta,
-                                                                            const uint32_t* __restrict__ cnts, const uint32_t* __restrict__ pstart,
-                                                                            const uint16_t* __restrict__ stab, uint32_t* __restrict__ fill,
-                                                                            uint32_t* __restrict__ src_of, const uint32_t* __restrict__ id_src,
-                                                                            uint32_t* __restrict__ id_dst, uint32_t* __restrict__ dbg_rank,
-                                                                            uint32_t* __restrict__ dbg_bad)
+// (src_of, ids) and the one this run derives is counted in dbg_bad (mpm_debug_last_sort).
+template <int CELL_BITS, int W, bool VERIFY>
+__device__ __forceinline__ void rank_tile(const RankArgs& A, uint32_t tile, uint32_t s0, uint32_t s1, uint32_t* wcnt, uint32_t* off, uint32_t* nb_tile,
+                                          uint32_t* nb_first, const uint32_t* bloom, uint32_t nfar, bool overflow)
 {
     using C = RankCfg<CELL_BITS>;
-    constexpr int RB = 8;  // rows per batch: their loads are issued together
-    __shared__ uint32_t wcnt[C::W][C::RC];
-    __shared__ uint32_t off[C::RC];      // arrivals from lower tiles, per region cell
-    __shared__ uint32_t nb_tile[27], nb_first[28];  // neighbour tiles below this one and the running size of their overlap boxes
-    __shared__ uint32_t bloom[64];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    constexpr int GS = 32 * W;  // threads working on the tile
+    constexpr int RB = 4;       // rows per batch: their loads are issued together
+    const RankGeom& g = A.g;
+    const int lane = threadIdx.x & 31, w = (W == 1) ? 0 : (int)(threadIdx.x >> 5), gt = (W == 1) ? lane : (int)threadIdx.x;
     const unsigned lt = (1u << lane) - 1u;
-    const uint32_t nfar_all = far_n[0];
-    const bool overflow = nfar_all > (uint32_t)FAR_CAP;
-    const uint32_t nfar = overflow ? 0u : nfar_all;
-    if (nfar) {
-        if (threadIdx.x < 64) bloom[threadIdx.x] = 0;
-        __syncthreads();
-        for (uint32_t f = threadIdx.x; f < nfar; f += C::THREADS) { const uint32_t h = far_hash(far_list[2 * f + 1]); atomicOr(&bloom[h >> 5], 1u << (h & 31u)); }
-        __syncthreads();
+    auto sync = [&]() { if (W == 1) __syncwarp(); else __syncthreads(); };
+    const TileCtx tc = tile_ctx(tile, g);
+    const int tbx = tc.tbx, tby = tc.tby, tbz = tc.tbz;
+    for (int k = gt; k < W * C::RC; k += GS) wcnt[k] = 0;
+    if (W > 1) for (int k = gt; k < C::RC; k += GS) off[k] = 0;
+    // the 26 neighbouring tiles: those that come before this one and held particles contribute to the cells their
+    // region shares with ours (a box of 2 or T cells per axis)
+    if (gt < 27) {
+        const int dz = gt % 3 - 1, dy = gt / 3 % 3 - 1, dx = gt / 9 - 1;
+        const int bx = tbx + dx, by = tby + dy, bz = tbz + dz;
+        uint32_t t2 = 0xffffffffu;
+        if ((dx | dy | dz) != 0 && bx >= 0 && by >= 0 && bz >= 0 && bx < g.nbx && by < g.nby && bz < g.nbz) {
+            t2 = (uint32_t)((bx * g.nby + by) * g.nbz + bz);
+            if (t2 >= tile || A.bsum_prev[t2] == 0) t2 = 0xffffffffu;
+        }
+        nb_tile[gt] = t2;
     }
-    const uint32_t na = *nact_prev;
-    for (uint32_t t = blockIdx.x; t < na; t += gridDim.x) {
-        const uint32_t tile = active_prev[t];
-        const TileCtx tc = tile_ctx(tile, g);
-        const int tbx = tc.tbx, tby = tc.tby, tbz = tc.tbz;
-        for (int k = threadIdx.x; k < C::W * C::RC; k += C::THREADS) (&wcnt[0][0])[k] = 0;
-        for (int k = threadIdx.x; k < C::RC; k += C::THREADS) off[k] = 0;
-        // the 26 neighbouring tiles: those that come before this one and held particles contribute to the cells their
-        // region shares with ours (a box of 2 or T cells per axis)
-        if (threadIdx.x < 27) {
-            const int dz = (int)threadIdx.x % 3 - 1, dy = (int)threadIdx.x / 3 % 3 - 1, dx = (int)threadIdx.x / 9 - 1;
-            const int bx = tbx + dx, by = tby + dy, bz = tbz + dz;
-            uint32_t t2 = 0xffffffffu;
-            if ((dx | dy | dz) != 0 && bx >= 0 && by >= 0 && bz >= 0 && bx < g.nbx && by < g.nby && bz < g.nbz) {
-                t2 = (uint32_t)((bx * g.nby + by) * g.nbz + bz);
-                if (t2 >= tile || bsum_prev[t2] == 0) t2 = 0xffffffffu;
+    sync();
+    if (gt == 0) {
+        uint32_t run = 0;
+        for (int q = 0; q < 27; ++q) {
+            nb_first[q] = run;
+            if (nb_tile[q] != 0xffffffffu) {
+                const int dz = q % 3 - 1, dy = q / 3 % 3 - 1, dx = q / 9 - 1;
+                run += (uint32_t)((dx ? 2 : C::T) * (dy ? 2 : C::T) * (dz ? 2 : C::T));
             }
-            nb_tile[threadIdx.x] = t2;
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t run = 0;
-            for (int q = 0; q < 27; ++q) {
-                nb_first[q] = run;
-                if (nb_tile[q] != 0xffffffffu) {
-                    const int dz = q % 3 - 1, dy = q / 3 % 3 - 1, dx = q / 9 - 1;
-                    run += (uint32_t)((dx ? 2 : C::T) * (dy ? 2 : C::T) * (dz ? 2 : C::T));
-                }
-            }
-            nb_first[27] = run;
-        }
-        const uint32_t s0 = bbase_prev[tile], s1 = bbase_prev[tile + 1];
-        const uint32_t nrows = (s1 - s0 + 31u) >> 5, rpw = (nrows + C::W - 1) / C::W;
-        const uint32_t r0 = min((uint32_t)w * rpw, nrows), r1 = min(r0 + rpw, nrows);
+        nb_first[27] = run;
+    }
+    const uint32_t nrows = (s1 - s0 + 31u) >> 5, rpw = (nrows + W - 1) / W;
+    const uint32_t r0 = min((uint32_t)w * rpw, nrows), r1 = min(r0 + rpw, nrows);
+    if (W > 1) {
         // 1. counts of this warp's rows
-        for (uint32_t row = r0; row < r1; row += RB) {
-            uint32_t key[RB];
+        for (uint32_t row = r0; row < r1; row += 8) {
+            uint32_t key[8];
 #pragma unroll
-            for (int j = 0; j < RB; ++j) {
+            for (int j = 0; j < 8; ++j) {
                 const uint32_t i = s0 + (row + j) * 32u + lane;
-                key[j] = (row + j < r1 && i < s1) ? keys[i] : 0xffffffffu;
+                key[j] = (row + j < r1 && i < s1) ? A.keys[i] : 0xffffffffu;
             }
 #pragma unroll
-            for (int j = 0; j < RB; ++j) {
+            for (int j = 0; j < 8; ++j) {
                 const uint32_t i = s0 + (row + j) * 32u + lane;
                 if (row + j < r1 && i < s1) {
                     const int r = region_index<CELL_BITS>(key[j], tc, g);
-                    if (r >= 0) atomicAdd(&wcnt[w][r], 1u);
+                    if (r >= 0) atomicAdd(&wcnt[w * C::RC + r], 1u);
                 }
             }
         }
-        __syncthreads();
-        // 2a. arrivals from lower tiles: all (neighbour, shared cell) pairs as one flat index space, so that the loads
-        // of a thread are independent of each other
-        for (uint32_t q = threadIdx.x; q < nb_first[27]; q += C::THREADS) {
-            int nb = 0;
-            while (nb_first[nb + 1] <= q) ++nb;   // (<= 26 steps; entries of absent neighbours are empty ranges)
-            const int dz = nb % 3 - 1, dy = nb / 3 % 3 - 1, dx = nb / 9 - 1;
-            const int ex = dx ? 2 : C::T, ey = dy ? 2 : C::T, ez = dz ? 2 : C::T;
-            uint32_t c = q - nb_first[nb];
-            const int cz = (int)(c % (uint32_t)ez), cy = (int)(c / (uint32_t)ez % (uint32_t)ey), cx = (int)(c / (uint32_t)(ez * ey));
-            (void)ex;
-            // our region coordinate r and the neighbour's r' = r - d * B on each axis: d = -1 -> r in {0, 1}; d = +1 -> r in {B, B + 1}
-            const int rx = dx < 0 ? cx : dx > 0 ? C::B + cx : cx, ry = dy < 0 ? cy : dy > 0 ? C::B + cy : cy, rz = dz < 0 ? cz : dz > 0 ? C::B + cz : cz;
-            const int qx = rx - dx * C::B, qy = ry - dy * C::B, qz = rz - dz * C::B;
-            const uint32_t v = tcount[(size_t)nb_tile[nb] * C::RC + (size_t)((qx * C::T + qy) * C::T + qz)];
-            if (v) atomicAdd(&off[(rx * C::T + ry) * C::T + rz], v);
-        }
-        __syncthreads();
+    }
+    sync();
+    // 2a. arrivals from lower tiles: all (neighbour, shared cell) pairs as one flat index space, so that the loads of a
+    // thread are independent of each other.  (One warp: straight into its counters.)
+    uint32_t* acc = (W == 1) ? wcnt : off;
+    for (uint32_t q = gt; q < nb_first[27]; q += GS) {
+        int nb = 0;
+        while (nb_first[nb + 1] <= q) ++nb;   // (<= 26 steps; entries of absent neighbours are empty ranges)
+        const int dz = nb % 3 - 1, dy = nb / 3 % 3 - 1, dx = nb / 9 - 1;
+        const int ey = dy ? 2 : C::T, ez = dz ? 2 : C::T;
+        const uint32_t c = q - nb_first[nb];
+        const int cz = (int)(c % (uint32_t)ez), cy = (int)(c / (uint32_t)ez % (uint32_t)ey), cx = (int)(c / (uint32_t)(ez * ey));
+        // our region coordinate r and the neighbour's r' = r - d * B on each axis: d = -1 -> r in {0, 1}; d = +1 -> r in {B, B + 1}
+        const int rx = dx > 0 ? C::B + cx : cx, ry = dy > 0 ? C::B + cy : cy, rz = dz > 0 ? C::B + cz : cz;
+        const int qx = rx - dx * C::B, qy = ry - dy * C::B, qz = rz - dz * C::B;
+        const uint32_t v = A.tcount[(size_t)nb_tile[nb] * C::RC + (size_t)((qx * C::T + qy) * C::T + qz)];
+        if (v) atomicAdd(&acc[(rx * C::T + ry) * C::T + rz], v);
+    }
+    sync();
+    if (W > 1) {
         // 2b. starting rank of every (warp, region cell): arrivals from lower tiles, then the warps in order
-        for (int k = threadIdx.x; k < C::RC; k += C::THREADS) {
+        for (int k = gt; k < C::RC; k += GS) {
             uint32_t o = off[k];
 #pragma unroll
-            for (int q = 0; q < C::W; ++q) { const uint32_t c = wcnt[q][k]; wcnt[q][k] = o; o += c; }
+            for (int q = 0; q < W; ++q) { const uint32_t c = wcnt[q * C::RC + k]; wcnt[q * C::RC + k] = o; o += c; }
         }
-        __syncthreads();
-        // 3. the warp's rows in order (batches of 4: the unrolled body of 8 no longer fitted the instruction cache)
-        constexpr int RB3 = 4;
-        for (uint32_t row = r0; row < r1; row += RB3) {
-            uint32_t key[RB3], id[RB3], rc[RB3];
-            int rg[RB3];
-            bool valid[RB3];
+        sync();
+    }
+    // 3. the warp's rows in order: rank = counter + lower lanes of the row with the same cell
+    uint32_t* ctr = wcnt + w * C::RC;
+    for (uint32_t row = r0; row < r1; row += RB) {
+        uint32_t key[RB], id[RB], rc[RB];
+        int rg[RB];
+        bool valid[RB];
 #pragma unroll
-            for (int j = 0; j < RB3; ++j) {
-                const uint32_t i = s0 + (row + j) * 32u + lane;
-                valid[j] = row + j < r1 && i < s1;
-                key[j] = valid[j] ? keys[i] : 0u;
-                id[j] = valid[j] ? id_src[i] : 0u;
-            }
+        for (int j = 0; j < RB; ++j) {
+            const uint32_t i = s0 + (row + j) * 32u + lane;
+            valid[j] = row + j < r1 && i < s1;
+            key[j] = valid[j] ? A.keys[i] : 0u;
+            id[j] = valid[j] ? A.id_src[i] : 0u;
+        }
 #pragma unroll
-            for (int j = 0; j < RB3; ++j) {
-                rg[j] = valid[j] ? region_index<CELL_BITS>(key[j], tc, g) : -1;
-                const uint32_t tag = rg[j] >= 0 ? (uint32_t)rg[j] : (0x80000000u | (uint32_t)lane);
-                const unsigned peers = __match_any_sync(0xffffffffu, tag);
-                uint32_t base = 0;
-                if (rg[j] >= 0) base = wcnt[w][rg[j]];
-                rc[j] = base + (uint32_t)__popc(peers & lt);
-                __syncwarp();
-                if (rg[j] >= 0 && lane == __ffs(peers) - 1) wcnt[w][rg[j]] = base + (uint32_t)__popc(peers);
-                __syncwarp();
-            }
-            if (nfar) {
+        for (int j = 0; j < RB; ++j) {
+            rg[j] = valid[j] ? region_index<CELL_BITS>(key[j], tc, g) : -1;
+            const uint32_t tag = rg[j] >= 0 ? (uint32_t)rg[j] : (0x80000000u | (uint32_t)lane);
+            const unsigned peers = __match_any_sync(0xffffffffu, tag);
+            uint32_t base = 0;
+            if (rg[j] >= 0) base = ctr[rg[j]];
+            rc[j] = base + (uint32_t)__popc(peers & lt);
+            __syncwarp();
+            if (rg[j] >= 0 && lane == __ffs(peers) - 1) ctr[rg[j]] = base + (uint32_t)__popc(peers);
+            __syncwarp();
+        }
+        if (nfar) {
 #pragma unroll
-                for (int j = 0; j < RB3; ++j) {
-                    if (!valid[j]) continue;
-                    const uint32_t i = s0 + (row + j) * 32u + lane;
-                    const uint32_t h = far_hash(key[j]);
-                    if (rg[j] >= 0 && !((bloom[h >> 5] >> (h & 31u)) & 1u)) continue;
-                    uint32_t add = 0;  // far movers of lower slots that go to the same cell
-                    for (uint32_t f = 0; f < nfar && far_list[2 * f] < i; ++f) add += far_list[2 * f + 1] == key[j];
-                    if (rg[j] >= 0) rc[j] += add;
-                    else {
-                        const uint32_t blk = key[j] >> CELL_BITS;
-                        const int bz = (int)(blk % (uint32_t)g.nbz), by = (int)(blk / (uint32_t)g.nbz % (uint32_t)g.nby), bx = (int)(blk / (uint32_t)(g.nbz * g.nby));
-                        const int cx = bx * C::B + (int)((key[j] >> (2 * C::LOGB)) & (C::B - 1)), cy = by * C::B + (int)((key[j] >> C::LOGB) & (C::B - 1)),
-                                  cz = bz * C::B + (int)(key[j] & (C::B - 1));
-                        rc[j] = lower_tiles_sum<CELL_BITS>(cx, cy, cz, tile, g, bsum_prev, tcount) + add;
-                    }
-                }
-            }
-            if (overflow && !VERIFY) {
-#pragma unroll
-                for (int j = 0; j < RB3; ++j) if (valid[j]) rc[j] = atomicAdd(&fill[key[j]], 1u);
-            }
-#pragma unroll
-            for (int j = 0; j < RB3; ++j) {
+            for (int j = 0; j < RB; ++j) {
                 if (!valid[j]) continue;
                 const uint32_t i = s0 + (row + j) * 32u + lane;
-                const uint32_t dest = place_slot<CELL_BITS>(key[j], rc[j], cellmeta, cnts, pstart, stab);
-                if (VERIFY) {
-                    dbg_rank[i] = rc[j];
-                    if (src_of[dest] != i || id_dst[dest] != id[j]) atomicAdd(dbg_bad, 1u);
-                } else {
-                    src_of[dest] = i;
-                    id_dst[dest] = id[j];
+                const uint32_t h = far_hash(key[j]);
+                if (rg[j] >= 0 && !((bloom[h >> 5] >> (h & 31u)) & 1u)) continue;
+                uint32_t add = 0;  // far movers of lower slots that go to the same cell
+                for (uint32_t f = 0; f < nfar && A.far_list[2 * f] < i; ++f) add += A.far_list[2 * f + 1] == key[j];
+                if (rg[j] >= 0) rc[j] += add;
+                else {
+                    const uint32_t blk = key[j] >> CELL_BITS;
+                    const int bz = (int)(blk % (uint32_t)g.nbz), by = (int)(blk / (uint32_t)g.nbz % (uint32_t)g.nby), bx = (int)(blk / (uint32_t)(g.nbz * g.nby));
+                    const int cx = bx * C::B + (int)((key[j] >> (2 * C::LOGB)) & (C::B - 1)), cy = by * C::B + (int)((key[j] >> C::LOGB) & (C::B - 1)),
+                              cz = bz * C::B + (int)(key[j] & (C::B - 1));
+                    rc[j] = lower_tiles_sum<CELL_BITS>(cx, cy, cz, tile, g, A.bsum_prev, A.tcount) + add;
                 }
             }
         }
-        __syncthreads();
+        if (overflow && !VERIFY) {
+#pragma unroll
+            for (int j = 0; j < RB; ++j) if (valid[j]) rc[j] = atomicAdd(&A.fill[key[j]], 1u);
+        }
+#pragma unroll
+        for (int j = 0; j < RB; ++j) {
+            if (!valid[j]) continue;
+            const uint32_t i = s0 + (row + j) * 32u + lane;
+            const uint32_t dest = place_slot<CELL_BITS>(key[j], rc[j], A.cellmeta, A.cnts, A.pstart, A.stab);
+            if (VERIFY) {
+                A.dbg_rank[i] = rc[j];
+                if (A.src_of[dest] != i || A.id_dst[dest] != id[j]) atomicAdd(A.dbg_bad, 1u);
+            } else {
+                A.src_of[dest] = i;
+                A.id_dst[dest] = id[j];
+            }
+        }
+    }
+    sync();
+}
+
+// Bloom filter of the far movers' keys (2048 bits), built by every CTA that ranks
+__device__ __forceinline__ void build_bloom(uint32_t* bloom, const uint32_t* __restrict__ far_list, uint32_t nfar)
+{
+    if (threadIdx.x < 64) bloom[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t f = threadIdx.x; f < nfar; f += blockDim.x) { const uint32_t h = far_hash(far_list[2 * f + 1]); atomicOr(&bloom[h >> 5], 1u << (h & 31u)); }
+    __syncthreads();
+}
+
+// light tiles: one warp per tile, four tiles per CTA
+template <int CELL_BITS, bool VERIFY>
+__global__ void __launch_bounds__(128, 8) k_rank_place(const __grid_constant__ RankArgs A)
+{
+    using C = RankCfg<CELL_BITS>;
+    __shared__ uint32_t wcnt[4][C::RC];
+    __shared__ uint32_t nb_tile[4][28], nb_first[4][28];
+    __shared__ uint32_t bloom[64];
+    const int w = threadIdx.x >> 5;
+    const uint32_t nfar_all = A.far_n[0];
+    const bool overflow = nfar_all > (uint32_t)FAR_CAP;
+    const uint32_t nfar = overflow ? 0u : nfar_all;
+    if (nfar) build_bloom(bloom, A.far_list, nfar);
+    const uint32_t na = *A.nact_prev;
+    for (uint32_t t = blockIdx.x * 4 + w; t < na; t += gridDim.x * 4) {
+        const uint32_t tile = A.active_prev[t];
+        const uint32_t s0 = A.bbase_prev[tile], s1 = A.bbase_prev[tile + 1];
+        if (((s1 - s0 + 31u) >> 5) > HEAVY_ROWS) continue;  // (k_rank_place_heavy)
+        rank_tile<CELL_BITS, 1, VERIFY>(A, tile, s0, s1, wcnt[w], nullptr, nb_tile[w], nb_first[w], bloom, nfar, overflow);
+    }
+}
+
+// heavy tiles: a CTA of 8 warps per tile
+template <int CELL_BITS, bool VERIFY>
+__global__ void __launch_bounds__(256) k_rank_place_heavy(const __grid_constant__ RankArgs A)
+{
+    using C = RankCfg<CELL_BITS>;
+    constexpr int W = 8;
+    __shared__ uint32_t wcnt[W * C::RC];
+    __shared__ uint32_t off[C::RC];
+    __shared__ uint32_t nb_tile[28], nb_first[28];
+    __shared__ uint32_t bloom[64];
+    const uint32_t nfar_all = A.far_n[0];
+    const bool overflow = nfar_all > (uint32_t)FAR_CAP;
+    const uint32_t nfar = overflow ? 0u : nfar_all;
+    if (nfar) build_bloom(bloom, A.far_list, nfar);
+    const uint32_t na = *A.nact_prev;
+    for (uint32_t t = blockIdx.x; t < na; t += gridDim.x) {
+        const uint32_t tile = A.active_prev[t];
+        const uint32_t s0 = A.bbase_prev[tile], s1 = A.bbase_prev[tile + 1];
+        if (((s1 - s0 + 31u) >> 5) <= HEAVY_ROWS) continue;  // (uniform over the CTA)
+        rank_tile<CELL_BITS, W, VERIFY>(A, tile, s0, s1, wcnt, off, nb_tile, nb_first, bloom, nfar, overflow);
     }
 }
 
@@ -932,19 +995,21 @@ int bin_particles(MpmSolver* s)
     s->launches += 3;
     if (n > 0 && stable) {
         const RankGeom rg{st->nbx, st->nby, st->nbz};
-        const unsigned grid_c = rank_grid(st, 12), grid = rank_grid(st, 8);  // (resident CTAs per SM)
-#define RANK_ARGS st->keys, st->bsum2[pl], st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->far_list, st->far_n, st->cellmeta, st->cnts, \
-                  st->pstart, st->stab, st->fill, st->src_of, s->orig_id, s->orig_id_alt, nullptr, nullptr
+        const unsigned grid_c = rank_grid(st, 12), grid_l = rank_grid(st, 8), grid_h = rank_grid(st, 4);  // (CTAs per SM)
+        const RankArgs ra{st->keys, st->bsum2[pl], st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->far_list, st->far_n, st->cellmeta,
+                          st->cnts, st->pstart, st->stab, st->fill, st->src_of, s->orig_id, s->orig_id_alt, nullptr, nullptr};
         if (st->cell_bits == 9) {
             k_rank_count<9><<<grid_c, RankCfg<9>::THREADS, 0, s->stream>>>(st->keys, st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->far_list, st->far_n);
             k_far_sort<<<1, 1024, 0, s->stream>>>(st->far_list, st->far_n);
-            k_rank_place<9, false><<<grid, RankCfg<9>::THREADS, 0, s->stream>>>(RANK_ARGS);
+            k_rank_place<9, false><<<grid_l, 128, 0, s->stream>>>(ra);
+            k_rank_place_heavy<9, false><<<grid_h, 256, 0, s->stream>>>(ra);
         } else {
             k_rank_count<6><<<grid_c, RankCfg<6>::THREADS, 0, s->stream>>>(st->keys, st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->far_list, st->far_n);
             k_far_sort<<<1, 1024, 0, s->stream>>>(st->far_list, st->far_n);
-            k_rank_place<6, false><<<grid, RankCfg<6>::THREADS, 0, s->stream>>>(RANK_ARGS);
+            k_rank_place<6, false><<<grid_l, 128, 0, s->stream>>>(ra);
+            k_rank_place_heavy<6, false><<<grid_h, 256, 0, s->stream>>>(ra);
         }
-        s->launches += 3;
+        s->launches += 4;
     } else if (n > 0) {
         if (st->cell_bits == 9) k_place<9><<<nb, 256, 0, s->stream>>>(st->keys, n, st->cellmeta, st->cnts, st->pstart, st->stab, st->fill, st->src_of, s->orig_id, s->orig_id_alt);
         else k_place<6><<<nb, 256, 0, s->stream>>>(st->keys, n, st->cellmeta, st->cnts, st->pstart, st->stab, st->fill, st->src_of, s->orig_id, s->orig_id_alt);
@@ -986,11 +1051,15 @@ int bin_debug_last(MpmSolver* s, uint32_t* keys_before, uint32_t* perm, int64_t 
     CKB(cudaMemsetAsync(d_bad, 0, sizeof(uint32_t), s->stream));
     const int pl = st->prev_lay;
     const RankGeom rg{st->nbx, st->nby, st->nbz};
-    const unsigned grid = rank_grid(st, 8);
-#define VERIFY_ARGS st->keys, st->bsum2[pl], st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->far_list, st->far_n, st->cellmeta, st->cnts, \
-                    st->pstart, st->stab, st->fill, st->src_of, s->orig_id, s->orig_id_alt, d_rank, d_bad
-    if (st->cell_bits == 9) k_rank_place<9, true><<<grid, RankCfg<9>::THREADS, 0, s->stream>>>(VERIFY_ARGS);
-    else k_rank_place<6, true><<<grid, RankCfg<6>::THREADS, 0, s->stream>>>(VERIFY_ARGS);
+    const RankArgs ra{st->keys, st->bsum2[pl], st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->far_list, st->far_n, st->cellmeta,
+                      st->cnts, st->pstart, st->stab, st->fill, st->src_of, s->orig_id, s->orig_id_alt, d_rank, d_bad};
+    if (st->cell_bits == 9) {
+        k_rank_place<9, true><<<rank_grid(st, 8), 128, 0, s->stream>>>(ra);
+        k_rank_place_heavy<9, true><<<rank_grid(st, 4), 256, 0, s->stream>>>(ra);
+    } else {
+        k_rank_place<6, true><<<rank_grid(st, 8), 128, 0, s->stream>>>(ra);
+        k_rank_place_heavy<6, true><<<rank_grid(st, 4), 256, 0, s->stream>>>(ra);
+    }
     std::vector<uint32_t> keys((size_t)n), rank((size_t)n);
     uint32_t bad = 0;
     CKB(cudaMemcpyAsync(keys.data(), st->keys, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s->stream));

@@ -231,6 +231,7 @@ struct CommState {
     int64_t migrated_out = 0, migrated_in = 0, overflow_rounds = 0;
     int64_t recuts = 0;            // times mpm_comm_rebalance moved a cut
     int64_t slab_jump_clamps = 0;  // particles held back because they would have crossed more than one slab in a step
+    int64_t n_global = 0;          // particles of the whole scene (the set the last upload / init handed to every rank)
     uint32_t sent_prev[2] = {0, 0}, recv_prev[2] = {0, 0};  // particles that crossed each edge in the previous step
 };
 
@@ -294,6 +295,14 @@ static int comm_attach(MpmSolver* s, Transport* tr, int rank, int world)
         CKM(cudaMalloc(&s->orig_id_alt, sizeof(uint32_t) * s->pitch));
     }
     s->sort_interval = 1;  // arrivals are appended unbinned: re-bin every step
+    return MPM_OK;
+}
+
+int64_t comm_global_count(const MpmSolver* s) { return s->comm ? s->comm->n_global : s->n; }
+int comm_rank_world(const MpmSolver* s, int* rank, int* world)
+{
+    *rank = s->comm ? s->comm->rank : 0;
+    *world = s->comm ? s->comm->world : 1;
     return MPM_OK;
 }
 
@@ -378,6 +387,7 @@ int comm_partition(MpmSolver* s)
     CommState* c = s->comm;
     if (!c || !c->pending) return MPM_OK;
     const int64_t n_global = s->n;
+    c->n_global = n_global;
     const int rx = s->dp.Rx;
     // 1. x-plane histogram -> equal-count cuts (identical on every rank: same data, same arithmetic)
     unsigned long long* d_hist = nullptr;

@@ -35,6 +35,8 @@ struct DevParams {
     int interaction;
     float sphere[3], sphere_r, mouse[2], mouse_r;
     int overflow_check;
+    int32_t* flags;      // device: [0] sticky fixed-point overflow flag (overflow_check), [1] particles skipped because their
+                         // position was non-finite or outside the grid (the reference throws IndexOutOfRangeException there)
     int n_extra;         // further sphere repulsors (mpm_set_colliders), applied after the first one
     float extra[7][4];   // x, y, z, radius
 };
@@ -104,7 +106,41 @@ __device__ __forceinline__ float eos_pow(float x, const DevParams& P)
     return __double2float_rn(pow((double)x, (double)P.eos_p));
 }
 
-__device__ __forceinline__ float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
+// (fmaxf / fminf return the other operand for a NaN: a non-finite position is pulled back into the clamp box instead of
+// travelling on as NaN; for every other value this is v < lo ? lo : (v > hi ? hi : v))
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+
+// ---- guards.  The reference indexes the grid with whatever (int)pos gives and lets the managed runtime throw; here a
+// particle whose 3x3(x3) stencil would leave the (local) grid is skipped and counted, and mpm_sync reports it.
+__device__ __forceinline__ bool stencil_in_grid(const DevParams& P, int cx, int cy, int cz)
+{
+    return cx - 1 >= P.gx0 && cx + 1 < P.gx0 + P.nxl && cy >= 1 && cy + 1 < P.Ry && (P.dim == 2 || (cz >= 1 && cz + 1 < P.Rz));
+}
+__device__ __forceinline__ void flag_bad_particle(const DevParams& P) { atomicAdd(P.flags + 1, 1); }
+
+// ---- overflow detector (MpmParams.overflow_check): EncodeFixedPoint saturates / the int32 accumulators wrap silently in
+// the reference too; with the detector on, every encode and every integer add is checked and a sticky flag is raised.
+__device__ __forceinline__ int encode_fixed_checked(float f, const DevParams& P)
+{
+    if (P.overflow_check && !(fabsf(__fmul_rn(f, P.fmult)) < 2147483648.0f)) atomicExch(P.flags, 1);  // (also NaN)
+    return encode_fixed(f, P.fmult);
+}
+// truncation of a value that is already in fixed-point units (MPM_MATH_FAST pre-scales by the multiplier)
+__device__ __forceinline__ int f2i_checked(float x, const DevParams& P)
+{
+    if (P.overflow_check && !(fabsf(x) < 2147483648.0f)) atomicExch(P.flags, 1);
+    return __float2int_rz(x);
+}
+__device__ __forceinline__ void int_add_checked(int* p, int v, const DevParams& P)
+{
+    if (P.overflow_check) {
+        const int old = atomicAdd(p, v);
+        const int sum = (int)((unsigned)old + (unsigned)v);
+        if (((old ^ sum) & (v ^ sum)) < 0) atomicExch(P.flags, 1);  // operands of one sign, result of the other
+    } else {
+        atomicAdd(p, v);
+    }
+}
 
 // local cell index of global node (nx, ny, nz)
 __device__ __forceinline__ int64_t cell_index(const DevParams& P, int nx, int ny, int nz)

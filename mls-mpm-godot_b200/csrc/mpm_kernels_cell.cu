@@ -30,7 +30,7 @@
 #define MPM_P2G_CTAS 3
 #endif
 #ifndef MPM_G2P_CTAS
-#define MPM_G2P_CTAS 4
+#define MPM_G2P_CTAS 3
 #endif
 
 namespace mpm {
@@ -800,10 +800,12 @@ __global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? MPM_G2P_CTAS :
     using CF = CellCfg<B>;
     // dynamic shared memory (above the 48 KB static limit together): the tile as the TMA unit delivers it -- [x][y][z]
     // cells of 4 x int32 -- | the velocity tile the stencils read | the per-warp staging of (px, py, pz, m) units
-    extern __shared__ __align__(128) unsigned char dsm[];
-    int4* raw = reinterpret_cast<int4*>(dsm);
-    float (*tv)[TL::WORDS] = reinterpret_cast<float (*)[TL::WORDS]>(dsm + G2PSmem<B>::RAW);
-    float4 (*s_quads)[2 * QuadStage::UNIT] = reinterpret_cast<float4 (*)[2 * QuadStage::UNIT]>(dsm + G2PSmem<B>::RAW + G2PSmem<B>::TV);
+    // (its own symbol: the bulk tensor copy needs a 128-byte aligned destination, and the alignment of a dynamic array is
+    // the one of its first declaration in the translation unit)
+    extern __shared__ __align__(128) unsigned char dsm_g2p[];
+    int4* raw = reinterpret_cast<int4*>(dsm_g2p);
+    float (*tv)[TL::WORDS] = reinterpret_cast<float (*)[TL::WORDS]>(dsm_g2p + G2PSmem<B>::RAW);
+    float4 (*s_quads)[2 * QuadStage::UNIT] = reinterpret_cast<float4 (*)[2 * QuadStage::UNIT]>(dsm_g2p + G2PSmem<B>::RAW + G2PSmem<B>::TV);
     __shared__ __align__(8) unsigned long long tile_bar;
     __shared__ BlockWork s_bw;
     __shared__ int s_next;

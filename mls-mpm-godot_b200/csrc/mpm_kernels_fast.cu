@@ -74,23 +74,25 @@ __global__ void __launch_bounds__(TILED_THREADS) k_p2g1_fast(DevParams P, TileGe
 #pragma unroll
                 for (int gz = 0; gz < 3; ++gz) {
                     const float mc = wxy * wzs[gz];
-                    const int em = __float2int_rz(mc);
-                    const int ex = __float2int_rz(mc * fmaf(c[6], dz[gz], bx));
-                    const int ey = __float2int_rz(mc * fmaf(c[7], dz[gz], by));
-                    const int ez = __float2int_rz(mc * fmaf(c[8], dz[gz], bz));
+                    const int em = f2i_checked(mc, P);
+                    const int ex = f2i_checked(mc * fmaf(c[6], dz[gz], bx), P);
+                    const int ey = f2i_checked(mc * fmaf(c[7], dz[gz], by), P);
+                    const int ez = f2i_checked(mc * fmaf(c[8], dz[gz], bz), P);
                     if constexpr (inside) {
                         const int idx = base + gx * TL::PX + gy * TL::PY + gz;
-                        atomicAdd(&tile[3][idx], em); atomicAdd(&tile[0][idx], ex);
-                        atomicAdd(&tile[1][idx], ey); atomicAdd(&tile[2][idx], ez);
+                        int_add_checked(&tile[3][idx], em, P); int_add_checked(&tile[0][idx], ex, P);
+                        int_add_checked(&tile[1][idx], ey, P); int_add_checked(&tile[2][idx], ez, P);
                     } else {
                         int* cc = grid + 4 * cell_index(P, cx + gx - 1, cy + gy - 1, cz + gz - 1);
-                        atomicAdd(cc + 3, em); atomicAdd(cc + 0, ex); atomicAdd(cc + 1, ey); atomicAdd(cc + 2, ez);
+                        int_add_checked(cc + 3, em, P); int_add_checked(cc + 0, ex, P); int_add_checked(cc + 1, ey, P); int_add_checked(cc + 2, ez, P);
                     }
                 }
             }
         }
         };
-        if (in_block) scatter(std::true_type{}); else scatter(std::false_type{});
+        if (in_block) scatter(std::true_type{});
+        else if (stencil_in_grid(P, cx, cy, cz)) scatter(std::false_type{});
+        else flag_bad_particle(P);
     }
     __syncthreads();
     for (int k = threadIdx.x; k < TL::NODES; k += TILED_THREADS) {
@@ -99,10 +101,10 @@ __global__ void __launch_bounds__(TILED_THREADS) k_p2g1_fast(DevParams P, TileGe
         const int ax = tile[0][idx], ay = tile[1][idx], az = tile[2][idx], m = tile[3][idx];
         if (!ok || (ax | ay | az | m) == 0) continue;
         int* cc = grid + 4 * ci;
-        if (ax) atomicAdd(cc + 0, ax);
-        if (ay) atomicAdd(cc + 1, ay);
-        if (az) atomicAdd(cc + 2, az);
-        if (m) atomicAdd(cc + 3, m);
+        if (ax) int_add_checked(cc + 0, ax, P);
+        if (ay) int_add_checked(cc + 1, ay, P);
+        if (az) int_add_checked(cc + 2, az, P);
+        if (m) int_add_checked(cc + 3, m, P);
     }
 }
 
@@ -165,7 +167,9 @@ __global__ void __launch_bounds__(TILED_THREADS) k_p2g2_fast(DevParams P, TileGe
                 density = fmaf(row, wxy, density);
             }
         };
-        if (in_block) gather(std::true_type{}); else gather(std::false_type{});
+        if (in_block) gather(std::true_type{});
+        else if (stencil_in_grid(P, cx, cy, cz)) gather(std::false_type{});
+        else continue;  // (a position outside the grid: counted by P2G_1, the particle stays as it is)
         // eq_16_term_0 = -volume * 4 * stress * dt, symmetric; pre-scaled to fixed-point units
         const float volume = __fdividef(m, density);
         const float pr = P.eos_k * (fast_eos_pow(density * inv_rest, P) - 1.0f);
@@ -187,21 +191,23 @@ __global__ void __launch_bounds__(TILED_THREADS) k_p2g2_fast(DevParams P, TileGe
 #pragma unroll
                 for (int gz = 0; gz < 3; ++gz) {
                     const float w = wxy * wz[gz];
-                    const int ex = __float2int_rz(w * fmaf(e02, dz[gz], bx));
-                    const int ey = __float2int_rz(w * fmaf(e12, dz[gz], by));
-                    const int ez = __float2int_rz(w * fmaf(e22, dz[gz], bz));
+                    const int ex = f2i_checked(w * fmaf(e02, dz[gz], bx), P);
+                    const int ey = f2i_checked(w * fmaf(e12, dz[gz], by), P);
+                    const int ez = f2i_checked(w * fmaf(e22, dz[gz], bz), P);
                     if constexpr (inside) {
                         const int idx = base + gx * TL::PX + gy * TL::PY + gz;
-                        atomicAdd(&tile[0][idx], ex); atomicAdd(&tile[1][idx], ey); atomicAdd(&tile[2][idx], ez);
+                        int_add_checked(&tile[0][idx], ex, P); int_add_checked(&tile[1][idx], ey, P); int_add_checked(&tile[2][idx], ez, P);
                     } else {
                         int* cc = grid + 4 * cell_index(P, cx + gx - 1, cy + gy - 1, cz + gz - 1);
-                        atomicAdd(cc + 0, ex); atomicAdd(cc + 1, ey); atomicAdd(cc + 2, ez);
+                        int_add_checked(cc + 0, ex, P); int_add_checked(cc + 1, ey, P); int_add_checked(cc + 2, ez, P);
                     }
                 }
             }
         }
         };
-        if (in_block) scatter(std::true_type{}); else scatter(std::false_type{});
+        if (in_block) scatter(std::true_type{});
+        else if (stencil_in_grid(P, cx, cy, cz)) scatter(std::false_type{});
+        else flag_bad_particle(P);
     }
     __syncthreads();
     for (int k = threadIdx.x; k < TL::NODES; k += TILED_THREADS) {
@@ -210,9 +216,9 @@ __global__ void __launch_bounds__(TILED_THREADS) k_p2g2_fast(DevParams P, TileGe
         const int ax = tile[0][idx], ay = tile[1][idx], az = tile[2][idx];
         if (!ok || (ax | ay | az) == 0) continue;
         int* cc = grid + 4 * ci;
-        if (ax) atomicAdd(cc + 0, ax);
-        if (ay) atomicAdd(cc + 1, ay);
-        if (az) atomicAdd(cc + 2, az);
+        if (ax) int_add_checked(cc + 0, ax, P);
+        if (ay) int_add_checked(cc + 1, ay, P);
+        if (az) int_add_checked(cc + 2, az, P);
     }
 }
 
@@ -287,7 +293,9 @@ __global__ void __launch_bounds__(TILED_THREADS) k_g2p_fast(DevParams P, TileGeo
             }
         }
         };
-        if (in_block) gather(std::true_type{}); else gather(std::false_type{});
+        if (in_block) gather(std::true_type{});
+        else if (stencil_in_grid(P, cx, cy, cz)) gather(std::false_type{});
+        else continue;  // (a position outside the grid: counted by P2G_1, the particle stays as it is)
         const float Bm[9] = {Bx[0], Bx[1], Bx[2], By[0], By[1], By[2], Bz[0], Bz[1], Bz[2]};
         float np[3], c[9];
         g2p_finish<3>(P, old, Bm, v, np, c);

@@ -9,9 +9,9 @@
 namespace mpm {
 
 template <bool FIXED>
-__device__ __forceinline__ void cell_add(void* grid, int64_t ci, int ch, float val, float fmult)
+__device__ __forceinline__ void cell_add(void* grid, int64_t ci, int ch, float val, const DevParams& P)
 {
-    if (FIXED) atomicAdd(reinterpret_cast<int*>(grid) + 4 * ci + ch, encode_fixed(val, fmult));
+    if (FIXED) int_add_checked(reinterpret_cast<int*>(grid) + 4 * ci + ch, encode_fixed_checked(val, P), P);
     else atomicAdd(reinterpret_cast<float*>(grid) + 4 * ci + ch, val);
 }
 
@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(256) k_p2g1_ref(DevParams P, ParticleView pv, 
     float wx[3], wy[3], wz[3] = {1.0f, 1.0f, 1.0f};
     const int cx = axis_weights(p.px, wx), cy = axis_weights(p.py, wy);
     const int cz = (DIM == 3) ? axis_weights(p.pz, wz) : 1;
+    if (!stencil_in_grid(P, cx, cy, cz)) { flag_bad_particle(P); return; }
 #pragma unroll
     for (int gx = 0; gx < 3; ++gx)
 #pragma unroll
@@ -44,10 +45,10 @@ __global__ void __launch_bounds__(256) k_p2g1_ref(DevParams P, ParticleView pv, 
                 float mc, ox, oy, oz;
                 p2g1_node<DIM>(p, weight, dx, dy, dz, mc, ox, oy, oz);
                 const int64_t ci = cell_index(P, nx, ny, nz);
-                cell_add<FIXED>(grid, ci, 3, mc, P.fmult);
-                cell_add<FIXED>(grid, ci, 0, ox, P.fmult);
-                cell_add<FIXED>(grid, ci, 1, oy, P.fmult);
-                if (DIM == 3) cell_add<FIXED>(grid, ci, 2, oz, P.fmult);
+                cell_add<FIXED>(grid, ci, 3, mc, P);
+                cell_add<FIXED>(grid, ci, 0, ox, P);
+                cell_add<FIXED>(grid, ci, 1, oy, P);
+                if (DIM == 3) cell_add<FIXED>(grid, ci, 2, oz, P);
             }
 }
 
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(256) k_p2g2_ref(DevParams P, ParticleView pv, 
     float wx[3], wy[3], wz[3] = {1.0f, 1.0f, 1.0f};
     const int cx = axis_weights(px, wx), cy = axis_weights(py, wy);
     const int cz = (DIM == 3) ? axis_weights(pz, wz) : 1;
+    if (!stencil_in_grid(P, cx, cy, cz)) return;  // (counted by P2G_1)
 
     float density = 0.0f;
 #pragma unroll
@@ -96,9 +98,9 @@ __global__ void __launch_bounds__(256) k_p2g2_ref(DevParams P, ParticleView pv, 
                 float ox, oy, oz;
                 p2g2_node<DIM>(e, weight, dx, dy, dz, ox, oy, oz);
                 const int64_t ci = cell_index(P, nx, ny, nz);
-                cell_add<FIXED>(grid, ci, 0, ox, P.fmult);
-                cell_add<FIXED>(grid, ci, 1, oy, P.fmult);
-                if (DIM == 3) cell_add<FIXED>(grid, ci, 2, oz, P.fmult);
+                cell_add<FIXED>(grid, ci, 0, ox, P);
+                cell_add<FIXED>(grid, ci, 1, oy, P);
+                if (DIM == 3) cell_add<FIXED>(grid, ci, 2, oz, P);
             }
 }
 
@@ -205,6 +207,7 @@ __global__ void __launch_bounds__(256) k_g2p_ref(DevParams P, ParticleView pv, i
     float wx[3], wy[3], wz[3] = {1.0f, 1.0f, 1.0f};
     const int cx = axis_weights(old[0], wx), cy = axis_weights(old[1], wy);
     const int cz = (DIM == 3) ? axis_weights(old[2], wz) : 1;
+    if (!stencil_in_grid(P, cx, cy, cz)) return;  // (counted by P2G_1; the particle stays as it is)
     float B[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, v[3] = {0, 0, 0};
 #pragma unroll
     for (int gx = 0; gx < 3; ++gx)

@@ -59,19 +59,21 @@ __global__ void __launch_bounds__(TILED_THREADS) k_p2g1_tiled(DevParams P, TileG
                     const int nx = cx + gx - 1, ny = cy + gy - 1, nz = cz + gz - 1;
                     float mc, ox, oy, oz;
                     p2g1_node<3>(p, weight, node_dist(nx, p.px), node_dist(ny, p.py), node_dist(nz, p.pz), mc, ox, oy, oz);
-                    const int em = encode_fixed(mc, P.fmult), ex = encode_fixed(ox, P.fmult), ey = encode_fixed(oy, P.fmult),
-                              ez = encode_fixed(oz, P.fmult);
+                    const int em = encode_fixed_checked(mc, P), ex = encode_fixed_checked(ox, P), ey = encode_fixed_checked(oy, P),
+                              ez = encode_fixed_checked(oz, P);
                     if constexpr (inside) {
                         const int idx = base + gx * TL::PX + gy * TL::PY + gz;
-                        atomicAdd(&tile[3][idx], em); atomicAdd(&tile[0][idx], ex);
-                        atomicAdd(&tile[1][idx], ey); atomicAdd(&tile[2][idx], ez);
+                        int_add_checked(&tile[3][idx], em, P); int_add_checked(&tile[0][idx], ex, P);
+                        int_add_checked(&tile[1][idx], ey, P); int_add_checked(&tile[2][idx], ez, P);
                     } else {
                         int* c = grid + 4 * cell_index(P, nx, ny, nz);
-                        atomicAdd(c + 3, em); atomicAdd(c + 0, ex); atomicAdd(c + 1, ey); atomicAdd(c + 2, ez);
+                        int_add_checked(c + 3, em, P); int_add_checked(c + 0, ex, P); int_add_checked(c + 1, ey, P); int_add_checked(c + 2, ez, P);
                     }
                 }
         };
-        if (in_block) scatter(std::true_type{}); else scatter(std::false_type{});
+        if (in_block) scatter(std::true_type{});
+        else if (stencil_in_grid(P, cx, cy, cz)) scatter(std::false_type{});
+        else flag_bad_particle(P);
     }
     __syncthreads();
     for (int k = threadIdx.x; k < TL::NODES; k += TILED_THREADS) {
@@ -80,10 +82,10 @@ __global__ void __launch_bounds__(TILED_THREADS) k_p2g1_tiled(DevParams P, TileG
         const int vx = tile[0][idx], vy = tile[1][idx], vz = tile[2][idx], m = tile[3][idx];
         if (!ok || (vx | vy | vz | m) == 0) continue;
         int* c = grid + 4 * ci;
-        if (vx) atomicAdd(c + 0, vx);
-        if (vy) atomicAdd(c + 1, vy);
-        if (vz) atomicAdd(c + 2, vz);
-        if (m) atomicAdd(c + 3, m);
+        if (vx) int_add_checked(c + 0, vx, P);
+        if (vy) int_add_checked(c + 1, vy, P);
+        if (vz) int_add_checked(c + 2, vz, P);
+        if (m) int_add_checked(c + 3, m, P);
     }
 }
 
@@ -131,7 +133,9 @@ __global__ void __launch_bounds__(TILED_THREADS) k_p2g2_tiled(DevParams P, TileG
                     density = sadd(density, smul(gm, weight));
                 }
         };
-        if (in_block) gather(std::true_type{}); else gather(std::false_type{});
+        if (in_block) gather(std::true_type{});
+        else if (stencil_in_grid(P, cx, cy, cz)) gather(std::false_type{});
+        else continue;  // (a position outside the grid: counted by P2G_1, the particle stays as it is)
         float e[9];
         p2g2_stress<3>(P, c, m, density, e);
         auto scatter = [&](auto in_tile) {
@@ -146,17 +150,19 @@ __global__ void __launch_bounds__(TILED_THREADS) k_p2g2_tiled(DevParams P, TileG
                     const int nx = cx + gx - 1, ny = cy + gy - 1, nz = cz + gz - 1;
                     float ox, oy, oz;
                     p2g2_node<3>(e, weight, node_dist(nx, px), node_dist(ny, py), node_dist(nz, pz), ox, oy, oz);
-                    const int ex = encode_fixed(ox, P.fmult), ey = encode_fixed(oy, P.fmult), ez = encode_fixed(oz, P.fmult);
+                    const int ex = encode_fixed_checked(ox, P), ey = encode_fixed_checked(oy, P), ez = encode_fixed_checked(oz, P);
                     if constexpr (inside) {
                         const int idx = base + gx * TL::PX + gy * TL::PY + gz;
-                        atomicAdd(&tile[0][idx], ex); atomicAdd(&tile[1][idx], ey); atomicAdd(&tile[2][idx], ez);
+                        int_add_checked(&tile[0][idx], ex, P); int_add_checked(&tile[1][idx], ey, P); int_add_checked(&tile[2][idx], ez, P);
                     } else {
                         int* cc = grid + 4 * cell_index(P, nx, ny, nz);
-                        atomicAdd(cc + 0, ex); atomicAdd(cc + 1, ey); atomicAdd(cc + 2, ez);
+                        int_add_checked(cc + 0, ex, P); int_add_checked(cc + 1, ey, P); int_add_checked(cc + 2, ez, P);
                     }
                 }
         };
-        if (in_block) scatter(std::true_type{}); else scatter(std::false_type{});
+        if (in_block) scatter(std::true_type{});
+        else if (stencil_in_grid(P, cx, cy, cz)) scatter(std::false_type{});
+        else flag_bad_particle(P);
     }
     __syncthreads();
     for (int k = threadIdx.x; k < TL::NODES; k += TILED_THREADS) {
@@ -165,9 +171,9 @@ __global__ void __launch_bounds__(TILED_THREADS) k_p2g2_tiled(DevParams P, TileG
         const int vx = tile[0][idx], vy = tile[1][idx], vz = tile[2][idx];
         if (!ok || (vx | vy | vz) == 0) continue;
         int* c = grid + 4 * ci;
-        if (vx) atomicAdd(c + 0, vx);
-        if (vy) atomicAdd(c + 1, vy);
-        if (vz) atomicAdd(c + 2, vz);
+        if (vx) int_add_checked(c + 0, vx, P);
+        if (vy) int_add_checked(c + 1, vy, P);
+        if (vz) int_add_checked(c + 2, vz, P);
     }
 }
 
@@ -221,7 +227,9 @@ __global__ void __launch_bounds__(TILED_THREADS) k_g2p_tiled(DevParams P, TileGe
                     g2p_node<3>(gvx, gvy, gvz, weight, node_dist(nx, old[0]), node_dist(ny, old[1]), node_dist(nz, old[2]), Bm, v);
                 }
         };
-        if (in_block) gather(std::true_type{}); else gather(std::false_type{});
+        if (in_block) gather(std::true_type{});
+        else if (stencil_in_grid(P, cx, cy, cz)) gather(std::false_type{});
+        else continue;  // (a position outside the grid: counted by P2G_1, the particle stays as it is)
         float np[3], c[9];
         g2p_finish<3>(P, old, Bm, v, np, c);
         pv.at(PX, i) = np[0]; pv.at(PY, i) = np[1]; pv.at(PZ, i) = np[2];

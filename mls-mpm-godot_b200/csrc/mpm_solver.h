@@ -47,7 +47,9 @@ struct MpmSolver {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t pos_ready[2] = {nullptr, nullptr}, pos_copied[2] = {nullptr, nullptr};
     int pos_buf = 0;
-    int32_t* overflow_flag = nullptr;  // device
+    int32_t* overflow_flag = nullptr;  // device: [0] overflow detector, [1] particles skipped for their position (DevParams::flags)
+    void* stage = nullptr;             // grow-only staging buffer of the upload / download calls
+    size_t stage_bytes = 0;
 
     int path = MPM_PATH_REFERENCE;  // resolved kernel path
     int sort_interval = 1;

@@ -52,14 +52,15 @@ struct SortState {
     int64_t last_n = 0;
 };
 
-__global__ void __launch_bounds__(256) k_make_keys(KeyGeom g, ParticleView pv, int64_t n, uint32_t* keys, uint32_t* vals,
+__global__ void __launch_bounds__(256) k_make_keys(KeyGeom g, ParticleView pv, int64_t n, uint32_t nkeys, uint32_t* keys, uint32_t* vals,
                                                    uint32_t* keys_before)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int cx = __float2int_rz(pv.at(PX, i)), cy = __float2int_rz(pv.at(PY, i));
     const int cz = (g.dim == 3) ? __float2int_rz(pv.at(PZ, i)) : 0;
-    const uint32_t k = cell_key(g, cx, cy, cz);
+    uint32_t k = cell_key(g, cx, cy, cz);
+    k = k < nkeys ? k : nkeys - 1;  // a NaN / out-of-grid position must not produce a block id past block_start[] (the kernels skip such particles)
     keys[i] = k;
     vals[i] = (uint32_t)i;
     keys_before[i] = k >> (g.dim * g.logB);  // the sort key proper: the block id
@@ -369,7 +370,7 @@ int sort_particles(MpmSolver* s)
     }
     KeyGeom g{s->dp.dim, st->logB, st->nby, st->nbz, s->dp.gx0 + (s->comm ? 1 : 0)};
     const unsigned nb = (unsigned)((n + 255) / 256);
-    k_make_keys<<<nb, 256, 0, s->stream>>>(g, s->view(), n, st->keys[0], st->vals[0], st->keys_before);
+    k_make_keys<<<nb, 256, 0, s->stream>>>(g, s->view(), n, (uint32_t)(st->nblocks << cell_bits), st->keys[0], st->vals[0], st->keys_before);
     s->launches += 1;
     const int64_t ntiles = (n + SORT_TILE - 1) / SORT_TILE;
     int cur = 0;

@@ -18,7 +18,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MPM_B200_LIB") or os.path.join(os.path.dirname(_HERE), "libmpm_b200.so")  # (override: A/B builds)
 
-OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_OVERFLOW, ERR_COMM = 0, 1, 2, 3, 4, 5
+OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_OVERFLOW, ERR_COMM, ERR_DOMAIN = 0, 1, 2, 3, 4, 5, 6
 GRID_FLOAT, GRID_FIXED = 0, 1
 MATH_STRICT, MATH_FAST = 0, 1
 PATH_AUTO, PATH_REFERENCE, PATH_TILED, PATH_CELL = 0, 1, 2, 3

@@ -582,7 +582,8 @@ def test_checkpoint_resume_is_bit_exact(lib, tmp_path):
         a.upload(pos, vel, Cm, mass)
         a.step(5)
         a.save_state(path)
-    assert os.path.getsize(path) == 64 + 80 * 20000
+    import ctypes as C
+    assert os.path.getsize(path) == 64 + (C.sizeof(mpm_b200.MpmParams) + 4 + 4 * 4 * 7) + 80 * 20000  # header | parameters | records
     with make_solver(op, 20000, kernel_path=2) as b:
         b.load_state(path)
         assert b.num_particles == 20000 and b.stats().steps == 5
@@ -594,6 +595,12 @@ def test_checkpoint_resume_is_bit_exact(lib, tmp_path):
     with make_solver(other, 20000) as c:
         with pytest.raises(mpm_b200.MpmError):
             c.load_state(path)     # written for another grid
+    stiffer = orc.variant("3d_gpu", 32)
+    stiffer.interaction = 0
+    stiffer.eos_stiffness = 2.0
+    with make_solver(stiffer, 20000, kernel_path=2) as d:
+        with pytest.raises(mpm_b200.MpmError, match="eos_stiffness"):
+            d.load_state(path)     # the file carries the parameters it was produced with: different physics is refused
 
 
 # ---------------------------------------------------------------- cell path: the binning is the stable sort, and reproducible
@@ -607,15 +614,15 @@ def test_cell_binning_permutation_is_the_stable_sort(lib, grid, B):
     verifies on the device that the layout in place (src_of, ids) is the one the ranks describe."""
     op = orc.variant("3d_gpu", grid)
     op.interaction = 0
-    n = 200001
-    pos, vel, Cm, mass = helpers.random_cloud(op, n, seed=33, vel_sigma=0.5)
-    crowd = 0.5 if B == 4 else 0.25                       # part of the cloud squeezed into a corner: many particles per cell
+    n = 200001 if B == 8 else 40001                        # (4^3 blocks: a gentler scene, their apron is a quarter of the block)
+    pos, vel, Cm, mass = helpers.random_cloud(op, n, seed=33, vel_sigma=0.5 if B == 8 else 0.2)
+    crowd = 0.25 if B == 8 else 0.6                        # part of the cloud squeezed into a corner: many particles per cell
     pos[: n // 2] = pos[: n // 2] * crowd + 4.0
     mass[: n // 2] *= crowd ** 3
     R = np.array(op.grid[:3], np.float32)
     centre = R * np.array([0.3, 0.75, 0.75], np.float32)
     d2 = ((pos - centre) ** 2).sum(1)
-    clump = np.argsort(d2)[:2000]                           # the 2000 particles nearest to `centre` move together ...
+    clump = np.argsort(d2)[:2000 if B == 8 else 500]        # the particles nearest to `centre` move together ...
     vel[clump] = np.array([22.0, 0.0, 0.0], np.float32)     # ... 4.4 cells per step: far movers, fewer than the list holds
     with make_solver(op, n, kernel_path=3, math_mode=1) as s:
         s.upload(pos, vel, Cm, mass)
@@ -659,7 +666,8 @@ def test_cell_binning_far_mover_overflow_falls_back_and_is_counted(lib):
         assert st.unordered_binnings >= 1 and st.far_movers > 4096, (st.unordered_binnings, st.far_movers)
         gp, gv, gc, gm = s.download()
     ref = orc.State(op, pos, vel, mass=mass); ref.step(3)
-    assert np.abs(gp - ref.pos).max() < 1e-3 and helpers.rel_err(gv, ref.vel) < 1e-4, (np.abs(gp - ref.pos).max(), helpers.rel_err(gv, ref.vel))
+    # (FAST against strict at |v| = 60: 36 cells travelled, a relative 1e-4 of that)
+    assert np.abs(gp - ref.pos).max() < 4e-3 and helpers.rel_err(gv, ref.vel) < 1e-4, (np.abs(gp - ref.pos).max(), helpers.rel_err(gv, ref.vel))
     helpers.assert_bit_equal(gm, mass, "mass / order")
 
 
@@ -871,3 +879,49 @@ def test_mouse_radial_push_2d(lib, variant):
     for what, a, b in (("pos", gp, ref.pos), ("vel", gv, ref.vel), ("C", gc, ref.C)):
         e = helpers.rel_err(a, b)
         assert e <= tol, f"{variant} mouse push {what}: rel err {e:.3g} > tol {tol:.3g}"
+
+
+# ---------------------------------------------------------------- guards: positions outside the grid, fixed-point overflow
+def test_bad_positions_are_rejected_and_never_index_outside_the_grid(lib):
+    """The reference indexes the grid with (int)pos unchecked (F:281-283: IndexOutOfRangeException).  Here an upload with
+    a non-finite position or one whose stencil leaves the grid is refused (MPM_ERR_DOMAIN), on every kernel path."""
+    import mpm_b200
+    op = orc.variant("3d_gpu", 32)
+    op.interaction = 0
+    pos, vel, Cm, mass = helpers.random_cloud(op, 5000, seed=3)
+    for path, math in ((1, 0), (2, 0), (3, 1)):
+        with make_solver(op, 5000, kernel_path=path, math_mode=math) as s:
+            for bad in (np.nan, np.inf, 0.5, 31.5, -3.0, 1e9):
+                q = pos.copy(); q[1234, 1] = bad
+                with pytest.raises(mpm_b200.MpmError) as e:
+                    s.upload(q, vel, Cm, mass)
+                assert e.value.code == mpm_b200.ERR_DOMAIN and s.num_particles == 0
+            s.upload(pos, vel, Cm, mass)       # the clean set still works afterwards
+            s.step(2); s.sync()
+            assert np.isfinite(s.download()[0]).all()
+
+
+def test_overflow_detector(lib):
+    """MpmParams.overflow_check: a node accumulating more than 2^31 / 1e7 = 214.7 mass units wraps the reference's int32 grid
+    silently; with the detector on, mpm_sync returns MPM_ERR_OVERFLOW and MpmStats.overflow is set.  AUTO + FAST keeps off
+    the cell path when the detector is requested, and asking for both explicitly is refused."""
+    import mpm_b200
+    op = orc.variant("3d_gpu", 32)
+    op.interaction = 0
+    rng = np.random.default_rng(5)
+    pos = (np.array([[12.0, 13.0, 14.0]], np.float32) + rng.uniform(0.01, 0.99, (3000, 3)).astype(np.float32))
+    heavy = np.full(3000, 1.0, np.float32)      # 3000 mass units on 27 nodes: far beyond 214.7
+    light = np.full(3000, 0.001, np.float32)
+    for path, math in ((1, 0), (2, 0), (2, 1), (0, 1)):
+        with make_solver(op, 3000, kernel_path=path, math_mode=math, overflow_check=1) as s:
+            assert s.stats().kernel_path in (1, 2)
+            s.upload(pos, mass=light)
+            s.run_phase(0); s.run_phase(1); s.sync()
+            assert s.stats().overflow == 0
+            s.upload(pos, mass=heavy)
+            s.run_phase(0); s.run_phase(1)
+            with pytest.raises(mpm_b200.MpmError) as e:
+                s.sync()
+            assert e.value.code == mpm_b200.ERR_OVERFLOW and s.stats().overflow == 1
+    with pytest.raises(mpm_b200.MpmError):
+        make_solver(op, 100, kernel_path=3, math_mode=1, overflow_check=1)
