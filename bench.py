@@ -9,9 +9,16 @@ particle set.  Workload at any N: BASELINE config 4 -- 3D dam-break, 256^3 grid,
 [4,164)^3 at spacing 0.5), parameters of the reference's shipping GPU scene
 (MLSMPM3DFluidMultithreadGPU.cs:54-84), int32 x 1e7 fixed-point grid.  Arithmetic: --math fast (default; FMA and
 re-association, parity within the tolerances stated in tests/test_parity_gpu.py) or --math strict (bit-exact against
-the reference algorithm; the tiled kernels).  N > 1 slab-shards that same scene (strong scaling).  `value` is device-timed with state resident in HBM; `e2e` is the same metric through
-the host-facing call sequence of one reference frame (_Process, MLSMPM3DFluidMultithreadGPU.cs:234-251): parameter
-block in (set_sphere), step, positions (x,y,z,|v|) out to pinned host memory (the particle_pos_tex hand-off).
+the reference algorithm; the tiled kernels).  N > 1 slab-shards that same scene (strong scaling).  `value` is
+device-timed with state resident in HBM; `e2e` is the same metric through the host-facing call sequence of one reference
+frame (_Process, MLSMPM3DFluidMultithreadGPU.cs:234-251): parameter block in (set_sphere), step, positions (x,y,z,|v|) out
+to pinned host memory (the particle_pos_tex hand-off).
+
+Beside the headline (steps W..W+K of the collapsing block) the line carries what the headline flatters:
+  evolved   the same scene after 100 steps (fluid spread out, pile-ups at the walls): ms/step, per-phase times, P2G+G2P fraction
+  configs   BASELINE configs 2 and 3 (64^3 / 262 144 and 128^3 / 4 096 000 particles) on this GPU (N = 1)
+  weak      weak scaling: a scene of N x 14.2 M particles (uniform pool, 64 x-planes per GPU), "scaling": "weak" inside it
+  cpu_baseline / same_config_pair   the CPU port on the SAME config 4 scene (and on config 3 beside our config 3 number)
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -34,6 +41,12 @@ WORKLOADS = {  # name: (grid, block lo, block hi, spacing)  -- SURVEY.md 8d synt
     # BASELINE config 5 (splash, deliberately non-uniform in x): the first block is listed here, the others in EXTRA_BLOCKS
     "c5": ((512, 256, 256), (4, 4, 4), (508, 68, 252), 0.5),      # pool: 63 995 904
 }
+
+
+def weak_workload(world):
+    """Weak scaling scene: 64 x-planes per GPU, a pool filling x in [4, 64 N - 4), y in [4, 132), z in [4, 252) at spacing
+    0.5: 112 x 256 x 496 = 14.2 M particles on one GPU, (128 N - 16) x 256 x 496 on N."""
+    return (64 * world, 256, 256), (4, 4, 4), (64 * world - 4, 132, 252), 0.5
 EXTRA_BLOCKS = {  # more lattice blocks appended to the scene (lo, hi, spacing)
     "c5": [((96, 90, 48), (256, 250, 208), 0.5),    # falling block, 32 768 000
            ((320, 90, 64), (448, 218, 192), 0.4)],  # dense block,   32 768 000
@@ -60,13 +73,15 @@ def lattice_count(lo, hi, sp):
 
 
 def ncu_traffic(workload):
-    """DRAM bytes per launch of each kernel from the committed `ncu --set full` capture (profiles/r1/traffic_<workload>.json)."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1", f"traffic_{workload}.json")) as f:
-            d = json.load(f)
-        return {k: v["dram_bytes"] for k, v in d["kernels"].items()}, d["source"]
-    except Exception:
-        return {}, None
+    """DRAM bytes per launch of each kernel from the committed `ncu --set full` capture of this round (profiles/r2/), else r1."""
+    for rnd in ("r2", "r1"):
+        try:
+            with open(os.path.join(ROOT, "profiles", rnd, f"traffic_{workload}.json")) as f:
+                d = json.load(f)
+            return {k: v["dram_bytes"] for k, v in d["kernels"].items()}, d["source"]
+        except Exception:
+            continue
+    return {}, None
 
 
 def peaks():
@@ -129,24 +144,47 @@ def scene_params(name):
     return op, lo, hi, sp
 
 
+def cpu_scene(workload, sample):
+    """Oracle state of the bench scene: the whole configured scene (every lattice block), or -- sample=True -- the bounded
+    stand-in used when the whole scene would take too long on the host: the corner sub-block [4,84)^3 of the first lattice
+    (4 096 000 particles) in a grid of at most 128^3."""
+    import numpy as np
+    from oracle import orc
+    grid, lo, hi, sp = WORKLOADS[workload]
+    if sample:
+        hi = tuple(min(h, 84) for h in hi)
+        grid = tuple(min(g, 128) for g in grid)
+        blocks = [(lo, hi, sp)]
+        what = f"sub-block {lo}-{hi} of the {WORKLOAD_DESC[workload]} lattice in a {grid} grid"
+    else:
+        blocks = [(lo, hi, sp)] + EXTRA_BLOCKS.get(workload, [])
+        what = f"the whole scene: {WORKLOAD_DESC[workload]}"
+    op = orc.variant("3d_gpu", grid)
+    op.interaction = 0  # sphere disabled (SURVEY 8d C2/C4)
+    pos = np.concatenate([orc.init_block(3, b[0], b[1], b[2]) for b in blocks])
+    return orc.State(op, pos), pos.shape[0], what
+
+
 def run_reference(args):
     """The reference algorithm on the host cores: the C restatement (oracle, kind "port") in the reference's own
     threading shape (fixed-point variant: every phase across all cores with atomic int adds,
-    MLSMPM3DFluidMultithreadNew.cs:277-288).  The .NET solver itself cannot run here (no dotnet/godot in the image)."""
+    MLSMPM3DFluidMultithreadNew.cs:277-288).  The .NET solver itself cannot run here (no dotnet/godot in the image).
+    It steps the SAME scene as the GPU arm (config 4: 32.8 M particles, ~3 s per step on 16 cores) unless a probe step says the
+    W + K steps would take longer than MPM_REF_BUDGET_S (default 300 s): then the bounded corner sample, and the line says so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import orc
-    op, lo, hi, sp = scene_params(args.workload)
-    # bounded sample: the corner sub-block [4,84)^3 of the same lattice (4 096 000 particles) in a 128^3 grid
-    sample_hi = tuple(min(h, 84) for h in hi)
-    sgrid = tuple(min(g, 128) for g in WORKLOADS[args.workload][0])
-    sop = orc.variant("3d_gpu", sgrid)
-    sop.interaction = 0
-    pos = orc.init_block(3, lo, sample_hi, sp)
-    n = pos.shape[0]
-    st = orc.State(sop, pos)
     cores = os.cpu_count() or 1
+    budget = float(os.environ.get("MPM_REF_BUDGET_S", "300"))
+    # probe on the small stand-in: the whole scene costs about (particles ratio) x as much per step
+    probe, n_probe, _ = cpu_scene(args.workload, True)
+    probe.step_mt(1, cores)
+    t0 = time.perf_counter(); probe.step_mt(1, cores); t_probe = time.perf_counter() - t0
+    grid, lo, hi, sp = WORKLOADS[args.workload]
+    n_full = sum(lattice_count(*b) for b in [(lo, hi, sp)] + EXTRA_BLOCKS.get(args.workload, []))
+    whole = t_probe * n_full / n_probe * (args.steps + args.warmup) <= budget
+    del probe
+    st, n, what = cpu_scene(args.workload, not whole)
     for _ in range(args.warmup):
         st.step_mt(1, cores)
     t0 = time.perf_counter()
@@ -154,36 +192,58 @@ def run_reference(args):
         st.step_mt(1, cores)
     dt = time.perf_counter() - t0
     val = n * args.steps / dt
-    sample = f"sub-block {lo}-{sample_hi} of the {WORKLOAD_DESC[args.workload]} lattice: {n} particles, {sgrid} grid"
+    sample = f"{what}: {n} particles, {args.steps} steps after {args.warmup}"
     line = {"impl": "reference", "metric": "particle-steps/s", "value": val, "unit": "particle-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32+int32-fixed-point", "data": "synthetic",
-            "config": {"workload": WORKLOAD_DESC[args.workload], "sample": sample},
+            "config": {"workload": WORKLOAD_DESC[args.workload], "same_scene_as_gpu_arm": bool(whole), "sample": sample},
             "cpu_baseline": {"value": val, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline(workload, budget_s=20.0):
-    from oracle import orc
-    op, lo, hi, sp = scene_params(workload)
-    sample_hi = tuple(min(h, 84) for h in hi)
-    sgrid = tuple(min(g, 128) for g in WORKLOADS[workload][0])
-    sop = orc.variant("3d_gpu", sgrid)
-    sop.interaction = 0
-    pos = orc.init_block(3, lo, sample_hi, sp)
-    n = pos.shape[0]
-    st = orc.State(sop, pos)
+def cpu_baseline(workload, budget_s=25.0):
+    """The CPU port on the bench scene itself (one warm-up step, then as many steps as fit the budget, at least one); the
+    corner sample instead if a single step of the whole scene would not fit."""
     cores = os.cpu_count() or 1
+    st, n, what = cpu_scene(workload, True)
     st.step_mt(1, cores)
+    t0 = time.perf_counter(); st.step_mt(1, cores); t_probe = time.perf_counter() - t0
+    grid, lo, hi, sp = WORKLOADS[workload]
+    n_full = sum(lattice_count(*b) for b in [(lo, hi, sp)] + EXTRA_BLOCKS.get(workload, []))
+    whole = 3.0 * t_probe * n_full / n <= budget_s  # (a warm-up step and at least two timed ones)
+    if whole:
+        del st
+        st, n, what = cpu_scene(workload, False)
+        st.step_mt(1, cores)
     steps, t0 = 0, time.perf_counter()
-    while steps < 8 and (time.perf_counter() - t0) < budget_s:
+    while steps < 8 and (steps == 0 or (time.perf_counter() - t0) * (steps + 1) / steps < budget_s):
         st.step_mt(1, cores)
         steps += 1
     dt = time.perf_counter() - t0
-    return {"value": n * steps / dt, "unit": "particle-steps/s", "cores": cores, "kind": "port",
-            "sample": f"{n} particles (corner sub-block of the same lattice, {sgrid} grid), {steps} steps, oracle C restatement, "
-                      f"all-core atomic fixed-point shape of MLSMPM3DFluidMultithreadNew.cs"}
+    return {"value": n * steps / dt, "unit": "particle-steps/s", "cores": cores, "kind": "port", "same_config": bool(whole),
+            "sample": f"{what}: {n} particles, {steps} steps, oracle C restatement, all-core atomic fixed-point shape of "
+                      f"MLSMPM3DFluidMultithreadNew.cs"}
+
+
+def time_scene(mpm_b200, grid, blocks, local_rank, math_mode, path, warmup, steps, presteps=0):
+    """One more scene on this GPU (single solver, no communicator): device-timed ms/step and per-phase times."""
+    params = mpm_b200.default_params("3d_gpu", grid=grid, interaction=0, kernel_path=path, math_mode=math_mode)
+    n = sum(lattice_count(*b) for b in blocks)
+    with mpm_b200.Solver(params, n, device=local_rank) as sv:
+        for k, (blo, bhi, bsp) in enumerate(blocks):
+            sv.initialise_sim(blo, bhi, bsp, append=k > 0)
+        if presteps:
+            sv.step(presteps)
+        sv.step(warmup); sv.sync()
+        sv.set_timing(True)
+        sv.step(steps); sv.sync()
+        st = sv.stats()
+    G = grid[0] * grid[1] * grid[2]
+    t3 = st.ms_p2g1 + st.ms_p2g2 + st.ms_g2p
+    return {"particles": n, "grid": list(grid), "ms_per_step": st.ms_step, "value": n / (st.ms_step * 1e-3),
+            "phase_ms": {"sort": st.ms_sort, "clear": st.ms_clear, "p2g1": st.ms_p2g1, "p2g2": st.ms_p2g2, "update": st.ms_update, "g2p": st.ms_g2p},
+            "p2g_g2p_gbs": (188 * n + 60 * G) / (t3 * 1e-3) / 1e9 if t3 > 0 else 0.0, "steps": steps, "warmup": warmup, "presteps": presteps}
 
 
 def main():
@@ -199,6 +259,8 @@ def main():
                     help="strict = bit-exact vs the reference algorithm; fast = FMA/hoisted (tolerance in tests)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--presteps", type=int, default=0, help="advance the scene this many untimed steps first (evolved-scene numbers)")
+    ap.add_argument("--evolved-at", type=int, default=100, help="also time K steps from this step on (0 = off); reported under `evolved`")
+    ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the config 2 / config 3 / weak-scaling measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
@@ -300,6 +362,66 @@ def main():
         mpm_b200.host_free(ptr)
     clocks = sampler.stop()
 
+    # ---- the numbers the headline flatters (device-timed, same solver / same GPU)
+    evolved = None
+    if args.evolved_at > 0 and args.workload == "c4":
+        done = solver.stats().steps
+        if done < args.evolved_at:
+            solver.step(int(args.evolved_at - done))
+        solver.sync()
+        solver.set_timing(True)
+        barrier()
+        solver.step(args.steps); solver.sync()
+        barrier()
+        se = solver.stats()
+        solver.set_timing(False)
+        t = torch.tensor([se.ms_step], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ems = float(t.item())
+        t3 = se.ms_p2g1 + se.ms_p2g2 + se.ms_g2p
+        evolved = {"from_step": int(se.steps - args.steps), "steps": args.steps, "ms_per_step": ems, "value": n_total / (ems * 1e-3),
+                   "phase_ms": {"sort": se.ms_sort, "clear": se.ms_clear, "p2g1": se.ms_p2g1, "p2g2": se.ms_p2g2, "update": se.ms_update,
+                                "g2p": se.ms_g2p, "exchange": se.ms_exchange},
+                   "p2g_g2p_gbs": (188 * se.local_particles + 60 * se.num_cells) / (t3 * 1e-3) / 1e9 if t3 > 0 else 0.0,
+                   "far_movers_last_binning": int(se.far_movers), "unordered_binnings": int(se.unordered_binnings)}
+    st_final = solver.stats()
+    sort_interval = solver.params.sort_interval or 1
+    solver.close()
+    solver = None
+    configs, weak = None, None
+    if args.extras and args.workload == "c4":
+        mm = 1 if args.math == "fast" else 0
+        if world == 1:
+            configs = {}
+            for name, k in (("c2", 50), ("c3", 30)):
+                g, lo2, hi2, sp2 = WORKLOADS[name]
+                configs[name] = dict(time_scene(mpm_b200, g, [(lo2, hi2, sp2)], local_rank, mm, args.path, 5, k), workload=WORKLOAD_DESC[name])
+        # weak scaling: N x 14.2 M particles, 64 x-planes per GPU
+        wg, wlo, whi, wsp = weak_workload(world)
+        wparams = mpm_b200.default_params("3d_gpu", grid=wg, interaction=0, kernel_path=args.path, math_mode=mm)
+        wn = lattice_count(wlo, whi, wsp)
+        ws = mpm_b200.Solver(wparams, wn, device=local_rank)
+        if world > 1:
+            uid = [mpm_b200.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            ws.comm_init(uid[0], rank, world)
+        ws.initialise_sim(wlo, whi, wsp)
+        ws.step(5); ws.sync()
+        ws.set_timing(True)
+        barrier()
+        ws.step(args.steps); ws.sync()
+        barrier()
+        wst = ws.stats()
+        ws.close()
+        t = torch.tensor([wst.ms_step], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wms = float(t.item())
+        weak = {"scaling": "weak", "workload": f"pool x in [4, {wg[0] - 4}), y in [4, 132), z in [4, 252) at spacing 0.5 in a {wg[0]}x256x256 grid: "
+                                                f"64 x-planes and ~14.2 M particles per GPU", "particles": wn, "n_gpus": world,
+                "ms_per_step": wms, "value": wn / (wms * 1e-3), "steps": args.steps, "warmup": 5, "exchange_ms_rank0": wst.ms_exchange}
+
     if rank == 0:
         peak, peak_kind = peaks()
         phases = {"sort": st.ms_sort, "clear": st.ms_clear, "p2g1": st.ms_p2g1, "p2g2": st.ms_p2g2, "update": st.ms_update,
@@ -322,7 +444,7 @@ def main():
             "vs_baseline": None, "dtype": "f32+int32-fixed-point", "data": "synthetic",
             "config": {"workload": WORKLOAD_DESC[args.workload], "grid": list(grid), "particles": n_total, "variant": "3d_gpu (H)",
                        "grid_mode": "fixed 1e7", "math": args.math, "kernel_path": {1: "reference-shaped", 2: "tiled", 3: "cell"}[st.kernel_path],
-                       "sort_interval": solver.params.sort_interval or 1, "parallelism": f"x-slab x{world}",
+                       "sort_interval": sort_interval, "parallelism": f"x-slab x{world}",
                        "presteps": args.presteps,
                        "l2": f"inputs ({64e-9 * n_total / world:.1f} GB of particle planes per GPU) exceed the 126 MB L2; no flush needed",
                        "timing": "CUDA events on the solver stream inside mpm_step; wall-clock cross-check in wall_ms_per_step"},
@@ -341,10 +463,24 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        line["binning"] = {"ranking": "atomic cursor" if (os.environ.get("MPM_ATOMIC_BINNING") or world > 1) else "stable (== std::stable_sort)",
+                           "far_movers_last_binning": int(st_final.far_movers), "unordered_binnings": int(st_final.unordered_binnings)}
+        if evolved is not None:
+            evolved["p2g_g2p_frac"] = evolved["p2g_g2p_gbs"] / peak
+            line["evolved"] = evolved
+        if configs is not None:
+            for c in configs.values():
+                c["p2g_g2p_frac"] = c["p2g_g2p_gbs"] / peak
+            line["configs"] = configs
+        if weak is not None:
+            line["weak"] = weak
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(args.workload)
+            if configs is not None and args.workload != "c3":  # a second pair on a scene the CPU finishes quickly: config 3 on both sides
+                cb3 = cpu_baseline("c3", budget_s=12.0)
+                line["same_config_pair"] = {"workload": WORKLOAD_DESC["c3"], "ours": configs["c3"]["value"], "cpu_port": cb3["value"],
+                                            "cores": cb3["cores"], "cpu_same_config": cb3["same_config"], "sample": cb3["sample"]}
         print(json.dumps(line), flush=True)
-    solver.close()
     if world > 1:
         dist.destroy_process_group()
 

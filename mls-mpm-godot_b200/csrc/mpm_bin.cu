@@ -512,14 +512,14 @@ __global__ void __launch_bounds__(RankCfg<CELL_BITS>::THREADS, 12) k_rank_count(
     }
 }
 
-// far movers ordered by old slot (bitonic sort in shared memory); far_n[1] counts the binnings whose list overflowed
+// far movers ordered by (key, old slot) (bitonic sort in shared memory); far_n[1] counts the binnings whose list overflowed
 __global__ void __launch_bounds__(1024) k_far_sort(uint32_t* __restrict__ far_list, uint32_t* __restrict__ far_n)
 {
     __shared__ uint2 a[FAR_CAP];
     const uint32_t n = far_n[0];
     if (n == 0) return;
     if (n > (uint32_t)FAR_CAP) { if (threadIdx.x == 0) far_n[1] += 1; return; }
-    for (int k = threadIdx.x; k < FAR_CAP; k += 1024) a[k] = (uint32_t)k < n ? make_uint2(far_list[2 * k], far_list[2 * k + 1]) : make_uint2(0xffffffffu, 0u);
+    for (int k = threadIdx.x; k < FAR_CAP; k += 1024) a[k] = (uint32_t)k < n ? make_uint2(far_list[2 * k], far_list[2 * k + 1]) : make_uint2(0xffffffffu, 0xffffffffu);
     __syncthreads();
     for (int size = 2; size <= FAR_CAP; size <<= 1)
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -527,14 +527,26 @@ __global__ void __launch_bounds__(1024) k_far_sort(uint32_t* __restrict__ far_li
                 const int lo = 2 * k - (k & (stride - 1)), hi = lo + stride;
                 const bool up = (lo & size) == 0;
                 const uint2 x = a[lo], y = a[hi];
-                if ((x.x > y.x) == up) { a[lo] = y; a[hi] = x; }
+                const bool gt = x.y > y.y || (x.y == y.y && x.x > y.x);  // order: (key, slot)
+                if (gt == up) { a[lo] = y; a[hi] = x; }
             }
             __syncthreads();
         }
     for (int k = threadIdx.x; k < (int)n; k += 1024) { far_list[2 * k] = a[k].x; far_list[2 * k + 1] = a[k].y; }
 }
 
-__device__ __forceinline__ uint32_t far_hash(uint32_t key) { return (key * 2654435761u) >> 21; }  // 11 bits
+constexpr int BLOOM_WORDS = 512;  // 16384 bits: a few hundred far movers (the outliers of an evolved scene) leave it ~2 % full
+__device__ __forceinline__ uint32_t far_hash(uint32_t key) { return (key * 2654435761u) >> 18; }  // 14 bits
+
+// far movers with cell `key` and an old slot below i (the list is ordered by (key, slot): binary search, then a short run)
+__device__ __noinline__ uint32_t far_before(const uint32_t* __restrict__ far_list, uint32_t nfar, uint32_t key, uint32_t i)
+{
+    uint32_t lo = 0, hi = nfar;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (far_list[2 * mid + 1] < key) lo = mid + 1; else hi = mid; }
+    uint32_t add = 0;
+    for (uint32_t f = lo; f < nfar && far_list[2 * f + 1] == key && far_list[2 * f] < i; ++f) ++add;
+    return add;
+}
 
 struct RankArgs {
     const uint32_t* keys;
@@ -594,17 +606,6 @@ __device__ __forceinline__ void rank_tile(const RankArgs& A, uint32_t tile, uint
         nb_tile[gt] = t2;
     }
     sync();
-    if (gt == 0) {
-        uint32_t run = 0;
-        for (int q = 0; q < 27; ++q) {
-            nb_first[q] = run;
-            if (nb_tile[q] != 0xffffffffu) {
-                const int dz = q % 3 - 1, dy = q / 3 % 3 - 1, dx = q / 9 - 1;
-                run += (uint32_t)((dx ? 2 : C::T) * (dy ? 2 : C::T) * (dz ? 2 : C::T));
-            }
-        }
-        nb_first[27] = run;
-    }
     const uint32_t nrows = (s1 - s0 + 31u) >> 5, rpw = (nrows + W - 1) / W;
     const uint32_t r0 = min((uint32_t)w * rpw, nrows), r1 = min(r0 + rpw, nrows);
     if (W > 1) {
@@ -627,21 +628,28 @@ __device__ __forceinline__ void rank_tile(const RankArgs& A, uint32_t tile, uint
         }
     }
     sync();
-    // 2a. arrivals from lower tiles: all (neighbour, shared cell) pairs as one flat index space, so that the loads of a
-    // thread are independent of each other.  (One warp: straight into its counters.)
+    // 2a. arrivals from lower tiles: for every such neighbour, the box of cells its region shares with ours (2 or T cells
+    // per axis); the threads stride over the box, a neighbour's counts are one contiguous row of tcount
     uint32_t* acc = (W == 1) ? wcnt : off;
-    for (uint32_t q = gt; q < nb_first[27]; q += GS) {
-        int nb = 0;
-        while (nb_first[nb + 1] <= q) ++nb;   // (<= 26 steps; entries of absent neighbours are empty ranges)
+#pragma unroll 1
+    for (int nb = 0; nb < 27; ++nb) {
+        const uint32_t t2 = nb_tile[nb];
+        if (t2 == 0xffffffffu) continue;
         const int dz = nb % 3 - 1, dy = nb / 3 % 3 - 1, dx = nb / 9 - 1;
         const int ey = dy ? 2 : C::T, ez = dz ? 2 : C::T;
-        const uint32_t c = q - nb_first[nb];
-        const int cz = (int)(c % (uint32_t)ez), cy = (int)(c / (uint32_t)ez % (uint32_t)ey), cx = (int)(c / (uint32_t)(ez * ey));
-        // our region coordinate r and the neighbour's r' = r - d * B on each axis: d = -1 -> r in {0, 1}; d = +1 -> r in {B, B + 1}
-        const int rx = dx > 0 ? C::B + cx : cx, ry = dy > 0 ? C::B + cy : cy, rz = dz > 0 ? C::B + cz : cz;
-        const int qx = rx - dx * C::B, qy = ry - dy * C::B, qz = rz - dz * C::B;
-        const uint32_t v = A.tcount[(size_t)nb_tile[nb] * C::RC + (size_t)((qx * C::T + qy) * C::T + qz)];
-        if (v) atomicAdd(&acc[(rx * C::T + ry) * C::T + rz], v);
+        const int ncell = (dx ? 2 : C::T) * ey * ez;
+        const uint32_t* row = A.tcount + (size_t)t2 * C::RC;
+        // our region coordinate r = (d > 0 ? B : 0) + c and the neighbour's r' = r - d * B, per axis
+        const int ox = dx > 0 ? C::B : 0, oy = dy > 0 ? C::B : 0, oz = dz > 0 ? C::B : 0;
+        for (int c = gt; c < ncell; c += GS) {
+            int cz, cy, cx, q = c;
+            if (dz) { cz = q & 1; q >>= 1; } else { cz = q % C::T; q /= C::T; }
+            if (dy) { cy = q & 1; q >>= 1; } else { cy = q % C::T; q /= C::T; }
+            cx = q;
+            const int rx = ox + cx, ry = oy + cy, rz = oz + cz;
+            const uint32_t v = row[((rx - dx * C::B) * C::T + (ry - dy * C::B)) * C::T + (rz - dz * C::B)];
+            if (v) atomicAdd(&acc[(rx * C::T + ry) * C::T + rz], v);
+        }
     }
     sync();
     if (W > 1) {
@@ -666,18 +674,23 @@ __device__ __forceinline__ void rank_tile(const RankArgs& A, uint32_t tile, uint
             key[j] = valid[j] ? A.keys[i] : 0u;
             id[j] = valid[j] ? A.id_src[i] : 0u;
         }
+        // Per row: the lanes with the same cell form a group (match.any); its lowest lane bumps the cell's counter by the
+        // group's size and hands the old value to the others.  The four atomics of a batch are issued back to back --
+        // shared-memory accesses of one warp are performed in order, so row j's sees row j - 1's -- and the returned
+        // values are collected afterwards: one shared-memory round trip per batch instead of a load -> store chain per row.
+        unsigned peers[RB];
+        uint32_t old[RB];
 #pragma unroll
         for (int j = 0; j < RB; ++j) {
             rg[j] = valid[j] ? region_index<CELL_BITS>(key[j], tc, g) : -1;
             const uint32_t tag = rg[j] >= 0 ? (uint32_t)rg[j] : (0x80000000u | (uint32_t)lane);
-            const unsigned peers = __match_any_sync(0xffffffffu, tag);
-            uint32_t base = 0;
-            if (rg[j] >= 0) base = ctr[rg[j]];
-            rc[j] = base + (uint32_t)__popc(peers & lt);
-            __syncwarp();
-            if (rg[j] >= 0 && lane == __ffs(peers) - 1) ctr[rg[j]] = base + (uint32_t)__popc(peers);
+            peers[j] = __match_any_sync(0xffffffffu, tag);
+            old[j] = 0;
+            if (rg[j] >= 0 && lane == __ffs(peers[j]) - 1) old[j] = atomicAdd(&ctr[rg[j]], (uint32_t)__popc(peers[j]));
             __syncwarp();
         }
+#pragma unroll
+        for (int j = 0; j < RB; ++j) rc[j] = __shfl_sync(0xffffffffu, old[j], __ffs(peers[j]) - 1) + (uint32_t)__popc(peers[j] & lt);
         if (nfar) {
 #pragma unroll
             for (int j = 0; j < RB; ++j) {
@@ -685,8 +698,7 @@ __device__ __forceinline__ void rank_tile(const RankArgs& A, uint32_t tile, uint
                 const uint32_t i = s0 + (row + j) * 32u + lane;
                 const uint32_t h = far_hash(key[j]);
                 if (rg[j] >= 0 && !((bloom[h >> 5] >> (h & 31u)) & 1u)) continue;
-                uint32_t add = 0;  // far movers of lower slots that go to the same cell
-                for (uint32_t f = 0; f < nfar && A.far_list[2 * f] < i; ++f) add += A.far_list[2 * f + 1] == key[j];
+                const uint32_t add = far_before(A.far_list, nfar, key[j], i);  // far movers of lower slots that go to the same cell
                 if (rg[j] >= 0) rc[j] += add;
                 else {
                     const uint32_t blk = key[j] >> CELL_BITS;
@@ -718,10 +730,10 @@ __device__ __forceinline__ void rank_tile(const RankArgs& A, uint32_t tile, uint
     sync();
 }
 
-// Bloom filter of the far movers' keys (2048 bits), built by every CTA that ranks
+// Bloom filter of the far movers' keys, built by every CTA that ranks
 __device__ __forceinline__ void build_bloom(uint32_t* bloom, const uint32_t* __restrict__ far_list, uint32_t nfar)
 {
-    if (threadIdx.x < 64) bloom[threadIdx.x] = 0;
+    for (int k = threadIdx.x; k < BLOOM_WORDS; k += blockDim.x) bloom[k] = 0;
     __syncthreads();
     for (uint32_t f = threadIdx.x; f < nfar; f += blockDim.x) { const uint32_t h = far_hash(far_list[2 * f + 1]); atomicOr(&bloom[h >> 5], 1u << (h & 31u)); }
     __syncthreads();
@@ -734,7 +746,7 @@ __global__ void __launch_bounds__(128, 8) k_rank_place(const __grid_constant__ R
     using C = RankCfg<CELL_BITS>;
     __shared__ uint32_t wcnt[4][C::RC];
     __shared__ uint32_t nb_tile[4][28], nb_first[4][28];
-    __shared__ uint32_t bloom[64];
+    __shared__ uint32_t bloom[BLOOM_WORDS];
     const int w = threadIdx.x >> 5;
     const uint32_t nfar_all = A.far_n[0];
     const bool overflow = nfar_all > (uint32_t)FAR_CAP;
@@ -758,7 +770,7 @@ __global__ void __launch_bounds__(256) k_rank_place_heavy(const __grid_constant_
     __shared__ uint32_t wcnt[W * C::RC];
     __shared__ uint32_t off[C::RC];
     __shared__ uint32_t nb_tile[28], nb_first[28];
-    __shared__ uint32_t bloom[64];
+    __shared__ uint32_t bloom[BLOOM_WORDS];
     const uint32_t nfar_all = A.far_n[0];
     const bool overflow = nfar_all > (uint32_t)FAR_CAP;
     const uint32_t nfar = overflow ? 0u : nfar_all;

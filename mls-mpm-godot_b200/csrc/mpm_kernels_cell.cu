@@ -37,6 +37,35 @@ namespace mpm {
 
 KeyGeom bin_key_geom(const MpmSolver* s);
 
+// Tile of (B+2)^3 nodes for the cell kernels: DENSE, node (tx, ty, tz) at (tx * T + ty) * T + tz -- the order a bulk tensor
+// copy of the box delivers and the order of a flat loop over the nodes.  (The tiled kernels pad their tile so that 32
+// consecutive cells hit 32 banks; here a warp's lanes are the cells of a chunk in order of particle count, i.e. in no
+// spatial order, so the padding bought nothing and cost 2.5x the shared memory: 40 KB against 16 KB for the four channels.)
+template <int B>
+struct CTile {
+    static constexpr int T = B + 2;
+    static constexpr int PY = T;
+    static constexpr int PX = T * T;
+    static constexpr int NODES = T * T * T;
+    static constexpr int WORDS = (NODES + 3) / 4 * 4;  // per channel
+    int ox, oy, oz;
+    __device__ __forceinline__ void init(const TileGeom& g, int b)
+    {
+        const int bz = b % g.nbz, by = (b / g.nbz) % g.nby, bx = b / (g.nbz * g.nby);
+        ox = g.x_owned0 + bx * B - 1; oy = by * B - 1; oz = bz * B - 1;
+    }
+    // k-th node of the tile -> its index (k itself) and global cell index (false if outside the local grid)
+    __device__ __forceinline__ bool node(const DevParams& P, int k, int& idx, int64_t& ci) const
+    {
+        const int tz = k % T, ty = (k / T) % T, tx = k / (T * T);
+        idx = k;
+        const int nx = ox + tx, ny = oy + ty, nz = oz + tz;
+        if (nx < P.gx0 || nx >= P.gx0 + P.nxl || ny < 0 || ny >= P.Ry || nz < 0 || nz >= P.Rz) return false;
+        ci = cell_index(P, nx, ny, nz);
+        return true;
+    }
+};
+
 template <int B>
 struct CellCfg {
     static constexpr int LOGB = (B == 8) ? 3 : 2;
@@ -254,11 +283,11 @@ struct CellPos {  // the cell (id L inside the block) this lane owns in the curr
     int base;
     float2 fcxy;  // (x, y) of the cell as an aligned pair: the x and y weights are computed packed
     float fcz;
-    __device__ __forceinline__ void set(const Tile<B>& tl, int L)
+    __device__ __forceinline__ void set(const CTile<B>& tl, int L)
     {
         constexpr int LOGB = CellCfg<B>::LOGB;
         const int lx = L >> (2 * LOGB), ly = (L >> LOGB) & (B - 1), lz = L & (B - 1);
-        base = lx * Tile<B>::PX + ly * Tile<B>::PY + lz;
+        base = lx * CTile<B>::PX + ly * CTile<B>::PY + lz;
         fcxy = make_float2((float)(tl.ox + 1 + lx), (float)(tl.oy + 1 + ly)); fcz = (float)(tl.oz + 1 + lz);
     }
 };
@@ -365,7 +394,7 @@ struct QuadStage {
 // ---------------------------------------------------------------- P2G_1
 template <int B>
 struct P2G1Body {
-    using TL = Tile<B>;
+    using TL = CTile<B>;
     const DevParams& P;
     const ParticleView& pv;  // out: position and mass planes in slot order (what G2P reads)
     const TL& tl;
@@ -459,7 +488,7 @@ __global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? MPM_P2G_CTAS :
                                                                                      int* __restrict__ grid, const float* __restrict__ rec,
                                                                                      const uint32_t* __restrict__ src_of)
 {
-    using TL = Tile<B>;
+    using TL = CTile<B>;
     using CF = CellCfg<B>;
     extern __shared__ __align__(16) unsigned char dsm[];  // tile | staging (above the 48 KB static limit together)
     int (*tile)[TL::WORDS] = reinterpret_cast<int (*)[TL::WORDS]>(dsm);
@@ -510,7 +539,7 @@ __device__ __forceinline__ float cell_eos_pow(float x, const DevParams& P)
 
 template <int B>
 struct P2G2Body {
-    using TL = Tile<B>;
+    using TL = CTile<B>;
     const DevParams& P;
     const TL& tl;
     int (*tile)[TL::WORDS];
@@ -616,30 +645,68 @@ struct P2G2Body {
 };
 
 template <int B>
+struct P2G2Smem {  // byte sizes of the dynamic shared-memory regions of k_p2g2_cell
+    static constexpr size_t RAW = (sizeof(int4) * CTile<B>::NODES + 127) / 128 * 128;  // the tile as the TMA unit delivers it
+    static constexpr size_t ACC = sizeof(int) * 3 * CTile<B>::WORDS;                     // momentum accumulators
+    static constexpr size_t MASS = sizeof(float) * CTile<B>::WORDS;                      // node masses of the stencils
+    static constexpr size_t STAGE = sizeof(float) * CellCfg<B>::NWARP * 2 * RowStage::WORDS;
+    static constexpr size_t TOTAL = RAW + ACC + MASS + STAGE;
+};
+
+// The node masses P2G_2's density sums need are the .w words of the block's grid tile: like G2P, the kernel asks the TMA
+// unit for the NEXT block's tile before it walks the current one (the whole 16-byte cells: the mass words alone would be
+// 4-byte pieces at a 16-byte stride, and the sectors are the same).
+template <int B>
 __global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? MPM_P2G_CTAS : 6) k_p2g2_cell(DevParams P, TileGeom g, ParticleView pv, CellArgs a,
                                                                                      int* __restrict__ grid, const float* __restrict__ rec,
-                                                                                     const uint32_t* __restrict__ src_of)
+                                                                                     const uint32_t* __restrict__ src_of,
+                                                                                     const __grid_constant__ CUtensorMap grid_map)
 {
-    using TL = Tile<B>;
+    using TL = CTile<B>;
     using CF = CellCfg<B>;
-    extern __shared__ __align__(16) unsigned char dsm[];  // tile | mass tile | staging
-    int (*tile)[TL::WORDS] = reinterpret_cast<int (*)[TL::WORDS]>(dsm);
-    float* tmass = reinterpret_cast<float*>(dsm + sizeof(int) * 3 * TL::WORDS);
-    float* stg = tmass + TL::WORDS;
+    using SM = P2G2Smem<B>;
+    extern __shared__ __align__(128) unsigned char dsm128[];  // raw tile | accumulators | mass tile | staging
+    int4* raw = reinterpret_cast<int4*>(dsm128);
+    int (*tile)[TL::WORDS] = reinterpret_cast<int (*)[TL::WORDS]>(dsm128 + SM::RAW);
+    float* tmass = reinterpret_cast<float*>(dsm128 + SM::RAW + SM::ACC);
+    float* stg = reinterpret_cast<float*>(dsm128 + SM::RAW + SM::ACC + SM::MASS);
+    __shared__ __align__(8) unsigned long long tile_bar;
     __shared__ BlockWork s_bw;
+    __shared__ int s_next;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float inv_mult = 1.0f / P.fmult;
-    for (;;) {
-        const int b = fetch_block<CF::NWARP>(a, BIN_WORK_P2G2, &s_bw);
-        if (b < 0) break;
+    constexpr unsigned TILE_BYTES = sizeof(int4) * TL::NODES;
+    auto request_tile = [&](int blk) {  // (one thread)
+        TL t2; t2.init(g, blk);
+        mbar_expect_tx(&tile_bar, TILE_BYTES);
+        tma_load_tile(raw, &grid_map, t2.oz, t2.oy, t2.ox - P.gx0, &tile_bar);
+    };
+    auto claim = [&]() -> int {  // (one thread) next non-empty block of the list, or -1
+        const uint32_t bi = atomicAdd(&a.misc[BIN_WORK_P2G2], 1u);
+        return (bi < a.misc[BIN_N_ACTIVE]) ? (int)a.active[bi] : -1;
+    };
+    if (threadIdx.x == 0) {
+        mbar_init(&tile_bar, 1);
+        s_next = claim();
+        if (s_next >= 0) request_tile(s_next);
+    }
+    __syncthreads();
+    int b = s_next;
+    unsigned phase = 0;
+    while (b >= 0) {
         TL tl; tl.init(g, b);
-        for (int k = threadIdx.x; k < 3 * TL::WORDS; k += CF::THREADS) reinterpret_cast<int*>(dsm)[k] = 0;
-        for (int k = threadIdx.x; k < TL::NODES; k += CF::THREADS) {
-            int idx; int64_t ci;
-            const bool ok = tl.node(P, k, idx, ci);
-            tmass[idx] = ok ? (float)grid[4 * ci + 3] * inv_mult : 0.0f;
+        for (int k = threadIdx.x; k < 3 * TL::WORDS; k += CF::THREADS) (&tile[0][0])[k] = 0;
+        mbar_wait(&tile_bar, phase);
+        phase ^= 1u;
+        for (int k = threadIdx.x; k < TL::NODES; k += CF::THREADS) tmass[k] = (float)raw[k].w * inv_mult;  // (nodes outside the grid: 0)
+        __syncthreads();  // mass tile and cleared accumulators are in place, raw is free again
+        if (threadIdx.x == 0) {
+            s_bw.next_chunk = CF::NWARP;  // chunk `warp` is every warp's first one
+            s_next = claim();
+            if (s_next >= 0) request_tile(s_next);  // in flight while this block is walked
         }
         __syncthreads();
+        const int b_next = s_next;
         P2G2Body<B> body(P, tl, tile, tmass, RowStage(rec, src_of, stg + warp * (2 * RowStage::WORDS), lane));
         walk_chunks<B>(a, b, lane, warp, &s_bw, body);
         __syncthreads();
@@ -653,13 +720,15 @@ __global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? MPM_P2G_CTAS :
             if (vy) atomicAdd(cc + 1, vy);
             if (vz) atomicAdd(cc + 2, vz);
         }
+        __syncthreads();  // the accumulators are cleared again at the top
+        b = b_next;
     }
 }
 
 // ---------------------------------------------------------------- G2P
 template <int B, bool COMM, bool EXTRA>  // COMM: multi-GPU (lists the particles that leave the slab); EXTRA: sphere list
 struct G2PBody {
-    using TL = Tile<B>;
+    using TL = CTile<B>;
     const DevParams& P;
     const ParticleView& pv;
     const TL& tl;
@@ -784,8 +853,8 @@ struct G2PBody {
 // The multi-GPU classification is a separate instantiation: as a run-time branch it cost the single-GPU kernel 0.045 ms.
 template <int B>
 struct G2PSmem {  // byte sizes of the three dynamic shared-memory regions of k_g2p_cell
-    static constexpr size_t RAW = (sizeof(int4) * Tile<B>::NODES + 127) / 128 * 128;
-    static constexpr size_t TV = sizeof(float) * 3 * Tile<B>::WORDS;
+    static constexpr size_t RAW = (sizeof(int4) * CTile<B>::NODES + 127) / 128 * 128;
+    static constexpr size_t TV = sizeof(float) * 3 * CTile<B>::WORDS;
     static constexpr size_t QUADS = sizeof(float4) * CellCfg<B>::NWARP * 2 * QuadStage::UNIT;
     static constexpr size_t TOTAL = RAW + TV + QUADS;
 };
@@ -796,16 +865,16 @@ __global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? MPM_G2P_CTAS :
                                                                                     uint32_t* __restrict__ keys, uint32_t* __restrict__ cnt_next,
                                                                                     MigClassify mg, float4* __restrict__ rec)
 {
-    using TL = Tile<B>;
+    using TL = CTile<B>;
     using CF = CellCfg<B>;
     // dynamic shared memory (above the 48 KB static limit together): the tile as the TMA unit delivers it -- [x][y][z]
     // cells of 4 x int32 -- | the velocity tile the stencils read | the per-warp staging of (px, py, pz, m) units
     // (its own symbol: the bulk tensor copy needs a 128-byte aligned destination, and the alignment of a dynamic array is
     // the one of its first declaration in the translation unit)
-    extern __shared__ __align__(128) unsigned char dsm_g2p[];
-    int4* raw = reinterpret_cast<int4*>(dsm_g2p);
-    float (*tv)[TL::WORDS] = reinterpret_cast<float (*)[TL::WORDS]>(dsm_g2p + G2PSmem<B>::RAW);
-    float4 (*s_quads)[2 * QuadStage::UNIT] = reinterpret_cast<float4 (*)[2 * QuadStage::UNIT]>(dsm_g2p + G2PSmem<B>::RAW + G2PSmem<B>::TV);
+    extern __shared__ __align__(128) unsigned char dsm128[];
+    int4* raw = reinterpret_cast<int4*>(dsm128);
+    float (*tv)[TL::WORDS] = reinterpret_cast<float (*)[TL::WORDS]>(dsm128 + G2PSmem<B>::RAW);
+    float4 (*s_quads)[2 * QuadStage::UNIT] = reinterpret_cast<float4 (*)[2 * QuadStage::UNIT]>(dsm128 + G2PSmem<B>::RAW + G2PSmem<B>::TV);
     __shared__ __align__(8) unsigned long long tile_bar;
     __shared__ BlockWork s_bw;
     __shared__ int s_next;
@@ -835,7 +904,7 @@ __global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? MPM_G2P_CTAS :
         phase ^= 1u;
         for (int k = threadIdx.x; k < TL::NODES; k += CF::THREADS) {
             const int tz = k % TL::T, ty = (k / TL::T) % TL::T, tx = k / (TL::T * TL::T);
-            const int idx = tx * TL::PX + ty * TL::PY + tz;
+            const int idx = k;  // (dense tile: the order the tensor copy delivered)
             const int4 c = raw[k];
             float vx = 0.0f, vy = 0.0f, vz = 0.0f;
             if (!raw_grid) {  // the grid update already ran: cells hold velocities
@@ -915,38 +984,7 @@ static unsigned persistent_grid(K kernel, int threads, size_t smem)
     } while (0)
 
 template <int B>
-constexpr size_t p2g1_smem() { return sizeof(int) * 4 * Tile<B>::WORDS + sizeof(float) * CellCfg<B>::NWARP * 2 * RowStage::WORDS; }
-template <int B>
-constexpr size_t p2g2_smem() { return sizeof(int) * 3 * Tile<B>::WORDS + sizeof(float) * Tile<B>::WORDS + sizeof(float) * CellCfg<B>::NWARP * 2 * RowStage::WORDS; }
-
-int cell_p2g1(MpmSolver* s)
-{
-    int rc = check_cell_supported(s);
-    if (rc) return rc;
-    if (s->n == 0) return MPM_OK;
-    LAUNCH_CELL(k_p2g1_cell, p2g1_smem<8>(), p2g1_smem<4>(), reinterpret_cast<int*>(s->grid), s->rec, s->bin->src_of);
-    s->g2p_inputs = true;
-    return MPM_OK;
-}
-
-int cell_p2g2(MpmSolver* s)
-{
-    int rc = check_cell_supported(s);
-    if (rc) return rc;
-    if (s->n == 0) return MPM_OK;
-    LAUNCH_CELL(k_p2g2_cell, p2g2_smem<8>(), p2g2_smem<4>(), reinterpret_cast<int*>(s->grid), s->rec, s->bin->src_of);
-    return MPM_OK;
-}
-
-// the two G2P instantiations as names the launch macro can take
-template <int B>
-constexpr auto k_g2p_cell_single = k_g2p_cell<B, false, false>;
-template <int B>
-constexpr auto k_g2p_cell_comm = k_g2p_cell<B, true, false>;
-template <int B>
-constexpr auto k_g2p_cell_single_x = k_g2p_cell<B, false, true>;
-template <int B>
-constexpr auto k_g2p_cell_comm_x = k_g2p_cell<B, true, true>;
+constexpr size_t p2g1_smem() { return sizeof(int) * 4 * CTile<B>::WORDS + sizeof(float) * CellCfg<B>::NWARP * 2 * RowStage::WORDS; }
 
 // 4-D tensor map (channel, z, y, x) of the local grid, box = one block's tile; encoded once per solver
 static int grid_tensor_map(MpmSolver* s)
@@ -972,6 +1010,36 @@ static int grid_tensor_map(MpmSolver* s)
     bs->grid_map_valid = true;
     return MPM_OK;
 }
+
+int cell_p2g1(MpmSolver* s)
+{
+    int rc = check_cell_supported(s);
+    if (rc) return rc;
+    if (s->n == 0) return MPM_OK;
+    LAUNCH_CELL(k_p2g1_cell, p2g1_smem<8>(), p2g1_smem<4>(), reinterpret_cast<int*>(s->grid), s->rec, s->bin->src_of);
+    s->g2p_inputs = true;
+    return MPM_OK;
+}
+
+int cell_p2g2(MpmSolver* s)
+{
+    int rc = check_cell_supported(s);
+    if (rc) return rc;
+    if (s->n == 0) return MPM_OK;
+    if ((rc = grid_tensor_map(s))) return rc;
+    LAUNCH_CELL(k_p2g2_cell, P2G2Smem<8>::TOTAL, P2G2Smem<4>::TOTAL, reinterpret_cast<int*>(s->grid), s->rec, s->bin->src_of, s->bin->grid_map);
+    return MPM_OK;
+}
+
+// the two G2P instantiations as names the launch macro can take
+template <int B>
+constexpr auto k_g2p_cell_single = k_g2p_cell<B, false, false>;
+template <int B>
+constexpr auto k_g2p_cell_comm = k_g2p_cell<B, true, false>;
+template <int B>
+constexpr auto k_g2p_cell_single_x = k_g2p_cell<B, false, true>;
+template <int B>
+constexpr auto k_g2p_cell_comm_x = k_g2p_cell<B, true, true>;
 
 int cell_g2p(MpmSolver* s)
 {
