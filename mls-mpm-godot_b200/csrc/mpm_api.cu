@@ -913,12 +913,12 @@ extern "C" int32_t mpm_get_stats(MpmSolver* s, MpmStats* st)
         cudaMemcpy(&st->overflow, s->overflow_flag, sizeof(int32_t), cudaMemcpyDeviceToHost);
     }
     if (s->bin && s->bin->far_n) {
-        uint32_t f[2] = {0, 0};
+        uint32_t f[4] = {0, 0, 0, 0};
         cudaSetDevice(s->device);
         cudaStreamSynchronize(s->stream);
         cudaMemcpy(f, s->bin->far_n, sizeof(f), cudaMemcpyDeviceToHost);
-        st->unordered_binnings = f[1];
-        st->far_movers = f[0];
+        st->unordered_binnings = f[1] + (f[3] ? 1 : 0);
+        st->far_movers = f[2];
     }
     comm_fill_stats(s, st);
     return MPM_OK;

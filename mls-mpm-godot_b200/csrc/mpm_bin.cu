@@ -95,7 +95,10 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(const uint32_t* __restrict
                                                       uint32_t* __restrict__ active, uint32_t* __restrict__ misc, BoxGeom bg,
                                                       int* __restrict__ box, int cleared, uint32_t* __restrict__ nact_out, uint32_t* __restrict__ far_n)
 {
-    if (threadIdx.x == 0) far_n[0] = 0;  // the far-mover list of the stable ranking starts empty
+    if (threadIdx.x == 0) {  // stable ranking: the list of cells with far arrivals starts empty; last binning's verdict is booked
+        if (far_n[3]) { far_n[1] += 1; far_n[3] = 0; }
+        far_n[0] = 0; far_n[2] = 0;
+    }
     __shared__ uint32_t wsum[32], wact[32];
     __shared__ int wbox[32][6];
     int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {-1, -1, -1};  // block coordinates of the non-empty blocks of this thread
@@ -376,12 +379,12 @@ __global__ void __launch_bounds__(256) k_place(const uint32_t* __restrict__ keys
 // (neighbour offset + prefix over the warps) and walks its rows in order: rank = counter + lower lanes of the row with
 // the same cell (match.any), leader lane bumps the counter.  No global atomics, no dependence on scheduling.
 //
-// Particles that leave their tile's region (|v| dt > 1 cell: numerical outliers) are "far movers": k_rank_count lists
-// them (old slot, key), k_far_sort orders the list by slot, and every rank is corrected exactly -- a far mover ranks
-// after the regular arrivals of lower tiles and the far movers of lower slots, a regular particle gains one per far
-// mover of a lower slot in its cell (a 2048-bit Bloom filter of the far keys keeps that test off the common path).  A
-// list overflow (> FAR_CAP in one step: the simulation has blown up) falls back to atomic ranks for that binning and is
-// counted in MpmStats.unordered_binnings.
+// Particles that leave their tile's region (more than a cell per step past the block's edge: the fast part of a violent
+// scene -- 2 % of the particles of the C4 dam-break after 100 steps) are "far movers".  They are placed BEHIND the regular
+// arrivals of their cell (rank = count - far arrivals + an atomic ticket), and k_fix_far then restores the exact order
+// cell by cell: the regular part of a cell is already in slot order, its few far arrivals are sorted and merged in.
+// A cell with more than FIX_FAR_MAX far arrivals, or more than FIX_CAP such cells in one binning, stays as placed (a valid
+// cell sort in atomic order) and the binning is counted in MpmStats.unordered_binnings.
 struct RankGeom { int nbx, nby, nbz; };
 
 template <int CELL_BITS>
@@ -444,37 +447,11 @@ __device__ __forceinline__ int region_index(uint32_t key, const TileCtx& c, cons
     return region_index_moved<CELL_BITS>(key, c.tile, c.tbx, c.tby, c.tbz, g.nbx, g.nby, g.nbz);  // (out of line: rare, and large)
 }
 
-// particles of the tiles below `tile` that go to the cell (cx, cy, cz) (block-grid cell coordinates): the cell's own
-// block and the neighbours whose one-cell apron holds it
-template <int CELL_BITS>
-__device__ __noinline__ uint32_t lower_tiles_sum(int cx, int cy, int cz, uint32_t tile, const RankGeom& g, const uint32_t* __restrict__ bsum_prev,
-                                                    const uint32_t* __restrict__ tcount)
-{
-    using C = RankCfg<CELL_BITS>;
-    if (cx < 0 || cy < 0 || cz < 0 || cx >= g.nbx * C::B || cy >= g.nby * C::B || cz >= g.nbz * C::B) return 0;
-    int bx[2], by[2], bz[2], nx = 1, ny = 1, nz = 1;
-    bx[0] = cx >> C::LOGB; by[0] = cy >> C::LOGB; bz[0] = cz >> C::LOGB;
-    const int lx = cx & (C::B - 1), ly = cy & (C::B - 1), lz = cz & (C::B - 1);
-    if (lx == 0 && bx[0] > 0) bx[nx++] = bx[0] - 1; else if (lx == C::B - 1 && bx[0] + 1 < g.nbx) bx[nx++] = bx[0] + 1;
-    if (ly == 0 && by[0] > 0) by[ny++] = by[0] - 1; else if (ly == C::B - 1 && by[0] + 1 < g.nby) by[ny++] = by[0] + 1;
-    if (lz == 0 && bz[0] > 0) bz[nz++] = bz[0] - 1; else if (lz == C::B - 1 && bz[0] + 1 < g.nbz) bz[nz++] = bz[0] + 1;
-    uint32_t sum = 0;
-    for (int a = 0; a < nx; ++a)
-        for (int b = 0; b < ny; ++b)
-            for (int c = 0; c < nz; ++c) {
-                const uint32_t t2 = (uint32_t)((bx[a] * g.nby + by[b]) * g.nbz + bz[c]);
-                if (t2 >= tile || bsum_prev[t2] == 0) continue;
-                const int rx = cx - bx[a] * C::B + 1, ry = cy - by[b] * C::B + 1, rz = cz - bz[c] * C::B + 1;
-                sum += tcount[(size_t)t2 * C::RC + (size_t)((rx * C::T + ry) * C::T + rz)];
-            }
-    return sum;
-}
-
 template <int CELL_BITS>
 __global__ void __launch_bounds__(RankCfg<CELL_BITS>::THREADS, 12) k_rank_count(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ bbase_prev,
                                                                                 const uint32_t* __restrict__ active_prev, const uint32_t* __restrict__ nact_prev,
-                                                                                RankGeom g, uint32_t* __restrict__ tcount, uint32_t* __restrict__ far_list,
-                                                                                uint32_t* __restrict__ far_n)
+                                                                                RankGeom g, uint32_t* __restrict__ tcount, uint32_t* __restrict__ fill,
+                                                                                uint32_t* __restrict__ fixlist, uint32_t* __restrict__ far_n)
 {
     using C = RankCfg<CELL_BITS>;
     constexpr int KB = 8;  // keys per thread and batch: their loads are issued together
@@ -500,9 +477,12 @@ __global__ void __launch_bounds__(RankCfg<CELL_BITS>::THREADS, 12) k_rank_count(
                 if (i >= s1) continue;
                 const int r = region_index<CELL_BITS>(key[j], tc, g);
                 if (r >= 0) atomicAdd(&cnt[r], 1u);
-                else {
-                    const uint32_t f = atomicAdd(far_n, 1u);
-                    if (f < (uint32_t)FAR_CAP) { far_list[2 * f] = i; far_list[2 * f + 1] = key[j]; }
+                else {  // a far mover: counted per target cell (fill[] was cleared with the block's layout); the first one lists the cell
+                    atomicAdd(far_n + 2, 1u);
+                    if (atomicAdd(&fill[key[j]], 1u) == 0u) {
+                        const uint32_t f = atomicAdd(far_n, 1u);
+                        if (f < (uint32_t)FIX_CAP) fixlist[f] = key[j];
+                    }
                 }
             }
         }
@@ -510,42 +490,6 @@ __global__ void __launch_bounds__(RankCfg<CELL_BITS>::THREADS, 12) k_rank_count(
         for (int k = threadIdx.x; k < C::RC; k += C::THREADS) tcount[(size_t)tile * C::RC + k] = cnt[k];
         __syncthreads();
     }
-}
-
-// far movers ordered by (key, old slot) (bitonic sort in shared memory); far_n[1] counts the binnings whose list overflowed
-__global__ void __launch_bounds__(1024) k_far_sort(uint32_t* __restrict__ far_list, uint32_t* __restrict__ far_n)
-{
-    __shared__ uint2 a[FAR_CAP];
-    const uint32_t n = far_n[0];
-    if (n == 0) return;
-    if (n > (uint32_t)FAR_CAP) { if (threadIdx.x == 0) far_n[1] += 1; return; }
-    for (int k = threadIdx.x; k < FAR_CAP; k += 1024) a[k] = (uint32_t)k < n ? make_uint2(far_list[2 * k], far_list[2 * k + 1]) : make_uint2(0xffffffffu, 0xffffffffu);
-    __syncthreads();
-    for (int size = 2; size <= FAR_CAP; size <<= 1)
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int k = threadIdx.x; k < FAR_CAP / 2; k += 1024) {
-                const int lo = 2 * k - (k & (stride - 1)), hi = lo + stride;
-                const bool up = (lo & size) == 0;
-                const uint2 x = a[lo], y = a[hi];
-                const bool gt = x.y > y.y || (x.y == y.y && x.x > y.x);  // order: (key, slot)
-                if (gt == up) { a[lo] = y; a[hi] = x; }
-            }
-            __syncthreads();
-        }
-    for (int k = threadIdx.x; k < (int)n; k += 1024) { far_list[2 * k] = a[k].x; far_list[2 * k + 1] = a[k].y; }
-}
-
-constexpr int BLOOM_WORDS = 512;  // 16384 bits: a few hundred far movers (the outliers of an evolved scene) leave it ~2 % full
-__device__ __forceinline__ uint32_t far_hash(uint32_t key) { return (key * 2654435761u) >> 18; }  // 14 bits
-
-// far movers with cell `key` and an old slot below i (the list is ordered by (key, slot): binary search, then a short run)
-__device__ __noinline__ uint32_t far_before(const uint32_t* __restrict__ far_list, uint32_t nfar, uint32_t key, uint32_t i)
-{
-    uint32_t lo = 0, hi = nfar;
-    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (far_list[2 * mid + 1] < key) lo = mid + 1; else hi = mid; }
-    uint32_t add = 0;
-    for (uint32_t f = lo; f < nfar && far_list[2 * f + 1] == key && far_list[2 * f] < i; ++f) ++add;
-    return add;
 }
 
 struct RankArgs {
@@ -556,8 +500,7 @@ struct RankArgs {
     const uint32_t* nact_prev;
     RankGeom g;
     const uint32_t* tcount;
-    const uint32_t* far_list;
-    const uint32_t* far_n;
+    const uint32_t* cnt;     // particles per new cell (what G2P counted)
     const uint2* cellmeta;
     const uint32_t* cnts;
     const uint32_t* pstart;
@@ -566,8 +509,6 @@ struct RankArgs {
     uint32_t* src_of;
     const uint32_t* id_src;
     uint32_t* id_dst;
-    uint32_t* dbg_rank;  // VERIFY only
-    uint32_t* dbg_bad;
 };
 
 // tiles with more rows than this are ranked by a whole CTA (k_rank_place_heavy), the others by one warp each
@@ -576,11 +517,8 @@ constexpr uint32_t HEAVY_ROWS = 256;
 // One tile, W warps.  W = 1: a warp on its own (no block-wide barrier anywhere: the usual tile of ~100 rows is latency-bound,
 // and thousands of independent warps hide that); W > 1: a CTA of W warps for the pile-up tiles of an evolved scene, each
 // warp owning the w-th part of the rows, with a counting pass first so that every warp knows where its ranks start.
-// VERIFY: nothing is stored; the rank of every old slot goes to dbg_rank and a mismatch between the layout in place
-// (src_of, ids) and the one this run derives is counted in dbg_bad (mpm_debug_last_sort).
-template <int CELL_BITS, int W, bool VERIFY>
-__device__ __forceinline__ void rank_tile(const RankArgs& A, uint32_t tile, uint32_t s0, uint32_t s1, uint32_t* wcnt, uint32_t* off, uint32_t* nb_tile,
-                                          uint32_t* nb_first, const uint32_t* bloom, uint32_t nfar, bool overflow)
+template <int CELL_BITS, int W>
+__device__ __forceinline__ void rank_tile(const RankArgs& A, uint32_t tile, uint32_t s0, uint32_t s1, uint32_t* wcnt, uint32_t* off, uint32_t* nb_tile)
 {
     using C = RankCfg<CELL_BITS>;
     constexpr int GS = 32 * W;  // threads working on the tile
@@ -691,97 +629,115 @@ __device__ __forceinline__ void rank_tile(const RankArgs& A, uint32_t tile, uint
         }
 #pragma unroll
         for (int j = 0; j < RB; ++j) rc[j] = __shfl_sync(0xffffffffu, old[j], __ffs(peers[j]) - 1) + (uint32_t)__popc(peers[j] & lt);
-        if (nfar) {
+        // far movers go behind their cell's regular arrivals: ticket from the high half of fill[] (the low half keeps the
+        // cell's far count for k_fix_far, which puts them where the stable order wants them)
 #pragma unroll
-            for (int j = 0; j < RB; ++j) {
-                if (!valid[j]) continue;
-                const uint32_t i = s0 + (row + j) * 32u + lane;
-                const uint32_t h = far_hash(key[j]);
-                if (rg[j] >= 0 && !((bloom[h >> 5] >> (h & 31u)) & 1u)) continue;
-                const uint32_t add = far_before(A.far_list, nfar, key[j], i);  // far movers of lower slots that go to the same cell
-                if (rg[j] >= 0) rc[j] += add;
-                else {
-                    const uint32_t blk = key[j] >> CELL_BITS;
-                    const int bz = (int)(blk % (uint32_t)g.nbz), by = (int)(blk / (uint32_t)g.nbz % (uint32_t)g.nby), bx = (int)(blk / (uint32_t)(g.nbz * g.nby));
-                    const int cx = bx * C::B + (int)((key[j] >> (2 * C::LOGB)) & (C::B - 1)), cy = by * C::B + (int)((key[j] >> C::LOGB) & (C::B - 1)),
-                              cz = bz * C::B + (int)(key[j] & (C::B - 1));
-                    rc[j] = lower_tiles_sum<CELL_BITS>(cx, cy, cz, tile, g, A.bsum_prev, A.tcount) + add;
-                }
+        for (int j = 0; j < RB; ++j) {
+            if (valid[j] && rg[j] < 0) {
+                const uint32_t oldf = atomicAdd(&A.fill[key[j]], 0x10000u);
+                rc[j] = A.cnt[key[j]] - (oldf & 0xffffu) + (oldf >> 16);
             }
-        }
-        if (overflow && !VERIFY) {
-#pragma unroll
-            for (int j = 0; j < RB; ++j) if (valid[j]) rc[j] = atomicAdd(&A.fill[key[j]], 1u);
         }
 #pragma unroll
         for (int j = 0; j < RB; ++j) {
             if (!valid[j]) continue;
             const uint32_t i = s0 + (row + j) * 32u + lane;
             const uint32_t dest = place_slot<CELL_BITS>(key[j], rc[j], A.cellmeta, A.cnts, A.pstart, A.stab);
-            if (VERIFY) {
-                A.dbg_rank[i] = rc[j];
-                if (A.src_of[dest] != i || A.id_dst[dest] != id[j]) atomicAdd(A.dbg_bad, 1u);
-            } else {
-                A.src_of[dest] = i;
-                A.id_dst[dest] = id[j];
-            }
+            A.src_of[dest] = i;
+            A.id_dst[dest] = id[j];
         }
     }
     sync();
 }
 
-// Bloom filter of the far movers' keys, built by every CTA that ranks
-__device__ __forceinline__ void build_bloom(uint32_t* bloom, const uint32_t* __restrict__ far_list, uint32_t nfar)
-{
-    for (int k = threadIdx.x; k < BLOOM_WORDS; k += blockDim.x) bloom[k] = 0;
-    __syncthreads();
-    for (uint32_t f = threadIdx.x; f < nfar; f += blockDim.x) { const uint32_t h = far_hash(far_list[2 * f + 1]); atomicOr(&bloom[h >> 5], 1u << (h & 31u)); }
-    __syncthreads();
-}
-
 // light tiles: one warp per tile, four tiles per CTA
-template <int CELL_BITS, bool VERIFY>
+template <int CELL_BITS>
 __global__ void __launch_bounds__(128, 8) k_rank_place(const __grid_constant__ RankArgs A)
 {
     using C = RankCfg<CELL_BITS>;
     __shared__ uint32_t wcnt[4][C::RC];
-    __shared__ uint32_t nb_tile[4][28], nb_first[4][28];
-    __shared__ uint32_t bloom[BLOOM_WORDS];
+    __shared__ uint32_t nb_tile[4][28];
     const int w = threadIdx.x >> 5;
-    const uint32_t nfar_all = A.far_n[0];
-    const bool overflow = nfar_all > (uint32_t)FAR_CAP;
-    const uint32_t nfar = overflow ? 0u : nfar_all;
-    if (nfar) build_bloom(bloom, A.far_list, nfar);
     const uint32_t na = *A.nact_prev;
     for (uint32_t t = blockIdx.x * 4 + w; t < na; t += gridDim.x * 4) {
         const uint32_t tile = A.active_prev[t];
         const uint32_t s0 = A.bbase_prev[tile], s1 = A.bbase_prev[tile + 1];
         if (((s1 - s0 + 31u) >> 5) > HEAVY_ROWS) continue;  // (k_rank_place_heavy)
-        rank_tile<CELL_BITS, 1, VERIFY>(A, tile, s0, s1, wcnt[w], nullptr, nb_tile[w], nb_first[w], bloom, nfar, overflow);
+        rank_tile<CELL_BITS, 1>(A, tile, s0, s1, wcnt[w], nullptr, nb_tile[w]);
     }
 }
 
 // heavy tiles: a CTA of 8 warps per tile
-template <int CELL_BITS, bool VERIFY>
+template <int CELL_BITS>
 __global__ void __launch_bounds__(256) k_rank_place_heavy(const __grid_constant__ RankArgs A)
 {
     using C = RankCfg<CELL_BITS>;
     constexpr int W = 8;
     __shared__ uint32_t wcnt[W * C::RC];
     __shared__ uint32_t off[C::RC];
-    __shared__ uint32_t nb_tile[28], nb_first[28];
-    __shared__ uint32_t bloom[BLOOM_WORDS];
-    const uint32_t nfar_all = A.far_n[0];
-    const bool overflow = nfar_all > (uint32_t)FAR_CAP;
-    const uint32_t nfar = overflow ? 0u : nfar_all;
-    if (nfar) build_bloom(bloom, A.far_list, nfar);
+    __shared__ uint32_t nb_tile[28];
     const uint32_t na = *A.nact_prev;
     for (uint32_t t = blockIdx.x; t < na; t += gridDim.x) {
         const uint32_t tile = A.active_prev[t];
         const uint32_t s0 = A.bbase_prev[tile], s1 = A.bbase_prev[tile + 1];
         if (((s1 - s0 + 31u) >> 5) <= HEAVY_ROWS) continue;  // (uniform over the CTA)
-        rank_tile<CELL_BITS, W, VERIFY>(A, tile, s0, s1, wcnt, off, nb_tile, nb_first, bloom, nfar, overflow);
+        rank_tile<CELL_BITS, W>(A, tile, s0, s1, wcnt, off, nb_tile);
     }
+}
+
+// One thread per cell that received far movers: its regular arrivals sit at ranks [0, c - f) in slot order, the f far
+// arrivals behind them in ticket order.  Sort the far ones by old slot, then merge from the back (in place: a write never
+// passes the regular entry that is read next).  far_n[3] flags cells that are left as they are.
+constexpr int FIX_FAR_MAX = 32;
+template <int CELL_BITS>
+__global__ void __launch_bounds__(128) k_fix_far(const uint32_t* __restrict__ fixlist, uint32_t* __restrict__ far_n, const uint32_t* __restrict__ cnt,
+                                                 const uint32_t* __restrict__ fill, const uint2* __restrict__ cellmeta, const uint32_t* __restrict__ cnts,
+                                                 const uint32_t* __restrict__ pstart, const uint16_t* __restrict__ stab, uint32_t* __restrict__ src_of,
+                                                 uint32_t* __restrict__ ids)
+{
+    const uint32_t listed = far_n[0];
+    if (listed == 0) return;
+    if (listed > (uint32_t)FIX_CAP && blockIdx.x == 0 && threadIdx.x == 0) far_n[3] = 1;
+    const uint32_t ncell = min(listed, (uint32_t)FIX_CAP);
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < ncell; q += gridDim.x * blockDim.x) {
+        const uint32_t key = fixlist[q];
+        const uint32_t c = cnt[key], f = fill[key] & 0xffffu;
+        if (f == 0 || f > c) continue;
+        if (f > (uint32_t)FIX_FAR_MAX) { far_n[3] = 1; continue; }
+        auto slot = [&](uint32_t r) { return place_slot<CELL_BITS>(key, r, cellmeta, cnts, pstart, stab); };
+        uint32_t fv[FIX_FAR_MAX], fi[FIX_FAR_MAX];
+        for (uint32_t k = 0; k < f; ++k) {  // insertion sort of the far arrivals by old slot
+            const uint32_t sl = slot(c - f + k);
+            const uint32_t v = src_of[sl], id = ids[sl];
+            uint32_t j = k;
+            while (j > 0 && fv[j - 1] > v) { fv[j] = fv[j - 1]; fi[j] = fi[j - 1]; --j; }
+            fv[j] = v; fi[j] = id;
+        }
+        // merge from the back
+        int a = (int)(c - f) - 1, b = (int)f - 1;  // last regular, last far
+        uint32_t rv = 0, rid = 0;
+        bool have = false;
+        for (int w = (int)c - 1; b >= 0; --w) {
+            if (a >= 0 && !have) { const uint32_t sl = slot((uint32_t)a); rv = src_of[sl]; rid = ids[sl]; have = true; }
+            const uint32_t sw = slot((uint32_t)w);
+            if (a >= 0 && rv > fv[b]) { src_of[sw] = rv; ids[sw] = rid; --a; have = false; }
+            else { src_of[sw] = fv[b]; ids[sw] = fi[b]; --b; }
+        }
+    }
+}
+
+// check of a layout against ranks given from outside (mpm_debug_last_sort: the host derives them from the definition)
+template <int CELL_BITS>
+__global__ void __launch_bounds__(256) k_verify_layout(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ rank, int64_t n,
+                                                       const uint2* __restrict__ cellmeta, const uint32_t* __restrict__ cnts,
+                                                       const uint32_t* __restrict__ pstart, const uint16_t* __restrict__ stab,
+                                                       const uint32_t* __restrict__ src_of, const uint32_t* __restrict__ id_src,
+                                                       const uint32_t* __restrict__ id_dst, uint32_t* __restrict__ bad)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t dest = place_slot<CELL_BITS>(keys[i], rank[i], cellmeta, cnts, pstart, stab);
+    if (src_of[dest] != (uint32_t)i || id_dst[dest] != id_src[i]) atomicAdd(bad, 1u);
 }
 
 // grouped planes -> 64-byte records (a freshly uploaded or edited particle set enters the cell path)
@@ -885,9 +841,9 @@ int bin_create(MpmSolver* s)
     st->stable = getenv("MPM_ATOMIC_BINNING") == nullptr;
     const int64_t T = st->B + 2;
     CKB(cudaMalloc(&st->tcount, sizeof(uint32_t) * st->nblocks * T * T * T));
-    CKB(cudaMalloc(&st->far_list, sizeof(uint32_t) * 2 * FAR_CAP));
-    CKB(cudaMalloc(&st->far_n, sizeof(uint32_t) * 2));
-    CKB(cudaMemsetAsync(st->far_n, 0, sizeof(uint32_t) * 2, s->stream));
+    CKB(cudaMalloc(&st->fixlist, sizeof(uint32_t) * FIX_CAP));
+    CKB(cudaMalloc(&st->far_n, sizeof(uint32_t) * 4));
+    CKB(cudaMemsetAsync(st->far_n, 0, sizeof(uint32_t) * 4, s->stream));
     CKB(cudaMalloc(&st->fill, sizeof(uint32_t) * st->nslots));
     CKB(cudaMemsetAsync(st->fill, 0, sizeof(uint32_t) * st->nslots, s->stream));
     CKB(cudaMalloc(&st->keys, sizeof(uint32_t) * s->pitch));
@@ -909,7 +865,7 @@ void bin_destroy(MpmSolver* s)
     if (!st) return;
     cudaFree(st->cnt[0]); cudaFree(st->cnt[1]); cudaFree(st->cnts); cudaFree(st->ord); cudaFree(st->cellmeta); cudaFree(st->pstart); cudaFree(st->stab);
     for (int k = 0; k < 2; ++k) { cudaFree(st->bsum2[k]); cudaFree(st->bbase2[k]); cudaFree(st->active2[k]); }
-    cudaFree(st->nact); cudaFree(st->tcount); cudaFree(st->far_list); cudaFree(st->far_n);
+    cudaFree(st->nact); cudaFree(st->tcount); cudaFree(st->fixlist); cudaFree(st->far_n);
     cudaFree(st->fill); cudaFree(st->keys); cudaFree(st->src_of);
     cudaFree(st->misc); cudaFree(st->box);
     delete st;
@@ -1008,18 +964,19 @@ int bin_particles(MpmSolver* s)
     if (n > 0 && stable) {
         const RankGeom rg{st->nbx, st->nby, st->nbz};
         const unsigned grid_c = rank_grid(st, 12), grid_l = rank_grid(st, 8), grid_h = rank_grid(st, 4);  // (CTAs per SM)
-        const RankArgs ra{st->keys, st->bsum2[pl], st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->far_list, st->far_n, st->cellmeta,
-                          st->cnts, st->pstart, st->stab, st->fill, st->src_of, s->orig_id, s->orig_id_alt, nullptr, nullptr};
+        const RankArgs ra{st->keys, st->bsum2[pl], st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->cnt[nxt], st->cellmeta,
+                          st->cnts, st->pstart, st->stab, st->fill, st->src_of, s->orig_id, s->orig_id_alt};
+        const unsigned grid_f = rank_grid(st, 4);
         if (st->cell_bits == 9) {
-            k_rank_count<9><<<grid_c, RankCfg<9>::THREADS, 0, s->stream>>>(st->keys, st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->far_list, st->far_n);
-            k_far_sort<<<1, 1024, 0, s->stream>>>(st->far_list, st->far_n);
-            k_rank_place<9, false><<<grid_l, 128, 0, s->stream>>>(ra);
-            k_rank_place_heavy<9, false><<<grid_h, 256, 0, s->stream>>>(ra);
+            k_rank_count<9><<<grid_c, RankCfg<9>::THREADS, 0, s->stream>>>(st->keys, st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->fill, st->fixlist, st->far_n);
+            k_rank_place<9><<<grid_l, 128, 0, s->stream>>>(ra);
+            k_rank_place_heavy<9><<<grid_h, 256, 0, s->stream>>>(ra);
+            k_fix_far<9><<<grid_f, 128, 0, s->stream>>>(st->fixlist, st->far_n, st->cnt[nxt], st->fill, st->cellmeta, st->cnts, st->pstart, st->stab, st->src_of, s->orig_id_alt);
         } else {
-            k_rank_count<6><<<grid_c, RankCfg<6>::THREADS, 0, s->stream>>>(st->keys, st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->far_list, st->far_n);
-            k_far_sort<<<1, 1024, 0, s->stream>>>(st->far_list, st->far_n);
-            k_rank_place<6, false><<<grid_l, 128, 0, s->stream>>>(ra);
-            k_rank_place_heavy<6, false><<<grid_h, 256, 0, s->stream>>>(ra);
+            k_rank_count<6><<<grid_c, RankCfg<6>::THREADS, 0, s->stream>>>(st->keys, st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->fill, st->fixlist, st->far_n);
+            k_rank_place<6><<<grid_l, 128, 0, s->stream>>>(ra);
+            k_rank_place_heavy<6><<<grid_h, 256, 0, s->stream>>>(ra);
+            k_fix_far<6><<<grid_f, 128, 0, s->stream>>>(st->fixlist, st->far_n, st->cnt[nxt], st->fill, st->cellmeta, st->cnts, st->pstart, st->stab, st->src_of, s->orig_id_alt);
         }
         s->launches += 4;
     } else if (n > 0) {
@@ -1057,50 +1014,33 @@ int bin_debug_last(MpmSolver* s, uint32_t* keys_before, uint32_t* perm, int64_t 
     const int64_t n = s->n;
     if (cap < n) { s->err = "destination too small"; return MPM_ERR_INVALID; }
     if (n == 0) return MPM_OK;
+    // the definition: rank inside the cell = number of earlier records (lower old slot) with the same key
+    std::vector<uint32_t> keys((size_t)n), rank((size_t)n);
+    CKB(cudaMemcpyAsync(keys.data(), st->keys, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s->stream));
+    CKB(cudaStreamSynchronize(s->stream));
+    std::vector<uint32_t> start((size_t)st->nslots + 1, 0u);
+    for (int64_t i = 0; i < n; ++i) rank[(size_t)i] = start[keys[(size_t)i] + 1]++;
+    // the layout in place must put record i at (cell keys[i], rank[i]), with its original index
     uint32_t *d_rank = nullptr, *d_bad = nullptr;
+    uint32_t bad = 0;
     CKB(cudaMalloc(&d_rank, sizeof(uint32_t) * n));
     CKB(cudaMalloc(&d_bad, sizeof(uint32_t)));
     CKB(cudaMemsetAsync(d_bad, 0, sizeof(uint32_t), s->stream));
-    const int pl = st->prev_lay;
-    const RankGeom rg{st->nbx, st->nby, st->nbz};
-    const RankArgs ra{st->keys, st->bsum2[pl], st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->far_list, st->far_n, st->cellmeta,
-                      st->cnts, st->pstart, st->stab, st->fill, st->src_of, s->orig_id, s->orig_id_alt, d_rank, d_bad};
-    if (st->cell_bits == 9) {
-        k_rank_place<9, true><<<rank_grid(st, 8), 128, 0, s->stream>>>(ra);
-        k_rank_place_heavy<9, true><<<rank_grid(st, 4), 256, 0, s->stream>>>(ra);
-    } else {
-        k_rank_place<6, true><<<rank_grid(st, 8), 128, 0, s->stream>>>(ra);
-        k_rank_place_heavy<6, true><<<rank_grid(st, 4), 256, 0, s->stream>>>(ra);
-    }
-    std::vector<uint32_t> keys((size_t)n), rank((size_t)n);
-    uint32_t bad = 0;
-    CKB(cudaMemcpyAsync(keys.data(), st->keys, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s->stream));
-    CKB(cudaMemcpyAsync(rank.data(), d_rank, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s->stream));
+    CKB(cudaMemcpyAsync(d_rank, rank.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, s->stream));
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    if (st->cell_bits == 9) k_verify_layout<9><<<nb, 256, 0, s->stream>>>(st->keys, d_rank, n, st->cellmeta, st->cnts, st->pstart, st->stab, st->src_of, s->orig_id, s->orig_id_alt, d_bad);
+    else k_verify_layout<6><<<nb, 256, 0, s->stream>>>(st->keys, d_rank, n, st->cellmeta, st->cnts, st->pstart, st->stab, st->src_of, s->orig_id, s->orig_id_alt, d_bad);
     CKB(cudaMemcpyAsync(&bad, d_bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
     CKB(cudaStreamSynchronize(s->stream));
     cudaFree(d_rank); cudaFree(d_bad);
-    if (getenv("MPM_DEBUG_BIN")) {  // development aid: which side is off -- the ranks of the verify run against the definition
-        std::vector<uint32_t> seen_cnt((size_t)st->nslots, 0u);
-        uint64_t wrong = 0;
-        for (int64_t i = 0; i < n; ++i) wrong += rank[(size_t)i] != seen_cnt[keys[(size_t)i]]++;
-        uint32_t f[2] = {0, 0};
-        cudaMemcpy(f, st->far_n, sizeof(f), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[mpm bin debug] n=%lld bad=%u verify-ranks-not-stable=%llu far_n=%u unordered=%u pl=%d lay=%d\n", (long long)n, bad,
-                (unsigned long long)wrong, f[0], f[1], pl, st->lay);
+    if (bad) {
+        s->err = "binning introspection: " + std::to_string(bad) + " records are not where the stable sort by cell key puts them";
+        return MPM_ERR_STATE;
     }
-    if (bad) { s->err = "binning introspection: the layout in place differs from the re-derived one for " + std::to_string(bad) + " particles"; return MPM_ERR_STATE; }
     if (keys_before) std::copy(keys.begin(), keys.end(), keys_before);
-    if (perm) {
-        std::vector<uint32_t> start((size_t)st->nslots + 1, 0u);
-        for (int64_t i = 0; i < n; ++i) start[keys[(size_t)i] + 1] += 1;
+    if (perm) {  // cell-major position -> record index, as the (verified) layout has it
         for (int64_t k = 0; k < st->nslots; ++k) start[(size_t)k + 1] += start[(size_t)k];
-        std::vector<uint8_t> seen((size_t)n, 0);
-        for (int64_t i = 0; i < n; ++i) {
-            const uint64_t p = (uint64_t)start[keys[(size_t)i]] + rank[(size_t)i];
-            if (p >= (uint64_t)start[keys[(size_t)i] + 1] || seen[p]) { s->err = "binning introspection: ranks inside a cell are not a permutation"; return MPM_ERR_STATE; }
-            seen[p] = 1;
-            perm[p] = (uint32_t)i;
-        }
+        for (int64_t i = 0; i < n; ++i) perm[(size_t)start[keys[(size_t)i]] + rank[(size_t)i]] = (uint32_t)i;
     }
     return MPM_OK;
 }

@@ -40,8 +40,9 @@ struct BinState {
     uint32_t* fill = nullptr;        // [nslots] placement cursor (atomic ranking only)
     // stable ranking (k_rank_count / k_rank_place): particles of old block T that go to cell r of T's (B+2)^3 region
     uint32_t* tcount = nullptr;      // [nblocks][(B+2)^3]; row T is valid while bsum2[previous][T] > 0
-    uint32_t* far_list = nullptr;    // [2][FAR_CAP] {old slot, key} of the particles that left their block's region ("far movers")
-    uint32_t* far_n = nullptr;       // [2]: [0] count of this binning, [1] binnings that fell back to atomic ranks (overflow of the list)
+    uint32_t* fixlist = nullptr;     // [FIX_CAP] cells that received "far movers" (particles that left their block's region) in this binning
+    uint32_t* far_n = nullptr;       // [4]: [0] cells listed, [1] binnings with a cell left in atomic order, [2] far movers of this binning,
+                                     // [3] flag: this binning left a cell unordered (booked into [1] by the next scan)
     CUtensorMap grid_map;            // TMA descriptor of the local grid (box = one block's tile), for G2P's tile prefetch
     bool grid_map_valid = false;     // (re-encoded when the grid is re-created: multi-GPU re-cuts)
     bool stable = true;              // rank inside a cell = order of the old slots (std::stable_sort); false: atomic cursor
@@ -61,7 +62,7 @@ int bin_g2p_inputs(MpmSolver* s);  // position / mass planes in slot order, when
 // cell keys of the last binning's input (record order) and its permutation (cell-major rank -> input index), re-derived
 // by a verification run of the ranking kernels that also checks the layout in place against it
 int bin_debug_last(MpmSolver* s, uint32_t* keys_before, uint32_t* perm, int64_t cap);
-constexpr int FAR_CAP = 4096;
+constexpr int FIX_CAP = 1 << 21;  // cells with far arrivals a binning can put in order (8 MB)
 
 // cell kernels (mpm_kernels_cell.cu)
 int cell_p2g1(MpmSolver* s);

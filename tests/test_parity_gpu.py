@@ -649,10 +649,10 @@ def test_cell_binning_permutation_is_the_stable_sort(lib, grid, B):
         assert far_seen > 100, "the scene produced no far movers: that branch went untested"
 
 
-def test_cell_binning_far_mover_overflow_falls_back_and_is_counted(lib):
-    """More than 4096 particles leaving their block's apron in one step (a block of fluid thrown 12 cells per step): the
-    stable ranking cannot keep its list, the binning falls back to atomic ranks -- still a valid cell sort: the steps match
-    the oracle -- and says so in the stats."""
+def test_cell_binning_far_movers_at_scale(lib):
+    """A block of fluid thrown 12 cells per step: EVERY particle leaves its block's apron in every step.  The binning still
+    equals the stable sort (far arrivals are placed behind a cell's regular ones, then merged into slot order), the steps
+    match the oracle, and nothing is booked as unordered."""
     op = orc.variant("3d_gpu", 96)
     op.interaction = 0
     pos = orc.init_block(3, (10, 40, 40), (22, 52, 52), 0.5)  # 24^3 = 13824 particles
@@ -661,13 +661,35 @@ def test_cell_binning_far_mover_overflow_falls_back_and_is_counted(lib):
     mass = np.full(n, 0.01, np.float32)                      # keeps mass * |v| inside the int32 x 1e7 range
     with make_solver(op, n, kernel_path=3, math_mode=1) as s:
         s.upload(pos, vel, mass=mass)
-        s.step(3)                                            # the 2nd and 3rd binning see every particle 12 cells away
+        s.step(3)
+        s.run_phase(5)                                       # the binning of the state after 3 steps: all of it far movers
         st = s.stats()
-        assert st.unordered_binnings >= 1 and st.far_movers > 4096, (st.unordered_binnings, st.far_movers)
+        assert st.far_movers > 10000 and st.unordered_binnings == 0, (st.far_movers, st.unordered_binnings)
+        keys, perm = s.last_sort()                           # (verifies the layout in place on the device)
+        assert np.array_equal(perm.astype(np.int32), orc.stable_sort_perm(keys))
         gp, gv, gc, gm = s.download()
     ref = orc.State(op, pos, vel, mass=mass); ref.step(3)
     # (FAST against strict at |v| = 60: 36 cells travelled, a relative 1e-4 of that)
     assert np.abs(gp - ref.pos).max() < 4e-3 and helpers.rel_err(gv, ref.vel) < 1e-4, (np.abs(gp - ref.pos).max(), helpers.rel_err(gv, ref.vel))
+    helpers.assert_bit_equal(gm, mass, "mass / order")
+
+
+def test_cell_binning_too_many_far_arrivals_in_one_cell_is_counted(lib):
+    """More than 32 far arrivals in ONE cell (200 particles of one cell thrown together): that cell is left in atomic order
+    -- still a valid cell sort, the step matches the oracle -- and the binning is booked in MpmStats.unordered_binnings."""
+    op = orc.variant("3d_gpu", 96)
+    op.interaction = 0
+    rng = np.random.default_rng(9)
+    pos = (np.array([[20.0, 45.0, 45.0]], np.float32) + rng.uniform(0.05, 0.95, (200, 3)).astype(np.float32))
+    vel = np.zeros_like(pos); vel[:, 0] = 60.0
+    mass = np.full(200, 0.01, np.float32)
+    with make_solver(op, 200, kernel_path=3, math_mode=1) as s:
+        s.upload(pos, vel, mass=mass)
+        s.step(3)
+        assert s.stats().unordered_binnings >= 1
+        gp, gv, _, gm = s.download()
+    ref = orc.State(op, pos, vel, mass=mass); ref.step(3)
+    assert np.abs(gp - ref.pos).max() < 4e-3 and helpers.rel_err(gv, ref.vel) < 1e-3
     helpers.assert_bit_equal(gm, mass, "mass / order")
 
 
