@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(1 << CELL_BITS) k_block_order(const uint32_t* 
                                                                const uint32_t* __restrict__ active, const uint32_t* __restrict__ misc,
                                                                uint16_t* __restrict__ ord, uint32_t* __restrict__ cnts,
                                                                uint2* __restrict__ cellmeta, uint32_t* __restrict__ pstart,
-                                                               uint16_t* __restrict__ stab, uint32_t* __restrict__ fill)
+                                                               uint16_t* __restrict__ stab, uint32_t* __restrict__ fill, uint32_t* __restrict__ farcnt)
 {
     constexpr int NC = 1 << CELL_BITS, NV = 2 * NC, NBIN = 64, NW = NC / 32, EXTRA = NV - NC;
     __shared__ uint32_t hist[NBIN], base[NBIN];
@@ -213,7 +213,8 @@ __global__ void __launch_bounds__(1 << CELL_BITS) k_block_order(const uint32_t* 
     if (t == 0) carry_s = 0;
     __syncthreads();
     const uint32_t c = cnt[blk0 + t];
-    fill[blk0 + t] = 0;  // k_place's cursor: only the cells of non-empty blocks are ever used, so they are reset here
+    fill[blk0 + t] = 0;  // the placement cursor and the far-arrival counter: only the cells of non-empty blocks are ever used,
+    farcnt[blk0 + t] = 0;  // so they are reset here
     // extra virtual cells this cell wants, granted in cell order while the block's budget lasts
     const uint32_t want = c > VROWS ? (c + VROWS - 1) / VROWS - 1 : 0;
     uint32_t x = want;
@@ -450,7 +451,7 @@ __device__ __forceinline__ int region_index(uint32_t key, const TileCtx& c, cons
 template <int CELL_BITS>
 __global__ void __launch_bounds__(RankCfg<CELL_BITS>::THREADS, 12) k_rank_count(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ bbase_prev,
                                                                                 const uint32_t* __restrict__ active_prev, const uint32_t* __restrict__ nact_prev,
-                                                                                RankGeom g, uint32_t* __restrict__ tcount, uint32_t* __restrict__ fill,
+                                                                                RankGeom g, uint32_t* __restrict__ tcount, uint32_t* __restrict__ farcnt,
                                                                                 uint32_t* __restrict__ fixlist, uint32_t* __restrict__ far_n)
 {
     using C = RankCfg<CELL_BITS>;
@@ -477,9 +478,9 @@ __global__ void __launch_bounds__(RankCfg<CELL_BITS>::THREADS, 12) k_rank_count(
                 if (i >= s1) continue;
                 const int r = region_index<CELL_BITS>(key[j], tc, g);
                 if (r >= 0) atomicAdd(&cnt[r], 1u);
-                else {  // a far mover: counted per target cell (fill[] was cleared with the block's layout); the first one lists the cell
+                else {  // a far mover: counted per target cell (farcnt[] was cleared with the block's layout); the first one lists the cell
                     atomicAdd(far_n + 2, 1u);
-                    if (atomicAdd(&fill[key[j]], 1u) == 0u) {
+                    if (atomicAdd(&farcnt[key[j]], 1u) == 0u) {
                         const uint32_t f = atomicAdd(far_n, 1u);
                         if (f < (uint32_t)FIX_CAP) fixlist[f] = key[j];
                     }
@@ -505,11 +506,17 @@ struct RankArgs {
     const uint32_t* cnts;
     const uint32_t* pstart;
     const uint16_t* stab;
-    uint32_t* fill;
+    uint32_t* fill;      // atomic placement cursor (only when a binning gives up on the stable order)
+    uint32_t* farcnt;    // far arrivals per cell: low half = count (k_rank_count), high half = tickets handed out
+    uint32_t* far_n;
     uint32_t* src_of;
     const uint32_t* id_src;
     uint32_t* id_dst;
 };
+
+// A binning with more far movers than this is ranked with the atomic cursor altogether (and booked as unordered): bulk
+// motion of more than a cell per step breaks the premise of the tile regions, and the exact fix-up is sized for outliers.
+constexpr uint32_t FAR_LIMIT = 1u << 17;
 
 // tiles with more rows than this are ranked by a whole CTA (k_rank_place_heavy), the others by one warp each
 constexpr uint32_t HEAVY_ROWS = 256;
@@ -527,6 +534,16 @@ __device__ __forceinline__ void rank_tile(const RankArgs& A, uint32_t tile, uint
     const int lane = threadIdx.x & 31, w = (W == 1) ? 0 : (int)(threadIdx.x >> 5), gt = (W == 1) ? lane : (int)threadIdx.x;
     const unsigned lt = (1u << lane) - 1u;
     auto sync = [&]() { if (W == 1) __syncwarp(); else __syncthreads(); };
+    if (A.far_n[2] > FAR_LIMIT) {  // (uniform over the launch) too violent a step for the stable order: atomic ranks
+        if (gt == 0) A.far_n[3] = 1;
+        for (uint32_t i = s0 + gt; i < s1; i += GS) {
+            const uint32_t key = A.keys[i];
+            const uint32_t dest = place_slot<CELL_BITS>(key, atomicAdd(&A.fill[key], 1u), A.cellmeta, A.cnts, A.pstart, A.stab);
+            A.src_of[dest] = i;
+            A.id_dst[dest] = A.id_src[i];
+        }
+        return;
+    }
     const TileCtx tc = tile_ctx(tile, g);
     const int tbx = tc.tbx, tby = tc.tby, tbz = tc.tbz;
     for (int k = gt; k < W * C::RC; k += GS) wcnt[k] = 0;
@@ -629,12 +646,12 @@ __device__ __forceinline__ void rank_tile(const RankArgs& A, uint32_t tile, uint
         }
 #pragma unroll
         for (int j = 0; j < RB; ++j) rc[j] = __shfl_sync(0xffffffffu, old[j], __ffs(peers[j]) - 1) + (uint32_t)__popc(peers[j] & lt);
-        // far movers go behind their cell's regular arrivals: ticket from the high half of fill[] (the low half keeps the
+        // far movers go behind their cell's regular arrivals: ticket from the high half of farcnt[] (the low half keeps the
         // cell's far count for k_fix_far, which puts them where the stable order wants them)
 #pragma unroll
         for (int j = 0; j < RB; ++j) {
             if (valid[j] && rg[j] < 0) {
-                const uint32_t oldf = atomicAdd(&A.fill[key[j]], 0x10000u);
+                const uint32_t oldf = atomicAdd(&A.farcnt[key[j]], 0x10000u);
                 rc[j] = A.cnt[key[j]] - (oldf & 0xffffu) + (oldf >> 16);
             }
         }
@@ -696,7 +713,7 @@ __global__ void __launch_bounds__(128) k_fix_far(const uint32_t* __restrict__ fi
                                                  uint32_t* __restrict__ ids)
 {
     const uint32_t listed = far_n[0];
-    if (listed == 0) return;
+    if (listed == 0 || far_n[2] > FAR_LIMIT) return;
     if (listed > (uint32_t)FIX_CAP && blockIdx.x == 0 && threadIdx.x == 0) far_n[3] = 1;
     const uint32_t ncell = min(listed, (uint32_t)FIX_CAP);
     for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < ncell; q += gridDim.x * blockDim.x) {
@@ -846,6 +863,8 @@ int bin_create(MpmSolver* s)
     CKB(cudaMemsetAsync(st->far_n, 0, sizeof(uint32_t) * 4, s->stream));
     CKB(cudaMalloc(&st->fill, sizeof(uint32_t) * st->nslots));
     CKB(cudaMemsetAsync(st->fill, 0, sizeof(uint32_t) * st->nslots, s->stream));
+    CKB(cudaMalloc(&st->farcnt, sizeof(uint32_t) * st->nslots));
+    CKB(cudaMemsetAsync(st->farcnt, 0, sizeof(uint32_t) * st->nslots, s->stream));
     CKB(cudaMalloc(&st->keys, sizeof(uint32_t) * s->pitch));
     CKB(cudaMalloc(&st->src_of, sizeof(uint32_t) * (s->pitch + 192)));  // (the cell kernels read up to two units past the last slot)
     CKB(cudaMemsetAsync(st->src_of, 0, sizeof(uint32_t) * (s->pitch + 192), s->stream));
@@ -866,7 +885,7 @@ void bin_destroy(MpmSolver* s)
     cudaFree(st->cnt[0]); cudaFree(st->cnt[1]); cudaFree(st->cnts); cudaFree(st->ord); cudaFree(st->cellmeta); cudaFree(st->pstart); cudaFree(st->stab);
     for (int k = 0; k < 2; ++k) { cudaFree(st->bsum2[k]); cudaFree(st->bbase2[k]); cudaFree(st->active2[k]); }
     cudaFree(st->nact); cudaFree(st->tcount); cudaFree(st->fixlist); cudaFree(st->far_n);
-    cudaFree(st->fill); cudaFree(st->keys); cudaFree(st->src_of);
+    cudaFree(st->fill); cudaFree(st->farcnt); cudaFree(st->keys); cudaFree(st->src_of);
     cudaFree(st->misc); cudaFree(st->box);
     delete st;
     s->bin = nullptr;
@@ -954,29 +973,29 @@ int bin_particles(MpmSolver* s)
     if (st->cell_bits == 9) {
         k_block_sums<9><<<nbw, 256, 0, s->stream>>>(st->cnt[nxt], st->nblocks, bsum);
         k_scan_blocks<<<1, 1024, 0, s->stream>>>(bsum, st->nblocks, bbase, active, st->misc, bg, st->box, st->box_cleared ? 1 : 0, st->nact + nl, st->far_n);
-        k_block_order<9><<<(unsigned)st->nblocks, 512, 0, s->stream>>>(st->cnt[nxt], bbase, active, st->misc, st->ord, st->cnts, st->cellmeta, st->pstart, st->stab, st->fill);
+        k_block_order<9><<<(unsigned)st->nblocks, 512, 0, s->stream>>>(st->cnt[nxt], bbase, active, st->misc, st->ord, st->cnts, st->cellmeta, st->pstart, st->stab, st->fill, st->farcnt);
     } else {
         k_block_sums<6><<<nbw, 256, 0, s->stream>>>(st->cnt[nxt], st->nblocks, bsum);
         k_scan_blocks<<<1, 1024, 0, s->stream>>>(bsum, st->nblocks, bbase, active, st->misc, bg, st->box, st->box_cleared ? 1 : 0, st->nact + nl, st->far_n);
-        k_block_order<6><<<(unsigned)st->nblocks, 64, 0, s->stream>>>(st->cnt[nxt], bbase, active, st->misc, st->ord, st->cnts, st->cellmeta, st->pstart, st->stab, st->fill);
+        k_block_order<6><<<(unsigned)st->nblocks, 64, 0, s->stream>>>(st->cnt[nxt], bbase, active, st->misc, st->ord, st->cnts, st->cellmeta, st->pstart, st->stab, st->fill, st->farcnt);
     }
     s->launches += 3;
     if (n > 0 && stable) {
         const RankGeom rg{st->nbx, st->nby, st->nbz};
         const unsigned grid_c = rank_grid(st, 12), grid_l = rank_grid(st, 8), grid_h = rank_grid(st, 4);  // (CTAs per SM)
         const RankArgs ra{st->keys, st->bsum2[pl], st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->cnt[nxt], st->cellmeta,
-                          st->cnts, st->pstart, st->stab, st->fill, st->src_of, s->orig_id, s->orig_id_alt};
+                          st->cnts, st->pstart, st->stab, st->fill, st->farcnt, st->far_n, st->src_of, s->orig_id, s->orig_id_alt};
         const unsigned grid_f = rank_grid(st, 4);
         if (st->cell_bits == 9) {
-            k_rank_count<9><<<grid_c, RankCfg<9>::THREADS, 0, s->stream>>>(st->keys, st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->fill, st->fixlist, st->far_n);
+            k_rank_count<9><<<grid_c, RankCfg<9>::THREADS, 0, s->stream>>>(st->keys, st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->farcnt, st->fixlist, st->far_n);
             k_rank_place<9><<<grid_l, 128, 0, s->stream>>>(ra);
             k_rank_place_heavy<9><<<grid_h, 256, 0, s->stream>>>(ra);
-            k_fix_far<9><<<grid_f, 128, 0, s->stream>>>(st->fixlist, st->far_n, st->cnt[nxt], st->fill, st->cellmeta, st->cnts, st->pstart, st->stab, st->src_of, s->orig_id_alt);
+            k_fix_far<9><<<grid_f, 128, 0, s->stream>>>(st->fixlist, st->far_n, st->cnt[nxt], st->farcnt, st->cellmeta, st->cnts, st->pstart, st->stab, st->src_of, s->orig_id_alt);
         } else {
-            k_rank_count<6><<<grid_c, RankCfg<6>::THREADS, 0, s->stream>>>(st->keys, st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->fill, st->fixlist, st->far_n);
+            k_rank_count<6><<<grid_c, RankCfg<6>::THREADS, 0, s->stream>>>(st->keys, st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->farcnt, st->fixlist, st->far_n);
             k_rank_place<6><<<grid_l, 128, 0, s->stream>>>(ra);
             k_rank_place_heavy<6><<<grid_h, 256, 0, s->stream>>>(ra);
-            k_fix_far<6><<<grid_f, 128, 0, s->stream>>>(st->fixlist, st->far_n, st->cnt[nxt], st->fill, st->cellmeta, st->cnts, st->pstart, st->stab, st->src_of, s->orig_id_alt);
+            k_fix_far<6><<<grid_f, 128, 0, s->stream>>>(st->fixlist, st->far_n, st->cnt[nxt], st->farcnt, st->cellmeta, st->cnts, st->pstart, st->stab, st->src_of, s->orig_id_alt);
         }
         s->launches += 4;
     } else if (n > 0) {

@@ -38,6 +38,7 @@ struct BinState {
     uint32_t* bsum = nullptr;        // = bsum2[lay]
     uint32_t* bbase = nullptr;       // = bbase2[lay]
     uint32_t* fill = nullptr;        // [nslots] placement cursor (atomic ranking only)
+    uint32_t* farcnt = nullptr;      // [nslots] far arrivals per cell (stable ranking): count | tickets << 16
     // stable ranking (k_rank_count / k_rank_place): particles of old block T that go to cell r of T's (B+2)^3 region
     uint32_t* tcount = nullptr;      // [nblocks][(B+2)^3]; row T is valid while bsum2[previous][T] > 0
     uint32_t* fixlist = nullptr;     // [FIX_CAP] cells that received "far movers" (particles that left their block's region) in this binning

@@ -689,7 +689,8 @@ def test_cell_binning_too_many_far_arrivals_in_one_cell_is_counted(lib):
         assert s.stats().unordered_binnings >= 1
         gp, gv, _, gm = s.download()
     ref = orc.State(op, pos, vel, mass=mass); ref.step(3)
-    assert np.abs(gp - ref.pos).max() < 4e-3 and helpers.rel_err(gv, ref.vel) < 1e-3
+    # (200 fp32 addends per node before the one truncation, |v| = 60, 36 cells travelled: a relative 5e-4 of that)
+    assert np.abs(gp - ref.pos).max() < 2e-2 and helpers.rel_err(gv, ref.vel) < 1e-3
     helpers.assert_bit_equal(gm, mass, "mass / order")
 
 
