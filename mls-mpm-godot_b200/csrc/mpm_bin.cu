@@ -509,6 +509,7 @@ struct RankArgs {
     uint32_t* fill;      // atomic placement cursor (only when a binning gives up on the stable order)
     uint32_t* farcnt;    // far arrivals per cell: low half = count (k_rank_count), high half = tickets handed out
     uint32_t* far_n;
+    uint32_t n_total;    // particles
     uint32_t* src_of;
     const uint32_t* id_src;
     uint32_t* id_dst;
@@ -534,16 +535,6 @@ __device__ __forceinline__ void rank_tile(const RankArgs& A, uint32_t tile, uint
     const int lane = threadIdx.x & 31, w = (W == 1) ? 0 : (int)(threadIdx.x >> 5), gt = (W == 1) ? lane : (int)threadIdx.x;
     const unsigned lt = (1u << lane) - 1u;
     auto sync = [&]() { if (W == 1) __syncwarp(); else __syncthreads(); };
-    if (A.far_n[2] > FAR_LIMIT) {  // (uniform over the launch) too violent a step for the stable order: atomic ranks
-        if (gt == 0) A.far_n[3] = 1;
-        for (uint32_t i = s0 + gt; i < s1; i += GS) {
-            const uint32_t key = A.keys[i];
-            const uint32_t dest = place_slot<CELL_BITS>(key, atomicAdd(&A.fill[key], 1u), A.cellmeta, A.cnts, A.pstart, A.stab);
-            A.src_of[dest] = i;
-            A.id_dst[dest] = A.id_src[i];
-        }
-        return;
-    }
     const TileCtx tc = tile_ctx(tile, g);
     const int tbx = tc.tbx, tby = tc.tby, tbz = tc.tbz;
     for (int k = gt; k < W * C::RC; k += GS) wcnt[k] = 0;
@@ -675,6 +666,28 @@ __global__ void __launch_bounds__(128, 8) k_rank_place(const __grid_constant__ R
     __shared__ uint32_t wcnt[4][C::RC];
     __shared__ uint32_t nb_tile[4][28];
     const int w = threadIdx.x >> 5;
+    if (A.far_n[2] > FAR_LIMIT) {
+        // too violent a step for the stable order (uniform over the launch): every particle takes its rank from the atomic
+        // cursor, all threads of the grid striding over the particles, four loads in flight each
+        if (blockIdx.x == 0 && threadIdx.x == 0) A.far_n[3] = 1;
+        const uint32_t n = A.n_total, stride = gridDim.x * blockDim.x;
+        for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
+            uint32_t key[4], id[4], rk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const uint32_t i = i0 + j * stride; key[j] = i < n ? A.keys[i] : 0u; id[j] = i < n ? A.id_src[i] : 0u; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rk[j] = (i0 + j * stride < n) ? atomicAdd(&A.fill[key[j]], 1u) : 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t i = i0 + j * stride;
+                if (i >= n) continue;
+                const uint32_t dest = place_slot<CELL_BITS>(key[j], rk[j], A.cellmeta, A.cnts, A.pstart, A.stab);
+                A.src_of[dest] = i;
+                A.id_dst[dest] = id[j];
+            }
+        }
+        return;
+    }
     const uint32_t na = *A.nact_prev;
     for (uint32_t t = blockIdx.x * 4 + w; t < na; t += gridDim.x * 4) {
         const uint32_t tile = A.active_prev[t];
@@ -693,6 +706,7 @@ __global__ void __launch_bounds__(256) k_rank_place_heavy(const __grid_constant_
     __shared__ uint32_t wcnt[W * C::RC];
     __shared__ uint32_t off[C::RC];
     __shared__ uint32_t nb_tile[28];
+    if (A.far_n[2] > FAR_LIMIT) return;  // (k_rank_place ranks everything atomically)
     const uint32_t na = *A.nact_prev;
     for (uint32_t t = blockIdx.x; t < na; t += gridDim.x) {
         const uint32_t tile = A.active_prev[t];
@@ -984,7 +998,7 @@ int bin_particles(MpmSolver* s)
         const RankGeom rg{st->nbx, st->nby, st->nbz};
         const unsigned grid_c = rank_grid(st, 12), grid_l = rank_grid(st, 8), grid_h = rank_grid(st, 4);  // (CTAs per SM)
         const RankArgs ra{st->keys, st->bsum2[pl], st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->cnt[nxt], st->cellmeta,
-                          st->cnts, st->pstart, st->stab, st->fill, st->farcnt, st->far_n, st->src_of, s->orig_id, s->orig_id_alt};
+                          st->cnts, st->pstart, st->stab, st->fill, st->farcnt, st->far_n, (uint32_t)n, st->src_of, s->orig_id, s->orig_id_alt};
         const unsigned grid_f = rank_grid(st, 4);
         if (st->cell_bits == 9) {
             k_rank_count<9><<<grid_c, RankCfg<9>::THREADS, 0, s->stream>>>(st->keys, st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->farcnt, st->fixlist, st->far_n);
