@@ -161,11 +161,14 @@ typedef struct MpmStats {
     int64_t migrated;         /* particles this rank has sent to its neighbours since the communicator was attached */
     int64_t slab_jump_clamps; /* multi-GPU: particles that would have crossed more than one slab in a single step (|v| dt
                                  larger than the neighbouring slab is wide) and were held back in that slab's far plane */
-    int64_t unordered_binnings; /* cell path: bin phases that could not rank stably (more than 4096 particles jumped out of
-                                   their grid block's one-cell apron in one step: the simulation has blown up) and used an
-                                   atomic cursor instead; 0 means every binning so far equals std::stable_sort */
+    int64_t unordered_binnings; /* cell path: bin phases that left cells in atomic order instead of the stable one: more than
+                                   131072 particles jumped out of their grid block's one-cell apron in that step (bulk motion of
+                                   more than a cell per step), or one cell received more than 32 such particles.  0 means every
+                                   binning so far equals std::stable_sort */
     int64_t far_movers;         /* cell path: particles of the most recent bin phase that had left their grid block's one-cell
-                                   apron (ranked exactly through the sorted far-mover list; normally 0) */
+                                   apron (put in order by the fix-up pass; a lower bound once a binning has given up) */
+    int64_t halo_peer_exchanges; /* multi-GPU: halo exchanges done by direct peer stores (k_halo_push / k_halo_wait_add over
+                                   CUDA IPC or in-process peer pointers) rather than through the transport */
 } MpmStats;
 
 typedef struct MpmSolver MpmSolver; /* opaque */

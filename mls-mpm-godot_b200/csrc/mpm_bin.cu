@@ -388,6 +388,10 @@ __global__ void __launch_bounds__(256) k_place(const uint32_t* __restrict__ keys
 // cell sort in atomic order) and the binning is counted in MpmStats.unordered_binnings.
 struct RankGeom { int nbx, nby, nbz; };
 
+// A binning with more far movers than this is ranked with the atomic cursor altogether (and booked as unordered): bulk
+// motion of more than a cell per step breaks the premise of the tile regions, and the exact fix-up is sized for outliers.
+constexpr uint32_t FAR_LIMIT = 1u << 17;
+
 template <int CELL_BITS>
 struct RankCfg {
     static constexpr int LOGB = CELL_BITS / 3, B = 1 << LOGB, T = B + 2, RC = T * T * T;
@@ -465,6 +469,7 @@ __global__ void __launch_bounds__(RankCfg<CELL_BITS>::THREADS, 12) k_rank_count(
         for (int k = threadIdx.x; k < C::RC; k += C::THREADS) cnt[k] = 0;
         __syncthreads();
         const uint32_t s0 = bbase_prev[tile], s1 = bbase_prev[tile + 1];
+        const bool gave_up = *reinterpret_cast<volatile uint32_t*>(far_n + 2) > FAR_LIMIT;  // (then MpmStats.far_movers is a lower bound)
         for (uint32_t base = s0; base < s1; base += C::THREADS * KB) {
             uint32_t key[KB];
 #pragma unroll
@@ -475,13 +480,26 @@ __global__ void __launch_bounds__(RankCfg<CELL_BITS>::THREADS, 12) k_rank_count(
 #pragma unroll
             for (int j = 0; j < KB; ++j) {
                 const uint32_t i = base + j * C::THREADS + threadIdx.x;
-                if (i >= s1) continue;
-                const int r = region_index<CELL_BITS>(key[j], tc, g);
-                if (r >= 0) atomicAdd(&cnt[r], 1u);
-                else {  // a far mover: counted per target cell (farcnt[] was cleared with the block's layout); the first one lists the cell
-                    atomicAdd(far_n + 2, 1u);
-                    if (atomicAdd(&farcnt[key[j]], 1u) == 0u) {
-                        const uint32_t f = atomicAdd(far_n, 1u);
+                const int r = i < s1 ? region_index<CELL_BITS>(key[j], tc, g) : 0;
+                const bool far = i < s1 && r < 0;
+                if (i < s1 && r >= 0) atomicAdd(&cnt[r], 1u);
+                // far movers: counted per target cell (farcnt[] was cleared with the block's layout); the first one of a cell
+                // lists the cell.  The two global counters are bumped once per warp, not per particle (a violent scene has
+                // hundreds of thousands of far movers: per-particle atomics on one address took over a millisecond), and not at
+                // all once the binning is past the point where it gives up on the stable order anyway.
+                const unsigned mf = __ballot_sync(0xffffffffu, far && !gave_up);
+                if (mf) {
+                    const int lane = threadIdx.x & 31;
+                    const bool first = ((mf >> lane) & 1u) && atomicAdd(&farcnt[key[j]], 1u) == 0u;
+                    const unsigned ml = __ballot_sync(0xffffffffu, first);
+                    uint32_t at = 0;
+                    if (lane == __ffs(mf) - 1) {
+                        atomicAdd(far_n + 2, (uint32_t)__popc(mf));
+                        if (ml) at = atomicAdd(far_n, (uint32_t)__popc(ml));
+                    }
+                    at = __shfl_sync(0xffffffffu, at, __ffs(mf) - 1);
+                    if (first) {
+                        const uint32_t f = at + (uint32_t)__popc(ml & ((1u << lane) - 1u));
                         if (f < (uint32_t)FIX_CAP) fixlist[f] = key[j];
                     }
                 }
@@ -515,9 +533,7 @@ struct RankArgs {
     uint32_t* id_dst;
 };
 
-// A binning with more far movers than this is ranked with the atomic cursor altogether (and booked as unordered): bulk
-// motion of more than a cell per step breaks the premise of the tile regions, and the exact fix-up is sized for outliers.
-constexpr uint32_t FAR_LIMIT = 1u << 17;
+
 
 // tiles with more rows than this are ranked by a whole CTA (k_rank_place_heavy), the others by one warp each
 constexpr uint32_t HEAVY_ROWS = 256;

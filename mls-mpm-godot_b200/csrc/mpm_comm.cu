@@ -53,6 +53,10 @@ struct Transport {
     // true when every rank is its own process on its own GPU: halo planes can then be written straight into the
     // neighbour's memory over NVLink (CUDA IPC) with kernels that wait on each other's flags
     virtual bool separate_gpus() const { return false; }
+    // ranks of one process (LOCAL): hand every rank the device pointers of its neighbours' receive allocation, so that
+    // the same peer-store halo kernels run as with CUDA IPC between processes.  `mine` may be null (set-up failed here);
+    // returns true only if EVERY rank of the chain offered a pointer (all ranks then take the peer-store path).
+    virtual bool share_pointers(void* mine, int device, void** left, void** right, int* dev_left, int* dev_right) { return false; }
 };
 
 // ---------------------------------------------------------------- NCCL
@@ -135,6 +139,12 @@ struct MpmLocalHub {
     std::vector<mpm::Mailbox> to_right;  // [r]: r -> r+1
     std::vector<mpm::Mailbox> to_left;   // [r]: r -> r-1
     int timeout_s = 60;
+    // one-time rendezvous of the peer-store halo set-up: every rank publishes the device pointer of its receive allocation
+    std::mutex pm;
+    std::condition_variable pcv;
+    std::vector<void*> p2p_ptr;
+    std::vector<int> p2p_dev;
+    int p2p_arrived = 0;
 };
 
 namespace mpm {
@@ -182,6 +192,22 @@ struct LocalTransport : Transport {
         cudaStreamWaitEvent(st, mb.done, 0);
         return MPM_OK;
     }
+    bool share_pointers(void* mine, int dev, void** left, void** right, int* dev_left, int* dev_right) override
+    {
+        std::unique_lock<std::mutex> lk(hub->pm);
+        if ((int)hub->p2p_ptr.size() != world) { hub->p2p_ptr.assign(world, nullptr); hub->p2p_dev.assign(world, 0); }
+        hub->p2p_ptr[rank] = mine; hub->p2p_dev[rank] = dev;
+        hub->p2p_arrived += 1;
+        hub->pcv.notify_all();
+        if (!hub->pcv.wait_for(lk, std::chrono::seconds(hub->timeout_s), [&] { return hub->p2p_arrived >= world; })) return false;
+        bool all = true;
+        for (int r = 0; r < world; ++r) all = all && hub->p2p_ptr[r] != nullptr;
+        *left = rank > 0 ? hub->p2p_ptr[rank - 1] : nullptr;
+        *right = rank < world - 1 ? hub->p2p_ptr[rank + 1] : nullptr;
+        *dev_left = rank > 0 ? hub->p2p_dev[rank - 1] : dev;
+        *dev_right = rank < world - 1 ? hub->p2p_dev[rank + 1] : dev;
+        return all;
+    }
     int exchange(const void* sendL, size_t nsl, void* recvL, size_t nrl, const void* sendR, size_t nsr, void* recvR,
                  size_t nrr, cudaStream_t st, std::string& err) override
     {
@@ -213,7 +239,7 @@ struct CommState {
     int4* halo_snap[2] = {nullptr, nullptr};
     int64_t halo_cells = 0;  // 2 * Ry * Rz
     // direct peer stores for the halo planes (CUDA IPC over NVLink): own = [side][pass] receive regions + flags
-    bool p2p_tried = false, p2p_ready = false;
+    bool p2p_tried = false, p2p_ready = false, p2p_inproc = false;
     uint8_t* p2p_own = nullptr;
     uint8_t* p2p_peer[2] = {nullptr, nullptr};  // the left / right neighbour's allocation, mapped here
     uint32_t p2p_seq[2] = {0, 0};               // messages sent so far, per pass
@@ -257,7 +283,7 @@ void comm_destroy(MpmSolver* s)
     CommState* c = s->comm;
     if (!c) return;
     free_slab_buffers(c);
-    for (int k = 0; k < 2; ++k) if (c->p2p_peer[k]) cudaIpcCloseMemHandle(c->p2p_peer[k]);
+    if (!c->p2p_inproc) for (int k = 0; k < 2; ++k) if (c->p2p_peer[k]) cudaIpcCloseMemHandle(c->p2p_peer[k]);
     cudaFree(c->p2p_own); cudaFree(c->p2p_done);
     for (int k = 0; k < 2; ++k) { cudaFree(c->send_rec[k]); cudaFree(c->recv_rec[k]); }
     cudaFree(c->d_cnt); cudaFree(c->holes); cudaFree(c->fillers); cudaFree(c->leave[0]); cudaFree(c->leave[1]);
@@ -313,6 +339,7 @@ void comm_fill_stats(const MpmSolver* s, MpmStats* st)
     st->world = s->comm->world;
     st->slab_jump_clamps = s->comm->slab_jump_clamps;
     st->migrated = s->comm->migrated_out;
+    st->halo_peer_exchanges = s->comm->p2p_seq[0] + s->comm->p2p_seq[1];
 }
 
 // ================================================================ slab set-up at upload time
@@ -570,9 +597,28 @@ static void p2p_setup(MpmSolver* s)
 {
     CommState* c = s->comm;
     c->p2p_tried = true;
-    if (!c->tr->separate_gpus() || getenv("MPM_NO_P2P")) return;
+    if (getenv("MPM_NO_P2P")) return;
     const bool hasL = c->rank > 0, hasR = c->rank < c->world - 1;
     const size_t region = 16 * (size_t)c->halo_cells, total = 4 * region + 4 * P2P_FLAG_STRIDE * sizeof(uint32_t);
+    if (!c->tr->separate_gpus()) {
+        // ranks of one process: plain device pointers instead of IPC handles (peer access enabled when the devices differ)
+        bool ok = cudaMalloc(&c->p2p_own, total) == cudaSuccess && cudaMemset(c->p2p_own, 0, total) == cudaSuccess &&
+                  cudaMalloc(&c->p2p_done, 8 * sizeof(uint32_t)) == cudaSuccess && cudaMemset(c->p2p_done, 0, 8 * sizeof(uint32_t)) == cudaSuccess;
+        void *pl = nullptr, *pr = nullptr;
+        int dl = s->device, dr = s->device;
+        ok = c->tr->share_pointers(ok ? c->p2p_own : nullptr, s->device, &pl, &pr, &dl, &dr) && ok;
+        for (int d : {dl, dr})
+            if (ok && d != s->device) {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(d, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = false;
+                cudaGetLastError();
+            }
+        // (a rank whose peer access failed cannot tell the others any more: the halo kernels' 10 s time-out reports it)
+        c->p2p_peer[0] = (uint8_t*)pl; c->p2p_peer[1] = (uint8_t*)pr;
+        c->p2p_inproc = true;
+        c->p2p_ready = ok;
+        return;
+    }
     uint8_t *hs = nullptr, *hr = nullptr;  // device staging: [0..63] handle for/from the left, [64..127] right
     bool ok = cudaMalloc(&c->p2p_own, total) == cudaSuccess && cudaMemset(c->p2p_own, 0, total) == cudaSuccess &&
               cudaMalloc(&c->p2p_done, 8 * sizeof(uint32_t)) == cudaSuccess && cudaMemset(c->p2p_done, 0, 8 * sizeof(uint32_t)) == cudaSuccess &&

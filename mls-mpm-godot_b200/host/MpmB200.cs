@@ -52,7 +52,7 @@ namespace MpmB200
         public long num_particles, num_cells, steps, kernel_launches;
         public float ms_sort, ms_clear, ms_p2g1, ms_p2g2, ms_update, ms_g2p, ms_exchange, ms_step;
         public int kernel_path, overflow, rank, world;
-        public long local_particles, migrated, slab_jump_clamps, unordered_binnings, far_movers;
+        public long local_particles, migrated, slab_jump_clamps, unordered_binnings, far_movers, halo_peer_exchanges;
     }
 
     public static unsafe class Native

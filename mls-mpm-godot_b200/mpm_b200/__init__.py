@@ -57,7 +57,7 @@ class MpmStats(C.Structure):
         ("ms_sort", C.c_float), ("ms_clear", C.c_float), ("ms_p2g1", C.c_float), ("ms_p2g2", C.c_float),
         ("ms_update", C.c_float), ("ms_g2p", C.c_float), ("ms_exchange", C.c_float), ("ms_step", C.c_float),
         ("kernel_path", C.c_int32), ("overflow", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
-        ("local_particles", C.c_int64), ("migrated", C.c_int64), ("slab_jump_clamps", C.c_int64), ("unordered_binnings", C.c_int64), ("far_movers", C.c_int64),
+        ("local_particles", C.c_int64), ("migrated", C.c_int64), ("slab_jump_clamps", C.c_int64), ("unordered_binnings", C.c_int64), ("far_movers", C.c_int64), ("halo_peer_exchanges", C.c_int64),
     ]
 
 

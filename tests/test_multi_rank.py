@@ -272,6 +272,70 @@ def test_k_slabs_cell_path_within_fast_tolerance(lib):
     for r in ranks:
         fp[r["ids"]], fv[r["ids"]] = r["pos"], r["vel"]
     assert np.abs(fp - ref.pos).max() < 2e-4 and helpers.rel_err(fv, ref.vel) < 2e-4
+    # the halo planes went by direct peer stores (k_halo_push / k_halo_wait_add), as between the processes of a multi-GPU run
+    assert all(r["stats"].halo_peer_exchanges == 2 * steps for r in ranks), [r["stats"].halo_peer_exchanges for r in ranks]
+
+
+@pytest.mark.gpu
+def test_halo_transports_agree_bit_for_bit(lib, monkeypatch):
+    """The same 3-slab run with the halo planes sent through the transport (MPM_NO_P2P=1: copies + add kernels) and by
+    peer stores (flags, no copies): identical bits, and identical to the oracle (strict path)."""
+    op = orc.variant("3d_gpu", (48, 32, 32))
+    op.interaction = 0
+    n, steps = 40000, 5
+    pos, vel, Cm, mass = helpers.random_cloud(op, n, seed=23, vel_sigma=1.0)
+    ref = orc.State(op, pos, vel, Cm, mass); ref.step(steps)
+    res = {}
+    for mode in ("peer", "copy"):
+        if mode == "copy":
+            monkeypatch.setenv("MPM_NO_P2P", "1")
+        ranks = _run_ranks(op, 3, pos, vel, Cm, mass, steps, kernel_path=2)
+        assert all((r["stats"].halo_peer_exchanges > 0) == (mode == "peer") for r in ranks)
+        full = np.zeros_like(ref.pos)
+        for r in ranks:
+            full[r["ids"]] = r["pos"]
+        res[mode] = full
+        helpers.assert_bit_equal(full, ref.pos, f"pos, halos by {mode}")
+    helpers.assert_bit_equal(res["peer"], res["copy"], "peer-store halos vs copied halos")
+
+
+@pytest.mark.gpu
+def test_per_rank_checkpoint_resumes_on_any_world_size(lib, tmp_path):
+    """mpm_save_state under a communicator writes one file per rank (records + global indices); mpm_load_state finds them,
+    restores the original particle order, and the run continues -- here on ONE solver -- bit-identically to the oracle."""
+    import mpm_b200
+    op = orc.variant("3d_gpu", (48, 32, 32))
+    op.interaction = 0
+    n = 30000
+    pos, vel, Cm, mass = helpers.random_cloud(op, n, seed=29, vel_sigma=1.0)
+    ref = orc.State(op, pos, vel, Cm, mass); ref.step(7)
+    path = str(tmp_path / "state.mpm")
+    world = 3
+    hub = mpm_b200.LocalHub(world)
+    errs = []
+
+    def work(r):
+        try:
+            with mpm_b200.Solver(helpers.mpm_params_from_orc(op, kernel_path=2), n) as s:
+                s.comm_init_local(hub, r, world)
+                s.upload(pos, vel, Cm, mass)
+                s.step(4)
+                s.save_state(path)
+        except Exception as e:  # noqa: BLE001
+            errs.append((r, e))
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    [t.start() for t in th]
+    [t.join(300) for t in th]
+    hub.close()
+    assert not errs, errs
+    assert all(os.path.exists(f"{path}.rank{r}of{world}") for r in range(world)) and not os.path.exists(path)
+    with mpm_b200.Solver(helpers.mpm_params_from_orc(op, kernel_path=2), n) as s:
+        s.load_state(path)
+        assert s.num_particles == n and s.stats().steps == 4
+        s.step(3)
+        gp, gv, gc, gm = s.download()
+    helpers.assert_bit_equal(gp, ref.pos, "pos"); helpers.assert_bit_equal(gv, ref.vel, "vel"); helpers.assert_bit_equal(gm, ref.mass, "mass")
 
 
 @pytest.mark.gpu
@@ -314,20 +378,20 @@ def test_slab_dam_break_trajectory_and_balance(lib):
 
 
 # ---------------------------------------------------------------- GPU x2: the NCCL transport, one process per GPU
-def _nccl_worker(rank, world, uid, op_bytes, arrs, steps, q):
+def _nccl_worker(rank, world, uid, op_bytes, arrs, steps, q, path=2, math=0):
     import ctypes
     import mpm_b200
     op = orc.OrcParams.from_buffer_copy(op_bytes)
     pos, vel, Cm, mass = arrs
     try:
-        with mpm_b200.Solver(helpers.mpm_params_from_orc(op, kernel_path=2), pos.shape[0], device=rank) as s:
+        with mpm_b200.Solver(helpers.mpm_params_from_orc(op, kernel_path=path, math_mode=math), pos.shape[0], device=rank) as s:
             s.comm_init(uid, rank, world)
             s.upload(pos, vel, Cm, mass)
             s.step(steps)
             gp, gv, gc, gm = s.download()
-            q.put((rank, gp, gv, gc, s.download_ids(), None))
+            q.put((rank, gp, gv, gc, s.download_ids(), None, s.stats().halo_peer_exchanges))
     except Exception as e:  # noqa: BLE001
-        q.put((rank, None, None, None, None, repr(e)))
+        q.put((rank, None, None, None, None, repr(e), 0))
 
 
 @pytest.mark.gpu
@@ -351,8 +415,39 @@ def test_nccl_two_gpus_bit_identical_to_oracle(lib):
     [p.join(60) for p in procs]
     assert all(r[5] is None for r in res), [r[5] for r in res]
     fp, fv, fc = np.zeros_like(ref.pos), np.zeros_like(ref.vel), np.zeros_like(ref.C)
-    for _, gp, gv, gc, ids, _ in res:
+    for _, gp, gv, gc, ids, _, _ in res:
         fp[ids], fv[ids], fc[ids] = gp, gv, gc
     helpers.assert_bit_equal(fp, ref.pos, "pos (2 GPUs, NCCL)")
     helpers.assert_bit_equal(fv, ref.vel, "vel (2 GPUs, NCCL)")
     helpers.assert_bit_equal(fc, ref.C, "C (2 GPUs, NCCL)")
+
+
+@pytest.mark.gpu
+def test_two_gpus_cell_path_ipc_halos_within_fast_tolerance(lib):
+    """What the scaling benchmark runs: one process per GPU, cell kernels (FAST), halo planes by peer stores over CUDA IPC,
+    migration through NCCL.  Against the strict oracle within the FAST tolerance; exact particle bookkeeping."""
+    import mpm_b200
+    if lib.mpm_device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    op = orc.variant("3d_gpu", (96, 64, 64))
+    op.interaction = 0
+    n, steps = 200000, 6
+    pos, vel, Cm, mass = helpers.random_cloud(op, n, seed=31, vel_sigma=1.5)
+    ref = orc.State(op, pos, vel, Cm, mass)
+    ref.step(steps)
+    uid = mpm_b200.comm_unique_id()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, uid, bytes(op), (pos, vel, Cm, mass), steps, q, 3, 1)) for r in range(2)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=300) for _ in procs]
+    [p.join(60) for p in procs]
+    assert all(r[5] is None for r in res), [r[5] for r in res]
+    assert all(r[6] == 2 * steps for r in res), "the halos did not go by peer stores"
+    ids = np.concatenate([r[4] for r in res])
+    assert np.array_equal(np.sort(ids), np.arange(n, dtype=np.uint32))
+    fp, fv = np.zeros_like(ref.pos), np.zeros_like(ref.vel)
+    for _, gp, gv, gc, i, _, _ in res:
+        fp[i], fv[i] = gp, gv
+    assert np.abs(fp - ref.pos).max() < 2e-4 and helpers.rel_err(fv, ref.vel) < 2e-4
