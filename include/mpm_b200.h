@@ -242,6 +242,15 @@ MPM_API int32_t mpm_run_phase(MpmSolver* s, int32_t phase);
 MPM_API int32_t mpm_get_positions(MpmSolver* s, float* dst4, int64_t cap, void** device_ptr,
                                   uint32_t* tex_width);
 
+/* Zero-copy hand-off (H:340-355, 402-412: the reference's positions never leave the GPU -- G2P writes a storage image the
+ * MultiMesh shader samples).  The (x, y, z, |v|) array lives in an allocation made with cuMemCreate; *fd receives a new POSIX
+ * file descriptor for it (the caller owns and closes it) that a renderer imports once -- Vulkan: VkImportMemoryFdInfoKHR with
+ * VK_EXTERNAL_MEMORY_HANDLE_TYPE_OPAQUE_FD_BIT; CUDA in another process: cuMemImportFromShareableHandle /
+ * cudaImportExternalMemory -- *bytes the allocation's size (the array starts at offset 0, 16 bytes per particle, index i at
+ * texel (i % width, i / width)).  After every step, mpm_get_positions(s, NULL, 0, NULL, NULL) refreshes the array on the
+ * solver's stream and mpm_sync() makes it visible: no byte crosses PCIe.  MPM_ERR_STATE if the driver cannot export. */
+MPM_API int32_t mpm_export_positions(MpmSolver* s, int32_t* fd, uint64_t* bytes, uint32_t* tex_width);
+
 /* Pipelined form of the hand-off for hosts that render while the next step runs (double buffering): enqueues the
  * hand-off array and its copy into dst4 (pinned host memory from mpm_host_alloc) on a separate copy stream and returns
  * at once, so the device-to-host transfer overlaps the following mpm_step.  dst4 is complete after

@@ -175,7 +175,9 @@ extern "C" int32_t mpm_create(const MpmParams* p, int64_t max_particles, int32_t
     CKC(cudaMalloc(&s->part, sizeof(float) * NPLANES * s->pitch));
     CKC(cudaMalloc(&s->orig_id, sizeof(uint32_t) * s->pitch));
     CKC(cudaMalloc(&s->grid, 16 * s->ncells));
-    CKC(cudaMalloc(&s->positions, sizeof(float4) * s->pitch));
+    // the hand-off array: exportable (file descriptor for Vulkan / another process) where the driver allows, else plain
+    if (vmm_alloc(device, sizeof(float4) * s->pitch, &s->positions_mem)) s->positions = reinterpret_cast<float4*>(s->positions_mem.ptr);
+    else CKC(cudaMalloc(&s->positions, sizeof(float4) * s->pitch));
     CKC(cudaMalloc(&s->overflow_flag, 2 * sizeof(int32_t)));  // [0] overflow detector, [1] particles skipped for their position
     s->dp.flags = s->overflow_flag;
     CKC(cudaMemsetAsync(s->grid, 0, 16 * s->ncells, s->stream));
@@ -217,7 +219,8 @@ extern "C" int32_t mpm_destroy(MpmSolver* s)
     bin_destroy(s);
     for (cudaEvent_t ev : s->ev) cudaEventDestroy(ev);
     cudaFree(s->part); cudaFree(s->part_alt); cudaFree(s->rec); cudaFree(s->orig_id); cudaFree(s->orig_id_alt);
-    cudaFree(s->grid); cudaFree(s->positions); cudaFree(s->positions_b); cudaFree(s->overflow_flag); cudaFree(s->stage);
+    if (s->positions_mem.ptr) vmm_free(&s->positions_mem); else cudaFree(s->positions);
+    cudaFree(s->grid); cudaFree(s->positions_b); cudaFree(s->overflow_flag); cudaFree(s->stage);
     if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); }
     for (int k = 0; k < 2; ++k) { if (s->pos_ready[k]) cudaEventDestroy(s->pos_ready[k]); if (s->pos_copied[k]) cudaEventDestroy(s->pos_copied[k]); }
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -830,6 +833,19 @@ extern "C" int32_t mpm_get_positions(MpmSolver* s, float* dst4, int64_t cap, voi
         CK(cudaMemcpyAsync(dst4, s->positions, sizeof(float4) * s->n, cudaMemcpyDeviceToHost, s->stream));
         CK(cudaStreamSynchronize(s->stream));
     }
+    return MPM_OK;
+}
+
+extern "C" int32_t mpm_export_positions(MpmSolver* s, int32_t* fd, uint64_t* bytes, uint32_t* tex_width)
+{
+    if (!s || !fd) return MPM_ERR_INVALID;
+    CK(cudaSetDevice(s->device));
+    if (!s->positions_mem.ptr) return fail(s, MPM_ERR_STATE, "the position array is not in an exportable allocation (driver without cuMemCreate / POSIX-FD handles)");
+    int out = -1;
+    if (!vmm_export_fd(s->positions_mem, &out)) return fail(s, MPM_ERR_CUDA, "cuMemExportToShareableHandle failed");
+    *fd = out;
+    if (bytes) *bytes = s->positions_mem.bytes;
+    if (tex_width) *tex_width = (uint32_t)sqrtf((float)s->n) + 1;  // MLSMPM3DFluidMultithreadGPU.cs:196
     return MPM_OK;
 }
 

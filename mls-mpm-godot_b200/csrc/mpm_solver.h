@@ -9,6 +9,15 @@
 #include "mpm_common.cuh"
 
 namespace mpm {
+// device memory that can be exported to another API / process as a POSIX file descriptor (mpm_vmm.cu)
+struct ExportableAlloc {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    unsigned long long handle = 0;
+};
+bool vmm_alloc(int device, size_t bytes, ExportableAlloc* out);
+void vmm_free(ExportableAlloc* a);
+bool vmm_export_fd(const ExportableAlloc& a, int* fd);
 struct SortState;  // mpm_sort.cu
 struct BinState;   // mpm_bin.cu
 struct CommState;  // mpm_comm.cu
@@ -41,6 +50,7 @@ struct MpmSolver {
     void* grid = nullptr;  // ncells_local * 16 B
     int64_t ncells = 0;    // local cells (nxl * Ry * Rz)
     float4* positions = nullptr;  // (x, y, z, |v|) in original index order
+    mpm::ExportableAlloc positions_mem;  // ... inside an exportable allocation when the driver offers one (mpm_export_positions)
     bool positions_valid = false;
     // pipelined hand-off (mpm_get_positions_async): second device array, copy stream, events
     float4* positions_b = nullptr;

@@ -76,7 +76,7 @@ EXPORTS = [
     "mpm_get_stream", "mpm_host_alloc", "mpm_host_free", "mpm_comm_unique_id", "mpm_comm_init",
     "mpm_local_hub_create", "mpm_local_hub_destroy", "mpm_comm_init_local", "mpm_comm_slab", "mpm_download_ids",
     "mpm_slab_cuts", "mpm_get_positions_async", "mpm_wait_positions", "mpm_comm_rebalance", "mpm_set_colliders",
-    "mpm_save_state", "mpm_load_state",
+    "mpm_save_state", "mpm_load_state", "mpm_export_positions",
 ]
 
 _lib = None
@@ -134,6 +134,7 @@ def load():
         "mpm_set_colliders": (i32, [vp, fp, i32]),
         "mpm_save_state": (i32, [vp, C.c_char_p]),
         "mpm_load_state": (i32, [vp, C.c_char_p]),
+        "mpm_export_positions": (i32, [vp, C.POINTER(i32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     }
     for name, (res, args) in sig.items():
         try:
@@ -291,6 +292,17 @@ class Solver:
 
     def wait_positions(self):
         self._ck(self._L.mpm_wait_positions(self._h))
+
+    def export_positions(self):
+        """(fd, bytes, tex_width): a POSIX file descriptor of the allocation that holds the (x, y, z, |v|) array, for a
+        renderer / another process to import (zero-copy hand-off); the caller closes the fd."""
+        fd, nbytes, w = C.c_int32(-1), C.c_uint64(0), C.c_uint32(0)
+        self._ck(self._L.mpm_export_positions(self._h, C.byref(fd), C.byref(nbytes), C.byref(w)))
+        return fd.value, nbytes.value, w.value
+
+    def refresh_positions(self):
+        """Bring the device-side (x, y, z, |v|) array up to date (no host copy)."""
+        self._ck(self._L.mpm_get_positions(self._h, None, 0, None, None))
 
     def positions_device(self):
         dp, w = C.c_void_p(), C.c_uint32()

@@ -948,3 +948,35 @@ def test_overflow_detector(lib):
             assert e.value.code == mpm_b200.ERR_OVERFLOW and s.stats().overflow == 1
     with pytest.raises(mpm_b200.MpmError):
         make_solver(op, 100, kernel_path=3, math_mode=1, overflow_check=1)
+
+
+# ---------------------------------------------------------------- zero-copy hand-off
+def test_zero_copy_hand_off_to_another_process(lib):
+    """The reference's positions never leave the GPU (G2P writes the texture the MultiMesh shader samples, H:340-355,
+    402-412).  mpm_export_positions gives a file descriptor of the allocation that holds the (x, y, z, |v|) array; a second
+    PROCESS imports it through the CUDA driver API (as a renderer would through VK_KHR_external_memory_fd) and reads, with no
+    copy through the exporting process, exactly the bytes mpm_get_positions returns -- also after further steps, without
+    exporting again."""
+    import hashlib
+    import subprocess
+    op = orc.variant("3d_gpu", 32)
+    lo, hi = (4, 4, 4), (20, 20, 20)
+    tool = os.path.join(os.path.dirname(__file__), "tools", "import_positions.py")
+    for path, math in ((3, 1), (2, 0)):
+        with make_solver(op, 32768, kernel_path=path, math_mode=math) as s:
+            n = s.initialise_sim(lo, hi, 0.5)
+            s.step(3)
+            fd, nbytes, width = s.export_positions()
+            assert fd >= 0 and nbytes >= 16 * n and width == int(np.sqrt(np.float32(n))) + 1
+            try:
+                for more in (0, 2):
+                    if more:
+                        s.step(more)
+                    s.refresh_positions(); s.sync()          # device-side only: nothing is copied to the host here
+                    out = subprocess.run([sys.executable, tool, str(fd), str(nbytes), str(n)], pass_fds=(fd,), capture_output=True,
+                                         text=True, timeout=120)
+                    assert out.returncode == 0, out.stderr[-2000:]
+                    want = hashlib.sha256(s.positions().tobytes()).hexdigest()
+                    assert out.stdout.split()[-1] == want, "the importing process sees other bytes than mpm_get_positions"
+            finally:
+                os.close(fd)
