@@ -38,6 +38,11 @@
 
 namespace mpm {
 
+// A binning with more "far movers" (particles that left their grid block's one-cell apron, see the stable ranking below)
+// than this is ranked with the atomic cursor altogether and booked as unordered: bulk motion of more than a cell per step
+// breaks the premise of the tile regions, and the exact fix-up is sized for outliers.
+constexpr uint32_t FAR_LIMIT = 1u << 17;
+
 #define CKB(call)                                                          \
     do {                                                                   \
         cudaError_t e_ = (call);                                           \
@@ -97,7 +102,13 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(const uint32_t* __restrict
 {
     if (threadIdx.x == 0) {  // stable ranking: the list of cells with far arrivals starts empty; last binning's verdict is booked
         if (far_n[3]) { far_n[1] += 1; far_n[3] = 0; }
-        far_n[0] = 0; far_n[2] = 0;
+        // A binning that had to give up (more than FAR_LIMIT far movers: bulk motion of more than a cell per step) marks the
+        // scene as violent: the next 15 binnings do not even try -- far_n[2] starts above the limit, k_rank_count returns at
+        // once and the placement is atomic -- and the 16th probes again.
+        const bool violent = far_n[2] > FAR_LIMIT;
+        far_n[4] = violent ? far_n[4] + 1 : 0;
+        far_n[0] = 0;
+        far_n[2] = (violent && (far_n[4] & 15u)) ? FAR_LIMIT + 1u : 0u;
     }
     __shared__ uint32_t wsum[32], wact[32];
     __shared__ int wbox[32][6];
@@ -388,10 +399,6 @@ __global__ void __launch_bounds__(256) k_place(const uint32_t* __restrict__ keys
 // cell sort in atomic order) and the binning is counted in MpmStats.unordered_binnings.
 struct RankGeom { int nbx, nby, nbz; };
 
-// A binning with more far movers than this is ranked with the atomic cursor altogether (and booked as unordered): bulk
-// motion of more than a cell per step breaks the premise of the tile regions, and the exact fix-up is sized for outliers.
-constexpr uint32_t FAR_LIMIT = 1u << 17;
-
 template <int CELL_BITS>
 struct RankCfg {
     static constexpr int LOGB = CELL_BITS / 3, B = 1 << LOGB, T = B + 2, RC = T * T * T;
@@ -461,6 +468,7 @@ __global__ void __launch_bounds__(RankCfg<CELL_BITS>::THREADS, 12) k_rank_count(
     using C = RankCfg<CELL_BITS>;
     constexpr int KB = 8;  // keys per thread and batch: their loads are issued together
     __shared__ uint32_t cnt[C::RC];
+    if (far_n[2] > FAR_LIMIT) return;  // (a violent scene, not probing this time: k_scan_blocks)
     const uint32_t na = *nact_prev;
     for (uint32_t t = blockIdx.x; t < na; t += gridDim.x) {
         const uint32_t tile = active_prev[t];
@@ -889,8 +897,8 @@ int bin_create(MpmSolver* s)
     const int64_t T = st->B + 2;
     CKB(cudaMalloc(&st->tcount, sizeof(uint32_t) * st->nblocks * T * T * T));
     CKB(cudaMalloc(&st->fixlist, sizeof(uint32_t) * FIX_CAP));
-    CKB(cudaMalloc(&st->far_n, sizeof(uint32_t) * 4));
-    CKB(cudaMemsetAsync(st->far_n, 0, sizeof(uint32_t) * 4, s->stream));
+    CKB(cudaMalloc(&st->far_n, sizeof(uint32_t) * 8));
+    CKB(cudaMemsetAsync(st->far_n, 0, sizeof(uint32_t) * 8, s->stream));
     CKB(cudaMalloc(&st->fill, sizeof(uint32_t) * st->nslots));
     CKB(cudaMemsetAsync(st->fill, 0, sizeof(uint32_t) * st->nslots, s->stream));
     CKB(cudaMalloc(&st->farcnt, sizeof(uint32_t) * st->nslots));

@@ -57,6 +57,12 @@ struct Transport {
     // the same peer-store halo kernels run as with CUDA IPC between processes.  `mine` may be null (set-up failed here);
     // returns true only if EVERY rank of the chain offered a pointer (all ranks then take the peer-store path).
     virtual bool share_pointers(void* mine, int device, void** left, void** right, int* dev_left, int* dev_right) { return false; }
+    // ... and order the neighbours' streams by events instead of letting kernels spin on each other's flags: ranks that share
+    // ONE GPU cannot rely on their kernels being co-resident (a kernel spinning for a flag can keep the kernel that would
+    // set it from ever being scheduled).  notify: my push of message `seq` (pass 0 / 1) towards side L / R is enqueued on st;
+    // await: make st wait for the push of message `seq` from that side.
+    virtual int notify(int side, int pass, uint32_t seq, cudaStream_t st, std::string& err) { return MPM_OK; }
+    virtual int await(int side, int pass, uint32_t seq, cudaStream_t st, std::string& err) { return MPM_OK; }
 };
 
 // ---------------------------------------------------------------- NCCL
@@ -145,6 +151,14 @@ struct MpmLocalHub {
     std::vector<void*> p2p_ptr;
     std::vector<int> p2p_dev;
     int p2p_arrived = 0;
+    // halo signals of the peer-store path between ranks of one process: [rank][side][pass]
+    struct Signal {
+        std::mutex m;
+        std::condition_variable cv;
+        uint32_t posted = 0, consumed = 0;
+        cudaEvent_t ev = nullptr;
+    };
+    std::vector<Signal> sig;  // world * 4
 };
 
 namespace mpm {
@@ -207,6 +221,36 @@ struct LocalTransport : Transport {
         *dev_left = rank > 0 ? hub->p2p_dev[rank - 1] : dev;
         *dev_right = rank < world - 1 ? hub->p2p_dev[rank + 1] : dev;
         return all;
+    }
+    MpmLocalHub::Signal& signal_of(int from_rank, int side, int pass) { return hub->sig[(size_t)(from_rank * 2 + side) * 2 + pass]; }
+    int notify(int side, int pass, uint32_t seq, cudaStream_t st, std::string& err) override
+    {
+        MpmLocalHub::Signal& sg = signal_of(rank, side, pass);
+        std::unique_lock<std::mutex> lk(sg.m);
+        // the event is recorded anew for every message: the receiver must have taken the previous one
+        if (!sg.cv.wait_for(lk, std::chrono::seconds(hub->timeout_s), [&] { return sg.consumed + 1 >= seq; })) {
+            err = "local transport: the neighbouring rank did not take the previous halo message";
+            return MPM_ERR_COMM;
+        }
+        if (!sg.ev) cudaEventCreateWithFlags(&sg.ev, cudaEventDisableTiming);
+        cudaEventRecord(sg.ev, st);
+        sg.posted = seq;
+        sg.cv.notify_all();
+        return MPM_OK;
+    }
+    int await(int side, int pass, uint32_t seq, cudaStream_t st, std::string& err) override
+    {
+        // the message from my LEFT neighbour is the one it sent to ITS right side (1), and vice versa
+        MpmLocalHub::Signal& sg = signal_of(side == 0 ? rank - 1 : rank + 1, side == 0 ? 1 : 0, pass);
+        std::unique_lock<std::mutex> lk(sg.m);
+        if (!sg.cv.wait_for(lk, std::chrono::seconds(hub->timeout_s), [&] { return sg.posted >= seq; })) {
+            err = "local transport: the neighbouring rank did not arrive (every rank must be stepping concurrently)";
+            return MPM_ERR_COMM;
+        }
+        cudaStreamWaitEvent(st, sg.ev, 0);
+        sg.consumed = seq;
+        sg.cv.notify_all();
+        return MPM_OK;
     }
     int exchange(const void* sendL, size_t nsl, void* recvL, size_t nrl, const void* sendR, size_t nsr, void* recvR,
                  size_t nrr, cudaStream_t st, std::string& err) override
@@ -690,6 +734,13 @@ static int exchange_halo_p2p(MpmSolver* s, int pass, int4* blockL, int4* blockR)
     uint32_t* fR = blockR ? flag_of(c->p2p_peer[1], 0) : nullptr;
     k_halo_push<<<nb, 256, 0, s->stream>>>(blockL, pass == 1 ? c->halo_snap[0] : nullptr, dstL, fL, blockR, pass == 1 ? c->halo_snap[1] : nullptr,
                                            dstR, fR, c->halo_cells, seq, c->p2p_done + pass);
+    if (c->p2p_inproc) {  // ranks of one process: the streams are ordered by events, the flags are already set when the wait kernel runs
+        int rc;
+        if (blockL && (rc = c->tr->notify(0, pass, seq, s->stream, s->err))) return rc;
+        if (blockR && (rc = c->tr->notify(1, pass, seq, s->stream, s->err))) return rc;
+        if (blockL && (rc = c->tr->await(0, pass, seq, s->stream, s->err))) return rc;
+        if (blockR && (rc = c->tr->await(1, pass, seq, s->stream, s->err))) return rc;
+    }
     k_halo_wait_add<<<nb, 256, 0, s->stream>>>(blockL, region_of(c->p2p_own, 0), pass == 0 ? c->halo_snap[0] : nullptr,
                                                blockL ? flag_of(c->p2p_own, 0) : nullptr, blockR, region_of(c->p2p_own, 1),
                                                pass == 0 ? c->halo_snap[1] : nullptr, blockR ? flag_of(c->p2p_own, 1) : nullptr, c->halo_cells,
@@ -1078,6 +1129,7 @@ extern "C" int32_t mpm_local_hub_create(int32_t world, MpmLocalHub** hub)
     h->world = world;
     h->to_right = std::vector<Mailbox>(world);
     h->to_left = std::vector<Mailbox>(world);
+    h->sig = std::vector<MpmLocalHub::Signal>((size_t)world * 4);
     *hub = h;
     return MPM_OK;
 }
@@ -1090,6 +1142,7 @@ extern "C" int32_t mpm_local_hub_destroy(MpmLocalHub* hub)
             if (mb.ready) cudaEventDestroy(mb.ready);
             if (mb.done) cudaEventDestroy(mb.done);
         }
+    for (auto& sg : hub->sig) if (sg.ev) cudaEventDestroy(sg.ev);
     delete hub;
     return MPM_OK;
 }
