@@ -276,7 +276,8 @@ extern "C" int32_t mpm_set_colliders(MpmSolver* s, const float* xyzr, int32_t co
 // multi-GPU (mpm_comm.cu): the GLOBAL set is written to the planes by init/add/upload; the slab partition
 // (histogram -> cuts -> keep own particles) runs lazily before the next step / download.
 namespace mpm {
-int comm_partition(MpmSolver* s);          // no-op unless a partition is pending
+int comm_partition(MpmSolver* s);          // no-op unless a partition is pending (also catches up on a pending migration's counts)
+int comm_partition_for_step(MpmSolver* s); // ... without the catching up (mpm_step)
 bool comm_partitioned(const MpmSolver* s);  // the planes hold this rank's local particles
 void comm_mark_global(MpmSolver* s);       // the planes now hold the global set again
 }
@@ -727,7 +728,7 @@ extern "C" int32_t mpm_step(MpmSolver* s, int32_t iterations)
 {
     if (!s || iterations < 0) return MPM_ERR_INVALID;
     CK(cudaSetDevice(s->device));
-    { int rc = comm_partition(s); if (rc) return rc; }
+    { int rc = comm_partition_for_step(s); if (rc) return rc; }
     if (s->timing) { for (double& v : s->ms_acc) v = 0; s->ms_step_acc = 0; s->timed_steps = 0; }
     size_t cursor = 0;
     std::vector<int> phases;

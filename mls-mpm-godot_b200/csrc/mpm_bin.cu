@@ -361,10 +361,10 @@ template <int CELL_BITS>
 __global__ void __launch_bounds__(256) k_place(const uint32_t* __restrict__ keys, int64_t n, const uint2* __restrict__ cellmeta,
                                                const uint32_t* __restrict__ cnts, const uint32_t* __restrict__ pstart,
                                                const uint16_t* __restrict__ stab, uint32_t* __restrict__ fill, uint32_t* __restrict__ src_of,
-                                               const uint32_t* __restrict__ id_src, uint32_t* __restrict__ id_dst)
+                                               const uint32_t* __restrict__ id_src, uint32_t* __restrict__ id_dst, const uint32_t* __restrict__ n_dev)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= (n_dev ? (int64_t)*n_dev : n)) return;  // (multi-GPU: the count of a migration the host has not read yet)
     const uint32_t key = keys[i];
     const uint32_t id = id_src[i];  // the particle's original index moves to its new slot here (coalesced read, one more
                                     // scattered 4-byte store) rather than as a scattered read in P2G_1
@@ -979,7 +979,7 @@ static int cold_sort(MpmSolver* s)
 int bin_particles(MpmSolver* s)
 {
     BinState* st = s->bin;
-    const int64_t n = s->n;
+    const int64_t n = s->n + s->n_launch_extra;  // (launch size; see MpmSolver::n_launch_extra)
     const int nxt = st->cur ^ 1;
     const unsigned nb = (unsigned)((n + 255) / 256);
     const bool stable = use_stable(s);
@@ -1037,8 +1037,8 @@ int bin_particles(MpmSolver* s)
         }
         s->launches += 4;
     } else if (n > 0) {
-        if (st->cell_bits == 9) k_place<9><<<nb, 256, 0, s->stream>>>(st->keys, n, st->cellmeta, st->cnts, st->pstart, st->stab, st->fill, st->src_of, s->orig_id, s->orig_id_alt);
-        else k_place<6><<<nb, 256, 0, s->stream>>>(st->keys, n, st->cellmeta, st->cnts, st->pstart, st->stab, st->fill, st->src_of, s->orig_id, s->orig_id_alt);
+        if (st->cell_bits == 9) k_place<9><<<nb, 256, 0, s->stream>>>(st->keys, n, st->cellmeta, st->cnts, st->pstart, st->stab, st->fill, st->src_of, s->orig_id, s->orig_id_alt, s->n_dev);
+        else k_place<6><<<nb, 256, 0, s->stream>>>(st->keys, n, st->cellmeta, st->cnts, st->pstart, st->stab, st->fill, st->src_of, s->orig_id, s->orig_id_alt, s->n_dev);
         s->launches += 1;
     }
     st->prev_lay = pl;
@@ -1105,6 +1105,8 @@ int bin_debug_last(MpmSolver* s, uint32_t* keys_before, uint32_t* perm, int64_t 
 // multi-GPU: keys of the particles that arrived by migration (slots [first, first + count)) join the keys and counts the
 // last G2P produced for the ones that stayed
 uint32_t* bin_next_keys(MpmSolver* s) { return (s->bin && s->bin->next_valid) ? s->bin->keys : nullptr; }
+uint32_t* bin_next_counts(MpmSolver* s) { return s->bin->cnt[s->bin->cur ^ 1]; }
+uint32_t bin_nslots(const MpmSolver* s) { return (uint32_t)s->bin->nslots; }
 
 int bin_keys_range(MpmSolver* s, int64_t first, int64_t count)
 {

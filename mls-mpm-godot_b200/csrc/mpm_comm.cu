@@ -32,6 +32,7 @@
 
 #include "mpm_kernels.h"
 #include "mpm_solver.h"
+#include "mpm_tile.cuh"
 
 namespace mpm {
 
@@ -222,7 +223,7 @@ struct LocalTransport : Transport {
         *dev_right = rank < world - 1 ? hub->p2p_dev[rank + 1] : dev;
         return all;
     }
-    MpmLocalHub::Signal& signal_of(int from_rank, int side, int pass) { return hub->sig[(size_t)(from_rank * 2 + side) * 2 + pass]; }
+    MpmLocalHub::Signal& signal_of(int from_rank, int side, int pass) { return hub->sig[(size_t)(from_rank * 2 + side) * 3 + pass]; }  // pass 2 = migration
     int notify(int side, int pass, uint32_t seq, cudaStream_t st, std::string& err) override
     {
         MpmLocalHub::Signal& sg = signal_of(rank, side, pass);
@@ -303,6 +304,13 @@ struct CommState {
     int64_t slab_jump_clamps = 0;  // particles held back because they would have crossed more than one slab in a step
     int64_t n_global = 0;          // particles of the whole scene (the set the last upload / init handed to every rank)
     uint32_t sent_prev[2] = {0, 0}, recv_prev[2] = {0, 0};  // particles that crossed each edge in the previous step
+    // migration by peer stores (cell path, peer-store halos available): the leavers are written straight into the neighbour's
+    // receive region, the counts stay on the device, and the host reads them one phase later (comm_finish_migration)
+    uint32_t mig_seq = 0;         // migration messages sent so far
+    uint32_t* n_dev = nullptr;    // [1] local particle count as the device knows it (written by the unpack kernel)
+    cudaEvent_t mig_done = nullptr;
+    bool mig_pending = false;     // an exchange is enqueued whose counts the host has not read yet
+    int64_t mig_n_before = 0;     // s->n when that exchange was enqueued
 };
 
 #define CKM(call)                                                          \
@@ -328,7 +336,8 @@ void comm_destroy(MpmSolver* s)
     if (!c) return;
     free_slab_buffers(c);
     if (!c->p2p_inproc) for (int k = 0; k < 2; ++k) if (c->p2p_peer[k]) cudaIpcCloseMemHandle(c->p2p_peer[k]);
-    cudaFree(c->p2p_own); cudaFree(c->p2p_done);
+    cudaFree(c->p2p_own); cudaFree(c->p2p_done); cudaFree(c->n_dev);
+    if (c->mig_done) cudaEventDestroy(c->mig_done);
     for (int k = 0; k < 2; ++k) { cudaFree(c->send_rec[k]); cudaFree(c->recv_rec[k]); }
     cudaFree(c->d_cnt); cudaFree(c->holes); cudaFree(c->fillers); cudaFree(c->leave[0]); cudaFree(c->leave[1]);
     if (c->h_cnt) cudaFreeHost(c->h_cnt);
@@ -453,10 +462,25 @@ bool comm_partitioned(const MpmSolver* s) { return s->comm && s->comm->slab_set;
 void comm_mark_global(MpmSolver* s) { s->comm->pending = true; s->comm->slab_set = false; }
 
 // The planes hold the GLOBAL particle set (s->n particles, ids in orig_id): cut the slabs, keep this rank's.
+int comm_finish_migration(MpmSolver* s);
+
+// what mpm_step calls: only the slab partition of a freshly uploaded set (a migration whose counts the host has not read
+// yet stays pending: the step's first kernels take the count from the device)
+int comm_partition_for_step(MpmSolver* s);
+
 int comm_partition(MpmSolver* s)
 {
     CommState* c = s->comm;
+    if (!c) return MPM_OK;
+    if (c->mig_pending) { int rc = comm_finish_migration(s); if (rc) return rc; }  // every caller but mpm_step needs s->n
+    return comm_partition_for_step(s);
+}
+
+int comm_partition_for_step(MpmSolver* s)
+{
+    CommState* c = s->comm;
     if (!c || !c->pending) return MPM_OK;
+    if (c->mig_pending) { int rc = comm_finish_migration(s); if (rc) return rc; }
     const int64_t n_global = s->n;
     c->n_global = n_global;
     const int rx = s->dp.Rx;
@@ -636,6 +660,16 @@ __global__ void __launch_bounds__(256) k_halo_wait_add(int4* __restrict__ blockL
     }
 }
 
+// Layout of a rank's receive allocation: 4 halo regions [side][pass] | 6 flags (4 halo, 2 migration) | 2 migration regions
+// [side]: MIG_HDR header words ([0] = particles in the message) + 17 planes (16 fields + original index) of rec_cap words.
+constexpr int MIG_HDR = 32;
+static size_t p2p_flags_offset(const CommState* c) { return 4 * 16 * (size_t)c->halo_cells; }
+static size_t p2p_mig_offset(const CommState* c) { return (p2p_flags_offset(c) + 6 * P2P_FLAG_STRIDE * sizeof(uint32_t) + 255) / 256 * 256; }
+static size_t p2p_mig_bytes(const CommState* c) { return (sizeof(uint32_t) * ((size_t)MIG_HDR + (size_t)REC_WORDS * c->rec_cap) + 255) / 256 * 256; }
+static size_t p2p_total_bytes(const CommState* c) { return p2p_mig_offset(c) + 2 * p2p_mig_bytes(c); }
+static uint32_t* p2p_mig_region(const CommState* c, uint8_t* base, int side) { return reinterpret_cast<uint32_t*>(base + p2p_mig_offset(c) + side * p2p_mig_bytes(c)); }
+static uint32_t* p2p_mig_flag(const CommState* c, uint8_t* base, int side) { return reinterpret_cast<uint32_t*>(base + p2p_flags_offset(c)) + (4 + side) * P2P_FLAG_STRIDE; }
+
 // one-time set-up: allocate, exchange IPC handles with both neighbours (through the transport), map
 static void p2p_setup(MpmSolver* s)
 {
@@ -643,10 +677,10 @@ static void p2p_setup(MpmSolver* s)
     c->p2p_tried = true;
     if (getenv("MPM_NO_P2P")) return;
     const bool hasL = c->rank > 0, hasR = c->rank < c->world - 1;
-    const size_t region = 16 * (size_t)c->halo_cells, total = 4 * region + 4 * P2P_FLAG_STRIDE * sizeof(uint32_t);
+    const size_t region = 16 * (size_t)c->halo_cells, total = p2p_total_bytes(c);
     if (!c->tr->separate_gpus()) {
         // ranks of one process: plain device pointers instead of IPC handles (peer access enabled when the devices differ)
-        bool ok = cudaMalloc(&c->p2p_own, total) == cudaSuccess && cudaMemset(c->p2p_own, 0, total) == cudaSuccess &&
+        bool ok = cudaMalloc(&c->p2p_own, total) == cudaSuccess && cudaMemset(c->p2p_own, 0, p2p_mig_offset(c)) == cudaSuccess &&
                   cudaMalloc(&c->p2p_done, 8 * sizeof(uint32_t)) == cudaSuccess && cudaMemset(c->p2p_done, 0, 8 * sizeof(uint32_t)) == cudaSuccess;
         void *pl = nullptr, *pr = nullptr;
         int dl = s->device, dr = s->device;
@@ -664,7 +698,7 @@ static void p2p_setup(MpmSolver* s)
         return;
     }
     uint8_t *hs = nullptr, *hr = nullptr;  // device staging: [0..63] handle for/from the left, [64..127] right
-    bool ok = cudaMalloc(&c->p2p_own, total) == cudaSuccess && cudaMemset(c->p2p_own, 0, total) == cudaSuccess &&
+    bool ok = cudaMalloc(&c->p2p_own, total) == cudaSuccess && cudaMemset(c->p2p_own, 0, p2p_mig_offset(c)) == cudaSuccess &&
               cudaMalloc(&c->p2p_done, 8 * sizeof(uint32_t)) == cudaSuccess && cudaMemset(c->p2p_done, 0, 8 * sizeof(uint32_t)) == cudaSuccess &&
               cudaMalloc(&hs, 128) == cudaSuccess && cudaMalloc(&hr, 128) == cudaSuccess;
     cudaIpcMemHandle_t mine, theirs[2];
@@ -753,6 +787,7 @@ int comm_exchange_halo(MpmSolver* s, int pass)
 {
     CommState* c = s->comm;
     if (!c->slab_set) { s->err = "multi-GPU: upload the particle set after mpm_comm_init*"; return MPM_ERR_STATE; }
+    { int rc = comm_finish_migration(s); if (rc) return rc; }  // the binning and P2G_1 of this step are enqueued: now the host catches up
     const bool hasL = c->rank > 0, hasR = c->rank < c->world - 1;
     if (!hasL && !hasR) return MPM_OK;
     int4* grid = reinterpret_cast<int4*>(s->grid);
@@ -814,7 +849,6 @@ __global__ void __launch_bounds__(256) k_mig_scan(MigGeom g, View pv, int64_t n,
 // agreed by both ends without talking: it is a function of the count that crossed this edge in the previous step, which
 // sender and receiver both know.  So a step needs ONE exchange and ONE host sync; only when the count grows by more than
 // the head-room from one step to the next does a second (overflow) exchange follow.
-constexpr int MIG_HDR = 32;
 
 static inline uint32_t mig_capacity(uint32_t prev)  // the same on both ends of an edge: depends on nothing rank-local
 {
@@ -903,6 +937,185 @@ __global__ void __launch_bounds__(256) k_mig_unpack(View pv, uint32_t* __restric
         for (int k = 0; k < NPLANES; ++k) pv.at(k, base + cap + j) = __uint_as_float(o[k]);
         ids[base + cap + j] = o[NPLANES];
     }
+}
+
+// ---------------------------------------------------------------- migration by peer stores (cell path)
+// The leavers go straight into the neighbour's receive region -- 17 planes of rec_cap words, so a warp's stores are full
+// lines over NVLink and no message size has to be agreed on (the NCCL path sizes its messages from the previous step's
+// count and needs a second round when a burst exceeds the head-room) -- and the last block publishes count + flag.
+__global__ void __launch_bounds__(256) k_mig_push(RecView pv, const uint32_t* __restrict__ ids, const uint32_t* __restrict__ n_dev, uint32_t rec_cap,
+                                                  const uint32_t* __restrict__ leaveL, const uint32_t* __restrict__ leaveR, uint32_t* dstL, uint32_t* dstR,
+                                                  uint32_t* flagL, uint32_t* flagR, uint32_t* __restrict__ holes, uint32_t* __restrict__ fillers, MigGeom g,
+                                                  uint32_t* __restrict__ cnt, uint32_t seq, uint32_t* done)
+{
+    const int64_t n = *n_dev;
+    const uint32_t nL = min(cnt[0], rec_cap), nR = min(cnt[1], rec_cap);
+    const int64_t n_stay = n - cnt[0] - cnt[1];
+    {   // stayers in the tail [n_stay, n) are the fillers of the holes the leavers below n_stay leave
+        const uint32_t nt = cnt[0] + cnt[1];
+        for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
+            const int64_t i = n_stay + t;
+            if (mig_side(g, pv.at(PX, i)) < 0) fillers[atomicAdd(cnt + 5, 1u)] = (uint32_t)i;
+        }
+    }
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nL + nR; j += gridDim.x * blockDim.x) {
+        const int side = j >= nL;
+        const uint32_t slot = side ? j - nL : j;
+        const uint32_t i = (side ? leaveR : leaveL)[slot];
+        if ((int64_t)i < n_stay) holes[atomicAdd(cnt + 4, 1u)] = i;
+        uint32_t* out = side ? dstR : dstL;
+        if (!out) continue;  // (no neighbour on that side: nothing can leave through a wall; the slot is a hole all the same)
+#pragma unroll
+        for (int k = 0; k < NPLANES; ++k) out[MIG_HDR + (size_t)k * rec_cap + slot] = __float_as_uint(pv.at(k, i));
+        out[MIG_HDR + (size_t)NPLANES * rec_cap + slot] = ids[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t prev = atomicAdd(done, 1u);
+        if (prev == gridDim.x - 1) {  // every block's stores are fenced: publish count, then flag
+            *done = 0;
+            if (dstL) dstL[0] = cnt[0];
+            if (dstR) dstR[0] = cnt[1];
+            __threadfence_system();
+            if (flagL) st_release_sys(flagL, seq);
+            if (flagR) st_release_sys(flagR, seq);
+        }
+    }
+}
+
+// arrivals appended behind the stayers (left arrivals first), their bin keys and counts for the next binning, and the new
+// particle count -- all from device-side numbers; the host reads cnt[] later
+__global__ void __launch_bounds__(256) k_mig_pull(RecView pv, uint32_t* __restrict__ ids, uint32_t* n_dev, uint32_t rec_cap, const uint32_t* msgL,
+                                                  const uint32_t* msgR, const uint32_t* flagL, const uint32_t* flagR, uint32_t seq, uint32_t* cnt,
+                                                  KeyGeom kg, uint32_t nslots, uint32_t* __restrict__ keys, uint32_t* __restrict__ cnt_next, uint32_t* done)
+{
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        for (int side = 0; side < 2; ++side) {
+            const uint32_t* f = side ? flagR : flagL;
+            if (!f) continue;
+            while ((int32_t)(ld_acquire_sys(f) - seq) < 0) {
+                if (clock64() - t0 > 20000000000ll) { atomicExch(cnt + 9, 1u); break; }  // ~10 s
+                __nanosleep(200);
+            }
+        }
+    }
+    __syncthreads();
+    const int64_t n = *n_dev;
+    const uint32_t mL = msgL ? min(__ldcv(msgL), rec_cap) : 0u, mR = msgR ? min(__ldcv(msgR), rec_cap) : 0u;
+    const int64_t n_stay = n - cnt[0] - cnt[1];
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < mL + mR; j += gridDim.x * blockDim.x) {
+        const int side = j >= mL;
+        const uint32_t* msg = side ? msgR : msgL;
+        const uint32_t q = side ? j - mL : j;
+        const int64_t dst = n_stay + j;
+#pragma unroll
+        for (int k = 0; k < NPLANES; ++k) pv.at(k, dst) = __uint_as_float(__ldcv(msg + MIG_HDR + (size_t)k * rec_cap + q));
+        ids[dst] = __ldcv(msg + MIG_HDR + (size_t)NPLANES * rec_cap + q);
+        if (keys) {  // (as bin_keys_range does for the NCCL path)
+            uint32_t key = cell_key(kg, __float2int_rz(pv.at(PX, dst)), __float2int_rz(pv.at(PY, dst)), __float2int_rz(pv.at(PZ, dst)));
+            key = key < nslots ? key : nslots - 1;
+            keys[dst] = key;
+            atomicAdd(&cnt_next[key], 1u);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t prev = atomicAdd(done, 1u);
+        if (prev == gridDim.x - 1) {  // every block has read the old count: publish the new one
+            *done = 0;
+            cnt[2] = msgL ? __ldcv(msgL) : 0u; cnt[3] = msgR ? __ldcv(msgR) : 0u;  // (unclipped: the host checks them against rec_cap)
+            *n_dev = (uint32_t)(n_stay + mL + mR);
+        }
+    }
+}
+
+KeyGeom bin_key_geom(const MpmSolver* s);
+uint32_t* bin_next_counts(MpmSolver* s);
+uint32_t bin_nslots(const MpmSolver* s);
+
+static bool mig_by_peer_stores(const MpmSolver* s)
+{
+    static const bool off = getenv("MPM_NCCL_MIGRATION") != nullptr;
+    const CommState* c = s->comm;
+    return !off && c->p2p_ready && s->path == MPM_PATH_CELL && s->in_rec && bin_next_keys(const_cast<MpmSolver*>(s)) != nullptr;
+}
+
+// enqueue one migration by peer stores; the host learns the counts in comm_finish_migration
+static int migrate_p2p(MpmSolver* s)
+{
+    CommState* c = s->comm;
+    const bool hasL = c->rank > 0, hasR = c->rank < c->world - 1;
+    MigGeom g{c->x0, c->x1, hasL ? c->cuts[c->rank - 1] : c->x0, hasR ? c->cuts[c->rank + 2] : c->x1};
+    if (!c->n_dev) {
+        CKM(cudaMalloc(&c->n_dev, sizeof(uint32_t)));
+        CKM(cudaEventCreateWithFlags(&c->mig_done, cudaEventDisableTiming));
+    }
+    if (!c->mig_pending) {  // (the device count is current unless the host has changed the set since: refresh it)
+        const uint32_t n32 = (uint32_t)s->n;
+        CKM(cudaMemcpyAsync(c->n_dev, &n32, sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+    }
+    const uint32_t seq = ++c->mig_seq;
+    uint32_t* dstL = hasL ? p2p_mig_region(c, c->p2p_peer[0], 1) : nullptr;  // my left neighbour receives on its RIGHT side
+    uint32_t* dstR = hasR ? p2p_mig_region(c, c->p2p_peer[1], 0) : nullptr;
+    uint32_t* fL = hasL ? p2p_mig_flag(c, c->p2p_peer[0], 1) : nullptr;
+    uint32_t* fR = hasR ? p2p_mig_flag(c, c->p2p_peer[1], 0) : nullptr;
+    k_mig_push<<<296, 256, 0, s->stream>>>(s->rview(), s->orig_id, c->n_dev, (uint32_t)c->rec_cap, c->leave[0], c->leave[1], dstL, dstR, fL, fR, c->holes,
+                                           c->fillers, g, c->d_cnt, seq, c->p2p_done + 2);
+    k_mig_fill<RecView><<<296, 256, 0, s->stream>>>(s->rview(), s->orig_id, bin_next_keys(s), c->holes, c->fillers, c->d_cnt);
+    if (c->p2p_inproc) {  // ranks of one process: order the streams by events (see exchange_halo_p2p)
+        int rc;
+        if (hasL && (rc = c->tr->notify(0, 2, seq, s->stream, s->err))) return rc;
+        if (hasR && (rc = c->tr->notify(1, 2, seq, s->stream, s->err))) return rc;
+        if (hasL && (rc = c->tr->await(0, 2, seq, s->stream, s->err))) return rc;
+        if (hasR && (rc = c->tr->await(1, 2, seq, s->stream, s->err))) return rc;
+    }
+    k_mig_pull<<<296, 256, 0, s->stream>>>(s->rview(), s->orig_id, c->n_dev, (uint32_t)c->rec_cap, hasL ? p2p_mig_region(c, c->p2p_own, 0) : nullptr,
+                                           hasR ? p2p_mig_region(c, c->p2p_own, 1) : nullptr, hasL ? p2p_mig_flag(c, c->p2p_own, 0) : nullptr,
+                                           hasR ? p2p_mig_flag(c, c->p2p_own, 1) : nullptr, seq, c->d_cnt, bin_key_geom(s), bin_nslots(s), bin_next_keys(s),
+                                           bin_next_counts(s), c->p2p_done + 3);
+    s->launches += 3;
+    CKM(cudaMemcpyAsync(c->h_cnt, c->d_cnt, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    CKM(cudaEventRecord(c->mig_done, s->stream));
+    c->classified = false;
+    c->mig_pending = true;
+    c->mig_n_before = s->n;
+    // until the host has read the counts, launches are sized for the most this rank can hold after the exchange
+    s->n_launch_extra = std::min<int64_t>(2 * c->rec_cap, s->cap - s->n);
+    s->n_dev = c->n_dev;
+    s->sorted_valid = false;
+    s->positions_valid = false;
+    return MPM_OK;
+}
+
+// the host side of a migration enqueued by migrate_p2p: counts, checks, bookkeeping.  Called when the next step has its
+// binning and P2G_1 enqueued (the GPU is busy, the copy of the counts arrived long ago), or by any call that needs s->n.
+int comm_finish_migration(MpmSolver* s)
+{
+    CommState* c = s->comm;
+    if (!c || !c->mig_pending) return MPM_OK;
+    c->mig_pending = false;
+    s->n_launch_extra = 0;
+    s->n_dev = nullptr;
+    CKM(cudaEventSynchronize(c->mig_done));
+    const bool hasL = c->rank > 0, hasR = c->rank < c->world - 1;
+    const uint32_t nL = c->h_cnt[0], nR = c->h_cnt[1], mL = hasL ? c->h_cnt[2] : 0, mR = hasR ? c->h_cnt[3] : 0;
+    c->slab_jump_clamps += c->h_cnt[8];
+    if (c->h_cnt[9]) { s->err = "multi-GPU: a neighbour's halo planes / migrants did not arrive within 10 s (peer-store path)"; return MPM_ERR_COMM; }
+    if ((int64_t)std::max(std::max(nL, nR), std::max(mL, mR)) > c->rec_cap) {
+        s->err = "multi-GPU: more particles crossed a slab boundary in one step than the migration buffer holds (raise max_particles)";
+        return MPM_ERR_COMM;
+    }
+    const int64_t n_stay = c->mig_n_before - nL - nR;
+    if (n_stay + mL + mR > s->cap) { s->err = "multi-GPU: arriving particles exceed max_particles of this rank"; return MPM_ERR_COMM; }
+    s->n = n_stay + mL + mR;
+    c->sent_prev[0] = nL; c->sent_prev[1] = nR; c->recv_prev[0] = mL; c->recv_prev[1] = mR;
+    c->migrated_out += nL + nR;
+    c->migrated_in += mL + mR;
+    static const bool trace = getenv("MPM_COMM_TRACE") != nullptr;
+    if (trace) fprintf(stderr, "[mig r%d p2p] n=%lld nL=%u nR=%u mL=%u mR=%u\n", c->rank, (long long)s->n, nL, nR, mL, mR);
+    return MPM_OK;
 }
 
 template <class View>
@@ -999,6 +1212,8 @@ int comm_migrate(MpmSolver* s)
 {
     CommState* c = s->comm;
     if (c->world < 2) return MPM_OK;
+    { int rc = comm_finish_migration(s); if (rc) return rc; }  // (normally done already, after the step's P2G_1 was enqueued)
+    if (mig_by_peer_stores(s)) return migrate_p2p(s);
     // after a cell-path G2P the particle state lives in the 64-byte records: migrate those
     return s->in_rec ? migrate_impl<RecView>(s, s->rview()) : migrate_impl<ParticleView>(s, s->view());
 }
@@ -1020,6 +1235,7 @@ __global__ void __launch_bounds__(256) k_hist_round(const unsigned long long* __
 static int rebalance(MpmSolver* s, int max_shift)
 {
     CommState* c = s->comm;
+    { int rc = comm_finish_migration(s); if (rc) return rc; }
     const int rx = s->dp.Rx, world = c->world;
     const bool hasL = c->rank > 0, hasR = c->rank < world - 1;
     max_shift = std::max(1, std::min(max_shift, MIN_SLAB_WIDTH - 1));  // a particle never has to travel further than the next rank
@@ -1129,7 +1345,7 @@ extern "C" int32_t mpm_local_hub_create(int32_t world, MpmLocalHub** hub)
     h->world = world;
     h->to_right = std::vector<Mailbox>(world);
     h->to_left = std::vector<Mailbox>(world);
-    h->sig = std::vector<MpmLocalHub::Signal>((size_t)world * 4);
+    h->sig = std::vector<MpmLocalHub::Signal>((size_t)world * 6);
     *hub = h;
     return MPM_OK;
 }

@@ -1015,7 +1015,7 @@ int cell_p2g1(MpmSolver* s)
 {
     int rc = check_cell_supported(s);
     if (rc) return rc;
-    if (s->n == 0) return MPM_OK;
+    if (s->n + s->n_launch_extra == 0) return MPM_OK;
     LAUNCH_CELL(k_p2g1_cell, p2g1_smem<8>(), p2g1_smem<4>(), reinterpret_cast<int*>(s->grid), s->rec, s->bin->src_of);
     s->g2p_inputs = true;
     return MPM_OK;
@@ -1025,7 +1025,7 @@ int cell_p2g2(MpmSolver* s)
 {
     int rc = check_cell_supported(s);
     if (rc) return rc;
-    if (s->n == 0) return MPM_OK;
+    if (s->n + s->n_launch_extra == 0) return MPM_OK;
     if ((rc = grid_tensor_map(s))) return rc;
     LAUNCH_CELL(k_p2g2_cell, P2G2Smem<8>::TOTAL, P2G2Smem<4>::TOTAL, reinterpret_cast<int*>(s->grid), s->rec, s->bin->src_of, s->bin->grid_map);
     return MPM_OK;
@@ -1045,7 +1045,7 @@ int cell_g2p(MpmSolver* s)
 {
     int rc = check_cell_supported(s);
     if (rc) return rc;
-    if (s->n == 0) return MPM_OK;
+    if (s->n + s->n_launch_extra == 0) return MPM_OK;
     BinState* bs = s->bin;
     if ((rc = bin_g2p_inputs(s))) return rc;
     // multi-GPU: particles that leave the slab are not counted here; the migration moves the keys of the particles it

@@ -34,6 +34,11 @@ struct MpmSolver {
     int64_t cap = 0;    // max particles
     int64_t pitch = 0;  // plane stride (floats)
     int64_t n = 0;      // particles currently held (local)
+    // multi-GPU, migration by peer stores: between the moment a migration is enqueued and the moment the host reads its counts,
+    // n is the count BEFORE the exchange; kernels launched in between are sized for n + n_launch_extra and take the true count
+    // from *n_dev (both are 0 / null otherwise)
+    int64_t n_launch_extra = 0;
+    const uint32_t* n_dev = nullptr;
     float* part = nullptr;      // NPLANES * pitch floats
     float* part_alt = nullptr;  // reorder target (tiled path)
     // Cell path: the particle state lives in 64-byte records (the 16 fields of a slot, contiguous).  G2P writes them in
