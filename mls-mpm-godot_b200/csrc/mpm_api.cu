@@ -278,6 +278,7 @@ extern "C" int32_t mpm_set_colliders(MpmSolver* s, const float* xyzr, int32_t co
 namespace mpm {
 int comm_partition(MpmSolver* s);          // no-op unless a partition is pending (also catches up on a pending migration's counts)
 int comm_partition_for_step(MpmSolver* s); // ... without the catching up (mpm_step)
+int comm_halo_planes(const MpmSolver* s, int side);  // stored planes at the low (0) / high (1) end that neighbours add to: 0 or 2
 bool comm_partitioned(const MpmSolver* s);  // the planes hold this rank's local particles
 void comm_mark_global(MpmSolver* s);       // the planes now hold the global set again
 }
@@ -663,7 +664,7 @@ struct PhaseTimer {
 static bool box_sweeps(const MpmSolver* s)
 {
     static const bool off = getenv("MPM_DENSE_SWEEPS") != nullptr;
-    return !off && s->path == MPM_PATH_CELL && !s->comm && s->sorted_valid && s->bin != nullptr;
+    return !off && s->path == MPM_PATH_CELL && s->sorted_valid && s->bin != nullptr;
 }
 
 static int run_phase(MpmSolver* s, int phase, size_t& cursor)
@@ -677,9 +678,9 @@ static int run_phase(MpmSolver* s, int phase, size_t& cursor)
             break;
         case PH_CLEAR:
             // Cell path: the binning of this step has run, so the blocks that can receive anything are known: clear and
-            // update only their bounding box (29 % of the C4 grid at the start of the dam-break).  Multi-GPU slabs keep the
-            // dense sweeps: the neighbours' halo contributions land outside a rank's own box.
-            if (box_sweeps(s)) { launch_clear_box(P, s->grid, s->bin->box + 6, s->stream); s->launches += 1; }
+            // update only their bounding box (29 % of the C4 grid at the start of the dam-break).  Multi-GPU slabs add the two
+            // overlap planes at either end, whole: that is where the neighbours' halo contributions land.
+            if (box_sweeps(s)) { launch_clear_box(P, s->grid, s->bin->box + 6, comm_halo_planes(s, 0), comm_halo_planes(s, 1), s->stream); s->launches += 1; }
             else CK(cudaMemsetAsync(s->grid, 0, 16 * s->ncells, s->stream));
             if (s->bin) s->bin->box_cleared = true;
             s->grid_raw = false;
@@ -695,7 +696,7 @@ static int run_phase(MpmSolver* s, int phase, size_t& cursor)
             else { launch_p2g2_ref(P, s->view(), s->n, s->grid, s->stream); s->launches += (s->n > 0); }
             break;
         case PH_UPDATE:
-            if (box_sweeps(s)) launch_update_box(P, s->grid, s->bin->box, s->stream);
+            if (box_sweeps(s)) launch_update_box(P, s->grid, s->bin->box, comm_halo_planes(s, 0), comm_halo_planes(s, 1), s->stream);
             else launch_update_grid(P, s->grid, s->ncells, s->stream);
             s->launches += 1;
             s->grid_raw = false;

@@ -377,6 +377,12 @@ static int comm_attach(MpmSolver* s, Transport* tr, int rank, int world)
     return MPM_OK;
 }
 
+int comm_halo_planes(const MpmSolver* s, int side)
+{
+    const CommState* c = s->comm;
+    if (!c || c->world < 2) return 0;
+    return (side == 0 ? c->rank > 0 : c->rank < c->world - 1) ? 2 : 0;
+}
 int64_t comm_global_count(const MpmSolver* s) { return s->comm ? s->comm->n_global : s->n; }
 int comm_rank_world(const MpmSolver* s, int* rank, int* world)
 {

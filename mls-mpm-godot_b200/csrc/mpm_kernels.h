@@ -9,8 +9,9 @@ void launch_p2g1_ref(const DevParams& P, ParticleView pv, int64_t n, void* grid,
 void launch_p2g2_ref(const DevParams& P, ParticleView pv, int64_t n, void* grid, cudaStream_t st);
 void launch_update_grid(const DevParams& P, void* grid, int64_t ncells, cudaStream_t st);
 // clear / update restricted to a device-resident box of cells {x0, x1, y0, y1, z0, z1} (3D fixed-point grid)
-void launch_clear_box(const DevParams& P, void* grid, const int* box, cudaStream_t st);
-void launch_update_box(const DevParams& P, void* grid, const int* box, cudaStream_t st);
+// (halo_lo / halo_hi: stored planes at the low / high end of a multi-GPU slab that are swept whole, see k_clear_box)
+void launch_clear_box(const DevParams& P, void* grid, const int* box, int halo_lo, int halo_hi, cudaStream_t st);
+void launch_update_box(const DevParams& P, void* grid, const int* box, int halo_lo, int halo_hi, cudaStream_t st);
 void launch_g2p_ref(const DevParams& P, ParticleView pv, int64_t n, const void* grid, const uint32_t* orig_id,
                     float4* positions, cudaStream_t st);
 

@@ -163,24 +163,30 @@ __global__ void __launch_bounds__(256) k_update_grid(DevParams P, void* grid, in
 // strips outside return at once.
 constexpr int BOX_ROWS = 8;  // (x, y) rows per CTA: one row per CTA made the launch itself (65536 tiny CTAs on C4) cost 35 us
 
-__global__ void __launch_bounds__(256) k_clear_box(DevParams P, int4* __restrict__ grid, const int* __restrict__ box)
+// (multi-GPU slabs: the first halo_lo and the last halo_hi stored planes are the overlap planes the neighbours add their
+// contributions to, anywhere in y and z: they are swept whole, the planes between them inside the rank's own box)
+__global__ void __launch_bounds__(256) k_clear_box(DevParams P, int4* __restrict__ grid, const int* __restrict__ box, int halo_lo, int halo_hi)
 {
     const int x = P.gx0 + blockIdx.y;
-    if (x < box[0] || x >= box[1]) return;
-    const int y0 = max((int)blockIdx.x * BOX_ROWS, box[2]), y1 = min(min((int)blockIdx.x * BOX_ROWS + BOX_ROWS, box[3]), P.Ry);
-    const int z0 = box[4], z1 = box[5];
+    const bool whole = (int)blockIdx.y < halo_lo || (int)blockIdx.y >= P.nxl - halo_hi;
+    if (!whole && (x < box[0] || x >= box[1])) return;
+    const int by0 = whole ? 0 : box[2], by1 = whole ? P.Ry : box[3];
+    const int y0 = max((int)blockIdx.x * BOX_ROWS, by0), y1 = min(min((int)blockIdx.x * BOX_ROWS + BOX_ROWS, by1), P.Ry);
+    const int z0 = whole ? 0 : box[4], z1 = whole ? P.Rz : box[5];
     for (int y = y0; y < y1; ++y) {
         int4* row = grid + ((int64_t)blockIdx.y * P.Ry + y) * P.Rz;
         for (int z = z0 + threadIdx.x; z < z1; z += blockDim.x) row[z] = make_int4(0, 0, 0, 0);
     }
 }
 
-__global__ void __launch_bounds__(256) k_update_box(DevParams P, int4* __restrict__ grid, const int* __restrict__ box)
+__global__ void __launch_bounds__(256) k_update_box(DevParams P, int4* __restrict__ grid, const int* __restrict__ box, int halo_lo, int halo_hi)
 {
     const int x = P.gx0 + blockIdx.y;
-    if (x < box[0] || x >= box[1]) return;
-    const int y0 = max((int)blockIdx.x * BOX_ROWS, box[2]), y1 = min(min((int)blockIdx.x * BOX_ROWS + BOX_ROWS, box[3]), P.Ry);
-    const int z0 = box[4], z1 = box[5];
+    const bool whole = (int)blockIdx.y < halo_lo || (int)blockIdx.y >= P.nxl - halo_hi;
+    if (!whole && (x < box[0] || x >= box[1])) return;
+    const int by0 = whole ? 0 : box[2], by1 = whole ? P.Ry : box[3];
+    const int y0 = max((int)blockIdx.x * BOX_ROWS, by0), y1 = min(min((int)blockIdx.x * BOX_ROWS + BOX_ROWS, by1), P.Ry);
+    const int z0 = whole ? 0 : box[4], z1 = whole ? P.Rz : box[5];
     const int hi = P.bc_hi_off;
     const bool ox = (x < 2 || x > P.Rx - hi);
     for (int y = y0; y < y1; ++y) {
@@ -269,13 +275,13 @@ void launch_update_grid(const DevParams& P, void* grid, int64_t ncells, cudaStre
 {
     DISPATCH_DIM_FIXED(k_update_grid, <<<blocks_for(ncells, 256), 256, 0, st>>>(P, grid, ncells));
 }
-void launch_clear_box(const DevParams& P, void* grid, const int* box, cudaStream_t st)
+void launch_clear_box(const DevParams& P, void* grid, const int* box, int halo_lo, int halo_hi, cudaStream_t st)
 {
-    k_clear_box<<<dim3((unsigned)((P.Ry + BOX_ROWS - 1) / BOX_ROWS), (unsigned)P.nxl), 256, 0, st>>>(P, reinterpret_cast<int4*>(grid), box);
+    k_clear_box<<<dim3((unsigned)((P.Ry + BOX_ROWS - 1) / BOX_ROWS), (unsigned)P.nxl), 256, 0, st>>>(P, reinterpret_cast<int4*>(grid), box, halo_lo, halo_hi);
 }
-void launch_update_box(const DevParams& P, void* grid, const int* box, cudaStream_t st)
+void launch_update_box(const DevParams& P, void* grid, const int* box, int halo_lo, int halo_hi, cudaStream_t st)
 {
-    k_update_box<<<dim3((unsigned)((P.Ry + BOX_ROWS - 1) / BOX_ROWS), (unsigned)P.nxl), 256, 0, st>>>(P, reinterpret_cast<int4*>(grid), box);
+    k_update_box<<<dim3((unsigned)((P.Ry + BOX_ROWS - 1) / BOX_ROWS), (unsigned)P.nxl), 256, 0, st>>>(P, reinterpret_cast<int4*>(grid), box, halo_lo, halo_hi);
 }
 void launch_g2p_ref(const DevParams& P, ParticleView pv, int64_t n, const void* grid, const uint32_t* orig_id,
                     float4* positions, cudaStream_t st)
