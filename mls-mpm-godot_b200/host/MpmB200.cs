@@ -60,6 +60,8 @@ namespace MpmB200
         const string Lib = "mpm_b200";
         const CallingConvention CC = CallingConvention.Cdecl;
         public const int VARIANT_3D_GPU = 4, MATH_STRICT = 0, MATH_FAST = 1;
+        public const int PATH_AUTO = 0, PATH_REFERENCE = 1, PATH_TILED = 2, PATH_CELL = 3;
+        public const int ERR_DOMAIN = 6;
 
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_abi_version();
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_device_count();
@@ -82,6 +84,7 @@ namespace MpmB200
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_sync(IntPtr s);
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_run_phase(IntPtr s, int phase);
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_get_positions(IntPtr s, IntPtr dst4, long cap, out IntPtr device_ptr, out uint tex_width);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_export_positions(IntPtr s, out int fd, out ulong bytes, out uint tex_width);
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_get_positions_async(IntPtr s, IntPtr dst4, long cap);
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_wait_positions(IntPtr s);
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_num_particles(IntPtr s, out long n);
@@ -133,10 +136,24 @@ namespace MpmB200
         [Export] float eos_stiffness { get => prm.eos_stiffness; set { prm.eos_stiffness = value; } }      // H:82
         [Export] float eos_power { get => prm.eos_power; set { prm.eos_power = value; } }                  // H:84
         [Export] PhysicsBody3D sphere_body;                                                                // H:90
+        // B200 solver controls (no reference counterpart).  The node defaults to the fast path -- MATH_FAST + PATH_AUTO
+        // resolves to the cell kernels (11.5 G particle-steps/s on the 32.8 M-particle benchmark scene, results within the
+        // FAST tolerance of the reference algorithm and reproducible run to run); MATH_STRICT gives the bit-exact tiled
+        // kernels (5.3 G).  Both are fixed when the solver is created (_Ready).
+        [Export(PropertyHint.Enum, "Strict (bit-exact),Fast")] int math_mode { get => prm.math_mode; set { prm.math_mode = value; } }
+        [Export(PropertyHint.Enum, "Auto,Reference-shaped,Tiled,Cell")] int kernel_path { get => prm.kernel_path; set { prm.kernel_path = value; } }
+        /// File descriptor of the device allocation that holds the (x, y, z, |v|) array (-1 if the driver cannot export):
+        /// a GDExtension renderer imports it once through VK_KHR_external_memory_fd and samples it with no host round trip.
+        public int particle_pos_fd = -1;
+        public ulong particle_pos_bytes;
+        /// false: skip the host copy in _Process (a renderer reads the exported allocation instead)
+        [Export] bool copy_positions_to_host = true;
 
         public MLSMPM3DFluidB200()
         {
             fixed (MpmParams* p = &prm) Native.mpm_default_params(Native.VARIANT_3D_GPU, p);
+            prm.math_mode = Native.MATH_FAST;      // (mpm_default_params gives MATH_STRICT, the conservative library default)
+            prm.kernel_path = Native.PATH_AUTO;
         }
 
         public override void _Ready()                                            // H:158-207
@@ -146,6 +163,7 @@ namespace MpmB200
             if (sphere_body != null) SetSphere(sphere_body.GlobalPosition); else GD.PrintErr("sphere_body not set");
             fixed (MpmParams* p = &prm) Native.Check(Native.mpm_create(p, max_particle_count, 0, out solver), IntPtr.Zero);
             InitialiseSim();
+            if (Native.mpm_export_positions(solver, out particle_pos_fd, out particle_pos_bytes, out _) != 0) particle_pos_fd = -1;
             particle_pos_tex_width = (uint)Mathf.Sqrt(num_particles) + 1;
             Native.Check(Native.mpm_host_alloc(16L * particle_pos_tex_width * particle_pos_tex_width, out host_positions), solver);
             particle_pos_img = Image.CreateEmpty((int)particle_pos_tex_width, (int)particle_pos_tex_width, false, Image.Format.Rgbaf);
@@ -192,8 +210,14 @@ namespace MpmB200
             if (sphere_body != null) SetSphere(sphere_body.GlobalPosition);
             Native.Check(Native.mpm_step(solver, sim_iterations), solver);        // sim_iterations x (clear, P2G_1, P2G_2, update, G2P)
             // particle_pos_tex hand-off (g2p.glsl:149-150): (x, y, z, |v|) at texel (i % W, i / W).
-            // With CUDA-Vulkan external-memory interop the device pointer (out device_ptr) is imported instead and
-            // this host round trip disappears; the copy below is the portable path.
+            // Zero-copy: a renderer that imported particle_pos_fd only needs the device array refreshed (dst = null).
+            if (!copy_positions_to_host)
+            {
+                Native.Check(Native.mpm_get_positions(solver, IntPtr.Zero, 0, out _, out _), solver);
+                Native.Check(Native.mpm_sync(solver), solver);
+                return;
+            }
+            // Portable path: through pinned host memory into an ImageTexture.
             Native.Check(Native.mpm_get_positions(solver, host_positions, num_particles, out _, out _), solver);
             var bytes = new byte[16 * particle_pos_tex_width * particle_pos_tex_width];
             Marshal.Copy(host_positions, bytes, 0, (int)(16 * num_particles));
