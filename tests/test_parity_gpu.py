@@ -93,7 +93,7 @@ def test_golden_fixed(lib, name, path):
 # FAST re-associates the arithmetic (FMA, hoisting, sum factorisation, reciprocal multiplies): every particle /
 # grid quantity differs from the strict result by rounding only.  Tolerances (relative to the largest magnitude
 # of the compared array, per step):  grid mass/momentum 2e-6, particle vel / C 2e-5 (C is a difference of O(1)
-# terms), positions 1e-6 of the domain.  Measured on B200: see profiles/r1/fast_math_errors.txt.
+# terms), positions 1e-6 of the domain.  Measured on B200: profiles/r2/fast_math_errors.txt (the lines these tests print).
 FAST_TOL = {"grid": 2e-6, "vel": 2e-5, "C": 2e-5, "pos": 1e-6}
 
 
@@ -117,10 +117,15 @@ def test_fast_math_each_phase_within_tolerance(lib, variant, grid, path):
             if ph in ("p2g1", "p2g2"):
                 assert errs[f"grid after {ph}"] <= FAST_TOL["grid"], (ph, errs)
             # after update_grid the cells hold v = momentum / mass: a one-unit (1e-7) difference in the momentum of a
-            # node with almost no mass is a large relative change THERE, but such nodes carry no weight in G2P,
-            # so the velocity grid is judged through the particles it produces (below), with a loose bound here
+            # node with almost no mass is a large relative change THERE (that is all the plain max-norm above sees: up to
+            # 4e-2 on the cell path, which truncates once per (cell, node)), but such a node carries no weight in G2P.
+            # So the velocity grid is judged by what a node's velocity stands for -- |v - v_ref| * mass against the
+            # largest momentum -- at twice the P2G tolerance (the division adds one rounding).
             if ph == "update_grid":
-                assert errs[f"grid after {ph}"] <= 5e-2, (ph, errs)
+                gr = ref.grid.astype(np.float64) / 1e7
+                errs["update_grid, mass-weighted"] = float(np.abs((g[:, :3] - gr[:, :3]) * gr[:, 3:4]).max() / np.abs(gr[:, :3] * gr[:, 3:4]).max())
+                assert errs["update_grid, mass-weighted"] <= 2 * FAST_TOL["grid"], (ph, errs)
+                assert helpers.rel_err(g[:, 3], gr[:, 3]) <= FAST_TOL["grid"], (ph, errs)
         gp, gv, gc, gm = s.download()
         assert s.stats().kernel_path == path
     errs["pos"] = float(np.abs(gp.astype(np.float64) - ref.pos).max() / max(op.grid))
@@ -128,6 +133,27 @@ def test_fast_math_each_phase_within_tolerance(lib, variant, grid, path):
     print("FAST_MATH_ERRORS", variant, grid, path, {k: f"{v:.3g}" for k, v in errs.items()})
     assert errs["pos"] <= FAST_TOL["pos"] and errs["vel"] <= FAST_TOL["vel"] and errs["C"] <= FAST_TOL["C"], errs
     helpers.assert_bit_equal(gm, ref.mass, "mass")
+
+
+def test_fast_tiled_kernels_with_a_stale_binning(lib):
+    """MPM_MATH_FAST on the tiled path with sort_interval = 4: between two bin phases particles drift out of their block
+    and take the kernels' slow path (global atomics / direct gathers).  Same per-particle bar as a fresh binning every step."""
+    op = orc.variant("3d_gpu", 32)
+    op.interaction = 0
+    pos = orc.init_block(3, (4, 4, 4), (20, 20, 20), 0.5)
+    ref = orc.State(op, pos); ref.step(12)
+    out = {}
+    for si in (1, 4):
+        with make_solver(op, pos.shape[0], kernel_path=2, math_mode=1, sort_interval=si) as s:
+            s.initialise_sim((4, 4, 4), (20, 20, 20), 0.5)
+            s.step(12)
+            out[si] = s.download()
+    for si in (1, 4):
+        gp, gv = out[si][0], out[si][1]
+        assert np.abs(gp.astype(np.float64) - ref.pos).max() / 32 <= 12 * FAST_TOL["pos"], si
+        assert helpers.rel_err(gv, ref.vel) <= 12 * FAST_TOL["vel"], si
+    # the slow path computes the same sums in another order: the two runs agree to rounding, not to the bit
+    assert np.abs(out[1][0] - out[4][0]).max() < 1e-4
 
 
 @pytest.mark.parametrize("path", [2, 3], ids=["tiled_path", "cell_path"])
