@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(const uint32_t* __restrict
         // once and the placement is atomic -- and the 16th probes again.
         const bool violent = far_n[2] > FAR_LIMIT;
         far_n[4] = violent ? far_n[4] + 1 : 0;
-        far_n[0] = 0;
+        far_n[0] = 0; far_n[5] = 0;
         far_n[2] = (violent && (far_n[4] & 15u)) ? FAR_LIMIT + 1u : 0u;
     }
     __shared__ uint32_t wsum[32], wact[32];
@@ -399,6 +399,11 @@ __global__ void __launch_bounds__(256) k_place(const uint32_t* __restrict__ keys
 // cell sort in atomic order) and the binning is counted in MpmStats.unordered_binnings.
 struct RankGeom { int nbx, nby, nbz; };
 
+// tiles with more rows than this are ranked by a whole CTA (k_rank_place_heavy), the others by one warp each; k_rank_count
+// lists them (far_n[5] = how many; beyond HEAVY_CAP the heavy kernel falls back to scanning every tile)
+constexpr uint32_t HEAVY_ROWS = 256;
+constexpr int HEAVY_CAP = 4096;
+
 template <int CELL_BITS>
 struct RankCfg {
     static constexpr int LOGB = CELL_BITS / 3, B = 1 << LOGB, T = B + 2, RC = T * T * T;
@@ -463,7 +468,8 @@ template <int CELL_BITS>
 __global__ void __launch_bounds__(RankCfg<CELL_BITS>::THREADS, 12) k_rank_count(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ bbase_prev,
                                                                                 const uint32_t* __restrict__ active_prev, const uint32_t* __restrict__ nact_prev,
                                                                                 RankGeom g, uint32_t* __restrict__ tcount, uint32_t* __restrict__ farcnt,
-                                                                                uint32_t* __restrict__ fixlist, uint32_t* __restrict__ far_n)
+                                                                                uint32_t* __restrict__ fixlist, uint32_t* __restrict__ far_n,
+                                                                                uint32_t* __restrict__ heavy)
 {
     using C = RankCfg<CELL_BITS>;
     constexpr int KB = 8;  // keys per thread and batch: their loads are issued together
@@ -477,6 +483,10 @@ __global__ void __launch_bounds__(RankCfg<CELL_BITS>::THREADS, 12) k_rank_count(
         for (int k = threadIdx.x; k < C::RC; k += C::THREADS) cnt[k] = 0;
         __syncthreads();
         const uint32_t s0 = bbase_prev[tile], s1 = bbase_prev[tile + 1];
+        if (threadIdx.x == 0 && ((s1 - s0 + 31u) >> 5) > HEAVY_ROWS) {  // the pile-up tiles get a whole CTA in k_rank_place_heavy
+            const uint32_t h = atomicAdd(far_n + 5, 1u);
+            if (h < (uint32_t)HEAVY_CAP) heavy[h] = tile;
+        }
         const bool gave_up = *reinterpret_cast<volatile uint32_t*>(far_n + 2) > FAR_LIMIT;  // (then MpmStats.far_movers is a lower bound)
         for (uint32_t base = s0; base < s1; base += C::THREADS * KB) {
             uint32_t key[KB];
@@ -535,6 +545,7 @@ struct RankArgs {
     uint32_t* fill;      // atomic placement cursor (only when a binning gives up on the stable order)
     uint32_t* farcnt;    // far arrivals per cell: low half = count (k_rank_count), high half = tickets handed out
     uint32_t* far_n;
+    const uint32_t* heavy;  // tiles for k_rank_place_heavy (k_rank_count)
     uint32_t n_total;    // particles
     uint32_t* src_of;
     const uint32_t* id_src;
@@ -543,8 +554,6 @@ struct RankArgs {
 
 
 
-// tiles with more rows than this are ranked by a whole CTA (k_rank_place_heavy), the others by one warp each
-constexpr uint32_t HEAVY_ROWS = 256;
 
 // One tile, W warps.  W = 1: a warp on its own (no block-wide barrier anywhere: the usual tile of ~100 rows is latency-bound,
 // and thousands of independent warps hide that); W > 1: a CTA of W warps for the pile-up tiles of an evolved scene, each
@@ -731,9 +740,11 @@ __global__ void __launch_bounds__(256) k_rank_place_heavy(const __grid_constant_
     __shared__ uint32_t off[C::RC];
     __shared__ uint32_t nb_tile[28];
     if (A.far_n[2] > FAR_LIMIT) return;  // (k_rank_place ranks everything atomically)
-    const uint32_t na = *A.nact_prev;
+    const uint32_t nheavy = A.far_n[5];
+    const bool listed = nheavy <= (uint32_t)HEAVY_CAP;
+    const uint32_t na = listed ? nheavy : *A.nact_prev;
     for (uint32_t t = blockIdx.x; t < na; t += gridDim.x) {
-        const uint32_t tile = A.active_prev[t];
+        const uint32_t tile = listed ? A.heavy[t] : A.active_prev[t];
         const uint32_t s0 = A.bbase_prev[tile], s1 = A.bbase_prev[tile + 1];
         if (((s1 - s0 + 31u) >> 5) <= HEAVY_ROWS) continue;  // (uniform over the CTA)
         rank_tile<CELL_BITS, W>(A, tile, s0, s1, wcnt, off, nb_tile);
@@ -897,6 +908,7 @@ int bin_create(MpmSolver* s)
     const int64_t T = st->B + 2;
     CKB(cudaMalloc(&st->tcount, sizeof(uint32_t) * st->nblocks * T * T * T));
     CKB(cudaMalloc(&st->fixlist, sizeof(uint32_t) * FIX_CAP));
+    CKB(cudaMalloc(&st->heavy, sizeof(uint32_t) * HEAVY_CAP));
     CKB(cudaMalloc(&st->far_n, sizeof(uint32_t) * 8));
     CKB(cudaMemsetAsync(st->far_n, 0, sizeof(uint32_t) * 8, s->stream));
     CKB(cudaMalloc(&st->fill, sizeof(uint32_t) * st->nslots));
@@ -922,7 +934,7 @@ void bin_destroy(MpmSolver* s)
     if (!st) return;
     cudaFree(st->cnt[0]); cudaFree(st->cnt[1]); cudaFree(st->cnts); cudaFree(st->ord); cudaFree(st->cellmeta); cudaFree(st->pstart); cudaFree(st->stab);
     for (int k = 0; k < 2; ++k) { cudaFree(st->bsum2[k]); cudaFree(st->bbase2[k]); cudaFree(st->active2[k]); }
-    cudaFree(st->nact); cudaFree(st->tcount); cudaFree(st->fixlist); cudaFree(st->far_n);
+    cudaFree(st->nact); cudaFree(st->tcount); cudaFree(st->fixlist); cudaFree(st->heavy); cudaFree(st->far_n);
     cudaFree(st->fill); cudaFree(st->farcnt); cudaFree(st->keys); cudaFree(st->src_of);
     cudaFree(st->misc); cudaFree(st->box);
     delete st;
@@ -1022,15 +1034,15 @@ int bin_particles(MpmSolver* s)
         const RankGeom rg{st->nbx, st->nby, st->nbz};
         const unsigned grid_c = rank_grid(st, 12), grid_l = rank_grid(st, 8), grid_h = rank_grid(st, 4);  // (CTAs per SM)
         const RankArgs ra{st->keys, st->bsum2[pl], st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->cnt[nxt], st->cellmeta,
-                          st->cnts, st->pstart, st->stab, st->fill, st->farcnt, st->far_n, (uint32_t)n, st->src_of, s->orig_id, s->orig_id_alt};
+                          st->cnts, st->pstart, st->stab, st->fill, st->farcnt, st->far_n, st->heavy, (uint32_t)n, st->src_of, s->orig_id, s->orig_id_alt};
         const unsigned grid_f = rank_grid(st, 4);
         if (st->cell_bits == 9) {
-            k_rank_count<9><<<grid_c, RankCfg<9>::THREADS, 0, s->stream>>>(st->keys, st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->farcnt, st->fixlist, st->far_n);
+            k_rank_count<9><<<grid_c, RankCfg<9>::THREADS, 0, s->stream>>>(st->keys, st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->farcnt, st->fixlist, st->far_n, st->heavy);
             k_rank_place<9><<<grid_l, 128, 0, s->stream>>>(ra);
             k_rank_place_heavy<9><<<grid_h, 256, 0, s->stream>>>(ra);
             k_fix_far<9><<<grid_f, 128, 0, s->stream>>>(st->fixlist, st->far_n, st->cnt[nxt], st->farcnt, st->cellmeta, st->cnts, st->pstart, st->stab, st->src_of, s->orig_id_alt);
         } else {
-            k_rank_count<6><<<grid_c, RankCfg<6>::THREADS, 0, s->stream>>>(st->keys, st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->farcnt, st->fixlist, st->far_n);
+            k_rank_count<6><<<grid_c, RankCfg<6>::THREADS, 0, s->stream>>>(st->keys, st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->farcnt, st->fixlist, st->far_n, st->heavy);
             k_rank_place<6><<<grid_l, 128, 0, s->stream>>>(ra);
             k_rank_place_heavy<6><<<grid_h, 256, 0, s->stream>>>(ra);
             k_fix_far<6><<<grid_f, 128, 0, s->stream>>>(st->fixlist, st->far_n, st->cnt[nxt], st->farcnt, st->cellmeta, st->cnts, st->pstart, st->stab, st->src_of, s->orig_id_alt);

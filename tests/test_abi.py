@@ -88,13 +88,21 @@ def test_reference_arm_of_the_bench_prints_the_contract_line():
 
 
 def test_committed_traffic_table_has_the_kernels_the_bench_reports():
-    """`bench.py` fills `roofline.traffic` / `kernels[*].traffic` from profiles/r1/traffic_c4.json (DRAM bytes per launch
-    from one committed `ncu --set full` capture): the table must name the three stencil kernels, cite its source file,
-    and that file must be in the repo."""
+    """`bench.py` fills `roofline.traffic` / `kernels[*].traffic` from profiles/r2/traffic_c4.json (DRAM bytes per launch
+    from one committed `ncu --set full` capture): the table must name the three stencil kernels, cite its source file, that
+    file must be in the repo, and the cell kernels must not have changed since the commit the capture was taken at (where a
+    git history is available: the GPU box runs from a snapshot without one)."""
     import json
-    with open(os.path.join(ROOT, "profiles", "r1", "traffic_c4.json")) as f:
+    import subprocess
+    with open(os.path.join(ROOT, "profiles", "r2", "traffic_c4.json")) as f:
         t = json.load(f)
     for k in ("k_p2g1_cell", "k_p2g2_cell", "k_g2p_cell"):
         assert t["kernels"][k]["dram_bytes"] > 1e9 and t["kernels"][k]["ncu_duration_s"] > 0
+        assert 1.0 <= t["kernels"][k]["dram_over_algorithmic"] < 1.5
     src = t["source"].split(" ")[0]
     assert os.path.exists(os.path.join(ROOT, src)), src
+    if os.path.isdir(os.path.join(ROOT, ".git")):
+        have = subprocess.run(["git", "-C", ROOT, "cat-file", "-e", t["commit"] + "^{commit}"], capture_output=True)
+        if have.returncode == 0:
+            changed = subprocess.run(["git", "-C", ROOT, "diff", "--quiet", t["commit"], "--", "mls-mpm-godot_b200/csrc/mpm_kernels_cell.cu"])
+            assert changed.returncode == 0, "the cell kernels changed after the committed ncu capture: re-capture profiles/r2/traffic_c4.json"
