@@ -916,8 +916,8 @@ int bin_create(MpmSolver* s)
     CKB(cudaMalloc(&st->farcnt, sizeof(uint32_t) * st->nslots));
     CKB(cudaMemsetAsync(st->farcnt, 0, sizeof(uint32_t) * st->nslots, s->stream));
     CKB(cudaMalloc(&st->keys, sizeof(uint32_t) * s->pitch));
-    CKB(cudaMalloc(&st->src_of, sizeof(uint32_t) * (s->pitch + 192)));  // (the cell kernels read up to two units past the last slot)
-    CKB(cudaMemsetAsync(st->src_of, 0, sizeof(uint32_t) * (s->pitch + 192), s->stream));
+    CKB(cudaMalloc(&st->src_of, sizeof(uint32_t) * (s->pitch + 512)));  // (the cell kernels read up to two units past the last slot)
+    CKB(cudaMemsetAsync(st->src_of, 0, sizeof(uint32_t) * (s->pitch + 512), s->stream));
 
     CKB(cudaMalloc(&st->box, sizeof(int) * 12));
     CKB(cudaMemsetAsync(st->box, 0, sizeof(int) * 12, s->stream));  // empty boxes

@@ -32,6 +32,10 @@
 #ifndef MPM_G2P_CTAS
 #define MPM_G2P_CTAS 3
 #endif
+// rows (of up to 32 particles) per pipeline unit: what one request brings in and one loop iteration of the walk consumes
+#ifndef MPM_UNIT_ROWS
+#define MPM_UNIT_ROWS 2
+#endif
 
 namespace mpm {
 
@@ -213,6 +217,8 @@ __device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async
 // lane walking for ages while 31 idle; the binning therefore splits any cell with more than 32 particles into several
 // VIRTUAL cells of at most 32 (mpm_bin.cu), each taken by its own lane.  The walk below only ever sees virtual cells:
 // a block has up to 2 * NC of them (NCHUNK chunks), ordered by count, descending.
+constexpr int RU = MPM_UNIT_ROWS;
+
 template <int B, class Body>
 __device__ __forceinline__ void walk_chunks(const CellArgs& a, int b, int lane, int warp, BlockWork* bw, Body& body)
 {
@@ -224,15 +230,23 @@ __device__ __forceinline__ void walk_chunks(const CellArgs& a, int b, int lane, 
     uint32_t c_nx = a.cnts[v0 + warp * 32 + lane];
     uint32_t L_nx = a.ord[v0 + warp * 32 + lane];
     uint32_t st_nx = a.pstart[(v0 >> 5) + warp];
+    // slots of the first unit (rows 0 .. RU - 1) of a chunk whose lanes hold `cnt` particles
+    auto first_unit = [&](uint32_t cnt) {
+        uint32_t n = 0;
+#pragma unroll
+        for (int u = 0; u < RU; ++u) n += __popc(__ballot_sync(0xffffffffu, cnt > (uint32_t)u));
+        return n;
+    };
 #pragma unroll 1
     for (;;) {
         const int chunk = chunk_nx;
         if (chunk >= CF::NCHUNK) break;
         const uint32_t c = c_nx, L = L_nx;
         uint32_t slot0 = st_nx;
-        unsigned mA = __ballot_sync(0xffffffffu, c > 0);
-        if (!mA) break;  // virtual cells are ordered by count, descending: every later chunk of the block is empty too
-        unsigned mB = __ballot_sync(0xffffffffu, c > 1);
+        unsigned m[RU];  // lanes that have a particle in row r + u
+#pragma unroll
+        for (int u = 0; u < RU; ++u) m[u] = __ballot_sync(0xffffffffu, c > (uint32_t)u);
+        if (!m[0]) break;  // virtual cells are ordered by count, descending: every later chunk of the block is empty too
         // claim the chunk after this one now, so that its metadata (and first unit) arrive while this one runs
         int g = 0;
         if (lane == 0) g = atomicAdd(&bw->next_chunk, 1);
@@ -243,35 +257,47 @@ __device__ __forceinline__ void walk_chunks(const CellArgs& a, int b, int lane, 
             L_nx = a.ord[v0 + chunk_nx * 32 + lane];
             st_nx = a.pstart[(v0 >> 5) + chunk_nx];
         }
-        if (!have) body.fetch(slot0, (uint32_t)(__popc(mA) + __popc(mB)), ROW_COLD);
+        if (!have) {
+            uint32_t n = 0;
+#pragma unroll
+            for (int u = 0; u < RU; ++u) n += __popc(m[u]);
+            body.fetch(slot0, n, ROW_COLD);
+        }
         have = false;
         body.begin_chunk((int)L);
 #pragma unroll 1
-        for (uint32_t r = 0;; r += 2) {
-            // rows r and r + 1 are the current unit: its slots are slot0 .. slot0 + nA + nB - 1
-            const uint32_t nA = __popc(mA), nB = __popc(mB);
-            const uint32_t tA = __popc(mA & lt), tB = nA + __popc(mB & lt);
-            const unsigned mC = __ballot_sync(0xffffffffu, r + 2 < c), mD = __ballot_sync(0xffffffffu, r + 3 < c);
+        for (uint32_t r = 0;; r += RU) {
+            // rows r .. r + RU - 1 are the current unit: its slots are slot0 .. slot0 + n_unit - 1, row after row
+            uint32_t t[RU], n_unit = 0;
+#pragma unroll
+            for (int u = 0; u < RU; ++u) { t[u] = n_unit + __popc(m[u] & lt); n_unit += __popc(m[u]); }
+            unsigned mn[RU];
+            uint32_t n_next = 0;
+#pragma unroll
+            for (int u = 0; u < RU; ++u) { mn[u] = __ballot_sync(0xffffffffu, r + RU + u < c); n_next += __popc(mn[u]); }
             // the next unit is requested BEFORE the current one is waited for: two units in flight while the warp waits
             bool fetched = true;
-            if (mC) {
-                body.fetch(slot0 + nA + nB, (uint32_t)(__popc(mC) + __popc(mD)), ROW_NEXT);
+            if (mn[0]) {
+                body.fetch(slot0 + n_unit, n_next, ROW_NEXT);
             } else {
-                const uint32_t n0 = __popc(__ballot_sync(0xffffffffu, c_nx > 0)), n1 = __popc(__ballot_sync(0xffffffffu, c_nx > 1));
-                if (n0) body.fetch(st_nx, n0 + n1, r > 0 ? ROW_HINTED : ROW_COLD);  // (single-unit chunk: no hint was given yet)
+                const uint32_t n0 = first_unit(c_nx);
+                if (n0) body.fetch(st_nx, n0, r > 0 ? ROW_HINTED : ROW_COLD);  // (single-unit chunk: no hint was given yet)
                 else fetched = false;
                 have = true;
             }
             body.take(fetched ? 1 : 0);
 #pragma unroll 1
-            for (uint32_t u = 0; u < 2; ++u) {  // (one copy of the body: two inlined copies get interleaved and spill)
-                const uint32_t t = u ? tB : tA;
-                if (r + u < c) body.compute(slot0 + t, t);
+            for (uint32_t u = 0; u < (uint32_t)RU; ++u) {  // (one copy of the body: inlined copies get interleaved and spill)
+                uint32_t tu = t[0];
+#pragma unroll
+                for (int k = 1; k < RU; ++k) tu = (u == (uint32_t)k) ? t[k] : tu;
+                if (r + u < c) body.compute(slot0 + tu, tu);
             }
             if (r == 0) body.hint_chunk(st_nx);  // (here, not where the chunk is claimed: st_nx has arrived by now)
-            slot0 += nA + nB;
-            mA = mC; mB = mD;
-            if (!mA) break;
+            slot0 += n_unit;
+#pragma unroll
+            for (int u = 0; u < RU; ++u) m[u] = mn[u];
+            if (!m[0]) break;
         }
         body.end_chunk(c > 0);
     }
@@ -304,39 +330,44 @@ struct CellPos {  // the cell (id L inside the block) this lane owns in the curr
 // a row ahead (ix_row) or, for the first row of the warp's next chunk, when that chunk is announced (ix_chunk), and are
 // passed around with SHFL; only the first row after a block change pays the load's latency.
 struct RowStage {
-    static constexpr int UNIT = 64;          // records per buffer (two rows)
+    static constexpr int UNIT = 32 * RU;     // records per buffer
     static constexpr int WORDS = UNIT * 16;  // one buffer, in 4-byte words
     const float4* rec4;
     const uint32_t* src_of;
     float* buf;   // the warp's two buffers
     unsigned sa;  // shared-memory address of the 16 bytes this lane fills for record q = lane / 4 of buffer 0
     int lane;
-    uint32_t ix_row[2] = {0, 0}, ix_chunk[2] = {0, 0};  // record indices of the 64 slots that follow the last request / start the next chunk
+    uint32_t ix_row[RU], ix_chunk[RU];  // record indices of the UNIT slots that follow the last request / start the next chunk
     int wr = 0, rd = 0;
     __device__ __forceinline__ RowStage(const float* rec_, const uint32_t* src_of_, float* buf_, int lane_)
         : rec4(reinterpret_cast<const float4*>(rec_)), src_of(src_of_), buf(buf_), lane(lane_)
     {
         const int q = lane >> 2, j = lane & 3;
         sa = (unsigned)__cvta_generic_to_shared(buf + q * 16 + ((j ^ (q >> 1)) & 3) * 4);
+#pragma unroll
+        for (int u = 0; u < RU; ++u) { ix_row[u] = 0; ix_chunk[u] = 0; }
     }
-    __device__ __forceinline__ void hint_chunk(uint32_t slot) { ix_chunk[0] = src_of[slot + lane]; ix_chunk[1] = src_of[slot + 32 + lane]; }
+    __device__ __forceinline__ void hint_chunk(uint32_t slot)
+    {
+#pragma unroll
+        for (int u = 0; u < RU; ++u) ix_chunk[u] = src_of[slot + 32 * u + lane];
+    }
     __device__ __forceinline__ void fetch(uint32_t base, uint32_t cnt, int kind)
     {
-        uint32_t ix0, ix1;
-        if (kind == ROW_NEXT) { ix0 = ix_row[0]; ix1 = ix_row[1]; }
-        else if (kind == ROW_HINTED) { ix0 = ix_chunk[0]; ix1 = ix_chunk[1]; }
-        else { ix0 = src_of[base + lane]; ix1 = src_of[base + 32 + lane]; }
+        uint32_t ix[RU];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) ix[u] = (kind == ROW_NEXT) ? ix_row[u] : (kind == ROW_HINTED) ? ix_chunk[u] : src_of[base + 32 * u + lane];
         const unsigned dst = sa + wr * (WORDS * 4);
         const uint32_t q = lane >> 2, j = lane & 3;
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {  // record t = 8 it + q; its swizzle (t >> 1) & 3 does not depend on it
-            const uint32_t src = __shfl_sync(0xffffffffu, it < 4 ? ix0 : ix1, (8 * it + q) & 31);
+        for (int it = 0; it < 4 * RU; ++it) {  // record t = 8 it + q; its swizzle (t >> 1) & 3 does not depend on it
+            const uint32_t src = __shfl_sync(0xffffffffu, ix[it / 4], (8 * it + q) & 31);
             cp_async16_if(dst + it * 512, rec4 + (src * 4u + j), 8 * it + q < cnt);
         }
         cp_async_commit();
         wr ^= 1;
-        ix_row[0] = src_of[base + cnt + lane];  // (src_of is padded: reading past the last particle is harmless)
-        ix_row[1] = src_of[base + cnt + 32 + lane];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) ix_row[u] = src_of[base + cnt + 32 * u + lane];  // (src_of is padded: reading past the last particle is harmless)
     }
     __device__ __forceinline__ void take(int pending)
     {
@@ -362,9 +393,9 @@ struct RowStage {
 };
 
 // units of (px, py, pz, m) quads for G2P: P2G_1 wrote them in slot order, so a unit is one contiguous run of 16-byte
-// elements; lane l copies elements l and l + 32
+// elements; lane l copies elements l, l + 32, ...
 struct QuadStage {
-    static constexpr int UNIT = 64;
+    static constexpr int UNIT = 32 * RU;
     const float4* pm;
     float4* buf;  // the warp's two buffers of UNIT quads
     unsigned sa;
@@ -377,8 +408,8 @@ struct QuadStage {
     __device__ __forceinline__ void fetch(uint32_t base, uint32_t cnt, int)
     {
         const unsigned dst = sa + wr * (UNIT * 16);
-        cp_async16_if(dst, pm + base + lane, (uint32_t)lane < cnt);
-        cp_async16_if(dst + 512, pm + base + 32 + lane, (uint32_t)lane + 32u < cnt);
+#pragma unroll
+        for (int u = 0; u < RU; ++u) cp_async16_if(dst + 512 * u, pm + base + 32 * u + lane, (uint32_t)(lane + 32 * u) < cnt);
         cp_async_commit();
         wr ^= 1;
     }
