@@ -226,22 +226,43 @@ def cpu_baseline(workload, budget_s=25.0):
                       f"MLSMPM3DFluidMultithreadNew.cs"}
 
 
+def timed_steps(solver, steps, sync_ranks=lambda: None):
+    """`steps` steps with two CUDA events around the whole mpm_step() call (timing level 2: the number that is reported),
+    then `steps` more with events around every phase of every step (level 1: the breakdown; the 12-18 event records of a
+    step cost a few percent of a sub-millisecond step, so that pass's own ms_step is reported beside, never instead)."""
+    solver.set_timing(2)
+    sync_ranks()
+    solver.step(steps); solver.sync()
+    sync_ranks()
+    whole_ms = solver.stats().ms_step
+    solver.set_timing(1)
+    solver.step(steps); solver.sync()
+    sync_ranks()
+    st = solver.stats()
+    solver.set_timing(0)
+    return whole_ms, st
+
+
 def time_scene(mpm_b200, grid, blocks, local_rank, math_mode, path, warmup, steps, presteps=0):
-    """One more scene on this GPU (single solver, no communicator): device-timed ms/step and per-phase times."""
+    """One more scene on this GPU (single solver, no communicator): device-timed ms/step (two events around the K steps)
+    and, from a second copy of the scene over the same steps, the per-phase times."""
     params = mpm_b200.default_params("3d_gpu", grid=grid, interaction=0, kernel_path=path, math_mode=math_mode)
     n = sum(lattice_count(*b) for b in blocks)
-    with mpm_b200.Solver(params, n, device=local_rank) as sv:
-        for k, (blo, bhi, bsp) in enumerate(blocks):
-            sv.initialise_sim(blo, bhi, bsp, append=k > 0)
-        if presteps:
-            sv.step(presteps)
-        sv.step(warmup); sv.sync()
-        sv.set_timing(True)
-        sv.step(steps); sv.sync()
-        st = sv.stats()
+    out = {}
+    for level in (1, 2):
+        with mpm_b200.Solver(params, n, device=local_rank) as sv:
+            for k, (blo, bhi, bsp) in enumerate(blocks):
+                sv.initialise_sim(blo, bhi, bsp, append=k > 0)
+            if presteps:
+                sv.step(presteps)
+            sv.step(warmup); sv.sync()
+            sv.set_timing(level)
+            sv.step(steps); sv.sync()
+            out[level] = sv.stats()
+    st, whole_ms = out[1], out[2].ms_step
     G = grid[0] * grid[1] * grid[2]
     t3 = st.ms_p2g1 + st.ms_p2g2 + st.ms_g2p
-    return {"particles": n, "grid": list(grid), "ms_per_step": st.ms_step, "value": n / (st.ms_step * 1e-3),
+    return {"particles": n, "grid": list(grid), "ms_per_step": whole_ms, "value": n / (whole_ms * 1e-3), "ms_per_step_phase_pass": st.ms_step,
             "phase_ms": {"sort": st.ms_sort, "clear": st.ms_clear, "p2g1": st.ms_p2g1, "p2g2": st.ms_p2g2, "update": st.ms_update, "g2p": st.ms_g2p},
             "p2g_g2p_gbs": (188 * n + 60 * G) / (t3 * 1e-3) / 1e9 if t3 > 0 else 0.0, "steps": steps, "warmup": warmup, "presteps": presteps}
 
@@ -290,16 +311,55 @@ def main():
     blocks = [(lo, hi, sp)] + EXTRA_BLOCKS.get(args.workload, [])
     n_total = sum(lattice_count(*b) for b in blocks)
     G = grid[0] * grid[1] * grid[2]
-    solver = mpm_b200.Solver(params, n_total, device=local_rank)
-    if world > 1:
-        uid = [mpm_b200.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        solver.comm_init(uid[0], rank, world)
-    # every rank generates the same lattice on its device; with a communicator the library cuts equal-count
-    # x-slabs from the particle histogram and keeps the particles of its own slab
-    for k, (blo, bhi, bsp) in enumerate(blocks):
-        solver.initialise_sim(blo, bhi, bsp, append=k > 0)
-    assert solver.num_particles == n_total, (solver.num_particles, n_total)
+    def build_scene():
+        sv = mpm_b200.Solver(params, n_total, device=local_rank)
+        if world > 1:
+            uid = [mpm_b200.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            sv.comm_init(uid[0], rank, world)
+        # every rank generates the same lattice on its device; with a communicator the library cuts equal-count
+        # x-slabs from the particle histogram and keeps the particles of its own slab
+        for k, (blo, bhi, bsp) in enumerate(blocks):
+            sv.initialise_sim(blo, bhi, bsp, append=k > 0)
+        assert sv.num_particles == n_total, (sv.num_particles, n_total)
+        return sv
+
+    # ---- pass A, the breakdown: the same scene, the same steps as the timed region below, with CUDA events around every
+    # phase of every step (12-18 event records per step: a few percent of a sub-millisecond step, which is why the headline
+    # is NOT taken from this pass).  Kernel durations of the roofline block come from here.
+    solver = build_scene()
+    if args.presteps > 0:
+        solver.step(args.presteps)
+    solver.step(max(args.warmup, 3))
+    solver.sync()
+    solver.set_timing(1)
+    barrier()
+    solver.step(args.steps)
+    solver.sync()
+    barrier()
+    st = solver.stats()
+    solver.set_timing(0)
+    if os.environ.get("MPM_BENCH_ALLRANKS"):  # per-rank phase times (load balance / exchange skew), to stderr
+        print(f"[rank {rank}] n_local={st.local_particles} cells={st.num_cells} ms_step={st.ms_step:.3f} sort={st.ms_sort:.3f} "
+              f"p2g1={st.ms_p2g1:.3f} p2g2={st.ms_p2g2:.3f} update={st.ms_update:.3f} g2p={st.ms_g2p:.3f} exchange={st.ms_exchange:.3f} "
+              f"(mass {st.ms_halo_mass:.3f} momentum {st.ms_halo_momentum:.3f} migration {st.ms_migration:.3f})",
+              file=sys.stderr, flush=True)
+    evolved_phases = None
+    if args.evolved_at > 0 and args.workload == "c4":
+        done = solver.stats().steps
+        if done < args.evolved_at:
+            solver.step(int(args.evolved_at - done))
+        solver.sync()
+        solver.set_timing(1)
+        barrier()
+        solver.step(args.steps); solver.sync()
+        barrier()
+        evolved_phases = solver.stats()
+        solver.set_timing(0)
+    solver.close()
+
+    # ---- pass B, the number: a fresh copy of the scene (the stable binning makes it the same bits on one GPU)
+    solver = build_scene()
     n_local = solver.stats().local_particles
 
     # ---- warm-up, then the timed region: K steps, device-timed on the solver's stream
@@ -309,24 +369,20 @@ def main():
         solver.step(args.presteps)
     solver.step(max(args.warmup, 3))
     solver.sync()
-    solver.set_timing(True)
+    solver.set_timing(2)  # two events around the K steps
     launches0 = solver.stats().kernel_launches
     barrier()
     sampler.mark_begin()
     t0 = time.perf_counter()
-    solver.step(args.steps)   # mpm_step records CUDA events on its own stream around the K steps and each phase
+    solver.step(args.steps)   # mpm_step records CUDA events on its own stream around the K steps
     solver.sync()
     wall_ms = (time.perf_counter() - t0) * 1e3
     sampler.mark_end()
     barrier()
-    st = solver.stats()
-    solver.set_timing(False)
-    if os.environ.get("MPM_BENCH_ALLRANKS"):  # per-rank phase times (load balance / exchange skew), to stderr
-        print(f"[rank {rank}] n_local={st.local_particles} cells={st.num_cells} ms_step={st.ms_step:.3f} sort={st.ms_sort:.3f} "
-              f"p2g1={st.ms_p2g1:.3f} p2g2={st.ms_p2g2:.3f} update={st.ms_update:.3f} g2p={st.ms_g2p:.3f} exchange={st.ms_exchange:.3f}",
-              file=sys.stderr, flush=True)
-    dev_ms = st.ms_step * args.steps
-    launches = st.kernel_launches - launches0
+    st_whole = solver.stats()
+    launches = st_whole.kernel_launches - launches0
+    solver.set_timing(0)
+    dev_ms = st_whole.ms_step * args.steps
     t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -369,18 +425,19 @@ def main():
         if done < args.evolved_at:
             solver.step(int(args.evolved_at - done))
         solver.sync()
-        solver.set_timing(True)
+        solver.set_timing(2)
         barrier()
         solver.step(args.steps); solver.sync()
         barrier()
-        se = solver.stats()
-        solver.set_timing(False)
-        t = torch.tensor([se.ms_step], dtype=torch.float64, device="cuda")
+        e_whole = solver.stats().ms_step
+        solver.set_timing(0)
+        se = evolved_phases
+        t = torch.tensor([e_whole], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ems = float(t.item())
         t3 = se.ms_p2g1 + se.ms_p2g2 + se.ms_g2p
-        evolved = {"from_step": int(se.steps - args.steps), "steps": args.steps, "ms_per_step": ems, "value": n_total / (ems * 1e-3),
+        evolved = {"from_step": int(se.steps - args.steps), "steps": args.steps, "ms_per_step": ems, "ms_per_step_phase_pass": se.ms_step, "value": n_total / (ems * 1e-3),
                    "phase_ms": {"sort": se.ms_sort, "clear": se.ms_clear, "p2g1": se.ms_p2g1, "p2g2": se.ms_p2g2, "update": se.ms_update,
                                 "g2p": se.ms_g2p, "exchange": se.ms_exchange},
                    "p2g_g2p_gbs": (188 * se.local_particles + 60 * se.num_cells) / (t3 * 1e-3) / 1e9 if t3 > 0 else 0.0,
@@ -408,13 +465,9 @@ def main():
             ws.comm_init(uid[0], rank, world)
         ws.initialise_sim(wlo, whi, wsp)
         ws.step(5); ws.sync()
-        ws.set_timing(True)
-        barrier()
-        ws.step(args.steps); ws.sync()
-        barrier()
-        wst = ws.stats()
+        w_whole, wst = timed_steps(ws, args.steps, barrier)
         ws.close()
-        t = torch.tensor([wst.ms_step], dtype=torch.float64, device="cuda")
+        t = torch.tensor([w_whole], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         wms = float(t.item())
@@ -447,15 +500,19 @@ def main():
                        "sort_interval": sort_interval, "parallelism": f"x-slab x{world}",
                        "presteps": args.presteps,
                        "l2": f"inputs ({64e-9 * n_total / world:.1f} GB of particle planes per GPU) exceed the 126 MB L2; no flush needed",
-                       "timing": "CUDA events on the solver stream inside mpm_step; wall-clock cross-check in wall_ms_per_step"},
+                       "timing": "value / ms_per_step: two CUDA events on the solver stream around the K timed steps (mpm_set_timing 2), max over "
+                                 "ranks; phase_ms / kernels / roofline: a second copy of the scene over the same steps with events around every "
+                                 "phase of every step (mpm_set_timing 1; that pass's own ms/step is ms_per_step_phase_pass); wall-clock "
+                                 "cross-check in wall_ms_per_step"},
             "wall_ms_per_step": wall_ms / args.steps,
+            "ms_per_step_phase_pass": st.ms_step,
             "phase_ms": phases,
             "p2g_g2p_gbs": headline, "p2g_g2p_frac": headline / peak,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_kind": peak_kind, "traffic": traffic.get(kname.get(dom)), "traffic_source": traffic_src,
                          "algorithmic_bytes": alg_bytes[dom],
                          "note": "algorithmic bytes = SURVEY 8d per-unit figures x (local particles, local cells); duration = CUDA "
-                                 "events around the kernel on the solver's stream, averaged over the timed steps"},
+                                 "events around the kernel on the solver's stream, averaged over the same K steps in the per-phase pass"},
             "kernels": per_kernel,
             "e2e": {"value": e2e_val, "unit": "particle-steps/s", "h2d_bytes_per_step": 140, "d2h_bytes_per_step": 16 * n_local,
                     "what": "per step: mpm_set_sphere (140-B parameter block), mpm_step(1), mpm_get_positions_async -> pinned host "

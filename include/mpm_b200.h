@@ -169,6 +169,10 @@ typedef struct MpmStats {
                                    apron (put in order by the fix-up pass; a lower bound once a binning has given up) */
     int64_t halo_peer_exchanges; /* multi-GPU: halo exchanges done by direct peer stores (k_halo_push / k_halo_wait_add over
                                    CUDA IPC or in-process peer pointers) rather than through the transport */
+    /* multi-GPU: ms_exchange split into its three parts (same averaging): the mass halo after P2G_1, the momentum halo after
+       P2G_2, the particle migration after G2P.  Each includes the wait for the neighbours. */
+    float ms_halo_mass, ms_halo_momentum, ms_migration;
+    int32_t reserved0;
 } MpmStats;
 
 typedef struct MpmSolver MpmSolver; /* opaque */
@@ -259,7 +263,9 @@ MPM_API int32_t mpm_get_positions_async(MpmSolver* s, float* dst4, int64_t cap);
 MPM_API int32_t mpm_wait_positions(MpmSolver* s);
 
 MPM_API int32_t mpm_num_particles(const MpmSolver* s, int64_t* n);
-/* Per-phase timing (Time.GetTicksUsec around each phase, F:190-219) is off by default. */
+/* Per-phase timing (Time.GetTicksUsec around each phase, F:190-219) is off by default.  enabled = 1: CUDA events around every
+ * phase of every step (MpmStats.ms_sort ... ms_step); enabled = 2: two events around the whole mpm_step() call only (ms_step;
+ * the per-phase fields read 0) -- the 12 to 18 event records of a step cost a few percent of a sub-millisecond step. */
 MPM_API int32_t mpm_set_timing(MpmSolver* s, int32_t enabled);
 MPM_API int32_t mpm_get_stats(MpmSolver* s, MpmStats* st);
 

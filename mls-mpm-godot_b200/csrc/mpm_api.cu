@@ -651,13 +651,13 @@ struct PhaseTimer {
     cudaEvent_t a = nullptr, b = nullptr;
     PhaseTimer(MpmSolver* s_, int phase_, size_t& cursor) : s(s_), phase(phase_)
     {
-        if (!s->timing) return;
+        if (s->timing != 1) return;
         while (s->ev.size() < cursor + 2) { cudaEvent_t e; cudaEventCreate(&e); s->ev.push_back(e); }
         a = s->ev[cursor]; b = s->ev[cursor + 1];
         cursor += 2;
         cudaEventRecord(a, s->stream);
     }
-    ~PhaseTimer() { if (s->timing) cudaEventRecord(b, s->stream); }
+    ~PhaseTimer() { if (b) cudaEventRecord(b, s->stream); }
 };
 
 // clear / update restricted to the bounding box the binning found (cell path, one GPU, binning valid for this step)
@@ -715,12 +715,14 @@ static int run_phase(MpmSolver* s, int phase, size_t& cursor)
 
 static int collect_timing(MpmSolver* s, size_t used, const std::vector<int>& phases)
 {
-    if (!s->timing || used == 0) return MPM_OK;
+    if (!s->timing) return MPM_OK;
     CK(cudaStreamSynchronize(s->stream));
+    if (s->timing != 1 || used == 0) return MPM_OK;
     for (size_t k = 0; k < phases.size(); ++k) {
         float ms = 0.0f;
         cudaEventElapsedTime(&ms, s->ev[2 * k], s->ev[2 * k + 1]);
         s->ms_acc[phases[k]] += ms;
+        if (phases[k] >= PH_EX_MASS && phases[k] <= PH_EX_MIG) s->ms_acc[PH_EXCHANGE] += ms;
     }
     return MPM_OK;
 }
@@ -749,9 +751,9 @@ extern "C" int32_t mpm_step(MpmSolver* s, int32_t iterations)
         }
         if ((rc = run_phase(s, PH_CLEAR, cursor))) return rc; phases.push_back(PH_CLEAR);
         if ((rc = run_phase(s, PH_P2G1, cursor))) return rc; phases.push_back(PH_P2G1);
-        if (s->comm) { PhaseTimer t(s, PH_EXCHANGE, cursor); phases.push_back(PH_EXCHANGE); if ((rc = comm_exchange_halo(s, 0))) return rc; }
+        if (s->comm) { PhaseTimer t(s, PH_EX_MASS, cursor); phases.push_back(PH_EX_MASS); if ((rc = comm_exchange_halo(s, 0))) return rc; }
         if ((rc = run_phase(s, PH_P2G2, cursor))) return rc; phases.push_back(PH_P2G2);
-        if (s->comm) { PhaseTimer t(s, PH_EXCHANGE, cursor); phases.push_back(PH_EXCHANGE); if ((rc = comm_exchange_halo(s, 1))) return rc; }
+        if (s->comm) { PhaseTimer t(s, PH_EX_MOM, cursor); phases.push_back(PH_EX_MOM); if ((rc = comm_exchange_halo(s, 1))) return rc; }
         // cell path: UpdateGrid is pointwise, so G2P can apply it while staging its tiles (MPM_FUSED_UPDATE=1).  Measured on
         // C4: 3.72 vs 3.75 ms/step at the start, 5.27 vs 5.22 ms after 100 steps -- no gain (the tile aprons redo 1.95x of
         // the update), so the separate kernel stays the default.
@@ -759,7 +761,7 @@ extern "C" int32_t mpm_step(MpmSolver* s, int32_t iterations)
         if (s->path == MPM_PATH_CELL && fuse_update) s->grid_raw = true;
         else { if ((rc = run_phase(s, PH_UPDATE, cursor))) return rc; phases.push_back(PH_UPDATE); }
         if ((rc = run_phase(s, PH_G2P, cursor))) return rc; phases.push_back(PH_G2P);
-        if (s->comm) { PhaseTimer t(s, PH_EXCHANGE, cursor); phases.push_back(PH_EXCHANGE); if ((rc = comm_migrate(s))) return rc; }
+        if (s->comm) { PhaseTimer t(s, PH_EX_MIG, cursor); phases.push_back(PH_EX_MIG); if ((rc = comm_migrate(s))) return rc; }
         s->steps += 1;
         s->steps_since_sort += 1;
     }
@@ -784,12 +786,12 @@ extern "C" int32_t mpm_run_phase(MpmSolver* s, int32_t phase)
     if (phase < 0 || phase > PH_SORT) return fail(s, MPM_ERR_INVALID, "phase must be 0..5");
     if (s->comm) return fail(s, MPM_ERR_STATE, "multi-GPU: phases cannot run one by one (halo exchanges sit between them); use mpm_step");
     if ((s->path == MPM_PATH_TILED || s->path == MPM_PATH_CELL) && phase != PH_SORT && phase != PH_CLEAR && phase != PH_UPDATE && !s->sorted_valid) {
-        size_t c0 = 0; bool tm = s->timing; s->timing = false;
+        size_t c0 = 0; const int tm = s->timing; s->timing = 0;
         int rc = run_phase(s, PH_SORT, c0);
         s->timing = tm;
         if (rc) return rc;
     }
-    bool tm = s->timing; s->timing = false;
+    const int tm = s->timing; s->timing = 0;
     size_t cursor = 0;
     int rc = run_phase(s, phase, cursor);
     s->timing = tm;
@@ -900,7 +902,7 @@ extern "C" int32_t mpm_num_particles(const MpmSolver* s, int64_t* n)
 extern "C" int32_t mpm_set_timing(MpmSolver* s, int32_t enabled)
 {
     if (!s) return MPM_ERR_INVALID;
-    s->timing = enabled != 0;
+    s->timing = enabled == 2 ? 2 : (enabled != 0 ? 1 : 0);
     return MPM_OK;
 }
 
@@ -924,6 +926,8 @@ extern "C" int32_t mpm_get_stats(MpmSolver* s, MpmStats* st)
         st->ms_p2g1 = (float)(s->ms_acc[PH_P2G1] * k); st->ms_p2g2 = (float)(s->ms_acc[PH_P2G2] * k);
         st->ms_update = (float)(s->ms_acc[PH_UPDATE] * k); st->ms_g2p = (float)(s->ms_acc[PH_G2P] * k);
         st->ms_exchange = (float)(s->ms_acc[PH_EXCHANGE] * k); st->ms_step = (float)(s->ms_step_acc * k);
+        st->ms_halo_mass = (float)(s->ms_acc[PH_EX_MASS] * k); st->ms_halo_momentum = (float)(s->ms_acc[PH_EX_MOM] * k);
+        st->ms_migration = (float)(s->ms_acc[PH_EX_MIG] * k);
     }
     if (s->hp.overflow_check && s->overflow_flag) {
         cudaSetDevice(s->device);

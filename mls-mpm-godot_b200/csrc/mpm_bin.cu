@@ -41,7 +41,7 @@ namespace mpm {
 // A binning with more "far movers" (particles that left their grid block's one-cell apron, see the stable ranking below)
 // than this is ranked with the atomic cursor altogether and booked as unordered: bulk motion of more than a cell per step
 // breaks the premise of the tile regions, and the exact fix-up is sized for outliers.
-constexpr uint32_t FAR_LIMIT = 1u << 17;
+constexpr uint32_t FAR_LIMIT_DEFAULT = 1u << 17;  // (far_n[6] holds the limit in force: MPM_FAR_LIMIT overrides it)
 
 #define CKB(call)                                                          \
     do {                                                                   \
@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(256) k_bin_keys(KeyGeom g, View pv, int64_t fi
 template <int CELL_BITS>
 __global__ void __launch_bounds__(256) k_block_sums(const uint32_t* __restrict__ cnt, int64_t nblocks, uint32_t* __restrict__ bsum)
 {
+    pdl_prologue();
     // one warp per grid block: 2^CELL_BITS counts (512 -> 4 uint4 per lane, 64 -> lanes 0..15 one uint4)
     const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -100,11 +101,13 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(const uint32_t* __restrict
                                                       uint32_t* __restrict__ active, uint32_t* __restrict__ misc, BoxGeom bg,
                                                       int* __restrict__ box, int cleared, uint32_t* __restrict__ nact_out, uint32_t* __restrict__ far_n)
 {
+    pdl_prologue();
     if (threadIdx.x == 0) {  // stable ranking: the list of cells with far arrivals starts empty; last binning's verdict is booked
         if (far_n[3]) { far_n[1] += 1; far_n[3] = 0; }
         // A binning that had to give up (more than FAR_LIMIT far movers: bulk motion of more than a cell per step) marks the
         // scene as violent: the next 15 binnings do not even try -- far_n[2] starts above the limit, k_rank_count returns at
         // once and the placement is atomic -- and the 16th probes again.
+        const uint32_t FAR_LIMIT = far_n[6];
         const bool violent = far_n[2] > FAR_LIMIT;
         far_n[4] = violent ? far_n[4] + 1 : 0;
         far_n[0] = 0; far_n[5] = 0;
@@ -207,6 +210,7 @@ __global__ void __launch_bounds__(1 << CELL_BITS) k_block_order(const uint32_t* 
                                                                uint2* __restrict__ cellmeta, uint32_t* __restrict__ pstart,
                                                                uint16_t* __restrict__ stab, uint32_t* __restrict__ fill, uint32_t* __restrict__ farcnt)
 {
+    pdl_prologue();
     constexpr int NC = 1 << CELL_BITS, NV = 2 * NC, NBIN = 64, NW = NC / 32, EXTRA = NV - NC;
     __shared__ uint32_t hist[NBIN], base[NBIN];
     __shared__ uint32_t wbin[NW][NBIN];  // per warp: cells of each bin, then the count in the lower warps
@@ -363,6 +367,7 @@ __global__ void __launch_bounds__(256) k_place(const uint32_t* __restrict__ keys
                                                const uint16_t* __restrict__ stab, uint32_t* __restrict__ fill, uint32_t* __restrict__ src_of,
                                                const uint32_t* __restrict__ id_src, uint32_t* __restrict__ id_dst, const uint32_t* __restrict__ n_dev)
 {
+    pdl_wait();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (n_dev ? (int64_t)*n_dev : n)) return;  // (multi-GPU: the count of a migration the host has not read yet)
     const uint32_t key = keys[i];
@@ -471,9 +476,11 @@ __global__ void __launch_bounds__(RankCfg<CELL_BITS>::THREADS, 12) k_rank_count(
                                                                                 uint32_t* __restrict__ fixlist, uint32_t* __restrict__ far_n,
                                                                                 uint32_t* __restrict__ heavy)
 {
+    pdl_wait();
     using C = RankCfg<CELL_BITS>;
     constexpr int KB = 8;  // keys per thread and batch: their loads are issued together
     __shared__ uint32_t cnt[C::RC];
+    const uint32_t FAR_LIMIT = far_n[6];
     if (far_n[2] > FAR_LIMIT) return;  // (a violent scene, not probing this time: k_scan_blocks)
     const uint32_t na = *nact_prev;
     for (uint32_t t = blockIdx.x; t < na; t += gridDim.x) {
@@ -695,11 +702,12 @@ __device__ __forceinline__ void rank_tile(const RankArgs& A, uint32_t tile, uint
 template <int CELL_BITS>
 __global__ void __launch_bounds__(128, 8) k_rank_place(const __grid_constant__ RankArgs A)
 {
+    pdl_wait();
     using C = RankCfg<CELL_BITS>;
     __shared__ uint32_t wcnt[4][C::RC];
     __shared__ uint32_t nb_tile[4][28];
     const int w = threadIdx.x >> 5;
-    if (A.far_n[2] > FAR_LIMIT) {
+    if (A.far_n[2] > A.far_n[6]) {
         // too violent a step for the stable order (uniform over the launch): every particle takes its rank from the atomic
         // cursor, all threads of the grid striding over the particles, four loads in flight each
         if (blockIdx.x == 0 && threadIdx.x == 0) A.far_n[3] = 1;
@@ -734,12 +742,13 @@ __global__ void __launch_bounds__(128, 8) k_rank_place(const __grid_constant__ R
 template <int CELL_BITS>
 __global__ void __launch_bounds__(256) k_rank_place_heavy(const __grid_constant__ RankArgs A)
 {
+    pdl_wait();
     using C = RankCfg<CELL_BITS>;
     constexpr int W = 8;
     __shared__ uint32_t wcnt[W * C::RC];
     __shared__ uint32_t off[C::RC];
     __shared__ uint32_t nb_tile[28];
-    if (A.far_n[2] > FAR_LIMIT) return;  // (k_rank_place ranks everything atomically)
+    if (A.far_n[2] > A.far_n[6]) return;  // (k_rank_place ranks everything atomically)
     const uint32_t nheavy = A.far_n[5];
     const bool listed = nheavy <= (uint32_t)HEAVY_CAP;
     const uint32_t na = listed ? nheavy : *A.nact_prev;
@@ -761,8 +770,9 @@ __global__ void __launch_bounds__(128) k_fix_far(const uint32_t* __restrict__ fi
                                                  const uint32_t* __restrict__ pstart, const uint16_t* __restrict__ stab, uint32_t* __restrict__ src_of,
                                                  uint32_t* __restrict__ ids)
 {
+    pdl_wait();
     const uint32_t listed = far_n[0];
-    if (listed == 0 || far_n[2] > FAR_LIMIT) return;
+    if (listed == 0 || far_n[2] > far_n[6]) return;
     if (listed > (uint32_t)FIX_CAP && blockIdx.x == 0 && threadIdx.x == 0) far_n[3] = 1;
     const uint32_t ncell = min(listed, (uint32_t)FIX_CAP);
     for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < ncell; q += gridDim.x * blockDim.x) {
@@ -911,6 +921,11 @@ int bin_create(MpmSolver* s)
     CKB(cudaMalloc(&st->heavy, sizeof(uint32_t) * HEAVY_CAP));
     CKB(cudaMalloc(&st->far_n, sizeof(uint32_t) * 8));
     CKB(cudaMemsetAsync(st->far_n, 0, sizeof(uint32_t) * 8, s->stream));
+    {
+        const char* e = getenv("MPM_FAR_LIMIT");
+        const uint32_t lim = e ? (uint32_t)strtoul(e, nullptr, 10) : FAR_LIMIT_DEFAULT;
+        CKB(cudaMemcpyAsync(st->far_n + 6, &lim, sizeof(lim), cudaMemcpyHostToDevice, s->stream));
+    }
     CKB(cudaMalloc(&st->fill, sizeof(uint32_t) * st->nslots));
     CKB(cudaMemsetAsync(st->fill, 0, sizeof(uint32_t) * st->nslots, s->stream));
     CKB(cudaMalloc(&st->farcnt, sizeof(uint32_t) * st->nslots));
@@ -1021,13 +1036,13 @@ int bin_particles(MpmSolver* s)
     uint32_t* bbase = st->bbase2[nl];
     uint32_t* active = st->active2[nl];
     if (st->cell_bits == 9) {
-        k_block_sums<9><<<nbw, 256, 0, s->stream>>>(st->cnt[nxt], st->nblocks, bsum);
-        k_scan_blocks<<<1, 1024, 0, s->stream>>>(bsum, st->nblocks, bbase, active, st->misc, bg, st->box, st->box_cleared ? 1 : 0, st->nact + nl, st->far_n);
-        k_block_order<9><<<(unsigned)st->nblocks, 512, 0, s->stream>>>(st->cnt[nxt], bbase, active, st->misc, st->ord, st->cnts, st->cellmeta, st->pstart, st->stab, st->fill, st->farcnt);
+        launch_pdl<PDL_BIN>(k_block_sums<9>, dim3(nbw), dim3(256), 0, s->stream, st->cnt[nxt], st->nblocks, bsum);
+        launch_pdl<PDL_BIN>(k_scan_blocks, dim3(1), dim3(1024), 0, s->stream, bsum, st->nblocks, bbase, active, st->misc, bg, st->box, st->box_cleared ? 1 : 0, st->nact + nl, st->far_n);
+        launch_pdl<PDL_BIN>(k_block_order<9>, dim3((unsigned)st->nblocks), dim3(512), 0, s->stream, st->cnt[nxt], bbase, active, st->misc, st->ord, st->cnts, st->cellmeta, st->pstart, st->stab, st->fill, st->farcnt);
     } else {
-        k_block_sums<6><<<nbw, 256, 0, s->stream>>>(st->cnt[nxt], st->nblocks, bsum);
-        k_scan_blocks<<<1, 1024, 0, s->stream>>>(bsum, st->nblocks, bbase, active, st->misc, bg, st->box, st->box_cleared ? 1 : 0, st->nact + nl, st->far_n);
-        k_block_order<6><<<(unsigned)st->nblocks, 64, 0, s->stream>>>(st->cnt[nxt], bbase, active, st->misc, st->ord, st->cnts, st->cellmeta, st->pstart, st->stab, st->fill, st->farcnt);
+        launch_pdl<PDL_BIN>(k_block_sums<6>, dim3(nbw), dim3(256), 0, s->stream, st->cnt[nxt], st->nblocks, bsum);
+        launch_pdl<PDL_BIN>(k_scan_blocks, dim3(1), dim3(1024), 0, s->stream, bsum, st->nblocks, bbase, active, st->misc, bg, st->box, st->box_cleared ? 1 : 0, st->nact + nl, st->far_n);
+        launch_pdl<PDL_BIN>(k_block_order<6>, dim3((unsigned)st->nblocks), dim3(64), 0, s->stream, st->cnt[nxt], bbase, active, st->misc, st->ord, st->cnts, st->cellmeta, st->pstart, st->stab, st->fill, st->farcnt);
     }
     s->launches += 3;
     if (n > 0 && stable) {
@@ -1037,20 +1052,20 @@ int bin_particles(MpmSolver* s)
                           st->cnts, st->pstart, st->stab, st->fill, st->farcnt, st->far_n, st->heavy, (uint32_t)n, st->src_of, s->orig_id, s->orig_id_alt};
         const unsigned grid_f = rank_grid(st, 4);
         if (st->cell_bits == 9) {
-            k_rank_count<9><<<grid_c, RankCfg<9>::THREADS, 0, s->stream>>>(st->keys, st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->farcnt, st->fixlist, st->far_n, st->heavy);
-            k_rank_place<9><<<grid_l, 128, 0, s->stream>>>(ra);
-            k_rank_place_heavy<9><<<grid_h, 256, 0, s->stream>>>(ra);
-            k_fix_far<9><<<grid_f, 128, 0, s->stream>>>(st->fixlist, st->far_n, st->cnt[nxt], st->farcnt, st->cellmeta, st->cnts, st->pstart, st->stab, st->src_of, s->orig_id_alt);
+            launch_pdl<PDL_RANK>(k_rank_count<9>, dim3(grid_c), dim3(RankCfg<9>::THREADS), 0, s->stream, st->keys, st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->farcnt, st->fixlist, st->far_n, st->heavy);
+            launch_pdl<PDL_RANK>(k_rank_place<9>, dim3(grid_l), dim3(128), 0, s->stream, ra);
+            launch_pdl<PDL_RANK>(k_rank_place_heavy<9>, dim3(grid_h), dim3(256), 0, s->stream, ra);
+            launch_pdl<PDL_RANK>(k_fix_far<9>, dim3(grid_f), dim3(128), 0, s->stream, st->fixlist, st->far_n, st->cnt[nxt], st->farcnt, st->cellmeta, st->cnts, st->pstart, st->stab, st->src_of, s->orig_id_alt);
         } else {
-            k_rank_count<6><<<grid_c, RankCfg<6>::THREADS, 0, s->stream>>>(st->keys, st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->farcnt, st->fixlist, st->far_n, st->heavy);
-            k_rank_place<6><<<grid_l, 128, 0, s->stream>>>(ra);
-            k_rank_place_heavy<6><<<grid_h, 256, 0, s->stream>>>(ra);
-            k_fix_far<6><<<grid_f, 128, 0, s->stream>>>(st->fixlist, st->far_n, st->cnt[nxt], st->farcnt, st->cellmeta, st->cnts, st->pstart, st->stab, st->src_of, s->orig_id_alt);
+            launch_pdl<PDL_RANK>(k_rank_count<6>, dim3(grid_c), dim3(RankCfg<6>::THREADS), 0, s->stream, st->keys, st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->farcnt, st->fixlist, st->far_n, st->heavy);
+            launch_pdl<PDL_RANK>(k_rank_place<6>, dim3(grid_l), dim3(128), 0, s->stream, ra);
+            launch_pdl<PDL_RANK>(k_rank_place_heavy<6>, dim3(grid_h), dim3(256), 0, s->stream, ra);
+            launch_pdl<PDL_RANK>(k_fix_far<6>, dim3(grid_f), dim3(128), 0, s->stream, st->fixlist, st->far_n, st->cnt[nxt], st->farcnt, st->cellmeta, st->cnts, st->pstart, st->stab, st->src_of, s->orig_id_alt);
         }
         s->launches += 4;
     } else if (n > 0) {
-        if (st->cell_bits == 9) k_place<9><<<nb, 256, 0, s->stream>>>(st->keys, n, st->cellmeta, st->cnts, st->pstart, st->stab, st->fill, st->src_of, s->orig_id, s->orig_id_alt, s->n_dev);
-        else k_place<6><<<nb, 256, 0, s->stream>>>(st->keys, n, st->cellmeta, st->cnts, st->pstart, st->stab, st->fill, st->src_of, s->orig_id, s->orig_id_alt, s->n_dev);
+        if (st->cell_bits == 9) launch_pdl<PDL_RANK>(k_place<9>, dim3(nb), dim3(256), 0, s->stream, st->keys, n, st->cellmeta, st->cnts, st->pstart, st->stab, st->fill, st->src_of, s->orig_id, s->orig_id_alt, s->n_dev);
+        else launch_pdl<PDL_RANK>(k_place<6>, dim3(nb), dim3(256), 0, s->stream, st->keys, n, st->cellmeta, st->cnts, st->pstart, st->stab, st->fill, st->src_of, s->orig_id, s->orig_id_alt, s->n_dev);
         s->launches += 1;
     }
     st->prev_lay = pl;

@@ -608,6 +608,7 @@ __global__ void __launch_bounds__(256) k_halo_push(const int4* __restrict__ bloc
                                                    uint32_t* flagL, const int4* __restrict__ blockR, const int4* __restrict__ snapR,
                                                    int4* __restrict__ dstR, uint32_t* flagR, int64_t cells, uint32_t seq, uint32_t* done)
 {
+    pdl_prologue();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < cells) {
         if (dstL) {
@@ -638,6 +639,7 @@ __global__ void __launch_bounds__(256) k_halo_wait_add(int4* __restrict__ blockL
                                                        int4* __restrict__ blockR, const int4* recvR, int4* __restrict__ snapR, const uint32_t* flagR,
                                                        int64_t cells, uint32_t seq, uint32_t* err)
 {
+    pdl_prologue();
     if (threadIdx.x == 0) {
         const long long t0 = clock64();
         for (int side = 0; side < 2; ++side) {
@@ -772,7 +774,7 @@ static int exchange_halo_p2p(MpmSolver* s, int pass, int4* blockL, int4* blockR)
     int4* dstR = blockR ? region_of(c->p2p_peer[1], 0) : nullptr;
     uint32_t* fL = blockL ? flag_of(c->p2p_peer[0], 1) : nullptr;
     uint32_t* fR = blockR ? flag_of(c->p2p_peer[1], 0) : nullptr;
-    k_halo_push<<<nb, 256, 0, s->stream>>>(blockL, pass == 1 ? c->halo_snap[0] : nullptr, dstL, fL, blockR, pass == 1 ? c->halo_snap[1] : nullptr,
+    launch_pdl<PDL_HALO>(k_halo_push, dim3(nb), dim3(256), 0, s->stream, blockL, pass == 1 ? c->halo_snap[0] : nullptr, dstL, fL, blockR, pass == 1 ? c->halo_snap[1] : nullptr,
                                            dstR, fR, c->halo_cells, seq, c->p2p_done + pass);
     if (c->p2p_inproc) {  // ranks of one process: the streams are ordered by events, the flags are already set when the wait kernel runs
         int rc;
@@ -781,7 +783,7 @@ static int exchange_halo_p2p(MpmSolver* s, int pass, int4* blockL, int4* blockR)
         if (blockL && (rc = c->tr->await(0, pass, seq, s->stream, s->err))) return rc;
         if (blockR && (rc = c->tr->await(1, pass, seq, s->stream, s->err))) return rc;
     }
-    k_halo_wait_add<<<nb, 256, 0, s->stream>>>(blockL, region_of(c->p2p_own, 0), pass == 0 ? c->halo_snap[0] : nullptr,
+    launch_pdl<PDL_HALO>(k_halo_wait_add, dim3(nb), dim3(256), 0, s->stream, blockL, region_of(c->p2p_own, 0), pass == 0 ? c->halo_snap[0] : nullptr,
                                                blockL ? flag_of(c->p2p_own, 0) : nullptr, blockR, region_of(c->p2p_own, 1),
                                                pass == 0 ? c->halo_snap[1] : nullptr, blockR ? flag_of(c->p2p_own, 1) : nullptr, c->halo_cells,
                                                seq, c->d_cnt + 9);
@@ -905,6 +907,7 @@ __global__ void __launch_bounds__(256) k_mig_fill(View pv, uint32_t* __restrict_
                                                   const uint32_t* __restrict__ holes, const uint32_t* __restrict__ fillers,
                                                   const uint32_t* __restrict__ cnt)
 {
+    pdl_prologue();
     const uint32_t nh = cnt[4];
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nh; j += gridDim.x * blockDim.x) {
         const uint32_t dst = holes[j], src = fillers[j];
@@ -954,6 +957,7 @@ __global__ void __launch_bounds__(256) k_mig_push(RecView pv, const uint32_t* __
                                                   uint32_t* flagL, uint32_t* flagR, uint32_t* __restrict__ holes, uint32_t* __restrict__ fillers, MigGeom g,
                                                   uint32_t* __restrict__ cnt, uint32_t seq, uint32_t* done)
 {
+    pdl_prologue();
     const int64_t n = *n_dev;
     const uint32_t nL = min(cnt[0], rec_cap), nR = min(cnt[1], rec_cap);
     const int64_t n_stay = n - cnt[0] - cnt[1];
@@ -996,6 +1000,7 @@ __global__ void __launch_bounds__(256) k_mig_pull(RecView pv, uint32_t* __restri
                                                   const uint32_t* msgR, const uint32_t* flagL, const uint32_t* flagR, uint32_t seq, uint32_t* cnt,
                                                   KeyGeom kg, uint32_t nslots, uint32_t* __restrict__ keys, uint32_t* __restrict__ cnt_next, uint32_t* done)
 {
+    pdl_prologue();
     if (threadIdx.x == 0) {
         const long long t0 = clock64();
         for (int side = 0; side < 2; ++side) {
@@ -1067,9 +1072,9 @@ static int migrate_p2p(MpmSolver* s)
     uint32_t* dstR = hasR ? p2p_mig_region(c, c->p2p_peer[1], 0) : nullptr;
     uint32_t* fL = hasL ? p2p_mig_flag(c, c->p2p_peer[0], 1) : nullptr;
     uint32_t* fR = hasR ? p2p_mig_flag(c, c->p2p_peer[1], 0) : nullptr;
-    k_mig_push<<<296, 256, 0, s->stream>>>(s->rview(), s->orig_id, c->n_dev, (uint32_t)c->rec_cap, c->leave[0], c->leave[1], dstL, dstR, fL, fR, c->holes,
+    launch_pdl<PDL_MIG>(k_mig_push, dim3(296), dim3(256), 0, s->stream, s->rview(), s->orig_id, c->n_dev, (uint32_t)c->rec_cap, c->leave[0], c->leave[1], dstL, dstR, fL, fR, c->holes,
                                            c->fillers, g, c->d_cnt, seq, c->p2p_done + 2);
-    k_mig_fill<RecView><<<296, 256, 0, s->stream>>>(s->rview(), s->orig_id, bin_next_keys(s), c->holes, c->fillers, c->d_cnt);
+    launch_pdl<PDL_MIG>(k_mig_fill<RecView>, dim3(296), dim3(256), 0, s->stream, s->rview(), s->orig_id, bin_next_keys(s), c->holes, c->fillers, c->d_cnt);
     if (c->p2p_inproc) {  // ranks of one process: order the streams by events (see exchange_halo_p2p)
         int rc;
         if (hasL && (rc = c->tr->notify(0, 2, seq, s->stream, s->err))) return rc;
@@ -1077,7 +1082,7 @@ static int migrate_p2p(MpmSolver* s)
         if (hasL && (rc = c->tr->await(0, 2, seq, s->stream, s->err))) return rc;
         if (hasR && (rc = c->tr->await(1, 2, seq, s->stream, s->err))) return rc;
     }
-    k_mig_pull<<<296, 256, 0, s->stream>>>(s->rview(), s->orig_id, c->n_dev, (uint32_t)c->rec_cap, hasL ? p2p_mig_region(c, c->p2p_own, 0) : nullptr,
+    launch_pdl<PDL_MIG>(k_mig_pull, dim3(296), dim3(256), 0, s->stream, s->rview(), s->orig_id, c->n_dev, (uint32_t)c->rec_cap, hasL ? p2p_mig_region(c, c->p2p_own, 0) : nullptr,
                                            hasR ? p2p_mig_region(c, c->p2p_own, 1) : nullptr, hasL ? p2p_mig_flag(c, c->p2p_own, 0) : nullptr,
                                            hasR ? p2p_mig_flag(c, c->p2p_own, 1) : nullptr, seq, c->d_cnt, bin_key_geom(s), bin_nslots(s), bin_next_keys(s),
                                            bin_next_counts(s), c->p2p_done + 3);

@@ -15,8 +15,26 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <utility>
 
 namespace mpm {
+
+// host side of pdl_prologue(): an ordinary launch with the programmatic-stream-serialization attribute (MPM_NO_PDL=1: without)
+enum { PDL_BIN = 1, PDL_RANK = 2, PDL_SWEEP = 4, PDL_CELL = 8, PDL_HALO = 16, PDL_MIG = 32 };  // kernel groups (MPM_PDL_MASK: which of them get the attribute)
+template <int GROUP = 63, class... KA, class... A>
+inline cudaError_t launch_pdl(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args)
+{
+    static const int mask = getenv("MPM_NO_PDL") ? 0 : (getenv("MPM_PDL_MASK") ? atoi(getenv("MPM_PDL_MASK")) : 63);
+    const bool off = (mask & GROUP) == 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = off ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<A>(args)...);  // (coerces the arguments to the kernel's parameter types)
+}
 
 enum Plane { PX = 0, PY, PZ, VX, VY, VZ, PM, C0, C1, C2, C3, C4, C5, C6, C7, C8, NPLANES };
 static_assert(NPLANES == 16, "the group layout below assumes 16 fields");
@@ -104,6 +122,30 @@ __device__ __forceinline__ float eos_pow(float x, const DevParams& P)
         return __double2float_rn(r);
     }
     return __double2float_rn(pow((double)x, (double)P.eos_p));
+}
+
+// ---- programmatic dependent launch (sm_90+).  The kernels of a step are short (3 - 700 us) and strictly ordered on one
+// stream; between two of them the GPU would sit idle for the launch latency and the ramp-up of the next grid (~2-4 us, 12 to
+// 25 times per step: a tenth of a 0.2 - 0.6 ms step).  A kernel launched with launch_pdl() may have its CTAs scheduled as
+// soon as every CTA of the kernel before it has executed launch_dependents (or exited); it then parks in griddepcontrol.wait
+// until that earlier grid has COMPLETED and its writes are visible: the ordering is the stream's, the idle gap is gone.
+// Every kernel launched that way must call pdl_prologue() (or pdl_wait()) before it touches global memory; in a kernel
+// launched the ordinary way both instructions are no-ops.
+//
+// Order: WAIT FIRST, then release the successor.  The other order (release, then wait) lets three generations of grids be
+// resident at once -- kernel N still running, N + 1 and N + 2 both parked -- and that is not safe: with the three small
+// migration kernels (push -> fill -> pull, all resident together) k_mig_pull then ran before k_mig_fill had finished and
+// particles were lost (tests/test_multi_rank.py; bisected kernel by kernel on a B200).  With wait-then-release a grid is
+// only ever released by a grid whose own prerequisite has completed: two generations in flight, as the feature is specified.
+//
+// pdl_wait() alone leaves the release to the CTA's exit: for kernels whose parked successors would cost them something --
+// the ranking kernels lean on L1 for their table look-ups, and a successor's shared memory comes out of the same 256 KB
+// (C4: +20 us on the binning with an early release, -10 us without it; C2 gains either way).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
 }
 
 // (fmaxf / fminf return the other operand for a NaN: a non-finite position is pulled back into the clamp box instead of

@@ -519,6 +519,7 @@ __global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? MPM_P2G_CTAS :
                                                                                      int* __restrict__ grid, const float* __restrict__ rec,
                                                                                      const uint32_t* __restrict__ src_of)
 {
+    pdl_prologue();
     using TL = CTile<B>;
     using CF = CellCfg<B>;
     extern __shared__ __align__(16) unsigned char dsm[];  // tile | staging (above the 48 KB static limit together)
@@ -693,6 +694,7 @@ __global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? MPM_P2G_CTAS :
                                                                                      const uint32_t* __restrict__ src_of,
                                                                                      const __grid_constant__ CUtensorMap grid_map)
 {
+    pdl_prologue();
     using TL = CTile<B>;
     using CF = CellCfg<B>;
     using SM = P2G2Smem<B>;
@@ -896,6 +898,7 @@ __global__ void __launch_bounds__(CellCfg<B>::THREADS, (B == 8) ? MPM_G2P_CTAS :
                                                                                     uint32_t* __restrict__ keys, uint32_t* __restrict__ cnt_next,
                                                                                     MigClassify mg, float4* __restrict__ rec)
 {
+    pdl_prologue();
     using TL = CTile<B>;
     using CF = CellCfg<B>;
     // dynamic shared memory (above the 48 KB static limit together): the tile as the TMA unit delivers it -- [x][y][z]
@@ -1004,12 +1007,12 @@ static unsigned persistent_grid(K kernel, int threads, size_t smem)
             static unsigned grid8_dev[MAX_DEVICES] = {};  /* per device: the shared-memory opt-in is a per-device attribute */ \
             unsigned& grid8 = grid8_dev[s->device & (MAX_DEVICES - 1)];                                                   \
             if (!grid8) grid8 = persistent_grid(KERNEL<8>, CellCfg<8>::THREADS, (SMEM8));                                 \
-            KERNEL<8><<<(unsigned)std::min<int64_t>(grid8, st->nblocks), CellCfg<8>::THREADS, (SMEM8), s->stream>>>(s->dp, g, s->view(), a, __VA_ARGS__); \
+            launch_pdl<PDL_CELL>(KERNEL<8>, dim3((unsigned)std::min<int64_t>(grid8, st->nblocks)), dim3(CellCfg<8>::THREADS), (SMEM8), s->stream, s->dp, g, s->view(), a, __VA_ARGS__); \
         } else {                                                                                                          \
             static unsigned grid4_dev[MAX_DEVICES] = {};                                                                  \
             unsigned& grid4 = grid4_dev[s->device & (MAX_DEVICES - 1)];                                                   \
             if (!grid4) grid4 = persistent_grid(KERNEL<4>, CellCfg<4>::THREADS, (SMEM4));                                 \
-            KERNEL<4><<<(unsigned)std::min<int64_t>(grid4, st->nblocks), CellCfg<4>::THREADS, (SMEM4), s->stream>>>(s->dp, g, s->view(), a, __VA_ARGS__); \
+            launch_pdl<PDL_CELL>(KERNEL<4>, dim3((unsigned)std::min<int64_t>(grid4, st->nblocks)), dim3(CellCfg<4>::THREADS), (SMEM4), s->stream, s->dp, g, s->view(), a, __VA_ARGS__); \
         }                                                                                                                 \
         s->launches += 1;                                                                                                 \
     } while (0)

@@ -167,6 +167,7 @@ constexpr int BOX_ROWS = 8;  // (x, y) rows per CTA: one row per CTA made the la
 // contributions to, anywhere in y and z: they are swept whole, the planes between them inside the rank's own box)
 __global__ void __launch_bounds__(256) k_clear_box(DevParams P, int4* __restrict__ grid, const int* __restrict__ box, int halo_lo, int halo_hi)
 {
+    pdl_prologue();
     const int x = P.gx0 + blockIdx.y;
     const bool whole = (int)blockIdx.y < halo_lo || (int)blockIdx.y >= P.nxl - halo_hi;
     if (!whole && (x < box[0] || x >= box[1])) return;
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(256) k_clear_box(DevParams P, int4* __restrict
 
 __global__ void __launch_bounds__(256) k_update_box(DevParams P, int4* __restrict__ grid, const int* __restrict__ box, int halo_lo, int halo_hi)
 {
+    pdl_prologue();
     const int x = P.gx0 + blockIdx.y;
     const bool whole = (int)blockIdx.y < halo_lo || (int)blockIdx.y >= P.nxl - halo_hi;
     if (!whole && (x < box[0] || x >= box[1])) return;
@@ -277,11 +279,11 @@ void launch_update_grid(const DevParams& P, void* grid, int64_t ncells, cudaStre
 }
 void launch_clear_box(const DevParams& P, void* grid, const int* box, int halo_lo, int halo_hi, cudaStream_t st)
 {
-    k_clear_box<<<dim3((unsigned)((P.Ry + BOX_ROWS - 1) / BOX_ROWS), (unsigned)P.nxl), 256, 0, st>>>(P, reinterpret_cast<int4*>(grid), box, halo_lo, halo_hi);
+    launch_pdl<PDL_SWEEP>(k_clear_box, dim3((unsigned)((P.Ry + BOX_ROWS - 1) / BOX_ROWS), (unsigned)P.nxl), dim3(256), 0, st, P, reinterpret_cast<int4*>(grid), box, halo_lo, halo_hi);
 }
 void launch_update_box(const DevParams& P, void* grid, const int* box, int halo_lo, int halo_hi, cudaStream_t st)
 {
-    k_update_box<<<dim3((unsigned)((P.Ry + BOX_ROWS - 1) / BOX_ROWS), (unsigned)P.nxl), 256, 0, st>>>(P, reinterpret_cast<int4*>(grid), box, halo_lo, halo_hi);
+    launch_pdl<PDL_SWEEP>(k_update_box, dim3((unsigned)((P.Ry + BOX_ROWS - 1) / BOX_ROWS), (unsigned)P.nxl), dim3(256), 0, st, P, reinterpret_cast<int4*>(grid), box, halo_lo, halo_hi);
 }
 void launch_g2p_ref(const DevParams& P, ParticleView pv, int64_t n, const void* grid, const uint32_t* orig_id,
                     float4* positions, cudaStream_t st)

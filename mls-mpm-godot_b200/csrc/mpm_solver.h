@@ -23,7 +23,8 @@ struct BinState;   // mpm_bin.cu
 struct CommState;  // mpm_comm.cu
 }  // namespace mpm
 
-enum { PH_CLEAR = 0, PH_P2G1, PH_P2G2, PH_UPDATE, PH_G2P, PH_SORT, PH_EXCHANGE, PH_COUNT };
+// PH_EX_MASS / PH_EX_MOM / PH_EX_MIG: the three exchanges of a multi-GPU step (their sum is reported as ms_exchange too)
+enum { PH_CLEAR = 0, PH_P2G1, PH_P2G2, PH_UPDATE, PH_G2P, PH_SORT, PH_EXCHANGE, PH_EX_MASS, PH_EX_MOM, PH_EX_MIG, PH_COUNT };
 
 struct MpmSolver {
     MpmParams hp{};
@@ -77,7 +78,7 @@ struct MpmSolver {
     mpm::CommState* comm = nullptr;
 
     // per-phase timing
-    bool timing = false;
+    int timing = 0;  // MPM_TIMING_*: 0 off, 1 events around every phase, 2 events around the whole mpm_step() call only
     std::vector<cudaEvent_t> ev;  // 2 events per phase per step, recycled
     double ms_acc[PH_COUNT] = {0};
     double ms_step_acc = 0;

@@ -53,6 +53,8 @@ namespace MpmB200
         public float ms_sort, ms_clear, ms_p2g1, ms_p2g2, ms_update, ms_g2p, ms_exchange, ms_step;
         public int kernel_path, overflow, rank, world;
         public long local_particles, migrated, slab_jump_clamps, unordered_binnings, far_movers, halo_peer_exchanges;
+        public float ms_halo_mass, ms_halo_momentum, ms_migration;
+        public int reserved0;
     }
 
     public static unsafe class Native

@@ -58,6 +58,7 @@ class MpmStats(C.Structure):
         ("ms_update", C.c_float), ("ms_g2p", C.c_float), ("ms_exchange", C.c_float), ("ms_step", C.c_float),
         ("kernel_path", C.c_int32), ("overflow", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
         ("local_particles", C.c_int64), ("migrated", C.c_int64), ("slab_jump_clamps", C.c_int64), ("unordered_binnings", C.c_int64), ("far_movers", C.c_int64), ("halo_peer_exchanges", C.c_int64),
+        ("ms_halo_mass", C.c_float), ("ms_halo_momentum", C.c_float), ("ms_migration", C.c_float), ("reserved0", C.c_int32),
     ]
 
 
@@ -316,7 +317,7 @@ class Solver:
         return n.value
 
     def set_timing(self, on=True):
-        self._ck(self._L.mpm_set_timing(self._h, 1 if on else 0))
+        self._ck(self._L.mpm_set_timing(self._h, int(on)))  # True / 1: per phase, 2: whole call only
 
     def stats(self):
         st = MpmStats()

@@ -1,0 +1,14 @@
+cd $GRAFT_REPO_ROOT
+O=gpurun_out/r2w; mkdir -p $O
+timeout 1500 python -m pytest tests -m gpu -q > $O/pytest.log 2>&1; tail -4 $O/pytest.log
+for m in 63 0; do
+for w in c4 c2 c3; do
+st=20; [ $w = c2 ] && st=200; [ $w = c3 ] && st=50
+MPM_PDL_MASK=$m python bench.py --workload $w --steps $st --warmup 5 --no-cpu-baseline --no-extras --evolved-at 0 > $O/${w}_mask$m.json 2> $O/${w}_mask$m.err
+python - $O/${w}_mask$m.json $m $w <<'PY'
+import json,sys
+l=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+print(sys.argv[3], "mask", sys.argv[2], "ms/step %.4f (phase pass %.4f)"%(l["ms_per_step"], l["ms_per_step_phase_pass"]), {k:round(v,4) for k,v in l["phase_ms"].items() if k!='exchange'})
+PY
+done
+done
