@@ -414,6 +414,22 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = n_total * e2e_steps / float(t.item())
+    # the same frame loop with the quantised hand-off (4 x uint16 per particle: half the bytes over PCIe); reported beside
+    # e2e, never instead of it -- e2e is the reference-shaped float4 array
+    solver.positions_q16_into_async(pinned[0], n_total); solver.wait_positions(); solver.sync()
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        solver.set_sphere((-21.648403 + 0.01 * k, 0.0, 31.707275))
+        solver.step(1)
+        solver.positions_q16_into_async(pinned[k & 1], n_total)
+    solver.wait_positions()
+    solver.sync()
+    barrier()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_q16_val = n_total * e2e_steps / float(t.item())
     for ptr in pinned:
         mpm_b200.host_free(ptr)
     clocks = sampler.stop()
@@ -517,6 +533,8 @@ def main():
             "e2e": {"value": e2e_val, "unit": "particle-steps/s", "h2d_bytes_per_step": 140, "d2h_bytes_per_step": 16 * n_local,
                     "what": "per step: mpm_set_sphere (140-B parameter block), mpm_step(1), mpm_get_positions_async -> pinned host "
                             "(two buffers: the D2H copy of step k overlaps step k+1; every step's array reaches the host)"},
+            "e2e_q16": {"value": e2e_q16_val, "unit": "particle-steps/s", "d2h_bytes_per_step": 8 * n_local,
+                        "what": "the same frame loop with mpm_get_positions_q16_async (x, y, z as uint16 fractions of the domain, |v| as binary16)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

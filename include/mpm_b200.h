@@ -261,6 +261,11 @@ MPM_API int32_t mpm_export_positions(MpmSolver* s, int32_t* fd, uint64_t* bytes,
  * mpm_wait_positions(); the caller alternates between two host buffers.  Two device arrays are kept internally. */
 MPM_API int32_t mpm_get_positions_async(MpmSolver* s, float* dst4, int64_t cap);
 MPM_API int32_t mpm_wait_positions(MpmSolver* s);
+/* The same pipelined hand-off at half the bytes for hosts that must copy (the transfer over PCIe is what bounds them: 16 bytes
+ * per particle at ~56 GB/s): 4 x uint16 per particle -- x, y, z as fractions of the domain, code = rint(p / grid_size * 65535)
+ * (decode p = code * grid_size / 65535: a step of 0.004 cell on a 256-cell axis), and |v| as an IEEE binary16.  A renderer
+ * uploads it as an RGBA16 texture.  No reference counterpart (the reference never copies). */
+MPM_API int32_t mpm_get_positions_q16_async(MpmSolver* s, uint16_t* dst4, int64_t cap);
 
 MPM_API int32_t mpm_num_particles(const MpmSolver* s, int64_t* n);
 /* Per-phase timing (Time.GetTicksUsec around each phase, F:190-219) is off by default.  enabled = 1: CUDA events around every

@@ -853,7 +853,7 @@ extern "C" int32_t mpm_export_positions(MpmSolver* s, int32_t* fd, uint64_t* byt
     return MPM_OK;
 }
 
-extern "C" int32_t mpm_get_positions_async(MpmSolver* s, float* dst4, int64_t cap)
+static int32_t positions_async(MpmSolver* s, void* dst4, int64_t cap, bool q16)
 {
     if (!s || !dst4) return MPM_ERR_INVALID;
     CK(cudaSetDevice(s->device));
@@ -872,17 +872,25 @@ extern "C" int32_t mpm_get_positions_async(MpmSolver* s, float* dst4, int64_t ca
     const int b = s->pos_buf;
     float4* dev = b ? s->positions_b : s->positions;
     CK(cudaStreamWaitEvent(s->stream, s->pos_copied[b], 0));  // the copy that last read this device array is done
-    if (s->in_rec) launch_positions_rec(s->rview(), s->comm ? nullptr : s->orig_id, dev, s->n, s->stream);
+    if (q16) {
+        const float scale[3] = {65535.0f / (float)s->hp.grid_size[0], 65535.0f / (float)s->hp.grid_size[1],
+                                65535.0f / (float)std::max(s->hp.grid_size[2], 1)};
+        if (s->in_rec) launch_positions_q16_rec(s->rview(), s->comm ? nullptr : s->orig_id, dev, s->n, scale, s->stream);
+        else launch_positions_q16(s->view(), s->comm ? nullptr : s->orig_id, dev, s->n, scale, s->stream);
+    } else if (s->in_rec) launch_positions_rec(s->rview(), s->comm ? nullptr : s->orig_id, dev, s->n, s->stream);
     else launch_positions(s->view(), s->comm ? nullptr : s->orig_id, dev, s->n, s->stream);
     s->launches += 1;
     CK(cudaEventRecord(s->pos_ready[b], s->stream));
     CK(cudaStreamWaitEvent(s->copy_stream, s->pos_ready[b], 0));
-    CK(cudaMemcpyAsync(dst4, dev, sizeof(float4) * s->n, cudaMemcpyDeviceToHost, s->copy_stream));
+    CK(cudaMemcpyAsync(dst4, dev, (q16 ? sizeof(ushort4) : sizeof(float4)) * s->n, cudaMemcpyDeviceToHost, s->copy_stream));
     CK(cudaEventRecord(s->pos_copied[b], s->copy_stream));
     s->pos_buf ^= 1;
     if (b == 0) s->positions_valid = false;  // (the synchronous getter's array was just rewritten for this snapshot)
     return MPM_OK;
 }
+
+extern "C" int32_t mpm_get_positions_async(MpmSolver* s, float* dst4, int64_t cap) { return positions_async(s, dst4, cap, false); }
+extern "C" int32_t mpm_get_positions_q16_async(MpmSolver* s, uint16_t* dst4, int64_t cap) { return positions_async(s, dst4, cap, true); }
 
 extern "C" int32_t mpm_wait_positions(MpmSolver* s)
 {

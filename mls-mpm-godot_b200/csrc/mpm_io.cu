@@ -1,5 +1,6 @@
 // mpm_io.cu -- layout conversion between the reference's buffers and the solver's SoA planes, the
 // position hand-off array, and the lattice scene generator.  None of this is on the per-step hot path.
+#include <cuda_fp16.h>
 #include "mpm_kernels.h"
 
 namespace mpm {
@@ -86,6 +87,21 @@ __global__ void __launch_bounds__(256) k_positions(View pv, const uint32_t* __re
     positions[orig_id ? orig_id[i] : (uint32_t)i] = make_float4(pv.at(PX, i), pv.at(PY, i), pv.at(PZ, i), len);
 }
 
+// the same hand-off at half the bytes, for hosts that must copy it over PCIe: x, y, z as unsigned 16-bit fractions of the
+// domain (code q = rint(p / R * 65535): a step of R / 65535 cells, 0.004 cell at R = 256), |v| as an IEEE half
+template <class View>
+__global__ void __launch_bounds__(256) k_positions_q16(View pv, const uint32_t* __restrict__ orig_id, ushort4* __restrict__ out,
+                                                       int64_t n, float sx, float sy, float sz)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float vx = pv.at(VX, i), vy = pv.at(VY, i), vz = pv.at(VZ, i);
+    const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz)));
+    auto q = [](float p, float s) { return (unsigned short)__float2uint_rn(fminf(fmaxf(p * s, 0.0f), 65535.0f)); };
+    out[orig_id ? orig_id[i] : (uint32_t)i] = make_ushort4(q(pv.at(PX, i), sx), q(pv.at(PY, i), sy), q(pv.at(PZ, i), sz),
+                                                           __half_as_ushort(__float2half_rn(len)));
+}
+
 __global__ void __launch_bounds__(256) k_lattice(const float* __restrict__ xs, int nx, const float* __restrict__ ys,
                                                  int ny, const float* __restrict__ zs, int nz, ParticleView pv,
                                                  int64_t dst_off)
@@ -132,6 +148,15 @@ void launch_positions(ParticleView pv, const uint32_t* orig_id, float4* position
 void launch_positions_rec(RecView rv, const uint32_t* orig_id, float4* positions, int64_t n, cudaStream_t st)
 {
     if (n > 0) k_positions<RecView><<<nb(n), 256, 0, st>>>(rv, orig_id, positions, n);
+}
+
+void launch_positions_q16(ParticleView pv, const uint32_t* orig_id, void* out, int64_t n, const float scale[3], cudaStream_t st)
+{
+    if (n > 0) k_positions_q16<ParticleView><<<nb(n), 256, 0, st>>>(pv, orig_id, static_cast<ushort4*>(out), n, scale[0], scale[1], scale[2]);
+}
+void launch_positions_q16_rec(RecView rv, const uint32_t* orig_id, void* out, int64_t n, const float scale[3], cudaStream_t st)
+{
+    if (n > 0) k_positions_q16<RecView><<<nb(n), 256, 0, st>>>(rv, orig_id, static_cast<ushort4*>(out), n, scale[0], scale[1], scale[2]);
 }
 
 // 64-byte records (slot order) back into the grouped planes

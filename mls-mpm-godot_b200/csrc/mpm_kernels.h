@@ -28,6 +28,8 @@ void launch_soa_to_packed(ParticleView pv, const uint32_t* orig_id, float* pos, 
 void launch_iota(uint32_t* p, uint32_t start, int64_t n, cudaStream_t st);
 void launch_positions(ParticleView pv, const uint32_t* orig_id, float4* positions, int64_t n, cudaStream_t st);
 void launch_positions_rec(RecView rv, const uint32_t* orig_id, float4* positions, int64_t n, cudaStream_t st);
+void launch_positions_q16(ParticleView pv, const uint32_t* orig_id, void* out, int64_t n, const float scale[3], cudaStream_t st);
+void launch_positions_q16_rec(RecView rv, const uint32_t* orig_id, void* out, int64_t n, const float scale[3], cudaStream_t st);
 void launch_rec_to_planes(RecView rv, ParticleView pv, int64_t n, cudaStream_t st);
 // lattice block with per-axis coordinate tables (the fp32 accumulating loops run on the host: they are
 // O(R) work), vel = 0, C = 0, mass = 1

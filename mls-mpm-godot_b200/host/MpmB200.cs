@@ -88,6 +88,7 @@ namespace MpmB200
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_get_positions(IntPtr s, IntPtr dst4, long cap, out IntPtr device_ptr, out uint tex_width);
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_export_positions(IntPtr s, out int fd, out ulong bytes, out uint tex_width);
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_get_positions_async(IntPtr s, IntPtr dst4, long cap);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_get_positions_q16_async(IntPtr s, IntPtr dst4, long cap);  // 4 x uint16 per particle
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_wait_positions(IntPtr s);
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_num_particles(IntPtr s, out long n);
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_set_timing(IntPtr s, int enabled);

@@ -76,7 +76,7 @@ EXPORTS = [
     "mpm_get_positions", "mpm_num_particles", "mpm_set_timing", "mpm_get_stats", "mpm_debug_last_sort",
     "mpm_get_stream", "mpm_host_alloc", "mpm_host_free", "mpm_comm_unique_id", "mpm_comm_init",
     "mpm_local_hub_create", "mpm_local_hub_destroy", "mpm_comm_init_local", "mpm_comm_slab", "mpm_download_ids",
-    "mpm_slab_cuts", "mpm_get_positions_async", "mpm_wait_positions", "mpm_comm_rebalance", "mpm_set_colliders",
+    "mpm_slab_cuts", "mpm_get_positions_async", "mpm_get_positions_q16_async", "mpm_wait_positions", "mpm_comm_rebalance", "mpm_set_colliders",
     "mpm_save_state", "mpm_load_state", "mpm_export_positions",
 ]
 
@@ -130,6 +130,7 @@ def load():
         "mpm_download_ids": (i32, [vp, vp, i64]),
         "mpm_slab_cuts": (i32, [C.POINTER(i64), i32, i32, i32, C.POINTER(i32)]),
         "mpm_get_positions_async": (i32, [vp, vp, i64]),
+        "mpm_get_positions_q16_async": (i32, [vp, vp, i64]),
         "mpm_wait_positions": (i32, [vp]),
         "mpm_comm_rebalance": (i32, [vp, i32]),
         "mpm_set_colliders": (i32, [vp, fp, i32]),
@@ -290,6 +291,10 @@ class Solver:
     def positions_into_async(self, host_ptr, cap):
         """Pipelined hand-off: returns at once; the pinned buffer is complete after wait_positions()."""
         self._ck(self._L.mpm_get_positions_async(self._h, C.c_void_p(host_ptr), int(cap)))
+
+    def positions_q16_into_async(self, host_ptr, cap):
+        """The same at 8 bytes per particle: 4 x uint16 = x, y, z as fractions of the domain (code * grid_size / 65535), |v| as binary16."""
+        self._ck(self._L.mpm_get_positions_q16_async(self._h, C.c_void_p(host_ptr), int(cap)))
 
     def wait_positions(self):
         self._ck(self._L.mpm_wait_positions(self._h))

@@ -5,6 +5,7 @@ GLSL shaders) -> grid words, particle floats, cell keys and the binning permutat
 oracle.  Float grid mode -> atomic order differs from the reference's serial order, so the tolerance is
 calibrated from the oracle's own sensitivity to particle order and written in the test.
 PARITY UNPINNED: the oracle is a restatement (no reference golden vectors exist)."""
+import ctypes as C
 import os
 import sys
 
@@ -739,6 +740,69 @@ def test_cell_path_is_reproducible_bit_for_bit(lib, scene):
         helpers.assert_bit_equal(runs[0][0][k], runs[1][0][k], f"{scene}: {what} differs between two runs")
     helpers.assert_bit_equal(runs[0][1], runs[1][1], "grid differs between two runs")
     assert runs[0][2] == 0 and runs[1][2] == 0
+
+
+def test_quantised_position_hand_off_matches_the_float_one(lib):
+    """mpm_get_positions_q16_async: 4 x uint16 per particle (x, y, z as fractions of the domain, |v| as binary16) in original
+    index order, through the same double-buffered copy as the float4 hand-off.  Decoded positions are within half a code
+    step (grid_size / 65535 / 2, plus the fp32 rounding of the scaling) of mpm_get_positions, |v| within binary16 rounding."""
+    import mpm_b200
+    op = orc.variant("3d_gpu", 64)
+    op.interaction = 0
+    for path, math in ((3, 1), (2, 0)):
+        with make_solver(op, 262144, kernel_path=path, math_mode=math) as s:
+            n = s.initialise_sim((4, 4, 4), (36, 36, 36), 0.5)
+            s.step(7)
+            ref = s.positions().copy()
+            buf = mpm_b200.host_alloc(8 * n)
+            try:
+                s.positions_q16_into_async(buf, n)
+                s.wait_positions()
+                q = np.ctypeslib.as_array((C.c_uint16 * (4 * n)).from_address(buf)).reshape(n, 4).copy()
+            finally:
+                mpm_b200.host_free(buf)
+        dec = q[:, :3].astype(np.float64) * 64.0 / 65535.0
+        assert np.abs(dec - ref[:, :3]).max() <= 0.505 * 64.0 / 65535.0  # (half a code step, and the fp32 rounding of p * scale)
+        speed = q[:, 3].copy().view(np.float16).astype(np.float64)
+        assert np.abs(speed - ref[:, 3]).max() <= 1e-3 * max(1.0, float(ref[:, 3].max()))
+
+
+def test_programmatic_dependent_launch_changes_no_bit(lib):
+    """The per-step kernels are launched with the programmatic-stream-serialization attribute and start with
+    griddepcontrol.wait (mpm_common.cuh: pdl_prologue): the next grid's CTAs are scheduled while the current grid drains.
+    That must only remove idle time.  The same scene stepped in a child process with the attribute (default) and without
+    (MPM_NO_PDL=1) ends in the same bits, for a grid with 4^3-cell blocks and one with 8^3-cell blocks."""
+    import subprocess
+    tool = os.path.join(os.path.dirname(__file__), "tools", "state_hash.py")
+    for grid, steps in ((64, 30), (128, 12)):
+        outs = []
+        for extra in ({}, {"MPM_NO_PDL": "1"}):
+            env = dict(os.environ, **extra)
+            env.pop("MPM_PDL_MASK", None)
+            r = subprocess.run([sys.executable, tool, str(grid), str(steps)], capture_output=True, text=True, timeout=300, env=env)
+            assert r.returncode == 0, r.stderr[-2000:]
+            outs.append(r.stdout.split()[-3:])
+        assert outs[0] == outs[1], (grid, outs)
+        assert outs[0][0] == "0"  # every binning in the stable order: the runs are comparable bit for bit
+
+
+def test_timing_levels_agree(lib):
+    """mpm_set_timing(2) brackets the whole mpm_step() call with two events; level 1 adds events around every phase.  Both
+    report the same kind of number: the per-phase sum of level 1 is within its own ms_step, and the level-2 ms_step is not
+    larger than level 1's (the events themselves cost time) beyond noise; the per-phase fields read 0 at level 2."""
+    op = orc.variant("3d_gpu", 64)
+    op.interaction = 0
+    with make_solver(op, 262144, kernel_path=3, math_mode=1) as s:
+        s.initialise_sim((4, 4, 4), (36, 36, 36), 0.5)
+        s.step(5); s.sync()
+        s.set_timing(2); s.step(40); s.sync()
+        st2 = s.stats()
+        s.set_timing(1); s.step(40); s.sync()
+        st1 = s.stats()
+    assert st2.ms_step > 0 and st2.ms_p2g1 == 0 and st2.ms_sort == 0
+    phases = st1.ms_sort + st1.ms_clear + st1.ms_p2g1 + st1.ms_p2g2 + st1.ms_update + st1.ms_g2p
+    assert 0 < phases <= st1.ms_step * 1.001
+    assert st2.ms_step <= st1.ms_step * 1.10, (st2.ms_step, st1.ms_step)
 
 
 # ---------------------------------------------------------------- cell path against the ORACLE on the BASELINE configs
