@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(const uint32_t* __restrict
 //   cellmeta[cell] = {position of the cell's first full virtual cell | position of the one holding the remainder << 16,
 //                     number of full ones}
 constexpr uint32_t VROWS = 32;
+constexpr int STAB_ROW = 32;  // uint16 per chunk in stab[]: two 32-byte sectors (layout: k_block_order)
 
 template <int CELL_BITS>
 __global__ void __launch_bounds__(1 << CELL_BITS) k_block_order(const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ bbase,
@@ -289,11 +290,14 @@ __global__ void __launch_bounds__(1 << CELL_BITS) k_block_order(const uint32_t* 
         if (lane == 31) wsum[w] = xs;
         __syncthreads();
         const int chunk = p >> 5;
-        // Chunk row for k_place (one 32-byte sector): [0] flags chunks whose counts are not strictly ordered (a count >= 63
+        // Chunk row for k_place.  First 32-byte sector: [0] flags chunks whose counts are not strictly ordered (a count >= 63
         // shares the last sort bin: those take the general path); [1..13] S(r) = sum over the chunk's virtual cells of
         // min(count, r), the first slot of the rank-r row; [14..15] the chunk's start slot (also in pstart[] for the walk).
+        // Second sector: [16..31] = S(14..29), written only for chunks that have such rows -- the cells of a pile-up; without
+        // them every particle of rank >= 14 took the general path (32 counts read and compared per particle), which in the
+        // evolved dam-break is every warp of the placement.
         const uint32_t maxc = __reduce_max_sync(0xffffffffu, v);
-        uint16_t* st = stab + ((size_t)(v0 >> 5) + chunk) * 16;
+        uint16_t* st = stab + ((size_t)(v0 >> 5) + chunk) * STAB_ROW;
         if (lane == 0) {
             uint32_t off = carry_s;
             for (int k = 0; k < w; ++k) off += wsum[k];
@@ -306,6 +310,13 @@ __global__ void __launch_bounds__(1 << CELL_BITS) k_block_order(const uint32_t* 
         for (int r = 1; r < 14; ++r) {
             const uint32_t sr = __reduce_add_sync(0xffffffffu, min(v, (uint32_t)r));
             if (lane == 0) st[r] = (uint16_t)sr;
+        }
+        if (maxc > 14u) {  // (uniform over the warp)
+#pragma unroll
+            for (int r = 14; r < 30; ++r) {
+                const uint32_t sr = __reduce_add_sync(0xffffffffu, min(v, (uint32_t)r));
+                if (lane == 0) st[r + 2] = (uint16_t)sr;
+            }
         }
         __syncthreads();
         if (t == NC - 1) {
@@ -349,10 +360,10 @@ __device__ __forceinline__ uint32_t place_slot(uint32_t key, uint32_t rc, const 
     const uint32_t v0 = (key >> CELL_BITS) * NV;
     const uint32_t chunk = pos >> 5, lane = pos & 31u;
     const uint32_t gchunk = (v0 >> 5) + chunk;
-    const uint16_t* row = stab + (size_t)gchunk * 16;
-    if (r < 14u && row[0] == 0) {
+    const uint16_t* row = stab + (size_t)gchunk * STAB_ROW;
+    if (r < 30u && row[0] == 0) {
         // counts strictly ordered, descending: every lower lane still has a particle at rank r (r < own count <= theirs)
-        const uint32_t below = r ? row[r] : 0u;
+        const uint32_t below = r ? row[r < 14u ? r : r + 2u] : 0u;  // (rows 14..29: the chunk's second sector)
         const uint32_t ps = *reinterpret_cast<const uint32_t*>(row + 14);
         return ps + below + lane;
     }
@@ -901,7 +912,7 @@ int bin_create(MpmSolver* s)
     CKB(cudaMalloc(&st->ord, sizeof(uint16_t) * nvpos));
     CKB(cudaMalloc(&st->cellmeta, sizeof(uint2) * st->nslots));
     CKB(cudaMalloc(&st->pstart, sizeof(uint32_t) * (nvpos >> 5)));
-    CKB(cudaMalloc(&st->stab, sizeof(uint16_t) * 16 * (nvpos >> 5)));
+    CKB(cudaMalloc(&st->stab, sizeof(uint16_t) * STAB_ROW * (nvpos >> 5)));
     for (int k = 0; k < 2; ++k) {
         CKB(cudaMalloc(&st->bsum2[k], sizeof(uint32_t) * (st->nblocks + SCAN_PAD)));
         CKB(cudaMemsetAsync(st->bsum2[k], 0, sizeof(uint32_t) * (st->nblocks + SCAN_PAD), s->stream));

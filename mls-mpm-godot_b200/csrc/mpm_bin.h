@@ -23,7 +23,7 @@ struct BinState {
     uint16_t* ord = nullptr;         // [2 * nslots] position -> cell id inside the block
     uint2* cellmeta = nullptr;       // [nslots] cell -> {first full virtual cell | remainder's position << 16, number of full ones}
     uint32_t* pstart = nullptr;      // [2 * nslots / 32] first slot of every chunk
-    uint16_t* stab = nullptr;        // [2 * nslots / 32][16] per chunk: [0] irregular flag, [1..13] first slot of the rank-r row
+    uint16_t* stab = nullptr;        // [2 * nslots / 32][32] per chunk: [0] irregular flag, [1..13] and [16..31] first slot of the rank-r row (r = 1..13, 14..29)
                                      // relative to the chunk start, [14..15] the chunk start (one 32-B sector for k_place)
     // per-block totals, their exclusive scan and the list of non-empty blocks, double-buffered: [lay] describes the current
     // layout, [lay ^ 1] the previous one -- which is the order the records (and keys[]) are in when the next binning runs,
