@@ -43,8 +43,9 @@ struct BinState {
     uint32_t* tcount = nullptr;      // [nblocks][(B+2)^3]; row T is valid while bsum2[previous][T] > 0
     uint32_t* fixlist = nullptr;     // [FIX_CAP] cells that received "far movers" (particles that left their block's region) in this binning
     uint32_t* heavy = nullptr;       // [HEAVY_CAP] tiles with more than HEAVY_ROWS rows (ranked by a whole CTA each)
-    uint32_t* far_n = nullptr;       // [4]: [0] cells listed, [1] binnings with a cell left in atomic order, [2] far movers of this binning,
-                                     // [3] flag: this binning left a cell unordered (booked into [1] by the next scan)
+    uint32_t* far_n = nullptr;       // [8]: [0] cells listed, [1] binnings with a cell left in atomic order, [2] far movers of this binning,
+                                     // [3] flag: this binning left a cell unordered (booked into [1] by the next scan), [4] consecutive
+                                     // violent binnings, [5] heavy tiles listed, [6] the far-mover limit in force (MPM_FAR_LIMIT)
     CUtensorMap grid_map;            // TMA descriptor of the local grid (box = one block's tile), for G2P's tile prefetch
     bool grid_map_valid = false;     // (re-encoded when the grid is re-created: multi-GPU re-cuts)
     bool stable = true;              // rank inside a cell = order of the old slots (std::stable_sort); false: atomic cursor
