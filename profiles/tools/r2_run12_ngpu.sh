@@ -1,6 +1,6 @@
 cd $GRAFT_REPO_ROOT
 N=$1
-O=gpurun_out/r2m; mkdir -p $O
+O=gpurun_out/r2n8; mkdir -p $O
 MPM_BENCH_ALLRANKS=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 > $O/bench_c4_n$N.json 2> $O/bench_c4_n$N.err
 grep "^\[rank" $O/bench_c4_n$N.err | tr ']' '\n' | grep -c n_local
 grep -o "\[rank [0-9]\] n_local=[0-9]* cells=[0-9]* ms_step=[0-9.]* sort=[0-9.]* p2g1=[0-9.]* p2g2=[0-9.]* update=[0-9.]* g2p=[0-9.]* exchange=[0-9.]*" $O/bench_c4_n$N.err | head -8
