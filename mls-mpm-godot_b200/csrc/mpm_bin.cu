@@ -417,6 +417,9 @@ struct RankGeom { int nbx, nby, nbz; };
 
 // tiles with more rows than this are ranked by a whole CTA (k_rank_place_heavy), the others by one warp each; k_rank_count
 // lists them (far_n[5] = how many; beyond HEAVY_CAP the heavy kernel falls back to scanning every tile)
+#ifndef MPM_RANK_CTAS
+#define MPM_RANK_CTAS 8  // CTAs of k_rank_place per SM (64 registers; 10 and 12 were measured: see profiles/r2/README.md)
+#endif
 constexpr uint32_t HEAVY_ROWS = 256;
 constexpr int HEAVY_CAP = 4096;
 
@@ -711,7 +714,7 @@ __device__ __forceinline__ void rank_tile(const RankArgs& A, uint32_t tile, uint
 
 // light tiles: one warp per tile, four tiles per CTA
 template <int CELL_BITS>
-__global__ void __launch_bounds__(128, 8) k_rank_place(const __grid_constant__ RankArgs A)
+__global__ void __launch_bounds__(128, MPM_RANK_CTAS) k_rank_place(const __grid_constant__ RankArgs A)
 {
     pdl_wait();
     using C = RankCfg<CELL_BITS>;
@@ -1058,7 +1061,7 @@ int bin_particles(MpmSolver* s)
     s->launches += 3;
     if (n > 0 && stable) {
         const RankGeom rg{st->nbx, st->nby, st->nbz};
-        const unsigned grid_c = rank_grid(st, 12), grid_l = rank_grid(st, 8), grid_h = rank_grid(st, 4);  // (CTAs per SM)
+        const unsigned grid_c = rank_grid(st, 12), grid_l = rank_grid(st, MPM_RANK_CTAS), grid_h = rank_grid(st, 4);  // (CTAs per SM)
         const RankArgs ra{st->keys, st->bsum2[pl], st->bbase2[pl], st->active2[pl], st->nact + pl, rg, st->tcount, st->cnt[nxt], st->cellmeta,
                           st->cnts, st->pstart, st->stab, st->fill, st->farcnt, st->far_n, st->heavy, (uint32_t)n, st->src_of, s->orig_id, s->orig_id_alt};
         const unsigned grid_f = rank_grid(st, 4);
