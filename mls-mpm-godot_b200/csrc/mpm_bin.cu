@@ -895,6 +895,7 @@ int bin_create(MpmSolver* s)
     s->bin = st;
     const int64_t cells = (int64_t)s->dp.nxl * s->dp.Ry * s->dp.Rz;
     st->B = (cells >= (int64_t)96 * 96 * 96) ? 8 : 4;
+    if (const char* e = getenv("MPM_BLOCK_EDGE")) { if (atoi(e) == 4 || atoi(e) == 8) st->B = atoi(e); }  // (A/B: profiles/r2/README.md)
     st->logB = (st->B == 8) ? 3 : 2;
     st->cell_bits = 3 * st->logB;
     st->nbx = (s->dp.nxl + st->B - 1) / st->B;
