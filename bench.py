@@ -282,6 +282,9 @@ def main():
     ap.add_argument("--presteps", type=int, default=0, help="advance the scene this many untimed steps first (evolved-scene numbers)")
     ap.add_argument("--evolved-at", type=int, default=100, help="also time K steps from this step on (0 = off); reported under `evolved`")
     ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the config 2 / config 3 / weak-scaling measurements")
+    ap.add_argument("--rebalance", type=int, default=-1,
+                    help="multi-GPU: before the warm-up, this many rounds of (2 steps, 4 timed steps, mpm_comm_rebalance_weighted with the rank's "
+                         "measured compute ms per million particles); default 0 (measured on config 5: profiles/r2/README.md)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
@@ -311,6 +314,8 @@ def main():
     blocks = [(lo, hi, sp)] + EXTRA_BLOCKS.get(args.workload, [])
     n_total = sum(lattice_count(*b) for b in blocks)
     G = grid[0] * grid[1] * grid[2]
+    n_rebalance = max(args.rebalance, 0)
+
     def build_scene():
         sv = mpm_b200.Solver(params, n_total, device=local_rank)
         if world > 1:
@@ -322,6 +327,14 @@ def main():
         for k, (blo, bhi, bsp) in enumerate(blocks):
             sv.initialise_sim(blo, bhi, bsp, append=k > 0)
         assert sv.num_particles == n_total, (sv.num_particles, n_total)
+        for _ in range(n_rebalance if world > 1 else 0):  # cuts by measured time: what a host does between frames
+            sv.step(2)          # (the first binning after an upload or a re-cut is a cold start: not what a step costs)
+            sv.set_timing(1)
+            sv.step(4); sv.sync()
+            t = sv.stats()
+            sv.set_timing(0)
+            compute_ms = t.ms_sort + t.ms_clear + t.ms_p2g1 + t.ms_p2g2 + t.ms_update + t.ms_g2p
+            sv.comm_rebalance(3, cost_per_particle=compute_ms / max(t.local_particles, 1) * 1e6)
         return sv
 
     # ---- pass A, the breakdown: the same scene, the same steps as the timed region below, with CUDA events around every
@@ -515,6 +528,8 @@ def main():
                        "grid_mode": "fixed 1e7", "math": args.math, "kernel_path": {1: "reference-shaped", 2: "tiled", 3: "cell"}[st.kernel_path],
                        "sort_interval": sort_interval, "parallelism": f"x-slab x{world}",
                        "presteps": args.presteps,
+                       "rebalance": (f"{n_rebalance} rounds of 2 + 4 timed steps + mpm_comm_rebalance_weighted(3 planes, measured compute ms per "
+                                     f"million particles) before the warm-up" if (world > 1 and n_rebalance) else "none (equal-count cuts from the upload)"),
                        "l2": f"inputs ({64e-9 * n_total / world:.1f} GB of particle planes per GPU) exceed the 126 MB L2; no flush needed",
                        "timing": "value / ms_per_step: two CUDA events on the solver stream around the K timed steps (mpm_set_timing 2), max over "
                                  "ranks; phase_ms / kernels / roofline: a second copy of the scene over the same steps with events around every "

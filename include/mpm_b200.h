@@ -317,6 +317,12 @@ MPM_API int32_t mpm_comm_init_local(MpmSolver* s, MpmLocalHub* hub, int32_t rank
  * (1..3), migrates the particles that changed owner and re-creates the rank's local grid.  Results are unaffected
  * (ownership is not physics): bit-identical in MPM_GRID_FIXED. */
 MPM_API int32_t mpm_comm_rebalance(MpmSolver* s, int32_t max_shift);
+/* The same with the ranks' particles weighted: cost_per_particle is THIS rank's measured cost of a particle in a unit all
+ * ranks share and that keeps the numbers around 1 (e.g. its compute milliseconds per step and million local particles,
+ * from mpm_set_timing(1) + mpm_get_stats; quantised to 1/4096; <= 0 or NaN counts as 1).  The cuts then equalise the
+ * summed cost instead of the counts -- for scenes whose ranks need different times for the same number of particles
+ * (BASELINE config 5: bodies of different density).  Equal costs on all ranks == mpm_comm_rebalance. */
+MPM_API int32_t mpm_comm_rebalance_weighted(MpmSolver* s, int32_t max_shift, float cost_per_particle);
 /* Slab of this rank: owned planes [x0, x1), stored planes [gx0, gx0 + nxl) (what mpm_download_grid returns). */
 MPM_API int32_t mpm_comm_slab(const MpmSolver* s, int32_t* x0, int32_t* x1, int32_t* gx0, int32_t* nxl);
 /* Global (original) index of each local particle, in the slot order of mpm_download_particles_soa. */

@@ -1240,10 +1240,19 @@ __global__ void __launch_bounds__(256) k_hist_round(const unsigned long long* __
     toL[x] = accR[x] + own[x];  // everything at or right of this rank
 }
 
+__global__ void __launch_bounds__(256) k_hist_scale(unsigned long long* __restrict__ own, int rx, unsigned long long w)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x < rx) own[x] *= w;
+}
+
 // Global x-plane histogram (world - 1 rounds of neighbour exchange: each round passes "all ranks on my left, plus me" to
-// the right and the mirror image to the left), new equal-count cuts moved at most max_shift planes from the current
-// ones, one migration round, local grid and binning re-created.  Collective over all ranks; call between steps.
-static int rebalance(MpmSolver* s, int max_shift)
+// the right and the mirror image to the left), new cuts moved at most max_shift planes from the current ones, one
+// migration round, local grid and binning re-created.  Collective over all ranks; call between steps.
+// wq = 1 on every rank: equal particle counts.  Otherwise every rank's planes count wq times (its cost per particle in
+// 1/4096 of the caller's unit): the cuts equalise the summed COST -- what a host does that has measured that its ranks
+// need different times for the same number of particles (denser cells, more pile-ups, a wider empty grid to scan).
+static int rebalance(MpmSolver* s, int max_shift, unsigned long long wq)
 {
     CommState* c = s->comm;
     { int rc = comm_finish_migration(s); if (rc) return rc; }
@@ -1260,6 +1269,7 @@ static int rebalance(MpmSolver* s, int max_shift)
         else k_xhist<ParticleView><<<blocks, 256, sizeof(uint32_t) * rx, s->stream>>>(s->view(), s->n, rx, own);
         s->launches += 1;
     }
+    if (wq != 1ull) { k_hist_scale<<<(rx + 255) / 256, 256, 0, s->stream>>>(own, rx, wq); s->launches += 1; }
     const size_t hb = sizeof(unsigned long long) * rx;
     int rc = MPM_OK;
     for (int round = 1; round < world && rc == MPM_OK; ++round) {
@@ -1391,7 +1401,21 @@ extern "C" int32_t mpm_comm_rebalance(MpmSolver* s, int32_t max_shift)
     if (cudaSetDevice(s->device) != cudaSuccess) { s->err = "cudaSetDevice failed"; return MPM_ERR_CUDA; }
     int rc = comm_partition(s);
     if (rc) return rc;
-    return rebalance(s, max_shift);
+    return rebalance(s, max_shift, 1ull);
+}
+
+extern "C" int32_t mpm_comm_rebalance_weighted(MpmSolver* s, int32_t max_shift, float cost_per_particle)
+{
+    if (!s) return MPM_ERR_INVALID;
+    if (!s->comm || s->comm->world < 2) return MPM_OK;
+    if (cudaSetDevice(s->device) != cudaSuccess) { s->err = "cudaSetDevice failed"; return MPM_ERR_CUDA; }
+    int rc = comm_partition(s);
+    if (rc) return rc;
+    // quantised to 1/4096 of the caller's unit, at least one step, at most 2^24 steps (a plane of 10^6 particles stays far
+    // below 2^63); not-a-number or non-positive costs count as 1.0
+    const float c = (cost_per_particle > 0.0f && cost_per_particle < 4096.0f) ? cost_per_particle : 1.0f;
+    const unsigned long long wq = std::max<unsigned long long>(1ull, (unsigned long long)llroundf(c * 4096.0f));
+    return rebalance(s, max_shift, wq);
 }
 
 extern "C" int32_t mpm_comm_slab(const MpmSolver* s, int32_t* x0, int32_t* x1, int32_t* gx0, int32_t* nxl)

@@ -106,6 +106,7 @@ namespace MpmB200
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_local_hub_destroy(IntPtr hub);
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_comm_init_local(IntPtr s, IntPtr hub, int rank, int world);
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_comm_rebalance(IntPtr s, int max_shift);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_comm_rebalance_weighted(IntPtr s, int max_shift, float cost_per_particle);
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_comm_slab(IntPtr s, out int x0, out int x1, out int gx0, out int nxl);
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_download_ids(IntPtr s, uint* ids, long cap);
         [DllImport(Lib, CallingConvention = CC)] public static extern int mpm_slab_cuts(long* hist, int rx, int world, int min_width, int* cuts);

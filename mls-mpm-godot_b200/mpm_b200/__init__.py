@@ -76,7 +76,7 @@ EXPORTS = [
     "mpm_get_positions", "mpm_num_particles", "mpm_set_timing", "mpm_get_stats", "mpm_debug_last_sort",
     "mpm_get_stream", "mpm_host_alloc", "mpm_host_free", "mpm_comm_unique_id", "mpm_comm_init",
     "mpm_local_hub_create", "mpm_local_hub_destroy", "mpm_comm_init_local", "mpm_comm_slab", "mpm_download_ids",
-    "mpm_slab_cuts", "mpm_get_positions_async", "mpm_get_positions_q16_async", "mpm_wait_positions", "mpm_comm_rebalance", "mpm_set_colliders",
+    "mpm_slab_cuts", "mpm_get_positions_async", "mpm_get_positions_q16_async", "mpm_wait_positions", "mpm_comm_rebalance", "mpm_comm_rebalance_weighted", "mpm_set_colliders",
     "mpm_save_state", "mpm_load_state", "mpm_export_positions",
 ]
 
@@ -133,6 +133,7 @@ def load():
         "mpm_get_positions_q16_async": (i32, [vp, vp, i64]),
         "mpm_wait_positions": (i32, [vp]),
         "mpm_comm_rebalance": (i32, [vp, i32]),
+        "mpm_comm_rebalance_weighted": (i32, [vp, i32, C.c_float]),
         "mpm_set_colliders": (i32, [vp, fp, i32]),
         "mpm_save_state": (i32, [vp, C.c_char_p]),
         "mpm_load_state": (i32, [vp, C.c_char_p]),
@@ -358,9 +359,13 @@ class Solver:
         self._hub = hub  # keep it alive as long as the solver
         self._ck(self._L.mpm_comm_init_local(self._h, hub._h, rank, world))
 
-    def comm_rebalance(self, max_shift=2):
-        """Re-cut the slabs towards equal particle counts (collective; between steps)."""
-        self._ck(self._L.mpm_comm_rebalance(self._h, int(max_shift)))
+    def comm_rebalance(self, max_shift=2, cost_per_particle=None):
+        """Re-cut the slabs towards equal particle counts -- or, with this rank's measured cost per particle (a unit all
+        ranks share, numbers around 1), towards equal summed cost (collective; between steps)."""
+        if cost_per_particle is None:
+            self._ck(self._L.mpm_comm_rebalance(self._h, int(max_shift)))
+        else:
+            self._ck(self._L.mpm_comm_rebalance_weighted(self._h, int(max_shift), C.c_float(cost_per_particle)))
 
     def slab(self):
         """(x0, x1, gx0, nxl): owned planes [x0, x1), stored planes [gx0, gx0 + nxl)."""

@@ -256,6 +256,58 @@ def test_rebalance_moves_the_cuts_and_keeps_the_bits(lib):
 
 
 @pytest.mark.gpu
+def test_weighted_rebalance_cuts_by_cost(lib):
+    """mpm_comm_rebalance_weighted: a rank that reports three times the cost per particle ends up with about a third of
+    the particles of the others (the cuts equalise count x cost), nothing is lost, and the physics is untouched
+    (bit-identical to the oracle on the strict path).  Equal costs behave like mpm_comm_rebalance."""
+    import mpm_b200
+    op = orc.variant("3d_gpu", (96, 32, 32))
+    op.interaction = 0
+    n = 60000
+    pos, vel, Cm, mass = helpers.random_cloud(op, n, seed=23, vel_sigma=0.1)   # uniform in x over [3.5, 92.5)
+    steps, world = 12, 3
+    ref = orc.State(op, pos, vel, Cm, mass)
+    ref.step(steps)
+    res = {}
+    for tag, costs in (("weighted", (3.0, 1.0, 1.0)), ("equal", (0.7, 0.7, 0.7))):
+        hub = mpm_b200.LocalHub(world)
+        out, errs = [None] * world, []
+
+        def work(r):
+            try:
+                with mpm_b200.Solver(helpers.mpm_params_from_orc(op, kernel_path=2), n) as s:
+                    s.comm_init_local(hub, r, world)
+                    s.upload(pos, vel, Cm, mass)
+                    for k in range(steps // 2):
+                        s.step(2)
+                        s.comm_rebalance(3, cost_per_particle=costs[r])
+                    gp, gv, gc, gm = s.download()
+                    out[r] = dict(pos=gp, vel=gv, C=gc, ids=s.download_ids(), slab=s.slab(), stats=s.stats())
+            except Exception as e:  # noqa: BLE001
+                errs.append((r, e))
+
+        th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+        [t.start() for t in th]
+        [t.join(300) for t in th]
+        hub.close()
+        assert not errs, errs
+        ids = np.concatenate([o["ids"] for o in out])
+        assert np.array_equal(np.sort(ids), np.arange(n, dtype=np.uint32)), "particles lost or duplicated"
+        for what in ("pos", "vel", "C"):
+            full = np.zeros_like(getattr(ref, what))
+            for o in out:
+                full[o["ids"]] = o[what]
+            helpers.assert_bit_equal(full, getattr(ref, what), f"{what} with cost-weighted cuts ({tag})")
+        res[tag] = [o["stats"].local_particles for o in out]
+    cw, ce = res["weighted"], res["equal"]
+    # equal costs: equal counts (to the width of a plane: 60000 / 89 planes = 674 particles)
+    assert max(ce) - min(ce) < 2 * 700, ce
+    # cost 3 : 1 : 1 -> counts 1/7 : 3/7 : 3/7 of n, reached within the 6 re-cuts of <= 3 planes each (the first cut has to
+    # move from plane 32 to plane ~16)
+    assert abs(cw[0] - n / 7) < 0.05 * n and abs(cw[1] - 3 * n / 7) < 0.05 * n and abs(cw[2] - 3 * n / 7) < 0.05 * n, cw
+
+
+@pytest.mark.gpu
 def test_k_slabs_cell_path_within_fast_tolerance(lib):
     """The cell path (FAST math) on 3 slabs: float accumulation order differs from the 1-slab run, so the bar is the
     FAST tolerance against the strict oracle, plus exact particle bookkeeping."""
