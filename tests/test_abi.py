@@ -106,3 +106,34 @@ def test_committed_traffic_table_has_the_kernels_the_bench_reports():
         if have.returncode == 0:
             changed = subprocess.run(["git", "-C", ROOT, "diff", "--quiet", t["commit"], "--", "mls-mpm-godot_b200/csrc/mpm_kernels_cell.cu"])
             assert changed.returncode == 0, "the cell kernels changed after the committed ncu capture: re-capture profiles/r2/traffic_c4.json"
+
+
+def test_every_kernel_launched_with_the_pdl_attribute_waits_first():
+    """A kernel launched through launch_pdl() (programmatic stream serialization) may be scheduled while the kernel before it
+    is still running: it must execute griddepcontrol.wait -- pdl_prologue() or pdl_wait() -- before anything else.  Static check
+    over the sources: every kernel name that appears in a launch_pdl(...) call has one of the two as the first statement
+    of its body."""
+    import glob
+    import re
+    src = {f: open(f).read() for f in glob.glob(os.path.join(ROOT, "mls-mpm-godot_b200", "csrc", "*.cu*"))}
+    text = "\n".join(src.values())
+    launched = set(re.findall(r"launch_pdl(?:<[^>]*>)?\(\s*([A-Za-z_0-9]+)", text))
+    launched |= set(re.findall(r"LAUNCH_CELL\(\s*([A-Za-z_0-9]+)", text))  # (the macro launches its first argument)
+    launched -= {"KERNEL", "void"}      # the macro's own parameter; launch_pdl's definition
+    aliases = dict(re.findall(r"constexpr auto ([A-Za-z_0-9]+) = ([A-Za-z_0-9]+)<", text))  # k_g2p_cell_comm = k_g2p_cell<...>
+    kernels = {aliases.get(k, k) for k in launched}
+    assert len(kernels) >= 15, kernels
+    for k in sorted(kernels):
+        m = None
+        for m in re.finditer(r"__global__[^;{]*?\b" + k + r"\s*\(", text):
+            i, depth = m.end(), 1
+            while depth:
+                depth += {"(": 1, ")": -1}.get(text[i], 0)
+                i += 1
+            j = text.index("{", i)
+            if text[i:j].strip():
+                continue  # a declaration
+            body = text[j + 1:j + 200].lstrip()
+            assert body.startswith("pdl_prologue();") or body.startswith("pdl_wait();"), f"{k} does not wait first"
+            break
+        assert m is not None, f"kernel {k} not found"
