@@ -35,6 +35,20 @@ def test_slab_cuts_balance_and_constraints(lib):
         mpm_b200.slab_cuts(np.ones(8, np.int64), 4)
 
 
+def test_slab_cuts_of_a_cost_weighted_histogram(lib):
+    """What mpm_comm_rebalance_weighted hands to the cut routine: every rank's planes scaled by its cost per particle
+    (quantised to 1/4096).  Two slabs of equal particle density, the right half three times as expensive per particle:
+    the cut that equalises the summed cost sits where the cheap side holds 3/4 of the cost-free count."""
+    import mpm_b200
+    hist = np.zeros(128, np.int64)
+    hist[4:124] = 100_000
+    wq = np.where(np.arange(128) < 64, 4096, 3 * 4096).astype(np.int64)   # planes owned by rank 0 / rank 1 before the re-cut
+    cuts = mpm_b200.slab_cuts(hist * wq, 2)
+    # total cost = 60 planes x 1 + 60 planes x 3 = 240 plane-units; half = 120 = 60 cheap planes + 20 expensive ones
+    assert abs(cuts[1] - 84) <= 1, cuts
+    assert mpm_b200.slab_cuts(hist * 4096, 2)[1] == mpm_b200.slab_cuts(hist, 2)[1] == 64   # equal costs == equal counts
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
